@@ -1,0 +1,691 @@
+// jp_oracle.cpp -- CPU ORACLE (TEST INFRASTRUCTURE ONLY, never on the product path).
+//
+// Plain C++ restatement of the posterior-integration hot path of chriselrod/JointPosteriors.jl.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+// load this library; the product (libjpcuda.so) never links or calls it.
+//
+// PARITY PINNING.  The reference is Julia 0.6 and cannot run here (no julia, and its three
+// sibling packages SparseQuadratureGrids / ConstrainedParameters / LogDensities are not
+// vendored: reference REQUIRE:1-8, README.md:13-16).  What IS in the reference is restated
+// line by line and cited below (Cholesky / triangular inverse / eigen fallback / centring /
+// moments / 100-knot Grid CDF / quantile bisection).  What is NOT in the reference (Smolyak
+// construction, the affine map's importance correction, the constraint transforms) follows the
+// published maths and is pinned by
+//   (1) the reference's only numeric test, test/runtests.jl:69-70 (tau: mu 0.5504, sigma 0.077,
+//       quantiles [0.391 0.495 0.55 0.602 0.696] at rtol 10^-1.5) and the README prints
+//       (README.md:110-128), and
+//   (2) brute-force tensor Gauss-Legendre truth for the README model (tests/test_oracle_pin.py).
+// Beyond that tolerance the Smolyak stages are "parity unpinned" (no upstream source exists to
+// compare against); DESIGN.md says the same.
+//
+// Build: see oracle/Makefile (g++ -O2 -ffp-contract=off -pthread -shared).
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <vector>
+#include <atomic>
+#include <thread>
+
+#include "jp_rule_tables.h"
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------
+// Scale matrix: Cholesky, triangular inverse, eigen fallback.  Column-major d x d (Julia).
+// ------------------------------------------------------------------------------------------
+#define A_(M, i, j, ld) (M)[(size_t)(i) + (size_t)(j) * (ld)]
+
+// reference src/joint_posterior.jl:15-29 (try_chol!) -- upper factor U'U = Sigma, column by
+// column; returns 0 when a pivot is not positive (the `false` at :26), leaving U partial.
+int orc_try_chol(double* U, const double* S, int d) {
+  for (int i = 0; i < d; ++i) {
+    A_(U, i, i, d) = A_(S, i, i, d);
+    for (int j = 0; j < i; ++j) {
+      A_(U, j, i, d) = A_(S, j, i, d);
+      for (int k = 0; k < j; ++k) A_(U, j, i, d) -= A_(U, k, i, d) * A_(U, k, j, d);
+      A_(U, j, i, d) /= A_(U, j, j, d);
+      A_(U, i, i, d) -= A_(U, j, i, d) * A_(U, j, i, d);
+    }
+    if (A_(U, i, i, d) > 0)
+      A_(U, i, i, d) = std::sqrt(A_(U, i, i, d));
+    else
+      return 0;
+  }
+  return 1;
+}
+
+// reference src/joint_posterior.jl:30-43 (chol!) -- same recurrence, no pivot check.
+void orc_chol(double* U, const double* S, int d) {
+  for (int i = 0; i < d; ++i) {
+    A_(U, i, i, d) = A_(S, i, i, d);
+    for (int j = 0; j < i; ++j) {
+      A_(U, j, i, d) = A_(S, j, i, d);
+      for (int k = 0; k < j; ++k) A_(U, j, i, d) -= A_(U, k, i, d) * A_(U, k, j, d);
+      A_(U, j, i, d) /= A_(U, j, j, d);
+      A_(U, i, i, d) -= A_(U, j, i, d) * A_(U, j, i, d);
+    }
+    A_(U, i, i, d) = std::sqrt(A_(U, i, i, d));
+  }
+}
+
+// reference src/joint_posterior.jl:56-68 (inv!, in place) -- inverse of an upper-triangular
+// matrix by row-wise back substitution.  The strictly lower triangle is left untouched.
+void orc_inv_upper(double* U, int d) {
+  for (int i = 0; i < d; ++i) {
+    A_(U, i, i, d) = 1.0 / A_(U, i, i, d);
+    for (int j = i + 1; j < d; ++j) {
+      A_(U, i, j, d) = A_(U, i, j, d) * A_(U, i, i, d);
+      for (int k = i + 1; k < j; ++k) A_(U, i, j, d) += A_(U, k, j, d) * A_(U, i, k, d);
+      A_(U, i, j, d) /= -A_(U, j, j, d);
+    }
+  }
+}
+
+// reference src/joint_posterior.jl:72-76 (inv_chol!) -- U = chol(H)^-1, so U U' = H^-1.
+// The lower triangle is zeroed here (the reference leaves whatever M.Grid.U held; eval_grid!
+// only ever multiplies by the upper triangle).
+void orc_inv_chol(double* U, const double* H, int d) {
+  for (int i = 0; i < d * d; ++i) U[i] = 0.0;
+  orc_chol(U, H, d);
+  orc_inv_upper(U, d);
+}
+
+// Cyclic Jacobi eigen-decomposition of a symmetric matrix (stands in for LAPACK behind
+// `eigfact!(Symmetric(H))`, reference src/joint_posterior.jl:99); eigenvalues ascending,
+// eigenvectors as columns of V (column-major), each normalised with its largest-|.| entry > 0.
+static void jacobi_eig(const double* H, int d, std::vector<double>& val, std::vector<double>& V) {
+  std::vector<double> A(H, H + (size_t)d * d);
+  V.assign((size_t)d * d, 0.0);
+  for (int i = 0; i < d; ++i) A_(V, i, i, d) = 1.0;
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    double off = 0;
+    for (int p = 0; p < d; ++p)
+      for (int q = p + 1; q < d; ++q) off += A_(A, p, q, d) * A_(A, p, q, d);
+    if (off < 1e-300) break;
+    for (int p = 0; p < d; ++p)
+      for (int q = p + 1; q < d; ++q) {
+        double apq = A_(A, p, q, d);
+        if (apq == 0.0) continue;
+        double theta = (A_(A, q, q, d) - A_(A, p, p, d)) / (2 * apq);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
+        double c = 1 / std::sqrt(t * t + 1), s = t * c;
+        for (int k = 0; k < d; ++k) {
+          double akp = A_(A, k, p, d), akq = A_(A, k, q, d);
+          A_(A, k, p, d) = c * akp - s * akq;
+          A_(A, k, q, d) = s * akp + c * akq;
+        }
+        for (int k = 0; k < d; ++k) {
+          double apk = A_(A, p, k, d), aqk = A_(A, q, k, d);
+          A_(A, p, k, d) = c * apk - s * aqk;
+          A_(A, q, k, d) = s * apk + c * aqk;
+        }
+        for (int k = 0; k < d; ++k) {
+          double vkp = A_(V, k, p, d), vkq = A_(V, k, q, d);
+          A_(V, k, p, d) = c * vkp - s * vkq;
+          A_(V, k, q, d) = s * vkp + c * vkq;
+        }
+      }
+  }
+  std::vector<int> ord(d);
+  std::iota(ord.begin(), ord.end(), 0);
+  std::sort(ord.begin(), ord.end(), [&](int a, int b) { return A_(A, a, a, d) < A_(A, b, b, d); });
+  std::vector<double> Vs((size_t)d * d);
+  val.resize(d);
+  for (int c = 0; c < d; ++c) {
+    val[c] = A_(A, ord[c], ord[c], d);
+    int big = 0;
+    for (int k = 1; k < d; ++k)
+      if (std::fabs(A_(V, k, ord[c], d)) > std::fabs(A_(V, big, ord[c], d))) big = k;
+    double sg = A_(V, big, ord[c], d) < 0 ? -1.0 : 1.0;
+    for (int k = 0; k < d; ++k) A_(Vs, k, c, d) = sg * A_(V, k, ord[c], d);
+  }
+  V.swap(Vs);
+}
+
+// reference src/joint_posterior.jl:98-110 (reduce_dimensions!, Dynamic) and :120-134
+// (FixedRank{p}: max_rank > 0) -- keep eigenpairs with lambda >= 1e-11 in ascending order,
+// column g = v_i / sqrt(lambda_i).  out is d x p column-major; returns p.
+int orc_reduce_dimensions(const double* H, int d, int max_rank, double* out) {
+  std::vector<double> val, V;
+  jacobi_eig(H, d, val, V);
+  int g0 = 0;
+  for (int i = 0; i < d; ++i) {
+    if (val[i] < 1e-11) continue;          // :103 / :125
+    if (max_rank > 0 && g0 >= max_rank) break;  // :127-128
+    for (int k = 0; k < d; ++k) A_(out, k, g0, d) = A_(V, k, i, d) / std::sqrt(val[i]);  // :107
+    ++g0;
+  }
+  return g0;
+}
+
+// reference src/joint_posterior.jl:136-138 (deduce_scale!, Dynamic): Cholesky when H is
+// positive definite, else the eigen fallback.  (`safe_inv_chol!` at :69-71 calls an undefined
+// `try_inv!`; the evident intent -- try_chol! then inv! -- is what is restated.)
+// Returns the rank p; U is d x p column-major.
+int orc_deduce_scale_dynamic(const double* H, int d, double* U) {
+  for (int i = 0; i < d * d; ++i) U[i] = 0.0;
+  if (orc_try_chol(U, H, d)) {
+    orc_inv_upper(U, d);
+    return d;
+  }
+  for (int i = 0; i < d * d; ++i) U[i] = 0.0;
+  return orc_reduce_dimensions(H, d, 0, U);
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage 1: Smolyak sparse grid (published maths; the reference delegates to
+// SparseQuadratureGrids, call sites src/joint_posterior.jl:180,186).
+// ------------------------------------------------------------------------------------------
+struct Rule {
+  int levels, nmax;
+  const int* npts;
+  const double* nodes;    // z-space master nodes
+  const double* weights;  // [levels][nmax]
+};
+static Rule get_rule(int rule_id) {
+  if (rule_id == 1) return Rule{JP_KP_LEVELS, JP_KP_NMAX, jp_kp_npts, jp_kp_znodes, &jp_kp_weights[0][0]};
+  return Rule{JP_GK_LEVELS, JP_GK_NMAX, jp_gk_npts, jp_gk_nodes, &jp_gk_weights[0][0]};
+}
+
+int orc_rule_info(int rule_id, int* levels, int* nmax, int* npts, double* nodes, double* weights) {
+  Rule r = get_rule(rule_id);
+  *levels = r.levels;
+  *nmax = r.nmax;
+  if (npts) std::memcpy(npts, r.npts, sizeof(int) * r.levels);
+  if (nodes) std::memcpy(nodes, r.nodes, sizeof(double) * r.nmax);
+  if (weights) std::memcpy(weights, r.weights, sizeof(double) * r.levels * r.nmax);
+  return 0;
+}
+
+static double binom(int n, int k) {
+  if (k < 0 || k > n) return 0.0;
+  double r = 1;
+  for (int i = 1; i <= k; ++i) r = r * (double)(n - k + i) / (double)i;  // exact for the sizes used
+  return std::round(r);
+}
+
+// Combination-technique coefficient of multi-index i (1-based levels) for the index set
+//   I = { i : |i|_1 <= q, 1 <= i_k <= cap },  q = L + d - 1,
+// c_i = sum_{e in {0,1}^d, i+e in I} (-1)^{|e|}.  With n = #{k : i_k < cap} free directions and
+// J = min(n, q - |i|):  c_i = (-1)^J C(n-1, J)  (n >= 1),  c_i = 1 (n = 0).  For cap >= L this is
+// the classical (-1)^{q-|i|} C(d-1, q-|i|).
+static double comb_coeff(const int* mi, int d, int q, int cap) {
+  int s = 0, n = 0;
+  for (int k = 0; k < d; ++k) {
+    s += mi[k];
+    if (mi[k] < cap) ++n;
+  }
+  if (n == 0) return 1.0;
+  int J = std::min(n, q - s);
+  if (J >= n) return 0.0;
+  double c = binom(n - 1, J);
+  return (J & 1) ? -c : c;
+}
+
+struct MultiIndexSet {
+  std::vector<int> mi;      // flattened, d per entry
+  std::vector<double> coef;
+};
+
+// Canonical multi-index order shared with the CUDA builder: ascending |i|_1, lexicographic
+// inside a class; only multi-indices with non-zero coefficient are kept.
+static void rec_compositions(int k, int d, int rem, int cap, int q, std::vector<int>& cur, MultiIndexSet& out) {
+  if (k == d - 1) {
+    if (rem < 1 || rem > cap) return;
+    cur[k] = rem;
+    double c = comb_coeff(cur.data(), d, q, cap);
+    if (c != 0.0) {
+      out.mi.insert(out.mi.end(), cur.begin(), cur.end());
+      out.coef.push_back(c);
+    }
+    return;
+  }
+  int left = d - 1 - k;
+  int lo = std::max(1, rem - left * cap), hi = std::min(cap, rem - left);
+  for (int v = lo; v <= hi; ++v) {
+    cur[k] = v;
+    rec_compositions(k + 1, d, rem - v, cap, q, cur, out);
+  }
+}
+static void enumerate_multi_indices(int d, int L, int cap, MultiIndexSet& out) {
+  int q = L + d - 1;
+  int smin = std::max(d, q - d + 1);
+  std::vector<int> cur(d);
+  for (int s = smin; s <= q; ++s) rec_compositions(0, d, s, cap, q, cur, out);
+}
+
+// Number of pre-merge tensor-product points and multi-indices (for sizing / reporting).
+int orc_smolyak_sizes(int rule_id, int d, int L, long long* n_multi, long long* n_premerge) {
+  Rule r = get_rule(rule_id);
+  int cap = std::min(L, r.levels);
+  MultiIndexSet S;
+  enumerate_multi_indices(d, L, cap, S);
+  long long tot = 0;
+  for (size_t a = 0; a < S.coef.size(); ++a) {
+    long long p = 1;
+    for (int k = 0; k < d; ++k) p *= r.npts[S.mi[a * d + k] - 1];
+    tot += p;
+  }
+  *n_multi = (long long)S.coef.size();
+  *n_premerge = tot;
+  return 0;
+}
+
+// Build the merged grid.  Nodes are identified by their integer key (one master-node index per
+// dimension); merged nodes come out in ascending lexicographic key order (dimension 0 most
+// significant); weights of duplicates are summed in generation order (multi-index order, then
+// mixed-radix point order with the LAST dimension fastest) -- the CUDA builder reproduces the
+// same order, which is what makes the weight table bit-exact.
+// Pass idx == NULL to query M only.  idx is M x d row-major (uint8), w is M.
+long long orc_smolyak_build(int rule_id, int d, int L, uint8_t* idx, double* w, long long cap_M) {
+  Rule r = get_rule(rule_id);
+  int cap = std::min(L, r.levels);
+  MultiIndexSet S;
+  enumerate_multi_indices(d, L, cap, S);
+  std::map<std::vector<uint8_t>, double> acc;
+  std::vector<uint8_t> key(d);
+  std::vector<int> np(d), j(d);
+  for (size_t a = 0; a < S.coef.size(); ++a) {
+    const int* mi = &S.mi[a * d];
+    for (int k = 0; k < d; ++k) np[k] = r.npts[mi[k] - 1], j[k] = 0;
+    while (true) {
+      double wt = S.coef[a];
+      for (int k = 0; k < d; ++k) {
+        wt = wt * r.weights[(size_t)(mi[k] - 1) * r.nmax + j[k]];
+        key[k] = (uint8_t)j[k];
+      }
+      auto it = acc.find(key);
+      if (it == acc.end())
+        acc.emplace(key, wt);
+      else
+        it->second = it->second + wt;
+      int k = d - 1;
+      for (; k >= 0; --k) {
+        if (++j[k] < np[k]) break;
+        j[k] = 0;
+      }
+      if (k < 0) break;
+    }
+  }
+  long long M = (long long)acc.size();
+  if (!idx) return M;
+  if (M > cap_M) return -M;
+  long long m = 0;
+  for (auto& kv : acc) {
+    std::memcpy(idx + m * d, kv.first.data(), d);
+    w[m] = kv.second;
+    ++m;
+  }
+  return M;
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage 2: constraint transforms (ConstrainedParameters restated from its call sites,
+// reference src/joint_posterior.jl:148,152; README.md:32,247-248).
+// code 0 RealVector: theta = x.            code 1 PositiveVector: theta = exp(x), log|J| = x.
+// code 2 ProbabilityVector: theta = 1/(1+exp(-x)), log|J| = -log(2 + e^x + e^-x)
+//        (sign convention of nlogit_lj, reference src/interp.jl:321-324).
+// ------------------------------------------------------------------------------------------
+static inline double transform_one(int code, double x, double* lj) {
+  if (code == 1) {
+    *lj += x;
+    return std::exp(x);
+  }
+  if (code == 2) {
+    double ex = std::exp(x);
+    *lj -= std::log(2 + ex + 1 / ex);
+    return 1.0 / (1.0 + std::exp(-x));
+  }
+  return x;
+}
+
+void orc_transform(const int* code, int d, const double* x, double* theta, double* logjac) {
+  double lj = 0;
+  for (int k = 0; k < d; ++k) theta[k] = transform_one(code[k], x[k], &lj);
+  *logjac = lj;
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage 3: likelihood families (user `log_density(Theta, data)` in the reference).
+// obs is N x C row-major; hyper holds the family's prior constants.
+// ------------------------------------------------------------------------------------------
+static const double LOG_2PI = 1.8378770664093454835606594728112;
+
+static inline double softplus(double x) { return (x > 0 ? x : 0.0) + std::log1p(std::exp(-std::fabs(x))); }
+static inline double lpdf_normal(double x, double mu, double sd) {
+  double z = (x - mu) / sd;
+  return -0.5 * z * z - std::log(sd) - 0.5 * LOG_2PI;
+}
+
+// family 0: README binomial mixture, reference README.md:62-72 / test/runtests.jl:19-26.
+// theta = (tau, theta_minus, theta_plus); obs columns (X, freq, NmX);
+// hyper = (a_m-1, b_m-1, a_p-1, b_p-1, a_tau-1, b_tau-1).
+static double ld_binmix(const double* p, const double* obs, long long N, const double* h) {
+  double lp = h[0] * std::log(p[1]) + h[1] * std::log(1 - p[1]) + h[2] * std::log(p[2]) +
+              h[3] * std::log(1 - p[2]) + h[4] * std::log(p[0]) + h[5] * std::log(1 - p[0]);
+  for (long long i = 0; i < N; ++i) {
+    const double* r = obs + i * 3;
+    lp += r[1] * std::log(p[0] * std::pow(1 - p[1], r[0]) * std::pow(p[1], r[2]) +
+                          (1 - p[0]) * std::pow(p[2], r[0]) * std::pow(1 - p[2], r[2]));
+  }
+  return lp;
+}
+// family 1: logistic regression, beta ~ N(0, hyper[0]^2); obs columns (x_0..x_{d-1}, y).
+static double ld_logistic(const double* b, int d, const double* obs, long long N, const double* h) {
+  double lp = 0;
+  for (int k = 0; k < d; ++k) lp += lpdf_normal(b[k], 0.0, h[0]);
+  for (long long i = 0; i < N; ++i) {
+    const double* r = obs + i * (d + 1);
+    double eta = 0;
+    for (int k = 0; k < d; ++k) eta += r[k] * b[k];
+    lp += r[d] * eta - softplus(eta);
+  }
+  return lp;
+}
+// family 2: Poisson regression (log link), beta ~ N(0, hyper[0]^2); the theta-independent
+// -lgamma(y+1) is omitted (it cancels in the normalisation, reference src/joint_posterior.jl:149).
+static double ld_poisson(const double* b, int d, const double* obs, long long N, const double* h) {
+  double lp = 0;
+  for (int k = 0; k < d; ++k) lp += lpdf_normal(b[k], 0.0, h[0]);
+  for (long long i = 0; i < N; ++i) {
+    const double* r = obs + i * (d + 1);
+    double eta = 0;
+    for (int k = 0; k < d; ++k) eta += r[k] * b[k];
+    lp += r[d] * eta - std::exp(eta);
+  }
+  return lp;
+}
+// family 3: hierarchical normal ("eight schools"): theta = (mu, tau, theta_1..theta_J), obs
+// columns (y_j, s_j); y_j ~ N(theta_j, s_j^2), theta_j ~ N(mu, tau^2), flat mu,
+// tau ~ half-Cauchy(0, hyper[0]).
+static double ld_hier(const double* t, int d, const double* obs, long long N, const double* h) {
+  double mu = t[0], tau = t[1];
+  double lp = std::log(2.0 / (M_PI * h[0])) - std::log1p((tau / h[0]) * (tau / h[0]));
+  for (long long j = 0; j < N; ++j) {
+    const double* r = obs + j * 2;
+    lp += lpdf_normal(r[0], t[2 + j], r[1]) + lpdf_normal(t[2 + j], mu, tau);
+  }
+  (void)d;
+  return lp;
+}
+// family 4: README "HiWorld" linear regression (reference README.md:245-258):
+// theta = (beta_0..beta_{p-1}, sigma); obs columns (x_0..x_{p-1}, y);
+// lpdf_normal(beta,0,hyper[0]) + lpdf_normal(sigma,0,hyper[1]) + lpdf_normal(y, X beta, sigma).
+static double ld_linreg(const double* t, int d, const double* obs, long long N, const double* h) {
+  int p = d - 1;
+  double sigma = t[p];
+  double lp = lpdf_normal(sigma, 0.0, h[1]);
+  for (int k = 0; k < p; ++k) lp += lpdf_normal(t[k], 0.0, h[0]);
+  for (long long i = 0; i < N; ++i) {
+    const double* r = obs + i * (p + 1);
+    double eta = 0;
+    for (int k = 0; k < p; ++k) eta += r[k] * t[k];
+    lp += lpdf_normal(r[p], eta, sigma);
+  }
+  return lp;
+}
+
+double orc_log_density(int family, const double* theta, int d, const double* obs, long long N, const double* hyper) {
+  switch (family) {
+    case 0: return ld_binmix(theta, obs, N, hyper);
+    case 1: return ld_logistic(theta, d, obs, N, hyper);
+    case 2: return ld_poisson(theta, d, obs, N, hyper);
+    case 3: return ld_hier(theta, d, obs, N, hyper);
+    case 4: return ld_linreg(theta, d, obs, N, hyper);
+  }
+  return NAN;
+}
+
+// Unconstrained log-density: transform, user density, log-Jacobian.
+// reference src/joint_posterior.jl:147-154 (log_density! / log_density_cache) without neg_min.
+double orc_log_density_unc(int family, const int* code, const double* x, int d, const double* obs, long long N,
+                           const double* hyper, double* theta_out) {
+  std::vector<double> th(d);
+  double lj;
+  orc_transform(code, d, x, th.data(), &lj);
+  if (theta_out) std::memcpy(theta_out, th.data(), sizeof(double) * d);
+  return orc_log_density(family, th.data(), d, obs, N, hyper) + lj;
+}
+
+// ------------------------------------------------------------------------------------------
+// Stages 2-4: eval_grid! restated from its call sites (reference src/joint_posterior.jl:180,186
+// and the consumers src/marginal_posterior.jl:98-123, src/interp.jl:448-455 which require
+// sum(density) == 1).  For node m with standard-normal-space coordinates z_m:
+//    x_m = mu_hat + U z_m ;  a_m = log_density_unc(x_m) + neg_min + |z_m|^2 / 2
+//    density_m = w_m exp(a_m - max a) / sum_m' w_m' exp(a_m' - max a)
+// (|z|^2/2 is the importance correction for integrating against the Gaussian-weight rule.)
+// Theta is written SoA: Theta[k*M + m].  m0/m1 restrict the evaluated node range (bounded CPU
+// baselines); normalisation is over the evaluated range.  threads <= 0 -> all cores.
+// ------------------------------------------------------------------------------------------
+int orc_eval_grid(int rule_id, int family, const int* code, int d, int p, const uint8_t* idx, const double* w,
+                  long long M, long long m0, long long m1, const double* mu_hat, const double* U, double neg_min,
+                  const double* obs, long long N, const double* hyper, double* Theta, double* logdens,
+                  double* density, int threads) {
+  Rule r = get_rule(rule_id);
+  if (m1 > M) m1 = M;
+  std::vector<double> a(M, -INFINITY);
+  int nthr = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  if (nthr < 1) nthr = 1;
+  std::atomic<long long> next(m0);
+  auto worker = [&]() {
+    std::vector<double> x(d), th(d);
+    while (true) {
+      long long mb = next.fetch_add(16);
+      if (mb >= m1) break;
+      long long me = std::min(mb + 16, m1);
+      for (long long m = mb; m < me; ++m) {
+    double zz = 0;
+    for (int k = 0; k < d; ++k) x[k] = mu_hat[k];
+    for (int j = 0; j < p; ++j) {
+      double z = r.nodes[idx[m * p + j]];
+      zz += z * z;
+      if (z != 0.0)
+        for (int k = 0; k < d; ++k) x[k] += A_(U, k, j, d) * z;
+    }
+    double lj;
+    orc_transform(code, d, x.data(), th.data(), &lj);
+    double ld = orc_log_density(family, th.data(), d, obs, N, hyper) + lj + neg_min;
+    if (Theta)
+      for (int k = 0; k < d; ++k) Theta[(size_t)k * M + m] = th[k];
+    if (logdens) logdens[m] = ld;
+    a[m] = ld + 0.5 * zz;
+      }
+    }
+  };
+  if (nthr == 1) {
+    worker();
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthr; ++t) pool.emplace_back(worker);
+    for (auto& t : pool) t.join();
+  }
+  double amax = -INFINITY;
+  for (long long m = m0; m < m1; ++m)
+    if (a[m] > amax) amax = a[m];
+  long double S = 0;
+  for (long long m = m0; m < m1; ++m) {
+    density[m] = w[m] * std::exp(a[m] - amax);
+    S += density[m];
+  }
+  for (long long m = m0; m < m1; ++m) density[m] = (double)(density[m] / S);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage 5: marginal (reference src/marginal_posterior.jl:117-123) and Grid CDF
+// (reference src/interp.jl:21-31, 448-481).
+// ------------------------------------------------------------------------------------------
+
+// Julia 0.6 Base.cumsum on a Float64 vector: pairwise accumulation, block size 128
+// (Base._accumulate_pairwise!); restated because interp.jl:30 calls cumsum.
+static double accumulate_pairwise(double* c, const double* v, double s, long long i1, long long n) {
+  if (n < 128) {
+    double s_ = v[i1];
+    c[i1] = s + s_;
+    for (long long i = i1 + 1; i < i1 + n; ++i) {
+      s_ = s_ + v[i];
+      c[i] = s + s_;
+    }
+    return s_;
+  }
+  long long n2 = n >> 1;
+  double s_ = accumulate_pairwise(c, v, s, i1, n2);
+  s_ = s_ + accumulate_pairwise(c, v, s + s_, i1 + n2, n - n2);
+  return s_;
+}
+
+// Julia Base.searchsortedfirst / searchsortedlast (Base.Sort), verbatim bisection; 1-based
+// results.  Needed because quantile() runs them on weight_nodes, which need not be monotone
+// (signed Smolyak weights) -- reference src/interp.jl:473,475.
+static int jl_searchsortedfirst(const double* v, int n, double x) {
+  int lo = 0, hi = n + 1;
+  while (lo < hi - 1) {
+    int m = (int)(((unsigned)lo + (unsigned)hi) >> 1);
+    if (v[m - 1] < x)
+      lo = m;
+    else
+      hi = m;
+  }
+  return hi;
+}
+static int jl_searchsortedlast(const double* v, int n, double x) {
+  int lo = 0, hi = n + 1;
+  while (lo < hi - 1) {
+    int m = (int)(((unsigned)lo + (unsigned)hi) >> 1);
+    if (x < v[m - 1])
+      hi = m;
+    else
+      lo = m;
+  }
+  return lo;
+}
+static long long searchsortedlast_ll(const double* v, long long n, double x) {
+  long long lo = 0, hi = n + 1;
+  while (lo < hi - 1) {
+    long long m = (lo + hi) >> 1;
+    if (x < v[m - 1])
+      hi = m;
+    else
+      lo = m;
+  }
+  return lo;
+}
+
+// reference src/interp.jl:479-481 (grid_interp), 1-based i.
+static double grid_interp(const double* x, const double* y, int i, double z) {
+  return y[i - 2] + (z - x[i - 2]) * (y[i - 1] - y[i - 2]) / (x[i - 1] - x[i - 2]);
+}
+
+// marginal(jp, f) with the Grid CDF.  values/weights are the outputs of weights_values
+// (src/marginal_posterior.jl:98-115).  Outputs: mu, sigma (:120-121, no renormalisation, no
+// clamp), the 100 value/weight knots (interp.jl:448-457) and optionally the sorted arrays and
+// the cumulative weights.
+int orc_marginal(const double* values, const double* weights, long long M, double* mu, double* sigma,
+                 double* value_nodes, double* weight_nodes, double* sorted_v, double* sorted_w, double* cum_w) {
+  long double m1 = 0, m2 = 0;
+  for (long long i = 0; i < M; ++i) {
+    m1 += (long double)weights[i] * values[i];
+    m2 += (long double)weights[i] * (values[i] * values[i]);
+  }
+  *mu = (double)m1;
+  *sigma = std::sqrt((double)m2 - (*mu) * (*mu));
+  // interp.jl:21-26 simultaneous_sort!: sortperm is stable (MergeSort)
+  std::vector<long long> si(M);
+  std::iota(si.begin(), si.end(), 0LL);
+  std::stable_sort(si.begin(), si.end(), [&](long long a, long long b) { return values[a] < values[b]; });
+  std::vector<double> v(M), wt(M), c(M);
+  for (long long i = 0; i < M; ++i) v[i] = values[si[i]], wt[i] = weights[si[i]];
+  accumulate_pairwise(c.data(), wt.data(), 0.0, 0, M);  // interp.jl:30 cumsum
+  // interp.jl:450 linspace(min, max, 100): Julia's twice-precision range, i.e. the correctly
+  // rounded lerp; long double reproduces it to the last bit for all but pathological inputs.
+  for (int i = 0; i < 100; ++i) {
+    long double t = (long double)i / 99.0L;
+    value_nodes[i] = (double)((long double)v[0] + t * ((long double)v[M - 1] - (long double)v[0]));
+  }
+  value_nodes[0] = v[0];
+  value_nodes[99] = v[M - 1];
+  for (int i = 0; i < 100; ++i) weight_nodes[i] = 0.0;  // :451
+  weight_nodes[99] = 1.0;                                // :452
+  for (int i = 1; i < 99; ++i) {                         // :453-455, itp[x] Gridded(Linear())
+    double x = value_nodes[i];
+    long long ix = searchsortedlast_ll(v.data(), M, x);  // last knot <= x (ties: last duplicate)
+    if (ix < 1) ix = 1;
+    if (ix > M - 1) ix = M - 1;
+    double k0 = v[ix - 1], k1 = v[ix];
+    double fx = (x - k0) / (k1 - k0);
+    weight_nodes[i] = c[ix - 1] * (1 - fx) + c[ix] * fx;
+  }
+  if (sorted_v) std::memcpy(sorted_v, v.data(), sizeof(double) * M);
+  if (sorted_w) std::memcpy(sorted_w, wt.data(), sizeof(double) * M);
+  if (cum_w) std::memcpy(cum_w, c.data(), sizeof(double) * M);
+  return 0;
+}
+
+// reference src/interp.jl:467-478 (quantile(::Grid, p)); field order Grid(weights, values).
+double orc_quantile(const double* weight_nodes, const double* value_nodes, int n, double p) {
+  if (p <= 0) return -INFINITY;
+  if (p >= 1) return INFINITY;
+  int i;
+  if (p < 0.5)
+    i = jl_searchsortedfirst(weight_nodes, n, p);
+  else
+    i = jl_searchsortedlast(weight_nodes, n, p) + 1;
+  return grid_interp(weight_nodes, value_nodes, i, p);
+}
+
+// reference src/interp.jl:458-466 (cdf(::Grid, x)).
+double orc_cdf(const double* weight_nodes, const double* value_nodes, int n, double x) {
+  if (x < value_nodes[0]) return 0.0;
+  if (x > value_nodes[n - 1]) return 1.0;
+  return grid_interp(value_nodes, weight_nodes, jl_searchsortedfirst(value_nodes, n, x), x);
+}
+
+// ------------------------------------------------------------------------------------------
+// GLM score / information at beta (used by the test-side Newton mode finder; upstream of the
+// five stages, reference src/joint_posterior.jl:164-168).  family 1 or 2.
+// g = d/dbeta log posterior, Hneg = -d2/dbeta2 log posterior (d x d column-major).
+// ------------------------------------------------------------------------------------------
+double orc_glm_grad_hess(int family, const double* beta, int d, const double* obs, long long N, const double* hyper,
+                         double* g, double* Hneg) {
+  std::vector<long double> G(d, 0), Hh((size_t)d * d, 0);
+  long double ll = 0;
+  for (long long i = 0; i < N; ++i) {
+    const double* r = obs + i * (d + 1);
+    double eta = 0;
+    for (int k = 0; k < d; ++k) eta += r[k] * beta[k];
+    double mu, wgt;
+    if (family == 1) {
+      mu = 1.0 / (1.0 + std::exp(-eta));
+      wgt = mu * (1 - mu);
+      ll += r[d] * eta - softplus(eta);
+    } else {
+      mu = std::exp(eta);
+      wgt = mu;
+      ll += r[d] * eta - mu;
+    }
+    double res = r[d] - mu;
+    for (int k = 0; k < d; ++k) {
+      G[k] += res * r[k];
+      for (int l = 0; l <= k; ++l) Hh[(size_t)l + (size_t)k * d] += wgt * r[k] * r[l];
+    }
+  }
+  double s2 = hyper[0] * hyper[0];
+  for (int k = 0; k < d; ++k) {
+    ll += lpdf_normal(beta[k], 0.0, hyper[0]);
+    g[k] = (double)G[k] - beta[k] / s2;
+    for (int l = 0; l <= k; ++l) {
+      double h = (double)Hh[(size_t)l + (size_t)k * d] + (l == k ? 1.0 / s2 : 0.0);
+      A_(Hneg, l, k, d) = h;
+      A_(Hneg, k, l, d) = h;
+    }
+  }
+  return (double)ll;
+}
+
+int orc_num_threads() { return (int)std::thread::hardware_concurrency(); }
+
+}  // extern "C"

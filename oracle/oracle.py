@@ -1,0 +1,239 @@
+"""ctypes/numpy front end of the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this module.  See the header of oracle/jp_oracle.cpp for what is restated from where and how the
+oracle is pinned.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+FAMILY = {"binomial_mixture": 0, "logistic": 1, "poisson": 2, "hier_normal": 3, "normal_linear": 4}
+RULE = {"GenzKeister": 0, "KronrodPatterson": 1}
+REAL, POSITIVE, PROBABILITY = 0, 1, 2
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_bp = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libjporacle.so")
+    src = os.path.join(_HERE, "jp_oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libjporacle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libjporacle.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        L.orc_log_density.restype = C.c_double
+        L.orc_log_density_unc.restype = C.c_double
+        L.orc_quantile.restype = C.c_double
+        L.orc_cdf.restype = C.c_double
+        L.orc_glm_grad_hess.restype = C.c_double
+        L.orc_smolyak_build.restype = C.c_longlong
+        _LIB = L
+    return _LIB
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+# ---------------------------------------------------------------- scale matrix
+def _colmajor(A):
+    return np.asfortranarray(np.array(A, dtype=np.float64))
+
+
+def chol(S):
+    S = _colmajor(S)
+    d = S.shape[0]
+    U = np.zeros((d, d), order="F")
+    lib().orc_chol(_ptr(U), _ptr(S), C.c_int(d))
+    return U
+
+
+def try_chol(S):
+    S = _colmajor(S)
+    d = S.shape[0]
+    U = np.zeros((d, d), order="F")
+    ok = lib().orc_try_chol(_ptr(U), _ptr(S), C.c_int(d))
+    return bool(ok), U
+
+
+def inv_upper(U):
+    U = _colmajor(U).copy(order="F")
+    lib().orc_inv_upper(_ptr(U), C.c_int(U.shape[0]))
+    return U
+
+
+def inv_chol(H):
+    H = _colmajor(H)
+    d = H.shape[0]
+    U = np.zeros((d, d), order="F")
+    lib().orc_inv_chol(_ptr(U), _ptr(H), C.c_int(d))
+    return U
+
+
+def reduce_dimensions(H, max_rank=0):
+    H = _colmajor(H)
+    d = H.shape[0]
+    out = np.zeros((d, d), order="F")
+    p = lib().orc_reduce_dimensions(_ptr(H), C.c_int(d), C.c_int(max_rank), _ptr(out))
+    return np.asfortranarray(out[:, :p])
+
+
+def deduce_scale_dynamic(H):
+    H = _colmajor(H)
+    d = H.shape[0]
+    U = np.zeros((d, d), order="F")
+    p = lib().orc_deduce_scale_dynamic(_ptr(H), C.c_int(d), _ptr(U))
+    return np.asfortranarray(U[:, :p])
+
+
+# ---------------------------------------------------------------- stage 1
+def rule_info(rule=0):
+    lv, nm = C.c_int(), C.c_int()
+    lib().orc_rule_info(C.c_int(rule), C.byref(lv), C.byref(nm), None, None, None)
+    npts = np.zeros(lv.value, dtype=np.int32)
+    nodes = np.zeros(nm.value)
+    weights = np.zeros((lv.value, nm.value))
+    lib().orc_rule_info(C.c_int(rule), C.byref(lv), C.byref(nm), _ptr(npts), _ptr(nodes), _ptr(weights))
+    return npts, nodes, weights
+
+
+def smolyak_sizes(rule, d, L):
+    a, b = C.c_longlong(), C.c_longlong()
+    lib().orc_smolyak_sizes(C.c_int(rule), C.c_int(d), C.c_int(L), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def smolyak(rule, d, L):
+    """-> (idx uint8 [M, d], w float64 [M]) in ascending lexicographic key order."""
+    M = lib().orc_smolyak_build(C.c_int(rule), C.c_int(d), C.c_int(L), None, None, C.c_longlong(0))
+    idx = np.zeros((M, d), dtype=np.uint8)
+    w = np.zeros(M)
+    r = lib().orc_smolyak_build(C.c_int(rule), C.c_int(d), C.c_int(L), _ptr(idx), _ptr(w), C.c_longlong(M))
+    assert r == M
+    return idx, w
+
+
+# ---------------------------------------------------------------- stages 2-4
+def transform(code, x):
+    code = np.ascontiguousarray(code, dtype=np.int32)
+    x = _d(x)
+    th = np.zeros_like(x)
+    lj = C.c_double()
+    lib().orc_transform(_ptr(code), C.c_int(len(x)), _ptr(x), _ptr(th), C.byref(lj))
+    return th, lj.value
+
+
+def log_density(family, theta, obs, hyper):
+    theta, obs, hyper = _d(theta), _d(obs), _d(hyper)
+    N = obs.shape[0]
+    return lib().orc_log_density(C.c_int(family), _ptr(theta), C.c_int(len(theta)), _ptr(obs), C.c_longlong(N), _ptr(hyper))
+
+
+def log_density_unc(family, code, x, obs, hyper):
+    code = np.ascontiguousarray(code, dtype=np.int32)
+    x, obs, hyper = _d(x), _d(obs), _d(hyper)
+    return lib().orc_log_density_unc(C.c_int(family), _ptr(code), _ptr(x), C.c_int(len(x)), _ptr(obs),
+                                     C.c_longlong(obs.shape[0]), _ptr(hyper), None)
+
+
+def eval_grid(rule, family, code, idx, w, mu_hat, U, neg_min, obs, hyper, m0=0, m1=None, threads=0, want_theta=True):
+    """-> dict(theta [d, M], logdens [M], density [M]).  U is d x p (any memory order)."""
+    code = np.ascontiguousarray(code, dtype=np.int32)
+    idx = np.ascontiguousarray(idx, dtype=np.uint8)
+    w, mu_hat, obs, hyper = _d(w), _d(mu_hat), _d(obs), _d(hyper)
+    U = _colmajor(U)
+    d, p = U.shape
+    M = idx.shape[0]
+    assert idx.shape[1] == p and len(mu_hat) == d
+    if m1 is None:
+        m1 = M
+    theta = np.zeros((d, M)) if want_theta else None
+    ld = np.zeros(M)
+    dens = np.zeros(M)
+    lib().orc_eval_grid(C.c_int(rule), C.c_int(family), _ptr(code), C.c_int(d), C.c_int(p), _ptr(idx), _ptr(w),
+                        C.c_longlong(M), C.c_longlong(m0), C.c_longlong(m1), _ptr(mu_hat), _ptr(U),
+                        C.c_double(neg_min), _ptr(obs), C.c_longlong(obs.shape[0]), _ptr(hyper),
+                        _ptr(theta), _ptr(ld), _ptr(dens), C.c_int(threads))
+    return dict(theta=theta, logdens=ld, density=dens)
+
+
+# ---------------------------------------------------------------- stage 5
+def marginal(values, weights, want_sorted=False):
+    values, weights = _d(values), _d(weights)
+    M = len(values)
+    mu, sg = C.c_double(), C.c_double()
+    vn, wn = np.zeros(100), np.zeros(100)
+    sv = np.zeros(M) if want_sorted else None
+    sw = np.zeros(M) if want_sorted else None
+    cw = np.zeros(M) if want_sorted else None
+    lib().orc_marginal(_ptr(values), _ptr(weights), C.c_longlong(M), C.byref(mu), C.byref(sg), _ptr(vn), _ptr(wn),
+                       _ptr(sv), _ptr(sw), _ptr(cw))
+    out = dict(mu=mu.value, sigma=sg.value, value_nodes=vn, weight_nodes=wn)
+    if want_sorted:
+        out.update(sorted_values=sv, sorted_weights=sw, cum_weights=cw)
+    return out
+
+
+def quantile(weight_nodes, value_nodes, p):
+    wn, vn = _d(weight_nodes), _d(value_nodes)
+    return lib().orc_quantile(_ptr(wn), _ptr(vn), C.c_int(len(wn)), C.c_double(p))
+
+
+def cdf(weight_nodes, value_nodes, x):
+    wn, vn = _d(weight_nodes), _d(value_nodes)
+    return lib().orc_cdf(_ptr(wn), _ptr(vn), C.c_int(len(wn)), C.c_double(x))
+
+
+# ---------------------------------------------------------------- GLM mode (test side)
+def glm_grad_hess(family, beta, obs, hyper):
+    beta, obs, hyper = _d(beta), _d(obs), _d(hyper)
+    d = len(beta)
+    g = np.zeros(d)
+    H = np.zeros((d, d), order="F")
+    ll = lib().orc_glm_grad_hess(C.c_int(family), _ptr(beta), C.c_int(d), _ptr(obs), C.c_longlong(obs.shape[0]),
+                                 _ptr(hyper), _ptr(g), _ptr(H))
+    return ll, g, H
+
+
+def glm_mode(family, obs, hyper, d, iters=50, tol=1e-13):
+    """Newton iteration for the posterior mode; returns (beta_hat, Hneg, log posterior at the mode)."""
+    beta = np.zeros(d)
+    for _ in range(iters):
+        ll, g, H = glm_grad_hess(family, beta, obs, hyper)
+        step = np.linalg.solve(H, g)
+        # damp while the objective does not increase
+        t = 1.0
+        while t > 1e-8:
+            ll2, _, _ = glm_grad_hess(family, beta + t * step, obs, hyper)
+            if ll2 >= ll - 1e-12 * abs(ll):
+                break
+            t *= 0.5
+        beta = beta + t * step
+        if np.max(np.abs(t * step)) < tol * (1 + np.max(np.abs(beta))):
+            break
+    ll, g, H = glm_grad_hess(family, beta, obs, hyper)
+    return beta, H, ll
+
+
+def num_threads():
+    return lib().orc_num_threads()
