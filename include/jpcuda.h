@@ -1,0 +1,225 @@
+/* jpcuda.h -- C ABI of libjpcuda.so: the B200 (sm_100a) implementation of the posterior-integration
+ * hot path of chriselrod/JointPosteriors.jl.
+ *
+ * The reference has no FFI seam of its own (pure Julia, multiple dispatch).  The seam this library
+ * replaces is the internal call pair
+ *     eval_grid!(M.Grid, ldc, mu_hat, U, index(...), MP)      reference src/joint_posterior.jl:180,186
+ *     weights_values(jp, f) + Grid(wv)                        reference src/marginal_posterior.jl:98-123,
+ *                                                             src/interp.jl:448-457
+ * plus the small host-side scale-matrix helpers around it (src/joint_posterior.jl:15-144).
+ * INTEGRATION.md shows the Julia `ccall` shim a maintainer would add; the Python mirror in
+ * jointposteriors.jl_b200/ binds exactly these symbols through ctypes.
+ *
+ * Conventions
+ *   - every entry point returns a jp_status (0 = ok); jp_last_error() gives the message
+ *     (thread-local), mirroring the reference's Bool/throw conventions
+ *     (src/joint_posterior.jl:26, src/interp.jl:444).
+ *   - matrices named U/H/S are COLUMN-major (Julia layout); `obs` is ROW-major N x ncols.
+ *   - pointers prefixed h_ are host memory, d_ are device memory on the context's GPU.
+ *   - one jp_ctx = one GPU + one CUDA stream; calls on one ctx are serialised by the caller.
+ *     Entry points that write h_ outputs block until the data is on the host; entry points that
+ *     only touch d_ buffers are asynchronous on the ctx stream.
+ *   - there is no CPU fallback: without a CUDA device jp_ctx_create fails with JP_ERR_NO_DEVICE.
+ */
+#ifndef JPCUDA_H
+#define JPCUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum jp_status {
+  JP_OK = 0,
+  JP_ERR_BAD_ARG = 1,
+  JP_ERR_NOT_PD = 2,      /* Cholesky pivot <= 0: the `false` of try_chol!, src/joint_posterior.jl:26 */
+  JP_ERR_CUDA = 3,
+  JP_ERR_NO_DEVICE = 4,
+  JP_ERR_ALLOC = 5,
+  JP_ERR_UNSUPPORTED = 6
+} jp_status;
+
+/* quadrature rule families (SparseQuadratureGrids.GenzKeister / KronrodPatterson, reference test/runtests.jl:42) */
+enum { JP_RULE_GENZ_KEISTER = 0, JP_RULE_KRONROD_PATTERSON = 1 };
+/* constraint transforms (ConstrainedParameters RealVector / PositiveVector / ProbabilityVector,
+ * reference src/JointPosteriors.jl:22-26, README.md:32,247-248) -- one code per unconstrained coordinate */
+enum { JP_T_REAL = 0, JP_T_POSITIVE = 1, JP_T_PROBABILITY = 2 };
+/* likelihood families registered in the library (device-function plugins, csrc/jp_family.cuh) */
+enum {
+  JP_FAM_BINOMIAL_MIXTURE = 0, /* README Example 1, reference README.md:62-72 */
+  JP_FAM_LOGISTIC = 1,         /* logistic regression, N(0, s^2) prior */
+  JP_FAM_POISSON = 2,          /* Poisson regression (log link), N(0, s^2) prior */
+  JP_FAM_HIER_NORMAL = 3,      /* hierarchical normal ("eight schools") */
+  JP_FAM_NORMAL_LINEAR = 4     /* README Example 2 "HiWorld", reference README.md:245-258 */
+};
+/* log-density evaluation path of jp_fit */
+enum {
+  JP_PATH_AUTO = 0,
+  JP_PATH_FP64 = 1,   /* generic plugin kernel, FP64 throughout: every family */
+  JP_PATH_TC = 2      /* GLM families only: tcgen05 3xTF32 X*dTheta' contraction + centred epilogue */
+};
+
+typedef struct jp_ctx jp_ctx;
+typedef struct jp_grid jp_grid;
+typedef struct jp_data jp_data;
+typedef struct jp_posterior jp_posterior;
+
+const char* jp_last_error(void);
+int jp_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-side scale matrix helpers (no GPU needed).  d x d column-major.
+ * --------------------------------------------------------------------------------------------- */
+/* chol!      reference src/joint_posterior.jl:30-43  */
+int jp_chol(double* h_U, const double* h_S, int d);
+/* try_chol!  reference src/joint_posterior.jl:15-29; JP_ERR_NOT_PD when a pivot is not positive */
+int jp_try_chol(double* h_U, const double* h_S, int d);
+/* inv!       reference src/joint_posterior.jl:56-68 (in place, upper triangular) */
+int jp_inv_upper(double* h_U, int d);
+/* inv_chol!  reference src/joint_posterior.jl:72-76 : U = chol(H)^-1 (lower triangle zeroed) */
+int jp_inv_chol(double* h_U, const double* h_H, int d);
+/* reduce_dimensions!  reference src/joint_posterior.jl:98-110 (max_rank = 0) and :120-134
+ * (FixedRank{p}: max_rank = p).  h_out is d x d storage; *rank receives the kept column count. */
+int jp_reduce_dimensions(const double* h_H, int d, int max_rank, double* h_out, int* rank);
+/* deduce_scale!(..., Dynamic)  reference src/joint_posterior.jl:136-138 : Cholesky if H is positive
+ * definite, else the eigen fallback.  *rank receives p; h_U is d x p column-major in d x d storage. */
+int jp_deduce_scale_dynamic(const double* h_H, int d, double* h_U, int* rank);
+
+/* ---------------------------------------------------------------------------------------------
+ * Context
+ * --------------------------------------------------------------------------------------------- */
+int jp_ctx_create(int device, jp_ctx** out);
+int jp_ctx_destroy(jp_ctx* ctx);
+/* run all subsequent work of this ctx on an externally owned cudaStream_t (e.g. torch's current
+ * stream, so that torch.distributed collectives order with the library's kernels). */
+int jp_ctx_set_stream(jp_ctx* ctx, void* cuda_stream);
+int jp_ctx_sync(jp_ctx* ctx);
+/* number of kernels this ctx has launched since creation (for bench.py's gpu_launches) */
+long long jp_ctx_launch_count(const jp_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 1 -- Smolyak sparse grid, built on the GPU and cached per ctx by (rule, d_eff, level),
+ * the analogue of the reference's grid cache key index(U, R, data, n), src/joint_posterior.jl:157-162.
+ * Nodes are integer keys (one 1-D master-node index per dimension); merged nodes are in ascending
+ * lexicographic key order.
+ * --------------------------------------------------------------------------------------------- */
+int jp_grid_get(jp_ctx* ctx, int rule, int d_eff, int level, jp_grid** out);
+long long jp_grid_size(const jp_grid* g);
+int jp_grid_dim(const jp_grid* g);
+/* pre-merge statistics of the build: number of multi-indices with non-zero combination coefficient
+ * and number of tensor-product points before the duplicate merge */
+int jp_grid_build_stats(const jp_grid* g, long long* n_multi, long long* n_premerge);
+/* h_idx: M x d_eff row-major uint8 keys; h_w: M weights.  Either may be NULL. */
+int jp_grid_download(const jp_grid* g, uint8_t* h_idx, double* h_w);
+/* 1-D rule tables (master z-nodes, per-level weights) as compiled into the library */
+int jp_rule_info(int rule, int* levels, int* nmax, int* h_npts, double* h_nodes, double* h_weights);
+
+/* ---------------------------------------------------------------------------------------------
+ * Observations
+ * --------------------------------------------------------------------------------------------- */
+/* h_obs: N x ncols row-major doubles, family-specific columns:
+ *   BINOMIAL_MIXTURE (X, freq, NmX)            hyper = (a_m-1, b_m-1, a_p-1, b_p-1, a_tau-1, b_tau-1)
+ *   LOGISTIC/POISSON (x_0..x_{d-1}, y)         hyper = (prior sd)
+ *   HIER_NORMAL      (y_j, s_j)                hyper = (half-Cauchy scale of tau)
+ *   NORMAL_LINEAR    (x_0..x_{p-1}, y)         hyper = (sd of beta prior, sd of sigma prior) */
+int jp_data_upload(jp_ctx* ctx, int family, long long N, int ncols, const double* h_obs, const double* h_hyper,
+                   int n_hyper, jp_data** out);
+int jp_data_free(jp_data* data);
+
+/* GLM score and observed information at beta on the GPU (mode finding, upstream of the five
+ * stages: reference src/joint_posterior.jl:164-168).  h_g: d; h_Hneg: d x d column-major =
+ * -Hessian of the log posterior; *h_logpost: log posterior at beta. */
+int jp_glm_grad_hess(jp_ctx* ctx, const jp_data* data, int d, const double* h_beta, double* h_g, double* h_Hneg,
+                     double* h_logpost);
+
+/* Unconstrained log-density  log_density(transform(x), data) + log|J(x)|  at K arbitrary points: the
+ * objective `mode` minimises (reference src/joint_posterior.jl:164-168, sign flipped, no neg_min),
+ * evaluated by the same family plugins as the grid path.  h_x: K x d row-major; h_ld: K.  Blocking. */
+int jp_log_density_points(jp_ctx* ctx, const jp_data* data, int d, const int* h_transform, long long K,
+                          const double* h_x, double* h_ld);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stages 2-4 -- fit: theta = transform(mu_hat + U z), log-density per node, normalised weights.
+ * Replaces eval_grid!, reference src/joint_posterior.jl:180,186.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct jp_fit_args {
+  int d;                        /* number of unconstrained coordinates */
+  int p;                        /* columns of U (= grid dimension d_eff), p <= d */
+  const int* h_transform;       /* d transform codes */
+  const double* h_mu_hat;       /* d: unconstrained mode, `M.diff_buffer.state.x` (:167) */
+  const double* h_U;            /* d x p column-major scale matrix from deduce_scale! */
+  double neg_min;               /* minimised objective, added to every log-density (:149,:153) */
+  int path;                     /* JP_PATH_* */
+  long long node_begin;         /* node shard [node_begin, node_end) of the merged grid owned by */
+  long long node_end;           /*   this ctx; (0, -1) = all nodes */
+} jp_fit_args;
+
+/* allocate the device-resident result (Theta SoA [d][M_local], density, work buffers) */
+int jp_posterior_create(jp_ctx* ctx, const jp_grid* g, const jp_data* data, const jp_fit_args* args,
+                        jp_posterior** out);
+int jp_posterior_free(jp_posterior* post);
+long long jp_posterior_size(const jp_posterior* post); /* local node count */
+
+/* single-GPU fit: all of stages 2-4, asynchronous on the ctx stream. */
+int jp_fit(jp_posterior* post, const jp_fit_args* args);
+
+/* multi-GPU fit in phases; the host performs the (tiny) collectives on the d_ buffers between them:
+ *   jp_fit_local(post, args, d_local_max)        stages 2-3 on the shard; writes max_m a_m (1 double)
+ *   jp_fit_local_sum(post, d_global_max, d_sum)  e_m = w_m exp(a_m - gmax); writes sum_m e_m (1 double)
+ *   jp_fit_normalise(post, d_global_sum)         density_m = e_m / gsum                               */
+int jp_fit_local(jp_posterior* post, const jp_fit_args* args, double* d_local_max);
+int jp_fit_local_sum(jp_posterior* post, const double* d_global_max, double* d_local_sum);
+int jp_fit_normalise(jp_posterior* post, const double* d_global_sum);
+
+/* results to the host (blocking).  h_theta: d x M_local row-major (coordinate k of node m at
+ * [k*M_local + m]); h_logdens: log-density + neg_min per node; h_density: normalised weights. */
+int jp_get_theta(jp_posterior* post, double* h_theta);
+int jp_get_logdens(jp_posterior* post, double* h_logdens);
+int jp_get_density(jp_posterior* post, double* h_density);
+/* device views for zero-copy consumers (valid until jp_posterior_free) */
+const double* jp_dev_theta(const jp_posterior* post);
+const double* jp_dev_density(const jp_posterior* post);
+/* which path the last jp_fit took (JP_PATH_FP64 or JP_PATH_TC) */
+int jp_fit_path_used(const jp_posterior* post);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 5 -- marginal(jp, f): weighted mean / sigma and the 100-knot Grid CDF.
+ * Replaces weights_values + marginal + Grid, reference src/marginal_posterior.jl:98-123,
+ * src/interp.jl:21-31,448-457.  Batched over K functions f.
+ *   coordinate selectors f(Theta) = Theta[coord] are evaluated on the device (zero-copy views of
+ *   the Theta SoA); arbitrary host closures are supported by uploading their values f(Theta_m).
+ * Outputs per marginal k: h_mu[k], h_sigma[k], h_value_nodes[k*100 ..], h_weight_nodes[k*100 ..].
+ * --------------------------------------------------------------------------------------------- */
+#define JP_GRID_KNOTS 100
+int jp_marginal_coords(jp_posterior* post, int K, const int* h_coords, double* h_mu, double* h_sigma,
+                       double* h_value_nodes, double* h_weight_nodes);
+int jp_marginal_values(jp_posterior* post, int K, const double* h_values /* K x M_local */, double* h_mu,
+                       double* h_sigma, double* h_value_nodes, double* h_weight_nodes);
+/* sorted (values, weights) of marginal k of the last jp_marginal_* call: the `wv` field of the
+ * reference's marginal struct after simultaneous_sort!, src/interp.jl:21-26.  Blocking. */
+int jp_marginal_sorted(jp_posterior* post, int k, double* h_sorted_values, double* h_sorted_weights,
+                       double* h_cum_weights);
+
+/* multi-GPU marginal in phases (sort-free splitter histogram):
+ *   jp_marginal_local_moments: d_out[k*4 + {0,1,2,3}] = (sum w v, sum w v^2, min v, max v) on the shard
+ *   jp_marginal_local_knots:   given the GLOBAL (min, max) per marginal in d_minmax[k*2 + {0,1}], for each
+ *     interior knot i = 1..98 writes d_out[(k*98 + i-1)*6 + {0..5}] =
+ *       (S = sum of w over v <= x_i,  pred = max v <= x_i (-inf if none),
+ *        succ = min v > x_i (+inf if none), global index of the lowest-index element attaining succ,
+ *        its weight, 0)
+ *   the host combines over ranks (jointposteriors.jl_b200.distributed) into the 100-knot Grid.
+ * h_coords may be NULL when d_values (K x M_local, device) is given instead. */
+int jp_marginal_local_moments(jp_posterior* post, int K, const int* h_coords, const double* d_values, double* d_out);
+int jp_marginal_local_knots(jp_posterior* post, int K, const int* h_coords, const double* d_values,
+                            const double* d_minmax, double* d_out);
+
+/* quantile(::Grid, p) and cdf(::Grid, x): reference src/interp.jl:458-481 (host, no GPU).
+ * Field order as in the reference: Grid(weights, values). */
+double jp_quantile(const double* h_weight_nodes, const double* h_value_nodes, int n, double p);
+double jp_cdf(const double* h_weight_nodes, const double* h_value_nodes, int n, double x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JPCUDA_H */

@@ -1,0 +1,22 @@
+"""B200-native posterior integration behind the JointPosteriors.jl API (Model / fit / marginal).
+
+Everything numerical runs in libjpcuda.so (hand-written sm_100a CUDA, C ABI in include/jpcuda.h);
+this package is the host-side mirror of the reference's Julia interface and binds the library with
+ctypes.  There is no CPU fallback: importing works anywhere, computing needs a B200.
+"""
+from ._lib import JPError, NotPositiveDefinite, PATH_AUTO, PATH_FP64, PATH_TC, lib
+from .data import (BinaryClassificationData, Data, HierNormalData, LogisticData, NormalLinearData, PoissonData)
+from .linalg import chol, deduce_scale_dynamic, inv_chol, inv_upper, reduce_dimensions, try_chol
+from .marginals import Grid, cdf, marginal, marginals, quantile
+from .model import (Context, DeviceData, Dynamic, FixedRank, Full, GenzKeister, JointPosterior, JointPosteriorRaw,
+                    KronrodPatterson, Model, Smolyak, SmolyakRaw, default, fit, log_density_unc, mode)
+from .params import PositiveVector, ProbabilityVector, RealVector, parameter
+
+__all__ = [
+    "Model", "fit", "marginal", "marginals", "mode", "quantile", "cdf", "Grid", "JointPosterior", "JointPosteriorRaw",
+    "parameter", "RealVector", "PositiveVector", "ProbabilityVector", "Data", "BinaryClassificationData",
+    "LogisticData", "PoissonData", "HierNormalData", "NormalLinearData", "Smolyak", "SmolyakRaw", "GenzKeister",
+    "KronrodPatterson", "Dynamic", "Full", "FixedRank", "default", "Context", "DeviceData", "chol", "try_chol",
+    "inv_upper", "inv_chol", "reduce_dimensions", "deduce_scale_dynamic", "JPError", "NotPositiveDefinite",
+    "PATH_AUTO", "PATH_FP64", "PATH_TC", "log_density_unc",
+]

@@ -1,0 +1,236 @@
+// jp_api.cu -- handles and plumbing of the C ABI (include/jpcuda.h): context, grid cache,
+// observation upload, posterior buffers, host getters.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include "jp_common.cuh"
+#include "jp_family.cuh"
+
+extern "C" {
+
+int jp_ctx_create(int device, jp_ctx** out) {
+  JP_REQUIRE(out, "jp_ctx_create: null output");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    jp_set_error("jp_ctx_create: no CUDA device (%s); libjpcuda has no CPU fallback",
+                 e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    cudaGetLastError();
+    return JP_ERR_NO_DEVICE;
+  }
+  JP_REQUIRE(device >= 0 && device < count, "jp_ctx_create: device %d out of range [0,%d)", device, count);
+  JP_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  JP_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    jp_set_error("jp_ctx_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                 prop.major, prop.minor);
+    return JP_ERR_UNSUPPORTED;
+  }
+  jp_ctx* ctx = new (std::nothrow) jp_ctx();
+  if (!ctx) return JP_ERR_ALLOC;
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  JP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->own_stream = true;
+  JP_CUDA(cudaMalloc(&ctx->d_scratch, sizeof(double) * JP_SCRATCH_DOUBLES));
+  JP_CUDA(cudaMallocHost(&ctx->h_pinned, sizeof(double) * JP_PINNED_DOUBLES));
+  *out = ctx;
+  return JP_OK;
+}
+
+static void free_grid(jp_grid* g) {
+  if (!g) return;
+  cudaFree(g->d_idx);
+  cudaFree(g->d_w);
+  cudaFree(g->d_hzz);
+  delete g;
+}
+
+int jp_ctx_destroy(jp_ctx* ctx) {
+  if (!ctx) return JP_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->grids) free_grid(kv.second);
+  cudaFree(ctx->d_scratch);
+  cudaFreeHost(ctx->h_pinned);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return JP_OK;
+}
+
+int jp_ctx_set_stream(jp_ctx* ctx, void* cuda_stream) {
+  JP_REQUIRE(ctx, "jp_ctx_set_stream: null ctx");
+  JP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->own_stream = false;
+  return JP_OK;
+}
+
+int jp_ctx_sync(jp_ctx* ctx) {
+  JP_REQUIRE(ctx, "jp_ctx_sync: null ctx");
+  JP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return JP_OK;
+}
+
+long long jp_ctx_launch_count(const jp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------ stage 1
+int jp_grid_get(jp_ctx* ctx, int rule, int d_eff, int level, jp_grid** out) {
+  JP_REQUIRE(ctx && out, "jp_grid_get: null argument");
+  JP_CUDA(cudaSetDevice(ctx->device));
+  auto key = std::make_tuple(rule, d_eff, level);
+  auto it = ctx->grids.find(key);
+  if (it != ctx->grids.end()) {
+    *out = it->second;
+    return JP_OK;
+  }
+  jp_grid* g = new (std::nothrow) jp_grid();
+  if (!g) return JP_ERR_ALLOC;
+  int st = jp_grid_build(ctx, rule, d_eff, level, g);
+  if (st != JP_OK) {
+    free_grid(g);
+    return st;
+  }
+  ctx->grids[key] = g;
+  *out = g;
+  return JP_OK;
+}
+
+long long jp_grid_size(const jp_grid* g) { return g ? g->M : -1; }
+int jp_grid_dim(const jp_grid* g) { return g ? g->d : -1; }
+
+int jp_grid_build_stats(const jp_grid* g, long long* n_multi, long long* n_premerge) {
+  JP_REQUIRE(g, "jp_grid_build_stats: null grid");
+  if (n_multi) *n_multi = g->n_multi;
+  if (n_premerge) *n_premerge = g->n_premerge;
+  return JP_OK;
+}
+
+int jp_grid_download(const jp_grid* g, uint8_t* h_idx, double* h_w) {
+  JP_REQUIRE(g, "jp_grid_download: null grid");
+  JP_CUDA(cudaSetDevice(g->ctx->device));
+  JP_CUDA(cudaStreamSynchronize(g->ctx->stream));
+  if (h_idx) {
+    std::vector<uint8_t> soa((size_t)g->M * g->d);
+    JP_CUDA(cudaMemcpy(soa.data(), g->d_idx, soa.size(), cudaMemcpyDeviceToHost));
+    for (long long m = 0; m < g->M; ++m)
+      for (int k = 0; k < g->d; ++k) h_idx[(size_t)m * g->d + k] = soa[(size_t)k * g->M + m];
+  }
+  if (h_w) JP_CUDA(cudaMemcpy(h_w, g->d_w, (size_t)g->M * 8, cudaMemcpyDeviceToHost));
+  return JP_OK;
+}
+
+int jp_rule_info(int rule, int* levels, int* nmax, int* h_npts, double* h_nodes, double* h_weights) {
+  JP_REQUIRE(rule == 0 || rule == 1, "jp_rule_info: unknown rule %d", rule);
+  JpRule R = jp_get_rule(rule);
+  if (levels) *levels = R.levels;
+  if (nmax) *nmax = R.nmax;
+  if (h_npts) std::memcpy(h_npts, R.npts, sizeof(int) * R.levels);
+  if (h_nodes) std::memcpy(h_nodes, R.nodes, sizeof(double) * R.nmax);
+  if (h_weights) std::memcpy(h_weights, R.weights, sizeof(double) * R.levels * R.nmax);
+  return JP_OK;
+}
+
+// ------------------------------------------------------------------------------------ data
+int jp_data_upload(jp_ctx* ctx, int family, long long N, int ncols, const double* h_obs, const double* h_hyper,
+                   int n_hyper, jp_data** out) {
+  JP_REQUIRE(ctx && h_obs && out, "jp_data_upload: null argument");
+  JP_REQUIRE(N >= 1 && ncols >= 1, "jp_data_upload: empty data (N=%lld, ncols=%d)", N, ncols);
+  JP_REQUIRE(n_hyper >= 0 && n_hyper <= JP_MAX_HYPER, "jp_data_upload: n_hyper=%d out of range", n_hyper);
+  JP_REQUIRE(jp_find_family(family) != nullptr, "jp_data_upload: family %d is not registered", family);
+  JP_CUDA(cudaSetDevice(ctx->device));
+  jp_data* dt = new (std::nothrow) jp_data();
+  if (!dt) return JP_ERR_ALLOC;
+  dt->ctx = ctx; dt->family = family; dt->N = N; dt->ncols = ncols; dt->n_hyper = n_hyper;
+  for (int i = 0; i < n_hyper; ++i) dt->hyper[i] = h_hyper[i];
+  size_t bytes = (size_t)N * ncols * sizeof(double);
+  cudaError_t e = cudaMalloc(&dt->d_obs, bytes);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dt->d_obs, h_obs, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) {
+    jp_set_error("jp_data_upload: %s", cudaGetErrorString(e));
+    cudaFree(dt->d_obs);
+    delete dt;
+    return JP_ERR_CUDA;
+  }
+  *out = dt;
+  return JP_OK;
+}
+
+int jp_data_free(jp_data* data) {
+  if (!data) return JP_OK;
+  cudaSetDevice(data->ctx->device);
+  cudaStreamSynchronize(data->ctx->stream);
+  jp_tc_data_free(data);
+  cudaFree(data->d_obs);
+  cudaFree(data->d_a3);
+  delete data;
+  return JP_OK;
+}
+
+// ------------------------------------------------------------------------------------ posterior
+int jp_posterior_create(jp_ctx* ctx, const jp_grid* g, const jp_data* data, const jp_fit_args* args,
+                        jp_posterior** out) {
+  JP_REQUIRE(ctx && g && data && args && out, "jp_posterior_create: null argument");
+  JP_REQUIRE(args->d >= 1 && args->d <= JP_MAX_D, "jp_posterior_create: d=%d out of range [1,%d]", args->d, JP_MAX_D);
+  JP_REQUIRE(args->p >= 1 && args->p <= args->d, "jp_posterior_create: p=%d must be in [1,d=%d]", args->p, args->d);
+  JP_REQUIRE(args->p == g->d, "jp_posterior_create: U has %d columns but the grid has dimension %d", args->p, g->d);
+  long long m0 = args->node_begin, m1 = args->node_end;
+  if (m1 < 0) m1 = g->M;
+  JP_REQUIRE(m0 >= 0 && m0 < m1 && m1 <= g->M, "jp_posterior_create: node shard [%lld,%lld) not inside [0,%lld)", m0, m1,
+             g->M);
+  JP_CUDA(cudaSetDevice(ctx->device));
+  jp_posterior* p = new (std::nothrow) jp_posterior();
+  if (!p) return JP_ERR_ALLOC;
+  p->ctx = ctx; p->grid = g; p->data = data; p->d = args->d; p->p = args->p;
+  p->m0 = m0; p->m1 = m1; p->M = m1 - m0;
+  size_t M = (size_t)p->M;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes); };
+  A((void**)&p->d_theta, M * p->d * 8);
+  A((void**)&p->d_a, M * 8);
+  A((void**)&p->d_logdens, M * 8);
+  A((void**)&p->d_density, M * 8);
+  A((void**)&p->d_part, M * (JP_POST_PART_SPLITS + 1) * 8);
+  A((void**)&p->d_stats, 16 * 8);
+  A((void**)&p->d_mu, (size_t)p->d * 8);
+  A((void**)&p->d_U, (size_t)p->d * p->p * 8);
+  A((void**)&p->d_tcode, (size_t)p->d * 4);
+  if (e != cudaSuccess) {
+    jp_set_error("jp_posterior_create: %s", cudaGetErrorString(e));
+    jp_posterior_free(p);
+    return JP_ERR_CUDA;
+  }
+  *out = p;
+  return JP_OK;
+}
+
+int jp_posterior_free(jp_posterior* p) {
+  if (!p) return JP_OK;
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  cudaFree(p->d_theta); cudaFree(p->d_a); cudaFree(p->d_logdens); cudaFree(p->d_density); cudaFree(p->d_part);
+  cudaFree(p->d_stats); cudaFree(p->d_mu); cudaFree(p->d_U); cudaFree(p->d_tcode); cudaFree(p->d_dtheta);
+  cudaFree(p->d_vals); cudaFree((void*)p->d_vptr); cudaFree(p->d_perm_a); cudaFree(p->d_perm_b); cudaFree(p->d_hist);
+  cudaFree(p->d_sv); cudaFree(p->d_sw); cudaFree(p->d_cw); cudaFree(p->d_mout);
+  delete p;
+  return JP_OK;
+}
+
+long long jp_posterior_size(const jp_posterior* p) { return p ? p->M : -1; }
+const double* jp_dev_theta(const jp_posterior* p) { return p ? p->d_theta : nullptr; }
+const double* jp_dev_density(const jp_posterior* p) { return p ? p->d_density : nullptr; }
+int jp_fit_path_used(const jp_posterior* p) { return p ? p->path_used : 0; }
+
+static int download(jp_posterior* p, const double* d_src, double* h_dst, size_t n) {
+  JP_REQUIRE(p && h_dst, "jp_get_*: null argument");
+  JP_CUDA(cudaMemcpyAsync(h_dst, d_src, n * 8, cudaMemcpyDeviceToHost, p->ctx->stream));
+  JP_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  return JP_OK;
+}
+int jp_get_theta(jp_posterior* p, double* h) { return download(p, p ? p->d_theta : nullptr, h, p ? (size_t)p->M * p->d : 0); }
+int jp_get_logdens(jp_posterior* p, double* h) { return download(p, p ? p->d_logdens : nullptr, h, p ? (size_t)p->M : 0); }
+int jp_get_density(jp_posterior* p, double* h) { return download(p, p ? p->d_density : nullptr, h, p ? (size_t)p->M : 0); }
+
+}  // extern "C"

@@ -1,0 +1,210 @@
+// jp_common.cuh -- shared internals of libjpcuda.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+#include <tuple>
+
+#include "../../include/jpcuda.h"
+
+#define JP_NUM_SMS_B200 148
+#define JP_MAX_D 64          // maximum number of unconstrained coordinates
+#define JP_MAX_HYPER 8
+
+// ---------------------------------------------------------------------------- errors
+void jp_set_error(const char* fmt, ...);
+
+#define JP_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      jp_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));          \
+      return JP_ERR_CUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+#define JP_CHECK_LAUNCH(ctx)                                                                       \
+  do {                                                                                             \
+    (ctx)->launches++;                                                                             \
+    cudaError_t _e = cudaGetLastError();                                                           \
+    if (_e != cudaSuccess) {                                                                       \
+      jp_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e));      \
+      return JP_ERR_CUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+#define JP_REQUIRE(cond, ...)                                                                      \
+  do {                                                                                             \
+    if (!(cond)) {                                                                                 \
+      jp_set_error(__VA_ARGS__);                                                                   \
+      return JP_ERR_BAD_ARG;                                                                       \
+    }                                                                                              \
+  } while (0)
+
+#define JP_TRY(expr)                                                                               \
+  do {                                                                                             \
+    int _s = (expr);                                                                               \
+    if (_s != JP_OK) return _s;                                                                    \
+  } while (0)
+
+// ---------------------------------------------------------------------------- handles
+struct jp_grid {
+  jp_ctx* ctx = nullptr;
+  int rule = 0, d = 0, level = 0;
+  long long M = 0;
+  long long n_multi = 0, n_premerge = 0;
+  uint8_t* d_idx = nullptr;   // SoA keys: d_idx[k * M + m]
+  double* d_w = nullptr;      // merged quadrature weights
+  double* d_hzz = nullptr;    // 0.5 * |z_m|^2 (importance correction)
+  double zmax2 = 0;           // max_m |z_m|^2
+};
+
+struct jp_ctx {
+  int device = 0;
+  int sm_count = JP_NUM_SMS_B200;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  long long launches = 0;
+  std::map<std::tuple<int, int, int>, jp_grid*> grids;
+  // scratch for small reductions / scalars (device) and pinned host staging
+  double* d_scratch = nullptr;     // JP_SCRATCH_DOUBLES doubles
+  double* h_pinned = nullptr;      // JP_PINNED_DOUBLES doubles
+};
+#define JP_SCRATCH_DOUBLES (1 << 16)
+#define JP_PINNED_DOUBLES (1 << 16)
+
+struct jp_data {
+  jp_ctx* ctx = nullptr;
+  int family = 0;
+  long long N = 0;
+  int ncols = 0;
+  double* d_obs = nullptr;      // N x ncols row-major
+  double hyper[JP_MAX_HYPER] = {0};
+  int n_hyper = 0;
+  // GLM tensor-core operand (built lazily): A' = [x_hi | x_lo | x_hi] in TF32-representable FP32,
+  // N_pad x kp row-major, kp = 3*d rounded up to a multiple of 32 (one 128-byte swizzle atom per 32)
+  float* d_a3 = nullptr;
+  int a3_kp = 0;
+  long long a3_rows = 0;
+  void* tc_state = nullptr;     // opaque per-data state of the TC path (tensor maps, per-obs coefficients)
+};
+
+struct jp_posterior {
+  jp_ctx* ctx = nullptr;
+  const jp_grid* grid = nullptr;
+  const jp_data* data = nullptr;
+  int d = 0, p = 0;
+  long long m0 = 0, m1 = 0, M = 0;   // shard [m0, m1), M = m1 - m0
+  int path_used = 0;
+  double* d_theta = nullptr;     // SoA constrained parameters [d][M]
+  double* d_a = nullptr;         // log-density + neg_min + 0.5|z|^2
+  double* d_logdens = nullptr;   // log-density + neg_min
+  double* d_density = nullptr;   // normalised weights
+  double* d_part = nullptr;      // (JP_POST_PART_SPLITS + 1) x M doubles, see below
+  double* d_stats = nullptr;     // [0]=max, [1]=sum (device scalars for the single-GPU path)
+  double* d_dtheta = nullptr;    // TC path: U z per node, SoA [d][M] FP64 (centred offsets)
+  // per-fit constants on the device
+  double* d_mu = nullptr;        // d
+  double* d_U = nullptr;         // d x p column-major
+  int* d_tcode = nullptr;        // d
+  // stage-5 work buffers (allocated on first use, sized for K_cap marginals)
+  int K_cap = 0;
+  int K_last = 0;
+  double* d_vals = nullptr;      // uploaded values K x M (host closures)
+  const double** d_vptr = nullptr;  // K device pointers to the value columns
+  uint32_t* d_perm_a = nullptr;  // K x M
+  uint32_t* d_perm_b = nullptr;  // K x M
+  uint32_t* d_hist = nullptr;    // radix histograms
+  double* d_sv = nullptr;        // sorted values K x M
+  double* d_sw = nullptr;        // sorted weights K x M
+  double* d_cw = nullptr;        // cumulative weights K x M
+  double* d_mout = nullptr;      // K x (2 + 200) results
+};
+#define JP_POST_PART_SPLITS 32   // d_part holds [splits <= 32][M] observation partial sums + [M] (lj + prior)
+
+// ---------------------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ double jp_warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double jp_warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double jp_warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Deterministic block sum: fixed shuffle tree inside warps, fixed order across warps.
+// All threads must call; result valid in every thread.  smem: >= 33 doubles.
+__device__ __forceinline__ double jp_block_sum(double v, double* smem) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = jp_warp_sum(v);
+  __syncthreads();
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int i = 0; i < nw; ++i) s += smem[i];
+    smem[32] = s;
+  }
+  __syncthreads();
+  return smem[32];
+}
+__device__ __forceinline__ double jp_block_max(double v, double* smem) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = jp_warp_max(v);
+  __syncthreads();
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = smem[0];
+    for (int i = 1; i < nw; ++i) s = fmax(s, smem[i]);
+    smem[32] = s;
+  }
+  __syncthreads();
+  return smem[32];
+}
+__device__ __forceinline__ double jp_block_min(double v, double* smem) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = jp_warp_min(v);
+  __syncthreads();
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = smem[0];
+    for (int i = 1; i < nw; ++i) s = fmin(s, smem[i]);
+    smem[32] = s;
+  }
+  __syncthreads();
+  return smem[32];
+}
+// order-preserving map double -> uint64 (ascending), -0.0 < +0.0; NaNs sort last/first by sign
+__device__ __forceinline__ unsigned long long jp_sortable(double x) {
+  unsigned long long u = (unsigned long long)__double_as_longlong(x);
+  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+#endif
+
+// ---------------------------------------------------------------------------- internal entry points
+int jp_grid_build(jp_ctx* ctx, int rule, int d, int level, jp_grid* g);
+int jp_fit_fp64_launch(jp_posterior* post, const jp_fit_args* args);   // stages 2-3, generic plugin kernel
+int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args);     // stages 2-3, GLM tensor-core path
+bool jp_fit_tc_supported(const jp_posterior* post, const jp_fit_args* args);
+void jp_tc_data_free(jp_data* data);
+const double* jp_rule_nodes_dev(int rule);   // device copy of the master z-node table
+
+struct JpRule {
+  int levels, nmax;
+  const int* npts;
+  const double* nodes;
+  const double* weights;
+};
+JpRule jp_get_rule(int rule);

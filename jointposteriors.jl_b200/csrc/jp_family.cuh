@@ -1,0 +1,145 @@
+// jp_family.cuh -- likelihood families as CUDA device-function plugins.
+//
+// In the reference the likelihood is the user's Julia method `log_density(Theta, data)`, called once
+// per grid node from the closures at reference src/joint_posterior.jl:147-154.  Julia closures cannot
+// run on the device, so a family here is a struct of static __device__ functions that the generic
+// node x observation kernel (jp_fit.cu) is instantiated with, and a registry entry mapping the
+// family id of the C ABI to the instantiated launcher.  Adding a family = one struct + one
+// JP_REGISTER_FAMILY line; nothing else in the library changes.
+//
+// Plugin concept (all static):
+//   kId                      family id of include/jpcuda.h
+//   kName
+//   __host__ bool shape_ok(d, ncols, N)                 argument validation at fit time
+//   __device__ double prior(th, d, N, hyper)            terms that do not loop over observations
+//   __device__ double obs(th, d, rec, n, hyper)         log-density term of observation n;
+//                                                       rec -> its ncols doubles in SHARED memory
+// `th` is the constrained parameter vector of the calling thread's node, a register array of
+// compile-time size DPAD >= d with zeros beyond d.
+#pragma once
+#include "jp_common.cuh"
+
+#define JP_LOG_2PI 1.8378770664093454835606594728112
+
+__device__ __forceinline__ double jp_softplus(double x) { return fmax(x, 0.0) + log1p(exp(-fabs(x))); }
+__device__ __forceinline__ double jp_lpdf_normal(double x, double mu, double sd) {
+  double z = (x - mu) / sd;
+  return -0.5 * z * z - log(sd) - 0.5 * JP_LOG_2PI;
+}
+
+// README Example 1 (reference README.md:62-72, test/runtests.jl:19-26):
+// theta = (tau, theta_minus, theta_plus); record (X, freq, NmX).
+struct FamBinomialMixture {
+  static constexpr int kId = JP_FAM_BINOMIAL_MIXTURE;
+  static constexpr const char* kName = "binomial_mixture";
+  static bool shape_ok(int d, int ncols, long long) { return d == 3 && ncols == 3; }
+  template <int DPAD>
+  __device__ static double prior(const double (&p)[DPAD], int, long long, const double* h) {
+    return h[0] * log(p[1]) + h[1] * log(1 - p[1]) + h[2] * log(p[2]) + h[3] * log(1 - p[2]) + h[4] * log(p[0]) +
+           h[5] * log(1 - p[0]);
+  }
+  template <int DPAD>
+  __device__ static double obs(const double (&p)[DPAD], int, const double* r, long long, const double*) {
+    return r[1] * log(p[0] * pow(1 - p[1], r[0]) * pow(p[1], r[2]) + (1 - p[0]) * pow(p[2], r[0]) * pow(1 - p[2], r[2]));
+  }
+};
+
+// shared linear predictor: eta = sum_k x_k th_k over the padded width (th is zero beyond d)
+template <int DPAD>
+__device__ __forceinline__ double jp_eta(const double (&th)[DPAD], int d, const double* r) {
+  double eta = 0;
+  if (DPAD <= 32) {
+#pragma unroll
+    for (int k = 0; k < DPAD; ++k)
+      if (k < d) eta += r[k] * th[k];
+  } else {
+    for (int k = 0; k < d; ++k) eta += r[k] * th[k];
+  }
+  return eta;
+}
+
+// logistic regression, beta_k ~ N(0, hyper[0]^2); record (x_0..x_{d-1}, y)
+struct FamLogistic {
+  static constexpr int kId = JP_FAM_LOGISTIC;
+  static constexpr const char* kName = "logistic";
+  static bool shape_ok(int d, int ncols, long long) { return ncols == d + 1; }
+  template <int DPAD>
+  __device__ static double prior(const double (&b)[DPAD], int d, long long, const double* h) {
+    double lp = 0;
+    for (int k = 0; k < d; ++k) lp += jp_lpdf_normal(b[k], 0.0, h[0]);
+    return lp;
+  }
+  template <int DPAD>
+  __device__ static double obs(const double (&b)[DPAD], int d, const double* r, long long, const double*) {
+    double eta = jp_eta(b, d, r);
+    return r[d] * eta - jp_softplus(eta);
+  }
+};
+
+// Poisson regression (log link), beta_k ~ N(0, hyper[0]^2); the theta-independent -lgamma(y+1) is dropped
+struct FamPoisson {
+  static constexpr int kId = JP_FAM_POISSON;
+  static constexpr const char* kName = "poisson";
+  static bool shape_ok(int d, int ncols, long long) { return ncols == d + 1; }
+  template <int DPAD>
+  __device__ static double prior(const double (&b)[DPAD], int d, long long, const double* h) {
+    double lp = 0;
+    for (int k = 0; k < d; ++k) lp += jp_lpdf_normal(b[k], 0.0, h[0]);
+    return lp;
+  }
+  template <int DPAD>
+  __device__ static double obs(const double (&b)[DPAD], int d, const double* r, long long, const double*) {
+    double eta = jp_eta(b, d, r);
+    return r[d] * eta - exp(eta);
+  }
+};
+
+// hierarchical normal ("eight schools"): theta = (mu, tau, theta_1..theta_J); record (y_j, s_j);
+// y_j ~ N(theta_j, s_j^2), theta_j ~ N(mu, tau^2), flat mu, tau ~ half-Cauchy(0, hyper[0])
+struct FamHierNormal {
+  static constexpr int kId = JP_FAM_HIER_NORMAL;
+  static constexpr const char* kName = "hier_normal";
+  static bool shape_ok(int d, int ncols, long long N) { return ncols == 2 && d == (int)N + 2; }
+  template <int DPAD>
+  __device__ static double prior(const double (&t)[DPAD], int, long long, const double* h) {
+    double r = t[1] / h[0];
+    return log(2.0 / (M_PI * h[0])) - log1p(r * r);
+  }
+  template <int DPAD>
+  __device__ static double obs(const double (&t)[DPAD], int, const double* r, long long n, const double*) {
+    double tj = t[2 + n];
+    return jp_lpdf_normal(r[0], tj, r[1]) + jp_lpdf_normal(tj, t[0], t[1]);
+  }
+};
+
+// README Example 2 "HiWorld" (reference README.md:245-258): theta = (beta_0..beta_{p-1}, sigma);
+// record (x_0..x_{p-1}, y); hyper = (sd of beta prior, sd of sigma prior)
+struct FamNormalLinear {
+  static constexpr int kId = JP_FAM_NORMAL_LINEAR;
+  static constexpr const char* kName = "normal_linear";
+  static bool shape_ok(int d, int ncols, long long) { return ncols == d; }
+  template <int DPAD>
+  __device__ static double prior(const double (&t)[DPAD], int d, long long, const double* h) {
+    double lp = jp_lpdf_normal(t[d - 1], 0.0, h[1]);
+    for (int k = 0; k < d - 1; ++k) lp += jp_lpdf_normal(t[k], 0.0, h[0]);
+    return lp;
+  }
+  template <int DPAD>
+  __device__ static double obs(const double (&t)[DPAD], int d, const double* r, long long, const double*) {
+    double eta = jp_eta(t, d - 1, r);
+    return jp_lpdf_normal(r[d - 1], eta, t[d - 1]);
+  }
+};
+
+// ------------------------------------------------------------------------------------ registry
+struct JpFitLaunchParams;   // defined in jp_fit.cu
+typedef int (*jp_family_launcher)(jp_posterior* post, const JpFitLaunchParams& lp);
+typedef bool (*jp_family_shape_ok)(int d, int ncols, long long N);
+struct JpFamilyEntry {
+  int id;
+  const char* name;
+  jp_family_launcher launch;
+  jp_family_shape_ok shape_ok;
+};
+void jp_register_family(const JpFamilyEntry& e);
+const JpFamilyEntry* jp_find_family(int id);

@@ -1,0 +1,403 @@
+// jp_fit.cu -- STAGES 2-4 (FP64 path): node -> theta map, node x observation log-density through
+// the family plugins, max / log-sum-exp weight normalisation.
+//
+// Replaces eval_grid! (reference call sites src/joint_posterior.jl:180,186) and the per-node closures
+// log_density! / log_density_cache (reference src/joint_posterior.jl:147-154):
+//     x_m = mu_hat + U z_m                       (z_m from the integer node keys of stage 1)
+//     theta_m = transform(x_m), lj_m = log|J|    (ConstrainedParameters' construct/update!)
+//     ld_m = log_density(theta_m, data) + lj_m + neg_min
+//     a_m  = ld_m + |z_m|^2/2 ;  density_m = w_m exp(a_m - max a) / sum_m' w_m' exp(a_m' - max a)
+//
+// Kernel layout of the log-density kernel: one thread per grid node (theta lives in registers),
+// a block of JP_FIT_THREADS nodes streams the observation records through shared memory in
+// coalesced contiguous tiles (the row-major record array is read exactly once per block), and
+// gridDim.y splits the observations when there are too few node blocks to fill 148 SMs.  The
+// per-node sums are sequential in n inside a split and the splits are combined in order, so the
+// result is deterministic.
+#include <algorithm>
+#include <cmath>
+#include "jp_common.cuh"
+#include "jp_family.cuh"
+
+#define JP_FIT_THREADS 128
+#define JP_FIT_TILE_DOUBLES 4096     // shared-memory tile of observation records (32 KB)
+
+struct JpFitLaunchParams {
+  int d, p, ncols, rule;
+  long long N, M, m0;          // M = local node count, m0 = first global node of the shard
+  long long M_grid;            // global node count (stride of the SoA key array)
+  int splits;                  // gridDim.y
+  long long obs_per_split;
+  double neg_min;
+  const uint8_t* idx;          // grid keys SoA [p][M_grid]
+  const double* mu;            // d
+  const double* U;             // d x p column-major
+  const int* tcode;            // d
+  const double* obs;           // N x ncols row-major
+  double hyper[JP_MAX_HYPER];
+  double* theta;               // [d][M]
+  double* lj_prior;            // [M]: log-Jacobian + prior(theta)
+  double* part;                // [splits][M] observation sums
+  const double* xpts;          // non-null: explicit unconstrained points [M][d] instead of grid keys
+};
+
+__constant__ double c_fit_nodes[2][64];
+static bool g_fit_nodes_uploaded = false;
+
+__device__ __forceinline__ double jp_transform(int code, double x, double& lj) {
+  if (code == JP_T_POSITIVE) {
+    lj += x;
+    return exp(x);
+  }
+  if (code == JP_T_PROBABILITY) {
+    double ex = exp(x);
+    lj -= log(2.0 + ex + 1.0 / ex);     // sign convention of nlogit_lj, reference src/interp.jl:321-324
+    return 1.0 / (1.0 + exp(-x));
+  }
+  return x;
+}
+
+template <class F, int DPAD>
+__global__ void __launch_bounds__(JP_FIT_THREADS)
+jp_fit_nodes_kernel(const JpFitLaunchParams P) {
+  extern __shared__ double tile[];
+  double* s_U = tile + JP_FIT_TILE_DOUBLES;          // d x p
+  double* s_mu = s_U + P.d * P.p;                     // d
+  int* s_code = reinterpret_cast<int*>(s_mu + P.d);   // d
+  for (int i = threadIdx.x; i < P.d; i += JP_FIT_THREADS) {
+    s_mu[i] = P.mu ? P.mu[i] : 0.0;
+    s_code[i] = P.tcode[i];
+  }
+  if (P.U)
+    for (int i = threadIdx.x; i < P.d * P.p; i += JP_FIT_THREADS) s_U[i] = P.U[i];
+  __syncthreads();
+
+  const long long m = (long long)blockIdx.x * JP_FIT_THREADS + threadIdx.x;   // local node
+  const bool live = m < P.M;
+  double th[DPAD];
+#pragma unroll
+  for (int k = 0; k < DPAD; ++k) th[k] = 0.0;
+  double ljp = 0.0;
+  if (live) {
+    // ---- stage 2: affine map from the integer key, then the constraint transforms
+    if (P.xpts) {
+#pragma unroll
+      for (int k = 0; k < DPAD; ++k)
+        if (k < P.d) th[k] = P.xpts[(size_t)m * P.d + k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < DPAD; ++k)
+        if (k < P.d) th[k] = s_mu[k];
+    }
+    for (int j = 0; j < (P.xpts ? 0 : P.p); ++j) {
+      int key = P.idx[(size_t)j * P.M_grid + (P.m0 + m)];
+      if (key != 0) {   // key 0 is the centre node z = 0: most coordinates of a sparse-grid node
+        double z = c_fit_nodes[P.rule][key];
+#pragma unroll
+        for (int k = 0; k < DPAD; ++k)
+          if (k < P.d) th[k] += s_U[j * P.d + k] * z;
+      }
+    }
+    double lj = 0.0;
+#pragma unroll
+    for (int k = 0; k < DPAD; ++k)
+      if (k < P.d) th[k] = jp_transform(s_code[k], th[k], lj);
+    if (blockIdx.y == 0) {
+#pragma unroll
+      for (int k = 0; k < DPAD; ++k)
+        if (k < P.d) P.theta[(size_t)k * P.M + m] = th[k];
+      ljp = lj + F::template prior<DPAD>(th, P.d, P.N, P.hyper);
+      P.lj_prior[m] = ljp;
+    }
+  }
+  // ---- stage 3: stream this split's observation records through shared memory
+  const long long n_begin = (long long)blockIdx.y * P.obs_per_split;
+  const long long n_end = min(P.N, n_begin + P.obs_per_split);
+  const int tile_obs = JP_FIT_TILE_DOUBLES / P.ncols;
+  double acc = 0.0;
+  for (long long base = n_begin; base < n_end; base += tile_obs) {
+    const int cnt = (int)min((long long)tile_obs, n_end - base);
+    const double* src = P.obs + (size_t)base * P.ncols;
+    const int nd = cnt * P.ncols;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nd; i += JP_FIT_THREADS) tile[i] = __ldg(src + i);
+    __syncthreads();
+    if (live) {
+      for (int n = 0; n < cnt; ++n) acc += F::template obs<DPAD>(th, P.d, tile + n * P.ncols, base + n, P.hyper);
+    }
+  }
+  if (live) P.part[(size_t)blockIdx.y * P.M + m] = acc;
+}
+
+// ld = lj + prior + sum_s part[s] + neg_min ; a = ld + |z|^2/2
+__global__ void jp_fit_finish_kernel(long long M, long long m0, int splits, const double* __restrict__ part,
+                                     const double* __restrict__ lj_prior, const double* __restrict__ hzz,
+                                     double neg_min, double* __restrict__ logdens, double* __restrict__ a) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  double s = 0;
+  for (int k = 0; k < splits; ++k) s += part[(size_t)k * M + m];
+  double ld = (s + lj_prior[m]) + neg_min;
+  logdens[m] = ld;
+  a[m] = ld + hzz[m0 + m];
+}
+
+// single-block deterministic reductions over the (L2-resident) node arrays
+__global__ void __launch_bounds__(1024) jp_reduce_max_kernel(const double* __restrict__ a, long long M,
+                                                             double* __restrict__ out) {
+  __shared__ double sm[33];
+  double v = -INFINITY;
+  for (long long i = threadIdx.x; i < M; i += 1024) v = fmax(v, a[i]);
+  v = jp_block_max(v, sm);
+  if (threadIdx.x == 0) out[0] = v;
+}
+__global__ void jp_expw_kernel(long long M, long long m0, const double* __restrict__ a, const double* __restrict__ w,
+                               const double* __restrict__ gmax, double* __restrict__ e) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < M) e[m] = w[m0 + m] * exp(a[m] - gmax[0]);
+}
+__global__ void __launch_bounds__(1024) jp_reduce_sum_kernel(const double* __restrict__ e, long long M,
+                                                             double* __restrict__ out) {
+  __shared__ double sm[33];
+  // fixed assignment: thread t owns the contiguous chunk t, summed in order; chunks combined by the
+  // fixed shuffle tree -> bitwise reproducible
+  long long chunk = (M + 1023) / 1024;
+  long long b = threadIdx.x * chunk, en = min(M, b + chunk);
+  double s = 0;
+  for (long long i = b; i < en; ++i) s += e[i];
+  s = jp_block_sum(s, sm);
+  if (threadIdx.x == 0) out[0] = s;
+}
+__global__ void jp_scale_kernel(long long M, double* __restrict__ e, const double* __restrict__ gsum) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < M) e[m] = e[m] / gsum[0];
+}
+
+// ------------------------------------------------------------------------------------ registry
+static JpFamilyEntry g_families[16];
+static int g_nfamilies = 0;
+void jp_register_family(const JpFamilyEntry& e) {
+  if (g_nfamilies < 16) g_families[g_nfamilies++] = e;
+}
+const JpFamilyEntry* jp_find_family(int id) {
+  for (int i = 0; i < g_nfamilies; ++i)
+    if (g_families[i].id == id) return &g_families[i];
+  return nullptr;
+}
+
+template <class F, int DPAD>
+static int launch_nodes(jp_posterior* post, const JpFitLaunchParams& lp) {
+  dim3 grid((unsigned)((lp.M + JP_FIT_THREADS - 1) / JP_FIT_THREADS), lp.splits);
+  size_t smem = (size_t)(JP_FIT_TILE_DOUBLES + lp.d * lp.p + lp.d) * sizeof(double) + (size_t)lp.d * sizeof(int);
+  if (smem > 48 * 1024)
+    JP_CUDA(cudaFuncSetAttribute(jp_fit_nodes_kernel<F, DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  jp_fit_nodes_kernel<F, DPAD><<<grid, JP_FIT_THREADS, smem, post->ctx->stream>>>(lp);
+  JP_CHECK_LAUNCH(post->ctx);
+  return JP_OK;
+}
+template <class F>
+static int launch_family(jp_posterior* post, const JpFitLaunchParams& lp) {
+  int d = lp.d;
+  if (d <= 4) return launch_nodes<F, 4>(post, lp);
+  if (d <= 8) return launch_nodes<F, 8>(post, lp);
+  if (d <= 12) return launch_nodes<F, 12>(post, lp);
+  if (d <= 16) return launch_nodes<F, 16>(post, lp);
+  if (d <= 20) return launch_nodes<F, 20>(post, lp);
+  if (d <= 24) return launch_nodes<F, 24>(post, lp);
+  if (d <= 32) return launch_nodes<F, 32>(post, lp);
+  return launch_nodes<F, JP_MAX_D>(post, lp);
+}
+#define JP_REGISTER_FAMILY(F)                                                                  \
+  static struct Reg##F {                                                                        \
+    Reg##F() { jp_register_family(JpFamilyEntry{F::kId, F::kName, &launch_family<F>, &F::shape_ok}); } \
+  } g_reg_##F;
+
+JP_REGISTER_FAMILY(FamBinomialMixture)
+JP_REGISTER_FAMILY(FamLogistic)
+JP_REGISTER_FAMILY(FamPoisson)
+JP_REGISTER_FAMILY(FamHierNormal)
+JP_REGISTER_FAMILY(FamNormalLinear)
+
+// ------------------------------------------------------------------------------------ host side
+static int upload_fit_consts(jp_posterior* post, const jp_fit_args* args) {
+  jp_ctx* ctx = post->ctx;
+  if (!g_fit_nodes_uploaded) {
+    for (int r = 0; r < 2; ++r) {
+      JpRule R = jp_get_rule(r);
+      double nodes[64] = {0};
+      for (int j = 0; j < R.nmax; ++j) nodes[j] = R.nodes[j];
+      JP_CUDA(cudaMemcpyToSymbol(c_fit_nodes, nodes, sizeof nodes, sizeof(double) * 64 * r));
+    }
+    g_fit_nodes_uploaded = true;
+  }
+  // stage through pinned memory so the copies are truly asynchronous
+  double* hp = ctx->h_pinned;
+  int d = args->d, p = args->p;
+  JP_CUDA(cudaStreamSynchronize(ctx->stream));   // pinned staging area is reused across calls
+  for (int i = 0; i < d; ++i) hp[i] = args->h_mu_hat[i];
+  for (int i = 0; i < d * p; ++i) hp[d + i] = args->h_U[i];
+  int* hc = reinterpret_cast<int*>(hp + d + d * p);
+  for (int i = 0; i < d; ++i) hc[i] = args->h_transform[i];
+  JP_CUDA(cudaMemcpyAsync(post->d_mu, hp, sizeof(double) * d, cudaMemcpyHostToDevice, ctx->stream));
+  JP_CUDA(cudaMemcpyAsync(post->d_U, hp + d, sizeof(double) * d * p, cudaMemcpyHostToDevice, ctx->stream));
+  JP_CUDA(cudaMemcpyAsync(post->d_tcode, hc, sizeof(int) * d, cudaMemcpyHostToDevice, ctx->stream));
+  return JP_OK;
+}
+
+int jp_fit_check_args(const jp_posterior* post, const jp_fit_args* args) {
+  JP_REQUIRE(post && args, "jp_fit: null argument");
+  JP_REQUIRE(args->d == post->d && args->p == post->p, "jp_fit: (d,p)=(%d,%d) differs from the posterior's (%d,%d)",
+             args->d, args->p, post->d, post->p);
+  JP_REQUIRE(args->h_transform && args->h_mu_hat && args->h_U, "jp_fit: null host array");
+  for (int k = 0; k < args->d; ++k)
+    JP_REQUIRE(args->h_transform[k] >= 0 && args->h_transform[k] <= 2, "jp_fit: unknown transform code %d",
+               args->h_transform[k]);
+  return JP_OK;
+}
+
+int jp_fit_fp64_launch(jp_posterior* post, const jp_fit_args* args) {
+  jp_ctx* ctx = post->ctx;
+  const jp_data* data = post->data;
+  const JpFamilyEntry* fam = jp_find_family(data->family);
+  JP_REQUIRE(fam != nullptr, "jp_fit: family %d is not registered", data->family);
+  JP_REQUIRE(fam->shape_ok(args->d, data->ncols, data->N), "jp_fit: family %s does not accept d=%d ncols=%d N=%lld",
+             fam->name, args->d, data->ncols, data->N);
+  JP_REQUIRE(data->ncols <= JP_FIT_TILE_DOUBLES / 2, "jp_fit: %d columns per observation is too many", data->ncols);
+  JP_TRY(upload_fit_consts(post, args));
+  JpFitLaunchParams lp;
+  lp.d = args->d; lp.p = args->p; lp.ncols = data->ncols; lp.rule = post->grid->rule;
+  lp.N = data->N; lp.M = post->M; lp.m0 = post->m0; lp.M_grid = post->grid->M;
+  lp.neg_min = args->neg_min;
+  lp.idx = post->grid->d_idx; lp.mu = post->d_mu; lp.U = post->d_U; lp.tcode = post->d_tcode;
+  lp.obs = data->d_obs;
+  for (int i = 0; i < JP_MAX_HYPER; ++i) lp.hyper[i] = data->hyper[i];
+  lp.theta = post->d_theta;
+  // observation splits: aim for >= 4 blocks per SM, bounded by the partial buffer and by tiles
+  long long node_blocks = (post->M + JP_FIT_THREADS - 1) / JP_FIT_THREADS;
+  int tile_obs = JP_FIT_TILE_DOUBLES / data->ncols;
+  long long max_by_tiles = std::max(1LL, data->N / (4LL * tile_obs));
+  long long want = (4LL * ctx->sm_count + node_blocks - 1) / node_blocks;
+  long long cap = std::max(1LL, (long long)JP_POST_PART_SPLITS);
+  int splits = (int)std::max(1LL, std::min(std::min(want, max_by_tiles), cap));
+  lp.splits = splits;
+  lp.obs_per_split = (data->N + splits - 1) / splits;
+  // round the split length to whole tiles so tiles never straddle a split boundary unevenly
+  lp.obs_per_split = ((lp.obs_per_split + tile_obs - 1) / tile_obs) * tile_obs;
+  lp.xpts = nullptr;
+  lp.part = post->d_part;
+  lp.lj_prior = post->d_part + (size_t)JP_POST_PART_SPLITS * post->M;
+  JP_TRY(fam->launch(post, lp));
+  unsigned gb = (unsigned)((post->M + 255) / 256);
+  jp_fit_finish_kernel<<<gb, 256, 0, ctx->stream>>>(post->M, post->m0, splits, lp.part, lp.lj_prior,
+                                                     post->grid->d_hzz, args->neg_min, post->d_logdens, post->d_a);
+  JP_CHECK_LAUNCH(ctx);
+  post->path_used = JP_PATH_FP64;
+  return JP_OK;
+}
+
+__global__ void jp_points_finish_kernel(long long K, int splits, const double* __restrict__ part,
+                                        const double* __restrict__ lj_prior, double* __restrict__ out) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= K) return;
+  double s = 0;
+  for (int k = 0; k < splits; ++k) s += part[(size_t)k * K + m];
+  out[m] = s + lj_prior[m];
+}
+
+extern "C" {
+
+int jp_log_density_points(jp_ctx* ctx, const jp_data* data, int d, const int* h_transform, long long K,
+                          const double* h_x, double* h_ld) {
+  JP_REQUIRE(ctx && data && h_transform && h_x && h_ld, "jp_log_density_points: null argument");
+  JP_REQUIRE(d >= 1 && d <= JP_MAX_D && K >= 1, "jp_log_density_points: bad shape d=%d K=%lld", d, K);
+  const JpFamilyEntry* fam = jp_find_family(data->family);
+  JP_REQUIRE(fam != nullptr, "jp_log_density_points: family %d is not registered", data->family);
+  JP_REQUIRE(fam->shape_ok(d, data->ncols, data->N), "jp_log_density_points: family %s does not accept d=%d ncols=%d N=%lld",
+             fam->name, d, data->ncols, data->N);
+  for (int k = 0; k < d; ++k)
+    JP_REQUIRE(h_transform[k] >= 0 && h_transform[k] <= 2, "jp_log_density_points: unknown transform code %d", h_transform[k]);
+  JP_CUDA(cudaSetDevice(ctx->device));
+  const int splits = 1;
+  double *d_x = nullptr, *d_theta = nullptr, *d_part = nullptr, *d_out = nullptr;
+  int* d_code = nullptr;
+  jp_posterior tmp;   // only ctx is used by the launcher
+  tmp.ctx = ctx;
+  int st = JP_OK;
+  cudaError_t e = cudaMalloc(&d_x, (size_t)K * d * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&d_theta, (size_t)K * d * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&d_part, (size_t)K * (splits + 1) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)K * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&d_code, (size_t)d * 4);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_x, h_x, (size_t)K * d * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_code, h_transform, (size_t)d * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    JpFitLaunchParams lp;
+    lp.d = d; lp.p = 0; lp.ncols = data->ncols; lp.rule = 0;
+    lp.N = data->N; lp.M = K; lp.m0 = 0; lp.M_grid = K; lp.neg_min = 0.0;
+    lp.idx = nullptr; lp.mu = nullptr; lp.U = nullptr; lp.tcode = d_code; lp.obs = data->d_obs;
+    for (int i = 0; i < JP_MAX_HYPER; ++i) lp.hyper[i] = data->hyper[i];
+    lp.theta = d_theta; lp.splits = splits; lp.obs_per_split = data->N;
+    lp.part = d_part; lp.lj_prior = d_part + (size_t)splits * K; lp.xpts = d_x;
+    st = fam->launch(&tmp, lp);
+    if (st == JP_OK) {
+      jp_points_finish_kernel<<<(unsigned)((K + 255) / 256), 256, 0, ctx->stream>>>(K, splits, lp.part, lp.lj_prior, d_out);
+      ctx->launches++;
+      e = cudaGetLastError();
+    }
+    if (st == JP_OK && e == cudaSuccess) e = cudaMemcpyAsync(h_ld, d_out, (size_t)K * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (st == JP_OK && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(d_x); cudaFree(d_theta); cudaFree(d_part); cudaFree(d_out); cudaFree(d_code);
+  if (st != JP_OK) return st;
+  if (e != cudaSuccess) {
+    jp_set_error("jp_log_density_points: %s", cudaGetErrorString(e));
+    return JP_ERR_CUDA;
+  }
+  return JP_OK;
+}
+
+int jp_fit_local(jp_posterior* post, const jp_fit_args* args, double* d_local_max) {
+  JP_TRY(jp_fit_check_args(post, args));
+  JP_REQUIRE(d_local_max, "jp_fit_local: null output");
+  int path = args->path;
+  if (path == JP_PATH_AUTO) path = jp_fit_tc_supported(post, args) ? JP_PATH_TC : JP_PATH_FP64;
+  if (path == JP_PATH_TC) {
+    JP_REQUIRE(jp_fit_tc_supported(post, args), "jp_fit: the tensor-core path does not support this model (%s)",
+               jp_last_error());
+    JP_TRY(jp_fit_tc_launch(post, args));
+  } else {
+    JP_TRY(jp_fit_fp64_launch(post, args));
+  }
+  jp_reduce_max_kernel<<<1, 1024, 0, post->ctx->stream>>>(post->d_a, post->M, d_local_max);
+  JP_CHECK_LAUNCH(post->ctx);
+  return JP_OK;
+}
+
+int jp_fit_local_sum(jp_posterior* post, const double* d_global_max, double* d_local_sum) {
+  JP_REQUIRE(post && d_global_max && d_local_sum, "jp_fit_local_sum: null argument");
+  unsigned gb = (unsigned)((post->M + 255) / 256);
+  jp_expw_kernel<<<gb, 256, 0, post->ctx->stream>>>(post->M, post->m0, post->d_a, post->grid->d_w, d_global_max,
+                                                     post->d_density);
+  JP_CHECK_LAUNCH(post->ctx);
+  jp_reduce_sum_kernel<<<1, 1024, 0, post->ctx->stream>>>(post->d_density, post->M, d_local_sum);
+  JP_CHECK_LAUNCH(post->ctx);
+  return JP_OK;
+}
+
+int jp_fit_normalise(jp_posterior* post, const double* d_global_sum) {
+  JP_REQUIRE(post && d_global_sum, "jp_fit_normalise: null argument");
+  unsigned gb = (unsigned)((post->M + 255) / 256);
+  jp_scale_kernel<<<gb, 256, 0, post->ctx->stream>>>(post->M, post->d_density, d_global_sum);
+  JP_CHECK_LAUNCH(post->ctx);
+  return JP_OK;
+}
+
+int jp_fit(jp_posterior* post, const jp_fit_args* args) {
+  JP_REQUIRE(post, "jp_fit: null posterior");
+  JP_TRY(jp_fit_local(post, args, post->d_stats));
+  JP_TRY(jp_fit_local_sum(post, post->d_stats, post->d_stats + 1));
+  JP_TRY(jp_fit_normalise(post, post->d_stats + 1));
+  return JP_OK;
+}
+
+}  // extern "C"

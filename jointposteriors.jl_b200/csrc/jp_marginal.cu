@@ -1,0 +1,325 @@
+// jp_marginal.cu -- STAGE 5: marginal(jp, f): weighted mean / sigma and the 100-knot Grid CDF.
+//
+// Replaces weights_values + marginal + Grid (reference src/marginal_posterior.jl:98-123,
+// src/interp.jl:21-31,448-457), batched over K functions f:
+//   mu = dot(w, v); sigma = sqrt(dot(w, v.^2) - mu^2)            marginal_posterior.jl:120-121
+//   stable sort of v carrying w (simultaneous_sort!)              interp.jl:21-26
+//   c = cumsum(w_sorted); itp = linear interpolant of (v_sorted, c)   interp.jl:28-31
+//   value_nodes = linspace(v_min, v_max, 100); weight_nodes = (0, itp[value_nodes[2:99]], 1)   interp.jl:448-457
+// Single-GPU path: 8-bit LSD radix sort of a permutation (8 passes over the order-preserving
+// 64-bit image of the doubles), gather + inclusive scan, 98 binary searches.  Multi-GPU path: a
+// sort-free splitter pass producing per-knot (mass below, predecessor, successor) candidates that
+// the host combines across ranks; both reproduce the same interpolant, including its tie rule
+// (left knot = LAST duplicate <= x, right knot = first element of the next tie group).
+#include <algorithm>
+#include <cmath>
+#include "jp_common.cuh"
+#include "jp_sort.cuh"
+
+#define JP_MOUT_STRIDE (2 + 2 * JP_GRID_KNOTS + 2)   // mu, sigma, value_nodes, weight_nodes, min, max
+
+__device__ __forceinline__ double jp_knot_value(double vmin, double vmax, int i) {
+  // i-th of 100 equispaced knots; end knots exact (linspace semantics, interp.jl:450)
+  if (i <= 0) return vmin;
+  if (i >= JP_GRID_KNOTS - 1) return vmax;
+  return fma((double)i / (double)(JP_GRID_KNOTS - 1), vmax - vmin, vmin);
+}
+
+// one block per marginal: (sum w v, sum w v^2, min v, max v); contiguous chunk per thread, fixed tree
+__global__ void __launch_bounds__(1024)
+jp_moments_kernel(const double* const* __restrict__ vptr, const double* __restrict__ w, long long M,
+                  double* __restrict__ out, int out_stride) {
+  __shared__ double sm[33];
+  const double* v = vptr[blockIdx.x];
+  long long chunk = (M + 1023) / 1024;
+  long long b = threadIdx.x * chunk, e = min(M, b + chunk);
+  double s1 = 0, s2 = 0, mn = INFINITY, mx = -INFINITY;
+  for (long long i = b; i < e; ++i) {
+    double x = v[i], wi = w[i];
+    s1 += wi * x;
+    s2 += wi * (x * x);
+    mn = fmin(mn, x);
+    mx = fmax(mx, x);
+  }
+  s1 = jp_block_sum(s1, sm);
+  s2 = jp_block_sum(s2, sm);
+  mn = jp_block_min(mn, sm);
+  mx = jp_block_max(mx, sm);
+  if (threadIdx.x == 0) {
+    double* o = out + (size_t)blockIdx.x * out_stride;
+    o[0] = s1; o[1] = s2; o[2] = mn; o[3] = mx;
+  }
+}
+
+struct ValueDigit {
+  const double* const* vptr;
+  int shift;
+  __device__ __forceinline__ unsigned operator()(int batch, uint32_t src) const {
+    return (unsigned)((jp_sortable(vptr[batch][src]) >> shift) & 0xFFull);
+  }
+};
+
+// one block per marginal: gather by the sorted permutation and inclusive-scan the weights
+__global__ void __launch_bounds__(1024)
+jp_gather_scan_kernel(const double* const* __restrict__ vptr, const double* __restrict__ w,
+                      const uint32_t* __restrict__ perm, long long M, double* __restrict__ sv,
+                      double* __restrict__ sw, double* __restrict__ cw) {
+  __shared__ double wsum[32];
+  __shared__ double carry_s;
+  const int k = blockIdx.x;
+  const double* v = vptr[k];
+  const uint32_t* pm = perm + (size_t)k * M;
+  double* osv = sv + (size_t)k * M;
+  double* osw = sw + (size_t)k * M;
+  double* ocw = cw + (size_t)k * M;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0.0;
+  __syncthreads();
+  for (long long base = 0; base < M; base += 1024) {
+    long long i = base + threadIdx.x;
+    double x = 0, wi = 0;
+    if (i < M) {
+      uint32_t src = pm[i];
+      x = v[src];
+      wi = w[src];
+      osv[i] = x;
+      osw[i] = wi;
+    }
+    // inclusive warp scan
+    double s = wi;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      double t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    if (lane == 31) wsum[wid] = s;
+    __syncthreads();
+    if (wid == 0) {
+      double t = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        double u = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += u;
+      }
+      wsum[lane] = t;   // inclusive prefix of warp totals
+    }
+    __syncthreads();
+    double pre = carry_s + (wid > 0 ? wsum[wid - 1] : 0.0);
+    if (i < M) ocw[i] = pre + s;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = pre + s;
+    __syncthreads();
+  }
+}
+
+// one block per marginal: the 100 knots from the sorted arrays
+__global__ void __launch_bounds__(128)
+jp_knots_kernel(const double* __restrict__ sv, const double* __restrict__ cw, long long M,
+                const double* __restrict__ mom, int mom_stride, double* __restrict__ mout) {
+  const int k = blockIdx.x;
+  const double* v = sv + (size_t)k * M;
+  const double* c = cw + (size_t)k * M;
+  double* o = mout + (size_t)k * JP_MOUT_STRIDE;
+  const double vmin = v[0], vmax = v[M - 1];
+  int i = threadIdx.x;
+  if (i == 0) {
+    double s1 = mom[(size_t)k * mom_stride + 0], s2 = mom[(size_t)k * mom_stride + 1];
+    o[0] = s1;
+    o[1] = sqrt(s2 - s1 * s1);      // no clamp: a negative argument gives NaN, as in the reference
+    o[2 + 2 * JP_GRID_KNOTS] = vmin;
+    o[3 + 2 * JP_GRID_KNOTS] = vmax;
+  }
+  if (i >= JP_GRID_KNOTS) return;
+  double x = jp_knot_value(vmin, vmax, i);
+  o[2 + i] = x;
+  double wn;
+  if (i == 0) {
+    wn = 0.0;                       // interp.jl:451
+  } else if (i == JP_GRID_KNOTS - 1) {
+    wn = 1.0;                       // interp.jl:452
+  } else {
+    // searchsortedlast: last (1-based) index with v <= x
+    long long lo = 0, hi = M + 1;
+    while (lo < hi - 1) {
+      long long mid = (lo + hi) >> 1;
+      if (x < v[mid - 1]) hi = mid; else lo = mid;
+    }
+    long long ix = min(max(lo, 1LL), M - 1);
+    double k0 = v[ix - 1], k1 = v[ix];
+    double fx = (x - k0) / (k1 - k0);
+    wn = c[ix - 1] * (1.0 - fx) + c[ix] * fx;
+  }
+  o[2 + JP_GRID_KNOTS + i] = wn;
+}
+
+// ---- sort-free splitter pass: block (knot i-1, marginal k) scans the shard once
+__global__ void __launch_bounds__(256)
+jp_local_knots_kernel(const double* const* __restrict__ vptr, const double* __restrict__ w, long long M,
+                      long long m0, const double* __restrict__ minmax, double* __restrict__ out) {
+  __shared__ double sm[33];
+  __shared__ unsigned long long s_succ;
+  __shared__ unsigned long long s_idx;
+  const int k = blockIdx.y, i = blockIdx.x + 1;
+  const double* v = vptr[k];
+  const double x = jp_knot_value(minmax[2 * k], minmax[2 * k + 1], i);
+  long long chunk = (M + 255) / 256;
+  long long b = threadIdx.x * chunk, e = min(M, b + chunk);
+  double S = 0, pred = -INFINITY, succ = INFINITY;
+  for (long long j = b; j < e; ++j) {
+    double vj = v[j];
+    if (vj <= x) {
+      S += w[j];
+      pred = fmax(pred, vj);
+    } else {
+      succ = fmin(succ, vj);
+    }
+  }
+  S = jp_block_sum(S, sm);
+  pred = jp_block_max(pred, sm);
+  succ = jp_block_min(succ, sm);
+  // lowest global index attaining succ
+  if (threadIdx.x == 0) s_idx = ~0ull;
+  __syncthreads();
+  unsigned long long best = ~0ull;
+  if (succ < INFINITY)
+    for (long long j = b; j < e; ++j)
+      if (v[j] == succ) { best = (unsigned long long)(m0 + j); break; }
+  if (best != ~0ull) atomicMin(&s_idx, best);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double* o = out + ((size_t)k * (JP_GRID_KNOTS - 2) + (i - 1)) * 6;
+    o[0] = S; o[1] = pred; o[2] = succ;
+    o[3] = (s_idx == ~0ull) ? INFINITY : (double)s_idx;
+    o[4] = (s_idx == ~0ull) ? 0.0 : w[(long long)s_idx - m0];
+    o[5] = 0.0;
+  }
+  (void)s_succ;
+}
+
+// ------------------------------------------------------------------------------------ host side
+static int ensure_marginal_buffers(jp_posterior* post, int K) {
+  if (K <= post->K_cap) return JP_OK;
+  cudaFree(post->d_vals); cudaFree((void*)post->d_vptr); cudaFree(post->d_perm_a); cudaFree(post->d_perm_b);
+  cudaFree(post->d_hist); cudaFree(post->d_sv); cudaFree(post->d_sw); cudaFree(post->d_cw); cudaFree(post->d_mout);
+  post->K_cap = 0;
+  size_t KM = (size_t)K * post->M;
+  int nb = jp_sort_blocks(post->M);
+  JP_CUDA(cudaMalloc(&post->d_vals, KM * 8));
+  JP_CUDA(cudaMalloc((void**)&post->d_vptr, (size_t)K * sizeof(double*)));
+  JP_CUDA(cudaMalloc(&post->d_perm_a, KM * 4));
+  JP_CUDA(cudaMalloc(&post->d_perm_b, KM * 4));
+  JP_CUDA(cudaMalloc(&post->d_hist, (size_t)K * JP_SORT_BINS * nb * 4));
+  JP_CUDA(cudaMalloc(&post->d_sv, KM * 8));
+  JP_CUDA(cudaMalloc(&post->d_sw, KM * 8));
+  JP_CUDA(cudaMalloc(&post->d_cw, KM * 8));
+  JP_CUDA(cudaMalloc(&post->d_mout, (size_t)K * JP_MOUT_STRIDE * 8));
+  post->K_cap = K;
+  return JP_OK;
+}
+
+// fills post->d_vptr with the K value-column pointers
+static int set_value_pointers(jp_posterior* post, int K, const int* h_coords, const double* d_values) {
+  jp_ctx* ctx = post->ctx;
+  JP_REQUIRE(K >= 1 && K <= 4096, "marginal: K=%d out of range", K);
+  JP_REQUIRE((h_coords != nullptr) != (d_values != nullptr), "marginal: give exactly one of coords / values");
+  JP_CUDA(cudaStreamSynchronize(ctx->stream));   // pinned staging reuse
+  const double** hp = reinterpret_cast<const double**>(ctx->h_pinned);
+  for (int k = 0; k < K; ++k) {
+    if (h_coords) {
+      JP_REQUIRE(h_coords[k] >= 0 && h_coords[k] < post->d, "marginal: coordinate %d out of range [0,%d)", h_coords[k], post->d);
+      hp[k] = post->d_theta + (size_t)h_coords[k] * post->M;
+    } else {
+      hp[k] = d_values + (size_t)k * post->M;
+    }
+  }
+  JP_CUDA(cudaMemcpyAsync((void*)post->d_vptr, hp, (size_t)K * sizeof(double*), cudaMemcpyHostToDevice, ctx->stream));
+  return JP_OK;
+}
+
+static int run_marginals(jp_posterior* post, int K, double* h_mu, double* h_sigma, double* h_vn, double* h_wn) {
+  jp_ctx* ctx = post->ctx;
+  const long long M = post->M;
+  JP_REQUIRE(M >= 2, "marginal: need at least 2 nodes");
+  JP_REQUIRE((size_t)K * JP_MOUT_STRIDE <= JP_PINNED_DOUBLES, "marginal: K=%d too large for one call", K);
+  cudaStream_t st = ctx->stream;
+  double* d_mom = ctx->d_scratch;   // K x 4
+  jp_moments_kernel<<<K, 1024, 0, st>>>(post->d_vptr, post->d_density, M, d_mom, 4);
+  JP_CHECK_LAUNCH(ctx);
+  dim3 gi((unsigned)((M + 255) / 256), K);
+  jp_iota_kernel<<<gi, 256, 0, st>>>(post->d_perm_a, M, M);
+  JP_CHECK_LAUNCH(ctx);
+  uint32_t *pin = post->d_perm_a, *pout = post->d_perm_b;
+  for (int b = 0; b < 8; ++b) {
+    ValueDigit f{post->d_vptr, 8 * b};
+    JP_TRY(jp_radix_pass(ctx, f, pin, pout, M, M, post->d_hist, K));
+    std::swap(pin, pout);
+  }
+  jp_gather_scan_kernel<<<K, 1024, 0, st>>>(post->d_vptr, post->d_density, pin, M, post->d_sv, post->d_sw, post->d_cw);
+  JP_CHECK_LAUNCH(ctx);
+  jp_knots_kernel<<<K, 128, 0, st>>>(post->d_sv, post->d_cw, M, d_mom, 4, post->d_mout);
+  JP_CHECK_LAUNCH(ctx);
+  JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, post->d_mout, (size_t)K * JP_MOUT_STRIDE * 8, cudaMemcpyDeviceToHost, st));
+  JP_CUDA(cudaStreamSynchronize(st));
+  for (int k = 0; k < K; ++k) {
+    const double* o = ctx->h_pinned + (size_t)k * JP_MOUT_STRIDE;
+    if (h_mu) h_mu[k] = o[0];
+    if (h_sigma) h_sigma[k] = o[1];
+    if (h_vn) std::copy(o + 2, o + 2 + JP_GRID_KNOTS, h_vn + (size_t)k * JP_GRID_KNOTS);
+    if (h_wn) std::copy(o + 2 + JP_GRID_KNOTS, o + 2 + 2 * JP_GRID_KNOTS, h_wn + (size_t)k * JP_GRID_KNOTS);
+  }
+  post->K_last = K;
+  return JP_OK;
+}
+
+extern "C" {
+
+int jp_marginal_coords(jp_posterior* post, int K, const int* h_coords, double* h_mu, double* h_sigma,
+                       double* h_value_nodes, double* h_weight_nodes) {
+  JP_REQUIRE(post && h_coords, "jp_marginal_coords: null argument");
+  JP_TRY(ensure_marginal_buffers(post, K));
+  JP_TRY(set_value_pointers(post, K, h_coords, nullptr));
+  return run_marginals(post, K, h_mu, h_sigma, h_value_nodes, h_weight_nodes);
+}
+
+int jp_marginal_values(jp_posterior* post, int K, const double* h_values, double* h_mu, double* h_sigma,
+                       double* h_value_nodes, double* h_weight_nodes) {
+  JP_REQUIRE(post && h_values, "jp_marginal_values: null argument");
+  JP_TRY(ensure_marginal_buffers(post, K));
+  JP_CUDA(cudaMemcpyAsync(post->d_vals, h_values, (size_t)K * post->M * 8, cudaMemcpyHostToDevice, post->ctx->stream));
+  JP_TRY(set_value_pointers(post, K, nullptr, post->d_vals));
+  return run_marginals(post, K, h_mu, h_sigma, h_value_nodes, h_weight_nodes);
+}
+
+int jp_marginal_sorted(jp_posterior* post, int k, double* h_sv, double* h_sw, double* h_cw) {
+  JP_REQUIRE(post && k >= 0 && k < post->K_last, "jp_marginal_sorted: marginal %d was not computed by the last call", k);
+  size_t off = (size_t)k * post->M, bytes = (size_t)post->M * 8;
+  cudaStream_t st = post->ctx->stream;
+  if (h_sv) JP_CUDA(cudaMemcpyAsync(h_sv, post->d_sv + off, bytes, cudaMemcpyDeviceToHost, st));
+  if (h_sw) JP_CUDA(cudaMemcpyAsync(h_sw, post->d_sw + off, bytes, cudaMemcpyDeviceToHost, st));
+  if (h_cw) JP_CUDA(cudaMemcpyAsync(h_cw, post->d_cw + off, bytes, cudaMemcpyDeviceToHost, st));
+  JP_CUDA(cudaStreamSynchronize(st));
+  return JP_OK;
+}
+
+int jp_marginal_local_moments(jp_posterior* post, int K, const int* h_coords, const double* d_values, double* d_out) {
+  JP_REQUIRE(post && d_out, "jp_marginal_local_moments: null argument");
+  JP_TRY(ensure_marginal_buffers(post, K));
+  JP_TRY(set_value_pointers(post, K, h_coords, d_values));
+  jp_moments_kernel<<<K, 1024, 0, post->ctx->stream>>>(post->d_vptr, post->d_density, post->M, d_out, 4);
+  JP_CHECK_LAUNCH(post->ctx);
+  return JP_OK;
+}
+
+int jp_marginal_local_knots(jp_posterior* post, int K, const int* h_coords, const double* d_values,
+                            const double* d_minmax, double* d_out) {
+  JP_REQUIRE(post && d_minmax && d_out, "jp_marginal_local_knots: null argument");
+  JP_TRY(ensure_marginal_buffers(post, K));
+  JP_TRY(set_value_pointers(post, K, h_coords, d_values));
+  dim3 grid(JP_GRID_KNOTS - 2, K);
+  jp_local_knots_kernel<<<grid, 256, 0, post->ctx->stream>>>(post->d_vptr, post->d_density, post->M, post->m0,
+                                                             d_minmax, d_out);
+  JP_CHECK_LAUNCH(post->ctx);
+  return JP_OK;
+}
+
+}  // extern "C"

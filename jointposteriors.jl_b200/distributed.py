@@ -1,0 +1,155 @@
+"""Node-sharded fit / marginal across the GPUs of one box (one process per GPU, torch.distributed).
+
+The reference is single-threaded; its `eval_grid!` loop over nodes (reference
+src/joint_posterior.jl:180,186) carries no cross-node state until the normalisation, and `marginal`
+(reference src/marginal_posterior.jl:117-123, src/interp.jl:448-457) only needs global sums, extrema
+and -- for the 100-knot Grid -- per-knot (mass below, predecessor, successor).  So each rank owns a
+contiguous block of merged grid nodes and the ranks exchange only:
+
+    fit        all_gather(local max a)  -> global max ;  all_gather(local sum)  -> global sum
+    marginals  all_gather(K x 4 moments/extrema)  ;  all_gather(K x 98 x 6 knot candidates)
+
+Every combine sums in rank order, so all ranks hold bit-identical results.  The combine functions
+work on torch tensors of any device: on CUDA the collectives are NCCL over NVLink, on CPU (tests)
+gloo.  The per-rank "local phase" is an object with three methods; `CudaLocal` calls the C ABI,
+tests substitute a numpy stand-in.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import GRID_KNOTS, check, lib
+
+NK = GRID_KNOTS - 2   # interior knots
+
+
+def shard_bounds(M, rank, world):
+    """Contiguous node block [begin, end) of `rank`: sizes differ by at most one."""
+    base, rem = divmod(int(M), int(world))
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def _all_gather(t, group):
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1), group=group)
+    return out
+
+
+def knot_values(vmin, vmax):
+    """The 100 equispaced value knots, computed exactly as the device does (fma(i/99, max-min, min))."""
+    import torch
+    i = torch.arange(GRID_KNOTS, dtype=torch.float64, device=vmin.device)
+    t = i / float(GRID_KNOTS - 1)
+    x = torch.addcmul(vmin[:, None], t[None, :], (vmax - vmin)[:, None])
+    x[:, 0] = vmin
+    x[:, -1] = vmax
+    return x
+
+
+def combine_knots(gathered, vmin, vmax):
+    """gathered: [world, K, 98, 6] per-rank (S, pred, succ, succ_idx, succ_w, -) -> weight_nodes [K, 100].
+
+    Reproduces itp[x] of the reference (interp.jl:28-31,453-455): left knot = LAST element <= x with
+    cumulative weight S = sum of all weights <= x; right knot = first element of the next tie group
+    (lowest global index among the smallest values > x) with cumulative weight S + its weight."""
+    import torch
+    S = gathered[..., 0]
+    tot = torch.zeros_like(S[0])
+    for r in range(S.shape[0]):          # rank order -> identical on every rank
+        tot = tot + S[r]
+    pred = gathered[..., 1].max(dim=0).values
+    succ = gathered[..., 2].min(dim=0).values
+    is_min = gathered[..., 2] == succ[None]
+    idx = torch.where(is_min, gathered[..., 3], torch.full_like(gathered[..., 3], float("inf")))
+    owner = idx.argmin(dim=0, keepdim=True)
+    succ_w = torch.gather(gathered[..., 4], 0, owner)[0]
+    x = knot_values(vmin, vmax)[:, 1:-1]
+    fx = (x - pred) / (succ - pred)
+    inner = tot * (1.0 - fx) + (tot + succ_w) * fx
+    K = inner.shape[0]
+    wn = torch.zeros((K, GRID_KNOTS), dtype=torch.float64, device=inner.device)
+    wn[:, 1:-1] = inner
+    wn[:, -1] = 1.0
+    return wn
+
+
+class CudaLocal:
+    """Local phases of one rank through the C ABI, on torch's current CUDA stream."""
+
+    def __init__(self, jp):
+        import torch
+        self.jp = jp
+        self.torch = torch
+        self.dev = torch.device("cuda", jp.ctx.device)
+        jp.ctx.use_stream(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def _buf(self, *shape):
+        return self.torch.empty(shape, dtype=self.torch.float64, device=self.dev)
+
+    def fit_local_max(self):
+        out = self._buf(1)
+        check(lib().jp_fit_local(self.jp.handle, C.byref(self.jp._args), C.c_void_p(out.data_ptr())))
+        return out
+
+    def fit_local_sum(self, gmax):
+        out = self._buf(1)
+        check(lib().jp_fit_local_sum(self.jp.handle, C.c_void_p(gmax.data_ptr()), C.c_void_p(out.data_ptr())))
+        return out
+
+    def fit_normalise(self, gsum):
+        check(lib().jp_fit_normalise(self.jp.handle, C.c_void_p(gsum.data_ptr())))
+
+    def moments(self, coords):
+        cs = np.ascontiguousarray(coords, dtype=np.int32)
+        out = self._buf(len(cs), 4)
+        check(lib().jp_marginal_local_moments(self.jp.handle, C.c_int(len(cs)), cs.ctypes.data_as(C.c_void_p), None,
+                                              C.c_void_p(out.data_ptr())))
+        return out
+
+    def knots(self, coords, minmax):
+        cs = np.ascontiguousarray(coords, dtype=np.int32)
+        out = self._buf(len(cs), NK, 6)
+        check(lib().jp_marginal_local_knots(self.jp.handle, C.c_int(len(cs)), cs.ctypes.data_as(C.c_void_p), None,
+                                            C.c_void_p(minmax.data_ptr()), C.c_void_p(out.data_ptr())))
+        return out
+
+
+def fit_sharded(local, group=None):
+    """Normalise a node-sharded fit: two tiny all_gathers (max, then sum)."""
+    lmax = local.fit_local_max()
+    gmax = _all_gather(lmax, group).max(dim=0).values.contiguous()
+    lsum = local.fit_local_sum(gmax)
+    sums = _all_gather(lsum, group)
+    gsum = sums[0].clone()
+    for r in range(1, sums.shape[0]):
+        gsum = gsum + sums[r]
+    gsum = gsum.contiguous()
+    local.fit_normalise(gsum)
+    return gmax, gsum
+
+
+def marginals_sharded(local, coords, group=None):
+    """Global (mu, sigma, value_nodes, weight_nodes) for K coordinate marginals of a node-sharded
+    posterior: two all_gathers per batch, no global sort."""
+    import torch
+    mom = local.moments(coords)                       # [K, 4] = (sum w v, sum w v^2, min, max)
+    g = _all_gather(mom, group)                       # [world, K, 4]
+    s1 = g[0, :, 0].clone()
+    s2 = g[0, :, 1].clone()
+    for r in range(1, g.shape[0]):
+        s1 = s1 + g[r, :, 0]
+        s2 = s2 + g[r, :, 1]
+    vmin = g[:, :, 2].min(dim=0).values
+    vmax = g[:, :, 3].max(dim=0).values
+    minmax = torch.stack([vmin, vmax], dim=1).contiguous()
+    cand = local.knots(coords, minmax)                # [K, 98, 6]
+    gathered = _all_gather(cand, group)               # [world, K, 98, 6]
+    wn = combine_knots(gathered, vmin, vmax)
+    vn = knot_values(vmin, vmax)
+    mu = s1
+    sigma = torch.sqrt(s2 - s1 * s1)
+    return mu, sigma, vn, wn

@@ -1,0 +1,136 @@
+"""marginal / Grid / quantile / cdf: host-side mirror of reference src/marginal_posterior.jl and the
+Grid part of src/interp.jl.
+
+    marginal(jp, f) -> marginal with fields wv, μ, σ, itp       reference src/marginal_posterior.jl:3-8,117-123
+    quantile(m, p), cdf(m, x)                                    reference src/marginal_posterior.jl:140-148,
+                                                                 src/interp.jl:458-481
+    show(m)                                                      reference src/marginal_posterior.jl:150-155
+
+f may be a coordinate index, a selector such as `lambda Θ: Θ.p[0]` (recognised and evaluated on the
+device as a zero-copy view of the Theta array), or any function of the parameter blocks (evaluated on
+the host over the downloaded Theta and uploaded as values -- the path an arbitrary Julia closure takes).
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import GRID_KNOTS, check, f64, lib, ptr
+from .params import probe_coordinate
+
+
+class Grid:
+    """100-knot piecewise-linear CDF (reference struct Grid, src/interp.jl:9-12; field order weights, values)."""
+
+    def __init__(self, weights, values):
+        self.weights = f64(weights)
+        self.values = f64(values)
+
+
+class weights_values:
+    """Sorted (weights, values) pair (reference src/interp.jl:5-8 after simultaneous_sort!, :21-26)."""
+
+    def __init__(self, weights, values, cum_weights=None):
+        self.weights, self.values, self.cum_weights = weights, values, cum_weights
+
+
+class marginal_result:
+    """reference struct marginal{Ω,T}: wv, μ, σ, itp (src/marginal_posterior.jl:3-8)."""
+
+    def __init__(self, jp, k, mu, sigma, itp):
+        self._jp, self._k = jp, k
+        self.mu, self.sigma, self.itp = float(mu), float(sigma), itp
+        self._wv = None
+
+    μ = property(lambda self: self.mu)
+    σ = property(lambda self: self.sigma)
+
+    @property
+    def wv(self):
+        """Sorted weights/values; fetched from the device on first access (only valid until the next
+        marginal call on the same posterior)."""
+        if self._wv is None:
+            if self._jp is None:
+                raise RuntimeError("sorted weights/values are not available for this marginal")
+            M = self._jp.n_nodes
+            sv, sw, cw = np.zeros(M), np.zeros(M), np.zeros(M)
+            check(lib().jp_marginal_sorted(self._jp.handle, C.c_int(self._k), ptr(sv), ptr(sw), ptr(cw)))
+            self._wv = weights_values(sw, sv, cw)
+        return self._wv
+
+    def quantile(self, p):
+        return quantile(self, p)
+
+    def cdf(self, x):
+        return cdf(self, x)
+
+    def __repr__(self):   # reference src/marginal_posterior.jl:150-155
+        q = [quantile(self, p) for p in (.025, .25, .5, .75, .975)]
+        return "Marginal parameter\nμ: %r\nσ: %r\nQuantiles: [%s]" % (self.mu, self.sigma, " ".join("%.6g" % v for v in q))
+
+
+def quantile(m, p):
+    """quantile(::Grid, p) (reference src/interp.jl:467-478); vectorised over p."""
+    itp = m.itp if isinstance(m, marginal_result) else m
+    if np.ndim(p) > 0:
+        return np.array([quantile(itp, float(x)) for x in np.ravel(p)]).reshape(np.shape(p))
+    return lib().jp_quantile(ptr(itp.weights), ptr(itp.values), C.c_int(len(itp.weights)), C.c_double(float(p)))
+
+
+def cdf(m, x):
+    """cdf(::Grid, x) (reference src/interp.jl:458-466); vectorised over x."""
+    itp = m.itp if isinstance(m, marginal_result) else m
+    if np.ndim(x) > 0:
+        return np.array([cdf(itp, float(v)) for v in np.ravel(x)]).reshape(np.shape(x))
+    return lib().jp_cdf(ptr(itp.weights), ptr(itp.values), C.c_int(len(itp.weights)), C.c_double(float(x)))
+
+
+def _classify(jp, fs):
+    """Split the requested functions into device coordinate selectors and host-evaluated closures."""
+    coords, host = [], []
+    for i, f in enumerate(fs):
+        if isinstance(f, (int, np.integer)):
+            coords.append((i, int(f)))
+            continue
+        k = probe_coordinate(f, jp.M.blocks)
+        if k is not None:
+            coords.append((i, k))
+        else:
+            host.append((i, f))
+    return coords, host
+
+
+def marginals(jp, fs):
+    """Batched marginal(jp, f) for a list of functions: one library call per kind (device / host)."""
+    fs = list(fs)
+    out = [None] * len(fs)
+    coords, host = _classify(jp, fs)
+    L = lib()
+    if coords:
+        K = len(coords)
+        cs = np.array([k for _, k in coords], dtype=np.int32)
+        mu, sg = np.zeros(K), np.zeros(K)
+        vn, wn = np.zeros((K, GRID_KNOTS)), np.zeros((K, GRID_KNOTS))
+        check(L.jp_marginal_coords(jp.handle, C.c_int(K), ptr(cs), ptr(mu), ptr(sg), ptr(vn), ptr(wn)))
+        for j, (i, _) in enumerate(coords):
+            out[i] = marginal_result(jp if not host else None, j, mu[j], sg[j], Grid(wn[j].copy(), vn[j].copy()))
+    if host:
+        K = len(host)
+        view = jp.view()
+        vals = np.zeros((K, jp.n_nodes))
+        for j, (_, f) in enumerate(host):
+            v = f(view)
+            vals[j] = np.broadcast_to(np.asarray(v, dtype=np.float64), (jp.n_nodes,))
+        mu, sg = np.zeros(K), np.zeros(K)
+        vn, wn = np.zeros((K, GRID_KNOTS)), np.zeros((K, GRID_KNOTS))
+        check(L.jp_marginal_values(jp.handle, C.c_int(K), ptr(vals), ptr(mu), ptr(sg), ptr(vn), ptr(wn)))
+        for j, (i, _) in enumerate(host):
+            out[i] = marginal_result(jp, j, mu[j], sg[j], Grid(wn[j].copy(), vn[j].copy()))
+    return out
+
+
+def marginal(jp, f, kind=Grid):
+    """marginal(jp, f[, Grid]) (reference src/marginal_posterior.jl:116-123)."""
+    if kind is not Grid:
+        raise NotImplementedError("only the Grid CDF is on the accelerated path; the smooth NestedPolyGLM fit "
+                                  "(reference src/interp.jl:33-446) is out of scope (SURVEY section 8f)")
+    return marginals(jp, [f])[0]

@@ -1,0 +1,404 @@
+"""Model / mode / fit: the host-side mirror of reference src/joint_posterior.jl.
+
+    Model(ParamStruct | tuple-of-blocks [, build])          reference README.md:39, test/runtests.jl:45
+    fit(model, data [, n])  -> JointPosterior                reference src/joint_posterior.jl:177-188
+    mode(model, data)       -> (mu_hat, U, neg_min)          reference src/joint_posterior.jl:164-168
+
+All numerical work on the path (grid construction, node -> theta map, log-densities, weight
+normalisation) happens in libjpcuda.so on the GPU; there is no CPU fallback.  `mode` itself is
+upstream of the accelerated path: GLM families use a Newton iteration on the GPU
+score/information sums, other families a Newton iteration on finite differences of the
+GPU-evaluated log-density.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, linalg
+from ._lib import FitArgs, JPError, check, colmajor, f64, lib, ptr
+from .data import FAM_LOGISTIC, FAM_POISSON, Data
+from .params import ParamView, blocks_of, transform_codes
+
+
+# ----------------------------------------------------------------------------- rule / build / rank types
+class GenzKeister:
+    rule_id = 0
+
+
+class KronrodPatterson:
+    rule_id = 1
+
+
+class _Build:
+    raw = False
+
+    def __init__(self, rule=GenzKeister):
+        self.rule = rule
+
+    def __class_getitem__(cls, rule):   # Smolyak[GenzKeister] mirrors the reference's b{q}
+        return cls(rule)
+
+
+class Smolyak(_Build):
+    """CacheBuild: fit returns Theta per node (reference src/joint_posterior.jl:177-182)."""
+    raw = False
+
+
+class SmolyakRaw(_Build):
+    """RawBuild: fit keeps the unconstrained node cache (reference src/joint_posterior.jl:183-188)."""
+    raw = True
+
+
+class Dynamic:
+    """Cholesky if positive definite, else eigen fallback (reference src/joint_posterior.jl:136-138)."""
+
+
+class Full:
+    """Always Cholesky (reference src/joint_posterior.jl:139-141)."""
+
+
+class FixedRank:
+    """Keep at most p eigen directions (reference src/joint_posterior.jl:120-134)."""
+
+    def __init__(self, p):
+        self.p = int(p)
+
+
+def default(build=None):
+    """Default Smolyak level `default(B)` (reference src/joint_posterior.jl:177); the value lives in the
+    absent SparseQuadratureGrids package -- 5 here, the level SURVEY/BASELINE quote configs on."""
+    return 5
+
+
+# ----------------------------------------------------------------------------- context
+class Context:
+    """One GPU + one stream (jp_ctx).  Created lazily; shared by default."""
+    _default = {}
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        check(lib().jp_ctx_create(C.c_int(device), C.byref(h)))
+        self.handle = h
+        self.device = device
+        self._data_cache = {}
+
+    @classmethod
+    def get(cls, device=None):
+        if device is None:
+            device = 0
+        if device not in cls._default:
+            cls._default[device] = cls(device)
+        return cls._default[device]
+
+    def use_stream(self, cuda_stream_ptr):
+        check(lib().jp_ctx_set_stream(self.handle, C.c_void_p(cuda_stream_ptr)))
+
+    def sync(self):
+        check(lib().jp_ctx_sync(self.handle))
+
+    def launches(self):
+        return int(lib().jp_ctx_launch_count(self.handle))
+
+    def grid(self, rule_id, d_eff, level):
+        g = C.c_void_p()
+        check(lib().jp_grid_get(self.handle, C.c_int(rule_id), C.c_int(d_eff), C.c_int(level), C.byref(g)))
+        return g
+
+    def upload(self, data):
+        return DeviceData(self, data)
+
+
+class DeviceData:
+    """Observations resident on the GPU (jp_data)."""
+
+    def __init__(self, ctx, data):
+        obs, hyper = data.records()
+        obs = f64(obs)
+        hyper = f64(hyper)
+        h = C.c_void_p()
+        check(lib().jp_data_upload(ctx.handle, C.c_int(data.family), C.c_longlong(obs.shape[0]), C.c_int(obs.shape[1]),
+                                   ptr(obs), ptr(hyper), C.c_int(len(hyper)), C.byref(h)))
+        self.ctx, self.handle, self.family = ctx, h, data.family
+        self.N, self.ncols = obs.shape
+        self.nbytes = obs.nbytes
+
+    def free(self):
+        if self.handle:
+            lib().jp_data_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ----------------------------------------------------------------------------- model
+class Model:
+    """Model(ParamStruct) / Model(tuple, build): parameter layout + grid build + rank policy.
+
+    The reference's Model also owns mutable buffers (diff_buffer, Grid.U, MarginalBuffers); here the
+    device-resident buffers belong to the JointPosterior returned by fit.
+    """
+
+    def __init__(self, params, build=None, rank=Dynamic, device=None, hessian_scale=2.0):
+        self.blocks = blocks_of(params)
+        self.params = params
+        self.d = int(sum(b.n for _, b in self.blocks))
+        self.transform = transform_codes(self.blocks)
+        if build is None:
+            build = Smolyak(GenzKeister)
+        if isinstance(build, type):
+            build = build()
+        self.build = build
+        self.rank = rank
+        self.device = device
+        # reference src/joint_posterior.jl:167 passes 2 * Hessian to deduce_scale!
+        self.hessian_scale = float(hessian_scale)
+
+    @property
+    def ctx(self):
+        return Context.get(self.device)
+
+
+def _as_device_data(M, data):
+    if isinstance(data, DeviceData):
+        return data
+    if not isinstance(data, Data):
+        raise TypeError("data must be a jointposteriors Data object (one per registered likelihood family)")
+    return M.ctx.upload(data)
+
+
+def log_density_unc(M, ddata, X):
+    """Unconstrained log-density (with log-Jacobian) at the rows of X, evaluated on the GPU."""
+    X = f64(np.atleast_2d(X))
+    K, d = X.shape
+    out = np.zeros(K)
+    code = np.ascontiguousarray(M.transform, dtype=np.int32)
+    check(lib().jp_log_density_points(ddata.ctx.handle, ddata.handle, C.c_int(d), ptr(code), C.c_longlong(K),
+                                      ptr(X), ptr(out)))
+    return out
+
+
+def _fd_grad_hess(fbatch, x, h):
+    """Central finite-difference gradient and Hessian, O(h^2), all points in one GPU batch."""
+    d = len(x)
+    E = np.eye(d) * h
+    pts = [x]
+    for i in range(d):
+        pts += [x + E[i], x - E[i]]
+    pairs = [(i, j) for i in range(d) for j in range(i + 1, d)]
+    for i, j in pairs:
+        pts += [x + E[i] + E[j], x + E[i] - E[j], x - E[i] + E[j], x - E[i] - E[j]]
+    f = fbatch(np.array(pts))
+    f0 = f[0]
+    g = np.zeros(d)
+    H = np.zeros((d, d))
+    for i in range(d):
+        fp, fm = f[1 + 2 * i], f[2 + 2 * i]
+        g[i] = (fp - fm) / (2 * h)
+        H[i, i] = (fp - 2 * f0 + fm) / (h * h)
+    o = 1 + 2 * d
+    for q, (i, j) in enumerate(pairs):
+        a, b, c, e = f[o + 4 * q:o + 4 * q + 4]
+        H[i, j] = H[j, i] = (a - b - c + e) / (4 * h * h)
+    return f0, g, H
+
+
+def _richardson_grad_hess(fbatch, x, h=2e-3):
+    """O(h^4) derivatives from two central-difference evaluations."""
+    f0, g1, H1 = _fd_grad_hess(fbatch, x, h)
+    _, g2, H2 = _fd_grad_hess(fbatch, x, h / 2)
+    return f0, (4 * g2 - g1) / 3, (4 * H2 - H1) / 3
+
+
+def _newton_mode_generic(M, ddata, x0, iters=100):
+    f = lambda X: -log_density_unc(M, ddata, X)   # objective: negative log-density, as minimised by optBFGS!
+    x = np.array(x0, dtype=np.float64)
+    fx = f(x[None])[0]
+    for _ in range(iters):
+        _, g, H = _richardson_grad_hess(f, x)
+        try:
+            step = -np.linalg.solve(H, g)
+            if g @ step > 0:
+                step = -g
+        except np.linalg.LinAlgError:
+            step = -g
+        t = 1.0
+        while t > 1e-10:
+            fn = f((x + t * step)[None])[0]
+            if np.isfinite(fn) and fn <= fx:
+                break
+            t *= 0.5
+        x = x + t * step
+        done = abs(fx - fn) <= 1e-15 * (1 + abs(fx)) and np.max(np.abs(t * step)) < 1e-9 * (1 + np.max(np.abs(x)))
+        fx = fn
+        if done:
+            break
+    fx, g, H = _richardson_grad_hess(f, x)
+    return x, H, fx
+
+
+def _newton_mode_glm(M, ddata, x0, iters=60):
+    d = M.d
+    L = lib()
+
+    def gh(beta):
+        g = np.zeros(d)
+        H = np.zeros((d, d), order="F")
+        lp = C.c_double()
+        beta = f64(beta)
+        check(L.jp_glm_grad_hess(ddata.ctx.handle, ddata.handle, C.c_int(d), ptr(beta), ptr(g), ptr(H), C.byref(lp)))
+        return lp.value, g, np.array(H)
+
+    x = np.array(x0, dtype=np.float64)
+    lp, g, H = gh(x)
+    for _ in range(iters):
+        step = np.linalg.solve(H, g)
+        t = 1.0
+        while t > 1e-10:
+            lp2, g2, H2 = gh(x + t * step)
+            if np.isfinite(lp2) and lp2 >= lp - 1e-13 * abs(lp):
+                break
+            t *= 0.5
+        x = x + t * step
+        small = np.max(np.abs(t * step)) < 1e-13 * (1 + np.max(np.abs(x)))
+        lp, g, H = lp2, g2, H2
+        if small:
+            break
+    return x, H, -lp
+
+
+def deduce_scale(M, H):
+    """deduce_scale!(M, H, R) (reference src/joint_posterior.jl:136-144)."""
+    R = M.rank
+    if R is Full or isinstance(R, Full):
+        return linalg.inv_chol(H)
+    if isinstance(R, FixedRank):
+        return linalg.reduce_dimensions(H, R.p)
+    return linalg.deduce_scale_dynamic(H)
+
+
+def mode(M, data, x0=None):
+    """(mu_hat, U, neg_min): unconstrained posterior mode, scale matrix from hessian_scale x Hessian of
+    the negative log-density, and the minimised objective (reference src/joint_posterior.jl:164-168)."""
+    ddata = _as_device_data(M, data)
+    if x0 is None:
+        x0 = np.zeros(M.d)
+    if ddata.family in (FAM_LOGISTIC, FAM_POISSON) and np.all(M.transform == 0):
+        x, H, neg_min = _newton_mode_glm(M, ddata, x0)
+    else:
+        x, H, neg_min = _newton_mode_generic(M, ddata, x0)
+    U = deduce_scale(M, M.hessian_scale * H)
+    return x, U, neg_min
+
+
+# ----------------------------------------------------------------------------- joint posterior
+class JointPosterior:
+    """Result of fit (reference struct JointPosterior, src/joint_posterior.jl:2-8).
+
+    Fields: M (model), Θ / Theta (constrained parameters, [d, nodes]; device-resident, downloaded on
+    access), density (normalised, signed weights), μ_hat / mu_hat, U.
+    """
+
+    def __init__(self, M, ddata, grid, mu_hat, U, neg_min, path=_lib.PATH_AUTO, node_range=None):
+        self.M = M
+        self.data = ddata
+        self.grid = grid
+        self.mu_hat = f64(mu_hat)
+        self.U = colmajor(U)
+        self.neg_min = float(neg_min)
+        self.ctx = ddata.ctx
+        d, p = self.U.shape
+        self._code = np.ascontiguousarray(M.transform, dtype=np.int32)
+        self._args = FitArgs()
+        a = self._args
+        a.d, a.p = d, p
+        a.h_transform = self._code.ctypes.data_as(C.POINTER(C.c_int))
+        a.h_mu_hat = self.mu_hat.ctypes.data_as(C.POINTER(C.c_double))
+        a.h_U = self.U.ctypes.data_as(C.POINTER(C.c_double))
+        a.neg_min = self.neg_min
+        a.path = int(path)
+        a.node_begin, a.node_end = (0, -1) if node_range is None else node_range
+        h = C.c_void_p()
+        check(lib().jp_posterior_create(self.ctx.handle, grid, ddata.handle, C.byref(a), C.byref(h)))
+        self.handle = h
+        self.n_nodes = int(lib().jp_posterior_size(h))
+        self._theta = self._density = None
+
+    def update(self, mu_hat, U, neg_min):
+        """Re-point the posterior at a new (mu_hat, U, neg_min) of the same shape (buffers are reused)."""
+        self.mu_hat[:] = mu_hat
+        self.U[:] = U
+        self.neg_min = float(neg_min)
+        self._args.neg_min = self.neg_min
+        self._theta = self._density = None
+
+    def evaluate(self):
+        """Stages 2-4 on the GPU (asynchronous)."""
+        check(lib().jp_fit(self.handle, C.byref(self._args)))
+        self._theta = self._density = None
+        return self
+
+    @property
+    def path_used(self):
+        return int(lib().jp_fit_path_used(self.handle))
+
+    @property
+    def Theta(self):
+        if self._theta is None:
+            out = np.zeros((self._args.d, self.n_nodes))
+            check(lib().jp_get_theta(self.handle, ptr(out)))
+            self._theta = out
+        return self._theta
+
+    Θ = Theta
+
+    @property
+    def density(self):
+        if self._density is None:
+            out = np.zeros(self.n_nodes)
+            check(lib().jp_get_density(self.handle, ptr(out)))
+            self._density = out
+        return self._density
+
+    @property
+    def logdens(self):
+        out = np.zeros(self.n_nodes)
+        check(lib().jp_get_logdens(self.handle, ptr(out)))
+        return out
+
+    μ_hat = property(lambda self: self.mu_hat)
+
+    def view(self):
+        """Theta as named blocks (what marginal functions receive)."""
+        return ParamView(self.M.blocks, self.Theta)
+
+    def free(self):
+        if getattr(self, "handle", None):
+            lib().jp_posterior_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+JointPosteriorRaw = JointPosterior   # RawBuild keeps the same device-resident result here
+
+
+def fit(M, data, n=None, path=_lib.PATH_AUTO, mode_result=None):
+    """fit(M, data[, n]): mode -> scale -> grid evaluation -> normalised weights
+    (reference src/joint_posterior.jl:177-188).  n is the Smolyak level (default(B))."""
+    ddata = _as_device_data(M, data)
+    if n is None:
+        n = default(M.build)
+    mu_hat, U, neg_min = mode(M, ddata) if mode_result is None else mode_result
+    U = colmajor(U)
+    grid = M.ctx.grid(M.build.rule.rule_id, U.shape[1], int(n))   # cache key: (rule, rank, level), cf. index() :157-162
+    jp = JointPosterior(M, ddata, grid, mu_hat, U, neg_min, path=path)
+    jp.evaluate()
+    return jp

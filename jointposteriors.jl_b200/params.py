@@ -1,0 +1,123 @@
+"""Parameter blocks and their constraint transforms (host-side descriptors).
+
+Mirrors the ConstrainedParameters types the reference re-exports (reference
+src/JointPosteriors.jl:22-26) as used in its two model-declaration styles:
+  * tuple API     `model = (ProbabilityVector(3),)`                   reference test/runtests.jl:5
+  * struct API    `struct BinaryClassification{T} <: parameter{T}; x::Vector{T}; p::ProbabilityVector{3,T}; end`
+                                                                       reference README.md:30-33
+The transforms themselves run on the GPU (csrc/jp_fit.cu, jp_transform); this module only produces
+the per-coordinate transform codes of include/jpcuda.h and gives names to slices of Theta.
+"""
+import numpy as np
+
+T_REAL, T_POSITIVE, T_PROBABILITY = 0, 1, 2
+
+
+class _Block:
+    code = T_REAL
+
+    def __init__(self, n):
+        n = int(n)
+        if n < 1:
+            raise ValueError("parameter block length must be >= 1")
+        self.n = n
+
+    def __repr__(self):
+        return "%s(%d)" % (type(self).__name__, self.n)
+
+
+class RealVector(_Block):
+    """theta = x."""
+    code = T_REAL
+
+
+class PositiveVector(_Block):
+    """theta = exp(x), log|J| = x."""
+    code = T_POSITIVE
+
+
+class ProbabilityVector(_Block):
+    """theta = logistic(x), log|J| = -log(2 + e^x + e^-x) (sign convention of reference src/interp.jl:321-324)."""
+    code = T_PROBABILITY
+
+
+class parameter:
+    """Base class for the struct API: subclasses list their blocks as class attributes, in order.
+
+        class BinaryClassification(parameter):
+            p = ProbabilityVector(3)
+    (the reference's mandatory first field `x::Vector{T}` is the unconstrained storage; here it is implicit)
+    """
+
+
+def blocks_of(spec):
+    """Normalise a model specification to an ordered list of (name, block)."""
+    if isinstance(spec, type) and issubclass(spec, parameter):
+        out = [(k, v) for k, v in vars(spec).items() if isinstance(v, _Block)]
+        if not out:
+            raise ValueError("parameter struct %s declares no parameter blocks" % spec.__name__)
+        return out
+    if isinstance(spec, _Block):
+        spec = (spec,)
+    if isinstance(spec, (tuple, list)) and all(isinstance(b, _Block) for b in spec) and len(spec) > 0:
+        return [("p%d" % (i + 1), b) for i, b in enumerate(spec)]
+    raise TypeError("model must be a parameter subclass or a tuple of RealVector/PositiveVector/ProbabilityVector")
+
+
+def transform_codes(blocks):
+    return np.concatenate([np.full(b.n, b.code, dtype=np.int32) for _, b in blocks])
+
+
+class ParamView:
+    """What a marginal function f(Theta) receives: named blocks of the constrained parameters.
+
+    Field k is an array of shape (n_k, M) (or (n_k,) for a single node); the tuple API's positional
+    splat `f(j.Theta...)` (reference src/marginal_posterior.jl:102) corresponds to `view.blocks`.
+    """
+
+    def __init__(self, blocks, theta):
+        self._names = []
+        self.blocks = []
+        o = 0
+        for name, b in blocks:
+            v = theta[o:o + b.n]
+            setattr(self, name, v)
+            self._names.append(name)
+            self.blocks.append(v)
+            o += b.n
+
+    def __getitem__(self, i):  # tuple API with one block: p[1] style access falls through to the block
+        if len(self.blocks) == 1:
+            return self.blocks[0][i]
+        return self.blocks[i]
+
+
+class _CoordProbe:
+    """Stand-in for Theta that records which single coordinate a selector f picks."""
+
+    def __init__(self, blocks):
+        d = sum(b.n for _, b in blocks)
+        self.view = ParamView(blocks, np.arange(d, dtype=np.int64).view(_ProbeArray))
+
+
+class _ProbeArray(np.ndarray):
+    """integer array whose arithmetic is forbidden, so only pure selections survive"""
+
+    def __array_ufunc__(self, *a, **k):
+        raise TypeError("not a pure coordinate selection")
+
+
+def probe_coordinate(f, blocks):
+    """Return the flat coordinate index if f(Theta) merely selects one coordinate, else None."""
+    try:
+        pr = _CoordProbe(blocks)
+        r = f(pr.view)
+        if isinstance(r, _ProbeArray) and r.ndim == 0:
+            return int(np.asarray(r))
+        if isinstance(r, (np.integer,)):
+            return int(r)
+        if isinstance(r, _ProbeArray) and r.size == 1:
+            return int(np.asarray(r).reshape(-1)[0])
+    except Exception:
+        return None
+    return None
