@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py -- node x observation log-density evaluations per second of the posterior-integration hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--workload cfg3] [--path auto|fp64|tc] [--impl reference]
+
+One STEP = one pass of the hot path over the resident synthetic data set: stages 2-4 (`fit`: node -> theta
+map, node x obs log-density, weight normalisation) plus stage 5 (`marginal` of every coordinate: moments +
+100-knot Grid CDF) on the cached Smolyak grid (the reference caches its grid the same way,
+src/joint_posterior.jl:157-162; the grid build and the mode finder are timed once and reported beside it).
+
+  value  whole-job (node x obs pairs) / s with observations resident in HBM, CUDA-event timed, max over ranks
+  e2e    same metric through the public API with HOST buffers: jp_data_upload of the observation records
+         (H2D), fit, marginals, and the D2H of the results, all inside the timed region
+Multi-GPU (torchrun, one rank per GPU): WEAK scaling -- the grid nodes are sharded across ranks and the
+observation count grows with the rank count (N_obs = n_gpus x base), so per-GPU work is fixed; the only
+collectives are the tiny all_gathers of jointposteriors.jl_b200/distributed.py.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+METRIC = "node_x_obs_log_density_evals_per_sec"
+UNIT = "pairs/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)), samples=len(sm),
+                    reasons=sorted(reasons))
+
+
+def make_workload(jp, name, n_gpus):
+    from jointposteriors_jl_b200 import workloads
+    if name == "cfg3":
+        wl = workloads.cfg3_logistic(N=100_000 * n_gpus)
+        desc = "BASELINE cfg3: logistic regression d=10, Smolyak level 6 (114985 nodes), %d synthetic obs (1e5 x n_gpus)" % (100_000 * n_gpus)
+    elif name == "cfg4":
+        wl = workloads.cfg4_poisson(N=1_000_000 * max(1, n_gpus) // max(1, n_gpus))
+        desc = "BASELINE cfg4: Poisson regression d=20, Smolyak level 5 (189161 nodes), 1e6 synthetic obs, node-sharded"
+    elif name == "cfg5":
+        wl = workloads.cfg5_logistic()
+        desc = "BASELINE cfg5: logistic regression d=30, Smolyak level 4 (45201 nodes), 1e7 synthetic obs, node-sharded"
+    elif name == "cfg2":
+        wl = workloads.cfg2_eight_schools()
+        desc = "BASELINE cfg2: eight-schools hierarchical normal d=10, level 5 (17981 nodes), 8 groups"
+    elif name == "cfg1":
+        wl = workloads.cfg1_binary_classification()
+        desc = "BASELINE cfg1: README binomial mixture d=3, level 5 (495 nodes), 8 data rows"
+    elif name == "tiny":
+        wl = workloads.cfg3_logistic(N=2000 * n_gpus, d=4, level=4)
+        desc = "tiny logistic d=4 level 4, %d obs (smoke of the bench itself)" % (2000 * n_gpus)
+    else:
+        raise SystemExit("unknown workload %s" % name)
+    wl["desc"] = desc
+    return wl
+
+
+# ----------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's CPU path for the same workload: the C++ oracle restatement (the Julia 0.6 reference
+    and its three unvendored packages cannot be built here), all host threads, on a bounded
+    sample of the workload's grid nodes x ALL observations per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    jp = entry.load_package()
+    wl = make_workload(jp, args.workload, args.gpus)
+    data = wl["data"]
+    obs, hyper = data.records()
+    d = wl["d"]
+    fam = data.family
+    code = np.concatenate([np.full(b.n, b.code, dtype=np.int32) for b in wl["params"]])
+    cores = O.num_threads()
+    if fam in (1, 2):
+        # mode on a subsample is enough to place the sample nodes (timing only)
+        sub = obs[: min(len(obs), 20000)]
+        beta, H, ll = O.glm_mode(fam, sub, hyper, d)
+        H = H * (len(obs) / len(sub))
+        x, neg_min = beta, -ll * (len(obs) / len(sub))
+    else:
+        x, H, neg_min = np.zeros(d), np.eye(d), 0.0
+    U = O.inv_chol(2.0 * H)
+    idx, w = O.smolyak(0, d, wl["level"])
+    N = obs.shape[0]
+    # size the per-step node sample for ~2-4 s of all-core work
+    t0 = time.perf_counter()
+    probe = min(len(w), 4 * cores)
+    O.eval_grid(0, fam, code, idx, w, x, U, neg_min, obs, hyper, 0, probe, threads=cores, want_theta=False)
+    rate = probe * N / max(time.perf_counter() - t0, 1e-6)
+    m_step = int(max(cores, min(len(w), rate * 3.0 / N)))
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        res = O.eval_grid(0, fam, code, idx, w, x, U, neg_min, obs, hyper, 0, m_step, threads=cores, want_theta=True)
+        for k in range(d):
+            O.marginal(res["theta"][k][:m_step], res["density"][:m_step])
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = m_step * N / (ms * 1e-3)
+    sample = "first %d of %d merged grid nodes x all %d observations per step (fit + %d coordinate marginals), %d threads" % (
+        m_step, len(w), N, d, cores)
+    out = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
+               higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
+               config=dict(workload=wl["desc"], sample=sample),
+               cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind="port", sample=sample),
+               e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- product arm
+def cpu_baseline(wl, post_inputs, budget_s=12.0):
+    from oracle import oracle as O
+    O.build()
+    data = wl["data"]
+    obs, hyper = data.records()
+    d, fam = wl["d"], data.family
+    code = np.concatenate([np.full(b.n, b.code, dtype=np.int32) for b in wl["params"]])
+    x, U, neg_min = post_inputs
+    idx, w = O.smolyak(0, U.shape[1], wl["level"])
+    N = obs.shape[0]
+    cores = O.num_threads()
+    probe = min(len(w), 2 * cores)
+    t0 = time.perf_counter()
+    O.eval_grid(0, fam, code, idx, w, x, U, neg_min, obs, hyper, 0, probe, threads=cores, want_theta=False)
+    rate = probe * N / max(time.perf_counter() - t0, 1e-6)
+    m = int(max(cores, min(len(w), rate * budget_s / N)))
+    t0 = time.perf_counter()
+    O.eval_grid(0, fam, code, idx, w, x, U, neg_min, obs, hyper, 0, m, threads=cores, want_theta=False)
+    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    m1 = int(max(1, min(m, m // cores)))
+    O.eval_grid(0, fam, code, idx, w, x, U, neg_min, obs, hyper, 0, m1, threads=1, want_theta=False)
+    dt1 = time.perf_counter() - t1
+    return dict(value=m * N / dt, unit=UNIT, cores=cores, kind="port",
+                sample="oracle eval_grid on the first %d of %d merged nodes x all %d observations, %d threads (%.1f s); "
+                       "1 thread (the reference is single-threaded): %.4g pairs/s on %d nodes" % (m, len(w), N, cores, dt, m1 * N / dt1, m1),
+                single_thread_value=m1 * N / dt1)
+
+
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torchrun --nproc-per-node %d)" % (args.gpus, world, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libjpcuda has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    jp = entry.load_package()
+    from jointposteriors_jl_b200 import distributed as D
+    from jointposteriors_jl_b200.model import Context, JointPosterior
+    from jointposteriors_jl_b200 import _lib
+    peaks = load_peaks()
+    wl = make_workload(jp, args.workload, world)
+    data = wl["data"]
+    obs, hyper = data.records()
+    d = wl["d"]
+    path = dict(auto=_lib.PATH_AUTO, fp64=_lib.PATH_FP64, tc=_lib.PATH_TC)[args.path]
+    ctx = Context.get(local_rank)
+    stream = torch.cuda.current_stream(dev)
+    ctx.use_stream(stream.cuda_stream)
+    M = jp.Model(wl["params"], device=local_rank)
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    # ---- one-time setup: data upload, mode, grid build (timed, reported, not part of the step)
+    t0 = time.perf_counter()
+    dd = ctx.upload(data)
+    ctx.sync()
+    t_up = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    x, U, neg_min = jp.mode(M, dd)
+    t_mode = time.perf_counter() - t0
+    e0, e1 = ev(), ev()
+    e0.record(stream)
+    grid = ctx.grid(M.build.rule.rule_id, U.shape[1], wl["level"])
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    t_grid = e0.elapsed_time(e1)
+    Mtot = int(jp.lib().jp_grid_size(grid))
+    b, e = D.shard_bounds(Mtot, rank, world)
+    post = JointPosterior(M, dd, grid, x, U, neg_min, path=path, node_range=(b, e))
+    loc = D.CudaLocal(post)
+    coords = list(range(d))
+    N = obs.shape[0]
+    pairs = float(Mtot) * float(N)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # 256 MiB > 126 MB L2
+
+    def step_device():
+        if world == 1:
+            post.evaluate()
+            res = jp.marginals(post, coords)
+            return res[0].mu
+        D.fit_sharded(loc)
+        mu, sg, vn, wn = D.marginals_sharded(loc, coords)
+        return float(mu[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing ("value")
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    launches0 = ctx.launches()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    fit_ms, marg_ms, step_ms = [], [], []
+    for _ in range(args.steps):
+        flush.zero_()                      # evict the working set from L2 between timed iterations
+        torch.cuda.synchronize(dev)
+        a, bq, c = ev(), ev(), ev()
+        a.record(stream)
+        if world == 1:
+            post.evaluate()
+            bq.record(stream)
+            jp.marginals(post, coords)
+        else:
+            D.fit_sharded(loc)
+            bq.record(stream)
+            D.marginals_sharded(loc, coords)
+        c.record(stream)
+        torch.cuda.synchronize(dev)
+        fit_ms.append(a.elapsed_time(bq)); marg_ms.append(bq.elapsed_time(c)); step_ms.append(a.elapsed_time(c))
+    barrier()
+    launches = ctx.launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([float(np.sum(step_ms)), float(np.sum(fit_ms)), float(np.sum(marg_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot_ms, tot_fit_ms, tot_marg_ms = [float(v) for v in t.cpu()]
+    ms_per_step = tot_ms / args.steps
+    value = pairs / (ms_per_step * 1e-3)
+
+    # ---- dominant kernel alone (stages 2-3 log-density kernel), for the roofline
+    kern_ms = []
+    for _ in range(max(3, args.steps)):
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        a, bq = ev(), ev()
+        a.record(stream)
+        loc.fit_local_max()
+        bq.record(stream)
+        torch.cuda.synchronize(dev)
+        kern_ms.append(a.elapsed_time(bq))
+    kms = float(np.median(kern_ms))
+    path_used = post.path_used
+    local_pairs = float(e - b) * float(N)
+    if path_used == _lib.PATH_TC:
+        flops = 2.0 * d * local_pairs
+        tf32_peak = peaks["bf16_tflops"] / 2.0
+        roof = dict(bound="tensor", achieved=flops / (kms * 1e-3) / 1e12, peak=tf32_peak, unit="TFLOP/s",
+                    frac=flops / (kms * 1e-3) / 1e12 / tf32_peak, traffic=None,
+                    note="algorithmic 2*d flops per pair (issued 3xTF32 on K padded to 32: %dx more); peak = measured bf16/2 "
+                         "(TF32 dense is half the bf16 rate), %s; kernel is bound by its FP32 epilogue, see DESIGN.md" % (
+                             int(round(3 * 32 * ((d * 3 + 31) // 32) / (3.0 * d))), peaks["source"]))
+    else:
+        nbytes = 8.0 * N * (d + 1) + 8.0 * (e - b) * (d + 1)
+        roof = dict(bound="hbm", achieved=nbytes / (kms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
+                    frac=nbytes / (kms * 1e-3) / 1e9 / peaks["hbm_gbs"], traffic=None,
+                    note="FP64 plugin kernel: compulsory bytes 8N(d+1)+8M(d+1); the kernel is FP64-ALU bound "
+                         "(%.3g pairs/s), not HBM bound; %s" % (local_pairs / (kms * 1e-3), peaks["source"]))
+    roof["kernel_ms"] = kms
+    roof["kernel_pairs_per_s"] = local_pairs / (kms * 1e-3)
+
+    # ---- end to end through the public API with host buffers ("e2e")
+    obs_pinned = torch.from_numpy(obs).pin_memory()
+    hdata = type(data).__new__(type(data))
+    hdata.__dict__.update(data.__dict__)
+    hdata._obs = obs_pinned.numpy()
+
+    def step_e2e():
+        dde = ctx.upload(hdata)                                   # H2D of the observation records
+        pe = JointPosterior(M, dde, grid, x, U, neg_min, path=path, node_range=(b, e))
+        if world == 1:
+            pe.evaluate()
+            res = jp.marginals(pe, coords)                        # D2H of mu, sigma, 2 x 100 knots per coordinate
+            dens = pe.density                                     # D2H of the normalised weights
+            out = (res[0].mu, float(dens[0]))
+        else:
+            le = D.CudaLocal(pe)
+            D.fit_sharded(le)
+            mu, sg, vn, wn = D.marginals_sharded(le, coords)
+            dens = pe.density
+            out = (float(mu[0].cpu()), float(sg[0].cpu()), vn.cpu(), wn.cpu(), float(dens[0]))
+        pe.free()
+        dde.free()
+        return out
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        step_e2e()
+    barrier()
+    a, c = ev(), ev()
+    a.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    c.record(stream)
+    barrier()
+    e2e_wall = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([max(a.elapsed_time(c), e2e_wall)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.cpu()[0]) / args.steps
+    h2d = int(obs.nbytes + 8 * (d + d * U.shape[1]) + 4 * d)
+    d2h = int(8 * (e - b) + d * 8 * (2 + 200))
+    e2e = dict(value=pairs / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms)
+
+    if rank == 0:
+        cpu = cpu_baseline(wl, (x, U, neg_min)) if world == 1 and not args.no_cpu_baseline else None
+        out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                   ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+                   dtype="tf32x3+f64" if path_used == _lib.PATH_TC else "f64", data="synthetic",
+                   config=dict(workload=wl["desc"], nodes=Mtot, obs=int(N), d=d, level=wl["level"],
+                               parallelism="node-sharded x%d" % world, path="tc" if path_used == _lib.PATH_TC else "fp64",
+                               l2="256 MiB flush buffer written between timed iterations",
+                               marginals="%d coordinate marginals per step (moments + 100-knot Grid CDF)" % d),
+                   fit_ms=tot_fit_ms / args.steps, marginal_ms=tot_marg_ms / args.steps, grid_build_ms=t_grid,
+                   mode_ms=t_mode * 1e3, upload_ms=t_up * 1e3, clocks=clocks, e2e=e2e, gpu_launches=int(launches),
+                   roofline=roof)
+        if cpu:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3")
+    ap.add_argument("--path", default="auto", choices=["auto", "fp64", "tc"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

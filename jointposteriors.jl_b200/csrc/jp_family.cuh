@@ -48,13 +48,9 @@ struct FamBinomialMixture {
 template <int DPAD>
 __device__ __forceinline__ double jp_eta(const double (&th)[DPAD], int d, const double* r) {
   double eta = 0;
-  if (DPAD <= 32) {
 #pragma unroll
-    for (int k = 0; k < DPAD; ++k)
-      if (k < d) eta += r[k] * th[k];
-  } else {
-    for (int k = 0; k < d; ++k) eta += r[k] * th[k];
-  }
+  for (int k = 0; k < DPAD; ++k)
+    if (k < d) eta += r[k] * th[k];
   return eta;
 }
 
@@ -66,7 +62,9 @@ struct FamLogistic {
   template <int DPAD>
   __device__ static double prior(const double (&b)[DPAD], int d, long long, const double* h) {
     double lp = 0;
-    for (int k = 0; k < d; ++k) lp += jp_lpdf_normal(b[k], 0.0, h[0]);
+#pragma unroll
+    for (int k = 0; k < DPAD; ++k)
+      if (k < d) lp += jp_lpdf_normal(b[k], 0.0, h[0]);
     return lp;
   }
   template <int DPAD>
@@ -84,7 +82,9 @@ struct FamPoisson {
   template <int DPAD>
   __device__ static double prior(const double (&b)[DPAD], int d, long long, const double* h) {
     double lp = 0;
-    for (int k = 0; k < d; ++k) lp += jp_lpdf_normal(b[k], 0.0, h[0]);
+#pragma unroll
+    for (int k = 0; k < DPAD; ++k)
+      if (k < d) lp += jp_lpdf_normal(b[k], 0.0, h[0]);
     return lp;
   }
   template <int DPAD>
@@ -120,14 +120,23 @@ struct FamNormalLinear {
   static bool shape_ok(int d, int ncols, long long) { return ncols == d; }
   template <int DPAD>
   __device__ static double prior(const double (&t)[DPAD], int d, long long, const double* h) {
-    double lp = jp_lpdf_normal(t[d - 1], 0.0, h[1]);
-    for (int k = 0; k < d - 1; ++k) lp += jp_lpdf_normal(t[k], 0.0, h[0]);
-    return lp;
+    double lp = 0, sigma = 0;
+#pragma unroll
+    for (int k = 0; k < DPAD; ++k) {
+      if (k < d - 1) lp += jp_lpdf_normal(t[k], 0.0, h[0]);
+      if (k == d - 1) sigma = t[k];
+    }
+    return jp_lpdf_normal(sigma, 0.0, h[1]) + lp;
   }
   template <int DPAD>
   __device__ static double obs(const double (&t)[DPAD], int d, const double* r, long long, const double*) {
-    double eta = jp_eta(t, d - 1, r);
-    return jp_lpdf_normal(r[d - 1], eta, t[d - 1]);
+    double eta = 0, sigma = 0;
+#pragma unroll
+    for (int k = 0; k < DPAD; ++k) {
+      if (k < d - 1) eta += r[k] * t[k];
+      if (k == d - 1) sigma = t[k];
+    }
+    return jp_lpdf_normal(r[d - 1], eta, sigma);
   }
 };
 

@@ -118,12 +118,14 @@ class CudaLocal:
         return out
 
 
-def fit_sharded(local, group=None):
-    """Normalise a node-sharded fit: two tiny all_gathers (max, then sum)."""
+def fit_sharded(local, group=None, gather=None):
+    """Normalise a node-sharded fit: two tiny all_gathers (max, then sum).  `gather(t, group)` defaults to
+    torch.distributed all_gather; tests emulating several ranks on one GPU inject their own."""
+    gather = gather or _all_gather
     lmax = local.fit_local_max()
-    gmax = _all_gather(lmax, group).max(dim=0).values.contiguous()
+    gmax = gather(lmax, group).max(dim=0).values.contiguous()
     lsum = local.fit_local_sum(gmax)
-    sums = _all_gather(lsum, group)
+    sums = gather(lsum, group)
     gsum = sums[0].clone()
     for r in range(1, sums.shape[0]):
         gsum = gsum + sums[r]
@@ -132,12 +134,13 @@ def fit_sharded(local, group=None):
     return gmax, gsum
 
 
-def marginals_sharded(local, coords, group=None):
+def marginals_sharded(local, coords, group=None, gather=None):
     """Global (mu, sigma, value_nodes, weight_nodes) for K coordinate marginals of a node-sharded
     posterior: two all_gathers per batch, no global sort."""
     import torch
+    gather = gather or _all_gather
     mom = local.moments(coords)                       # [K, 4] = (sum w v, sum w v^2, min, max)
-    g = _all_gather(mom, group)                       # [world, K, 4]
+    g = gather(mom, group)                            # [world, K, 4]
     s1 = g[0, :, 0].clone()
     s2 = g[0, :, 1].clone()
     for r in range(1, g.shape[0]):
@@ -147,7 +150,7 @@ def marginals_sharded(local, coords, group=None):
     vmax = g[:, :, 3].max(dim=0).values
     minmax = torch.stack([vmin, vmax], dim=1).contiguous()
     cand = local.knots(coords, minmax)                # [K, 98, 6]
-    gathered = _all_gather(cand, group)               # [world, K, 98, 6]
+    gathered = gather(cand, group)                    # [world, K, 98, 6]
     wn = combine_knots(gathered, vmin, vmax)
     vn = knot_values(vmin, vmax)
     mu = s1

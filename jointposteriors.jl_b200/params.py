@@ -92,32 +92,25 @@ class ParamView:
         return self.blocks[i]
 
 
-class _CoordProbe:
-    """Stand-in for Theta that records which single coordinate a selector f picks."""
-
-    def __init__(self, blocks):
-        d = sum(b.n for _, b in blocks)
-        self.view = ParamView(blocks, np.arange(d, dtype=np.int64).view(_ProbeArray))
-
-
-class _ProbeArray(np.ndarray):
-    """integer array whose arithmetic is forbidden, so only pure selections survive"""
-
-    def __array_ufunc__(self, *a, **k):
-        raise TypeError("not a pure coordinate selection")
-
-
 def probe_coordinate(f, blocks):
-    """Return the flat coordinate index if f(Theta) merely selects one coordinate, else None."""
-    try:
-        pr = _CoordProbe(blocks)
-        r = f(pr.view)
-        if isinstance(r, _ProbeArray) and r.ndim == 0:
-            return int(np.asarray(r))
-        if isinstance(r, (np.integer,)):
-            return int(r)
-        if isinstance(r, _ProbeArray) and r.size == 1:
-            return int(np.asarray(r).reshape(-1)[0])
-    except Exception:
-        return None
-    return None
+    """Return the flat coordinate index if f(Theta) merely selects one coordinate, else None.
+
+    f is evaluated on three fixed pseudo-random parameter vectors; it is a pure selector of coordinate k
+    exactly when its result is bit-identical to entry k of every probe (any arithmetic breaks that)."""
+    d = sum(b.n for _, b in blocks)
+    rng = np.random.Generator(np.random.Philox(key=0x5E1EC7))
+    found = None
+    for _ in range(3):
+        v = rng.random(d) + 0.25
+        try:
+            r = f(ParamView(blocks, v))
+            r = np.asarray(r, dtype=np.float64)
+        except Exception:
+            return None
+        if r.size != 1:
+            return None
+        hits = np.nonzero(v == r.reshape(-1)[0])[0]
+        if len(hits) != 1 or (found is not None and hits[0] != found):
+            return None
+        found = int(hits[0])
+    return found

@@ -1,0 +1,90 @@
+"""Shared fixtures.  `-m "not gpu"` runs here (no GPU); `-m gpu` runs on a B200 and calls libjpcuda.so
+through its C ABI (ctypes).  The oracle (oracle/) is the checker in both."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import __graft_entry__ as entry  # noqa: E402
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+
+
+@pytest.fixture(scope="session")
+def O():
+    """The CPU oracle (test infrastructure)."""
+    from oracle import oracle
+    oracle.build()
+    return oracle
+
+
+@pytest.fixture(scope="session")
+def jp():
+    """The package (host mirror of the reference API over libjpcuda.so)."""
+    so = os.path.join(entry.PKG_DIR, "libjpcuda.so")
+    if not os.path.exists(so):
+        entry.build()
+    return entry.load_package()
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx(jp):
+    return jp.Context.get(0)
+
+
+README_X = [0, 1, 2, 3, 4, 7, 8, 9]
+README_FREQ = [10, 2, 2, 1, 2, 3, 2, 16]
+
+
+def readme_records():
+    """README Example 1 data (reference README.md:82-86): records (X, freq, NmX) and Beta(a,b) exponents."""
+    X = np.array(README_X, dtype=np.float64)
+    f = np.array(README_FREQ, dtype=np.float64)
+    obs = np.ascontiguousarray(np.stack([X, f, 9 - X], axis=1))
+    hyper = np.array([0.0, 1.0, 0.0, 1.0, 0.0, 0.0])
+    return obs, hyper
+
+
+def fd_hessian(f, x, h=1e-3):
+    d = len(x)
+    E = np.eye(d) * h
+    H = np.zeros((d, d))
+    for i in range(d):
+        for j in range(i, d):
+            H[i, j] = H[j, i] = (f(x + E[i] + E[j]) - f(x + E[i] - E[j]) - f(x - E[i] + E[j]) + f(x - E[i] - E[j])) / (4 * h * h)
+    return H
+
+
+def cpu_mode(O, family, code, obs, hyper, x0):
+    """Unconstrained posterior mode, Hessian of the negative log-density and its minimum, on the CPU."""
+    from scipy.optimize import minimize
+    code = np.ascontiguousarray(code, dtype=np.int32)
+    f = lambda x: -O.log_density_unc(family, code, x, obs, hyper)
+    r = minimize(f, np.asarray(x0, dtype=np.float64), method="Nelder-Mead",
+                 options=dict(xatol=1e-12, fatol=1e-14, maxiter=40000, maxfev=40000))
+    return r.x, fd_hessian(f, r.x), float(r.fun)
+
+
+def synth_glm(seed, N, d, kind, xscale=1.0):
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    beta = rng.standard_normal(d) / np.sqrt(d)
+    X = rng.standard_normal((N, d)) * xscale
+    X[:, 0] = 1.0
+    eta = X @ beta
+    if kind == "logistic":
+        y = (rng.random(N) < 1 / (1 + np.exp(-eta))).astype(np.float64)
+    else:
+        y = rng.poisson(np.exp(eta)).astype(np.float64)
+    return X, y
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))

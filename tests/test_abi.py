@@ -1,0 +1,152 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/jpcuda.h declares, its host-side
+helpers match the oracle bit for bit, and every compute entry point fails loudly when there is no device."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "jpcuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(jp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_exports_match_header(jp):
+    from jointposteriors_jl_b200 import _lib
+    declared = header_symbols()
+    assert sorted(_lib.SYMBOLS) == declared
+    L = jp.lib()
+    for name in declared:
+        assert hasattr(L, name), "libjpcuda.so does not export %s" % name
+    out = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ROOT, "jointposteriors.jl_b200", "libjpcuda.so")], text=True)
+    exported = sorted(set(re.findall(r" T (jp_[a-z0-9_]+)$", out, flags=re.M)))
+    assert [s for s in declared if s not in exported] == []
+
+
+def test_built_for_sm100a_only():
+    so = os.path.join(ROOT, "jointposteriors.jl_b200", "libjpcuda.so")
+    out = subprocess.check_output(["cuobjdump", "-lelf", so], text=True)
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_device_is_an_error_not_a_fallback(jp):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(jp.JPError) as e:
+        jp.Context(0)
+    assert e.value.status == 4   # JP_ERR_NO_DEVICE
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_touch_the_oracle():
+    """Nothing under the package may import, link or load oracle/."""
+    pkg = os.path.join(ROOT, "jointposteriors.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "jporacle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+    out = subprocess.check_output(["ldd", os.path.join(pkg, "libjpcuda.so")], text=True)
+    assert "oracle" not in out
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 10, 30, 64])
+def test_host_linalg_bit_exact_with_oracle(jp, O, d):
+    rng = np.random.default_rng(100 + d)
+    A = rng.standard_normal((d, d))
+    S = A @ A.T + d * np.eye(d)
+    assert np.array_equal(np.triu(jp.chol(S)), np.triu(O.chol(S)))
+    ok, U = jp.try_chol(S)
+    assert ok and np.array_equal(np.triu(U), np.triu(O.chol(S)))
+    assert np.array_equal(np.triu(jp.inv_upper(np.triu(U))), np.triu(O.inv_upper(np.triu(U))))
+    assert np.array_equal(jp.inv_chol(S), O.inv_chol(S))
+    assert np.array_equal(jp.deduce_scale_dynamic(S), O.deduce_scale_dynamic(S))
+
+
+def test_try_chol_not_pd(jp):
+    ok, _ = jp.try_chol(np.array([[1.0, 2.0], [2.0, 1.0]]))
+    assert not ok
+
+
+def test_reduce_dimensions_matches_oracle(jp, O):
+    rng = np.random.default_rng(7)
+    Q, _ = np.linalg.qr(rng.standard_normal((6, 6)))
+    lam = np.array([0.0, 1e-13, 0.5, 2.0, 9.0, 11.0])
+    H = (Q * lam) @ Q.T
+    for mr in (0, 2):
+        G, Go = jp.reduce_dimensions(H, mr), O.reduce_dimensions(H, mr)
+        assert G.shape == Go.shape
+        assert np.allclose(G @ G.T, Go @ Go.T, atol=1e-11)
+    U = jp.deduce_scale_dynamic(H)
+    assert U.shape == (6, 4)
+
+
+def test_quantile_cdf_bit_exact_with_oracle(jp, O):
+    rng = np.random.default_rng(3)
+    vn = np.linspace(-2.0, 3.0, 100)
+    wn = np.clip(np.linspace(0, 1, 100) + 0.03 * rng.standard_normal(100), -0.05, 1.05)
+    wn[0], wn[-1] = 0.0, 1.0
+    g = jp.Grid(wn, vn)
+    for p in [0.0, 1e-9, 0.025, 0.25, 0.49999, 0.5, 0.75, 0.975, 1 - 1e-9, 1.0]:
+        assert jp.quantile(g, p) == O.quantile(wn, vn, p)
+    for x in [-3.0, -2.0, -1.99, 0.0, 0.123, 2.99, 3.0, 4.0]:
+        assert jp.cdf(g, x) == O.cdf(wn, vn, x)
+
+
+def test_rule_tables_identical_to_oracle(jp, O):
+    L = jp.lib()
+    for rule in (0, 1):
+        npts, nodes, weights = O.rule_info(rule)
+        lv, nm = C.c_int(), C.c_int()
+        assert L.jp_rule_info(rule, C.byref(lv), C.byref(nm), None, None, None) == 0
+        n2 = np.zeros(lv.value, dtype=np.int32)
+        z2 = np.zeros(nm.value)
+        w2 = np.zeros((lv.value, nm.value))
+        assert L.jp_rule_info(rule, C.byref(lv), C.byref(nm), n2.ctypes.data_as(C.c_void_p),
+                              z2.ctypes.data_as(C.c_void_p), w2.ctypes.data_as(C.c_void_p)) == 0
+        assert np.array_equal(n2, npts) and np.array_equal(z2, nodes) and np.array_equal(w2, weights)
+
+
+def test_model_declaration_styles(jp):
+    """Tuple API (reference test/runtests.jl:5) and struct API (reference README.md:30-33)."""
+    m1 = jp.Model((jp.ProbabilityVector(3),))
+
+    class BinaryClassification(jp.parameter):
+        p = jp.ProbabilityVector(3)
+
+    m2 = jp.Model(BinaryClassification)
+    assert m1.d == m2.d == 3 and list(m1.transform) == list(m2.transform) == [2, 2, 2]
+    m3 = jp.Model((jp.RealVector(1), jp.PositiveVector(1), jp.RealVector(8)), jp.SmolyakRaw[jp.KronrodPatterson])
+    assert m3.d == 10 and list(m3.transform) == [0, 1] + [0] * 8 and m3.build.rule.rule_id == 1 and m3.build.raw
+    with pytest.raises(TypeError):
+        jp.Model(3)
+
+
+def test_coordinate_selector_detection(jp):
+    from jointposteriors_jl_b200.params import probe_coordinate
+    m = jp.Model((jp.RealVector(1), jp.PositiveVector(1), jp.RealVector(8)))
+    assert probe_coordinate(lambda t: t.p3[4], m.blocks) == 6
+    assert probe_coordinate(lambda t: t.p2[0], m.blocks) == 1
+    assert probe_coordinate(lambda t: t.p3[4] * 2, m.blocks) is None
+    assert probe_coordinate(lambda t: t.p3[1] - t.p3[0], m.blocks) is None
+    m1 = jp.Model((jp.ProbabilityVector(3),))
+    assert probe_coordinate(lambda p: p[0], m1.blocks) == 0
+
+
+def test_data_validation(jp):
+    with pytest.raises(ValueError):
+        jp.LogisticData(np.zeros((0, 3)), np.zeros(0))
+    with pytest.raises(ValueError):
+        jp.BinaryClassificationData([], [], 9)
+    with pytest.raises(ValueError):
+        jp.LogisticData(np.zeros((4, 3)), np.zeros(5))
+    obs, hyper = jp.BinaryClassificationData([0, 1], [2, 3], 9, βm=2, βp=2).records()
+    assert obs.tolist() == [[0, 2, 9], [1, 3, 8]] and hyper.tolist() == [0, 1, 0, 1, 0, 0]

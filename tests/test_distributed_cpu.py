@@ -1,0 +1,138 @@
+"""World-size-2 `gloo` test of the node-sharded combine (jointposteriors.jl_b200/distributed.py):
+the collectives + host combine reproduce the single-process oracle, including the Grid tie rule across
+shard boundaries.  The per-rank local phase is a numpy stand-in with the same contract as the CUDA
+kernels (jp_fit_local*, jp_marginal_local_moments, jp_marginal_local_knots)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class NumpyLocal:
+    """Same contract as distributed.CudaLocal, on numpy arrays (CPU)."""
+
+    def __init__(self, a, w, values, m0):
+        import torch
+        self.t = torch
+        self.a, self.w, self.values, self.m0 = a, w, values, m0
+        self.density = None
+
+    def _t(self, x):
+        return self.t.tensor(np.asarray(x, dtype=np.float64))
+
+    def fit_local_max(self):
+        return self._t([self.a.max()])
+
+    def fit_local_sum(self, gmax):
+        self.e = self.w * np.exp(self.a - float(gmax[0]))
+        return self._t([self.e.sum()])
+
+    def fit_normalise(self, gsum):
+        self.density = self.e / float(gsum[0])
+
+    def moments(self, coords):
+        out = []
+        for k in coords:
+            v = self.values[k]
+            out.append([(self.density * v).sum(), (self.density * v * v).sum(), v.min(), v.max()])
+        return self._t(out)
+
+    def knots(self, coords, minmax):
+        mm = minmax.numpy()
+        out = np.zeros((len(coords), 98, 6))
+        for j, k in enumerate(coords):
+            v = self.values[k]
+            for i in range(1, 99):
+                x = mm[j, 0] + (i / 99.0) * (mm[j, 1] - mm[j, 0])
+                x = float(np.float64(np.add(mm[j, 0], np.multiply(i / 99.0, mm[j, 1] - mm[j, 0]))))
+                le = v <= x
+                S = self.density[le].sum()
+                pred = v[le].max() if le.any() else -np.inf
+                gt = ~le
+                if gt.any():
+                    succ = v[gt].min()
+                    jj = int(np.nonzero(v == succ)[0][0])
+                    out[j, i - 1] = [S, pred, succ, self.m0 + jj, self.density[jj], 0]
+                else:
+                    out[j, i - 1] = [S, pred, np.inf, np.inf, 0, 0]
+        return self._t(out)
+
+
+def _worker(rank, world, port, a, w, values, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    entry.load_package()
+    from jointposteriors_jl_b200 import distributed as D
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    M = len(a)
+    b, e = D.shard_bounds(M, rank, world)
+    loc = NumpyLocal(a[b:e], w[b:e], [v[b:e] for v in values], b)
+    gmax, gsum = D.fit_sharded(loc)
+    mu, sg, vn, wn = D.marginals_sharded(loc, list(range(len(values))))
+    q.put((rank, b, e, loc.density, mu.numpy(), sg.numpy(), vn.numpy(), wn.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_combine_matches_oracle(O, jp, world):
+    import torch.multiprocessing as mp
+    rng = np.random.default_rng(5)
+    M = 1001
+    a = rng.standard_normal(M) * 3
+    w = rng.random(M) + 0.05              # signed quadrature weights: 10 % negative
+    w[rng.random(M) < 0.1] *= -1
+    # value columns: continuous, heavily tied (coordinate-marginal like), and ties straddling the shard cut
+    v0 = rng.standard_normal(M)
+    v1 = np.round(rng.standard_normal(M) * 2) / 2
+    v2 = np.sort(np.round(rng.standard_normal(M) * 4) / 4)
+    values = [v0, v1, v2]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, a, w, values, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    dens = np.concatenate([r[3] for r in res])
+    e = w * np.exp(a - a.max())
+    assert np.allclose(dens, e / e.sum(), rtol=1e-13, atol=0)
+    for r in res[1:]:                      # every rank holds bit-identical results
+        for x, y in zip(r[4:], res[0][4:]):
+            assert np.array_equal(x, y, equal_nan=True)
+    _, _, _, _, mu, sg, vn, wn = res[0]
+    for k, v in enumerate(values):
+        m = O.marginal(v, dens)
+        assert np.isclose(mu[k], m["mu"], rtol=1e-11, atol=1e-13)
+        assert np.isclose(sg[k], m["sigma"], rtol=1e-10, equal_nan=True)
+        assert np.allclose(vn[k], m["value_nodes"], rtol=1e-15, atol=1e-15)
+        assert np.allclose(wn[k], m["weight_nodes"], rtol=1e-10, atol=1e-12), np.max(np.abs(wn[k] - m["weight_nodes"]))
+
+
+def test_shard_bounds(jp):
+    from jointposteriors_jl_b200.distributed import shard_bounds
+    for M, W in [(10, 3), (1001, 8), (8, 8), (45201, 8)]:
+        cuts = [shard_bounds(M, r, W) for r in range(W)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == M
+        assert all(cuts[i][1] == cuts[i + 1][0] for i in range(W - 1))
+        sizes = [e - b for b, e in cuts]
+        assert max(sizes) - min(sizes) <= 1
