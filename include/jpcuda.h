@@ -44,7 +44,14 @@ typedef enum jp_status {
 enum { JP_RULE_GENZ_KEISTER = 0, JP_RULE_KRONROD_PATTERSON = 1 };
 /* constraint transforms (ConstrainedParameters RealVector / PositiveVector / ProbabilityVector,
  * reference src/JointPosteriors.jl:22-26, README.md:32,247-248) -- one code per unconstrained coordinate */
-enum { JP_T_REAL = 0, JP_T_POSITIVE = 1, JP_T_PROBABILITY = 2 };
+enum { JP_T_REAL = 0, JP_T_POSITIVE = 1, JP_T_PROBABILITY = 2, JP_T_NONCENTRED = 3 };
+/* JP_T_NONCENTRED couples coordinate k to two EARLIER constrained coordinates: theta_k = theta_loc + theta_scale * x_k,
+ * log|J| += log(theta_scale); loc and scale travel in the code word (hierarchical models whose centred
+ * parameterisation has no joint mode, e.g. eight schools).  Transforms are applied in coordinate order. */
+#define JP_T_NONCENTRED_CODE(loc, scale) (JP_T_NONCENTRED | ((loc) << 8) | ((scale) << 16))
+#define JP_T_KIND(code) ((code) & 0xFF)
+#define JP_T_LOC(code) (((code) >> 8) & 0xFF)
+#define JP_T_SCALE(code) (((code) >> 16) & 0xFF)
 /* likelihood families registered in the library (device-function plugins, csrc/jp_family.cuh) */
 enum {
   JP_FAM_BINOMIAL_MIXTURE = 0, /* README Example 1, reference README.md:62-72 */

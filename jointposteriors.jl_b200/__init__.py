@@ -10,11 +10,11 @@ from .linalg import chol, deduce_scale_dynamic, inv_chol, inv_upper, reduce_dime
 from .marginals import Grid, cdf, marginal, marginals, quantile
 from .model import (Context, DeviceData, Dynamic, FixedRank, Full, GenzKeister, JointPosterior, JointPosteriorRaw,
                     KronrodPatterson, Model, Smolyak, SmolyakRaw, default, fit, log_density_unc, mode)
-from .params import PositiveVector, ProbabilityVector, RealVector, parameter
+from .params import NonCentredVector, PositiveVector, ProbabilityVector, RealVector, parameter
 
 __all__ = [
     "Model", "fit", "marginal", "marginals", "mode", "quantile", "cdf", "Grid", "JointPosterior", "JointPosteriorRaw",
-    "parameter", "RealVector", "PositiveVector", "ProbabilityVector", "Data", "BinaryClassificationData",
+    "parameter", "RealVector", "PositiveVector", "ProbabilityVector", "NonCentredVector", "Data", "BinaryClassificationData",
     "LogisticData", "PoissonData", "HierNormalData", "NormalLinearData", "Smolyak", "SmolyakRaw", "GenzKeister",
     "KronrodPatterson", "Dynamic", "Full", "FixedRank", "default", "Context", "DeviceData", "chol", "try_chol",
     "inv_upper", "inv_chol", "reduce_dimensions", "deduce_scale_dynamic", "JPError", "NotPositiveDefinite",

@@ -100,8 +100,26 @@ jp_fit_nodes_kernel(const JpFitLaunchParams P) {
     }
     double lj = 0.0;
 #pragma unroll
-    for (int k = 0; k < DPAD; ++k)
-      if (k < P.d) th[k] = jp_transform(s_code[k], th[k], lj);
+    for (int k = 0; k < DPAD; ++k) {
+      if (k < P.d) {
+        const int code = s_code[k];
+        if (JP_T_KIND(code) == JP_T_NONCENTRED) {
+          // theta_k = theta_loc + theta_scale * x_k with loc, scale < k already transformed; the register
+          // array is searched with compile-time indices so that it never spills to local memory
+          const int il = JP_T_LOC(code), is = JP_T_SCALE(code);
+          double loc = 0.0, sc = 1.0;
+#pragma unroll
+          for (int j = 0; j < k; ++j) {
+            if (j == il) loc = th[j];
+            if (j == is) sc = th[j];
+          }
+          th[k] = fma(sc, th[k], loc);
+          lj += log(sc);
+        } else {
+          th[k] = jp_transform(code, th[k], lj);
+        }
+      }
+    }
     if (blockIdx.y == 0) {
 #pragma unroll
       for (int k = 0; k < DPAD; ++k)
@@ -244,14 +262,25 @@ static int upload_fit_consts(jp_posterior* post, const jp_fit_args* args) {
   return JP_OK;
 }
 
+int jp_check_transform_codes(const char* who, const int* code, int d) {
+  for (int k = 0; k < d; ++k) {
+    int kind = JP_T_KIND(code[k]);
+    JP_REQUIRE(kind >= 0 && kind <= JP_T_NONCENTRED && (kind == JP_T_NONCENTRED || code[k] == kind),
+               "%s: unknown transform code %d at coordinate %d", who, code[k], k);
+    if (kind == JP_T_NONCENTRED)
+      JP_REQUIRE(JP_T_LOC(code[k]) < k && JP_T_SCALE(code[k]) < k && (code[k] >> 24) == 0,
+                 "%s: non-centred coordinate %d must refer to earlier coordinates (loc %d, scale %d)", who, k,
+                 JP_T_LOC(code[k]), JP_T_SCALE(code[k]));
+  }
+  return JP_OK;
+}
+
 int jp_fit_check_args(const jp_posterior* post, const jp_fit_args* args) {
   JP_REQUIRE(post && args, "jp_fit: null argument");
   JP_REQUIRE(args->d == post->d && args->p == post->p, "jp_fit: (d,p)=(%d,%d) differs from the posterior's (%d,%d)",
              args->d, args->p, post->d, post->p);
   JP_REQUIRE(args->h_transform && args->h_mu_hat && args->h_U, "jp_fit: null host array");
-  for (int k = 0; k < args->d; ++k)
-    JP_REQUIRE(args->h_transform[k] >= 0 && args->h_transform[k] <= 2, "jp_fit: unknown transform code %d",
-               args->h_transform[k]);
+  JP_TRY(jp_check_transform_codes("jp_fit", args->h_transform, args->d));
   return JP_OK;
 }
 
@@ -314,8 +343,7 @@ int jp_log_density_points(jp_ctx* ctx, const jp_data* data, int d, const int* h_
   JP_REQUIRE(fam != nullptr, "jp_log_density_points: family %d is not registered", data->family);
   JP_REQUIRE(fam->shape_ok(d, data->ncols, data->N), "jp_log_density_points: family %s does not accept d=%d ncols=%d N=%lld",
              fam->name, d, data->ncols, data->N);
-  for (int k = 0; k < d; ++k)
-    JP_REQUIRE(h_transform[k] >= 0 && h_transform[k] <= 2, "jp_log_density_points: unknown transform code %d", h_transform[k]);
+  JP_TRY(jp_check_transform_codes("jp_log_density_points", h_transform, d));
   JP_CUDA(cudaSetDevice(ctx->device));
   const int splits = 1;
   double *d_x = nullptr, *d_theta = nullptr, *d_part = nullptr, *d_out = nullptr;

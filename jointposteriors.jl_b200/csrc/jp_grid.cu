@@ -278,8 +278,11 @@ int jp_grid_build(jp_ctx* ctx, int rule, int d, int level, jp_grid* g) {
   JpRule R = jp_get_rule(rule);
   const int cap = std::min(level, R.levels);
   const int q = level + d - 1;
-  const int smin = std::max(d, q - d + 1);
-  const int smax = q;
+  // non-zero combination coefficients need |i|_1 >= q - d + 1, or the all-cap index when the level
+  // outruns the rule table (then the grid is the full tensor product of the highest rules)
+  int smin = std::max(d, q - d + 1);
+  int smax = std::min(q, d * cap);
+  if (smax < smin) smin = smax = d * cap;
   // restricted-composition counts comp[k][s], k parts in [1,cap]
   std::vector<unsigned long long> comp((size_t)(d + 1) * (smax + 1), 0ull);
   comp[0] = 1;  // zero parts, sum zero

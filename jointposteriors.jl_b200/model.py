@@ -213,28 +213,44 @@ def _richardson_grad_hess(fbatch, x, h=2e-3):
     return f0, (4 * g2 - g1) / 3, (4 * H2 - H1) / 3
 
 
-def _newton_mode_generic(M, ddata, x0, iters=100):
+def _newton_mode_generic(M, ddata, x0, iters=200):
+    """Saddle-free Newton on the GPU-evaluated negative log-density (derivatives by Richardson finite
+    differences, every stencil one batched jp_log_density_points call).  The Hessian's eigenvalues are
+    replaced by their absolute values so that indefinite regions are descended, and at a stationary
+    point with negative curvature the iterate leaves along the most negative eigenvector."""
     f = lambda X: -log_density_unc(M, ddata, X)   # objective: negative log-density, as minimised by optBFGS!
     x = np.array(x0, dtype=np.float64)
     fx = f(x[None])[0]
     for _ in range(iters):
         _, g, H = _richardson_grad_hess(f, x)
-        try:
-            step = -np.linalg.solve(H, g)
-            if g @ step > 0:
-                step = -g
-        except np.linalg.LinAlgError:
-            step = -g
-        t = 1.0
-        while t > 1e-10:
+        lam, V = np.linalg.eigh(H)
+        scale = max(np.max(np.abs(lam)), 1e-300)
+        gnorm = np.max(np.abs(g))
+        if lam[0] < -1e-8 * scale and gnorm < 1e-6 * scale:
+            cands = [x + t * sgn * V[:, 0] for sgn in (1.0, -1.0) for t in (1.0, 0.25)]
+            fc = f(np.array(cands))
+            k = int(np.nanargmin(np.where(np.isfinite(fc), fc, np.inf)))
+            if not (np.isfinite(fc[k]) and fc[k] < fx):
+                break
+            x, fx = cands[k], fc[k]
+            continue
+        lam_mod = np.maximum(np.abs(lam), 1e-10 * scale)
+        step = -V @ ((V.T @ g) / lam_mod)
+        nrm = np.max(np.abs(step))
+        if nrm > 10.0:
+            step *= 10.0 / nrm
+        t, fn = 1.0, fx
+        while t > 1e-12:
             fn = f((x + t * step)[None])[0]
             if np.isfinite(fn) and fn <= fx:
                 break
             t *= 0.5
+        if not (np.isfinite(fn) and fn <= fx):
+            break
         x = x + t * step
         done = abs(fx - fn) <= 1e-15 * (1 + abs(fx)) and np.max(np.abs(t * step)) < 1e-9 * (1 + np.max(np.abs(x)))
         fx = fn
-        if done:
+        if done and lam[0] > 0:
             break
     fx, g, H = _richardson_grad_hess(f, x)
     return x, H, fx

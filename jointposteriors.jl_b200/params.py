@@ -10,7 +10,7 @@ the per-coordinate transform codes of include/jpcuda.h and gives names to slices
 """
 import numpy as np
 
-T_REAL, T_POSITIVE, T_PROBABILITY = 0, 1, 2
+T_REAL, T_POSITIVE, T_PROBABILITY, T_NONCENTRED = 0, 1, 2, 3
 
 
 class _Block:
@@ -41,6 +41,22 @@ class ProbabilityVector(_Block):
     code = T_PROBABILITY
 
 
+class NonCentredVector(_Block):
+    """theta_k = theta[loc] + theta[scale] * x_k, log|J| = n log(theta[scale]): the non-centred
+    parameterisation of a hierarchical block.  `loc` and `scale` are flat indices of EARLIER constrained
+    coordinates.  (Not a ConstrainedParameters type: the centred eight-schools posterior of BASELINE
+    config 2 has no joint mode -- its density is unbounded as tau -> 0 -- so a Laplace-centred grid needs it.)"""
+    code = T_NONCENTRED
+
+    def __init__(self, n, loc=0, scale=1):
+        super().__init__(n)
+        self.loc, self.scale = int(loc), int(scale)
+
+    @property
+    def code_word(self):
+        return T_NONCENTRED | (self.loc << 8) | (self.scale << 16)
+
+
 class parameter:
     """Base class for the struct API: subclasses list their blocks as class attributes, in order.
 
@@ -61,11 +77,11 @@ def blocks_of(spec):
         spec = (spec,)
     if isinstance(spec, (tuple, list)) and all(isinstance(b, _Block) for b in spec) and len(spec) > 0:
         return [("p%d" % (i + 1), b) for i, b in enumerate(spec)]
-    raise TypeError("model must be a parameter subclass or a tuple of RealVector/PositiveVector/ProbabilityVector")
+    raise TypeError("model must be a parameter subclass or a tuple of RealVector/PositiveVector/ProbabilityVector/NonCentredVector")
 
 
 def transform_codes(blocks):
-    return np.concatenate([np.full(b.n, b.code, dtype=np.int32) for _, b in blocks])
+    return np.concatenate([np.full(b.n, getattr(b, "code_word", b.code), dtype=np.int32) for _, b in blocks])
 
 
 class ParamView:

@@ -6,7 +6,7 @@ bench arms rebuild identical data without communication.
 import numpy as np
 
 from .data import BinaryClassificationData, HierNormalData, LogisticData, PoissonData
-from .params import PositiveVector, ProbabilityVector, RealVector
+from .params import NonCentredVector, PositiveVector, ProbabilityVector, RealVector
 
 
 def _rng(seed):
@@ -21,7 +21,7 @@ def cfg1_binary_classification():
 
 def cfg2_eight_schools():
     data = HierNormalData([28, 8, -3, 7, -1, 1, 18, 12], [15, 10, 16, 11, 9, 11, 10, 18], tau_scale=25.0)
-    return dict(name="cfg2", params=(RealVector(1), PositiveVector(1), RealVector(8)), data=data, level=5, d=10)
+    return dict(name="cfg2", params=(RealVector(1), PositiveVector(1), NonCentredVector(8, loc=0, scale=1)), data=data, level=5, d=10)
 
 
 def _glm(seed, d, N, kind, xscale=1.0, chunk=1 << 20):

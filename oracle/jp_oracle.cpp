@@ -251,11 +251,19 @@ static void rec_compositions(int k, int d, int rem, int cap, int q, std::vector<
     rec_compositions(k + 1, d, rem - v, cap, q, cur, out);
   }
 }
+// A coefficient is non-zero only when q - |i|_1 < n <= d, i.e. |i|_1 >= q - d + 1, or when i is the
+// all-cap index (n = 0).  When the level outruns the rule table so far that d*cap < q - d + 1 the
+// index set is the full box and the grid degenerates to the tensor product of the highest rules.
+static void sum_range(int d, int q, int cap, int* smin, int* smax) {
+  *smin = std::max(d, q - d + 1);
+  *smax = std::min(q, d * cap);
+  if (*smax < *smin) *smin = *smax = d * cap;
+}
 static void enumerate_multi_indices(int d, int L, int cap, MultiIndexSet& out) {
-  int q = L + d - 1;
-  int smin = std::max(d, q - d + 1);
+  int q = L + d - 1, smin, smax;
+  sum_range(d, q, cap, &smin, &smax);
   std::vector<int> cur(d);
-  for (int s = smin; s <= q; ++s) rec_compositions(0, d, s, cap, q, cur, out);
+  for (int s = smin; s <= smax; ++s) rec_compositions(0, d, s, cap, q, cur, out);
 }
 
 // Number of pre-merge tensor-product points and multi-indices (for sizing / reporting).
@@ -343,9 +351,19 @@ static inline double transform_one(int code, double x, double* lj) {
   return x;
 }
 
+// code 3 (kind in the low byte, loc in bits 8-15, scale in bits 16-23): non-centred coordinate
+//        theta_k = theta_loc + theta_scale * x_k, log|J| += log(theta_scale); loc, scale < k.
 void orc_transform(const int* code, int d, const double* x, double* theta, double* logjac) {
   double lj = 0;
-  for (int k = 0; k < d; ++k) theta[k] = transform_one(code[k], x[k], &lj);
+  for (int k = 0; k < d; ++k) {
+    if ((code[k] & 0xFF) == 3) {
+      double loc = theta[(code[k] >> 8) & 0xFF], sc = theta[(code[k] >> 16) & 0xFF];
+      theta[k] = loc + sc * x[k];
+      lj += std::log(sc);
+    } else {
+      theta[k] = transform_one(code[k], x[k], &lj);
+    }
+  }
   *logjac = lj;
 }
 

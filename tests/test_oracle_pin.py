@@ -281,3 +281,34 @@ def test_smolyak_order_is_lexicographic(O):
     idx, _ = O.smolyak(0, 4, 4)
     keys = [tuple(r) for r in idx.tolist()]
     assert keys == sorted(keys)
+
+
+def test_noncentred_transform_and_eight_schools_mode(O):
+    """JP_T_NONCENTRED (theta_k = theta_loc + theta_scale x_k): the Jacobian matches finite differences and the
+    non-centred eight-schools posterior (BASELINE config 2) has a proper mode with a positive-definite Hessian."""
+    nc = 3 | (0 << 8) | (1 << 16)
+    code = [0, 1] + [nc] * 8
+    x = np.array([0.3, -0.4, 1.0, -2.0, 0.5, 0.0, 0.1, 0.2, -0.3, 0.7])
+    th, lj = O.transform(code, x)
+    assert np.allclose(th[:2], [0.3, np.exp(-0.4)]) and np.allclose(th[2:], 0.3 + np.exp(-0.4) * x[2:])
+    J = np.zeros((10, 10))
+    for k in range(10):
+        e = np.zeros(10)
+        e[k] = 1e-6
+        J[:, k] = (O.transform(code, x + e)[0] - O.transform(code, x - e)[0]) / 2e-6
+    assert abs(np.log(abs(np.linalg.det(J))) - lj) < 1e-8
+    ys = np.array([28, 8, -3, 7, -1, 1, 18, 12.0])
+    ss = np.array([15, 10, 16, 11, 9, 11, 10, 18.0])
+    obs, hyper = np.column_stack([ys, ss]), np.array([25.0])
+    xm, H, fmin = cpu_mode(O, 3, code, obs, hyper, [4.0, 1.0] + [0.0] * 8)
+    assert np.all(np.linalg.eigvalsh(H) > 0) and np.isfinite(fmin)
+    th, _ = O.transform(code, xm)
+    assert 1.0 < th[1] < 100 and 0 < th[0] < 20
+
+
+def test_level_beyond_rule_table(O):
+    """When the level outruns the 5-level Genz-Keister table the grid saturates to the full tensor rule."""
+    idx, w = O.smolyak(0, 1, 9)
+    assert len(w) == 35 and abs(w.sum() - 1) < 1e-13
+    idx, w = O.smolyak(0, 2, 11)
+    assert len(w) == 35 * 35 and abs(w.sum() - 1) < 1e-12

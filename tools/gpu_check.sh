@@ -4,7 +4,7 @@
 TAG=${1:-r01}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_gpu.txt 2>&1
-timeout 1500 python -m pytest tests -q -m gpu -p no:cacheprovider 2>&1 | tail -60 > gpurun_out/${TAG}_pytest.log
+timeout 1500 python -m pytest tests -q -m gpu -p no:cacheprovider --tb=short 2>&1 | tail -400 > gpurun_out/${TAG}_pytest.log
 echo "pytest exit ${PIPESTATUS[0]}" >> gpurun_out/${TAG}_pytest.log
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1
 echo "smoke exit $?" >> gpurun_out/${TAG}_smoke.log
