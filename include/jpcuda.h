@@ -214,7 +214,7 @@ int jp_marginal_sorted(jp_posterior* post, int k, double* h_sorted_values, doubl
  *     interior knot i = 1..98 writes d_out[(k*98 + i-1)*6 + {0..5}] =
  *       (S = sum of w over v <= x_i,  pred = max v <= x_i (-inf if none),
  *        succ = min v > x_i (+inf if none), global index of the lowest-index element attaining succ,
- *        its weight, 0)
+ *        its weight, the knot value x_i)
  *   the host combines over ranks (jointposteriors.jl_b200.distributed) into the 100-knot Grid.
  * h_coords may be NULL when d_values (K x M_local, device) is given instead. */
 int jp_marginal_local_moments(jp_posterior* post, int K, const int* h_coords, const double* d_values, double* d_out);

@@ -19,10 +19,27 @@
 #define JP_MOUT_STRIDE (2 + 2 * JP_GRID_KNOTS + 2)   // mu, sigma, value_nodes, weight_nodes, min, max
 
 __device__ __forceinline__ double jp_knot_value(double vmin, double vmax, int i) {
-  // i-th of 100 equispaced knots; end knots exact (linspace semantics, interp.jl:450)
+  // i-th of 100 equispaced knots, end knots exact (linspace semantics, interp.jl:450).  Julia builds the
+  // range in twice precision, so interior knots are the correctly rounded vmin + (i/99)(vmax - vmin);
+  // double-double arithmetic reproduces that here.
   if (i <= 0) return vmin;
   if (i >= JP_GRID_KNOTS - 1) return vmax;
-  return fma((double)i / (double)(JP_GRID_KNOTS - 1), vmax - vmin, vmin);
+  const double n = (double)(JP_GRID_KNOTS - 1);
+  // d = vmax - vmin as (dh, dl)
+  double dh = vmax - vmin;
+  double bv = dh - vmax;
+  double dl = (vmax - (dh - bv)) + (-vmin - bv);
+  // t = i / 99 as (th, tl)
+  double th = (double)i / n;
+  double tl = fma(-th, n, (double)i) / n;
+  // p = t * d
+  double ph = th * dh;
+  double pl = fma(th, dh, -ph) + (th * dl + tl * dh);
+  // vmin + p
+  double sh = vmin + ph;
+  double bs = sh - vmin;
+  double sl = (vmin - (sh - bs)) + (ph - bs);
+  return sh + (sl + pl);
 }
 
 // one block per marginal: (sum w v, sum w v^2, min v, max v); contiguous chunk per thread, fixed tree
@@ -157,7 +174,6 @@ __global__ void __launch_bounds__(256)
 jp_local_knots_kernel(const double* const* __restrict__ vptr, const double* __restrict__ w, long long M,
                       long long m0, const double* __restrict__ minmax, double* __restrict__ out) {
   __shared__ double sm[33];
-  __shared__ unsigned long long s_succ;
   __shared__ unsigned long long s_idx;
   const int k = blockIdx.y, i = blockIdx.x + 1;
   const double* v = vptr[k];
@@ -191,9 +207,8 @@ jp_local_knots_kernel(const double* const* __restrict__ vptr, const double* __re
     o[0] = S; o[1] = pred; o[2] = succ;
     o[3] = (s_idx == ~0ull) ? INFINITY : (double)s_idx;
     o[4] = (s_idx == ~0ull) ? 0.0 : w[(long long)s_idx - m0];
-    o[5] = 0.0;
+    o[5] = x;
   }
-  (void)s_succ;
 }
 
 // ------------------------------------------------------------------------------------ host side

@@ -39,12 +39,13 @@ def _all_gather(t, group):
     return out
 
 
-def knot_values(vmin, vmax):
-    """The 100 equispaced value knots, computed exactly as the device does (fma(i/99, max-min, min))."""
+def knot_values(gathered, vmin, vmax):
+    """The 100 value knots [K, 100]: end knots are the global extrema, interior knots are the values the
+    device computed (slot 5 of every rank's candidates; all ranks derive them from the same (min, max))."""
     import torch
-    i = torch.arange(GRID_KNOTS, dtype=torch.float64, device=vmin.device)
-    t = i / float(GRID_KNOTS - 1)
-    x = torch.addcmul(vmin[:, None], t[None, :], (vmax - vmin)[:, None])
+    K = vmin.shape[0]
+    x = torch.empty((K, GRID_KNOTS), dtype=torch.float64, device=vmin.device)
+    x[:, 1:-1] = gathered[0, :, :, 5]
     x[:, 0] = vmin
     x[:, -1] = vmax
     return x
@@ -67,7 +68,7 @@ def combine_knots(gathered, vmin, vmax):
     idx = torch.where(is_min, gathered[..., 3], torch.full_like(gathered[..., 3], float("inf")))
     owner = idx.argmin(dim=0, keepdim=True)
     succ_w = torch.gather(gathered[..., 4], 0, owner)[0]
-    x = knot_values(vmin, vmax)[:, 1:-1]
+    x = gathered[0, :, :, 5]
     fx = (x - pred) / (succ - pred)
     inner = tot * (1.0 - fx) + (tot + succ_w) * fx
     K = inner.shape[0]
@@ -152,7 +153,7 @@ def marginals_sharded(local, coords, group=None, gather=None):
     cand = local.knots(coords, minmax)                # [K, 98, 6]
     gathered = gather(cand, group)                    # [world, K, 98, 6]
     wn = combine_knots(gathered, vmin, vmax)
-    vn = knot_values(vmin, vmax)
+    vn = knot_values(gathered, vmin, vmax)
     mu = s1
     sigma = torch.sqrt(s2 - s1 * s1)
     return mu, sigma, vn, wn

@@ -118,8 +118,10 @@ def marginals(jp, fs):
         view = jp.view()
         vals = np.zeros((K, jp.n_nodes))
         for j, (_, f) in enumerate(host):
-            v = f(view)
-            vals[j] = np.broadcast_to(np.asarray(v, dtype=np.float64), (jp.n_nodes,))
+            v = np.asarray(f(view), dtype=np.float64)
+            if v.size == jp.n_nodes:
+                v = v.reshape(-1)
+            vals[j] = np.broadcast_to(v, (jp.n_nodes,))
         mu, sg = np.zeros(K), np.zeros(K)
         vn, wn = np.zeros((K, GRID_KNOTS)), np.zeros((K, GRID_KNOTS))
         check(L.jp_marginal_values(jp.handle, C.c_int(K), ptr(vals), ptr(mu), ptr(sg), ptr(vn), ptr(wn)))

@@ -55,8 +55,7 @@ class NumpyLocal:
         for j, k in enumerate(coords):
             v = self.values[k]
             for i in range(1, 99):
-                x = mm[j, 0] + (i / 99.0) * (mm[j, 1] - mm[j, 0])
-                x = float(np.float64(np.add(mm[j, 0], np.multiply(i / 99.0, mm[j, 1] - mm[j, 0]))))
+                x = float(np.longdouble(mm[j, 0]) + (np.longdouble(i) / np.longdouble(99)) * (np.longdouble(mm[j, 1]) - np.longdouble(mm[j, 0])))
                 le = v <= x
                 S = self.density[le].sum()
                 pred = v[le].max() if le.any() else -np.inf
@@ -64,9 +63,9 @@ class NumpyLocal:
                 if gt.any():
                     succ = v[gt].min()
                     jj = int(np.nonzero(v == succ)[0][0])
-                    out[j, i - 1] = [S, pred, succ, self.m0 + jj, self.density[jj], 0]
+                    out[j, i - 1] = [S, pred, succ, self.m0 + jj, self.density[jj], x]
                 else:
-                    out[j, i - 1] = [S, pred, np.inf, np.inf, 0, 0]
+                    out[j, i - 1] = [S, pred, np.inf, np.inf, 0, x]
         return self._t(out)
 
 

@@ -16,6 +16,13 @@ TOL64 = 1e-10
 PROBS = (0.025, 0.25, 0.5, 0.75, 0.975)
 
 
+def knots_close(a, b):
+    """value knots agree to one ulp of the range's magnitude (both sides round the exact lerp; the device in
+    double-double, the oracle in x87 long double)"""
+    a, b = np.asarray(a), np.asarray(b)
+    return bool(np.all(np.abs(a - b) <= np.spacing(max(abs(b[0]), abs(b[-1])))))
+
+
 # ------------------------------------------------------------------------------ stage 1
 GRID_CASES = [(0, 1, 1), (0, 1, 5), (0, 1, 9), (0, 2, 3), (0, 3, 5), (0, 3, 7), (0, 3, 12), (1, 3, 6), (1, 2, 8),
               (0, 5, 4), (0, 10, 5), (0, 10, 6), (0, 20, 3), (0, 30, 2), (0, 30, 4), (1, 10, 4), (0, 64, 2)]
@@ -139,7 +146,7 @@ def _check_fit_and_marginals(jp, O, gpu_ctx, family, code, obs, hyper, rule, lev
         mo = O.marginal(ref["theta"][k], ref["density"], want_sorted=True)
         assert abs(m.mu - mo["mu"]) <= tol * max(abs(mo["mu"]), 1e-3)
         assert abs(m.sigma - mo["sigma"]) <= 10 * tol * abs(mo["sigma"])
-        assert np.allclose(m.itp.values, mo["value_nodes"], rtol=1e-14, atol=1e-300)
+        assert knots_close(m.itp.values, mo["value_nodes"])
         assert np.max(np.abs(m.itp.weights - mo["weight_nodes"])) < tol * 10
         for p in PROBS:
             q, qo = jp.quantile(m, p), O.quantile(mo["weight_nodes"], mo["value_nodes"], p)
@@ -324,12 +331,12 @@ def test_sharded_phases_match_single(jp, O, gpu_ctx, world):
     minmax = torch.stack([vmin, vmax], dim=1).contiguous()
     cand = torch.stack([l.knots(coords, minmax) for l in locs])
     wn = D.combine_knots(cand, vmin, vmax).cpu().numpy()
-    vn = D.knot_values(vmin, vmax).cpu().numpy()
+    vn = D.knot_values(cand, vmin, vmax).cpu().numpy()
     mu = g[:, :, 0].sum(dim=0).cpu().numpy()
     ms = jp.marginals(full, coords)
     for k in range(d):
         assert abs(mu[k] - ms[k].mu) < 1e-12 * max(1.0, abs(ms[k].mu))
-        assert np.allclose(vn[k], ms[k].itp.values, rtol=1e-15, atol=1e-300)
+        assert np.array_equal(vn[k], ms[k].itp.values)
         assert np.max(np.abs(wn[k] - ms[k].itp.weights)) < 1e-11, k
 
 

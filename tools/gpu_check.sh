@@ -11,3 +11,12 @@ echo "smoke exit $?" >> gpurun_out/${TAG}_smoke.log
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 echo "bench exit $?" >> gpurun_out/${TAG}_bench.err
 tail -5 gpurun_out/${TAG}_pytest.log; cat gpurun_out/${TAG}_smoke.log | tail -5; cat gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err
+if [ "${NCU:-0}" = "1" ]; then
+  BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --path ${NCU_PATH:-auto}"
+  $BENCH > gpurun_out/${TAG}_ncu_plain.log 2>&1 &&
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv $BENCH > gpurun_out/${TAG}_ncu_list.log 2>&1
+  echo "ncu list exit $?"
+  $BENCH > gpurun_out/${TAG}_ncu_plain2.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-jp_fit_nodes_kernel} -s 3 -c 1 -f -o gpurun_out/${TAG}_prof $BENCH > gpurun_out/${TAG}_ncu_full.log 2>&1
+  echo "ncu full exit $?"
+fi
