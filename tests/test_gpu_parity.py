@@ -20,7 +20,8 @@ def knots_close(a, b):
     """value knots agree to one ulp of the range's magnitude (both sides round the exact lerp; the device in
     double-double, the oracle in x87 long double)"""
     a, b = np.asarray(a), np.asarray(b)
-    return bool(np.all(np.abs(a - b) <= np.spacing(max(abs(b[0]), abs(b[-1])))))
+    slack = abs(a[0] - b[0]) + abs(a[-1] - b[-1])     # the end knots are data values (theta extrema)
+    return bool(np.all(np.abs(a - b) <= np.spacing(max(abs(b[0]), abs(b[-1]))) + slack))
 
 
 # ------------------------------------------------------------------------------ stage 1
