@@ -189,6 +189,11 @@ const double* jp_dev_theta(const jp_posterior* post);
 const double* jp_dev_density(const jp_posterior* post);
 /* which path the last jp_fit took (JP_PATH_FP64 or JP_PATH_TC) */
 int jp_fit_path_used(const jp_posterior* post);
+/* a-priori error figures of the tensor-core path for the last fit that tried it (csrc/jp_glm_tc.cu,
+ * jp_tc_choose_order): h_out8[0] = max |Delta eta| over (node, observation) pairs, [1] = truncation bound of the
+ * link-remainder series at |z| <= 6, [2] = statistical rounding estimate, [3] = series coefficients used
+ * (0 = bounds not met, FP64 kernel used), [4] = worst-case rounding bound; [5..7] reserved */
+int jp_fit_diagnostics(const jp_posterior* post, double* h_out8);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage 5 -- marginal(jp, f): weighted mean / sigma and the 100-knot Grid CDF.

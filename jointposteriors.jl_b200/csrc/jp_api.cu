@@ -164,7 +164,6 @@ int jp_data_free(jp_data* data) {
   cudaStreamSynchronize(data->ctx->stream);
   jp_tc_data_free(data);
   cudaFree(data->d_obs);
-  cudaFree(data->d_a3);
   delete data;
   return JP_OK;
 }
@@ -211,7 +210,7 @@ int jp_posterior_free(jp_posterior* p) {
   cudaSetDevice(p->ctx->device);
   cudaStreamSynchronize(p->ctx->stream);
   cudaFree(p->d_theta); cudaFree(p->d_a); cudaFree(p->d_logdens); cudaFree(p->d_density); cudaFree(p->d_part);
-  cudaFree(p->d_stats); cudaFree(p->d_mu); cudaFree(p->d_U); cudaFree(p->d_tcode); cudaFree(p->d_dtheta);
+  cudaFree(p->d_stats); cudaFree(p->d_mu); cudaFree(p->d_U); cudaFree(p->d_tcode); jp_tc_post_free(p);
   cudaFree(p->d_vals); cudaFree((void*)p->d_vptr); cudaFree(p->d_perm_a); cudaFree(p->d_perm_b); cudaFree(p->d_hist);
   cudaFree(p->d_sv); cudaFree(p->d_sw); cudaFree(p->d_cw); cudaFree(p->d_mout);
   delete p;
@@ -222,6 +221,11 @@ long long jp_posterior_size(const jp_posterior* p) { return p ? p->M : -1; }
 const double* jp_dev_theta(const jp_posterior* p) { return p ? p->d_theta : nullptr; }
 const double* jp_dev_density(const jp_posterior* p) { return p ? p->d_density : nullptr; }
 int jp_fit_path_used(const jp_posterior* p) { return p ? p->path_used : 0; }
+int jp_fit_diagnostics(const jp_posterior* p, double* h_out8) {
+  JP_REQUIRE(p && h_out8, "jp_fit_diagnostics: null argument");
+  for (int i = 0; i < 8; ++i) h_out8[i] = p->tc_bounds[i];
+  return JP_OK;
+}
 
 static int download(jp_posterior* p, const double* d_src, double* h_dst, size_t n) {
   JP_REQUIRE(p && h_dst, "jp_get_*: null argument");

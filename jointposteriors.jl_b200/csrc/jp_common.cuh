@@ -84,12 +84,8 @@ struct jp_data {
   double* d_obs = nullptr;      // N x ncols row-major
   double hyper[JP_MAX_HYPER] = {0};
   int n_hyper = 0;
-  // GLM tensor-core operand (built lazily): A' = [x_hi | x_lo | x_hi] in TF32-representable FP32,
-  // N_pad x kp row-major, kp = 3*d rounded up to a multiple of 32 (one 128-byte swizzle atom per 32)
-  float* d_a3 = nullptr;
-  int a3_kp = 0;
-  long long a3_rows = 0;
-  void* tc_state = nullptr;     // opaque per-data state of the TC path (tensor maps, per-obs coefficients)
+  void* tc_state = nullptr;     // per-data state of the GLM tensor-core path (jp_glm_tc.cu): the operand
+                                // [x_hi | x_lo | x_hi] in TF32-representable FP32, its TMA map, per-obs coefficients
 };
 
 struct jp_posterior {
@@ -105,7 +101,9 @@ struct jp_posterior {
   double* d_density = nullptr;   // normalised weights
   double* d_part = nullptr;      // (JP_POST_PART_SPLITS + 1) x M doubles, see below
   double* d_stats = nullptr;     // [0]=max, [1]=sum (device scalars for the single-GPU path)
-  double* d_dtheta = nullptr;    // TC path: U z per node, SoA [d][M] FP64 (centred offsets)
+  void* tc_state = nullptr;      // TC path: node operand, tensor map, quadratic part (jp_glm_tc.cu)
+  double tc_bounds[8] = {0};     // TC path diagnostics of the last fit: max|Delta|, truncation bound, rounding
+                                 // estimate, series coefficients used, worst-case rounding bound
   // per-fit constants on the device
   double* d_mu = nullptr;        // d
   double* d_U = nullptr;         // d x p column-major
@@ -199,6 +197,8 @@ int jp_fit_fp64_launch(jp_posterior* post, const jp_fit_args* args);   // stages
 int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args);     // stages 2-3, GLM tensor-core path
 bool jp_fit_tc_supported(const jp_posterior* post, const jp_fit_args* args);
 void jp_tc_data_free(jp_data* data);
+void jp_tc_post_free(jp_posterior* post);
+int jp_upload_fit_consts(jp_posterior* post, const jp_fit_args* args);   // mu_hat, U, transform codes -> device
 const double* jp_rule_nodes_dev(int rule);   // device copy of the master z-node table
 
 struct JpRule {

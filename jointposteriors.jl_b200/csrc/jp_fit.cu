@@ -237,7 +237,7 @@ JP_REGISTER_FAMILY(FamHierNormal)
 JP_REGISTER_FAMILY(FamNormalLinear)
 
 // ------------------------------------------------------------------------------------ host side
-static int upload_fit_consts(jp_posterior* post, const jp_fit_args* args) {
+int jp_upload_fit_consts(jp_posterior* post, const jp_fit_args* args) {
   jp_ctx* ctx = post->ctx;
   if (!g_fit_nodes_uploaded) {
     for (int r = 0; r < 2; ++r) {
@@ -292,7 +292,7 @@ int jp_fit_fp64_launch(jp_posterior* post, const jp_fit_args* args) {
   JP_REQUIRE(fam->shape_ok(args->d, data->ncols, data->N), "jp_fit: family %s does not accept d=%d ncols=%d N=%lld",
              fam->name, args->d, data->ncols, data->N);
   JP_REQUIRE(data->ncols <= JP_FIT_TILE_DOUBLES / 2, "jp_fit: %d columns per observation is too many", data->ncols);
-  JP_TRY(upload_fit_consts(post, args));
+  JP_TRY(jp_upload_fit_consts(post, args));
   JpFitLaunchParams lp;
   lp.d = args->d; lp.p = args->p; lp.ncols = data->ncols; lp.rule = post->grid->rule;
   lp.N = data->N; lp.M = post->M; lp.m0 = post->m0; lp.M_grid = post->grid->M;
@@ -387,15 +387,16 @@ int jp_log_density_points(jp_ctx* ctx, const jp_data* data, int d, const int* h_
 int jp_fit_local(jp_posterior* post, const jp_fit_args* args, double* d_local_max) {
   JP_TRY(jp_fit_check_args(post, args));
   JP_REQUIRE(d_local_max, "jp_fit_local: null output");
+  // AUTO: GLM families take the tensor-core path when its a-priori error bounds hold for this
+  // (data, U, grid); otherwise, and for every other family, the FP64 plugin kernel runs.
   int path = args->path;
   if (path == JP_PATH_AUTO) path = jp_fit_tc_supported(post, args) ? JP_PATH_TC : JP_PATH_FP64;
   if (path == JP_PATH_TC) {
-    JP_REQUIRE(jp_fit_tc_supported(post, args), "jp_fit: the tensor-core path does not support this model (%s)",
-               jp_last_error());
-    JP_TRY(jp_fit_tc_launch(post, args));
-  } else {
-    JP_TRY(jp_fit_fp64_launch(post, args));
+    int st = jp_fit_tc_launch(post, args);
+    if (st == JP_ERR_UNSUPPORTED && args->path == JP_PATH_AUTO) path = JP_PATH_FP64;
+    else JP_TRY(st);
   }
+  if (path == JP_PATH_FP64) JP_TRY(jp_fit_fp64_launch(post, args));
   jp_reduce_max_kernel<<<1, 1024, 0, post->ctx->stream>>>(post->d_a, post->M, d_local_max);
   JP_CHECK_LAUNCH(post->ctx);
   return JP_OK;

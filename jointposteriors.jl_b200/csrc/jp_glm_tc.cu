@@ -1,11 +1,795 @@
-// jp_glm_tc.cu -- GLM tensor-core log-density path (tcgen05 3xTF32).  Placeholder until the kernel lands.
+// jp_glm_tc.cu -- STAGES 2-3 for GLM families on the 5th-generation tensor cores (tcgen05 / TMEM / TMA).
+//
+// The hot loop of the reference is M grid nodes x N observations of the user's log_density
+// (reference src/joint_posterior.jl:147-154 called from eval_grid!, :180,186).  For a GLM that is the dense
+// contraction  eta = X Theta'  followed by a link-function term per (node, observation) pair.
+//
+// Centred form (mirrors the reference's own mode-centring `+ neg_min`, :149,153).  With theta_m = mu_hat +
+// delta_m, delta_m = U z_m, eta_hat_i = x_i . mu_hat and Delta_im = x_i . delta_m, a GLM log-likelihood
+// sum_i [ y_i eta_i - b(eta_i) ] expands EXACTLY into
+//     L_hat + g . delta_m - 1/2 delta_m' H delta_m - sum_i R_i(Delta_im)
+//     L_hat = sum_i y_i eta_hat_i - b(eta_hat_i),  g = X'(y - b'(eta_hat)),  H = X' diag(b''(eta_hat)) X      (FP64)
+//     R_i(D) = b(eta_hat_i + D) - b(eta_hat_i) - b'(eta_hat_i) D - 1/2 b''(eta_hat_i) D^2 = sum_{k>=3} c_{k,i} D^k
+// The FP64 pieces cost O(N d^2 + M d^2).  Only the third-order remainder needs the node x observation
+// product, and it is O(|Delta|^3) small, so FP32 arithmetic on a 3xTF32 contraction is ample: an error of
+// 1e-6 RELATIVE to R_i is ~1e-12 absolute per observation (see jp_tc_choose_order for the bounds that gate
+// the path; outside them the FP64 plugin kernel of jp_fit.cu is used).
+//
+// Kernel (one persistent CTA per SM, warp-specialised):
+//   warp 0      TMA producer: node-tile operand (256 nodes x K) once per work item, observation tiles
+//               (128 obs x K) through a ring of shared-memory stages; 128-byte swizzle, K-major
+//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::tf32, M = 128 (observations on TMEM lanes),
+//               N = 256 (nodes on TMEM columns), K = 8 per instruction; accumulators double-buffered in
+//               TMEM (2 x 256 columns); tcgen05.commit releases stages / publishes accumulators
+//   warps 2-9   epilogue: tcgen05.ld 16 columns at a time, R = D^3 (c3 + D (c4 + ...)) by Horner with the
+//               calling thread's own observation coefficients held in registers, accumulated per
+//               (thread = observation lane, column = node) in FP32 registers over all observation tiles of
+//               the item; per item one shuffle transpose-reduce + shared-memory combine in FP64.
+// 3xTF32: operand rows are [x_hi | x_lo | x_hi] and [d_hi | d_hi | d_lo] (TF32-representable FP32), so one
+// K = 3d contraction gives x_hi d_hi + x_lo d_hi + x_hi d_lo with FP32 accumulation in TMEM.
+#include <cuda.h>
+#include <algorithm>
+#include <cmath>
+#include <vector>
 #include "jp_common.cuh"
-bool jp_fit_tc_supported(const jp_posterior*, const jp_fit_args*) {
-  jp_set_error("tensor-core path not built");
-  return false;
+
+int jp_glm_sums_device(jp_ctx* ctx, const jp_data* data, int d, const double* d_beta, double* d_out, double* d_work,
+                       int nblocks);
+int jp_glm_num_blocks(const jp_ctx* ctx, long long N);
+
+#define TC_OBS_TILE 128          // MMA M: observations per tile (TMEM lanes)
+#define TC_NODE_TILE 256         // MMA N: nodes per tile (TMEM columns)
+#define TC_KATOM 32              // fp32 elements per 128-byte swizzle atom
+#define TC_NCMAX 12              // stored Taylor coefficients per observation: orders 3 .. 14
+#define TC_ORDER_MAX 16          // highest derivative order tabulated (tail bounds need two more than used)
+#define TC_THREADS 320           // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+#define TC_EPI_THREADS 256
+#define TC_MAX_STAGES 4
+#define TC_PREP_BLOCKS 296
+#define TC_NBOUND 10             // per-block bound partials, see tc_obs_prep_kernel
+
+// derivative polynomials of softplus in s = sigmoid(eta): f_1 = s, f_{k+1} = f_k'(s) (s - s^2)
+__constant__ double c_sp_poly[TC_ORDER_MAX + 1][TC_ORDER_MAX + 2];
+__constant__ double c_inv_fact[TC_ORDER_MAX + 2];
+
+struct TcDataState {
+  int d = 0, kp = 0, ka = 0;
+  long long N = 0, N_pad = 0;
+  float* d_xs = nullptr;       // [N_pad][kp]  (x_hi | x_lo | x_hi | 0)
+  float* d_coef = nullptr;     // [N_pad][TC_NCMAX]
+  double* d_sums = nullptr;    // packed (g[d], upper H[d(d+1)/2], L_hat)
+  double* d_work = nullptr;    // partials of the GLM sums
+  double* d_bounds = nullptr;  // [TC_PREP_BLOCKS][TC_NBOUND]
+  int glm_blocks = 0;
+  CUtensorMap tmA;
+};
+
+struct TcPostState {
+  long long M_pad = 0;
+  int kp = 0;
+  float* d_ds = nullptr;       // [M_pad][kp]  (d_hi | d_hi | d_lo | 0)
+  double* d_quad = nullptr;    // [M]
+  CUtensorMap tmB;
+};
+
+// ------------------------------------------------------------------------------------ small device helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r & 0xFFFFE000u);
 }
-int jp_fit_tc_launch(jp_posterior*, const jp_fit_args*) {
-  jp_set_error("tensor-core path not built");
-  return JP_ERR_UNSUPPORTED;
+__device__ __forceinline__ void tf32_split(double x, float& hi, float& lo) {
+  hi = tf32_round((float)x);
+  lo = tf32_round((float)(x - (double)hi));
 }
-void jp_tc_data_free(jp_data*) {}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// K-major, 128-byte swizzle: 8-row groups 1024 bytes apart (SBO), LBO unused (1), descriptor version 1
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t (&v)[16], uint32_t taddr) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// the registers are operands of the wait so that their uses cannot be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
+
+// ------------------------------------------------------------------------------------ operand preparation
+// X' = [x_hi | x_lo | x_hi | 0]: depends on the data only, built once per jp_data
+__global__ void tc_split_x_kernel(int d, int ncols, int kp, long long N, long long N_pad, const double* __restrict__ obs,
+                                  float* __restrict__ xs) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N_pad) return;
+  float* o = xs + (size_t)i * kp;
+  for (int k = 0; k < kp; ++k) o[k] = 0.f;
+  if (i >= N) return;
+  const double* r = obs + (size_t)i * ncols;
+  for (int k = 0; k < d; ++k) {
+    float hi, lo;
+    tf32_split(r[k], hi, lo);
+    o[k] = hi;
+    o[d + k] = lo;
+    o[2 * d + k] = hi;
+  }
+}
+
+// Per observation: eta_hat, Taylor coefficients c_3 .. c_14 of the link remainder, t = |U' x| (so that
+// |Delta| <= t |z|), and the ingredients of the order / eligibility decision reduced per block:
+//   [0] max_i t_i   [1] sum |c_3| t^3   [2+j], [5+j] (j = 0,1,2 <-> NC = 4, 8, 12): truncation tail bounds of
+//   the series stopped at order NC + 2, summed over observations at |z| = z_ref and |z| = z_max
+//   [8] sum_i |R_i| and [9] sum_i R_i^2 at |z| = z_ref (majorants)
+__global__ void __launch_bounds__(256)
+tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N_pad, const double* __restrict__ obs,
+                   const double* __restrict__ mu, const double* __restrict__ U, double z_ref, double z_max,
+                   float* __restrict__ coef, double* __restrict__ bounds) {
+  extern __shared__ double sh[];
+  double* s_mu = sh;            // d
+  double* s_U = sh + d;         // d x p column-major
+  __shared__ double red[33];
+  for (int k = threadIdx.x; k < d; k += blockDim.x) s_mu[k] = mu[k];
+  for (int k = threadIdx.x; k < d * p; k += blockDim.x) s_U[k] = U[k];
+  __syncthreads();
+  double b_tmax = 0, b_a1 = 0, b_ref[3] = {0, 0, 0}, b_max[3] = {0, 0, 0}, b_r = 0, b_r2 = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N_pad; i += (long long)gridDim.x * blockDim.x) {
+    float* o = coef + (size_t)i * TC_NCMAX;
+    if (i >= N) {
+      for (int k = 0; k < TC_NCMAX; ++k) o[k] = 0.f;
+      continue;
+    }
+    const double* r = obs + (size_t)i * ncols;
+    double eta = 0;
+    for (int k = 0; k < d; ++k) eta += r[k] * s_mu[k];
+    double t2 = 0;
+    for (int j = 0; j < p; ++j) {
+      double a = 0;
+      for (int k = 0; k < d; ++k) a += s_U[(size_t)j * d + k] * r[k];
+      t2 += a * a;
+    }
+    const double t = sqrt(t2);
+    double c[TC_ORDER_MAX + 1];   // c[k], k = 3 .. TC_ORDER_MAX
+    if (family == JP_FAM_LOGISTIC) {
+      const double s = 1.0 / (1.0 + exp(-eta));
+      for (int k = 3; k <= TC_ORDER_MAX; ++k) {
+        double v = c_sp_poly[k][k];
+        for (int j = k - 1; j >= 0; --j) v = fma(v, s, c_sp_poly[k][j]);
+        c[k] = v * c_inv_fact[k];
+      }
+    } else {
+      const double m = exp(eta);
+      for (int k = 3; k <= TC_ORDER_MAX; ++k) c[k] = m * c_inv_fact[k];
+    }
+    for (int k = 0; k < TC_NCMAX; ++k) o[k] = (float)c[3 + k];
+    // bounds
+    b_tmax = fmax(b_tmax, t);
+    b_a1 += fabs(c[3]) * t * t * t;
+    const double tr = t * z_ref, tm = t * z_max;
+    const double rho = (family == JP_FAM_LOGISTIC) ? 3.14159265358979323846 : 1e300;   // radius of convergence
+    double sr = 0;
+    for (int k = TC_ORDER_MAX; k >= 3; --k) sr = (sr + fabs(c[k])) * tr;
+    sr *= tr * tr;                                     // majorant of |R_i| at |z| = z_ref
+    b_r += sr;
+    b_r2 += sr * sr;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int K = 4 * (j + 1) + 2;                    // last order kept
+      // tail <= |c_{K+1}| t^{K+1} + |c_{K+2}| t^{K+2} / (1 - t / rho)   (geometric majorant of the remaining terms)
+      double gr = tr < rho ? 1.0 / (1.0 - tr / rho) : 1e300, gm = tm < rho ? 1.0 / (1.0 - tm / rho) : 1e300;
+      if (family != JP_FAM_LOGISTIC) { gr = exp(tr); gm = exp(tm); }
+      b_ref[j] += fabs(c[K + 1]) * pow(tr, K + 1) + fabs(c[K + 2]) * pow(tr, K + 2) * gr;
+      b_max[j] += fabs(c[K + 1]) * pow(tm, K + 1) + fabs(c[K + 2]) * pow(tm, K + 2) * gm;
+    }
+  }
+  double* ob = bounds + (size_t)blockIdx.x * TC_NBOUND;
+  double v = jp_block_max(b_tmax, red);
+  if (threadIdx.x == 0) ob[0] = v;
+  v = jp_block_sum(b_a1, red);
+  if (threadIdx.x == 0) ob[1] = v;
+  for (int j = 0; j < 3; ++j) {
+    v = jp_block_sum(b_ref[j], red);
+    if (threadIdx.x == 0) ob[2 + j] = v;
+    v = jp_block_sum(b_max[j], red);
+    if (threadIdx.x == 0) ob[5 + j] = v;
+  }
+  v = jp_block_sum(b_r, red);
+  if (threadIdx.x == 0) ob[8] = v;
+  v = jp_block_sum(b_r2, red);
+  if (threadIdx.x == 0) ob[9] = v;
+}
+
+// Per node: delta = U z, theta = mu + delta (all transforms are the identity on this path), the FP64
+// quadratic part  L_hat + g.delta - 1/2 delta' H delta + prior(theta),  and the operand row [d_hi | d_hi | d_lo | 0]
+__global__ void __launch_bounds__(128)
+tc_node_prep_kernel(int d, int p, int kp, int rule, long long M, long long m0, long long M_grid,
+                    const uint8_t* __restrict__ idx, const double* __restrict__ znodes, const double* __restrict__ mu,
+                    const double* __restrict__ U, const double* __restrict__ sums, double prior_sd,
+                    double* __restrict__ theta, double* __restrict__ quad, float* __restrict__ ds) {
+  extern __shared__ double sh[];
+  double* s_mu = sh;                  // d
+  double* s_U = s_mu + d;             // d x p
+  double* s_g = s_U + d * p;          // d
+  double* s_H = s_g + d;              // d x d (full, symmetric)
+  double* s_z = s_H + d * d;          // 64
+  double* s_dl = s_z + 64;            // blockDim.x x d  (delta of each thread, strided by thread)
+  for (int k = threadIdx.x; k < d; k += blockDim.x) {
+    s_mu[k] = mu[k];
+    s_g[k] = sums[k];
+  }
+  for (int k = threadIdx.x; k < d * p; k += blockDim.x) s_U[k] = U[k];
+  for (int k = threadIdx.x; k < 64; k += blockDim.x) s_z[k] = znodes[k];
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+    int r = e % d, c = e / d;
+    int rr = min(r, c), cc = max(r, c);
+    s_H[e] = sums[d + cc * (cc + 1) / 2 + rr];     // packed upper triangle, column by column
+  }
+  __syncthreads();
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  double* dl = s_dl + threadIdx.x;       // dl[k * blockDim.x]
+  for (int k = 0; k < d; ++k) dl[k * blockDim.x] = 0.0;
+  for (int j = 0; j < p; ++j) {
+    int key = idx[(size_t)j * M_grid + (m0 + m)];
+    if (key != 0) {
+      double z = s_z[key];
+      for (int k = 0; k < d; ++k) dl[k * blockDim.x] += s_U[(size_t)j * d + k] * z;   // same order as the FP64 path
+    }
+  }
+  const double L_hat = sums[d + d * (d + 1) / 2];
+  double lin = 0, qf = 0, prior = 0;
+  float* o = ds + (size_t)m * kp;
+  for (int k = 0; k < d; ++k) {
+    const double dk = dl[k * blockDim.x];
+    const double th = s_mu[k] + dk;
+    theta[(size_t)k * M + m] = th;
+    lin += s_g[k] * dk;
+    double hk = 0;
+    for (int l = 0; l < d; ++l) hk += s_H[(size_t)k * d + l] * dl[l * blockDim.x];
+    qf += dk * hk;
+    const double zz = th / prior_sd;
+    prior += -0.5 * zz * zz - log(prior_sd) - 0.5 * 1.8378770664093454835606594728112;
+    float hi, lo;
+    tf32_split(dk, hi, lo);
+    o[k] = hi;
+    o[d + k] = hi;
+    o[2 * d + k] = lo;
+  }
+  quad[m] = (L_hat + lin - 0.5 * qf) + prior;
+}
+
+// ld = quad - sum_c part[c] + neg_min ; a = ld + |z|^2/2
+__global__ void tc_finish_kernel(long long M, long long m0, int chunks, const double* __restrict__ part,
+                                 const double* __restrict__ quad, const double* __restrict__ hzz, double neg_min,
+                                 double* __restrict__ logdens, double* __restrict__ a) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  double s = 0;
+  for (int c = 0; c < chunks; ++c) s += part[(size_t)c * M + m];
+  double ld = (quad[m] - s) + neg_min;
+  logdens[m] = ld;
+  a[m] = ld + hzz[m0 + m];
+}
+
+// ------------------------------------------------------------------------------------ the tensor-core kernel
+struct TcKernelParams {
+  int ka;                 // 128-byte K atoms per operand row
+  int stages;             // observation-tile ring depth
+  int n_node_tiles;
+  int chunks;             // observation chunks (work items = n_node_tiles x chunks)
+  int tiles_per_chunk;
+  int n_obs_tiles;
+  long long M;            // local node count
+  const float* coef;      // [N_pad][TC_NCMAX]
+  double* part;           // [chunks][M]
+};
+
+template <int NC>
+__device__ __forceinline__ void tc_accumulate16(const uint32_t (&v)[16], const float (&c)[NC], float* acc) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float D = __uint_as_float(v[j]);
+    float pl = c[NC - 1];
+#pragma unroll
+    for (int k = NC - 2; k >= 0; --k) pl = fmaf(pl, D, c[k]);
+    const float D2 = D * D;
+    acc[j] = fmaf(D2 * D, pl, acc[j]);
+  }
+}
+
+// 32 x 32 transpose-reduce: on exit v[0] of lane l holds sum over lanes of the entry v[l]
+__device__ __forceinline__ float tc_transpose_reduce32(float* v, int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const float send = up ? v[j] : v[j + s];
+      const float keep = up ? v[j + s] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+template <int NC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcKernelParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  // carve-up (1024-byte aligned for the 128-byte swizzle): node operand, observation ring, reduction buffer, barriers
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sB = base;                                              // ka x (256 x 128 B)
+  const uint32_t b_bytes = (uint32_t)P.ka * TC_NODE_TILE * 128u;
+  const uint32_t sA = sB + b_bytes;                                      // stages x ka x (128 x 128 B)
+  const uint32_t a_bytes = (uint32_t)P.ka * TC_OBS_TILE * 128u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  double* red = reinterpret_cast<double*>(gen + b_bytes + (size_t)P.stages * a_bytes);   // 4 x 256 doubles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 4 * TC_NODE_TILE);
+  const uint32_t bar_full = smem_u32(bars);                 // [stages]
+  const uint32_t bar_empty = bar_full + 8u * TC_MAX_STAGES; // [stages]
+  const uint32_t bar_bfull = bar_empty + 8u * TC_MAX_STAGES;
+  const uint32_t bar_bempty = bar_bfull + 8u;
+  const uint32_t bar_tfull = bar_bempty + 8u;               // [2]
+  const uint32_t bar_tempty = bar_tfull + 16u;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.stages; ++s) {
+      mbar_init(bar_full + 8u * s, 1);
+      mbar_init(bar_empty + 8u * s, 1);
+    }
+    mbar_init(bar_bfull, 1);
+    mbar_init(bar_bempty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8u * b, 1);
+      mbar_init(bar_tempty + 8u * b, TC_EPI_THREADS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {   // TMEM: all 512 columns (two 256-column accumulator buffers)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_items = P.n_node_tiles * P.chunks;
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, bphase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int node_tile = item / P.chunks, chunk = item % P.chunks;
+        const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
+        mbar_wait(bar_bempty, bphase ^ 1);
+        mbar_expect_tx(bar_bfull, b_bytes);
+        for (int a = 0; a < P.ka; ++a)
+          tma_load_2d(sB + (uint32_t)a * TC_NODE_TILE * 128u, &tmB, bar_bfull, a * TC_KATOM, node_tile * TC_NODE_TILE);
+        bphase ^= 1;
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(bar_empty + 8u * stage, phase ^ 1);
+          mbar_expect_tx(bar_full + 8u * stage, a_bytes);
+          for (int a = 0; a < P.ka; ++a)
+            tma_load_2d(sA + (uint32_t)stage * a_bytes + (uint32_t)a * TC_OBS_TILE * 128u, &tmA, bar_full + 8u * stage,
+                        a * TC_KATOM, t * TC_OBS_TILE);
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_NODE_TILE >> 3) << 17) |
+                             ((uint32_t)(TC_OBS_TILE >> 4) << 24);
+      int stage = 0, buf = 0;
+      uint32_t phase = 0, bphase = 0, tphase[2] = {0, 0};
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int chunk = item % P.chunks;
+        const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
+        mbar_wait(bar_bfull, bphase);
+        bphase ^= 1;
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(bar_tempty + 8u * buf, tphase[buf] ^ 1);
+          mbar_wait(bar_full + 8u * stage, phase);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC_NODE_TILE;
+          for (int a = 0; a < P.ka; ++a) {
+            const uint32_t aA = sA + (uint32_t)stage * a_bytes + (uint32_t)a * TC_OBS_TILE * 128u;
+            const uint32_t aB = sB + (uint32_t)a * TC_NODE_TILE * 128u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)   // K = 8 tf32 = 32 bytes per instruction inside the 128-byte atom
+              umma_tf32(d_tmem, umma_desc(aA + 32u * j), umma_desc(aB + 32u * j), idesc, (a | j) ? 1u : 0u);
+          }
+          tc_commit(bar_empty + 8u * stage);        // frees the observation stage when the MMAs have read it
+          tc_commit(bar_tfull + 8u * buf);          // publishes the accumulator buffer
+          tphase[buf] ^= 1;
+          buf ^= 1;
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(bar_bempty);                      // node operand may be overwritten once every MMA has retired
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int h = (warp - 2) >> 2;           // column half handled by this warp
+    const int et = threadIdx.x - 64;         // 0 .. 255
+    float acc[128];
+#pragma unroll
+    for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+    int buf = 0;
+    uint32_t tphase[2] = {0, 0};
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int node_tile = item / P.chunks, chunk = item % P.chunks;
+      const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
+      for (int t = t0; t < t1; ++t) {
+        // this thread's observation: row of the tile = TMEM lane
+        const float4* cp = reinterpret_cast<const float4*>(P.coef + ((size_t)t * TC_OBS_TILE + q * 32 + lane) * TC_NCMAX);
+        float c[NC];
+#pragma unroll
+        for (int k = 0; k < NC / 4; ++k) {
+          const float4 f = __ldg(cp + k);
+          c[4 * k] = f.x; c[4 * k + 1] = f.y; c[4 * k + 2] = f.z; c[4 * k + 3] = f.w;
+        }
+        mbar_wait(bar_tfull + 8u * buf, tphase[buf]);
+        tphase[buf] ^= 1;
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_NODE_TILE + h * 128);
+        uint32_t va[16], vb[16];
+        tmem_ld16(va, taddr);
+#pragma unroll
+        for (int cc = 0; cc < 8; cc += 2) {
+          tmem_ld_wait16(va);
+          tmem_ld16(vb, taddr + 16u * (cc + 1));
+          tc_accumulate16<NC>(va, c, acc + 16 * cc);
+          tmem_ld_wait16(vb);
+          if (cc + 2 < 8) tmem_ld16(va, taddr + 16u * (cc + 2));
+          tc_accumulate16<NC>(vb, c, acc + 16 * (cc + 1));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8u * buf);
+        buf ^= 1;
+      }
+      // flush the item: sum over the 32 observation lanes by transpose-reduce, over the 4 lane quarters in
+      // shared memory (FP64), one partial per (chunk, node)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float s = tc_transpose_reduce32(acc + 32 * g, lane);
+        red[q * TC_NODE_TILE + h * 128 + g * 32 + lane] = (double)s;
+      }
+      epi_bar_sync();
+      {
+        const double s = (red[et] + red[TC_NODE_TILE + et]) + (red[2 * TC_NODE_TILE + et] + red[3 * TC_NODE_TILE + et]);
+        const long long node = (long long)node_tile * TC_NODE_TILE + et;
+        if (node < P.M) P.part[(size_t)chunk * P.M + node] = s;
+      }
+      epi_bar_sync();
+#pragma unroll
+      for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_tensor_map(CUtensorMap* map, float* base, long long rows, int kp, int box_rows) {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    JP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
+    if (!p || qr != cudaDriverEntryPointSuccess) {
+      jp_set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return JP_ERR_UNSUPPORTED;
+    }
+    fn = (PFN_encodeTiled)p;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)kp, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)kp * sizeof(float)};
+  cuuint32_t box[2] = {TC_KATOM, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    jp_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld kp=%d box_rows=%d)", (int)r, rows, kp, box_rows);
+    return JP_ERR_CUDA;
+  }
+  return JP_OK;
+}
+
+static int upload_tables() {
+  static bool done = false;
+  if (done) return JP_OK;
+  double poly[TC_ORDER_MAX + 1][TC_ORDER_MAX + 2] = {{0}};
+  double inv_fact[TC_ORDER_MAX + 2];
+  // f_1 = s ; f_{k+1} = f_k'(s) (s - s^2), exact in integers (|coefficients| < 2^53 up to order 16)
+  std::vector<long long> f = {0, 1};
+  for (int k = 1; k <= TC_ORDER_MAX; ++k) {
+    for (size_t j = 0; j < f.size(); ++j) poly[k][j] = (double)f[j];
+    std::vector<long long> df(f.size() - 1);
+    for (size_t j = 1; j < f.size(); ++j) df[j - 1] = (long long)j * f[j];
+    std::vector<long long> nx(df.size() + 2, 0);
+    for (size_t j = 0; j < df.size(); ++j) {
+      nx[j + 1] += df[j];
+      nx[j + 2] -= df[j];
+    }
+    f.swap(nx);
+  }
+  double fct = 1;
+  inv_fact[0] = 1;
+  for (int k = 1; k <= TC_ORDER_MAX + 1; ++k) {
+    fct *= k;
+    inv_fact[k] = 1.0 / fct;
+  }
+  JP_CUDA(cudaMemcpyToSymbol(c_sp_poly, poly, sizeof poly));
+  JP_CUDA(cudaMemcpyToSymbol(c_inv_fact, inv_fact, sizeof inv_fact));
+  done = true;
+  return JP_OK;
+}
+
+static bool tc_static_ok(const jp_posterior* post, const jp_fit_args* args) {
+  const jp_data* data = post->data;
+  if (data->family != JP_FAM_LOGISTIC && data->family != JP_FAM_POISSON) {
+    jp_set_error("tensor-core path: family %d is not a GLM", data->family);
+    return false;
+  }
+  if (3 * args->d > 3 * TC_KATOM) {   // three 128-byte K atoms per operand row fit the shared-memory budget
+    jp_set_error("tensor-core path: d=%d exceeds %d", args->d, TC_KATOM);
+    return false;
+  }
+  for (int k = 0; k < args->d; ++k)
+    if (args->h_transform[k] != JP_T_REAL) {
+      jp_set_error("tensor-core path: coordinate %d is constrained", k);
+      return false;
+    }
+  if (data->ncols != args->d + 1) {
+    jp_set_error("tensor-core path: %d columns for d=%d", data->ncols, args->d);
+    return false;
+  }
+  return true;
+}
+
+bool jp_fit_tc_supported(const jp_posterior* post, const jp_fit_args* args) { return tc_static_ok(post, args); }
+
+void jp_tc_data_free(jp_data* data) {
+  TcDataState* s = static_cast<TcDataState*>(data->tc_state);
+  if (!s) return;
+  cudaFree(s->d_xs); cudaFree(s->d_coef); cudaFree(s->d_sums); cudaFree(s->d_work); cudaFree(s->d_bounds);
+  delete s;
+  data->tc_state = nullptr;
+}
+void jp_tc_post_free(jp_posterior* post) {
+  TcPostState* s = static_cast<TcPostState*>(post->tc_state);
+  if (!s) return;
+  cudaFree(s->d_ds); cudaFree(s->d_quad);
+  delete s;
+  post->tc_state = nullptr;
+}
+
+static int ensure_data_state(jp_ctx* ctx, jp_data* data, int d) {
+  if (data->tc_state) return JP_OK;
+  TcDataState* s = new TcDataState();
+  data->tc_state = s;
+  s->d = d;
+  s->kp = ((3 * d + TC_KATOM - 1) / TC_KATOM) * TC_KATOM;
+  s->ka = s->kp / TC_KATOM;
+  s->N = data->N;
+  s->N_pad = ((data->N + TC_OBS_TILE - 1) / TC_OBS_TILE) * TC_OBS_TILE;
+  const int nE = d + d * (d + 1) / 2;
+  s->glm_blocks = jp_glm_num_blocks(ctx, data->N);
+  JP_CUDA(cudaMalloc(&s->d_xs, (size_t)s->N_pad * s->kp * sizeof(float)));
+  JP_CUDA(cudaMalloc(&s->d_coef, (size_t)s->N_pad * TC_NCMAX * sizeof(float)));
+  JP_CUDA(cudaMalloc(&s->d_sums, (size_t)(nE + 1) * 8));
+  JP_CUDA(cudaMalloc(&s->d_work, (size_t)s->glm_blocks * (nE + 1) * 8));
+  JP_CUDA(cudaMalloc(&s->d_bounds, (size_t)TC_PREP_BLOCKS * TC_NBOUND * 8));
+  tc_split_x_kernel<<<(unsigned)((s->N_pad + 255) / 256), 256, 0, ctx->stream>>>(d, data->ncols, s->kp, s->N, s->N_pad,
+                                                                                  data->d_obs, s->d_xs);
+  JP_CHECK_LAUNCH(ctx);
+  JP_TRY(make_tensor_map(&s->tmA, s->d_xs, s->N_pad, s->kp, TC_OBS_TILE));
+  return JP_OK;
+}
+
+static int ensure_post_state(jp_posterior* post, int kp) {
+  if (post->tc_state) return JP_OK;
+  TcPostState* s = new TcPostState();
+  post->tc_state = s;
+  s->kp = kp;
+  s->M_pad = ((post->M + TC_NODE_TILE - 1) / TC_NODE_TILE) * TC_NODE_TILE;
+  JP_CUDA(cudaMalloc(&s->d_ds, (size_t)s->M_pad * kp * sizeof(float)));
+  JP_CUDA(cudaMemsetAsync(s->d_ds, 0, (size_t)s->M_pad * kp * sizeof(float), post->ctx->stream));
+  JP_CUDA(cudaMalloc(&s->d_quad, (size_t)post->M * 8));
+  JP_TRY(make_tensor_map(&s->tmB, s->d_ds, s->M_pad, kp, TC_NODE_TILE));
+  return JP_OK;
+}
+
+// Order / eligibility decision from the reduced bounds (see tc_obs_prep_kernel).  Returns NC in {4, 8, 12}
+// or 0 when the series is not trustworthy for this (data, U, grid) and the FP64 kernel must be used.
+//   * series convergence (rigorous): max_i |Delta_i| <= t_max z_max must stay well inside the radius pi
+//   * truncation (rigorous): tail summed over ALL observations <= 1e-9 at |z| = z_ref = min(z_max, 6) and
+//     <= 1e-4 at z_max (nodes beyond |z| = 6 carry < e^-9 of the peak density, so 1e-4 relative on them is
+//     < 1e-8 of the largest weight)
+//   * rounding (statistical): FP32 Horner and the 3xTF32 contraction perturb each R_i by ~2e-6 |R_i| with
+//     pseudo-random sign, so the log-density error is ~2e-6 sqrt(sum_i R_i^2); a factor 8 of margin is
+//     required below 2e-7.  (The worst case with every error aligned, 2e-6 sum_i |R_i|, is reported too.)
+static int jp_tc_choose_order(const double* b, double* err_trunc, double* err_round) {
+  const double tdelta = b[0];
+  if (!(tdelta <= 2.0)) return 0;
+  *err_round = 2e-6 * std::sqrt(b[9]);
+  if (!(8.0 * *err_round <= 2e-7)) return 0;
+  for (int j = 0; j < 3; ++j)
+    if (b[2 + j] <= 1e-9 && b[5 + j] <= 1e-4) {
+      *err_trunc = b[2 + j];
+      return 4 * (j + 1);
+    }
+  return 0;
+}
+
+template <int NC>
+static int launch_tc(jp_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcKernelParams& kp, size_t smem) {
+  JP_CUDA(cudaFuncSetAttribute(jp_glm_tc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = std::min(ctx->sm_count, kp.n_node_tiles * kp.chunks);
+  jp_glm_tc_kernel<NC><<<grid, TC_THREADS, smem, ctx->stream>>>(tmA, tmB, kp);
+  JP_CHECK_LAUNCH(ctx);
+  return JP_OK;
+}
+
+int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
+  jp_ctx* ctx = post->ctx;
+  jp_data* data = const_cast<jp_data*>(post->data);
+  if (!tc_static_ok(post, args)) return JP_ERR_UNSUPPORTED;
+  const int d = args->d, p = args->p;
+  JP_TRY(upload_tables());
+  JP_TRY(ensure_data_state(ctx, data, d));
+  TcDataState* ds = static_cast<TcDataState*>(data->tc_state);
+  JP_REQUIRE(ds->d == d, "tensor-core path: data was prepared for d=%d", ds->d);
+  JP_TRY(ensure_post_state(post, ds->kp));
+  TcPostState* ps = static_cast<TcPostState*>(post->tc_state);
+  JP_TRY(jp_upload_fit_consts(post, args));
+  cudaStream_t st = ctx->stream;
+  // FP64 sums at the centre: g, H, L_hat
+  JP_TRY(jp_glm_sums_device(ctx, data, d, post->d_mu, ds->d_sums, ds->d_work, ds->glm_blocks));
+  // per-observation coefficients + bounds
+  const double z_max = std::sqrt(post->grid->zmax2), z_ref = std::min(z_max, 6.0);
+  size_t sm_obs = (size_t)(d + d * p) * 8;
+  tc_obs_prep_kernel<<<TC_PREP_BLOCKS, 256, sm_obs, st>>>(data->family, d, p, data->ncols, data->N, ds->N_pad, data->d_obs,
+                                                          post->d_mu, post->d_U, z_ref, z_max, ds->d_coef, ds->d_bounds);
+  JP_CHECK_LAUNCH(ctx);
+  double* hb = ctx->h_pinned + 4096;   // away from the constants staged by jp_upload_fit_consts
+  JP_CUDA(cudaMemcpyAsync(hb, ds->d_bounds, (size_t)TC_PREP_BLOCKS * TC_NBOUND * 8, cudaMemcpyDeviceToHost, st));
+  JP_CUDA(cudaStreamSynchronize(st));
+  double b[TC_NBOUND] = {0};
+  for (int blk = 0; blk < TC_PREP_BLOCKS; ++blk) {
+    const double* o = hb + (size_t)blk * TC_NBOUND;
+    b[0] = std::max(b[0], o[0]);
+    for (int j = 1; j < TC_NBOUND; ++j) b[j] += o[j];
+  }
+  b[0] *= z_max;
+  double err_trunc = 0, err_round = 0;
+  const int NC = jp_tc_choose_order(b, &err_trunc, &err_round);
+  post->tc_bounds[0] = b[0]; post->tc_bounds[1] = err_trunc; post->tc_bounds[2] = err_round; post->tc_bounds[3] = NC;
+  post->tc_bounds[4] = 2e-6 * b[8];
+  if (NC == 0) {
+    jp_set_error("tensor-core path: series bounds not met (max |Delta| %.3g, rounding estimate %.3g, truncation bounds %.3g/%.3g "
+                 "at order 14); use the FP64 path", b[0], 2e-6 * std::sqrt(b[9]), b[4], b[7]);
+    return JP_ERR_UNSUPPORTED;
+  }
+  // node operand, theta, FP64 quadratic part
+  size_t sm_node = (size_t)(d + d * p + d + d * d + 64 + 128 * d) * 8;
+  if (sm_node > 48 * 1024)
+    JP_CUDA(cudaFuncSetAttribute(tc_node_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_node));
+  tc_node_prep_kernel<<<(unsigned)((post->M + 127) / 128), 128, sm_node, st>>>(
+      d, p, ds->kp, post->grid->rule, post->M, post->m0, post->grid->M, post->grid->d_idx,
+      jp_rule_nodes_dev(post->grid->rule), post->d_mu, post->d_U, ds->d_sums, data->hyper[0], post->d_theta, ps->d_quad,
+      ps->d_ds);
+  JP_CHECK_LAUNCH(ctx);
+  // work decomposition: node tiles x observation chunks on a persistent grid
+  TcKernelParams kp;
+  kp.ka = ds->ka;
+  kp.n_node_tiles = (int)(ps->M_pad / TC_NODE_TILE);
+  kp.n_obs_tiles = (int)(ds->N_pad / TC_OBS_TILE);
+  const size_t b_bytes = (size_t)kp.ka * TC_NODE_TILE * 128, a_bytes = (size_t)kp.ka * TC_OBS_TILE * 128;
+  const size_t fixed = 1024 + b_bytes + 4 * TC_NODE_TILE * 8 + 256;
+  kp.stages = (int)std::max<size_t>(2, std::min<size_t>(TC_MAX_STAGES, (200 * 1024 - fixed) / a_bytes));
+  const size_t smem = fixed + (size_t)kp.stages * a_bytes;
+  int best_c = 1;
+  double best_eff = 0;
+  const int max_c = std::max(1, std::min(JP_POST_PART_SPLITS, kp.n_obs_tiles / 8));
+  for (int c = 1; c <= max_c; ++c) {
+    long long items = (long long)kp.n_node_tiles * c;
+    long long rounds = (items + ctx->sm_count - 1) / ctx->sm_count;
+    double eff = (double)items / (double)(rounds * ctx->sm_count);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best_c = c; }
+    if (eff >= 0.97) break;
+  }
+  kp.chunks = best_c;
+  kp.tiles_per_chunk = (kp.n_obs_tiles + kp.chunks - 1) / kp.chunks;
+  kp.chunks = (kp.n_obs_tiles + kp.tiles_per_chunk - 1) / kp.tiles_per_chunk;   // no empty chunk
+  kp.M = post->M;
+  kp.coef = ds->d_coef;
+  kp.part = post->d_part;
+  int stc;
+  if (NC == 4) stc = launch_tc<4>(ctx, ds->tmA, ps->tmB, kp, smem);
+  else if (NC == 8) stc = launch_tc<8>(ctx, ds->tmA, ps->tmB, kp, smem);
+  else stc = launch_tc<12>(ctx, ds->tmA, ps->tmB, kp, smem);
+  JP_TRY(stc);
+  tc_finish_kernel<<<(unsigned)((post->M + 255) / 256), 256, 0, st>>>(post->M, post->m0, kp.chunks, post->d_part, ps->d_quad,
+                                                                       post->grid->d_hzz, args->neg_min, post->d_logdens,
+                                                                       post->d_a);
+  JP_CHECK_LAUNCH(ctx);
+  post->path_used = JP_PATH_TC;
+  return JP_OK;
+}

@@ -362,6 +362,14 @@ class JointPosterior:
         return int(lib().jp_fit_path_used(self.handle))
 
     @property
+    def diagnostics(self):
+        """A-priori error figures of the tensor-core path (jp_fit_diagnostics)."""
+        out = np.zeros(8)
+        check(lib().jp_fit_diagnostics(self.handle, ptr(out)))
+        return dict(max_delta_eta=out[0], truncation_bound=out[1], rounding_estimate=out[2], series_terms=int(out[3]),
+                    rounding_worst_case=out[4])
+
+    @property
     def Theta(self):
         if self._theta is None:
             out = np.zeros((self._args.d, self.n_nodes))

@@ -371,3 +371,117 @@ def test_cfg3_full_size_properties(jp, O, gpu_ctx):
     assert relerr(dens, e / e.sum()) < 1e-11
     post2 = jp.fit(M, dd, wl["level"], path=jp.PATH_FP64, mode_result=(x, U, neg_min + 123.0))
     assert relerr(post2.density, dens) < 1e-9
+
+
+# ------------------------------------------------------------------------------ tensor-core GLM path
+TOLTC = 1e-6     # BASELINE.json north_star: 1e-6 on the TF32-compensated GLM path
+
+
+def _glm_case(kind, seed, N, d, xscale=1.0):
+    X, y = synth_glm(seed, N, d, kind, xscale)
+    return (1 if kind == "logistic" else 2), np.column_stack([X, y]), np.array([10.0])
+
+
+@pytest.mark.parametrize("kind,N,d,level,xscale", [("logistic", 50000, 6, 4, 1.0), ("poisson", 60000, 5, 4, 0.3),
+                                                   ("logistic", 40000, 10, 4, 1.0), ("poisson", 100000, 20, 3, 0.3),
+                                                   ("logistic", 200000, 30, 3, 1.0), ("logistic", 30001, 3, 6, 1.0)],
+                         ids=["logit-d6", "pois-d5", "logit-d10", "pois-d20-2atoms", "logit-d30-3atoms", "logit-d3-ragged"])
+def test_tc_path_matches_oracle(jp, O, gpu_ctx, kind, N, d, level, xscale):
+    """tcgen05 3xTF32 path vs the FP64 CPU oracle: normalised weights, moments, knots, quantiles <= 1e-6."""
+    family, obs, hyper = _glm_case(kind, 100 + d, N, d, xscale)
+    code = [0] * d
+    x, H, neg_min = _cpu_mode_for(O, family, code, obs, hyper)
+    U = O.inv_chol(2.0 * H)
+    M = _model_for(jp, code)
+    dd = _upload(jp, gpu_ctx, family, obs, hyper)
+    post = jp.fit(M, dd, level, path=jp.PATH_TC, mode_result=(x, U, neg_min))
+    assert post.path_used == jp.PATH_TC
+    diag = post.diagnostics
+    assert diag["series_terms"] in (4, 8, 12) and diag["max_delta_eta"] < 2.0
+    idx, w = O.smolyak(0, d, level)
+    ref = O.eval_grid(0, family, code, idx, w, x, U, neg_min, obs, hyper)
+    assert relerr(post.Theta, ref["theta"]) < 1e-14
+    assert relerr(post.density, ref["density"]) < TOLTC
+    # log-density error itself, on the nodes that carry weight
+    heavy = np.abs(ref["density"]) > 1e-6 * np.max(np.abs(ref["density"]))
+    assert np.max(np.abs(post.logdens - ref["logdens"])[heavy]) < TOLTC
+    ms = jp.marginals(post, list(range(d)))
+    for k, m in enumerate(ms):
+        mo = O.marginal(ref["theta"][k], ref["density"])
+        assert abs(m.mu - mo["mu"]) <= TOLTC * max(abs(mo["mu"]), 1e-3)
+        assert abs(m.sigma - mo["sigma"]) <= TOLTC * abs(mo["sigma"]) * 10
+        assert np.max(np.abs(m.itp.weights - mo["weight_nodes"])) < TOLTC * 10
+        for p in PROBS:
+            q, qo = jp.quantile(m, p), O.quantile(mo["weight_nodes"], mo["value_nodes"], p)
+            assert abs(q - qo) <= 1e2 * TOLTC * max(abs(qo), 1e-3), (k, p, q, qo)
+    # and against the FP64 CUDA kernel on the same inputs
+    post64 = jp.fit(M, dd, level, path=jp.PATH_FP64, mode_result=(x, U, neg_min))
+    assert relerr(post.density, post64.density) < TOLTC
+
+
+def test_tc_path_gating(jp, O, gpu_ctx):
+    """Outside its error bounds the tensor-core path refuses (forced) or falls back to FP64 (AUTO)."""
+    family, obs, hyper = _glm_case("logistic", 5, 500, 4)
+    code = [0] * 4
+    x, H, neg_min = _cpu_mode_for(O, family, code, obs, hyper)
+    U = O.inv_chol(2.0 * H)
+    M = _model_for(jp, code)
+    dd = _upload(jp, gpu_ctx, family, obs, hyper)
+    with pytest.raises(jp.JPError) as e:
+        jp.fit(M, dd, 5, path=jp.PATH_TC, mode_result=(x, U, neg_min))
+    assert e.value.status == 6 and "series bounds" in str(e.value)
+    post = jp.fit(M, dd, 5, mode_result=(x, U, neg_min))           # AUTO
+    assert post.path_used == jp.PATH_FP64 and post.diagnostics["series_terms"] == 0
+    idx, w = O.smolyak(0, 4, 5)
+    ref = O.eval_grid(0, family, code, idx, w, x, U, neg_min, obs, hyper)
+    assert relerr(post.density, ref["density"]) < TOL64
+    # non-GLM family / constrained coordinates: forced TC is an error, never a silent fallback
+    obs1, hyp1 = readme_records()
+    with pytest.raises(jp.JPError):
+        jp.fit(jp.Model((jp.ProbabilityVector(3),)), _upload(jp, gpu_ctx, 0, obs1, hyp1), 3, path=jp.PATH_TC,
+               mode_result=(np.array([0.2, -3.0, -2.0]), np.eye(3) * 0.3, 119.0))
+
+
+def test_tc_sharded_equals_unsharded(jp, O, gpu_ctx):
+    """Node shards through the TC kernel (ragged last tile, shard offsets) reproduce the full fit."""
+    from jointposteriors_jl_b200 import distributed as D
+    from jointposteriors_jl_b200.model import JointPosterior
+    family, obs, hyper = _glm_case("logistic", 9, 60000, 8)
+    code = [0] * 8
+    x, H, neg_min = _cpu_mode_for(O, family, code, obs, hyper)
+    U = O.inv_chol(2.0 * H)
+    M = _model_for(jp, code)
+    dd = _upload(jp, gpu_ctx, family, obs, hyper)
+    full = jp.fit(M, dd, 4, path=jp.PATH_TC, mode_result=(x, U, neg_min))
+    grid = gpu_ctx.grid(0, 8, 4)
+    ld = full.logdens
+    for r in range(3):
+        b, e = D.shard_bounds(full.n_nodes, r, 3)
+        sh = JointPosterior(M, dd, grid, x, U, neg_min, path=jp.PATH_TC, node_range=(b, e))
+        sh.evaluate()
+        assert sh.path_used == jp.PATH_TC
+        assert np.max(np.abs(sh.logdens - ld[b:e])) < 1e-9     # same arithmetic per node up to chunking of the sums
+
+
+def test_cfg3_full_size_tc(jp, O, gpu_ctx):
+    """BASELINE config 3 at full size on the tensor-core path vs the FP64 CUDA kernel and an oracle subsample."""
+    from jointposteriors_jl_b200 import workloads
+    wl = workloads.cfg3_logistic()
+    data = wl["data"]
+    obs, hyper = data.records()
+    M = jp.Model(wl["params"])
+    dd = gpu_ctx.upload(data)
+    x, U, neg_min = jp.mode(M, dd)
+    tc = jp.fit(M, dd, wl["level"], path=jp.PATH_TC, mode_result=(x, U, neg_min))
+    assert tc.path_used == jp.PATH_TC
+    f64 = jp.fit(M, dd, wl["level"], path=jp.PATH_FP64, mode_result=(x, U, neg_min))
+    assert relerr(tc.density, f64.density) < TOLTC
+    d64 = f64.density
+    heavy = np.abs(d64) > 1e-6 * np.max(np.abs(d64))
+    assert np.max(np.abs(tc.logdens - f64.logdens)[heavy]) < TOLTC
+    assert abs(tc.density.sum() - 1.0) < 1e-12
+    auto = jp.fit(M, dd, wl["level"], mode_result=(x, U, neg_min))
+    assert auto.path_used == jp.PATH_TC
+    mt, m6 = jp.marginals(tc, list(range(10))), jp.marginals(f64, list(range(10)))
+    for a, b in zip(mt, m6):
+        assert abs(a.mu - b.mu) <= TOLTC * max(abs(b.mu), 1e-3) and abs(a.sigma - b.sigma) <= 10 * TOLTC * b.sigma
