@@ -43,52 +43,53 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region: NVML polled from a thread every ~2 ms
+    (the timed region of this path is tens of milliseconds, too short for `nvidia-smi -lms`)."""
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.samples, self.stop_flag, self.th, self.err = index, [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:   # noqa: BLE001
+            self.nv, self.err = None, repr(e)
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((sm, rs, pw))
+            except Exception as e:   # noqa: BLE001
+                self.err = repr(e)
+                break
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+        if self.nv is None:
+            return
+        self.stop_flag = False
+        self.th = threading.Thread(target=self._poll, daemon=True)
+        self.th.start()
 
     def stop(self):
-        if not self.proc:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
-        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)), samples=len(sm),
-                    reasons=sorted(reasons))
+        if self.nv is None or self.th is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["NVML unavailable: %s" % self.err])
+        self.stop_flag = True
+        self.th.join(timeout=2)
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples: %s" % self.err])
+        nv = self.nv
+        bits = dict(hw_slowdown=nv.nvmlClocksEventReasonHwSlowdown, hw_thermal_slowdown=nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    sw_thermal_slowdown=nv.nvmlClocksEventReasonSwThermalSlowdown, sw_power_cap=nv.nvmlClocksEventReasonSwPowerCap)
+        reasons = sorted(n for n, b in bits.items() if any(r & b for _, r, _ in self.samples))
+        return dict(sm_mhz=float(np.median([s for s, _, _ in self.samples])), sm_max_mhz=float(self.max_sm),
+                    power_w_max=float(max(p for _, _, p in self.samples)), samples=len(self.samples), reasons=reasons)
 
 
 def make_workload(jp, name, n_gpus):
@@ -281,7 +282,7 @@ def run_product(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    fit_ms, marg_ms, step_ms = [], [], []
+    fit_ms, marg_ms, step_ms, kern_in_step = [], [], [], []
     for _ in range(args.steps):
         flush.zero_()                      # evict the working set from L2 between timed iterations
         torch.cuda.synchronize(dev)
@@ -298,6 +299,7 @@ def run_product(args):
         c.record(stream)
         torch.cuda.synchronize(dev)
         fit_ms.append(a.elapsed_time(bq)); marg_ms.append(bq.elapsed_time(c)); step_ms.append(a.elapsed_time(c))
+        kern_in_step.append(ctx.last_kernel_ms())      # CUDA events recorded around the kernel by the library
     barrier()
     launches = ctx.launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -308,18 +310,9 @@ def run_product(args):
     ms_per_step = tot_ms / args.steps
     value = pairs / (ms_per_step * 1e-3)
 
-    # ---- dominant kernel alone (stages 2-3 log-density kernel), for the roofline
-    kern_ms = []
-    for _ in range(max(3, args.steps)):
-        flush.zero_()
-        torch.cuda.synchronize(dev)
-        a, bq = ev(), ev()
-        a.record(stream)
-        loc.fit_local_max()
-        bq.record(stream)
-        torch.cuda.synchronize(dev)
-        kern_ms.append(a.elapsed_time(bq))
-    kms = float(np.median(kern_ms))
+    # ---- dominant kernel (node x obs log-density kernel): average launch duration over the timed region,
+    # from the CUDA events the library records around it on its stream
+    kms = float(np.mean(kern_in_step))
     path_used = post.path_used
     local_pairs = float(e - b) * float(N)
     if path_used == _lib.PATH_TC:
@@ -336,7 +329,17 @@ def run_product(args):
                     frac=nbytes / (kms * 1e-3) / 1e9 / peaks["hbm_gbs"], traffic=None,
                     note="FP64 plugin kernel: compulsory bytes 8N(d+1)+8M(d+1); the kernel is FP64-ALU bound "
                          "(%.3g pairs/s), not HBM bound; %s" % (local_pairs / (kms * 1e-3), peaks["source"]))
+    if path_used == _lib.PATH_TC:
+        nc = int(post.diagnostics["series_terms"])
+        clk = (clocks or {}).get("sm_mhz") or 1965.0
+        fp32_peak = 148 * 128 * clk * 1e6          # FP32 lane-instructions / s of the FMA pipes
+        roof["epilogue"] = dict(fp32_instr_per_pair=nc + 2, achieved_lane_instr_per_s=(nc + 2) * local_pairs / (kms * 1e-3),
+                                peak_lane_instr_per_s=fp32_peak, frac=(nc + 2) * local_pairs / (kms * 1e-3) / fp32_peak,
+                                note="the kernel's true limiter: %d FP32 FMA-pipe instructions per pair (Horner of the link "
+                                     "remainder series) against 148 SMs x 128 lanes x SM clock" % (nc + 2))
+    roof["kernel"] = "jp_glm_tc_kernel" if path_used == _lib.PATH_TC else "jp_fit_nodes_kernel"
     roof["kernel_ms"] = kms
+    roof["kernel_share_of_step"] = kms / ms_per_step
     roof["kernel_pairs_per_s"] = local_pairs / (kms * 1e-3)
 
     # ---- end to end through the public API with host buffers ("e2e")
@@ -393,6 +396,7 @@ def run_product(args):
                                marginals="%d coordinate marginals per step (moments + 100-knot Grid CDF)" % d),
                    fit_ms=tot_fit_ms / args.steps, marginal_ms=tot_marg_ms / args.steps, grid_build_ms=t_grid,
                    mode_ms=t_mode * 1e3, upload_ms=t_up * 1e3, clocks=clocks, e2e=e2e, gpu_launches=int(launches),
+                   tc_diagnostics=post.diagnostics,
                    roofline=roof)
         if cpu:
             out["cpu_baseline"] = cpu

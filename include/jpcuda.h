@@ -104,6 +104,9 @@ int jp_ctx_set_stream(jp_ctx* ctx, void* cuda_stream);
 int jp_ctx_sync(jp_ctx* ctx);
 /* number of kernels this ctx has launched since creation (for bench.py's gpu_launches) */
 long long jp_ctx_launch_count(const jp_ctx* ctx);
+/* device time (CUDA events on the ctx stream) of the most recent launch of the dominant kernel of the path:
+ * the node x observation log-density kernel of jp_fit (FP64 plugin kernel or tcgen05 GLM kernel).  Blocking. */
+int jp_ctx_last_kernel_ms(jp_ctx* ctx, float* ms);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage 1 -- Smolyak sparse grid, built on the GPU and cached per ctx by (rule, d_eff, level),

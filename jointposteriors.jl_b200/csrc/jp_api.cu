@@ -33,17 +33,26 @@ int jp_ctx_create(int device, jp_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   JP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->own_stream = true;
-  JP_CUDA(cudaMalloc(&ctx->d_scratch, sizeof(double) * JP_SCRATCH_DOUBLES));
+  {
+    // keep freed blocks cached in the pool instead of returning them to the driver at every sync
+    cudaMemPool_t pool;
+    JP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ull;
+    JP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+  JP_CUDA(jp_dmalloc(ctx, &ctx->d_scratch, sizeof(double) * JP_SCRATCH_DOUBLES));
   JP_CUDA(cudaMallocHost(&ctx->h_pinned, sizeof(double) * JP_PINNED_DOUBLES));
+  JP_CUDA(cudaEventCreate(&ctx->ev_k0));
+  JP_CUDA(cudaEventCreate(&ctx->ev_k1));
   *out = ctx;
   return JP_OK;
 }
 
-static void free_grid(jp_grid* g) {
+static void free_grid(jp_ctx* ctx, jp_grid* g) {
   if (!g) return;
-  cudaFree(g->d_idx);
-  cudaFree(g->d_w);
-  cudaFree(g->d_hzz);
+  jp_dfree(ctx, g->d_idx);
+  jp_dfree(ctx, g->d_w);
+  jp_dfree(ctx, g->d_hzz);
   delete g;
 }
 
@@ -51,9 +60,12 @@ int jp_ctx_destroy(jp_ctx* ctx) {
   if (!ctx) return JP_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (auto& kv : ctx->grids) free_grid(kv.second);
-  cudaFree(ctx->d_scratch);
+  for (auto& kv : ctx->grids) free_grid(ctx, kv.second);
+  jp_dfree(ctx, ctx->d_scratch);
+  cudaStreamSynchronize(ctx->stream);
   cudaFreeHost(ctx->h_pinned);
+  cudaEventDestroy(ctx->ev_k0);
+  cudaEventDestroy(ctx->ev_k1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return JP_OK;
@@ -76,6 +88,14 @@ int jp_ctx_sync(jp_ctx* ctx) {
 
 long long jp_ctx_launch_count(const jp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int jp_ctx_last_kernel_ms(jp_ctx* ctx, float* ms) {
+  JP_REQUIRE(ctx && ms, "jp_ctx_last_kernel_ms: null argument");
+  JP_REQUIRE(ctx->ev_valid, "jp_ctx_last_kernel_ms: no log-density kernel has been launched on this context");
+  JP_CUDA(cudaEventSynchronize(ctx->ev_k1));
+  JP_CUDA(cudaEventElapsedTime(ms, ctx->ev_k0, ctx->ev_k1));
+  return JP_OK;
+}
+
 // ------------------------------------------------------------------------------------ stage 1
 int jp_grid_get(jp_ctx* ctx, int rule, int d_eff, int level, jp_grid** out) {
   JP_REQUIRE(ctx && out, "jp_grid_get: null argument");
@@ -90,7 +110,7 @@ int jp_grid_get(jp_ctx* ctx, int rule, int d_eff, int level, jp_grid** out) {
   if (!g) return JP_ERR_ALLOC;
   int st = jp_grid_build(ctx, rule, d_eff, level, g);
   if (st != JP_OK) {
-    free_grid(g);
+    free_grid(ctx, g);
     return st;
   }
   ctx->grids[key] = g;
@@ -146,11 +166,11 @@ int jp_data_upload(jp_ctx* ctx, int family, long long N, int ncols, const double
   dt->ctx = ctx; dt->family = family; dt->N = N; dt->ncols = ncols; dt->n_hyper = n_hyper;
   for (int i = 0; i < n_hyper; ++i) dt->hyper[i] = h_hyper[i];
   size_t bytes = (size_t)N * ncols * sizeof(double);
-  cudaError_t e = cudaMalloc(&dt->d_obs, bytes);
+  cudaError_t e = jp_dmalloc(ctx, &dt->d_obs, bytes);
   if (e == cudaSuccess) e = cudaMemcpyAsync(dt->d_obs, h_obs, bytes, cudaMemcpyHostToDevice, ctx->stream);
   if (e != cudaSuccess) {
     jp_set_error("jp_data_upload: %s", cudaGetErrorString(e));
-    cudaFree(dt->d_obs);
+    jp_dfree(ctx, dt->d_obs);
     delete dt;
     return JP_ERR_CUDA;
   }
@@ -161,9 +181,8 @@ int jp_data_upload(jp_ctx* ctx, int family, long long N, int ncols, const double
 int jp_data_free(jp_data* data) {
   if (!data) return JP_OK;
   cudaSetDevice(data->ctx->device);
-  cudaStreamSynchronize(data->ctx->stream);
   jp_tc_data_free(data);
-  cudaFree(data->d_obs);
+  jp_dfree(data->ctx, data->d_obs);
   delete data;
   return JP_OK;
 }
@@ -186,7 +205,7 @@ int jp_posterior_create(jp_ctx* ctx, const jp_grid* g, const jp_data* data, cons
   p->m0 = m0; p->m1 = m1; p->M = m1 - m0;
   size_t M = (size_t)p->M;
   cudaError_t e = cudaSuccess;
-  auto A = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes); };
+  auto A = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = jp_dmalloc(ctx, ptr, bytes); };
   A((void**)&p->d_theta, M * p->d * 8);
   A((void**)&p->d_a, M * 8);
   A((void**)&p->d_logdens, M * 8);
@@ -208,11 +227,11 @@ int jp_posterior_create(jp_ctx* ctx, const jp_grid* g, const jp_data* data, cons
 int jp_posterior_free(jp_posterior* p) {
   if (!p) return JP_OK;
   cudaSetDevice(p->ctx->device);
-  cudaStreamSynchronize(p->ctx->stream);
-  cudaFree(p->d_theta); cudaFree(p->d_a); cudaFree(p->d_logdens); cudaFree(p->d_density); cudaFree(p->d_part);
-  cudaFree(p->d_stats); cudaFree(p->d_mu); cudaFree(p->d_U); cudaFree(p->d_tcode); jp_tc_post_free(p);
-  cudaFree(p->d_vals); cudaFree((void*)p->d_vptr); cudaFree(p->d_perm_a); cudaFree(p->d_perm_b); cudaFree(p->d_hist);
-  cudaFree(p->d_sv); cudaFree(p->d_sw); cudaFree(p->d_cw); cudaFree(p->d_mout);
+  jp_ctx* c = p->ctx;   // stream-ordered frees: work already queued on the ctx stream still sees the buffers
+  jp_dfree(c, p->d_theta); jp_dfree(c, p->d_a); jp_dfree(c, p->d_logdens); jp_dfree(c, p->d_density); jp_dfree(c, p->d_part);
+  jp_dfree(c, p->d_stats); jp_dfree(c, p->d_mu); jp_dfree(c, p->d_U); jp_dfree(c, p->d_tcode); jp_tc_post_free(p);
+  jp_dfree(c, p->d_vals); jp_dfree(c, (void*)p->d_vptr); jp_dfree(c, p->d_perm_a); jp_dfree(c, p->d_perm_b); jp_dfree(c, p->d_hist);
+  jp_dfree(c, p->d_sv); jp_dfree(c, p->d_sw); jp_dfree(c, p->d_cw); jp_dfree(c, p->d_mout);
   delete p;
   return JP_OK;
 }

@@ -68,11 +68,23 @@ struct jp_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   long long launches = 0;
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // bracket the last launch of the dominant (log-density) kernel
+  bool ev_valid = false;
   std::map<std::tuple<int, int, int>, jp_grid*> grids;
   // scratch for small reductions / scalars (device) and pinned host staging
   double* d_scratch = nullptr;     // JP_SCRATCH_DOUBLES doubles
   double* h_pinned = nullptr;      // JP_PINNED_DOUBLES doubles
 };
+// Stream-ordered device memory from the device's pool (cudaMallocAsync with an unbounded release
+// threshold, set in jp_ctx_create): the buffers of freed posteriors / data sets are recycled by the next
+// allocation without a device synchronisation, which is what keeps repeated fit() calls cheap.
+template <class T>
+inline cudaError_t jp_dmalloc(jp_ctx* ctx, T** p, size_t bytes) {
+  return cudaMallocAsync((void**)p, bytes ? bytes : 16, ctx->stream);
+}
+inline void jp_dfree(jp_ctx* ctx, const void* p) {
+  if (p) cudaFreeAsync(const_cast<void*>(p), ctx->stream);
+}
 #define JP_SCRATCH_DOUBLES (1 << 16)
 #define JP_PINNED_DOUBLES (1 << 16)
 

@@ -209,7 +209,10 @@ static int launch_nodes(jp_posterior* post, const JpFitLaunchParams& lp) {
   size_t smem = (size_t)(JP_FIT_TILE_DOUBLES + lp.d * lp.p + lp.d) * sizeof(double) + (size_t)lp.d * sizeof(int);
   if (smem > 48 * 1024)
     JP_CUDA(cudaFuncSetAttribute(jp_fit_nodes_kernel<F, DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEventRecord(post->ctx->ev_k0, post->ctx->stream);
   jp_fit_nodes_kernel<F, DPAD><<<grid, JP_FIT_THREADS, smem, post->ctx->stream>>>(lp);
+  cudaEventRecord(post->ctx->ev_k1, post->ctx->stream);
+  post->ctx->ev_valid = true;
   JP_CHECK_LAUNCH(post->ctx);
   return JP_OK;
 }
@@ -351,11 +354,11 @@ int jp_log_density_points(jp_ctx* ctx, const jp_data* data, int d, const int* h_
   jp_posterior tmp;   // only ctx is used by the launcher
   tmp.ctx = ctx;
   int st = JP_OK;
-  cudaError_t e = cudaMalloc(&d_x, (size_t)K * d * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&d_theta, (size_t)K * d * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&d_part, (size_t)K * (splits + 1) * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)K * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&d_code, (size_t)d * 4);
+  cudaError_t e = jp_dmalloc(ctx, &d_x, (size_t)K * d * 8);
+  if (e == cudaSuccess) e = jp_dmalloc(ctx, &d_theta, (size_t)K * d * 8);
+  if (e == cudaSuccess) e = jp_dmalloc(ctx, &d_part, (size_t)K * (splits + 1) * 8);
+  if (e == cudaSuccess) e = jp_dmalloc(ctx, &d_out, (size_t)K * 8);
+  if (e == cudaSuccess) e = jp_dmalloc(ctx, &d_code, (size_t)d * 4);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_x, h_x, (size_t)K * d * 8, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_code, h_transform, (size_t)d * 4, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) {
@@ -375,7 +378,7 @@ int jp_log_density_points(jp_ctx* ctx, const jp_data* data, int d, const int* h_
     if (st == JP_OK && e == cudaSuccess) e = cudaMemcpyAsync(h_ld, d_out, (size_t)K * 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (st == JP_OK && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   }
-  cudaFree(d_x); cudaFree(d_theta); cudaFree(d_part); cudaFree(d_out); cudaFree(d_code);
+  jp_dfree(ctx, d_x); jp_dfree(ctx, d_theta); jp_dfree(ctx, d_part); jp_dfree(ctx, d_out); jp_dfree(ctx, d_code);
   if (st != JP_OK) return st;
   if (e != cudaSuccess) {
     jp_set_error("jp_log_density_points: %s", cudaGetErrorString(e));

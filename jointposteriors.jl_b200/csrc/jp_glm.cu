@@ -129,9 +129,9 @@ extern "C" int jp_glm_grad_hess(jp_ctx* ctx, const jp_data* data, int d, const d
   int nE = d + d * (d + 1) / 2;
   int nb = jp_glm_num_blocks(ctx, data->N);
   double *d_beta = nullptr, *d_out = nullptr, *d_work = nullptr;
-  JP_CUDA(cudaMalloc(&d_beta, sizeof(double) * d));
-  JP_CUDA(cudaMalloc(&d_out, sizeof(double) * (nE + 1)));
-  JP_CUDA(cudaMalloc(&d_work, sizeof(double) * (size_t)nb * (nE + 1)));
+  JP_CUDA(jp_dmalloc(ctx, &d_beta, sizeof(double) * d));
+  JP_CUDA(jp_dmalloc(ctx, &d_out, sizeof(double) * (nE + 1)));
+  JP_CUDA(jp_dmalloc(ctx, &d_work, sizeof(double) * (size_t)nb * (nE + 1)));
   JP_CUDA(cudaMemcpyAsync(d_beta, h_beta, sizeof(double) * d, cudaMemcpyHostToDevice, ctx->stream));
   int st = jp_glm_sums_device(ctx, data, d, d_beta, d_out, d_work, nb);
   std::vector<double> out(nE + 1);
@@ -143,7 +143,7 @@ extern "C" int jp_glm_grad_hess(jp_ctx* ctx, const jp_data* data, int d, const d
       st = JP_ERR_CUDA;
     }
   }
-  cudaFree(d_beta); cudaFree(d_out); cudaFree(d_work);
+  jp_dfree(ctx, d_beta); jp_dfree(ctx, d_out); jp_dfree(ctx, d_work);
   JP_TRY(st);
   // add the N(0, s^2) prior and unpack
   double s2 = data->hyper[0] * data->hyper[0];

@@ -46,7 +46,8 @@ int jp_glm_num_blocks(const jp_ctx* ctx, long long N);
 #define TC_EPI_THREADS 256
 #define TC_MAX_STAGES 4
 #define TC_PREP_BLOCKS 296
-#define TC_NBOUND 10             // per-block bound partials, see tc_obs_prep_kernel
+#define TC_NBOUND 14             // per-block bound partials, see tc_obs_prep_kernel
+#define TC_NORD 5                // series lengths NC = 4, 6, 8, 10, 12 (orders 6 .. 14)
 
 // derivative polynomials of softplus in s = sigmoid(eta): f_1 = s, f_{k+1} = f_k'(s) (s - s^2)
 __constant__ double c_sp_poly[TC_ORDER_MAX + 1][TC_ORDER_MAX + 2];
@@ -92,17 +93,28 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+// epilogue-side wait: latency matters, spin on try_wait
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// producer / MMA-issuer wait: these single threads have thousands of cycles of slack (the kernel is bound by
+// the epilogue), and a tight spin steals issue slots from the epilogue warps of their SM sub-partition
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -174,9 +186,9 @@ __global__ void tc_split_x_kernel(int d, int ncols, int kp, long long N, long lo
 
 // Per observation: eta_hat, Taylor coefficients c_3 .. c_14 of the link remainder, t = |U' x| (so that
 // |Delta| <= t |z|), and the ingredients of the order / eligibility decision reduced per block:
-//   [0] max_i t_i   [1] sum |c_3| t^3   [2+j], [5+j] (j = 0,1,2 <-> NC = 4, 8, 12): truncation tail bounds of
+//   [0] max_i t_i   [1] sum |c_3| t^3   [2+j], [7+j] (j = 0..4 <-> NC = 4, 6, 8, 10, 12): truncation tail bounds of
 //   the series stopped at order NC + 2, summed over observations at |z| = z_ref and |z| = z_max
-//   [8] sum_i |R_i| and [9] sum_i R_i^2 at |z| = z_ref (majorants)
+//   [12] sum_i |R_i| and [13] sum_i R_i^2 at |z| = z_ref (majorants)
 __global__ void __launch_bounds__(256)
 tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N_pad, const double* __restrict__ obs,
                    const double* __restrict__ mu, const double* __restrict__ U, double z_ref, double z_max,
@@ -188,7 +200,7 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
   for (int k = threadIdx.x; k < d; k += blockDim.x) s_mu[k] = mu[k];
   for (int k = threadIdx.x; k < d * p; k += blockDim.x) s_U[k] = U[k];
   __syncthreads();
-  double b_tmax = 0, b_a1 = 0, b_ref[3] = {0, 0, 0}, b_max[3] = {0, 0, 0}, b_r = 0, b_r2 = 0;
+  double b_tmax = 0, b_a1 = 0, b_ref[TC_NORD] = {0}, b_max[TC_NORD] = {0}, b_r = 0, b_r2 = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N_pad; i += (long long)gridDim.x * blockDim.x) {
     float* o = coef + (size_t)i * TC_NCMAX;
     if (i >= N) {
@@ -229,8 +241,8 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
     b_r += sr;
     b_r2 += sr * sr;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int K = 4 * (j + 1) + 2;                    // last order kept
+    for (int j = 0; j < TC_NORD; ++j) {
+      const int K = 2 * j + 6;                          // last order kept (NC = K - 2 coefficients)
       // tail <= |c_{K+1}| t^{K+1} + |c_{K+2}| t^{K+2} / (1 - t / rho)   (geometric majorant of the remaining terms)
       double gr = tr < rho ? 1.0 / (1.0 - tr / rho) : 1e300, gm = tm < rho ? 1.0 / (1.0 - tm / rho) : 1e300;
       if (family != JP_FAM_LOGISTIC) { gr = exp(tr); gm = exp(tm); }
@@ -243,16 +255,16 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
   if (threadIdx.x == 0) ob[0] = v;
   v = jp_block_sum(b_a1, red);
   if (threadIdx.x == 0) ob[1] = v;
-  for (int j = 0; j < 3; ++j) {
+  for (int j = 0; j < TC_NORD; ++j) {
     v = jp_block_sum(b_ref[j], red);
     if (threadIdx.x == 0) ob[2 + j] = v;
     v = jp_block_sum(b_max[j], red);
-    if (threadIdx.x == 0) ob[5 + j] = v;
+    if (threadIdx.x == 0) ob[7 + j] = v;
   }
   v = jp_block_sum(b_r, red);
-  if (threadIdx.x == 0) ob[8] = v;
+  if (threadIdx.x == 0) ob[12] = v;
   v = jp_block_sum(b_r2, red);
-  if (threadIdx.x == 0) ob[9] = v;
+  if (threadIdx.x == 0) ob[13] = v;
 }
 
 // Per node: delta = U z, theta = mu + delta (all transforms are the identity on this path), the FP64
@@ -424,13 +436,13 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int node_tile = item / P.chunks, chunk = item % P.chunks;
         const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
-        mbar_wait(bar_bempty, bphase ^ 1);
+        mbar_wait_relaxed(bar_bempty, bphase ^ 1);
         mbar_expect_tx(bar_bfull, b_bytes);
         for (int a = 0; a < P.ka; ++a)
           tma_load_2d(sB + (uint32_t)a * TC_NODE_TILE * 128u, &tmB, bar_bfull, a * TC_KATOM, node_tile * TC_NODE_TILE);
         bphase ^= 1;
         for (int t = t0; t < t1; ++t) {
-          mbar_wait(bar_empty + 8u * stage, phase ^ 1);
+          mbar_wait_relaxed(bar_empty + 8u * stage, phase ^ 1);
           mbar_expect_tx(bar_full + 8u * stage, a_bytes);
           for (int a = 0; a < P.ka; ++a)
             tma_load_2d(sA + (uint32_t)stage * a_bytes + (uint32_t)a * TC_OBS_TILE * 128u, &tmA, bar_full + 8u * stage,
@@ -450,11 +462,11 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int chunk = item % P.chunks;
         const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
-        mbar_wait(bar_bfull, bphase);
+        mbar_wait_relaxed(bar_bfull, bphase);
         bphase ^= 1;
         for (int t = t0; t < t1; ++t) {
-          mbar_wait(bar_tempty + 8u * buf, tphase[buf] ^ 1);
-          mbar_wait(bar_full + 8u * stage, phase);
+          mbar_wait_relaxed(bar_tempty + 8u * buf, tphase[buf] ^ 1);
+          mbar_wait_relaxed(bar_full + 8u * stage, phase);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC_NODE_TILE;
           for (int a = 0; a < P.ka; ++a) {
@@ -488,12 +500,12 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
       for (int t = t0; t < t1; ++t) {
         // this thread's observation: row of the tile = TMEM lane
-        const float4* cp = reinterpret_cast<const float4*>(P.coef + ((size_t)t * TC_OBS_TILE + q * 32 + lane) * TC_NCMAX);
+        const float2* cp = reinterpret_cast<const float2*>(P.coef + ((size_t)t * TC_OBS_TILE + q * 32 + lane) * TC_NCMAX);
         float c[NC];
 #pragma unroll
-        for (int k = 0; k < NC / 4; ++k) {
-          const float4 f = __ldg(cp + k);
-          c[4 * k] = f.x; c[4 * k + 1] = f.y; c[4 * k + 2] = f.z; c[4 * k + 3] = f.w;
+        for (int k = 0; k < NC / 2; ++k) {
+          const float2 f = __ldg(cp + k);
+          c[2 * k] = f.x; c[2 * k + 1] = f.y;
         }
         mbar_wait(bar_tfull + 8u * buf, tphase[buf]);
         tphase[buf] ^= 1;
@@ -628,14 +640,15 @@ bool jp_fit_tc_supported(const jp_posterior* post, const jp_fit_args* args) { re
 void jp_tc_data_free(jp_data* data) {
   TcDataState* s = static_cast<TcDataState*>(data->tc_state);
   if (!s) return;
-  cudaFree(s->d_xs); cudaFree(s->d_coef); cudaFree(s->d_sums); cudaFree(s->d_work); cudaFree(s->d_bounds);
+  jp_dfree(data->ctx, s->d_xs); jp_dfree(data->ctx, s->d_coef); jp_dfree(data->ctx, s->d_sums);
+  jp_dfree(data->ctx, s->d_work); jp_dfree(data->ctx, s->d_bounds);
   delete s;
   data->tc_state = nullptr;
 }
 void jp_tc_post_free(jp_posterior* post) {
   TcPostState* s = static_cast<TcPostState*>(post->tc_state);
   if (!s) return;
-  cudaFree(s->d_ds); cudaFree(s->d_quad);
+  jp_dfree(post->ctx, s->d_ds); jp_dfree(post->ctx, s->d_quad);
   delete s;
   post->tc_state = nullptr;
 }
@@ -651,11 +664,11 @@ static int ensure_data_state(jp_ctx* ctx, jp_data* data, int d) {
   s->N_pad = ((data->N + TC_OBS_TILE - 1) / TC_OBS_TILE) * TC_OBS_TILE;
   const int nE = d + d * (d + 1) / 2;
   s->glm_blocks = jp_glm_num_blocks(ctx, data->N);
-  JP_CUDA(cudaMalloc(&s->d_xs, (size_t)s->N_pad * s->kp * sizeof(float)));
-  JP_CUDA(cudaMalloc(&s->d_coef, (size_t)s->N_pad * TC_NCMAX * sizeof(float)));
-  JP_CUDA(cudaMalloc(&s->d_sums, (size_t)(nE + 1) * 8));
-  JP_CUDA(cudaMalloc(&s->d_work, (size_t)s->glm_blocks * (nE + 1) * 8));
-  JP_CUDA(cudaMalloc(&s->d_bounds, (size_t)TC_PREP_BLOCKS * TC_NBOUND * 8));
+  JP_CUDA(jp_dmalloc(ctx, &s->d_xs, (size_t)s->N_pad * s->kp * sizeof(float)));
+  JP_CUDA(jp_dmalloc(ctx, &s->d_coef, (size_t)s->N_pad * TC_NCMAX * sizeof(float)));
+  JP_CUDA(jp_dmalloc(ctx, &s->d_sums, (size_t)(nE + 1) * 8));
+  JP_CUDA(jp_dmalloc(ctx, &s->d_work, (size_t)s->glm_blocks * (nE + 1) * 8));
+  JP_CUDA(jp_dmalloc(ctx, &s->d_bounds, (size_t)TC_PREP_BLOCKS * TC_NBOUND * 8));
   tc_split_x_kernel<<<(unsigned)((s->N_pad + 255) / 256), 256, 0, ctx->stream>>>(d, data->ncols, s->kp, s->N, s->N_pad,
                                                                                   data->d_obs, s->d_xs);
   JP_CHECK_LAUNCH(ctx);
@@ -669,14 +682,14 @@ static int ensure_post_state(jp_posterior* post, int kp) {
   post->tc_state = s;
   s->kp = kp;
   s->M_pad = ((post->M + TC_NODE_TILE - 1) / TC_NODE_TILE) * TC_NODE_TILE;
-  JP_CUDA(cudaMalloc(&s->d_ds, (size_t)s->M_pad * kp * sizeof(float)));
+  JP_CUDA(jp_dmalloc(post->ctx, &s->d_ds, (size_t)s->M_pad * kp * sizeof(float)));
   JP_CUDA(cudaMemsetAsync(s->d_ds, 0, (size_t)s->M_pad * kp * sizeof(float), post->ctx->stream));
-  JP_CUDA(cudaMalloc(&s->d_quad, (size_t)post->M * 8));
+  JP_CUDA(jp_dmalloc(post->ctx, &s->d_quad, (size_t)post->M * 8));
   JP_TRY(make_tensor_map(&s->tmB, s->d_ds, s->M_pad, kp, TC_NODE_TILE));
   return JP_OK;
 }
 
-// Order / eligibility decision from the reduced bounds (see tc_obs_prep_kernel).  Returns NC in {4, 8, 12}
+// Order / eligibility decision from the reduced bounds (see tc_obs_prep_kernel).  Returns NC in {4, 6, .. 12}
 // or 0 when the series is not trustworthy for this (data, U, grid) and the FP64 kernel must be used.
 //   * series convergence (rigorous): max_i |Delta_i| <= t_max z_max must stay well inside the radius pi
 //   * truncation (rigorous): tail summed over ALL observations <= 1e-9 at |z| = z_ref = min(z_max, 6) and
@@ -688,12 +701,12 @@ static int ensure_post_state(jp_posterior* post, int kp) {
 static int jp_tc_choose_order(const double* b, double* err_trunc, double* err_round) {
   const double tdelta = b[0];
   if (!(tdelta <= 2.0)) return 0;
-  *err_round = 2e-6 * std::sqrt(b[9]);
+  *err_round = 2e-6 * std::sqrt(b[13]);
   if (!(8.0 * *err_round <= 2e-7)) return 0;
-  for (int j = 0; j < 3; ++j)
-    if (b[2 + j] <= 1e-9 && b[5 + j] <= 1e-4) {
+  for (int j = 0; j < TC_NORD; ++j)
+    if (b[2 + j] <= 1e-9 && b[7 + j] <= 1e-4) {
       *err_trunc = b[2 + j];
-      return 4 * (j + 1);
+      return 2 * j + 4;
     }
   return 0;
 }
@@ -702,7 +715,10 @@ template <int NC>
 static int launch_tc(jp_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcKernelParams& kp, size_t smem) {
   JP_CUDA(cudaFuncSetAttribute(jp_glm_tc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = std::min(ctx->sm_count, kp.n_node_tiles * kp.chunks);
+  cudaEventRecord(ctx->ev_k0, ctx->stream);
   jp_glm_tc_kernel<NC><<<grid, TC_THREADS, smem, ctx->stream>>>(tmA, tmB, kp);
+  cudaEventRecord(ctx->ev_k1, ctx->stream);
+  ctx->ev_valid = true;
   JP_CHECK_LAUNCH(ctx);
   return JP_OK;
 }
@@ -741,10 +757,10 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   double err_trunc = 0, err_round = 0;
   const int NC = jp_tc_choose_order(b, &err_trunc, &err_round);
   post->tc_bounds[0] = b[0]; post->tc_bounds[1] = err_trunc; post->tc_bounds[2] = err_round; post->tc_bounds[3] = NC;
-  post->tc_bounds[4] = 2e-6 * b[8];
+  post->tc_bounds[4] = 2e-6 * b[12];
   if (NC == 0) {
     jp_set_error("tensor-core path: series bounds not met (max |Delta| %.3g, rounding estimate %.3g, truncation bounds %.3g/%.3g "
-                 "at order 14); use the FP64 path", b[0], 2e-6 * std::sqrt(b[9]), b[4], b[7]);
+                 "at order 14); use the FP64 path", b[0], 2e-6 * std::sqrt(b[13]), b[6], b[11]);
     return JP_ERR_UNSUPPORTED;
   }
   // node operand, theta, FP64 quadratic part
@@ -783,7 +799,9 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   kp.part = post->d_part;
   int stc;
   if (NC == 4) stc = launch_tc<4>(ctx, ds->tmA, ps->tmB, kp, smem);
+  else if (NC == 6) stc = launch_tc<6>(ctx, ds->tmA, ps->tmB, kp, smem);
   else if (NC == 8) stc = launch_tc<8>(ctx, ds->tmA, ps->tmB, kp, smem);
+  else if (NC == 10) stc = launch_tc<10>(ctx, ds->tmA, ps->tmB, kp, smem);
   else stc = launch_tc<12>(ctx, ds->tmA, ps->tmB, kp, smem);
   JP_TRY(stc);
   tc_finish_kernel<<<(unsigned)((post->M + 255) / 256), 256, 0, st>>>(post->M, post->m0, kp.chunks, post->d_part, ps->d_quad,

@@ -49,7 +49,7 @@ static int upload_rules() {
     JP_CUDA(cudaMemcpyToSymbol(c_rule_nodes, nodes, sizeof nodes, sizeof(double) * JP_RULE_NMAX * r));
     JP_CUDA(cudaMemcpyToSymbol(c_rule_weights, weights, sizeof weights, sizeof(double) * JP_RULE_LMAX * JP_RULE_NMAX * r));
     JP_CUDA(cudaMemcpyToSymbol(c_rule_npts, npts, sizeof npts, sizeof(int) * JP_RULE_LMAX * r));
-    JP_CUDA(cudaMalloc(&g_rule_nodes_dev[r], sizeof(double) * JP_RULE_NMAX));
+    JP_CUDA(cudaMalloc (&g_rule_nodes_dev[r], sizeof(double) * JP_RULE_NMAX));
     JP_CUDA(cudaMemcpy(g_rule_nodes_dev[r], nodes, sizeof nodes, cudaMemcpyHostToDevice));
   }
   done = true;
@@ -307,12 +307,12 @@ int jp_grid_build(jp_ctx* ctx, int rule, int d, int level, jp_grid* g) {
   unsigned long long *d_comp = nullptr, *d_npts = nullptr, *d_off = nullptr;
   uint8_t* d_mi = nullptr;
   double* d_coef = nullptr;
-  JP_CUDA(cudaMalloc(&d_comp, comp.size() * 8));
+  JP_CUDA(jp_dmalloc(ctx, &d_comp, comp.size() * 8));
   JP_CUDA(cudaMemcpyAsync(d_comp, comp.data(), comp.size() * 8, cudaMemcpyHostToDevice, st));
-  JP_CUDA(cudaMalloc(&d_mi, n_mi * d));
-  JP_CUDA(cudaMalloc(&d_coef, n_mi * 8));
-  JP_CUDA(cudaMalloc(&d_npts, n_mi * 8));
-  JP_CUDA(cudaMalloc(&d_off, (n_mi + 1) * 8));
+  JP_CUDA(jp_dmalloc(ctx, &d_mi, n_mi * d));
+  JP_CUDA(jp_dmalloc(ctx, &d_coef, n_mi * 8));
+  JP_CUDA(jp_dmalloc(ctx, &d_npts, n_mi * 8));
+  JP_CUDA(jp_dmalloc(ctx, &d_off, (n_mi + 1) * 8));
   jp_enum_kernel<<<(unsigned)((n_mi + 255) / 256), 256, 0, st>>>(P, d_comp, smax, n_mi, d_mi, d_coef, d_npts);
   JP_CHECK_LAUNCH(ctx);
   jp_scan64_kernel<<<1, 1024, 0, st>>>(d_npts, d_off, n_mi);
@@ -335,13 +335,13 @@ int jp_grid_build(jp_ctx* ctx, int rule, int d, int level, jp_grid* g) {
   double* d_wt = nullptr;
   uint32_t *d_pa = nullptr, *d_pb = nullptr, *d_hist = nullptr, *d_head = nullptr, *d_seg = nullptr, *d_start = nullptr;
   int nb = jp_sort_blocks((long long)Ptot);
-  JP_CUDA(cudaMalloc(&d_keys, Ptot * d));
-  JP_CUDA(cudaMalloc(&d_wt, Ptot * 8));
-  JP_CUDA(cudaMalloc(&d_pa, Ptot * 4));
-  JP_CUDA(cudaMalloc(&d_pb, Ptot * 4));
-  JP_CUDA(cudaMalloc(&d_hist, (size_t)JP_SORT_BINS * nb * 4));
-  JP_CUDA(cudaMalloc(&d_head, Ptot * 4));
-  JP_CUDA(cudaMalloc(&d_seg, (Ptot + 1) * 4));
+  JP_CUDA(jp_dmalloc(ctx, &d_keys, Ptot * d));
+  JP_CUDA(jp_dmalloc(ctx, &d_wt, Ptot * 8));
+  JP_CUDA(jp_dmalloc(ctx, &d_pa, Ptot * 4));
+  JP_CUDA(jp_dmalloc(ctx, &d_pb, Ptot * 4));
+  JP_CUDA(jp_dmalloc(ctx, &d_hist, (size_t)JP_SORT_BINS * nb * 4));
+  JP_CUDA(jp_dmalloc(ctx, &d_head, Ptot * 4));
+  JP_CUDA(jp_dmalloc(ctx, &d_seg, (Ptot + 1) * 4));
   unsigned gp = (unsigned)((Ptot + 255) / 256);
   jp_expand_kernel<<<gp, 256, 0, st>>>(d, rule, n_mi, d_mi, d_coef, d_off, Ptot, d_keys, d_wt);
   JP_CHECK_LAUNCH(ctx);
@@ -361,12 +361,12 @@ int jp_grid_build(jp_ctx* ctx, int rule, int d, int level, jp_grid* g) {
   JP_CUDA(cudaMemcpyAsync(&M32, d_seg + Ptot, 4, cudaMemcpyDeviceToHost, st));
   JP_CUDA(cudaStreamSynchronize(st));
   long long M = M32;
-  JP_CUDA(cudaMalloc(&d_start, (size_t)M * 4));
+  JP_CUDA(jp_dmalloc(ctx, &d_start, (size_t)M * 4));
   jp_segstart_kernel<<<gp, 256, 0, st>>>(Ptot, d_head, d_seg, d_start);
   JP_CHECK_LAUNCH(ctx);
-  JP_CUDA(cudaMalloc(&g->d_idx, (size_t)M * d));
-  JP_CUDA(cudaMalloc(&g->d_w, (size_t)M * 8));
-  JP_CUDA(cudaMalloc(&g->d_hzz, (size_t)M * 8));
+  JP_CUDA(jp_dmalloc(ctx, &g->d_idx, (size_t)M * d));
+  JP_CUDA(jp_dmalloc(ctx, &g->d_w, (size_t)M * 8));
+  JP_CUDA(jp_dmalloc(ctx, &g->d_hzz, (size_t)M * 8));
   jp_merge_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(d, rule, Ptot, M, d_keys, d_wt, pin, d_start,
                                                                  g->d_idx, g->d_w, g->d_hzz);
   JP_CHECK_LAUNCH(ctx);
@@ -382,8 +382,8 @@ int jp_grid_build(jp_ctx* ctx, int rule, int d, int level, jp_grid* g) {
     g->zmax2 = mx;
   }
   g->ctx = ctx; g->rule = rule; g->d = d; g->level = level; g->M = M;
-  cudaFree(d_comp); cudaFree(d_mi); cudaFree(d_coef); cudaFree(d_npts); cudaFree(d_off);
-  cudaFree(d_keys); cudaFree(d_wt); cudaFree(d_pa); cudaFree(d_pb); cudaFree(d_hist);
-  cudaFree(d_head); cudaFree(d_seg); cudaFree(d_start);
+  jp_dfree(ctx, d_comp); jp_dfree(ctx, d_mi); jp_dfree(ctx, d_coef); jp_dfree(ctx, d_npts); jp_dfree(ctx, d_off);
+  jp_dfree(ctx, d_keys); jp_dfree(ctx, d_wt); jp_dfree(ctx, d_pa); jp_dfree(ctx, d_pb); jp_dfree(ctx, d_hist);
+  jp_dfree(ctx, d_head); jp_dfree(ctx, d_seg); jp_dfree(ctx, d_start);
   return JP_OK;
 }

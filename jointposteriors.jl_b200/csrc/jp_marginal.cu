@@ -214,20 +214,20 @@ jp_local_knots_kernel(const double* const* __restrict__ vptr, const double* __re
 // ------------------------------------------------------------------------------------ host side
 static int ensure_marginal_buffers(jp_posterior* post, int K) {
   if (K <= post->K_cap) return JP_OK;
-  cudaFree(post->d_vals); cudaFree((void*)post->d_vptr); cudaFree(post->d_perm_a); cudaFree(post->d_perm_b);
-  cudaFree(post->d_hist); cudaFree(post->d_sv); cudaFree(post->d_sw); cudaFree(post->d_cw); cudaFree(post->d_mout);
+  jp_dfree(post->ctx, post->d_vals); jp_dfree(post->ctx, (void*)post->d_vptr); jp_dfree(post->ctx, post->d_perm_a); jp_dfree(post->ctx, post->d_perm_b);
+  jp_dfree(post->ctx, post->d_hist); jp_dfree(post->ctx, post->d_sv); jp_dfree(post->ctx, post->d_sw); jp_dfree(post->ctx, post->d_cw); jp_dfree(post->ctx, post->d_mout);
   post->K_cap = 0;
   size_t KM = (size_t)K * post->M;
   int nb = jp_sort_blocks(post->M);
-  JP_CUDA(cudaMalloc(&post->d_vals, KM * 8));
-  JP_CUDA(cudaMalloc((void**)&post->d_vptr, (size_t)K * sizeof(double*)));
-  JP_CUDA(cudaMalloc(&post->d_perm_a, KM * 4));
-  JP_CUDA(cudaMalloc(&post->d_perm_b, KM * 4));
-  JP_CUDA(cudaMalloc(&post->d_hist, (size_t)K * JP_SORT_BINS * nb * 4));
-  JP_CUDA(cudaMalloc(&post->d_sv, KM * 8));
-  JP_CUDA(cudaMalloc(&post->d_sw, KM * 8));
-  JP_CUDA(cudaMalloc(&post->d_cw, KM * 8));
-  JP_CUDA(cudaMalloc(&post->d_mout, (size_t)K * JP_MOUT_STRIDE * 8));
+  JP_CUDA(jp_dmalloc(post->ctx, &post->d_vals, KM * 8));
+  JP_CUDA(jp_dmalloc(post->ctx, (void**)&post->d_vptr, (size_t)K * sizeof(double*)));
+  JP_CUDA(jp_dmalloc(post->ctx, &post->d_perm_a, KM * 4));
+  JP_CUDA(jp_dmalloc(post->ctx, &post->d_perm_b, KM * 4));
+  JP_CUDA(jp_dmalloc(post->ctx, &post->d_hist, (size_t)K * JP_SORT_BINS * nb * 4));
+  JP_CUDA(jp_dmalloc(post->ctx, &post->d_sv, KM * 8));
+  JP_CUDA(jp_dmalloc(post->ctx, &post->d_sw, KM * 8));
+  JP_CUDA(jp_dmalloc(post->ctx, &post->d_cw, KM * 8));
+  JP_CUDA(jp_dmalloc(post->ctx, &post->d_mout, (size_t)K * JP_MOUT_STRIDE * 8));
   post->K_cap = K;
   return JP_OK;
 }

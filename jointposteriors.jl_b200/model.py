@@ -99,6 +99,12 @@ class Context:
     def launches(self):
         return int(lib().jp_ctx_launch_count(self.handle))
 
+    def last_kernel_ms(self):
+        """Device time of the last node x observation log-density kernel launch (CUDA events, blocking)."""
+        ms = C.c_float()
+        check(lib().jp_ctx_last_kernel_ms(self.handle, C.byref(ms)))
+        return float(ms.value)
+
     def grid(self, rule_id, d_eff, level):
         g = C.c_void_p()
         check(lib().jp_grid_get(self.handle, C.c_int(rule_id), C.c_int(d_eff), C.c_int(level), C.byref(g)))
