@@ -5,7 +5,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libjpcuda.so")
+# JPCUDA_LIB selects an alternative build of the same library (kernel A/B experiments); default: the in-tree build
+_SO = os.environ.get("JPCUDA_LIB") or os.path.join(_HERE, "libjpcuda.so")
 _lib = None
 
 JP_OK, JP_ERR_BAD_ARG, JP_ERR_NOT_PD, JP_ERR_CUDA, JP_ERR_NO_DEVICE, JP_ERR_ALLOC, JP_ERR_UNSUPPORTED = range(7)

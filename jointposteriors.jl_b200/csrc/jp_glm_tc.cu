@@ -16,12 +16,13 @@
 // the path; outside them the FP64 plugin kernel of jp_fit.cu is used).
 //
 // Kernel (one persistent CTA per SM, warp-specialised):
-//   warp 0      TMA producer: node-tile operand (256 nodes x K) once per work item, observation tiles
+//   warp 0      TMA producer: node-tile operand (128 nodes x K) once per work item, observation tiles
 //               (128 obs x K) through a ring of shared-memory stages; 128-byte swizzle, K-major
 //   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::tf32, M = 128 (observations on TMEM lanes),
-//               N = 256 (nodes on TMEM columns), K = 8 per instruction; accumulators double-buffered in
-//               TMEM (2 x 256 columns); tcgen05.commit releases stages / publishes accumulators
-//   warps 2-9   epilogue: tcgen05.ld 16 columns at a time, R = D^3 (c3 + D (c4 + ...)) by Horner with the
+//               N = 128 (nodes on TMEM columns), K = 8 per instruction; four accumulator buffers in
+//               TMEM (4 x 128 columns); tcgen05.commit releases stages / publishes accumulators
+//   warps 2-9   epilogue: tcgen05.ld 16 columns at a time, R = D^3 (c3 + D (c4 + ...)) by Horner (packed
+//               FFMA2, two node columns per instruction) with the
 //               calling thread's own observation coefficients held in registers, accumulated per
 //               (thread = observation lane, column = node) in FP32 registers over all observation tiles of
 //               the item; per item one shuffle transpose-reduce + shared-memory combine in FP64.
@@ -30,6 +31,7 @@
 #include <cuda.h>
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 #include "jp_common.cuh"
 
@@ -38,7 +40,12 @@ int jp_glm_sums_device(jp_ctx* ctx, const jp_data* data, int d, const double* d_
 int jp_glm_num_blocks(const jp_ctx* ctx, long long N);
 
 #define TC_OBS_TILE 128          // MMA M: observations per tile (TMEM lanes)
-#define TC_NODE_TILE 256         // MMA N: nodes per tile (TMEM columns)
+#ifndef TC_NODE_TILE
+#define TC_NODE_TILE 128         // MMA N: nodes per tile (TMEM columns)
+#endif
+#define TC_NBUF (512 / TC_NODE_TILE)            // accumulator buffers in TMEM (all 512 columns)
+#define TC_COLS_PER_WARP (TC_NODE_TILE / 2)     // each epilogue warp owns one lane quarter x half of the node columns
+#define TC_NCH (TC_COLS_PER_WARP / 16)          // 16-column tcgen05.ld chunks per warp and tile (even)
 #define TC_KATOM 32              // fp32 elements per 128-byte swizzle atom
 #define TC_NCMAX 12              // stored Taylor coefficients per observation: orders 3 .. 14
 #define TC_ORDER_MAX 16          // highest derivative order tabulated (tail bounds need two more than used)
@@ -352,16 +359,50 @@ struct TcKernelParams {
   double* part;           // [chunks][M]
 };
 
-template <int NC>
-__device__ __forceinline__ void tc_accumulate16(const uint32_t (&v)[16], const float (&c)[NC], float* acc) {
+// Packed FP32 arithmetic (Blackwell FFMA2 / FMUL2): one instruction works on two adjacent node columns, which
+// halves the issue slots of the epilogue -- the resource this kernel is bound by.
+__device__ __forceinline__ uint64_t f32x2_pack(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f32x2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// acc[j] += D^3 (c_3 + c_4 D + ... ) for 16 columns = 8 packed pairs; c2[k] holds (c_{3+k}, c_{3+k}).
+// Estrin form: e_m = c_{3+2m} + c_{4+2m} D are independent and share the operand D, then Horner in D^2.
+// Same instruction count as plain Horner (NC + 2 per pair), but a column pair carries its own instruction-
+// level parallelism and consecutive instructions reuse D (or D^2) in the same operand slot, which matters
+// because an FFMA2 with three distinct 64-bit register operands is register-file-bandwidth bound.
+template <int NC, int MODE>
+__device__ __forceinline__ void tc_accumulate16(const uint32_t (&v)[16], const uint64_t (&c2)[NC], uint64_t* acc2) {
+  if (MODE == 1) {   // profiling aid: TMEM traffic without the series arithmetic (results are meaningless)
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float D = __uint_as_float(v[j]);
-    float pl = c[NC - 1];
+    for (int j = 0; j < 8; ++j) acc2[j] = f32x2_fma(f32x2_pack(v[2 * j], v[2 * j + 1]), c2[0], acc2[j]);
+    return;
+  }
 #pragma unroll
-    for (int k = NC - 2; k >= 0; --k) pl = fmaf(pl, D, c[k]);
-    const float D2 = D * D;
-    acc[j] = fmaf(D2 * D, pl, acc[j]);
+  for (int j = 0; j < 8; ++j) {
+    const uint64_t D = f32x2_pack(v[2 * j], v[2 * j + 1]);
+    uint64_t e[NC / 2];
+#pragma unroll
+    for (int m = 0; m < NC / 2; ++m) e[m] = f32x2_fma(c2[2 * m + 1], D, c2[2 * m]);
+    const uint64_t D2 = f32x2_mul(D, D);
+    uint64_t t = e[NC / 2 - 1];
+#pragma unroll
+    for (int m = NC / 2 - 2; m >= 0; --m) t = f32x2_fma(t, D2, e[m]);
+    acc2[j] = f32x2_fma(f32x2_mul(D2, D), t, acc2[j]);
   }
 }
 
@@ -380,7 +421,9 @@ __device__ __forceinline__ float tc_transpose_reduce32(float* v, int lane) {
   return v[0];
 }
 
-template <int NC>
+// MODE 0 is the product; 1 (no series arithmetic) and 2 (no TMEM loads) exist only to attribute time to the
+// two resources the epilogue contends for (JP_TC_DEBUG_MODE, profiling builds of bench.py only)
+template <int NC, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcKernelParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -397,9 +440,9 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t bar_empty = bar_full + 8u * TC_MAX_STAGES; // [stages]
   const uint32_t bar_bfull = bar_empty + 8u * TC_MAX_STAGES;
   const uint32_t bar_bempty = bar_bfull + 8u;
-  const uint32_t bar_tfull = bar_bempty + 8u;               // [2]
-  const uint32_t bar_tempty = bar_tfull + 16u;              // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 6);
+  const uint32_t bar_tfull = bar_bempty + 8u;               // [TC_NBUF]
+  const uint32_t bar_tempty = bar_tfull + 8u * TC_NBUF;     // [TC_NBUF]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 2 + 2 * TC_NBUF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -409,7 +452,7 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     mbar_init(bar_bfull, 1);
     mbar_init(bar_bempty, 1);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < TC_NBUF; ++b) {
       mbar_init(bar_tfull + 8u * b, 1);
       mbar_init(bar_tempty + 8u * b, TC_EPI_THREADS / 32);
     }
@@ -417,7 +460,7 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
-  if (warp == 1) {   // TMEM: all 512 columns (two 256-column accumulator buffers)
+  if (warp == 1) {   // TMEM: all 512 columns (four 128-column accumulator buffers)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -454,18 +497,18 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
-      // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128
+      // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_NODE_TILE >> 3) << 17) |
                              ((uint32_t)(TC_OBS_TILE >> 4) << 24);
       int stage = 0, buf = 0;
-      uint32_t phase = 0, bphase = 0, tphase[2] = {0, 0};
+      uint32_t phase = 0, bphase = 0, tphase = 0;   // tphase: bit b = parity of accumulator buffer b
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int chunk = item % P.chunks;
         const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
         mbar_wait_relaxed(bar_bfull, bphase);
         bphase ^= 1;
         for (int t = t0; t < t1; ++t) {
-          mbar_wait_relaxed(bar_tempty + 8u * buf, tphase[buf] ^ 1);
+          mbar_wait_relaxed(bar_tempty + 8u * buf, ((tphase >> buf) & 1u) ^ 1u);
           mbar_wait_relaxed(bar_full + 8u * stage, phase);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC_NODE_TILE;
@@ -478,8 +521,8 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           tc_commit(bar_empty + 8u * stage);        // frees the observation stage when the MMAs have read it
           tc_commit(bar_tfull + 8u * buf);          // publishes the accumulator buffer
-          tphase[buf] ^= 1;
-          buf ^= 1;
+          tphase ^= 1u << buf;
+          buf = (buf + 1) % TC_NBUF;
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
         tc_commit(bar_bempty);                      // node operand may be overwritten once every MMA has retired
@@ -490,59 +533,89 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int h = (warp - 2) >> 2;           // column half handled by this warp
     const int et = threadIdx.x - 64;         // 0 .. 255
-    float acc[128];
+    uint64_t acc2[TC_COLS_PER_WARP / 2];     // 64 FP32 accumulators, packed in pairs of adjacent columns
 #pragma unroll
-    for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+    for (int j = 0; j < TC_COLS_PER_WARP / 2; ++j) acc2[j] = 0ull;
     int buf = 0;
-    uint32_t tphase[2] = {0, 0};
+    uint32_t tphase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int node_tile = item / P.chunks, chunk = item % P.chunks;
       const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
-      for (int t = t0; t < t1; ++t) {
+      // Software pipeline over (tile, 16-column chunk): the tcgen05.ld of the next chunk -- across a tile
+      // boundary too, the next accumulator buffer is normally complete long before -- and the coefficient
+      // loads of the next tile are in flight while the current chunk is evaluated.
+      uint32_t va[16], vb[16];
+      uint64_t c2[NC];
+      auto load_coef = [&](int t, uint64_t (&dst)[NC]) {
         // this thread's observation: row of the tile = TMEM lane
         const float2* cp = reinterpret_cast<const float2*>(P.coef + ((size_t)t * TC_OBS_TILE + q * 32 + lane) * TC_NCMAX);
-        float c[NC];
 #pragma unroll
         for (int k = 0; k < NC / 2; ++k) {
           const float2 f = __ldg(cp + k);
-          c[2 * k] = f.x; c[2 * k + 1] = f.y;
+          dst[2 * k] = f32x2_pack(__float_as_uint(f.x), __float_as_uint(f.x));
+          dst[2 * k + 1] = f32x2_pack(__float_as_uint(f.y), __float_as_uint(f.y));
         }
-        mbar_wait(bar_tfull + 8u * buf, tphase[buf]);
-        tphase[buf] ^= 1;
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_NODE_TILE + h * 128);
-        uint32_t va[16], vb[16];
-        tmem_ld16(va, taddr);
+      };
+      auto tile_addr = [&](int b) {
+        return tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * TC_NODE_TILE + h * TC_COLS_PER_WARP);
+      };
+      load_coef(t0, c2);
+      mbar_wait(bar_tfull + 8u * buf, (tphase >> buf) & 1u);
+      tphase ^= 1u << buf;
+      tc_fence_after();
+      tmem_ld16(va, tile_addr(buf));
+      for (int t = t0; t < t1; ++t) {
+        const bool more = t + 1 < t1;
+        const int nbuf = (buf + 1) % TC_NBUF;
+        uint64_t cn[NC];
+        if (more) load_coef(t + 1, cn);
+        const uint32_t taddr = tile_addr(buf);
 #pragma unroll
-        for (int cc = 0; cc < 8; cc += 2) {
+        for (int cc = 0; cc < TC_NCH; cc += 2) {
           tmem_ld_wait16(va);
-          tmem_ld16(vb, taddr + 16u * (cc + 1));
-          tc_accumulate16<NC>(va, c, acc + 16 * cc);
+          if (MODE != 2) tmem_ld16(vb, taddr + 16u * (cc + 1));
+          tc_accumulate16<NC, MODE>(va, c2, acc2 + 8 * cc);
           tmem_ld_wait16(vb);
-          if (cc + 2 < 8) tmem_ld16(va, taddr + 16u * (cc + 2));
-          tc_accumulate16<NC>(vb, c, acc + 16 * (cc + 1));
+          if (cc + 2 < TC_NCH) {
+            if (MODE != 2) tmem_ld16(va, taddr + 16u * (cc + 2));
+          } else if (more) {
+            mbar_wait(bar_tfull + 8u * nbuf, (tphase >> nbuf) & 1u);
+            tphase ^= 1u << nbuf;
+            tc_fence_after();
+            if (MODE != 2) tmem_ld16(va, tile_addr(nbuf));
+          }
+          tc_accumulate16<NC, MODE>(vb, c2, acc2 + 8 * (cc + 1));
         }
+        // every tcgen05.ld of this tile has completed (the last wait above precedes the prefetch's issue only
+        // for the next buffer): hand the accumulator buffer back to the MMA issuer
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8u * buf);
-        buf ^= 1;
+        buf = nbuf;
+        if (more) {
+#pragma unroll
+          for (int k = 0; k < NC; ++k) c2[k] = cn[k];
+        }
       }
       // flush the item: sum over the 32 observation lanes by transpose-reduce, over the 4 lane quarters in
       // shared memory (FP64), one partial per (chunk, node)
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float s = tc_transpose_reduce32(acc + 32 * g, lane);
-        red[q * TC_NODE_TILE + h * 128 + g * 32 + lane] = (double)s;
+      for (int g = 0; g < TC_COLS_PER_WARP / 32; ++g) {
+        float col[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f32x2_unpack(acc2[16 * g + j], col[2 * j], col[2 * j + 1]);
+        const float s = tc_transpose_reduce32(col, lane);
+        red[q * TC_NODE_TILE + h * TC_COLS_PER_WARP + g * 32 + lane] = (double)s;
       }
       epi_bar_sync();
-      {
+      if (et < TC_NODE_TILE) {
         const double s = (red[et] + red[TC_NODE_TILE + et]) + (red[2 * TC_NODE_TILE + et] + red[3 * TC_NODE_TILE + et]);
         const long long node = (long long)node_tile * TC_NODE_TILE + et;
         if (node < P.M) P.part[(size_t)chunk * P.M + node] = s;
       }
       epi_bar_sync();
 #pragma unroll
-      for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+      for (int j = 0; j < TC_COLS_PER_WARP / 2; ++j) acc2[j] = 0ull;
     }
   }
   tc_fence_before();
@@ -711,16 +784,26 @@ static int jp_tc_choose_order(const double* b, double* err_trunc, double* err_ro
   return 0;
 }
 
-template <int NC>
-static int launch_tc(jp_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcKernelParams& kp, size_t smem) {
-  JP_CUDA(cudaFuncSetAttribute(jp_glm_tc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int NC, int MODE>
+static int launch_tc_mode(jp_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcKernelParams& kp, size_t smem) {
+  JP_CUDA(cudaFuncSetAttribute(jp_glm_tc_kernel<NC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = std::min(ctx->sm_count, kp.n_node_tiles * kp.chunks);
   cudaEventRecord(ctx->ev_k0, ctx->stream);
-  jp_glm_tc_kernel<NC><<<grid, TC_THREADS, smem, ctx->stream>>>(tmA, tmB, kp);
+  jp_glm_tc_kernel<NC, MODE><<<grid, TC_THREADS, smem, ctx->stream>>>(tmA, tmB, kp);
   cudaEventRecord(ctx->ev_k1, ctx->stream);
   ctx->ev_valid = true;
   JP_CHECK_LAUNCH(ctx);
   return JP_OK;
+}
+
+template <int NC>
+static int launch_tc(jp_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcKernelParams& kp, size_t smem) {
+#ifdef JP_TC_PROFILING_MODES
+  static const int mode = getenv("JP_TC_DEBUG_MODE") ? atoi(getenv("JP_TC_DEBUG_MODE")) : 0;
+  if (mode == 1) return launch_tc_mode<NC, 1>(ctx, tmA, tmB, kp, smem);
+  if (mode == 2) return launch_tc_mode<NC, 2>(ctx, tmA, tmB, kp, smem);
+#endif
+  return launch_tc_mode<NC, 0>(ctx, tmA, tmB, kp, smem);
 }
 
 int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {

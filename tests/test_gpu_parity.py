@@ -460,7 +460,7 @@ def test_tc_sharded_equals_unsharded(jp, O, gpu_ctx):
         sh = JointPosterior(M, dd, grid, x, U, neg_min, path=jp.PATH_TC, node_range=(b, e))
         sh.evaluate()
         assert sh.path_used == jp.PATH_TC
-        assert np.max(np.abs(sh.logdens - ld[b:e])) < 1e-9     # same arithmetic per node up to chunking of the sums
+        assert np.max(np.abs(sh.logdens - ld[b:e])) < 2e-8     # same arithmetic per node up to the chunking of the FP32 partial sums
 
 
 def test_cfg3_full_size_tc(jp, O, gpu_ctx):
