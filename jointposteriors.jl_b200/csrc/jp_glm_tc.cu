@@ -77,6 +77,8 @@ struct TcPostState {
   int kp = 0;
   float* d_ds = nullptr;       // [M_pad][kp]  (d_hi | d_hi | d_lo | 0)
   double* d_quad = nullptr;    // [M]
+  double* d_part = nullptr;    // [part_chunks][M] per-chunk remainder sums
+  int part_chunks = 0;
   CUtensorMap tmB;
 };
 
@@ -366,6 +368,11 @@ __device__ __forceinline__ uint64_t f32x2_pack(uint32_t lo, uint32_t hi) {
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
   return r;
 }
+__device__ __forceinline__ uint64_t f32x2_bcast(float x) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
@@ -386,10 +393,12 @@ __device__ __forceinline__ uint64_t f32x2_mul(uint64_t a, uint64_t b) {
 // level parallelism and consecutive instructions reuse D (or D^2) in the same operand slot, which matters
 // because an FFMA2 with three distinct 64-bit register operands is register-file-bandwidth bound.
 template <int NC, int MODE>
-__device__ __forceinline__ void tc_accumulate16(const uint32_t (&v)[16], const uint64_t (&c2)[NC], uint64_t* acc2) {
+__device__ __forceinline__ void tc_accumulate16(const uint32_t (&v)[16], const float (&c)[NC], uint64_t* acc2) {
+  // coefficients stay scalar: ptxas folds the (c, c) pack into FFMA2's broadcast operand form (Rx.F32), which
+  // reads one register instead of a pair
   if (MODE == 1) {   // profiling aid: TMEM traffic without the series arithmetic (results are meaningless)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc2[j] = f32x2_fma(f32x2_pack(v[2 * j], v[2 * j + 1]), c2[0], acc2[j]);
+    for (int j = 0; j < 8; ++j) acc2[j] = f32x2_fma(f32x2_pack(v[2 * j], v[2 * j + 1]), f32x2_bcast(c[0]), acc2[j]);
     return;
   }
 #pragma unroll
@@ -397,7 +406,7 @@ __device__ __forceinline__ void tc_accumulate16(const uint32_t (&v)[16], const u
     const uint64_t D = f32x2_pack(v[2 * j], v[2 * j + 1]);
     uint64_t e[NC / 2];
 #pragma unroll
-    for (int m = 0; m < NC / 2; ++m) e[m] = f32x2_fma(c2[2 * m + 1], D, c2[2 * m]);
+    for (int m = 0; m < NC / 2; ++m) e[m] = f32x2_fma(f32x2_bcast(c[2 * m + 1]), D, f32x2_bcast(c[2 * m]));
     const uint64_t D2 = f32x2_mul(D, D);
     uint64_t t = e[NC / 2 - 1];
 #pragma unroll
@@ -477,7 +486,7 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0, bphase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int node_tile = item / P.chunks, chunk = item % P.chunks;
+        const int chunk = item / P.n_node_tiles, node_tile = item % P.n_node_tiles;
         const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
         mbar_wait_relaxed(bar_bempty, bphase ^ 1);
         mbar_expect_tx(bar_bfull, b_bytes);
@@ -503,7 +512,7 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0, buf = 0;
       uint32_t phase = 0, bphase = 0, tphase = 0;   // tphase: bit b = parity of accumulator buffer b
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int chunk = item % P.chunks;
+        const int chunk = item / P.n_node_tiles;
         const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
         mbar_wait_relaxed(bar_bfull, bphase);
         bphase ^= 1;
@@ -539,21 +548,21 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int buf = 0;
     uint32_t tphase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int node_tile = item / P.chunks, chunk = item % P.chunks;
+      const int chunk = item / P.n_node_tiles, node_tile = item % P.n_node_tiles;
       const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
       // Software pipeline over (tile, 16-column chunk): the tcgen05.ld of the next chunk -- across a tile
       // boundary too, the next accumulator buffer is normally complete long before -- and the coefficient
       // loads of the next tile are in flight while the current chunk is evaluated.
       uint32_t va[16], vb[16];
-      uint64_t c2[NC];
-      auto load_coef = [&](int t, uint64_t (&dst)[NC]) {
+      float c2[NC];
+      auto load_coef = [&](int t, float (&dst)[NC]) {
         // this thread's observation: row of the tile = TMEM lane
         const float2* cp = reinterpret_cast<const float2*>(P.coef + ((size_t)t * TC_OBS_TILE + q * 32 + lane) * TC_NCMAX);
 #pragma unroll
         for (int k = 0; k < NC / 2; ++k) {
           const float2 f = __ldg(cp + k);
-          dst[2 * k] = f32x2_pack(__float_as_uint(f.x), __float_as_uint(f.x));
-          dst[2 * k + 1] = f32x2_pack(__float_as_uint(f.y), __float_as_uint(f.y));
+          dst[2 * k] = f.x;
+          dst[2 * k + 1] = f.y;
         }
       };
       auto tile_addr = [&](int b) {
@@ -567,7 +576,7 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int t = t0; t < t1; ++t) {
         const bool more = t + 1 < t1;
         const int nbuf = (buf + 1) % TC_NBUF;
-        uint64_t cn[NC];
+        float cn[NC];
         if (more) load_coef(t + 1, cn);
         const uint32_t taddr = tile_addr(buf);
 #pragma unroll
@@ -721,7 +730,7 @@ void jp_tc_data_free(jp_data* data) {
 void jp_tc_post_free(jp_posterior* post) {
   TcPostState* s = static_cast<TcPostState*>(post->tc_state);
   if (!s) return;
-  jp_dfree(post->ctx, s->d_ds); jp_dfree(post->ctx, s->d_quad);
+  jp_dfree(post->ctx, s->d_ds); jp_dfree(post->ctx, s->d_quad); jp_dfree(post->ctx, s->d_part);
   delete s;
   post->tc_state = nullptr;
 }
@@ -864,10 +873,16 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   const size_t fixed = 1024 + b_bytes + 4 * TC_NODE_TILE * 8 + 256;
   kp.stages = (int)std::max<size_t>(2, std::min<size_t>(TC_MAX_STAGES, (200 * 1024 - fixed) / a_bytes));
   const size_t smem = fixed + (size_t)kp.stages * a_bytes;
-  int best_c = 1;
+  // Work items are (observation chunk, node tile) pairs in CHUNK-MAJOR order on the persistent grid: all CTAs sweep
+  // the same chunk of observation tiles at about the same time, so a chunk is read from HBM once and then served
+  // from the 126 MB L2 to every node tile.  A chunk is therefore sized to ~24 MB of operand rows; beyond that the
+  // chunk count is nudged until the last round of the static schedule is >= 97 % full.
+  const long long l2_tiles = std::max<long long>(8, (24ll << 20) / (long long)a_bytes);
+  const int c_min = (int)((kp.n_obs_tiles + l2_tiles - 1) / l2_tiles);
+  int best_c = c_min;
   double best_eff = 0;
-  const int max_c = std::max(1, std::min(JP_POST_PART_SPLITS, kp.n_obs_tiles / 8));
-  for (int c = 1; c <= max_c; ++c) {
+  for (int c = c_min; c <= c_min + 48; ++c) {
+    if (c > c_min && kp.n_obs_tiles / c < 8) break;
     long long items = (long long)kp.n_node_tiles * c;
     long long rounds = (items + ctx->sm_count - 1) / ctx->sm_count;
     double eff = (double)items / (double)(rounds * ctx->sm_count);
@@ -877,9 +892,16 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   kp.chunks = best_c;
   kp.tiles_per_chunk = (kp.n_obs_tiles + kp.chunks - 1) / kp.chunks;
   kp.chunks = (kp.n_obs_tiles + kp.tiles_per_chunk - 1) / kp.tiles_per_chunk;   // no empty chunk
+  if (kp.chunks > ps->part_chunks) {
+    jp_dfree(ctx, ps->d_part);
+    ps->d_part = nullptr;
+    ps->part_chunks = 0;
+    JP_CUDA(jp_dmalloc(ctx, &ps->d_part, (size_t)kp.chunks * post->M * 8));
+    ps->part_chunks = kp.chunks;
+  }
   kp.M = post->M;
   kp.coef = ds->d_coef;
-  kp.part = post->d_part;
+  kp.part = ps->d_part;
   int stc;
   if (NC == 4) stc = launch_tc<4>(ctx, ds->tmA, ps->tmB, kp, smem);
   else if (NC == 6) stc = launch_tc<6>(ctx, ds->tmA, ps->tmB, kp, smem);
@@ -887,7 +909,7 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   else if (NC == 10) stc = launch_tc<10>(ctx, ds->tmA, ps->tmB, kp, smem);
   else stc = launch_tc<12>(ctx, ds->tmA, ps->tmB, kp, smem);
   JP_TRY(stc);
-  tc_finish_kernel<<<(unsigned)((post->M + 255) / 256), 256, 0, st>>>(post->M, post->m0, kp.chunks, post->d_part, ps->d_quad,
+  tc_finish_kernel<<<(unsigned)((post->M + 255) / 256), 256, 0, st>>>(post->M, post->m0, kp.chunks, ps->d_part, ps->d_quad,
                                                                        post->grid->d_hzz, args->neg_min, post->d_logdens,
                                                                        post->d_a);
   JP_CHECK_LAUNCH(ctx);
