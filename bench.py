@@ -171,7 +171,7 @@ def run_reference(args):
                config=dict(workload=wl["desc"], sample=sample),
                cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind="port", sample=sample),
                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(out), flush=True)
+    _emit(out)
 
 
 # ----------------------------------------------------------------------------------------- product arm
@@ -400,10 +400,21 @@ def run_product(args):
                    roofline=roof)
         if cpu:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out), flush=True)
+        _emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _emit(obj):
+    """Print the ONE JSON line on the real stdout (fd saved before libraries could write to it)."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+# NCCL / CUDA libraries print banners ("NCCL version ...") on fd 1: keep stdout clean for the JSON line by
+# pointing fd 1 at stderr for the whole run and writing the result to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():

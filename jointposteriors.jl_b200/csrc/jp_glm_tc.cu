@@ -178,19 +178,19 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // X' = [x_hi | x_lo | x_hi | 0]: depends on the data only, built once per jp_data
 __global__ void tc_split_x_kernel(int d, int ncols, int kp, long long N, long long N_pad, const double* __restrict__ obs,
                                   float* __restrict__ xs) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N_pad) return;
-  float* o = xs + (size_t)i * kp;
-  for (int k = 0; k < kp; ++k) o[k] = 0.f;
-  if (i >= N) return;
-  const double* r = obs + (size_t)i * ncols;
-  for (int k = 0; k < d; ++k) {
+  // one thread per operand element: coalesced stores of the [N_pad][kp] operand, the record reads hit L1/L2
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N_pad * kp) return;
+  const long long i = e / kp;
+  const int c = (int)(e - i * kp);
+  float v = 0.f;
+  if (i < N && c < 3 * d) {
+    const int part = c / d, k = c - part * d;
     float hi, lo;
-    tf32_split(r[k], hi, lo);
-    o[k] = hi;
-    o[d + k] = lo;
-    o[2 * d + k] = hi;
+    tf32_split(obs[(size_t)i * ncols + k], hi, lo);
+    v = (part == 1) ? lo : hi;
   }
+  xs[e] = v;
 }
 
 // Per observation: eta_hat, Taylor coefficients c_3 .. c_14 of the link remainder, t = |U' x| (so that
@@ -249,14 +249,26 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
     sr *= tr * tr;                                     // majorant of |R_i| at |z| = z_ref
     b_r += sr;
     b_r2 += sr * sr;
+    // tail <= |c_{K+1}| t^{K+1} + |c_{K+2}| t^{K+2} G(t): G = 1 / (1 - t / rho) majorises the remaining terms of the
+    // logistic series (radius of convergence rho >= pi), e^t those of the Poisson series; powers by recurrence
+    double gr, gm;
+    if (family == JP_FAM_LOGISTIC) {
+      gr = tr < rho ? 1.0 / (1.0 - tr / rho) : 1e300;
+      gm = tm < rho ? 1.0 / (1.0 - tm / rho) : 1e300;
+    } else {
+      gr = exp(tr);
+      gm = exp(tm);
+    }
+    double pr = tr * tr, pm = tm * tm;      // t^2
+    pr *= pr * pr * tr;                     // t^7
+    pm *= pm * pm * tm;
 #pragma unroll
     for (int j = 0; j < TC_NORD; ++j) {
-      const int K = 2 * j + 6;                          // last order kept (NC = K - 2 coefficients)
-      // tail <= |c_{K+1}| t^{K+1} + |c_{K+2}| t^{K+2} / (1 - t / rho)   (geometric majorant of the remaining terms)
-      double gr = tr < rho ? 1.0 / (1.0 - tr / rho) : 1e300, gm = tm < rho ? 1.0 / (1.0 - tm / rho) : 1e300;
-      if (family != JP_FAM_LOGISTIC) { gr = exp(tr); gm = exp(tm); }
-      b_ref[j] += fabs(c[K + 1]) * pow(tr, K + 1) + fabs(c[K + 2]) * pow(tr, K + 2) * gr;
-      b_max[j] += fabs(c[K + 1]) * pow(tm, K + 1) + fabs(c[K + 2]) * pow(tm, K + 2) * gm;
+      const int K = 2 * j + 6;              // last order kept (NC = K - 2 coefficients); pr = tr^{K+1}
+      b_ref[j] += fabs(c[K + 1]) * pr + fabs(c[K + 2]) * pr * tr * gr;
+      b_max[j] += fabs(c[K + 1]) * pm + fabs(c[K + 2]) * pm * tm * gm;
+      pr *= tr * tr;
+      pm *= tm * tm;
     }
   }
   double* ob = bounds + (size_t)blockIdx.x * TC_NBOUND;
@@ -751,7 +763,7 @@ static int ensure_data_state(jp_ctx* ctx, jp_data* data, int d) {
   JP_CUDA(jp_dmalloc(ctx, &s->d_sums, (size_t)(nE + 1) * 8));
   JP_CUDA(jp_dmalloc(ctx, &s->d_work, (size_t)s->glm_blocks * (nE + 1) * 8));
   JP_CUDA(jp_dmalloc(ctx, &s->d_bounds, (size_t)TC_PREP_BLOCKS * TC_NBOUND * 8));
-  tc_split_x_kernel<<<(unsigned)((s->N_pad + 255) / 256), 256, 0, ctx->stream>>>(d, data->ncols, s->kp, s->N, s->N_pad,
+  tc_split_x_kernel<<<(unsigned)((s->N_pad * s->kp + 255) / 256), 256, 0, ctx->stream>>>(d, data->ncols, s->kp, s->N, s->N_pad,
                                                                                   data->d_obs, s->d_xs);
   JP_CHECK_LAUNCH(ctx);
   JP_TRY(make_tensor_map(&s->tmA, s->d_xs, s->N_pad, s->kp, TC_OBS_TILE));

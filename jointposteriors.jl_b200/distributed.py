@@ -58,12 +58,9 @@ def combine_knots(gathered, vmin, vmax):
     cumulative weight S = sum of all weights <= x; right knot = first element of the next tie group
     (lowest global index among the smallest values > x) with cumulative weight S + its weight."""
     import torch
-    S = gathered[..., 0]
-    tot = torch.zeros_like(S[0])
-    for r in range(S.shape[0]):          # rank order -> identical on every rank
-        tot = tot + S[r]
-    pred = gathered[..., 1].max(dim=0).values
-    succ = gathered[..., 2].min(dim=0).values
+    tot = gathered[..., 0].sum(dim=0)    # fixed reduction order over the rank axis -> identical on every rank
+    pred = gathered[..., 1].amax(dim=0)
+    succ = gathered[..., 2].amin(dim=0)
     is_min = gathered[..., 2] == succ[None]
     idx = torch.where(is_min, gathered[..., 3], torch.full_like(gathered[..., 3], float("inf")))
     owner = idx.argmin(dim=0, keepdim=True)
@@ -121,16 +118,11 @@ class CudaLocal:
 
 def fit_sharded(local, group=None, gather=None):
     """Normalise a node-sharded fit: two tiny all_gathers (max, then sum).  `gather(t, group)` defaults to
-    torch.distributed all_gather; tests emulating several ranks on one GPU inject their own."""
+    torch.distributed all_gather; tests emulating several ranks on one GPU inject their own.  Reductions over
+    the gathered rank axis have a fixed order, so every rank derives bit-identical scalars."""
     gather = gather or _all_gather
-    lmax = local.fit_local_max()
-    gmax = gather(lmax, group).max(dim=0).values.contiguous()
-    lsum = local.fit_local_sum(gmax)
-    sums = gather(lsum, group)
-    gsum = sums[0].clone()
-    for r in range(1, sums.shape[0]):
-        gsum = gsum + sums[r]
-    gsum = gsum.contiguous()
+    gmax = gather(local.fit_local_max(), group).amax(dim=0)
+    gsum = gather(local.fit_local_sum(gmax), group).sum(dim=0)
     local.fit_normalise(gsum)
     return gmax, gsum
 
@@ -140,20 +132,14 @@ def marginals_sharded(local, coords, group=None, gather=None):
     posterior: two all_gathers per batch, no global sort."""
     import torch
     gather = gather or _all_gather
-    mom = local.moments(coords)                       # [K, 4] = (sum w v, sum w v^2, min, max)
-    g = gather(mom, group)                            # [world, K, 4]
-    s1 = g[0, :, 0].clone()
-    s2 = g[0, :, 1].clone()
-    for r in range(1, g.shape[0]):
-        s1 = s1 + g[r, :, 0]
-        s2 = s2 + g[r, :, 1]
-    vmin = g[:, :, 2].min(dim=0).values
-    vmax = g[:, :, 3].max(dim=0).values
-    minmax = torch.stack([vmin, vmax], dim=1).contiguous()
-    cand = local.knots(coords, minmax)                # [K, 98, 6]
-    gathered = gather(cand, group)                    # [world, K, 98, 6]
+    g = gather(local.moments(coords), group)          # [world, K, 4] = (sum w v, sum w v^2, min, max)
+    s = g[:, :, :2].sum(dim=0)
+    vmin = g[:, :, 2].amin(dim=0)
+    vmax = g[:, :, 3].amax(dim=0)
+    minmax = torch.stack([vmin, vmax], dim=1)
+    gathered = gather(local.knots(coords, minmax), group)   # [world, K, 98, 6]
     wn = combine_knots(gathered, vmin, vmax)
     vn = knot_values(gathered, vmin, vmax)
-    mu = s1
-    sigma = torch.sqrt(s2 - s1 * s1)
+    mu = s[:, 0]
+    sigma = torch.sqrt(s[:, 1] - mu * mu)
     return mu, sigma, vn, wn
