@@ -338,6 +338,13 @@ def run_product(args):
                                 note="the kernel's true limiter: %d FP32 FMA-pipe instructions per pair (Horner of the link "
                                      "remainder series) against 148 SMs x 128 lanes x SM clock" % (nc + 2))
     roof["kernel"] = "jp_glm_tc_kernel" if path_used == _lib.PATH_TC else "jp_fit_nodes_kernel"
+    try:   # DRAM traffic of the same kernel on the same workload from the committed ncu capture (per launch)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("%s:%s" % (args.workload, roof["kernel"]))
+        if tr and world == 1:
+            roof["traffic"] = tr["dram_bytes"]
+            roof["traffic_source"] = tr["source"]
+    except (OSError, ValueError):
+        pass
     roof["kernel_ms"] = kms
     roof["kernel_share_of_step"] = kms / ms_per_step
     roof["kernel_pairs_per_s"] = local_pairs / (kms * 1e-3)

@@ -216,6 +216,11 @@ int jp_marginal_values(jp_posterior* post, int K, const double* h_values /* K x 
 int jp_marginal_sorted(jp_posterior* post, int k, double* h_sorted_values, double* h_sorted_weights,
                        double* h_cum_weights);
 
+/* The 100-knot Grid of the first K marginals of the last jp_marginal_* call recomputed from the explicit stable
+ * sort + cumulative sum, exactly as the reference does it (src/interp.jl:21-31,448-457).  The default path above
+ * gets the same knots from one binning pass without sorting; this entry point exists to cross-check it. */
+int jp_marginal_knots_from_sort(jp_posterior* post, int K, double* h_value_nodes, double* h_weight_nodes);
+
 /* multi-GPU marginal in phases (sort-free splitter histogram):
  *   jp_marginal_local_moments: d_out[k*4 + {0,1,2,3}] = (sum w v, sum w v^2, min v, max v) on the shard
  *   jp_marginal_local_knots:   given the GLOBAL (min, max) per marginal in d_minmax[k*2 + {0,1}], for each

@@ -52,7 +52,7 @@ SYMBOLS = [
     "jp_fit", "jp_fit_local", "jp_fit_local_sum", "jp_fit_normalise",
     "jp_get_theta", "jp_get_logdens", "jp_get_density", "jp_dev_theta", "jp_dev_density", "jp_fit_path_used",
     "jp_fit_diagnostics",
-    "jp_marginal_coords", "jp_marginal_values", "jp_marginal_sorted",
+    "jp_marginal_coords", "jp_marginal_values", "jp_marginal_sorted", "jp_marginal_knots_from_sort",
     "jp_marginal_local_moments", "jp_marginal_local_knots",
     "jp_quantile", "jp_cdf",
 ]

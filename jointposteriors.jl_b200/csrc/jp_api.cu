@@ -230,7 +230,7 @@ int jp_posterior_free(jp_posterior* p) {
   jp_ctx* c = p->ctx;   // stream-ordered frees: work already queued on the ctx stream still sees the buffers
   jp_dfree(c, p->d_theta); jp_dfree(c, p->d_a); jp_dfree(c, p->d_logdens); jp_dfree(c, p->d_density); jp_dfree(c, p->d_part);
   jp_dfree(c, p->d_stats); jp_dfree(c, p->d_mu); jp_dfree(c, p->d_U); jp_dfree(c, p->d_tcode); jp_tc_post_free(p);
-  jp_dfree(c, p->d_vals); jp_dfree(c, (void*)p->d_vptr); jp_dfree(c, p->d_perm_a); jp_dfree(c, p->d_perm_b); jp_dfree(c, p->d_hist);
+  jp_dfree(c, p->d_vals); jp_dfree(c, p->d_bins); jp_dfree(c, (void*)p->d_vptr); jp_dfree(c, p->d_perm_a); jp_dfree(c, p->d_perm_b); jp_dfree(c, p->d_hist);
   jp_dfree(c, p->d_sv); jp_dfree(c, p->d_sw); jp_dfree(c, p->d_cw); jp_dfree(c, p->d_mout);
   delete p;
   return JP_OK;

@@ -120,18 +120,23 @@ struct jp_posterior {
   double* d_mu = nullptr;        // d
   double* d_U = nullptr;         // d x p column-major
   int* d_tcode = nullptr;        // d
-  // stage-5 work buffers (allocated on first use, sized for K_cap marginals)
-  int K_cap = 0;
-  int K_last = 0;
+  // stage-5 work buffers (allocated on first use)
+  int K_cap = 0;                 // capacity of the default (sort-free) path: d_vptr, d_bins, d_mout
+  int K_cap_vals = 0;            // capacity of d_vals
+  int K_cap_sort = 0;            // capacity of the explicit sort: d_perm_*, d_hist, d_sv, d_sw, d_cw
+  int K_last = 0;                // marginals of the last call
+  bool sorted_valid = false;     // d_sv / d_sw / d_cw hold the sort of the last call's marginals
+  int bins_blocks = 0;
   double* d_vals = nullptr;      // uploaded values K x M (host closures)
   const double** d_vptr = nullptr;  // K device pointers to the value columns
+  double* d_bins = nullptr;      // [K][bins_blocks][99][5] per-block bins of the sort-free path
   uint32_t* d_perm_a = nullptr;  // K x M
   uint32_t* d_perm_b = nullptr;  // K x M
   uint32_t* d_hist = nullptr;    // radix histograms
   double* d_sv = nullptr;        // sorted values K x M
   double* d_sw = nullptr;        // sorted weights K x M
   double* d_cw = nullptr;        // cumulative weights K x M
-  double* d_mout = nullptr;      // K x (2 + 200) results
+  double* d_mout = nullptr;      // K x (2 + 200 + 2) results
 };
 #define JP_POST_PART_SPLITS 32   // d_part holds [splits <= 32][M] observation partial sums + [M] (lj + prior)
 

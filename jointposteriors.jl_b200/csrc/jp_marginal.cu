@@ -169,66 +169,199 @@ jp_knots_kernel(const double* __restrict__ sv, const double* __restrict__ cw, lo
   o[2 + JP_GRID_KNOTS + i] = wn;
 }
 
-// ---- sort-free splitter pass: block (knot i-1, marginal k) scans the shard once
-__global__ void __launch_bounds__(256)
-jp_local_knots_kernel(const double* const* __restrict__ vptr, const double* __restrict__ w, long long M,
-                      long long m0, const double* __restrict__ minmax, double* __restrict__ out) {
-  __shared__ double sm[33];
-  __shared__ unsigned long long s_idx;
-  const int k = blockIdx.y, i = blockIdx.x + 1;
+// ---- sort-free path: one pass over the values bins them between the 100 knots
+//
+// itp[x_i] of the reference (interp.jl:28-31,453-455) only needs, per interior knot x_i,
+//     S_i    = sum of the weights of all values <= x_i                (cumulative weight of the LAST element <= x_i)
+//     pred_i = largest value <= x_i, succ_i = smallest value > x_i
+//     the lowest-index element attaining succ_i and its weight        (first member of the next tie group)
+// so the sort + scan is replaced by binning: value v falls in bin b(v) = #{i in 1..98 : x_i < v} (0..98), a bin keeps
+// (sum w, max v, min v with its lowest node index and weight), and knot i reads bins < i and >= i.  Everything is
+// summed in a fixed order (lane order inside a warp step, warp order, block order), hence bitwise reproducible.
+#define JP_NBINS (JP_GRID_KNOTS - 1)     // 99
+#define JP_BIN_THREADS 256
+#define JP_BIN_WARPS (JP_BIN_THREADS / 32)
+#define JP_BIN_STRIDE 5                  // per bin: W, max, min, index of min (as double), weight at min
+
+__global__ void __launch_bounds__(JP_BIN_THREADS)
+jp_bins_kernel(const double* const* __restrict__ vptr, const double* __restrict__ w, long long M, long long m0,
+               const double* __restrict__ minmax, int minmax_stride, int minmax_off,
+               double* __restrict__ out /* [K][gridDim.x][JP_NBINS][JP_BIN_STRIDE] */) {
+  __shared__ double s_x[JP_GRID_KNOTS];
+  __shared__ double s_bin[JP_BIN_WARPS][JP_NBINS][JP_BIN_STRIDE];
+  const int k = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double* v = vptr[k];
-  const double x = jp_knot_value(minmax[2 * k], minmax[2 * k + 1], i);
-  long long chunk = (M + 255) / 256;
-  long long b = threadIdx.x * chunk, e = min(M, b + chunk);
-  double S = 0, pred = -INFINITY, succ = INFINITY;
-  for (long long j = b; j < e; ++j) {
-    double vj = v[j];
-    if (vj <= x) {
-      S += w[j];
-      pred = fmax(pred, vj);
-    } else {
-      succ = fmin(succ, vj);
+  const double vmin = minmax[(size_t)k * minmax_stride + minmax_off], vmax = minmax[(size_t)k * minmax_stride + minmax_off + 1];
+  for (int i = threadIdx.x; i < JP_GRID_KNOTS; i += JP_BIN_THREADS) s_x[i] = jp_knot_value(vmin, vmax, i);
+  for (int i = threadIdx.x; i < JP_BIN_WARPS * JP_NBINS; i += JP_BIN_THREADS) {
+    double* bn = &s_bin[0][0][0] + (size_t)i * JP_BIN_STRIDE;
+    bn[0] = 0.0; bn[1] = -INFINITY; bn[2] = INFINITY; bn[3] = INFINITY; bn[4] = 0.0;
+  }
+  __syncthreads();
+  // contiguous slice per block, contiguous sub-slice per warp: node indices increase along the visiting order
+  const long long per_block = (M + gridDim.x - 1) / gridDim.x;
+  const long long b0 = (long long)blockIdx.x * per_block, b1 = min(M, b0 + per_block);
+  const long long per_warp = ((per_block + JP_BIN_WARPS - 1) / JP_BIN_WARPS + 31) / 32 * 32;
+  const long long w0 = b0 + (long long)warp * per_warp, w1 = min(b1, w0 + per_warp);
+  const double scale = (vmax > vmin) ? (double)(JP_GRID_KNOTS - 1) / (vmax - vmin) : 0.0;
+  for (long long base = w0; base < w1; base += 32) {
+    const long long j = base + lane;
+    const bool live = j < w1;
+    double vj = live ? v[j] : 0.0, wj = live ? w[j] : 0.0;
+    int bin = -1;
+    if (live) {
+      int g = (int)floor((vj - vmin) * scale);          // guess, then make exact against the knot table
+      g = max(0, min(JP_NBINS - 1, g));
+      while (g < JP_NBINS - 1 && s_x[g + 1] < vj) ++g;  // b(v) = #{i >= 1 : x_i < v}
+      while (g > 0 && !(s_x[g] < vj)) --g;
+      bin = g;
+    }
+    // the lowest lane of every group of equal bins folds its group in lane order
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    const bool leader = live && (peers & ((1u << lane) - 1)) == 0;
+    double sW = 0.0, mx = -INFINITY, mn = INFINITY, mi = INFINITY, mw = 0.0;
+    for (int s2 = 0; s2 < 32; ++s2) {
+      const int bs = __shfl_sync(0xffffffffu, bin, s2);
+      const double vs = __shfl_sync(0xffffffffu, vj, s2), ws = __shfl_sync(0xffffffffu, wj, s2);
+      if (leader && bs == bin) {
+        sW += ws;
+        mx = fmax(mx, vs);
+        if (vs < mn) { mn = vs; mi = (double)(m0 + base + s2); mw = ws; }
+      }
+    }
+    if (leader) {
+      double* bn = s_bin[warp][bin];
+      bn[0] += sW;
+      bn[1] = fmax(bn[1], mx);
+      if (mn < bn[2]) { bn[2] = mn; bn[3] = mi; bn[4] = mw; }   // equal minima: the earlier (lower index) entry stays
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  double* o = out + ((size_t)k * gridDim.x + blockIdx.x) * JP_NBINS * JP_BIN_STRIDE;
+  for (int bq = threadIdx.x; bq < JP_NBINS; bq += JP_BIN_THREADS) {
+    double W = 0.0, mx = -INFINITY, mn = INFINITY, mi = INFINITY, mw = 0.0;
+    for (int ww = 0; ww < JP_BIN_WARPS; ++ww) {
+      const double* bn = s_bin[ww][bq];
+      W += bn[0];
+      mx = fmax(mx, bn[1]);
+      if (bn[2] < mn) { mn = bn[2]; mi = bn[3]; mw = bn[4]; }
+    }
+    double* ob = o + (size_t)bq * JP_BIN_STRIDE;
+    ob[0] = W; ob[1] = mx; ob[2] = mn; ob[3] = mi; ob[4] = mw;
+  }
+}
+
+// one block per marginal: blocks -> bins -> knots.  FINAL: the 100-knot Grid + (mu, sigma) into mout;
+// otherwise the per-knot candidates (S, pred, succ, index, weight, x) for the cross-rank combine.
+template <bool FINAL>
+__global__ void __launch_bounds__(128)
+jp_bins_combine_kernel(const double* __restrict__ bins, int nblocks, const double* __restrict__ minmax, int minmax_stride,
+                       int minmax_off, const double* __restrict__ mom, int mom_stride, double* __restrict__ out) {
+  __shared__ double sb[JP_NBINS][JP_BIN_STRIDE];
+  __shared__ double sS[JP_GRID_KNOTS], sP[JP_GRID_KNOTS], sSucc[JP_GRID_KNOTS][3];
+  const int k = blockIdx.x, t = threadIdx.x;
+  const double vmin = minmax[(size_t)k * minmax_stride + minmax_off], vmax = minmax[(size_t)k * minmax_stride + minmax_off + 1];
+  if (t < JP_NBINS) {
+    double W = 0.0, mx = -INFINITY, mn = INFINITY, mi = INFINITY, mw = 0.0;
+    for (int b = 0; b < nblocks; ++b) {     // block order = ascending node index
+      const double* bn = bins + (((size_t)k * nblocks + b) * JP_NBINS + t) * JP_BIN_STRIDE;
+      W += bn[0];
+      mx = fmax(mx, bn[1]);
+      if (bn[2] < mn) { mn = bn[2]; mi = bn[3]; mw = bn[4]; }
+    }
+    sb[t][0] = W; sb[t][1] = mx; sb[t][2] = mn; sb[t][3] = mi; sb[t][4] = mw;
+  }
+  __syncthreads();
+  if (t == 0) {   // 99 bins: sequential prefix (mass, predecessor) and suffix (successor)
+    double S = 0.0, pr = -INFINITY;
+    for (int i = 1; i <= JP_NBINS - 1; ++i) {        // knot i reads bins 0 .. i-1
+      S += sb[i - 1][0];
+      pr = fmax(pr, sb[i - 1][1]);
+      sS[i] = S;
+      sP[i] = pr;
+    }
+    double mn = INFINITY, mi = INFINITY, mw = 0.0;
+    for (int i = JP_NBINS - 1; i >= 1; --i) {        // knot i reads bins i .. 98; ties keep the lower bin's entry
+      if (sb[i][2] <= mn && sb[i][2] < INFINITY) { mn = sb[i][2]; mi = sb[i][3]; mw = sb[i][4]; }
+      sSucc[i][0] = mn; sSucc[i][1] = mi; sSucc[i][2] = mw;
     }
   }
-  S = jp_block_sum(S, sm);
-  pred = jp_block_max(pred, sm);
-  succ = jp_block_min(succ, sm);
-  // lowest global index attaining succ
-  if (threadIdx.x == 0) s_idx = ~0ull;
   __syncthreads();
-  unsigned long long best = ~0ull;
-  if (succ < INFINITY)
-    for (long long j = b; j < e; ++j)
-      if (v[j] == succ) { best = (unsigned long long)(m0 + j); break; }
-  if (best != ~0ull) atomicMin(&s_idx, best);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double* o = out + ((size_t)k * (JP_GRID_KNOTS - 2) + (i - 1)) * 6;
-    o[0] = S; o[1] = pred; o[2] = succ;
-    o[3] = (s_idx == ~0ull) ? INFINITY : (double)s_idx;
-    o[4] = (s_idx == ~0ull) ? 0.0 : w[(long long)s_idx - m0];
-    o[5] = x;
+  if (FINAL) {
+    double* o = out + (size_t)k * JP_MOUT_STRIDE;
+    if (t == 0) {
+      double s1 = mom[(size_t)k * mom_stride + 0], s2 = mom[(size_t)k * mom_stride + 1];
+      o[0] = s1;
+      o[1] = sqrt(s2 - s1 * s1);      // no clamp: a negative argument gives NaN, as in the reference
+      o[2 + 2 * JP_GRID_KNOTS] = vmin;
+      o[3 + 2 * JP_GRID_KNOTS] = vmax;
+    }
+    if (t < JP_GRID_KNOTS) {
+      const double x = jp_knot_value(vmin, vmax, t);
+      o[2 + t] = x;
+      double wn;
+      if (t == 0) wn = 0.0;                              // interp.jl:451
+      else if (t == JP_GRID_KNOTS - 1) wn = 1.0;         // interp.jl:452
+      else {
+        const double k0 = sP[t], k1 = sSucc[t][0], c0 = sS[t], c1 = sS[t] + sSucc[t][2];
+        const double fx = (x - k0) / (k1 - k0);
+        wn = c0 * (1.0 - fx) + c1 * fx;
+      }
+      o[2 + JP_GRID_KNOTS + t] = wn;
+    }
+  } else if (t >= 1 && t <= JP_GRID_KNOTS - 2) {
+    double* o = out + ((size_t)k * (JP_GRID_KNOTS - 2) + (t - 1)) * 6;
+    o[0] = sS[t]; o[1] = sP[t]; o[2] = sSucc[t][0]; o[3] = sSucc[t][1]; o[4] = sSucc[t][2];
+    o[5] = jp_knot_value(vmin, vmax, t);
   }
 }
 
 // ------------------------------------------------------------------------------------ host side
+static int bins_blocks_for(long long M) { return (int)std::max(1LL, std::min(64LL, (M + 4095) / 4096)); }
+
+// light buffers of the default (sort-free) path
 static int ensure_marginal_buffers(jp_posterior* post, int K) {
   if (K <= post->K_cap) return JP_OK;
-  jp_dfree(post->ctx, post->d_vals); jp_dfree(post->ctx, (void*)post->d_vptr); jp_dfree(post->ctx, post->d_perm_a); jp_dfree(post->ctx, post->d_perm_b);
-  jp_dfree(post->ctx, post->d_hist); jp_dfree(post->ctx, post->d_sv); jp_dfree(post->ctx, post->d_sw); jp_dfree(post->ctx, post->d_cw); jp_dfree(post->ctx, post->d_mout);
+  jp_ctx* c = post->ctx;
+  jp_dfree(c, (void*)post->d_vptr); jp_dfree(c, post->d_bins); jp_dfree(c, post->d_mout);
+  post->d_vptr = nullptr; post->d_bins = nullptr; post->d_mout = nullptr;
   post->K_cap = 0;
+  post->bins_blocks = bins_blocks_for(post->M);
+  JP_CUDA(jp_dmalloc(c, (void**)&post->d_vptr, (size_t)K * sizeof(double*)));
+  JP_CUDA(jp_dmalloc(c, &post->d_bins, (size_t)K * post->bins_blocks * JP_NBINS * JP_BIN_STRIDE * 8));
+  JP_CUDA(jp_dmalloc(c, &post->d_mout, (size_t)K * JP_MOUT_STRIDE * 8));
+  post->K_cap = K;
+  return JP_OK;
+}
+// uploaded value columns of host closures
+static int ensure_value_buffer(jp_posterior* post, int K) {
+  if (K <= post->K_cap_vals) return JP_OK;
+  jp_dfree(post->ctx, post->d_vals);
+  post->d_vals = nullptr;
+  post->K_cap_vals = 0;
+  JP_CUDA(jp_dmalloc(post->ctx, &post->d_vals, (size_t)K * post->M * 8));
+  post->K_cap_vals = K;
+  return JP_OK;
+}
+// buffers of the explicit sort (jp_marginal_sorted: the `wv` field of the reference's marginal struct)
+static int ensure_sort_buffers(jp_posterior* post, int K) {
+  if (K <= post->K_cap_sort) return JP_OK;
+  jp_ctx* c = post->ctx;
+  jp_dfree(c, post->d_perm_a); jp_dfree(c, post->d_perm_b); jp_dfree(c, post->d_hist);
+  jp_dfree(c, post->d_sv); jp_dfree(c, post->d_sw); jp_dfree(c, post->d_cw);
+  post->d_perm_a = post->d_perm_b = post->d_hist = nullptr;
+  post->d_sv = post->d_sw = post->d_cw = nullptr;
+  post->K_cap_sort = 0;
   size_t KM = (size_t)K * post->M;
   int nb = jp_sort_blocks(post->M);
-  JP_CUDA(jp_dmalloc(post->ctx, &post->d_vals, KM * 8));
-  JP_CUDA(jp_dmalloc(post->ctx, (void**)&post->d_vptr, (size_t)K * sizeof(double*)));
-  JP_CUDA(jp_dmalloc(post->ctx, &post->d_perm_a, KM * 4));
-  JP_CUDA(jp_dmalloc(post->ctx, &post->d_perm_b, KM * 4));
-  JP_CUDA(jp_dmalloc(post->ctx, &post->d_hist, (size_t)K * JP_SORT_BINS * nb * 4));
-  JP_CUDA(jp_dmalloc(post->ctx, &post->d_sv, KM * 8));
-  JP_CUDA(jp_dmalloc(post->ctx, &post->d_sw, KM * 8));
-  JP_CUDA(jp_dmalloc(post->ctx, &post->d_cw, KM * 8));
-  JP_CUDA(jp_dmalloc(post->ctx, &post->d_mout, (size_t)K * JP_MOUT_STRIDE * 8));
-  post->K_cap = K;
+  JP_CUDA(jp_dmalloc(c, &post->d_perm_a, KM * 4));
+  JP_CUDA(jp_dmalloc(c, &post->d_perm_b, KM * 4));
+  JP_CUDA(jp_dmalloc(c, &post->d_hist, (size_t)K * JP_SORT_BINS * nb * 4));
+  JP_CUDA(jp_dmalloc(c, &post->d_sv, KM * 8));
+  JP_CUDA(jp_dmalloc(c, &post->d_sw, KM * 8));
+  JP_CUDA(jp_dmalloc(c, &post->d_cw, KM * 8));
+  post->K_cap_sort = K;
   return JP_OK;
 }
 
@@ -248,30 +381,26 @@ static int set_value_pointers(jp_posterior* post, int K, const int* h_coords, co
     }
   }
   JP_CUDA(cudaMemcpyAsync((void*)post->d_vptr, hp, (size_t)K * sizeof(double*), cudaMemcpyHostToDevice, ctx->stream));
+  post->sorted_valid = false;
+  post->K_last = 0;
   return JP_OK;
 }
 
+// default path: moments -> bins -> knots, three launches for any K
 static int run_marginals(jp_posterior* post, int K, double* h_mu, double* h_sigma, double* h_vn, double* h_wn) {
   jp_ctx* ctx = post->ctx;
   const long long M = post->M;
   JP_REQUIRE(M >= 2, "marginal: need at least 2 nodes");
   JP_REQUIRE((size_t)K * JP_MOUT_STRIDE <= JP_PINNED_DOUBLES, "marginal: K=%d too large for one call", K);
+  JP_REQUIRE((size_t)K * 4 <= JP_SCRATCH_DOUBLES, "marginal: K=%d too large for one call", K);
   cudaStream_t st = ctx->stream;
-  double* d_mom = ctx->d_scratch;   // K x 4
+  double* d_mom = ctx->d_scratch;   // K x 4: sum w v, sum w v^2, min, max
   jp_moments_kernel<<<K, 1024, 0, st>>>(post->d_vptr, post->d_density, M, d_mom, 4);
   JP_CHECK_LAUNCH(ctx);
-  dim3 gi((unsigned)((M + 255) / 256), K);
-  jp_iota_kernel<<<gi, 256, 0, st>>>(post->d_perm_a, M, M);
+  dim3 gb(post->bins_blocks, K);
+  jp_bins_kernel<<<gb, JP_BIN_THREADS, 0, st>>>(post->d_vptr, post->d_density, M, post->m0, d_mom, 4, 2, post->d_bins);
   JP_CHECK_LAUNCH(ctx);
-  uint32_t *pin = post->d_perm_a, *pout = post->d_perm_b;
-  for (int b = 0; b < 8; ++b) {
-    ValueDigit f{post->d_vptr, 8 * b};
-    JP_TRY(jp_radix_pass(ctx, f, pin, pout, M, M, post->d_hist, K));
-    std::swap(pin, pout);
-  }
-  jp_gather_scan_kernel<<<K, 1024, 0, st>>>(post->d_vptr, post->d_density, pin, M, post->d_sv, post->d_sw, post->d_cw);
-  JP_CHECK_LAUNCH(ctx);
-  jp_knots_kernel<<<K, 128, 0, st>>>(post->d_sv, post->d_cw, M, d_mom, 4, post->d_mout);
+  jp_bins_combine_kernel<true><<<K, 128, 0, st>>>(post->d_bins, post->bins_blocks, d_mom, 4, 2, d_mom, 4, post->d_mout);
   JP_CHECK_LAUNCH(ctx);
   JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, post->d_mout, (size_t)K * JP_MOUT_STRIDE * 8, cudaMemcpyDeviceToHost, st));
   JP_CUDA(cudaStreamSynchronize(st));
@@ -283,6 +412,29 @@ static int run_marginals(jp_posterior* post, int K, double* h_mu, double* h_sigm
     if (h_wn) std::copy(o + 2 + JP_GRID_KNOTS, o + 2 + 2 * JP_GRID_KNOTS, h_wn + (size_t)k * JP_GRID_KNOTS);
   }
   post->K_last = K;
+  return JP_OK;
+}
+
+// explicit stable sort + cumulative weights of the K_last marginals of the last call (simultaneous_sort! +
+// cumsum, reference src/interp.jl:21-31); the knots computed from it (jp_knots_kernel) cross-check the bins
+static int run_sort(jp_posterior* post) {
+  jp_ctx* ctx = post->ctx;
+  const long long M = post->M;
+  const int K = post->K_last;
+  JP_TRY(ensure_sort_buffers(post, K));
+  cudaStream_t st = ctx->stream;
+  dim3 gi((unsigned)((M + 255) / 256), K);
+  jp_iota_kernel<<<gi, 256, 0, st>>>(post->d_perm_a, M, M);
+  JP_CHECK_LAUNCH(ctx);
+  uint32_t *pin = post->d_perm_a, *pout = post->d_perm_b;
+  for (int b = 0; b < 8; ++b) {
+    ValueDigit f{post->d_vptr, 8 * b};
+    JP_TRY(jp_radix_pass(ctx, f, pin, pout, M, M, post->d_hist, K));
+    std::swap(pin, pout);
+  }
+  jp_gather_scan_kernel<<<K, 1024, 0, st>>>(post->d_vptr, post->d_density, pin, M, post->d_sv, post->d_sw, post->d_cw);
+  JP_CHECK_LAUNCH(ctx);
+  post->sorted_valid = true;
   return JP_OK;
 }
 
@@ -300,6 +452,7 @@ int jp_marginal_values(jp_posterior* post, int K, const double* h_values, double
                        double* h_value_nodes, double* h_weight_nodes) {
   JP_REQUIRE(post && h_values, "jp_marginal_values: null argument");
   JP_TRY(ensure_marginal_buffers(post, K));
+  JP_TRY(ensure_value_buffer(post, K));
   JP_CUDA(cudaMemcpyAsync(post->d_vals, h_values, (size_t)K * post->M * 8, cudaMemcpyHostToDevice, post->ctx->stream));
   JP_TRY(set_value_pointers(post, K, nullptr, post->d_vals));
   return run_marginals(post, K, h_mu, h_sigma, h_value_nodes, h_weight_nodes);
@@ -307,6 +460,7 @@ int jp_marginal_values(jp_posterior* post, int K, const double* h_values, double
 
 int jp_marginal_sorted(jp_posterior* post, int k, double* h_sv, double* h_sw, double* h_cw) {
   JP_REQUIRE(post && k >= 0 && k < post->K_last, "jp_marginal_sorted: marginal %d was not computed by the last call", k);
+  if (!post->sorted_valid) JP_TRY(run_sort(post));
   size_t off = (size_t)k * post->M, bytes = (size_t)post->M * 8;
   cudaStream_t st = post->ctx->stream;
   if (h_sv) JP_CUDA(cudaMemcpyAsync(h_sv, post->d_sv + off, bytes, cudaMemcpyDeviceToHost, st));
@@ -316,12 +470,33 @@ int jp_marginal_sorted(jp_posterior* post, int k, double* h_sv, double* h_sw, do
   return JP_OK;
 }
 
+int jp_marginal_knots_from_sort(jp_posterior* post, int K, double* h_value_nodes, double* h_weight_nodes) {
+  JP_REQUIRE(post && K >= 1 && K <= post->K_last, "jp_marginal_knots_from_sort: no marginal batch of %d to sort", K);
+  jp_ctx* ctx = post->ctx;
+  if (!post->sorted_valid) JP_TRY(run_sort(post));
+  cudaStream_t st = ctx->stream;
+  double* d_mom = ctx->d_scratch;
+  jp_moments_kernel<<<K, 1024, 0, st>>>(post->d_vptr, post->d_density, post->M, d_mom, 4);
+  JP_CHECK_LAUNCH(ctx);
+  jp_knots_kernel<<<K, 128, 0, st>>>(post->d_sv, post->d_cw, post->M, d_mom, 4, post->d_mout);
+  JP_CHECK_LAUNCH(ctx);
+  JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, post->d_mout, (size_t)K * JP_MOUT_STRIDE * 8, cudaMemcpyDeviceToHost, st));
+  JP_CUDA(cudaStreamSynchronize(st));
+  for (int k = 0; k < K; ++k) {
+    const double* o = ctx->h_pinned + (size_t)k * JP_MOUT_STRIDE;
+    if (h_value_nodes) std::copy(o + 2, o + 2 + JP_GRID_KNOTS, h_value_nodes + (size_t)k * JP_GRID_KNOTS);
+    if (h_weight_nodes) std::copy(o + 2 + JP_GRID_KNOTS, o + 2 + 2 * JP_GRID_KNOTS, h_weight_nodes + (size_t)k * JP_GRID_KNOTS);
+  }
+  return JP_OK;
+}
+
 int jp_marginal_local_moments(jp_posterior* post, int K, const int* h_coords, const double* d_values, double* d_out) {
   JP_REQUIRE(post && d_out, "jp_marginal_local_moments: null argument");
   JP_TRY(ensure_marginal_buffers(post, K));
   JP_TRY(set_value_pointers(post, K, h_coords, d_values));
   jp_moments_kernel<<<K, 1024, 0, post->ctx->stream>>>(post->d_vptr, post->d_density, post->M, d_out, 4);
   JP_CHECK_LAUNCH(post->ctx);
+  post->K_last = K;
   return JP_OK;
 }
 
@@ -330,10 +505,14 @@ int jp_marginal_local_knots(jp_posterior* post, int K, const int* h_coords, cons
   JP_REQUIRE(post && d_minmax && d_out, "jp_marginal_local_knots: null argument");
   JP_TRY(ensure_marginal_buffers(post, K));
   JP_TRY(set_value_pointers(post, K, h_coords, d_values));
-  dim3 grid(JP_GRID_KNOTS - 2, K);
-  jp_local_knots_kernel<<<grid, 256, 0, post->ctx->stream>>>(post->d_vptr, post->d_density, post->M, post->m0,
-                                                             d_minmax, d_out);
+  dim3 gb(post->bins_blocks, K);
+  jp_bins_kernel<<<gb, JP_BIN_THREADS, 0, post->ctx->stream>>>(post->d_vptr, post->d_density, post->M, post->m0, d_minmax, 2,
+                                                                0, post->d_bins);
   JP_CHECK_LAUNCH(post->ctx);
+  jp_bins_combine_kernel<false><<<K, 128, 0, post->ctx->stream>>>(post->d_bins, post->bins_blocks, d_minmax, 2, 0, nullptr, 0,
+                                                                   d_out);
+  JP_CHECK_LAUNCH(post->ctx);
+  post->K_last = K;
   return JP_OK;
 }
 

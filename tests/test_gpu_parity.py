@@ -239,6 +239,32 @@ def test_marginal_host_closures_and_sorted_arrays(jp, O, gpu_ctx):
     assert np.allclose(m.wv.cum_weights, mo["cum_weights"], rtol=1e-12, atol=1e-15)
 
 
+def test_sort_free_knots_match_explicit_sort(jp, O, gpu_ctx):
+    """The default 100-knot Grid (one binning pass, no sort) equals the knots computed on the device from the explicit
+    stable sort + cumulative sum (reference src/interp.jl:21-31,448-457) -- coordinate values (heavily tied),
+    smooth closures, and values tied across bins."""
+    obs, hyper = readme_records()
+    post, ref = _check_fit_and_marginals(jp, O, gpu_ctx, 0, [2, 2, 2], obs, hyper, 0, 7)
+    L = jp.lib()
+    th = ref["theta"]
+    rng = np.random.default_rng(3)
+    vals = np.stack([th[0], th[1] - th[2], np.round(th[0] * 20) / 20, np.floor(th[2] * 99.0), rng.standard_normal(post.n_nodes),
+                     np.where(np.arange(post.n_nodes) % 2 == 0, -1.0, 3.0)])
+    K = len(vals)
+    mu, sg = np.zeros(K), np.zeros(K)
+    vn, wn = np.zeros((K, 100)), np.zeros((K, 100))
+    p_ = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert L.jp_marginal_values(post.handle, K, p_(vals), p_(mu), p_(sg), p_(vn), p_(wn)) == 0
+    vn2, wn2 = np.zeros((K, 100)), np.zeros((K, 100))
+    assert L.jp_marginal_knots_from_sort(post.handle, K, p_(vn2), p_(wn2)) == 0
+    assert np.array_equal(vn, vn2)
+    assert np.max(np.abs(wn - wn2)) < 1e-13
+    for k in range(K):
+        mo = O.marginal(vals[k], post.density)
+        assert np.max(np.abs(wn[k] - mo["weight_nodes"])) < 1e-12, k
+    assert L.jp_marginal_knots_from_sort(post.handle, K + 1, p_(vn2), p_(wn2)) != 0     # more than the last batch: a status
+
+
 def test_marginal_special_values(jp, O, gpu_ctx):
     """Negative values, -0.0 / +0.0, huge and tiny magnitudes sort like the CPU stable sort."""
     obs, hyper = readme_records()
