@@ -333,10 +333,12 @@ def run_product(args):
         nc = int(post.diagnostics["series_terms"])
         clk = (clocks or {}).get("sm_mhz") or 1965.0
         fp32_peak = 148 * 128 * clk * 1e6          # FP32 lane-instructions / s of the FMA pipes
-        roof["epilogue"] = dict(fp32_instr_per_pair=nc + 2, achieved_lane_instr_per_s=(nc + 2) * local_pairs / (kms * 1e-3),
-                                peak_lane_instr_per_s=fp32_peak, frac=(nc + 2) * local_pairs / (kms * 1e-3) / fp32_peak,
-                                note="the kernel's true limiter: %d FP32 FMA-pipe instructions per pair (Horner of the link "
-                                     "remainder series) against 148 SMs x 128 lanes x SM clock" % (nc + 2))
+        ops = (nc + 3) / 2.0                       # NC + 3 packed operations serve a mirror pair of nodes
+        roof["epilogue"] = dict(fp32_instr_per_pair=ops, achieved_lane_instr_per_s=ops * local_pairs / (kms * 1e-3),
+                                peak_lane_instr_per_s=fp32_peak, frac=ops * local_pairs / (kms * 1e-3) / fp32_peak,
+                                note="the kernel's true limiter: (NC + 3) / 2 = %.1f FP32 FMA-pipe instructions per (node, observation) "
+                                     "pair (even / odd split of the link remainder series shared by a mirror pair of grid nodes) "
+                                     "against 148 SMs x 128 lanes x SM clock" % ops)
     roof["kernel"] = "jp_glm_tc_kernel" if path_used == _lib.PATH_TC else "jp_fit_nodes_kernel"
     try:   # DRAM traffic of the same kernel on the same workload from the committed ncu capture (per launch)
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("%s:%s" % (args.workload, roof["kernel"]))

@@ -40,17 +40,16 @@ int jp_glm_sums_device(jp_ctx* ctx, const jp_data* data, int d, const double* d_
 int jp_glm_num_blocks(const jp_ctx* ctx, long long N);
 
 #define TC_OBS_TILE 128          // MMA M: observations per tile (TMEM lanes)
-#ifndef TC_NODE_TILE
-#define TC_NODE_TILE 128         // MMA N: nodes per tile (TMEM columns)
-#endif
-#define TC_NBUF (512 / TC_NODE_TILE)            // accumulator buffers in TMEM (all 512 columns)
-#define TC_COLS_PER_WARP (TC_NODE_TILE / 2)     // each epilogue warp owns one lane quarter x half of the node columns
-#define TC_NCH (TC_COLS_PER_WARP / 16)          // 16-column tcgen05.ld chunks per warp and tile (even)
+#define TC_PAIR_TILE 96          // MMA N: mirror pairs of grid nodes per tile (TMEM columns)
+#define TC_TMEM_STRIDE 96        // columns between accumulator buffers
+#define TC_NBUF 5                // accumulator buffers in TMEM (5 x 96 of the 512 columns)
+#define TC_COLS_PER_WARP 32      // each epilogue warp owns one lane quarter x one third of the pair columns
+#define TC_EPI_WARPS (4 * TC_PAIR_TILE / TC_COLS_PER_WARP)   // 12: three per SM sub-partition
 #define TC_KATOM 32              // fp32 elements per 128-byte swizzle atom
 #define TC_NCMAX 12              // stored Taylor coefficients per observation: orders 3 .. 14
 #define TC_ORDER_MAX 16          // highest derivative order tabulated (tail bounds need two more than used)
-#define TC_THREADS 320           // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
-#define TC_EPI_THREADS 256
+#define TC_EPI_THREADS (32 * TC_EPI_WARPS)
+#define TC_THREADS (64 + TC_EPI_THREADS)   // warp 0 TMA, warp 1 MMA, warps 2-13 epilogue
 #define TC_MAX_STAGES 4
 #define TC_PREP_BLOCKS 296
 #define TC_NBOUND 14             // per-block bound partials, see tc_obs_prep_kernel
@@ -73,11 +72,11 @@ struct TcDataState {
 };
 
 struct TcPostState {
-  long long M_pad = 0;
+  long long P = 0, P_pad = 0, j_lo = 0;   // mirror pairs touched by the local node range; first pair index
   int kp = 0;
-  float* d_ds = nullptr;       // [M_pad][kp]  (d_hi | d_hi | d_lo | 0)
+  float* d_ds = nullptr;       // [P_pad][kp]  (d_hi | d_hi | d_lo | 0) of each pair's first member
   double* d_quad = nullptr;    // [M]
-  double* d_part = nullptr;    // [part_chunks][M] per-chunk remainder sums
+  double* d_part = nullptr;    // [part_chunks][P][2] per-chunk even / odd remainder sums
   int part_chunks = 0;
   CUtensorMap tmB;
 };
@@ -121,9 +120,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 // producer / MMA-issuer wait: these single threads have thousands of cycles of slack (the kernel is bound by
-// the epilogue), and a tight spin steals issue slots from the epilogue warps of their SM sub-partition
+// the epilogue), and a spin loop steals issue slots from the epilogue warps of their SM sub-partition.  try_wait
+// with a suspend-time hint parks the thread in hardware until the phase completes (or the hint expires).
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(1000000u)
+        : "memory");
+  } while (!ok);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -169,6 +180,18 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
                  "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t (&v)[8], uint32_t taddr) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait8(uint32_t (&v)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7])
                :
                : "memory");
 }
@@ -288,10 +311,13 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
   if (threadIdx.x == 0) ob[13] = v;
 }
 
-// Per node: delta = U z, theta = mu + delta (all transforms are the identity on this path), the FP64
-// quadratic part  L_hat + g.delta - 1/2 delta' H delta + prior(theta),  and the operand row [d_hi | d_hi | d_lo | 0]
+// Per node: delta = U z, theta = mu + delta (all transforms are the identity on this path) and the FP64
+// quadratic part  L_hat + g.delta - 1/2 delta' H delta + prior(theta).  Per mirror pair (grid nodes 2j-1, 2j; pair 0
+// is the origin): the operand row [d_hi | d_hi | d_lo | 0] of the pair's FIRST member, written by that node's
+// thread -- or, when the local range starts on a second member, by its thread with the sign flipped
+// (delta(-z) = -delta(z) exactly: the sums below are sign-symmetric in IEEE arithmetic, and so is the TF32 split).
 __global__ void __launch_bounds__(128)
-tc_node_prep_kernel(int d, int p, int kp, int rule, long long M, long long m0, long long M_grid,
+tc_node_prep_kernel(int d, int p, int kp, int rule, long long M, long long m0, long long M_grid, long long j_lo,
                     const uint8_t* __restrict__ idx, const double* __restrict__ znodes, const double* __restrict__ mu,
                     const double* __restrict__ U, const double* __restrict__ sums, double prior_sd,
                     double* __restrict__ theta, double* __restrict__ quad, float* __restrict__ ds) {
@@ -327,7 +353,11 @@ tc_node_prep_kernel(int d, int p, int kp, int rule, long long M, long long m0, l
   }
   const double L_hat = sums[d + d * (d + 1) / 2];
   double lin = 0, qf = 0, prior = 0;
-  float* o = ds + (size_t)m * kp;
+  const long long gm = m0 + m;
+  const bool first_member = (gm & 1) || gm == 0;
+  const bool writes_row = first_member || m == 0;
+  const float sgn = first_member ? 1.f : -1.f;
+  float* o = ds + (size_t)(((gm + 1) >> 1) - j_lo) * kp;
   for (int k = 0; k < d; ++k) {
     const double dk = dl[k * blockDim.x];
     const double th = s_mu[k] + dk;
@@ -338,23 +368,32 @@ tc_node_prep_kernel(int d, int p, int kp, int rule, long long M, long long m0, l
     qf += dk * hk;
     const double zz = th / prior_sd;
     prior += -0.5 * zz * zz - log(prior_sd) - 0.5 * 1.8378770664093454835606594728112;
-    float hi, lo;
-    tf32_split(dk, hi, lo);
-    o[k] = hi;
-    o[d + k] = hi;
-    o[2 * d + k] = lo;
+    if (writes_row) {
+      float hi, lo;
+      tf32_split(dk, hi, lo);
+      o[k] = sgn * hi;
+      o[d + k] = sgn * hi;
+      o[2 * d + k] = sgn * lo;
+    }
   }
   quad[m] = (L_hat + lin - 0.5 * qf) + prior;
 }
 
-// ld = quad - sum_c part[c] + neg_min ; a = ld + |z|^2/2
-__global__ void tc_finish_kernel(long long M, long long m0, int chunks, const double* __restrict__ part,
-                                 const double* __restrict__ quad, const double* __restrict__ hzz, double neg_min,
-                                 double* __restrict__ logdens, double* __restrict__ a) {
+// ld = quad - sum_c (E[c] +- O[c]) + neg_min ; a = ld + |z|^2/2.  The first member of a mirror pair takes E + O,
+// the second E - O (R(-D) = E(D) - O(D)).
+__global__ void tc_finish_kernel(long long M, long long m0, long long j_lo, long long P, int chunks,
+                                 const double* __restrict__ part, const double* __restrict__ quad,
+                                 const double* __restrict__ hzz, double neg_min, double* __restrict__ logdens,
+                                 double* __restrict__ a) {
   long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
+  const long long gm = m0 + m, j = ((gm + 1) >> 1) - j_lo;
+  const double sgn = ((gm & 1) || gm == 0) ? 1.0 : -1.0;
   double s = 0;
-  for (int c = 0; c < chunks; ++c) s += part[(size_t)c * M + m];
+  for (int c = 0; c < chunks; ++c) {
+    const double2 eo = *reinterpret_cast<const double2*>(part + ((size_t)c * P + j) * 2);
+    s += eo.x + sgn * eo.y;
+  }
   double ld = (quad[m] - s) + neg_min;
   logdens[m] = ld;
   a[m] = ld + hzz[m0 + m];
@@ -364,17 +403,18 @@ __global__ void tc_finish_kernel(long long M, long long m0, int chunks, const do
 struct TcKernelParams {
   int ka;                 // 128-byte K atoms per operand row
   int stages;             // observation-tile ring depth
-  int n_node_tiles;
-  int chunks;             // observation chunks (work items = n_node_tiles x chunks)
+  int nbbuf;              // pair-operand buffers (2: the next item's operand loads under the current item)
+  int n_pair_tiles;
+  int chunks;             // observation chunks (work items = n_pair_tiles x chunks)
   int tiles_per_chunk;
   int n_obs_tiles;
-  long long M;            // local node count
+  long long P;            // local mirror pairs
   const float* coef;      // [N_pad][TC_NCMAX]
-  double* part;           // [chunks][M]
+  double* part;           // [chunks][P][2]: even and odd part of the remainder sum of a pair
 };
 
-// Packed FP32 arithmetic (Blackwell FFMA2 / FMUL2): one instruction works on two adjacent node columns, which
-// halves the issue slots of the epilogue -- the resource this kernel is bound by.
+// Packed FP32 arithmetic (Blackwell FFMA2 / FMUL2): one instruction works on two adjacent pair columns, which
+// halves the issue slots of the epilogue (the FMA pipe itself retires 32 lanes x 2 per two cycles either way).
 __device__ __forceinline__ uint64_t f32x2_pack(uint32_t lo, uint32_t hi) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
@@ -393,37 +433,41 @@ __device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+__device__ __forceinline__ void f32x2_fma_acc(uint64_t& acc, uint64_t a, uint64_t b) {   // acc += a * b, in place
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
 __device__ __forceinline__ uint64_t f32x2_mul(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
 
-// acc[j] += D^3 (c_3 + c_4 D + ... ) for 16 columns = 8 packed pairs; c2[k] holds (c_{3+k}, c_{3+k}).
-// Estrin form: e_m = c_{3+2m} + c_{4+2m} D are independent and share the operand D, then Horner in D^2.
-// Same instruction count as plain Horner (NC + 2 per pair), but a column pair carries its own instruction-
-// level parallelism and consecutive instructions reuse D (or D^2) in the same operand slot, which matters
-// because an FFMA2 with three distinct 64-bit register operands is register-file-bandwidth bound.
+// Mirror pairs.  A column of the accumulator tile is a PAIR of grid nodes (z, -z) (adjacent in the grid's mirror
+// order, jp_grid.cu), represented by D = x_i . delta(z); the partner sees -D.  Splitting the remainder series by
+// parity,   R_i(+-D) = E_i(D) +- O_i(D),   E = D^4 (c_4 + c_6 D^2 + ...),   O = D^3 (c_3 + c_5 D^2 + ...),
+// one pass over D yields both nodes: NC + 3 packed operations per column instead of 2 (NC + 2), and half the
+// contraction, TMEM reads and operand traffic.  accE / accO: 8 columns = 4 packed pairs each; c[k] = c_{3+k}.
 template <int NC, int MODE>
-__device__ __forceinline__ void tc_accumulate16(const uint32_t (&v)[16], const float (&c)[NC], uint64_t* acc2) {
+__device__ __forceinline__ void tc_accumulate8(const uint32_t (&v)[8], const float (&c)[NC], uint64_t* accE, uint64_t* accO) {
   // coefficients stay scalar: ptxas folds the (c, c) pack into FFMA2's broadcast operand form (Rx.F32), which
   // reads one register instead of a pair
   if (MODE == 1) {   // profiling aid: TMEM traffic without the series arithmetic (results are meaningless)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc2[j] = f32x2_fma(f32x2_pack(v[2 * j], v[2 * j + 1]), f32x2_bcast(c[0]), acc2[j]);
+    for (int j = 0; j < 4; ++j) accE[j] = f32x2_fma(f32x2_pack(v[2 * j], v[2 * j + 1]), f32x2_bcast(c[0]), accE[j]);
     return;
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 4; ++j) {
     const uint64_t D = f32x2_pack(v[2 * j], v[2 * j + 1]);
-    uint64_t e[NC / 2];
-#pragma unroll
-    for (int m = 0; m < NC / 2; ++m) e[m] = f32x2_fma(f32x2_bcast(c[2 * m + 1]), D, f32x2_bcast(c[2 * m]));
     const uint64_t D2 = f32x2_mul(D, D);
-    uint64_t t = e[NC / 2 - 1];
+    uint64_t pe = f32x2_bcast(c[NC - 1]), po = f32x2_bcast(c[NC - 2]);   // NC even: c_{NC+2} is an even order
 #pragma unroll
-    for (int m = NC / 2 - 2; m >= 0; --m) t = f32x2_fma(t, D2, e[m]);
-    acc2[j] = f32x2_fma(f32x2_mul(D2, D), t, acc2[j]);
+    for (int m = NC / 2 - 2; m >= 0; --m) {
+      pe = f32x2_fma(pe, D2, f32x2_bcast(c[2 * m + 1]));
+      po = f32x2_fma(po, D2, f32x2_bcast(c[2 * m]));
+    }
+    f32x2_fma_acc(accE[j], f32x2_mul(D2, D2), pe);
+    f32x2_fma_acc(accO[j], f32x2_mul(D2, D), po);
   }
 }
 
@@ -448,22 +492,22 @@ template <int NC, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcKernelParams P) {
   extern __shared__ uint8_t smem_raw[];
-  // carve-up (1024-byte aligned for the 128-byte swizzle): node operand, observation ring, reduction buffer, barriers
+  // carve-up (1024-byte aligned for the 128-byte swizzle): pair operands, observation ring, reduction buffer, barriers
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sB = base;                                              // ka x (256 x 128 B)
-  const uint32_t b_bytes = (uint32_t)P.ka * TC_NODE_TILE * 128u;
-  const uint32_t sA = sB + b_bytes;                                      // stages x ka x (128 x 128 B)
+  const uint32_t sB = base;                                              // nbbuf x ka x (96 x 128 B)
+  const uint32_t b_bytes = (uint32_t)P.ka * TC_PAIR_TILE * 128u;
+  const uint32_t sA = sB + (uint32_t)P.nbbuf * b_bytes;                  // stages x ka x (128 x 128 B)
   const uint32_t a_bytes = (uint32_t)P.ka * TC_OBS_TILE * 128u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  double* red = reinterpret_cast<double*>(gen + b_bytes + (size_t)P.stages * a_bytes);   // 4 x 256 doubles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 4 * TC_NODE_TILE);
-  const uint32_t bar_full = smem_u32(bars);                 // [stages]
-  const uint32_t bar_empty = bar_full + 8u * TC_MAX_STAGES; // [stages]
-  const uint32_t bar_bfull = bar_empty + 8u * TC_MAX_STAGES;
-  const uint32_t bar_bempty = bar_bfull + 8u;
-  const uint32_t bar_tfull = bar_bempty + 8u;               // [TC_NBUF]
+  double* red = reinterpret_cast<double*>(gen + (size_t)P.nbbuf * b_bytes + (size_t)P.stages * a_bytes);   // [4][96][2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 4 * TC_PAIR_TILE * 2);
+  const uint32_t bar_full = smem_u32(bars);                 // [TC_MAX_STAGES]
+  const uint32_t bar_empty = bar_full + 8u * TC_MAX_STAGES; // [TC_MAX_STAGES]
+  const uint32_t bar_bfull = bar_empty + 8u * TC_MAX_STAGES;// [2]
+  const uint32_t bar_bempty = bar_bfull + 16u;              // [2]
+  const uint32_t bar_tfull = bar_bempty + 16u;              // [TC_NBUF]
   const uint32_t bar_tempty = bar_tfull + 8u * TC_NBUF;     // [TC_NBUF]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 2 + 2 * TC_NBUF);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 4 + 2 * TC_NBUF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -471,17 +515,19 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(bar_full + 8u * s, 1);
       mbar_init(bar_empty + 8u * s, 1);
     }
-    mbar_init(bar_bfull, 1);
-    mbar_init(bar_bempty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_bfull + 8u * b, 1);
+      mbar_init(bar_bempty + 8u * b, 1);
+    }
     for (int b = 0; b < TC_NBUF; ++b) {
       mbar_init(bar_tfull + 8u * b, 1);
-      mbar_init(bar_tempty + 8u * b, TC_EPI_THREADS / 32);
+      mbar_init(bar_tempty + 8u * b, TC_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
-  if (warp == 1) {   // TMEM: all 512 columns (four 128-column accumulator buffers)
+  if (warp == 1) {   // TMEM: all 512 columns (TC_NBUF accumulator buffers of TC_PAIR_TILE columns)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -491,20 +537,22 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_items = P.n_node_tiles * P.chunks;
+  const int n_items = P.n_pair_tiles * P.chunks;
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0, bphase = 0;
+      int stage = 0, bb = 0;
+      uint32_t phase = 0, bphase = 0;   // bphase: bit b = parity of pair-operand buffer b
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int chunk = item / P.n_node_tiles, node_tile = item % P.n_node_tiles;
+        const int chunk = item / P.n_pair_tiles, pair_tile = item % P.n_pair_tiles;
         const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
-        mbar_wait_relaxed(bar_bempty, bphase ^ 1);
-        mbar_expect_tx(bar_bfull, b_bytes);
+        mbar_wait_relaxed(bar_bempty + 8u * bb, ((bphase >> bb) & 1u) ^ 1u);
+        mbar_expect_tx(bar_bfull + 8u * bb, b_bytes);
         for (int a = 0; a < P.ka; ++a)
-          tma_load_2d(sB + (uint32_t)a * TC_NODE_TILE * 128u, &tmB, bar_bfull, a * TC_KATOM, node_tile * TC_NODE_TILE);
-        bphase ^= 1;
+          tma_load_2d(sB + (uint32_t)bb * b_bytes + (uint32_t)a * TC_PAIR_TILE * 128u, &tmB, bar_bfull + 8u * bb,
+                      a * TC_KATOM, pair_tile * TC_PAIR_TILE);
+        bphase ^= 1u << bb;
+        if (++bb == P.nbbuf) bb = 0;
         for (int t = t0; t < t1; ++t) {
           mbar_wait_relaxed(bar_empty + 8u * stage, phase ^ 1);
           mbar_expect_tx(bar_full + 8u * stage, a_bytes);
@@ -518,24 +566,23 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
-      // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_NODE_TILE >> 3) << 17) |
+      // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 96 pairs, M = 128 observations
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_PAIR_TILE >> 3) << 17) |
                              ((uint32_t)(TC_OBS_TILE >> 4) << 24);
-      int stage = 0, buf = 0;
+      int stage = 0, buf = 0, bb = 0;
       uint32_t phase = 0, bphase = 0, tphase = 0;   // tphase: bit b = parity of accumulator buffer b
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int chunk = item / P.n_node_tiles;
+        const int chunk = item / P.n_pair_tiles;
         const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
-        mbar_wait_relaxed(bar_bfull, bphase);
-        bphase ^= 1;
+        mbar_wait_relaxed(bar_bfull + 8u * bb, (bphase >> bb) & 1u);
         for (int t = t0; t < t1; ++t) {
           mbar_wait_relaxed(bar_tempty + 8u * buf, ((tphase >> buf) & 1u) ^ 1u);
           mbar_wait_relaxed(bar_full + 8u * stage, phase);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC_NODE_TILE;
+          const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC_TMEM_STRIDE;
           for (int a = 0; a < P.ka; ++a) {
             const uint32_t aA = sA + (uint32_t)stage * a_bytes + (uint32_t)a * TC_OBS_TILE * 128u;
-            const uint32_t aB = sB + (uint32_t)a * TC_NODE_TILE * 128u;
+            const uint32_t aB = sB + (uint32_t)bb * b_bytes + (uint32_t)a * TC_PAIR_TILE * 128u;
 #pragma unroll
             for (int j = 0; j < 4; ++j)   // K = 8 tf32 = 32 bytes per instruction inside the 128-byte atom
               umma_tf32(d_tmem, umma_desc(aA + 32u * j), umma_desc(aB + 32u * j), idesc, (a | j) ? 1u : 0u);
@@ -543,33 +590,37 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_commit(bar_empty + 8u * stage);        // frees the observation stage when the MMAs have read it
           tc_commit(bar_tfull + 8u * buf);          // publishes the accumulator buffer
           tphase ^= 1u << buf;
-          buf = (buf + 1) % TC_NBUF;
+          if (++buf == TC_NBUF) buf = 0;
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(bar_bempty);                      // node operand may be overwritten once every MMA has retired
+        tc_commit(bar_bempty + 8u * bb);            // pair operand may be overwritten once every MMA has retired
+        bphase ^= 1u << bb;
+        if (++bb == P.nbbuf) bb = 0;
       }
     }
   } else {
     // ===================================================== epilogue warps
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int h = (warp - 2) >> 2;           // column half handled by this warp
-    const int et = threadIdx.x - 64;         // 0 .. 255
-    uint64_t acc2[TC_COLS_PER_WARP / 2];     // 64 FP32 accumulators, packed in pairs of adjacent columns
+    const int h = (warp - 2) >> 2;           // column third handled by this warp
+    const int et = threadIdx.x - 64;         // 0 .. TC_EPI_THREADS - 1
+    uint64_t accE[TC_COLS_PER_WARP / 2], accO[TC_COLS_PER_WARP / 2];   // FP32 sums, packed in pairs of adjacent columns
 #pragma unroll
-    for (int j = 0; j < TC_COLS_PER_WARP / 2; ++j) acc2[j] = 0ull;
+    for (int j = 0; j < TC_COLS_PER_WARP / 2; ++j) accE[j] = accO[j] = 0ull;
     int buf = 0;
     uint32_t tphase = 0;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * TC_COLS_PER_WARP);
+    const float* coef_row = P.coef + (size_t)(q * 32 + lane) * TC_NCMAX;   // this thread's observation: tile row = TMEM lane
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int chunk = item / P.n_node_tiles, node_tile = item % P.n_node_tiles;
+      const int chunk = item / P.n_pair_tiles, pair_tile = item % P.n_pair_tiles;
       const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
       // Software pipeline over (tile, 16-column chunk): the tcgen05.ld of the next chunk -- across a tile
       // boundary too, the next accumulator buffer is normally complete long before -- and the coefficient
-      // loads of the next tile are in flight while the current chunk is evaluated.
-      uint32_t va[16], vb[16];
-      float c2[NC];
+      // loads of the next tile are in flight while the current chunk is evaluated.  The tile loop is unrolled
+      // by two so that the two coefficient sets alternate without register copies.
+      uint32_t va[8], vb[8];
+      float ca[NC], cb[NC];
       auto load_coef = [&](int t, float (&dst)[NC]) {
-        // this thread's observation: row of the tile = TMEM lane
-        const float2* cp = reinterpret_cast<const float2*>(P.coef + ((size_t)t * TC_OBS_TILE + q * 32 + lane) * TC_NCMAX);
+        const float2* cp = reinterpret_cast<const float2*>(coef_row + (size_t)t * (TC_OBS_TILE * TC_NCMAX));
 #pragma unroll
         for (int k = 0; k < NC / 2; ++k) {
           const float2 f = __ldg(cp + k);
@@ -577,66 +628,72 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           dst[2 * k + 1] = f.y;
         }
       };
-      auto tile_addr = [&](int b) {
-        return tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * TC_NODE_TILE + h * TC_COLS_PER_WARP);
-      };
-      load_coef(t0, c2);
-      mbar_wait(bar_tfull + 8u * buf, (tphase >> buf) & 1u);
-      tphase ^= 1u << buf;
-      tc_fence_after();
-      tmem_ld16(va, tile_addr(buf));
-      for (int t = t0; t < t1; ++t) {
+      auto tile_step = [&](int t, const float (&cc)[NC], float (&cn)[NC]) {
         const bool more = t + 1 < t1;
-        const int nbuf = (buf + 1) % TC_NBUF;
-        float cn[NC];
+        const int nbuf = (buf + 1 == TC_NBUF) ? 0 : buf + 1;
         if (more) load_coef(t + 1, cn);
-        const uint32_t taddr = tile_addr(buf);
-#pragma unroll
-        for (int cc = 0; cc < TC_NCH; cc += 2) {
-          tmem_ld_wait16(va);
-          if (MODE != 2) tmem_ld16(vb, taddr + 16u * (cc + 1));
-          tc_accumulate16<NC, MODE>(va, c2, acc2 + 8 * cc);
-          tmem_ld_wait16(vb);
-          if (cc + 2 < TC_NCH) {
-            if (MODE != 2) tmem_ld16(va, taddr + 16u * (cc + 2));
-          } else if (more) {
-            mbar_wait(bar_tfull + 8u * nbuf, (tphase >> nbuf) & 1u);
-            tphase ^= 1u << nbuf;
-            tc_fence_after();
-            if (MODE != 2) tmem_ld16(va, tile_addr(nbuf));
-          }
-          tc_accumulate16<NC, MODE>(vb, c2, acc2 + 8 * (cc + 1));
-        }
-        // every tcgen05.ld of this tile has completed (the last wait above precedes the prefetch's issue only
-        // for the next buffer): hand the accumulator buffer back to the MMA issuer
+        const uint32_t taddr = lane_addr + (uint32_t)buf * TC_TMEM_STRIDE;
+        tmem_ld_wait8(va);
+        if (MODE != 2) tmem_ld8(vb, taddr + 8u);
+        tc_accumulate8<NC, MODE>(va, cc, accE, accO);
+        tmem_ld_wait8(vb);
+        if (MODE != 2) tmem_ld8(va, taddr + 16u);
+        tc_accumulate8<NC, MODE>(vb, cc, accE + 4, accO + 4);
+        tmem_ld_wait8(va);
+        if (MODE != 2) tmem_ld8(vb, taddr + 24u);
+        tc_accumulate8<NC, MODE>(va, cc, accE + 8, accO + 8);
+        tmem_ld_wait8(vb);
+        // every tcgen05.ld of this tile has completed: hand the accumulator buffer back to the MMA issuer
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8u * buf);
-        buf = nbuf;
         if (more) {
-#pragma unroll
-          for (int k = 0; k < NC; ++k) c2[k] = cn[k];
+          mbar_wait(bar_tfull + 8u * nbuf, (tphase >> nbuf) & 1u);
+          tphase ^= 1u << nbuf;
+          tc_fence_after();
+          if (MODE != 2) tmem_ld8(va, lane_addr + (uint32_t)nbuf * TC_TMEM_STRIDE);
         }
+        tc_accumulate8<NC, MODE>(vb, cc, accE + 12, accO + 12);
+        buf = nbuf;
+      };
+      int t = t0;
+      const bool odd = ((t1 - t0) & 1) != 0;
+      if (odd) load_coef(t0, cb); else load_coef(t0, ca);
+      mbar_wait(bar_tfull + 8u * buf, (tphase >> buf) & 1u);
+      tphase ^= 1u << buf;
+      tc_fence_after();
+      tmem_ld8(va, lane_addr + (uint32_t)buf * TC_TMEM_STRIDE);
+      if (odd) {       // peel one tile so that the main loop is two straight-line steps
+        tile_step(t, cb, ca);
+        ++t;
+      }
+      for (; t < t1; t += 2) {
+        tile_step(t, ca, cb);
+        tile_step(t + 1, cb, ca);
       }
       // flush the item: sum over the 32 observation lanes by transpose-reduce, over the 4 lane quarters in
-      // shared memory (FP64), one partial per (chunk, node)
-#pragma unroll
-      for (int g = 0; g < TC_COLS_PER_WARP / 32; ++g) {
+      // shared memory (FP64), one (even, odd) partial per (chunk, pair)
+      {
         float col[32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f32x2_unpack(acc2[16 * g + j], col[2 * j], col[2 * j + 1]);
-        const float s = tc_transpose_reduce32(col, lane);
-        red[q * TC_NODE_TILE + h * TC_COLS_PER_WARP + g * 32 + lane] = (double)s;
+        for (int j = 0; j < 16; ++j) f32x2_unpack(accE[j], col[2 * j], col[2 * j + 1]);
+        const float sE = tc_transpose_reduce32(col, lane);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f32x2_unpack(accO[j], col[2 * j], col[2 * j + 1]);
+        const float sO = tc_transpose_reduce32(col, lane);
+        double* r = red + ((size_t)q * TC_PAIR_TILE + h * TC_COLS_PER_WARP + lane) * 2;
+        r[0] = (double)sE;
+        r[1] = (double)sO;
       }
       epi_bar_sync();
-      if (et < TC_NODE_TILE) {
-        const double s = (red[et] + red[TC_NODE_TILE + et]) + (red[2 * TC_NODE_TILE + et] + red[3 * TC_NODE_TILE + et]);
-        const long long node = (long long)node_tile * TC_NODE_TILE + et;
-        if (node < P.M) P.part[(size_t)chunk * P.M + node] = s;
+      if (et < 2 * TC_PAIR_TILE) {
+        const double s = (red[et] + red[2 * TC_PAIR_TILE + et]) + (red[4 * TC_PAIR_TILE + et] + red[6 * TC_PAIR_TILE + et]);
+        const long long pair = (long long)pair_tile * TC_PAIR_TILE + (et >> 1);
+        if (pair < P.P) P.part[((size_t)chunk * P.P + pair) * 2 + (et & 1)] = s;
       }
       epi_bar_sync();
 #pragma unroll
-      for (int j = 0; j < TC_COLS_PER_WARP / 2; ++j) acc2[j] = 0ull;
+      for (int j = 0; j < TC_COLS_PER_WARP / 2; ++j) accE[j] = accO[j] = 0ull;
     }
   }
   tc_fence_before();
@@ -775,11 +832,14 @@ static int ensure_post_state(jp_posterior* post, int kp) {
   TcPostState* s = new TcPostState();
   post->tc_state = s;
   s->kp = kp;
-  s->M_pad = ((post->M + TC_NODE_TILE - 1) / TC_NODE_TILE) * TC_NODE_TILE;
-  JP_CUDA(jp_dmalloc(post->ctx, &s->d_ds, (size_t)s->M_pad * kp * sizeof(float)));
-  JP_CUDA(cudaMemsetAsync(s->d_ds, 0, (size_t)s->M_pad * kp * sizeof(float), post->ctx->stream));
+  // mirror pairs (grid nodes 2j-1, 2j; pair 0 = the origin) touched by the local node range [m0, m0 + M)
+  s->j_lo = (post->m0 + 1) >> 1;
+  s->P = ((post->m0 + post->M) >> 1) - s->j_lo + 1;
+  s->P_pad = ((s->P + TC_PAIR_TILE - 1) / TC_PAIR_TILE) * TC_PAIR_TILE;
+  JP_CUDA(jp_dmalloc(post->ctx, &s->d_ds, (size_t)s->P_pad * kp * sizeof(float)));
+  JP_CUDA(cudaMemsetAsync(s->d_ds, 0, (size_t)s->P_pad * kp * sizeof(float), post->ctx->stream));
   JP_CUDA(jp_dmalloc(post->ctx, &s->d_quad, (size_t)post->M * 8));
-  JP_TRY(make_tensor_map(&s->tmB, s->d_ds, s->M_pad, kp, TC_NODE_TILE));
+  JP_TRY(make_tensor_map(&s->tmB, s->d_ds, s->P_pad, kp, TC_PAIR_TILE));
   return JP_OK;
 }
 
@@ -808,7 +868,7 @@ static int jp_tc_choose_order(const double* b, double* err_trunc, double* err_ro
 template <int NC, int MODE>
 static int launch_tc_mode(jp_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcKernelParams& kp, size_t smem) {
   JP_CUDA(cudaFuncSetAttribute(jp_glm_tc_kernel<NC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = std::min(ctx->sm_count, kp.n_node_tiles * kp.chunks);
+  int grid = std::min(ctx->sm_count, kp.n_pair_tiles * kp.chunks);
   cudaEventRecord(ctx->ev_k0, ctx->stream);
   jp_glm_tc_kernel<NC, MODE><<<grid, TC_THREADS, smem, ctx->stream>>>(tmA, tmB, kp);
   cudaEventRecord(ctx->ev_k1, ctx->stream);
@@ -831,6 +891,7 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   jp_ctx* ctx = post->ctx;
   jp_data* data = const_cast<jp_data*>(post->data);
   if (!tc_static_ok(post, args)) return JP_ERR_UNSUPPORTED;
+  JP_REQUIRE(post->grid->M % 2 == 1, "tensor-core path: the grid is not in mirror order (even node count %lld)", post->grid->M);
   const int d = args->d, p = args->p;
   JP_TRY(upload_tables());
   JP_TRY(ensure_data_state(ctx, data, d));
@@ -872,18 +933,21 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   if (sm_node > 48 * 1024)
     JP_CUDA(cudaFuncSetAttribute(tc_node_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_node));
   tc_node_prep_kernel<<<(unsigned)((post->M + 127) / 128), 128, sm_node, st>>>(
-      d, p, ds->kp, post->grid->rule, post->M, post->m0, post->grid->M, post->grid->d_idx,
+      d, p, ds->kp, post->grid->rule, post->M, post->m0, post->grid->M, ps->j_lo, post->grid->d_idx,
       jp_rule_nodes_dev(post->grid->rule), post->d_mu, post->d_U, ds->d_sums, data->hyper[0], post->d_theta, ps->d_quad,
       ps->d_ds);
   JP_CHECK_LAUNCH(ctx);
   // work decomposition: node tiles x observation chunks on a persistent grid
   TcKernelParams kp;
   kp.ka = ds->ka;
-  kp.n_node_tiles = (int)(ps->M_pad / TC_NODE_TILE);
+  kp.n_pair_tiles = (int)(ps->P_pad / TC_PAIR_TILE);
   kp.n_obs_tiles = (int)(ds->N_pad / TC_OBS_TILE);
-  const size_t b_bytes = (size_t)kp.ka * TC_NODE_TILE * 128, a_bytes = (size_t)kp.ka * TC_OBS_TILE * 128;
-  const size_t fixed = 1024 + b_bytes + 4 * TC_NODE_TILE * 8 + 256;
-  kp.stages = (int)std::max<size_t>(2, std::min<size_t>(TC_MAX_STAGES, (200 * 1024 - fixed) / a_bytes));
+  const size_t b_bytes = (size_t)kp.ka * TC_PAIR_TILE * 128, a_bytes = (size_t)kp.ka * TC_OBS_TILE * 128;
+  const size_t budget = 216 * 1024, misc = 1024 + 4 * TC_PAIR_TILE * 2 * 8 + 256;
+  // two pair-operand buffers unless that would push the observation ring below three stages
+  kp.nbbuf = ((budget - misc - 2 * b_bytes) / a_bytes >= 3) ? 2 : 1;
+  const size_t fixed = misc + (size_t)kp.nbbuf * b_bytes;
+  kp.stages = (int)std::max<size_t>(2, std::min<size_t>(TC_MAX_STAGES, (budget - fixed) / a_bytes));
   const size_t smem = fixed + (size_t)kp.stages * a_bytes;
   // Work items are (observation chunk, node tile) pairs in CHUNK-MAJOR order on the persistent grid: all CTAs sweep
   // the same chunk of observation tiles at about the same time, so a chunk is read from HBM once and then served
@@ -895,7 +959,7 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   double best_eff = 0;
   for (int c = c_min; c <= c_min + 48; ++c) {
     if (c > c_min && kp.n_obs_tiles / c < 8) break;
-    long long items = (long long)kp.n_node_tiles * c;
+    long long items = (long long)kp.n_pair_tiles * c;
     long long rounds = (items + ctx->sm_count - 1) / ctx->sm_count;
     double eff = (double)items / (double)(rounds * ctx->sm_count);
     if (eff > best_eff + 1e-9) { best_eff = eff; best_c = c; }
@@ -908,10 +972,10 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
     jp_dfree(ctx, ps->d_part);
     ps->d_part = nullptr;
     ps->part_chunks = 0;
-    JP_CUDA(jp_dmalloc(ctx, &ps->d_part, (size_t)kp.chunks * post->M * 8));
+    JP_CUDA(jp_dmalloc(ctx, &ps->d_part, (size_t)kp.chunks * ps->P * 2 * 8));
     ps->part_chunks = kp.chunks;
   }
-  kp.M = post->M;
+  kp.P = ps->P;
   kp.coef = ds->d_coef;
   kp.part = ps->d_part;
   int stc;
@@ -921,7 +985,7 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   else if (NC == 10) stc = launch_tc<10>(ctx, ds->tmA, ps->tmB, kp, smem);
   else stc = launch_tc<12>(ctx, ds->tmA, ps->tmB, kp, smem);
   JP_TRY(stc);
-  tc_finish_kernel<<<(unsigned)((post->M + 255) / 256), 256, 0, st>>>(post->M, post->m0, kp.chunks, ps->d_part, ps->d_quad,
+  tc_finish_kernel<<<(unsigned)((post->M + 255) / 256), 256, 0, st>>>(post->M, post->m0, ps->j_lo, ps->P, kp.chunks, ps->d_part, ps->d_quad,
                                                                        post->grid->d_hzz, args->neg_min, post->d_logdens,
                                                                        post->d_a);
   JP_CHECK_LAUNCH(ctx);

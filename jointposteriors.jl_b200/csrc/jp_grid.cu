@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(1024) jp_scan64_kernel(const unsigned long lon
 
 __global__ void jp_expand_kernel(int d, int rule, unsigned long long n_mi, const uint8_t* __restrict__ mi,
                                  const double* __restrict__ coef, const unsigned long long* __restrict__ off,
-                                 unsigned long long P, uint8_t* __restrict__ keys, double* __restrict__ wt) {
+                                 unsigned long long P, uint8_t* __restrict__ keys, uint8_t* __restrict__ flip,
+                                 double* __restrict__ wt) {
   unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= P) return;
   // last multi-index a with off[a] <= t
@@ -187,16 +188,32 @@ __global__ void jp_expand_kernel(int d, int rule, unsigned long long n_mi, const
     local /= np;
   }
   double w = coef[lo];
+  uint8_t first = 0;     // first non-zero master index: even = negative node = this point is the mirrored member
   for (int k = 0; k < d; ++k) {
     w = __dmul_rn(w, c_rule_weights[rule][m[k] - 1][j[k]]);
     keys[(size_t)k * P + t] = j[k];
+    if (first == 0) first = j[k];
   }
+  flip[t] = (first != 0 && (first & 1) == 0) ? 1 : 0;
   wt[t] = w;
 }
 
+// Mirror order (see the CPU restatement, oracle/jp_oracle.cpp orc_smolyak_build): sort by the CANONICAL key -- the
+// point's own key when its first non-zero coordinate is a positive node (odd master index), else the key of -z
+// (master indices 2j-1 <-> 2j swapped) -- and, least significant, by the mirrored flag.  Node 0 is then the
+// origin and nodes 2j-1, 2j are a mirror pair (z, -z): the tensor-core GLM path evaluates a pair from one
+// contraction.  Duplicates share raw keys, hence canonical keys: the stable sort keeps their generation order.
 struct KeyDigit {
   const uint8_t* keys;   // column of the current dimension: keys + k * P
-  __device__ __forceinline__ unsigned operator()(int, uint32_t src) const { return keys[src]; }
+  const uint8_t* flip;
+  __device__ __forceinline__ unsigned operator()(int, uint32_t src) const {
+    const unsigned j = keys[src];
+    return (flip[src] && j) ? (((j - 1u) ^ 1u) + 1u) : j;
+  }
+};
+struct FlipDigit {
+  const uint8_t* flip;
+  __device__ __forceinline__ unsigned operator()(int, uint32_t src) const { return flip[src]; }
 };
 
 // head[i] = 1 if sorted element i starts a new key
@@ -331,11 +348,12 @@ int jp_grid_build(jp_ctx* ctx, int rule, int d, int level, jp_grid* g) {
   }
   g->n_premerge = (long long)Ptot;
 
-  uint8_t* d_keys = nullptr;
+  uint8_t *d_keys = nullptr, *d_flip = nullptr;
   double* d_wt = nullptr;
   uint32_t *d_pa = nullptr, *d_pb = nullptr, *d_hist = nullptr, *d_head = nullptr, *d_seg = nullptr, *d_start = nullptr;
   int nb = jp_sort_blocks((long long)Ptot);
   JP_CUDA(jp_dmalloc(ctx, &d_keys, Ptot * d));
+  JP_CUDA(jp_dmalloc(ctx, &d_flip, Ptot));
   JP_CUDA(jp_dmalloc(ctx, &d_wt, Ptot * 8));
   JP_CUDA(jp_dmalloc(ctx, &d_pa, Ptot * 4));
   JP_CUDA(jp_dmalloc(ctx, &d_pb, Ptot * 4));
@@ -343,13 +361,18 @@ int jp_grid_build(jp_ctx* ctx, int rule, int d, int level, jp_grid* g) {
   JP_CUDA(jp_dmalloc(ctx, &d_head, Ptot * 4));
   JP_CUDA(jp_dmalloc(ctx, &d_seg, (Ptot + 1) * 4));
   unsigned gp = (unsigned)((Ptot + 255) / 256);
-  jp_expand_kernel<<<gp, 256, 0, st>>>(d, rule, n_mi, d_mi, d_coef, d_off, Ptot, d_keys, d_wt);
+  jp_expand_kernel<<<gp, 256, 0, st>>>(d, rule, n_mi, d_mi, d_coef, d_off, Ptot, d_keys, d_flip, d_wt);
   JP_CHECK_LAUNCH(ctx);
   jp_iota_kernel<<<dim3(gp, 1), 256, 0, st>>>(d_pa, (long long)Ptot, (long long)Ptot);
   JP_CHECK_LAUNCH(ctx);
   uint32_t *pin = d_pa, *pout = d_pb;
+  {   // least significant of all: the mirrored flag
+    FlipDigit f{d_flip};
+    JP_TRY(jp_radix_pass(ctx, f, pin, pout, (long long)Ptot, (long long)Ptot, d_hist, 1));
+    std::swap(pin, pout);
+  }
   for (int k = d - 1; k >= 0; --k) {   // LSD: least significant dimension first
-    KeyDigit f{d_keys + (size_t)k * Ptot};
+    KeyDigit f{d_keys + (size_t)k * Ptot, d_flip};
     JP_TRY(jp_radix_pass(ctx, f, pin, pout, (long long)Ptot, (long long)Ptot, d_hist, 1));
     std::swap(pin, pout);
   }
@@ -383,7 +406,7 @@ int jp_grid_build(jp_ctx* ctx, int rule, int d, int level, jp_grid* g) {
   }
   g->ctx = ctx; g->rule = rule; g->d = d; g->level = level; g->M = M;
   jp_dfree(ctx, d_comp); jp_dfree(ctx, d_mi); jp_dfree(ctx, d_coef); jp_dfree(ctx, d_npts); jp_dfree(ctx, d_off);
-  jp_dfree(ctx, d_keys); jp_dfree(ctx, d_wt); jp_dfree(ctx, d_pa); jp_dfree(ctx, d_pb); jp_dfree(ctx, d_hist);
+  jp_dfree(ctx, d_keys); jp_dfree(ctx, d_flip); jp_dfree(ctx, d_wt); jp_dfree(ctx, d_pa); jp_dfree(ctx, d_pb); jp_dfree(ctx, d_hist);
   jp_dfree(ctx, d_head); jp_dfree(ctx, d_seg); jp_dfree(ctx, d_start);
   return JP_OK;
 }

@@ -24,10 +24,19 @@ NK = GRID_KNOTS - 2   # interior knots
 
 
 def shard_bounds(M, rank, world):
-    """Contiguous node block [begin, end) of `rank`: sizes differ by at most one."""
-    base, rem = divmod(int(M), int(world))
-    begin = rank * base + min(rank, rem)
-    return begin, begin + base + (1 if rank < rem else 0)
+    """Contiguous node block [begin, end) of `rank`.  The grid is in mirror order (node 0 = origin, nodes 2j-1, 2j
+    = a pair z, -z that the tensor-core path evaluates together), so interior cuts fall on odd indices: no pair
+    straddles two ranks.  Sizes differ by at most two."""
+    M, world = int(M), int(world)
+
+    def cut(r):
+        if r <= 0:
+            return 0
+        if r >= world:
+            return M
+        c = (r * M) // world
+        return min(M, c | 1)
+    return cut(rank), cut(rank + 1)
 
 
 def _all_gather(t, group):

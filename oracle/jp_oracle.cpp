@@ -284,11 +284,19 @@ int orc_smolyak_sizes(int rule_id, int d, int L, long long* n_multi, long long* 
 }
 
 // Build the merged grid.  Nodes are identified by their integer key (one master-node index per
-// dimension); merged nodes come out in ascending lexicographic key order (dimension 0 most
-// significant); weights of duplicates are summed in generation order (multi-index order, then
+// dimension); weights of duplicates are summed in generation order (multi-index order, then
 // mixed-radix point order with the LAST dimension fastest) -- the CUDA builder reproduces the
 // same order, which is what makes the weight table bit-exact.
+//
+// Node order ("mirror order"): the 1-D rules are symmetric (master indices 2j-1 / 2j are +g_j / -g_j), so the
+// grid is closed under z -> -z.  A node's CANONICAL key is its own key if its first non-zero coordinate
+// (lowest dimension) is positive, else the key of its mirror image -z; nodes are sorted by (canonical key in
+// ascending lexicographic order with dimension 0 most significant, then mirrored flag).  Hence node 0 is the
+// origin and nodes 2j-1, 2j (j >= 1) are a mirror pair (z, -z) with z's first non-zero coordinate positive.
+// (The order of the reference's grid is unknowable -- SparseQuadratureGrids is absent -- and only enters results
+// through the tie rule of the stable sort in `Grid`, reference src/interp.jl:21-26.)
 // Pass idx == NULL to query M only.  idx is M x d row-major (uint8), w is M.
+static inline uint8_t mirror_index(uint8_t j) { return j == 0 ? 0 : (uint8_t)((((j - 1) ^ 1)) + 1); }
 long long orc_smolyak_build(int rule_id, int d, int L, uint8_t* idx, double* w, long long cap_M) {
   Rule r = get_rule(rule_id);
   int cap = std::min(L, r.levels);
@@ -322,10 +330,29 @@ long long orc_smolyak_build(int rule_id, int d, int L, uint8_t* idx, double* w, 
   long long M = (long long)acc.size();
   if (!idx) return M;
   if (M > cap_M) return -M;
-  long long m = 0;
+  // mirror order: sort by (canonical key, mirrored flag)
+  struct Ent { std::vector<uint8_t> canon; int flag; const std::vector<uint8_t>* key; double w; };
+  std::vector<Ent> ents;
+  ents.reserve((size_t)M);
   for (auto& kv : acc) {
-    std::memcpy(idx + m * d, kv.first.data(), d);
-    w[m] = kv.second;
+    Ent e;
+    e.key = &kv.first;
+    e.w = kv.second;
+    e.flag = 0;
+    for (int k = 0; k < d; ++k)
+      if (kv.first[k] != 0) { e.flag = (kv.first[k] % 2 == 0); break; }
+    e.canon = kv.first;
+    if (e.flag) for (int k = 0; k < d; ++k) e.canon[k] = mirror_index(e.canon[k]);
+    ents.push_back(std::move(e));
+  }
+  std::sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) {
+    if (a.canon != b.canon) return a.canon < b.canon;
+    return a.flag < b.flag;
+  });
+  long long m = 0;
+  for (auto& e : ents) {
+    std::memcpy(idx + m * d, e.key->data(), d);
+    w[m] = e.w;
     ++m;
   }
   return M;

@@ -277,10 +277,23 @@ def test_smolyak_counts_match_survey(O):
     assert M == 17981
 
 
-def test_smolyak_order_is_lexicographic(O):
-    idx, _ = O.smolyak(0, 4, 4)
-    keys = [tuple(r) for r in idx.tolist()]
-    assert keys == sorted(keys)
+@pytest.mark.parametrize("rule,d,L", [(0, 4, 4), (0, 3, 7), (1, 5, 4), (0, 10, 3), (1, 2, 8)])
+def test_smolyak_mirror_order(O, rule, d, L):
+    """Node 0 is the origin; nodes 2j-1, 2j are a mirror pair (z, -z), z's first non-zero coordinate positive;
+    pairs ascend lexicographically by the key of their first member; mirror images carry the same weight."""
+    idx, w = O.smolyak(rule, d, L)
+    _, znodes, _ = O.rule_info(rule)
+    assert len(w) % 2 == 1 and not idx[0].any()
+    a, b = idx[1::2].astype(int), idx[2::2].astype(int)
+    assert np.array_equal(np.where(a == 0, 0, ((a - 1) ^ 1) + 1), b)
+    assert np.array_equal(znodes[a], -znodes[b])
+    first = a[np.arange(len(a)), (a != 0).argmax(axis=1)]
+    assert np.all(first % 2 == 1)                      # odd master index = positive node
+    keys = [tuple(r) for r in a.tolist()]
+    assert keys == sorted(keys) and len(set(keys)) == len(keys)
+    assert np.allclose(w[1::2], w[2::2], rtol=1e-12, atol=1e-300)
+    # same node set and weights as the plain lexicographic merge
+    assert len({tuple(r) for r in idx.tolist()}) == len(w)
 
 
 def test_noncentred_transform_and_eight_schools_mode(O):
