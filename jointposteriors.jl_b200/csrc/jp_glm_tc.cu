@@ -63,7 +63,7 @@ struct TcDataState {
   int d = 0, kp = 0, ka = 0;
   long long N = 0, N_pad = 0;
   float* d_xs = nullptr;       // [N_pad][kp]  (x_hi | x_lo | x_hi | 0)
-  float* d_coef = nullptr;     // [N_pad][TC_NCMAX]
+  float* d_coef = nullptr;     // [TC_NCMAX][N_pad]: coefficient k of every observation, contiguous per 128-observation tile
   double* d_sums = nullptr;    // packed (g[d], upper H[d(d+1)/2], L_hat)
   double* d_work = nullptr;    // partials of the GLM sums
   double* d_bounds = nullptr;  // [TC_PREP_BLOCKS][TC_NBOUND]
@@ -141,6 +141,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
 }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -234,9 +239,9 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
   __syncthreads();
   double b_tmax = 0, b_a1 = 0, b_ref[TC_NORD] = {0}, b_max[TC_NORD] = {0}, b_r = 0, b_r2 = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N_pad; i += (long long)gridDim.x * blockDim.x) {
-    float* o = coef + (size_t)i * TC_NCMAX;
+    float* o = coef + i;     // o[k * N_pad]
     if (i >= N) {
-      for (int k = 0; k < TC_NCMAX; ++k) o[k] = 0.f;
+      for (int k = 0; k < TC_NCMAX; ++k) o[(size_t)k * N_pad] = 0.f;
       continue;
     }
     const double* r = obs + (size_t)i * ncols;
@@ -261,7 +266,7 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
       const double m = exp(eta);
       for (int k = 3; k <= TC_ORDER_MAX; ++k) c[k] = m * c_inv_fact[k];
     }
-    for (int k = 0; k < TC_NCMAX; ++k) o[k] = (float)c[3 + k];
+    for (int k = 0; k < TC_NCMAX; ++k) o[(size_t)k * N_pad] = (float)c[3 + k];
     // bounds
     b_tmax = fmax(b_tmax, t);
     b_a1 += fabs(c[3]) * t * t * t;
@@ -409,7 +414,8 @@ struct TcKernelParams {
   int tiles_per_chunk;
   int n_obs_tiles;
   long long P;            // local mirror pairs
-  const float* coef;      // [N_pad][TC_NCMAX]
+  const float* coef;      // [TC_NCMAX][N_pad]
+  long long N_pad;
   double* part;           // [chunks][P][2]: even and odd part of the remainder sum of a pair
 };
 
@@ -499,7 +505,15 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t sA = sB + (uint32_t)P.nbbuf * b_bytes;                  // stages x ka x (128 x 128 B)
   const uint32_t a_bytes = (uint32_t)P.ka * TC_OBS_TILE * 128u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  double* red = reinterpret_cast<double*>(gen + (size_t)P.nbbuf * b_bytes + (size_t)P.stages * a_bytes);   // [4][96][2]
+  // per-observation series coefficients of the tiles in flight, [slot][k][128 observations]: a tile's slot lives from
+  // its TMA load until the epilogue has consumed its accumulator, i.e. across the observation ring AND the TMEM
+  // buffers, hence stages + TC_NBUF slots (a slot is reused only after empty[stage] of a tile `stages` later,
+  // which the MMA issuer signals after waiting for tempty of a tile TC_NBUF earlier still)
+  const int n_cslots = P.stages + TC_NBUF;
+  const uint32_t c_bytes = (uint32_t)NC * TC_OBS_TILE * 4u;
+  const uint32_t sC = sA + (uint32_t)P.stages * a_bytes;
+  double* red = reinterpret_cast<double*>(gen + (size_t)P.nbbuf * b_bytes + (size_t)P.stages * a_bytes +
+                                          (size_t)n_cslots * c_bytes);   // [4][96][2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(red + 4 * TC_PAIR_TILE * 2);
   const uint32_t bar_full = smem_u32(bars);                 // [TC_MAX_STAGES]
   const uint32_t bar_empty = bar_full + 8u * TC_MAX_STAGES; // [TC_MAX_STAGES]
@@ -509,7 +523,9 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t bar_tempty = bar_tfull + 8u * TC_NBUF;     // [TC_NBUF]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 4 + 2 * TC_NBUF);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps role / address arithmetic
+  // on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) {
       mbar_init(bar_full + 8u * s, 1);
@@ -541,7 +557,7 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
-      int stage = 0, bb = 0;
+      int stage = 0, bb = 0, cslot = 0;
       uint32_t phase = 0, bphase = 0;   // bphase: bit b = parity of pair-operand buffer b
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int chunk = item / P.n_pair_tiles, pair_tile = item % P.n_pair_tiles;
@@ -555,10 +571,15 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (++bb == P.nbbuf) bb = 0;
         for (int t = t0; t < t1; ++t) {
           mbar_wait_relaxed(bar_empty + 8u * stage, phase ^ 1);
-          mbar_expect_tx(bar_full + 8u * stage, a_bytes);
+          mbar_expect_tx(bar_full + 8u * stage, a_bytes + c_bytes);
           for (int a = 0; a < P.ka; ++a)
             tma_load_2d(sA + (uint32_t)stage * a_bytes + (uint32_t)a * TC_OBS_TILE * 128u, &tmA, bar_full + 8u * stage,
                         a * TC_KATOM, t * TC_OBS_TILE);
+#pragma unroll
+          for (int k = 0; k < NC; ++k)
+            bulk_load_1d(sC + (uint32_t)cslot * c_bytes + (uint32_t)k * TC_OBS_TILE * 4u,
+                         P.coef + (size_t)k * P.N_pad + (size_t)t * TC_OBS_TILE, TC_OBS_TILE * 4u, bar_full + 8u * stage);
+          if (++cslot == n_cslots) cslot = 0;
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -606,10 +627,10 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t accE[TC_COLS_PER_WARP / 2], accO[TC_COLS_PER_WARP / 2];   // FP32 sums, packed in pairs of adjacent columns
 #pragma unroll
     for (int j = 0; j < TC_COLS_PER_WARP / 2; ++j) accE[j] = accO[j] = 0ull;
-    int buf = 0;
+    int buf = 0, cslot = 0;
     uint32_t tphase = 0;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * TC_COLS_PER_WARP);
-    const float* coef_row = P.coef + (size_t)(q * 32 + lane) * TC_NCMAX;   // this thread's observation: tile row = TMEM lane
+    const uint32_t coef_addr = sC + (uint32_t)(q * 32 + lane) * 4u;   // this thread's observation: tile row = TMEM lane
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int chunk = item / P.n_pair_tiles, pair_tile = item % P.n_pair_tiles;
       const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
@@ -619,19 +640,17 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // by two so that the two coefficient sets alternate without register copies.
       uint32_t va[8], vb[8];
       float ca[NC], cb[NC];
-      auto load_coef = [&](int t, float (&dst)[NC]) {
-        const float2* cp = reinterpret_cast<const float2*>(coef_row + (size_t)t * (TC_OBS_TILE * TC_NCMAX));
+      // coefficients of the tile whose accumulator was just seen full (their TMA copy completed before its MMA ran)
+      auto load_coef = [&](float (&dst)[NC]) {
+        const uint32_t a = coef_addr + (uint32_t)cslot * c_bytes;
 #pragma unroll
-        for (int k = 0; k < NC / 2; ++k) {
-          const float2 f = __ldg(cp + k);
-          dst[2 * k] = f.x;
-          dst[2 * k + 1] = f.y;
-        }
+        for (int k = 0; k < NC; ++k)
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dst[k]) : "r"(a + (uint32_t)k * TC_OBS_TILE * 4u));
+        if (++cslot == n_cslots) cslot = 0;
       };
       auto tile_step = [&](int t, const float (&cc)[NC], float (&cn)[NC]) {
         const bool more = t + 1 < t1;
         const int nbuf = (buf + 1 == TC_NBUF) ? 0 : buf + 1;
-        if (more) load_coef(t + 1, cn);
         const uint32_t taddr = lane_addr + (uint32_t)buf * TC_TMEM_STRIDE;
         tmem_ld_wait8(va);
         if (MODE != 2) tmem_ld8(vb, taddr + 8u);
@@ -652,17 +671,18 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tphase ^= 1u << nbuf;
           tc_fence_after();
           if (MODE != 2) tmem_ld8(va, lane_addr + (uint32_t)nbuf * TC_TMEM_STRIDE);
+          load_coef(cn);
         }
         tc_accumulate8<NC, MODE>(vb, cc, accE + 12, accO + 12);
         buf = nbuf;
       };
       int t = t0;
       const bool odd = ((t1 - t0) & 1) != 0;
-      if (odd) load_coef(t0, cb); else load_coef(t0, ca);
       mbar_wait(bar_tfull + 8u * buf, (tphase >> buf) & 1u);
       tphase ^= 1u << buf;
       tc_fence_after();
       tmem_ld8(va, lane_addr + (uint32_t)buf * TC_TMEM_STRIDE);
+      if (odd) load_coef(cb); else load_coef(ca);
       if (odd) {       // peel one tile so that the main loop is two straight-line steps
         tile_step(t, cb, ca);
         ++t;
@@ -943,12 +963,13 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   kp.n_pair_tiles = (int)(ps->P_pad / TC_PAIR_TILE);
   kp.n_obs_tiles = (int)(ds->N_pad / TC_OBS_TILE);
   const size_t b_bytes = (size_t)kp.ka * TC_PAIR_TILE * 128, a_bytes = (size_t)kp.ka * TC_OBS_TILE * 128;
-  const size_t budget = 216 * 1024, misc = 1024 + 4 * TC_PAIR_TILE * 2 * 8 + 256;
+  const size_t c_bytes = (size_t)NC * TC_OBS_TILE * 4;      // coefficient slot of one tile
+  const size_t budget = 220 * 1024, misc = 1024 + 4 * TC_PAIR_TILE * 2 * 8 + 256 + TC_NBUF * c_bytes;
   // two pair-operand buffers unless that would push the observation ring below three stages
-  kp.nbbuf = ((budget - misc - 2 * b_bytes) / a_bytes >= 3) ? 2 : 1;
+  kp.nbbuf = ((budget - misc - 2 * b_bytes) / (a_bytes + c_bytes) >= 3) ? 2 : 1;
   const size_t fixed = misc + (size_t)kp.nbbuf * b_bytes;
-  kp.stages = (int)std::max<size_t>(2, std::min<size_t>(TC_MAX_STAGES, (budget - fixed) / a_bytes));
-  const size_t smem = fixed + (size_t)kp.stages * a_bytes;
+  kp.stages = (int)std::max<size_t>(2, std::min<size_t>(TC_MAX_STAGES, (budget - fixed) / (a_bytes + c_bytes)));
+  const size_t smem = fixed + (size_t)kp.stages * (a_bytes + c_bytes);
   // Work items are (observation chunk, node tile) pairs in CHUNK-MAJOR order on the persistent grid: all CTAs sweep
   // the same chunk of observation tiles at about the same time, so a chunk is read from HBM once and then served
   // from the 126 MB L2 to every node tile.  A chunk is therefore sized to ~24 MB of operand rows; beyond that the
@@ -977,6 +998,7 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   }
   kp.P = ps->P;
   kp.coef = ds->d_coef;
+  kp.N_pad = ds->N_pad;
   kp.part = ps->d_part;
   int stc;
   if (NC == 4) stc = launch_tc<4>(ctx, ds->tmA, ps->tmB, kp, smem);
