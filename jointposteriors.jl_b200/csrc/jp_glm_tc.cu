@@ -50,7 +50,12 @@ int jp_glm_num_blocks(const jp_ctx* ctx, long long N);
 #define TC_ORDER_MAX 16          // highest derivative order tabulated (tail bounds need two more than used)
 #define TC_EPI_THREADS (32 * TC_EPI_WARPS)
 #define TC_THREADS (64 + TC_EPI_THREADS)   // warp 0 TMA, warp 1 MMA, warps 2-13 epilogue
-#define TC_MAX_STAGES 4
+#ifndef TC_MAX_STAGES
+#define TC_MAX_STAGES 6          // observation-tile ring depth (shared memory permitting)
+#endif
+#ifndef TC_LDW
+#define TC_LDW 8                 // columns per tcgen05.ld of the epilogue (8 or 16)
+#endif
 #define TC_PREP_BLOCKS 296
 #define TC_NBOUND 14             // per-block bound partials, see tc_obs_prep_kernel
 #define TC_NORD 5                // series lengths NC = 4, 6, 8, 10, 12 (orders 6 .. 14)
@@ -200,6 +205,10 @@ __device__ __forceinline__ void tmem_ld_wait8(uint32_t (&v)[8]) {
                :
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld(uint32_t (&v)[8], uint32_t taddr) { tmem_ld8(v, taddr); }
+__device__ __forceinline__ void tmem_ld(uint32_t (&v)[16], uint32_t taddr) { tmem_ld16(v, taddr); }
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[8]) { tmem_ld_wait8(v); }
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[16]) { tmem_ld_wait16(v); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
 
 // ------------------------------------------------------------------------------------ operand preparation
@@ -452,18 +461,18 @@ __device__ __forceinline__ uint64_t f32x2_mul(uint64_t a, uint64_t b) {
 // order, jp_grid.cu), represented by D = x_i . delta(z); the partner sees -D.  Splitting the remainder series by
 // parity,   R_i(+-D) = E_i(D) +- O_i(D),   E = D^4 (c_4 + c_6 D^2 + ...),   O = D^3 (c_3 + c_5 D^2 + ...),
 // one pass over D yields both nodes: NC + 3 packed operations per column instead of 2 (NC + 2), and half the
-// contraction, TMEM reads and operand traffic.  accE / accO: 8 columns = 4 packed pairs each; c[k] = c_{3+k}.
-template <int NC, int MODE>
-__device__ __forceinline__ void tc_accumulate8(const uint32_t (&v)[8], const float (&c)[NC], uint64_t* accE, uint64_t* accO) {
+// contraction, TMEM reads and operand traffic.  accE / accO: W columns = W / 2 packed pairs each; c[k] = c_{3+k}.
+template <int NC, int MODE, int W>
+__device__ __forceinline__ void tc_accumulate(const uint32_t (&v)[W], const float (&c)[NC], uint64_t* accE, uint64_t* accO) {
   // coefficients stay scalar: ptxas folds the (c, c) pack into FFMA2's broadcast operand form (Rx.F32), which
   // reads one register instead of a pair
   if (MODE == 1) {   // profiling aid: TMEM traffic without the series arithmetic (results are meaningless)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) accE[j] = f32x2_fma(f32x2_pack(v[2 * j], v[2 * j + 1]), f32x2_bcast(c[0]), accE[j]);
+    for (int j = 0; j < W / 2; ++j) accE[j] = f32x2_fma(f32x2_pack(v[2 * j], v[2 * j + 1]), f32x2_bcast(c[0]), accE[j]);
     return;
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < W / 2; ++j) {
     const uint64_t D = f32x2_pack(v[2 * j], v[2 * j + 1]);
     const uint64_t D2 = f32x2_mul(D, D);
     uint64_t pe = f32x2_bcast(c[NC - 1]), po = f32x2_bcast(c[NC - 2]);   // NC even: c_{NC+2} is an even order
@@ -638,7 +647,7 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // boundary too, the next accumulator buffer is normally complete long before -- and the coefficient
       // loads of the next tile are in flight while the current chunk is evaluated.  The tile loop is unrolled
       // by two so that the two coefficient sets alternate without register copies.
-      uint32_t va[8], vb[8];
+      uint32_t va[TC_LDW], vb[TC_LDW];
       float ca[NC], cb[NC];
       // coefficients of the tile whose accumulator was just seen full (their TMA copy completed before its MMA ran)
       auto load_coef = [&](float (&dst)[NC]) {
@@ -652,28 +661,28 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool more = t + 1 < t1;
         const int nbuf = (buf + 1 == TC_NBUF) ? 0 : buf + 1;
         const uint32_t taddr = lane_addr + (uint32_t)buf * TC_TMEM_STRIDE;
-        tmem_ld_wait8(va);
-        if (MODE != 2) tmem_ld8(vb, taddr + 8u);
-        tc_accumulate8<NC, MODE>(va, cc, accE, accO);
-        tmem_ld_wait8(vb);
-        if (MODE != 2) tmem_ld8(va, taddr + 16u);
-        tc_accumulate8<NC, MODE>(vb, cc, accE + 4, accO + 4);
-        tmem_ld_wait8(va);
-        if (MODE != 2) tmem_ld8(vb, taddr + 24u);
-        tc_accumulate8<NC, MODE>(va, cc, accE + 8, accO + 8);
-        tmem_ld_wait8(vb);
-        // every tcgen05.ld of this tile has completed: hand the accumulator buffer back to the MMA issuer
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8u * buf);
-        if (more) {
-          mbar_wait(bar_tfull + 8u * nbuf, (tphase >> nbuf) & 1u);
-          tphase ^= 1u << nbuf;
-          tc_fence_after();
-          if (MODE != 2) tmem_ld8(va, lane_addr + (uint32_t)nbuf * TC_TMEM_STRIDE);
-          load_coef(cn);
+#pragma unroll
+        for (int c = 0; c < TC_COLS_PER_WARP / TC_LDW; ++c) {
+          uint32_t(&cur)[TC_LDW] = (c & 1) ? vb : va;
+          uint32_t(&nxt)[TC_LDW] = (c & 1) ? va : vb;
+          tmem_ld_wait(cur);
+          if (c + 1 < TC_COLS_PER_WARP / TC_LDW) {
+            if (MODE != 2) tmem_ld(nxt, taddr + (uint32_t)(TC_LDW * (c + 1)));
+          } else {
+            // every tcgen05.ld of this tile has completed: hand the accumulator buffer back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8u * buf);
+            if (more) {
+              mbar_wait(bar_tfull + 8u * nbuf, (tphase >> nbuf) & 1u);
+              tphase ^= 1u << nbuf;
+              tc_fence_after();
+              if (MODE != 2) tmem_ld(nxt, lane_addr + (uint32_t)nbuf * TC_TMEM_STRIDE);
+              load_coef(cn);
+            }
+          }
+          tc_accumulate<NC, MODE, TC_LDW>(cur, cc, accE + c * (TC_LDW / 2), accO + c * (TC_LDW / 2));
         }
-        tc_accumulate8<NC, MODE>(vb, cc, accE + 12, accO + 12);
         buf = nbuf;
       };
       int t = t0;
@@ -681,7 +690,7 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(bar_tfull + 8u * buf, (tphase >> buf) & 1u);
       tphase ^= 1u << buf;
       tc_fence_after();
-      tmem_ld8(va, lane_addr + (uint32_t)buf * TC_TMEM_STRIDE);
+      tmem_ld(va, lane_addr + (uint32_t)buf * TC_TMEM_STRIDE);
       if (odd) load_coef(cb); else load_coef(ca);
       if (odd) {       // peel one tile so that the main loop is two straight-line steps
         tile_step(t, cb, ca);
