@@ -41,6 +41,9 @@ int jp_ctx_create(int device, jp_ctx** out) {
     JP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   }
   JP_CUDA(jp_dmalloc(ctx, &ctx->d_scratch, sizeof(double) * JP_SCRATCH_DOUBLES));
+  JP_CUDA(jp_dmalloc(ctx, &ctx->d_counters, sizeof(unsigned int) * JP_COUNTERS));
+  JP_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned int) * JP_COUNTERS, ctx->stream));
+  JP_CUDA(jp_dmalloc(ctx, &ctx->d_bpart, sizeof(double) * JP_BPART_DOUBLES));
   JP_CUDA(cudaMallocHost(&ctx->h_pinned, sizeof(double) * JP_PINNED_DOUBLES));
   JP_CUDA(cudaEventCreate(&ctx->ev_k0));
   JP_CUDA(cudaEventCreate(&ctx->ev_k1));
@@ -61,7 +64,7 @@ int jp_ctx_destroy(jp_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->grids) free_grid(ctx, kv.second);
-  jp_dfree(ctx, ctx->d_scratch);
+  jp_dfree(ctx, ctx->d_scratch); jp_dfree(ctx, ctx->d_counters); jp_dfree(ctx, ctx->d_bpart);
   cudaStreamSynchronize(ctx->stream);
   cudaFreeHost(ctx->h_pinned);
   cudaEventDestroy(ctx->ev_k0);

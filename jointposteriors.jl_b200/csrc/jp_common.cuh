@@ -1,5 +1,6 @@
 // jp_common.cuh -- shared internals of libjpcuda.so (sm_100a only).
 #pragma once
+#include <algorithm>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -74,7 +75,12 @@ struct jp_ctx {
   // scratch for small reductions / scalars (device) and pinned host staging
   double* d_scratch = nullptr;     // JP_SCRATCH_DOUBLES doubles
   double* h_pinned = nullptr;      // JP_PINNED_DOUBLES doubles
+  unsigned int* d_counters = nullptr;   // JP_COUNTERS arrival counters of multi-block reductions (zero between kernels)
+  double* d_bpart = nullptr;       // JP_BPART_DOUBLES per-block partials of those reductions
 };
+#define JP_COUNTERS 1024
+#define JP_BPART_DOUBLES 4096
+#define JP_RED_BLOCKS_MAX 512
 // Stream-ordered device memory from the device's pool (cudaMallocAsync with an unbounded release
 // threshold, set in jp_ctx_create): the buffers of freed posteriors / data sets are recycled by the next
 // allocation without a device synchronisation, which is what keeps repeated fit() calls cheap.
@@ -201,6 +207,23 @@ __device__ __forceinline__ double jp_block_min(double v, double* smem) {
   __syncthreads();
   return smem[32];
 }
+// Multi-block reduction, second stage in the same launch: every block publishes its partial, the block that arrives
+// last (arrival counter, self-resetting) combines the partials in block order -- deterministic -- and writes the result.
+// Call with all threads after the block's partial has been written by thread 0; true in the last block only.
+__device__ __forceinline__ bool jp_last_block(unsigned int* counter, unsigned int nblocks) {
+  __shared__ unsigned int s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(counter, 1u);
+    s_last = (t == nblocks - 1u);
+    if (s_last) *counter = 0u;
+  }
+  __syncthreads();
+  const bool last = s_last != 0u;
+  if (last) __threadfence();
+  return last;
+}
+static inline int jp_red_blocks(long long M) { return (int)std::max(1LL, std::min((long long)JP_RED_BLOCKS_MAX, (M + 1023) / 1024)); }
 // order-preserving map double -> uint64 (ascending), -0.0 < +0.0; NaNs sort last/first by sign
 __device__ __forceinline__ unsigned long long jp_sortable(double x) {
   unsigned long long u = (unsigned long long)__double_as_longlong(x);

@@ -160,31 +160,45 @@ __global__ void jp_fit_finish_kernel(long long M, long long m0, int splits, cons
   a[m] = ld + hzz[m0 + m];
 }
 
-// single-block deterministic reductions over the (L2-resident) node arrays
-__global__ void __launch_bounds__(1024) jp_reduce_max_kernel(const double* __restrict__ a, long long M,
-                                                             double* __restrict__ out) {
+// Stage 4 reductions over the (L2-resident) node arrays: multi-block, coalesced, second stage by the last block to
+// arrive (jp_last_block) in block order -> bitwise reproducible.
+__global__ void __launch_bounds__(256) jp_reduce_max_kernel(const double* __restrict__ a, long long M, double* __restrict__ bpart,
+                                                            unsigned int* __restrict__ counter, double* __restrict__ out) {
   __shared__ double sm[33];
+  const long long per = (M + gridDim.x - 1) / gridDim.x, b0 = (long long)blockIdx.x * per, b1 = min(M, b0 + per);
   double v = -INFINITY;
-  for (long long i = threadIdx.x; i < M; i += 1024) v = fmax(v, a[i]);
+  for (long long i = b0 + threadIdx.x; i < b1; i += 256) v = fmax(v, a[i]);
+  v = jp_block_max(v, sm);
+  if (threadIdx.x == 0) bpart[blockIdx.x] = v;
+  if (!jp_last_block(counter, gridDim.x)) return;
+  v = -INFINITY;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += 256) v = fmax(v, __ldcg(bpart + b));
   v = jp_block_max(v, sm);
   if (threadIdx.x == 0) out[0] = v;
 }
-__global__ void jp_expw_kernel(long long M, long long m0, const double* __restrict__ a, const double* __restrict__ w,
-                               const double* __restrict__ gmax, double* __restrict__ e) {
-  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m < M) e[m] = w[m0 + m] * exp(a[m] - gmax[0]);
-}
-__global__ void __launch_bounds__(1024) jp_reduce_sum_kernel(const double* __restrict__ e, long long M,
-                                                             double* __restrict__ out) {
+// e = w exp(a - max) and its sum: thread t of a block adds its elements in ascending order, the block combines by the
+// fixed tree of jp_block_sum, the last block adds the block sums in block order
+__global__ void __launch_bounds__(256) jp_expw_sum_kernel(long long M, long long m0, const double* __restrict__ a,
+                                                          const double* __restrict__ w, const double* __restrict__ gmax,
+                                                          double* __restrict__ e, double* __restrict__ bpart,
+                                                          unsigned int* __restrict__ counter, double* __restrict__ out) {
   __shared__ double sm[33];
-  // fixed assignment: thread t owns the contiguous chunk t, summed in order; chunks combined by the
-  // fixed shuffle tree -> bitwise reproducible
-  long long chunk = (M + 1023) / 1024;
-  long long b = threadIdx.x * chunk, en = min(M, b + chunk);
+  const long long per = (M + gridDim.x - 1) / gridDim.x, b0 = (long long)blockIdx.x * per, b1 = min(M, b0 + per);
+  const double mx = gmax[0];
   double s = 0;
-  for (long long i = b; i < en; ++i) s += e[i];
+  for (long long i = b0 + threadIdx.x; i < b1; i += 256) {
+    const double v = w[m0 + i] * exp(a[i] - mx);
+    e[i] = v;
+    s += v;
+  }
   s = jp_block_sum(s, sm);
-  if (threadIdx.x == 0) out[0] = s;
+  if (threadIdx.x == 0) bpart[blockIdx.x] = s;
+  if (!jp_last_block(counter, gridDim.x)) return;
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(bpart + b);
+    out[0] = t;
+  }
 }
 __global__ void jp_scale_kernel(long long M, double* __restrict__ e, const double* __restrict__ gsum) {
   long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -400,18 +414,17 @@ int jp_fit_local(jp_posterior* post, const jp_fit_args* args, double* d_local_ma
     else JP_TRY(st);
   }
   if (path == JP_PATH_FP64) JP_TRY(jp_fit_fp64_launch(post, args));
-  jp_reduce_max_kernel<<<1, 1024, 0, post->ctx->stream>>>(post->d_a, post->M, d_local_max);
+  jp_reduce_max_kernel<<<jp_red_blocks(post->M), 256, 0, post->ctx->stream>>>(post->d_a, post->M, post->ctx->d_bpart,
+                                                                              post->ctx->d_counters, d_local_max);
   JP_CHECK_LAUNCH(post->ctx);
   return JP_OK;
 }
 
 int jp_fit_local_sum(jp_posterior* post, const double* d_global_max, double* d_local_sum) {
   JP_REQUIRE(post && d_global_max && d_local_sum, "jp_fit_local_sum: null argument");
-  unsigned gb = (unsigned)((post->M + 255) / 256);
-  jp_expw_kernel<<<gb, 256, 0, post->ctx->stream>>>(post->M, post->m0, post->d_a, post->grid->d_w, d_global_max,
-                                                     post->d_density);
-  JP_CHECK_LAUNCH(post->ctx);
-  jp_reduce_sum_kernel<<<1, 1024, 0, post->ctx->stream>>>(post->d_density, post->M, d_local_sum);
+  jp_expw_sum_kernel<<<jp_red_blocks(post->M), 256, 0, post->ctx->stream>>>(post->M, post->m0, post->d_a, post->grid->d_w,
+                                                                            d_global_max, post->d_density, post->ctx->d_bpart,
+                                                                            post->ctx->d_counters, d_local_sum);
   JP_CHECK_LAUNCH(post->ctx);
   return JP_OK;
 }

@@ -90,12 +90,15 @@ jp_glm_partials_kernel(int family, int d, long long N, const double* __restrict_
   if (threadIdx.x == 0) o[nE] = ll;
 }
 
-__global__ void jp_glm_combine_kernel(int nblocks, int nE1, const double* __restrict__ part, double* __restrict__ out) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per entry: lane l adds blocks l, l + 32, ... in ascending order, then the fixed shuffle tree (deterministic)
+__global__ void __launch_bounds__(256) jp_glm_combine_kernel(int nblocks, int nE1, const double* __restrict__ part,
+                                                             double* __restrict__ out) {
+  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (e >= nE1) return;
   double s = 0;
-  for (int b = 0; b < nblocks; ++b) s += part[(size_t)b * nE1 + e];
-  out[e] = s;
+  for (int b = lane; b < nblocks; b += 32) s += part[(size_t)b * nE1 + e];
+  s = jp_warp_sum(s);
+  if (lane == 0) out[e] = s;
 }
 
 // device-side entry used by both the C ABI and the TC path: packed sums into d_out[nE + 1]
@@ -109,7 +112,7 @@ int jp_glm_sums_device(jp_ctx* ctx, const jp_data* data, int d, const double* d_
   jp_glm_partials_kernel<<<nblocks, JP_GLM_THREADS, smem, ctx->stream>>>(data->family, d, data->N, data->d_obs, d_beta,
                                                                            nE, d_work);
   JP_CHECK_LAUNCH(ctx);
-  jp_glm_combine_kernel<<<(nE + 1 + 127) / 128, 128, 0, ctx->stream>>>(nblocks, nE + 1, d_work, d_out);
+  jp_glm_combine_kernel<<<(nE + 1 + 7) / 8, 256, 0, ctx->stream>>>(nblocks, nE + 1, d_work, d_out);
   JP_CHECK_LAUNCH(ctx);
   return JP_OK;
 }

@@ -42,16 +42,20 @@ __device__ __forceinline__ double jp_knot_value(double vmin, double vmax, int i)
   return sh + (sl + pl);
 }
 
-// one block per marginal: (sum w v, sum w v^2, min v, max v); contiguous chunk per thread, fixed tree
-__global__ void __launch_bounds__(1024)
+// (sum w v, sum w v^2, min v, max v) of marginal blockIdx.y: a block owns a contiguous slice (coalesced reads, thread t
+// adds its elements in ascending order, fixed tree across threads), the last block to arrive adds the block partials in
+// block order -> bitwise reproducible
+#define JP_MOM_THREADS 256
+__global__ void __launch_bounds__(JP_MOM_THREADS)
 jp_moments_kernel(const double* const* __restrict__ vptr, const double* __restrict__ w, long long M,
+                  double* __restrict__ bpart /* [K][gridDim.x][4] */, unsigned int* __restrict__ counters /* [K] */,
                   double* __restrict__ out, int out_stride) {
   __shared__ double sm[33];
-  const double* v = vptr[blockIdx.x];
-  long long chunk = (M + 1023) / 1024;
-  long long b = threadIdx.x * chunk, e = min(M, b + chunk);
+  const int k = blockIdx.y;
+  const double* v = vptr[k];
+  const long long per = (M + gridDim.x - 1) / gridDim.x, b0 = (long long)blockIdx.x * per, b1 = min(M, b0 + per);
   double s1 = 0, s2 = 0, mn = INFINITY, mx = -INFINITY;
-  for (long long i = b; i < e; ++i) {
+  for (long long i = b0 + threadIdx.x; i < b1; i += JP_MOM_THREADS) {
     double x = v[i], wi = w[i];
     s1 += wi * x;
     s2 += wi * (x * x);
@@ -62,8 +66,19 @@ jp_moments_kernel(const double* const* __restrict__ vptr, const double* __restri
   s2 = jp_block_sum(s2, sm);
   mn = jp_block_min(mn, sm);
   mx = jp_block_max(mx, sm);
+  double* bp = bpart + (size_t)k * gridDim.x * 4;
   if (threadIdx.x == 0) {
-    double* o = out + (size_t)blockIdx.x * out_stride;
+    double* o = bp + (size_t)blockIdx.x * 4;
+    o[0] = s1; o[1] = s2; o[2] = mn; o[3] = mx;
+  }
+  if (!jp_last_block(counters + k, gridDim.x)) return;
+  if (threadIdx.x == 0) {
+    s1 = 0; s2 = 0; mn = INFINITY; mx = -INFINITY;
+    for (int b = 0; b < (int)gridDim.x; ++b) {
+      s1 += __ldcg(bp + 4 * b); s2 += __ldcg(bp + 4 * b + 1);
+      mn = fmin(mn, __ldcg(bp + 4 * b + 2)); mx = fmax(mx, __ldcg(bp + 4 * b + 3));
+    }
+    double* o = out + (size_t)k * out_stride;
     o[0] = s1; o[1] = s2; o[2] = mn; o[3] = mx;
   }
 }
@@ -216,17 +231,20 @@ jp_bins_kernel(const double* const* __restrict__ vptr, const double* __restrict_
       while (g > 0 && !(s_x[g] < vj)) --g;
       bin = g;
     }
-    // the lowest lane of every group of equal bins folds its group in lane order
+    // the lowest lane of every group of equal bins folds its group in lane order; the loop runs as many times as the
+    // largest group has members (all 32 only when the whole step falls into one bin)
     const unsigned peers = __match_any_sync(0xffffffffu, bin);
     const bool leader = live && (peers & ((1u << lane) - 1)) == 0;
     double sW = 0.0, mx = -INFINITY, mn = INFINITY, mi = INFINITY, mw = 0.0;
-    for (int s2 = 0; s2 < 32; ++s2) {
-      const int bs = __shfl_sync(0xffffffffu, bin, s2);
+    unsigned rest = leader ? peers : 0u;
+    while (__any_sync(0xffffffffu, rest != 0u)) {
+      const int s2 = rest ? (__ffs(rest) - 1) : lane;
       const double vs = __shfl_sync(0xffffffffu, vj, s2), ws = __shfl_sync(0xffffffffu, wj, s2);
-      if (leader && bs == bin) {
+      if (rest) {
         sW += ws;
         mx = fmax(mx, vs);
         if (vs < mn) { mn = vs; mi = (double)(m0 + base + s2); mw = ws; }
+        rest &= rest - 1u;
       }
     }
     if (leader) {
@@ -320,6 +338,18 @@ jp_bins_combine_kernel(const double* __restrict__ bins, int nblocks, const doubl
 // ------------------------------------------------------------------------------------ host side
 static int bins_blocks_for(long long M) { return (int)std::max(1LL, std::min(64LL, (M + 4095) / 4096)); }
 
+// moments of the K value columns in post->d_vptr into d_out[K][4]; partials live in the ctx scratch behind K x 4
+static int launch_moments(jp_posterior* post, int K, double* d_out) {
+  jp_ctx* ctx = post->ctx;
+  const int nb = bins_blocks_for(post->M);
+  JP_REQUIRE(K <= JP_COUNTERS && (size_t)K * 4 * (1 + nb) <= JP_SCRATCH_DOUBLES, "marginal: K=%d too large for one call", K);
+  dim3 g(nb, K);
+  jp_moments_kernel<<<g, JP_MOM_THREADS, 0, ctx->stream>>>(post->d_vptr, post->d_density, post->M, ctx->d_scratch + (size_t)K * 4,
+                                                           ctx->d_counters, d_out, 4);
+  JP_CHECK_LAUNCH(ctx);
+  return JP_OK;
+}
+
 // light buffers of the default (sort-free) path
 static int ensure_marginal_buffers(jp_posterior* post, int K) {
   if (K <= post->K_cap) return JP_OK;
@@ -395,7 +425,7 @@ static int run_marginals(jp_posterior* post, int K, double* h_mu, double* h_sigm
   JP_REQUIRE((size_t)K * 4 <= JP_SCRATCH_DOUBLES, "marginal: K=%d too large for one call", K);
   cudaStream_t st = ctx->stream;
   double* d_mom = ctx->d_scratch;   // K x 4: sum w v, sum w v^2, min, max
-  jp_moments_kernel<<<K, 1024, 0, st>>>(post->d_vptr, post->d_density, M, d_mom, 4);
+  JP_TRY(launch_moments(post, K, d_mom));
   JP_CHECK_LAUNCH(ctx);
   dim3 gb(post->bins_blocks, K);
   jp_bins_kernel<<<gb, JP_BIN_THREADS, 0, st>>>(post->d_vptr, post->d_density, M, post->m0, d_mom, 4, 2, post->d_bins);
@@ -476,7 +506,7 @@ int jp_marginal_knots_from_sort(jp_posterior* post, int K, double* h_value_nodes
   if (!post->sorted_valid) JP_TRY(run_sort(post));
   cudaStream_t st = ctx->stream;
   double* d_mom = ctx->d_scratch;
-  jp_moments_kernel<<<K, 1024, 0, st>>>(post->d_vptr, post->d_density, post->M, d_mom, 4);
+  JP_TRY(launch_moments(post, K, d_mom));
   JP_CHECK_LAUNCH(ctx);
   jp_knots_kernel<<<K, 128, 0, st>>>(post->d_sv, post->d_cw, post->M, d_mom, 4, post->d_mout);
   JP_CHECK_LAUNCH(ctx);
@@ -494,7 +524,7 @@ int jp_marginal_local_moments(jp_posterior* post, int K, const int* h_coords, co
   JP_REQUIRE(post && d_out, "jp_marginal_local_moments: null argument");
   JP_TRY(ensure_marginal_buffers(post, K));
   JP_TRY(set_value_pointers(post, K, h_coords, d_values));
-  jp_moments_kernel<<<K, 1024, 0, post->ctx->stream>>>(post->d_vptr, post->d_density, post->M, d_out, 4);
+  JP_TRY(launch_moments(post, K, d_out));
   JP_CHECK_LAUNCH(post->ctx);
   post->K_last = K;
   return JP_OK;
