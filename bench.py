@@ -370,7 +370,7 @@ def run_product(args):
             D.fit_sharded(le)
             mu, sg, vn, wn = D.marginals_sharded(le, coords)
             dens = pe.density
-            out = (float(mu[0].cpu()), float(sg[0].cpu()), vn.cpu(), wn.cpu(), float(dens[0]))
+            out = (float(mu[0]), float(sg[0]), vn, wn, float(dens[0]))
         pe.free()
         dde.free()
         return out

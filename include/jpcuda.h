@@ -182,6 +182,16 @@ int jp_fit_local(jp_posterior* post, const jp_fit_args* args, double* d_local_ma
 int jp_fit_local_sum(jp_posterior* post, const double* d_global_max, double* d_local_sum);
 int jp_fit_normalise(jp_posterior* post, const double* d_global_sum);
 
+/* The same normalisation with ONE collective per fit (what the sharded path uses):
+ *   jp_fit_local_stats(post, args, d_stats)      stages 2-3 on the shard; d_stats[0] = m_r = max_m a_m,
+ *                                                e_m = w_m exp(a_m - m_r), d_stats[1] = s_r = sum_m e_m
+ *   -- all_gather of the (m_r, s_r) pairs into d_gathered[world][2] --
+ *   jp_fit_normalise_gathered(post, d_gathered, world, rank)
+ *                                                M = max_r m_r, S = sum_r s_r exp(m_r - M) (rank order, identical on
+ *                                                every rank), density_m = e_m exp(m_rank - M) / S                      */
+int jp_fit_local_stats(jp_posterior* post, const jp_fit_args* args, double* d_stats);
+int jp_fit_normalise_gathered(jp_posterior* post, const double* d_gathered, int world, int rank);
+
 /* results to the host (blocking).  h_theta: d x M_local row-major (coordinate k of node m at
  * [k*M_local + m]); h_logdens: log-density + neg_min per node; h_density: normalised weights. */
 int jp_get_theta(jp_posterior* post, double* h_theta);
@@ -233,6 +243,19 @@ int jp_marginal_knots_from_sort(jp_posterior* post, int K, double* h_value_nodes
 int jp_marginal_local_moments(jp_posterior* post, int K, const int* h_coords, const double* d_values, double* d_out);
 int jp_marginal_local_knots(jp_posterior* post, int K, const int* h_coords, const double* d_values,
                             const double* d_minmax, double* d_out);
+/* The same two phases driven by the gathered buffers themselves, so that the host does no arithmetic between the
+ * collectives (two all_gathers and four launches per batch of K marginals):
+ *   jp_marginal_local_knots_gathered: the global (min, max) are taken from the all_gathered moments
+ *     d_gathered_moments[world][K][4]
+ *   jp_marginal_combine_gathered:     combines d_gathered_moments and the all_gathered candidates
+ *     d_gathered_cands[world][K][98][6] over the ranks (fixed rank order: every rank gets identical bits) into
+ *     mu, sigma and the 100-knot Grid of each marginal, exactly like jp_marginal_coords (reference
+ *     src/marginal_posterior.jl:118-122, src/interp.jl:448-457); results to the host (blocking). */
+int jp_marginal_local_knots_gathered(jp_posterior* post, int K, const int* h_coords, const double* d_values,
+                                     const double* d_gathered_moments, int world, double* d_out);
+int jp_marginal_combine_gathered(jp_posterior* post, int K, int world, const double* d_gathered_moments,
+                                 const double* d_gathered_cands, double* h_mu, double* h_sigma, double* h_value_nodes,
+                                 double* h_weight_nodes);
 
 /* quantile(::Grid, p) and cdf(::Grid, x): reference src/interp.jl:458-481 (host, no GPU).
  * Field order as in the reference: Grid(weights, values). */

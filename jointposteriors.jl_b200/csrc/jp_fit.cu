@@ -205,6 +205,17 @@ __global__ void jp_scale_kernel(long long M, double* __restrict__ e, const doubl
   if (m < M) e[m] = e[m] / gsum[0];
 }
 
+// density_m = e_m exp(m_rank - M) / S with M = max_r m_r and S = sum_r s_r exp(m_r - M) from the gathered (m_r, s_r)
+__global__ void jp_scale_gathered_kernel(long long M, double* __restrict__ e, const double* __restrict__ g, int world, int rank) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  double mx = -INFINITY;
+  for (int r = 0; r < world; ++r) mx = fmax(mx, g[2 * r]);
+  double S = 0;
+  for (int r = 0; r < world; ++r) S += (g[2 * r + 1] == 0.0) ? 0.0 : g[2 * r + 1] * exp(g[2 * r] - mx);   // empty shards: (-inf, 0)
+  e[m] = e[m] * exp(g[2 * rank] - mx) / S;
+}
+
 // ------------------------------------------------------------------------------------ registry
 static JpFamilyEntry g_families[16];
 static int g_nfamilies = 0;
@@ -433,6 +444,21 @@ int jp_fit_normalise(jp_posterior* post, const double* d_global_sum) {
   JP_REQUIRE(post && d_global_sum, "jp_fit_normalise: null argument");
   unsigned gb = (unsigned)((post->M + 255) / 256);
   jp_scale_kernel<<<gb, 256, 0, post->ctx->stream>>>(post->M, post->d_density, d_global_sum);
+  JP_CHECK_LAUNCH(post->ctx);
+  return JP_OK;
+}
+
+int jp_fit_local_stats(jp_posterior* post, const jp_fit_args* args, double* d_stats) {
+  JP_REQUIRE(d_stats, "jp_fit_local_stats: null output");
+  JP_TRY(jp_fit_local(post, args, d_stats));
+  return jp_fit_local_sum(post, d_stats, d_stats + 1);
+}
+
+int jp_fit_normalise_gathered(jp_posterior* post, const double* d_gathered, int world, int rank) {
+  JP_REQUIRE(post && d_gathered && world >= 1 && rank >= 0 && rank < world, "jp_fit_normalise_gathered: bad argument");
+  if (post->M == 0) return JP_OK;
+  unsigned gb = (unsigned)((post->M + 255) / 256);
+  jp_scale_gathered_kernel<<<gb, 256, 0, post->ctx->stream>>>(post->M, post->d_density, d_gathered, world, rank);
   JP_CHECK_LAUNCH(post->ctx);
   return JP_OK;
 }

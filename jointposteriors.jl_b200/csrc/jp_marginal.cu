@@ -335,6 +335,62 @@ jp_bins_combine_kernel(const double* __restrict__ bins, int nblocks, const doubl
   }
 }
 
+// ---- cross-rank combine on the device (node-sharded posterior): gathered moments [world][K][4], candidates
+// [world][K][98][6]; every rank runs the same kernel on the same gathered bits in rank order
+__global__ void jp_minmax_gathered_kernel(const double* __restrict__ gm, int world, int K, double* __restrict__ minmax) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  double mn = INFINITY, mx = -INFINITY;
+  for (int r = 0; r < world; ++r) {
+    mn = fmin(mn, gm[((size_t)r * K + k) * 4 + 2]);
+    mx = fmax(mx, gm[((size_t)r * K + k) * 4 + 3]);
+  }
+  minmax[2 * k] = mn;
+  minmax[2 * k + 1] = mx;
+}
+
+__global__ void __launch_bounds__(128)
+jp_combine_gathered_kernel(const double* __restrict__ gm, const double* __restrict__ gc, int world, int K,
+                           double* __restrict__ mout) {
+  const int k = blockIdx.x, t = threadIdx.x;
+  double* o = mout + (size_t)k * JP_MOUT_STRIDE;
+  double vmin = INFINITY, vmax = -INFINITY;
+  for (int r = 0; r < world; ++r) {
+    vmin = fmin(vmin, gm[((size_t)r * K + k) * 4 + 2]);
+    vmax = fmax(vmax, gm[((size_t)r * K + k) * 4 + 3]);
+  }
+  if (t == 0) {
+    double s1 = 0, s2 = 0;
+    for (int r = 0; r < world; ++r) {
+      s1 += gm[((size_t)r * K + k) * 4 + 0];
+      s2 += gm[((size_t)r * K + k) * 4 + 1];
+    }
+    o[0] = s1;
+    o[1] = sqrt(s2 - s1 * s1);      // no clamp, as in the reference
+    o[2 + 2 * JP_GRID_KNOTS] = vmin;
+    o[3 + 2 * JP_GRID_KNOTS] = vmax;
+    o[2] = vmin;
+    o[2 + JP_GRID_KNOTS - 1] = vmax;
+    o[2 + JP_GRID_KNOTS] = 0.0;                                  // interp.jl:451
+    o[2 + 2 * JP_GRID_KNOTS - 1] = 1.0;                          // interp.jl:452
+  }
+  if (t >= 1 && t <= JP_GRID_KNOTS - 2) {
+    // left knot: the LAST element <= x over all ranks, cumulative weight = total mass <= x; right knot: the first
+    // member of the next tie group = lowest global index among the smallest values > x (interp.jl:28-31)
+    double tot = 0, pred = -INFINITY, succ = INFINITY, sidx = INFINITY, sw = 0, x = 0;
+    for (int r = 0; r < world; ++r) {
+      const double* c = gc + (((size_t)r * K + k) * (JP_GRID_KNOTS - 2) + (t - 1)) * 6;
+      tot += c[0];
+      pred = fmax(pred, c[1]);
+      if (c[2] < succ || (c[2] == succ && c[3] < sidx)) { succ = c[2]; sidx = c[3]; sw = c[4]; }
+      if (r == 0) x = c[5];
+    }
+    const double fx = (x - pred) / (succ - pred);
+    o[2 + t] = x;
+    o[2 + JP_GRID_KNOTS + t] = tot * (1.0 - fx) + (tot + sw) * fx;
+  }
+}
+
 // ------------------------------------------------------------------------------------ host side
 static int bins_blocks_for(long long M) { return (int)std::max(1LL, std::min(64LL, (M + 4095) / 4096)); }
 
@@ -534,7 +590,8 @@ int jp_marginal_local_knots(jp_posterior* post, int K, const int* h_coords, cons
                             const double* d_minmax, double* d_out) {
   JP_REQUIRE(post && d_minmax && d_out, "jp_marginal_local_knots: null argument");
   JP_TRY(ensure_marginal_buffers(post, K));
-  JP_TRY(set_value_pointers(post, K, h_coords, d_values));
+  if (h_coords || d_values) JP_TRY(set_value_pointers(post, K, h_coords, d_values));
+  else JP_REQUIRE(K == post->K_last, "jp_marginal_local_knots: no value columns given and the last call had %d, not %d", post->K_last, K);
   dim3 gb(post->bins_blocks, K);
   jp_bins_kernel<<<gb, JP_BIN_THREADS, 0, post->ctx->stream>>>(post->d_vptr, post->d_density, post->M, post->m0, d_minmax, 2,
                                                                 0, post->d_bins);
@@ -543,6 +600,37 @@ int jp_marginal_local_knots(jp_posterior* post, int K, const int* h_coords, cons
                                                                    d_out);
   JP_CHECK_LAUNCH(post->ctx);
   post->K_last = K;
+  return JP_OK;
+}
+
+int jp_marginal_local_knots_gathered(jp_posterior* post, int K, const int* h_coords, const double* d_values,
+                                     const double* d_gathered_moments, int world, double* d_out) {
+  JP_REQUIRE(post && d_gathered_moments && d_out && world >= 1, "jp_marginal_local_knots_gathered: bad argument");
+  JP_REQUIRE((size_t)K * 2 <= JP_BPART_DOUBLES, "marginal: K=%d too large for one call", K);
+  double* d_minmax = post->ctx->d_bpart;    // K x 2 (no reduction of this ctx is in flight: one stream)
+  jp_minmax_gathered_kernel<<<(K + 127) / 128, 128, 0, post->ctx->stream>>>(d_gathered_moments, world, K, d_minmax);
+  JP_CHECK_LAUNCH(post->ctx);
+  return jp_marginal_local_knots(post, K, h_coords, d_values, d_minmax, d_out);
+}
+
+int jp_marginal_combine_gathered(jp_posterior* post, int K, int world, const double* d_gathered_moments,
+                                 const double* d_gathered_cands, double* h_mu, double* h_sigma, double* h_vn, double* h_wn) {
+  JP_REQUIRE(post && d_gathered_moments && d_gathered_cands && world >= 1, "jp_marginal_combine_gathered: bad argument");
+  jp_ctx* ctx = post->ctx;
+  JP_REQUIRE((size_t)K * JP_MOUT_STRIDE <= JP_PINNED_DOUBLES, "marginal: K=%d too large for one call", K);
+  JP_TRY(ensure_marginal_buffers(post, K));
+  cudaStream_t st = ctx->stream;
+  jp_combine_gathered_kernel<<<K, 128, 0, st>>>(d_gathered_moments, d_gathered_cands, world, K, post->d_mout);
+  JP_CHECK_LAUNCH(ctx);
+  JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, post->d_mout, (size_t)K * JP_MOUT_STRIDE * 8, cudaMemcpyDeviceToHost, st));
+  JP_CUDA(cudaStreamSynchronize(st));
+  for (int k = 0; k < K; ++k) {
+    const double* o = ctx->h_pinned + (size_t)k * JP_MOUT_STRIDE;
+    if (h_mu) h_mu[k] = o[0];
+    if (h_sigma) h_sigma[k] = o[1];
+    if (h_vn) std::copy(o + 2, o + 2 + JP_GRID_KNOTS, h_vn + (size_t)k * JP_GRID_KNOTS);
+    if (h_wn) std::copy(o + 2 + JP_GRID_KNOTS, o + 2 + 2 * JP_GRID_KNOTS, h_wn + (size_t)k * JP_GRID_KNOTS);
+  }
   return JP_OK;
 }
 

@@ -6,13 +6,15 @@ src/joint_posterior.jl:180,186) carries no cross-node state until the normalisat
 and -- for the 100-knot Grid -- per-knot (mass below, predecessor, successor).  So each rank owns a
 contiguous block of merged grid nodes and the ranks exchange only:
 
-    fit        all_gather(local max a)  -> global max ;  all_gather(local sum)  -> global sum
+    fit        all_gather(local max m_r, local sum s_r relative to m_r)             one collective
     marginals  all_gather(K x 4 moments/extrema)  ;  all_gather(K x 98 x 6 knot candidates)
 
-Every combine sums in rank order, so all ranks hold bit-identical results.  The combine functions
-work on torch tensors of any device: on CUDA the collectives are NCCL over NVLink, on CPU (tests)
-gloo.  The per-rank "local phase" is an object with three methods; `CudaLocal` calls the C ABI,
-tests substitute a numpy stand-in.
+Between the collectives the host does no arithmetic: the gathered buffers go straight back into the
+library (jp_fit_normalise_gathered, jp_marginal_local_knots_gathered, jp_marginal_combine_gathered),
+which combines them in rank order, so all ranks hold bit-identical results.  On CUDA the collectives
+are NCCL over NVLink, on CPU (tests) gloo.  The per-rank "local phase" is an object with five methods;
+`CudaLocal` calls the C ABI, tests substitute a numpy stand-in built on the `reference_*` functions
+below (the same combine written with torch ops, also used to cross-check the CUDA combine).
 """
 import ctypes as C
 
@@ -48,7 +50,7 @@ def _all_gather(t, group):
     return out
 
 
-def knot_values(gathered, vmin, vmax):
+def reference_knot_values(gathered, vmin, vmax):
     """The 100 value knots [K, 100]: end knots are the global extrema, interior knots are the values the
     device computed (slot 5 of every rank's candidates; all ranks derive them from the same (min, max))."""
     import torch
@@ -60,7 +62,7 @@ def knot_values(gathered, vmin, vmax):
     return x
 
 
-def combine_knots(gathered, vmin, vmax):
+def reference_combine_knots(gathered, vmin, vmax):
     """gathered: [world, K, 98, 6] per-rank (S, pred, succ, succ_idx, succ_w, -) -> weight_nodes [K, 100].
 
     Reproduces itp[x] of the reference (interp.jl:28-31,453-455): left knot = LAST element <= x with
@@ -84,6 +86,31 @@ def combine_knots(gathered, vmin, vmax):
     return wn
 
 
+def reference_fit_scale(g, rank):
+    """Scale factor of rank `rank` from the gathered (m_r, s_r) pairs [world, 2]: density = e exp(m_rank - M) / S with
+    M = max_r m_r, S = sum_r s_r exp(m_r - M) in rank order (what jp_scale_gathered_kernel computes)."""
+    import torch
+    M = g[:, 0].amax()
+    S = torch.zeros((), dtype=torch.float64, device=g.device)
+    for r in range(g.shape[0]):
+        S = S + (g[r, 1] * torch.exp(g[r, 0] - M) if float(g[r, 1]) != 0.0 else 0.0)
+    return torch.exp(g[rank, 0] - M) / S
+
+
+def reference_combine(gm, gc):
+    """(mu, sigma, value_nodes, weight_nodes) from the gathered moments [world, K, 4] and candidates [world, K, 98, 6]
+    with torch ops (what jp_combine_gathered_kernel computes)."""
+    import torch
+    s = gm[:, :, :2].sum(dim=0)
+    vmin = gm[:, :, 2].amin(dim=0)
+    vmax = gm[:, :, 3].amax(dim=0)
+    wn = reference_combine_knots(gc, vmin, vmax)
+    vn = reference_knot_values(gc, vmin, vmax)
+    mu = s[:, 0]
+    sigma = torch.sqrt(s[:, 1] - mu * mu)
+    return mu, sigma, vn, wn
+
+
 class CudaLocal:
     """Local phases of one rank through the C ABI, on torch's current CUDA stream."""
 
@@ -97,6 +124,43 @@ class CudaLocal:
     def _buf(self, *shape):
         return self.torch.empty(shape, dtype=self.torch.float64, device=self.dev)
 
+    # ---- one-collective protocol (what fit_sharded / marginals_sharded drive)
+    def fit_local_stats(self):
+        out = self._buf(2)
+        check(lib().jp_fit_local_stats(self.jp.handle, C.byref(self.jp._args), C.c_void_p(out.data_ptr())))
+        return out
+
+    def fit_normalise_gathered(self, g, rank):
+        g = g.contiguous()
+        check(lib().jp_fit_normalise_gathered(self.jp.handle, C.c_void_p(g.data_ptr()), C.c_int(g.shape[0]), C.c_int(rank)))
+
+    def moments(self, coords):
+        cs = np.ascontiguousarray(coords, dtype=np.int32)
+        out = self._buf(len(cs), 4)
+        check(lib().jp_marginal_local_moments(self.jp.handle, C.c_int(len(cs)), cs.ctypes.data_as(C.c_void_p), None,
+                                              C.c_void_p(out.data_ptr())))
+        return out
+
+    def knots_gathered(self, coords, gm):
+        """Knot candidates of the value columns of the preceding `moments` call, global extrema from the gathered moments."""
+        gm = gm.contiguous()
+        K = len(coords)
+        out = self._buf(K, NK, 6)
+        check(lib().jp_marginal_local_knots_gathered(self.jp.handle, C.c_int(K), None, None, C.c_void_p(gm.data_ptr()),
+                                                     C.c_int(gm.shape[0]), C.c_void_p(out.data_ptr())))
+        return out
+
+    def combine_gathered(self, gm, gc):
+        gm, gc = gm.contiguous(), gc.contiguous()
+        world, K = gm.shape[0], gm.shape[1]
+        mu, sg = np.zeros(K), np.zeros(K)
+        vn, wn = np.zeros((K, GRID_KNOTS)), np.zeros((K, GRID_KNOTS))
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(lib().jp_marginal_combine_gathered(self.jp.handle, C.c_int(K), C.c_int(world), C.c_void_p(gm.data_ptr()),
+                                                 C.c_void_p(gc.data_ptr()), p(mu), p(sg), p(vn), p(wn)))
+        return mu, sg, vn, wn
+
+    # ---- two-collective fit / explicit (min, max) knots: the phases of include/jpcuda.h one by one
     def fit_local_max(self):
         out = self._buf(1)
         check(lib().jp_fit_local(self.jp.handle, C.byref(self.jp._args), C.c_void_p(out.data_ptr())))
@@ -110,13 +174,6 @@ class CudaLocal:
     def fit_normalise(self, gsum):
         check(lib().jp_fit_normalise(self.jp.handle, C.c_void_p(gsum.data_ptr())))
 
-    def moments(self, coords):
-        cs = np.ascontiguousarray(coords, dtype=np.int32)
-        out = self._buf(len(cs), 4)
-        check(lib().jp_marginal_local_moments(self.jp.handle, C.c_int(len(cs)), cs.ctypes.data_as(C.c_void_p), None,
-                                              C.c_void_p(out.data_ptr())))
-        return out
-
     def knots(self, coords, minmax):
         cs = np.ascontiguousarray(coords, dtype=np.int32)
         out = self._buf(len(cs), NK, 6)
@@ -125,30 +182,25 @@ class CudaLocal:
         return out
 
 
-def fit_sharded(local, group=None, gather=None):
-    """Normalise a node-sharded fit: two tiny all_gathers (max, then sum).  `gather(t, group)` defaults to
-    torch.distributed all_gather; tests emulating several ranks on one GPU inject their own.  Reductions over
-    the gathered rank axis have a fixed order, so every rank derives bit-identical scalars."""
+def _rank(group):
+    import torch.distributed as dist
+    return dist.get_rank(group)
+
+
+def fit_sharded(local, group=None, gather=None, rank=None):
+    """Normalise a node-sharded fit with one tiny all_gather of (local max, local sum).  `gather(t, group)` defaults
+    to torch.distributed all_gather; tests emulating several ranks inject their own.  The combine runs in rank
+    order on every rank, so all ranks derive bit-identical scalars."""
     gather = gather or _all_gather
-    gmax = gather(local.fit_local_max(), group).amax(dim=0)
-    gsum = gather(local.fit_local_sum(gmax), group).sum(dim=0)
-    local.fit_normalise(gsum)
-    return gmax, gsum
+    g = gather(local.fit_local_stats(), group)      # [world, 2]
+    local.fit_normalise_gathered(g, _rank(group) if rank is None else rank)
+    return g
 
 
 def marginals_sharded(local, coords, group=None, gather=None):
-    """Global (mu, sigma, value_nodes, weight_nodes) for K coordinate marginals of a node-sharded
-    posterior: two all_gathers per batch, no global sort."""
-    import torch
+    """Global (mu, sigma, value_nodes, weight_nodes) for K coordinate marginals of a node-sharded posterior:
+    two all_gathers per batch, no global sort, no host arithmetic in between."""
     gather = gather or _all_gather
-    g = gather(local.moments(coords), group)          # [world, K, 4] = (sum w v, sum w v^2, min, max)
-    s = g[:, :, :2].sum(dim=0)
-    vmin = g[:, :, 2].amin(dim=0)
-    vmax = g[:, :, 3].amax(dim=0)
-    minmax = torch.stack([vmin, vmax], dim=1)
-    gathered = gather(local.knots(coords, minmax), group)   # [world, K, 98, 6]
-    wn = combine_knots(gathered, vmin, vmax)
-    vn = knot_values(gathered, vmin, vmax)
-    mu = s[:, 0]
-    sigma = torch.sqrt(s[:, 1] - mu * mu)
-    return mu, sigma, vn, wn
+    gm = gather(local.moments(coords), group)                   # [world, K, 4] = (sum w v, sum w v^2, min, max)
+    gc = gather(local.knots_gathered(coords, gm), group)        # [world, K, 98, 6]
+    return local.combine_gathered(gm, gc)

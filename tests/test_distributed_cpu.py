@@ -1,7 +1,9 @@
 """World-size-2 `gloo` test of the node-sharded combine (jointposteriors.jl_b200/distributed.py):
-the collectives + host combine reproduce the single-process oracle, including the Grid tie rule across
+the collectives + rank-ordered combine reproduce the single-process oracle, including the Grid tie rule across
 shard boundaries.  The per-rank local phase is a numpy stand-in with the same contract as the CUDA
-kernels (jp_fit_local*, jp_marginal_local_moments, jp_marginal_local_knots)."""
+entry points (jp_fit_local_stats, jp_fit_normalise_gathered, jp_marginal_local_moments,
+jp_marginal_local_knots_gathered, jp_marginal_combine_gathered); its combine is distributed.reference_*, the
+torch restatement the GPU tests hold the CUDA combine kernels against."""
 import os
 import socket
 import sys
@@ -23,24 +25,23 @@ def _free_port():
 class NumpyLocal:
     """Same contract as distributed.CudaLocal, on numpy arrays (CPU)."""
 
-    def __init__(self, a, w, values, m0):
+    def __init__(self, a, w, values, m0, D):
         import torch
         self.t = torch
+        self.D = D
         self.a, self.w, self.values, self.m0 = a, w, values, m0
         self.density = None
 
     def _t(self, x):
         return self.t.tensor(np.asarray(x, dtype=np.float64))
 
-    def fit_local_max(self):
-        return self._t([self.a.max()])
+    def fit_local_stats(self):
+        m = self.a.max()
+        self.e = self.w * np.exp(self.a - m)
+        return self._t([m, self.e.sum()])
 
-    def fit_local_sum(self, gmax):
-        self.e = self.w * np.exp(self.a - float(gmax[0]))
-        return self._t([self.e.sum()])
-
-    def fit_normalise(self, gsum):
-        self.density = self.e / float(gsum[0])
+    def fit_normalise_gathered(self, g, rank):
+        self.density = self.e * float(self.D.reference_fit_scale(g, rank))
 
     def moments(self, coords):
         out = []
@@ -49,8 +50,8 @@ class NumpyLocal:
             out.append([(self.density * v).sum(), (self.density * v * v).sum(), v.min(), v.max()])
         return self._t(out)
 
-    def knots(self, coords, minmax):
-        mm = minmax.numpy()
+    def knots_gathered(self, coords, gm):
+        mm = self.t.stack([gm[:, :, 2].amin(dim=0), gm[:, :, 3].amax(dim=0)], dim=1).numpy()
         out = np.zeros((len(coords), 98, 6))
         for j, k in enumerate(coords):
             v = self.values[k]
@@ -68,6 +69,9 @@ class NumpyLocal:
                     out[j, i - 1] = [S, pred, np.inf, np.inf, 0, x]
         return self._t(out)
 
+    def combine_gathered(self, gm, gc):
+        return tuple(x.numpy() for x in self.D.reference_combine(gm, gc))
+
 
 def _worker(rank, world, port, a, w, values, q):
     sys.path.insert(0, ROOT)
@@ -81,10 +85,10 @@ def _worker(rank, world, port, a, w, values, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     M = len(a)
     b, e = D.shard_bounds(M, rank, world)
-    loc = NumpyLocal(a[b:e], w[b:e], [v[b:e] for v in values], b)
-    gmax, gsum = D.fit_sharded(loc)
+    loc = NumpyLocal(a[b:e], w[b:e], [v[b:e] for v in values], b, D)
+    D.fit_sharded(loc)
     mu, sg, vn, wn = D.marginals_sharded(loc, list(range(len(values))))
-    q.put((rank, b, e, loc.density, mu.numpy(), sg.numpy(), vn.numpy(), wn.numpy()))
+    q.put((rank, b, e, loc.density, mu, sg, vn, wn))
     dist.barrier()
     dist.destroy_process_group()
 

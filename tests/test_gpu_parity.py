@@ -326,8 +326,9 @@ def test_reduced_rank_scale(jp, O, gpu_ctx):
 # ------------------------------------------------------------------------------ node sharding on one GPU
 @pytest.mark.parametrize("world", [2, 5])
 def test_sharded_phases_match_single(jp, O, gpu_ctx, world):
-    """The multi-GPU phases (jp_fit_local / _local_sum / _normalise, jp_marginal_local_*) run as `world`
-    node shards on ONE GPU with the collectives emulated by torch.stack reproduce the unsharded result."""
+    """The multi-GPU phases (jp_fit_local_stats / _normalise_gathered, jp_marginal_local_moments /
+    _local_knots_gathered / _combine_gathered) run as `world` node shards on ONE GPU with the collectives emulated by
+    torch.stack reproduce the unsharded result."""
     import torch
     from jointposteriors_jl_b200 import distributed as D
     from jointposteriors_jl_b200.model import JointPosterior
@@ -343,6 +344,34 @@ def test_sharded_phases_match_single(jp, O, gpu_ctx, world):
     shards = [JointPosterior(Mo, dd, grid, x, U, neg_min, path=jp.PATH_FP64, node_range=D.shard_bounds(Mtot, r, world))
               for r in range(world)]
     locs = [D.CudaLocal(s) for s in shards]
+    # one-collective protocol (what distributed.fit_sharded / marginals_sharded drive), all_gather = torch.stack
+    g = torch.stack([l.fit_local_stats() for l in locs]).contiguous()
+    for r, l in enumerate(locs):
+        l.fit_normalise_gathered(g, r)
+    dens = np.concatenate([s.density for s in shards])
+    assert relerr(dens, full.density) < 1e-13
+    coords = list(range(d))
+    gm = torch.stack([l.moments(coords) for l in locs]).contiguous()
+    gc = torch.stack([l.knots_gathered(coords, gm) for l in locs]).contiguous()
+    res = [l.combine_gathered(gm, gc) for l in locs]
+    for r in res[1:]:                       # every rank derives identical bits
+        assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(res[0], r))
+    mu, sg, vn, wn = res[0]
+    ms = jp.marginals(full, coords)
+    for k in range(d):
+        assert abs(mu[k] - ms[k].mu) < 1e-12 * max(1.0, abs(ms[k].mu))
+        assert abs(sg[k] - ms[k].sigma) < 1e-10 * ms[k].sigma
+        assert np.array_equal(vn[k], ms[k].itp.values)
+        assert np.max(np.abs(wn[k] - ms[k].itp.weights)) < 1e-11, k
+    # the CUDA combine kernels against their torch restatement
+    rmu, rsg, rvn, rwn = [x.cpu().numpy() for x in D.reference_combine(gm, gc)]
+    assert np.allclose(mu, rmu, rtol=1e-15, atol=0) and np.allclose(sg, rsg, rtol=1e-13, atol=0)
+    assert np.array_equal(vn, rvn) and np.max(np.abs(wn - rwn)) < 1e-15
+    for r in range(world):
+        sc = float(D.reference_fit_scale(g, r))
+        assert abs(sc * float(g[r, 1]) - shards[r].density.sum()) < 1e-12      # sum of a shard's density = s_r x its scale
+    # the two-collective phases of include/jpcuda.h (jp_fit_local / _local_sum / _normalise, jp_marginal_local_knots
+    # with explicit extrema) give the same result
     gmax = torch.stack([l.fit_local_max() for l in locs]).max(dim=0).values.contiguous()
     sums = torch.stack([l.fit_local_sum(gmax) for l in locs])
     gsum = sums[0].clone()
@@ -350,21 +379,14 @@ def test_sharded_phases_match_single(jp, O, gpu_ctx, world):
         gsum = gsum + sums[r]
     for l in locs:
         l.fit_normalise(gsum.contiguous())
-    dens = np.concatenate([s.density for s in shards])
-    assert relerr(dens, full.density) < 1e-13
-    coords = list(range(d))
-    g = torch.stack([l.moments(coords) for l in locs])
-    vmin, vmax = g[:, :, 2].min(dim=0).values, g[:, :, 3].max(dim=0).values
+    dens2 = np.concatenate([s.density for s in shards])
+    assert relerr(dens2, dens) < 1e-14
+    g2 = torch.stack([l.moments(coords) for l in locs])
+    vmin, vmax = g2[:, :, 2].min(dim=0).values, g2[:, :, 3].max(dim=0).values
     minmax = torch.stack([vmin, vmax], dim=1).contiguous()
     cand = torch.stack([l.knots(coords, minmax) for l in locs])
-    wn = D.combine_knots(cand, vmin, vmax).cpu().numpy()
-    vn = D.knot_values(cand, vmin, vmax).cpu().numpy()
-    mu = g[:, :, 0].sum(dim=0).cpu().numpy()
-    ms = jp.marginals(full, coords)
-    for k in range(d):
-        assert abs(mu[k] - ms[k].mu) < 1e-12 * max(1.0, abs(ms[k].mu))
-        assert np.array_equal(vn[k], ms[k].itp.values)
-        assert np.max(np.abs(wn[k] - ms[k].itp.weights)) < 1e-11, k
+    wn2 = D.reference_combine_knots(cand, vmin, vmax).cpu().numpy()
+    assert np.max(np.abs(wn2 - wn)) < 1e-12
 
 
 # ------------------------------------------------------------------------------ BASELINE sizes: properties
