@@ -56,7 +56,7 @@ int jp_glm_num_blocks(const jp_ctx* ctx, long long N);
 #ifndef TC_LDW
 #define TC_LDW 8                 // columns per tcgen05.ld of the epilogue (8 or 16)
 #endif
-#define TC_PREP_BLOCKS 296
+#define TC_PREP_BLOCKS 592       // 4 per SM: 8 x 40 KB of staged records keep the FP64 pipe fed
 #define TC_NBOUND 14             // per-block bound partials, see tc_obs_prep_kernel
 #define TC_NORD 5                // series lengths NC = 4, 6, 8, 10, 12 (orders 6 .. 14)
 
@@ -212,22 +212,26 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[16]) { tmem_ld_wait16
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
 
 // ------------------------------------------------------------------------------------ operand preparation
-// X' = [x_hi | x_lo | x_hi | 0]: depends on the data only, built once per jp_data
+// X' = [x_hi | x_lo | x_hi | 0]: depends on the data only, built once per jp_data.  HBM-bound streaming kernel
+// (8 N (d + 1) bytes in, 4 N_pad kp out): threadIdx.x is the operand column, threadIdx.y the row inside the block's
+// slab, so the stores of the [N_pad][kp] operand are coalesced, the three reads of a record hit L1, and no thread
+// divides.
+#define TC_SPLIT_ROWS 8
 __global__ void tc_split_x_kernel(int d, int ncols, int kp, long long N, long long N_pad, const double* __restrict__ obs,
                                   float* __restrict__ xs) {
-  // one thread per operand element: coalesced stores of the [N_pad][kp] operand, the record reads hit L1/L2
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= N_pad * kp) return;
-  const long long i = e / kp;
-  const int c = (int)(e - i * kp);
-  float v = 0.f;
-  if (i < N && c < 3 * d) {
-    const int part = c / d, k = c - part * d;
-    float hi, lo;
-    tf32_split(obs[(size_t)i * ncols + k], hi, lo);
-    v = (part == 1) ? lo : hi;
+  const int c = threadIdx.x;                     // 0 .. kp - 1
+  const int part = (c >= 2 * d) ? 2 : (c >= d ? 1 : 0);
+  const int k = c - part * d;
+  const bool live = c < 3 * d;
+  for (long long i = (long long)blockIdx.x * TC_SPLIT_ROWS + threadIdx.y; i < N_pad; i += (long long)gridDim.x * TC_SPLIT_ROWS) {
+    float v = 0.f;
+    if (live && i < N) {
+      float hi, lo;
+      tf32_split(__ldg(obs + (size_t)i * ncols + k), hi, lo);
+      v = (part == 1) ? lo : hi;
+    }
+    xs[(size_t)i * kp + c] = v;
   }
-  xs[e] = v;
 }
 
 // Per observation: eta_hat, Taylor coefficients c_3 .. c_14 of the link remainder, t = |U' x| (so that
@@ -235,32 +239,72 @@ __global__ void tc_split_x_kernel(int d, int ncols, int kp, long long N, long lo
 //   [0] max_i t_i   [1] sum |c_3| t^3   [2+j], [7+j] (j = 0..4 <-> NC = 4, 6, 8, 10, 12): truncation tail bounds of
 //   the series stopped at order NC + 2, summed over observations at |z| = z_ref and |z| = z_max
 //   [12] sum_i |R_i| and [13] sum_i R_i^2 at |z| = z_ref (majorants)
-__global__ void __launch_bounds__(256)
+#define TC_PREP_THREADS 128      // = observations per staged tile
+__global__ void __launch_bounds__(TC_PREP_THREADS)
 tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N_pad, const double* __restrict__ obs,
                    const double* __restrict__ mu, const double* __restrict__ U, double z_ref, double z_max,
                    float* __restrict__ coef, double* __restrict__ bounds) {
-  extern __shared__ double sh[];
-  double* s_mu = sh;            // d
-  double* s_U = sh + d;         // d x p column-major
+  // HBM-bound streaming kernel (8 N (d + 1) bytes in, 48 N_pad out): a block copies a tile of 128 records to shared
+  // memory with coalesced loads (row stride padded to an odd number of doubles: conflict-free column access), then a
+  // thread owns one record.  t^2 = |U' x|^2 takes U four columns at a time (two 16-byte broadcast loads per record
+  // element and four FMAs), so the loop is bound by the FP64 pipe, not by shared-memory traffic.
+  extern __shared__ __align__(16) double sh[];
+  const int p4 = (p + 3) & ~3, rs = ncols | 1;
+  double* s_mu = sh;                       // d
+  double* s_U = sh + ((d + 1) & ~1);       // d x p4 row-major: s_U[k * p4 + j] = U[k + j * d]  (16-byte aligned rows)
+  double* s_tile = s_U + (size_t)d * p4;   // TC_PREP_THREADS x rs
   __shared__ double red[33];
+  __shared__ int s_kend[16];               // per block of four columns of U: one past its last non-zero row
   for (int k = threadIdx.x; k < d; k += blockDim.x) s_mu[k] = mu[k];
-  for (int k = threadIdx.x; k < d * p; k += blockDim.x) s_U[k] = U[k];
-  __syncthreads();
+  for (int e = threadIdx.x; e < d * p4; e += blockDim.x) {
+    const int k = e / p4, j = e - k * p4;
+    s_U[e] = (j < p) ? U[(size_t)j * d + k] : 0.0;
+  }
+  // the Cholesky scale matrix is upper triangular (reference src/joint_posterior.jl:56-76): its zero rows are skipped
+  if (threadIdx.x < p4 / 4) {
+    int kend = 0;
+    for (int k = 0; k < d; ++k)
+      for (int j = 4 * threadIdx.x; j < min(p, 4 * (int)threadIdx.x + 4); ++j)
+        if (U[(size_t)j * d + k] != 0.0) kend = k + 1;
+    s_kend[threadIdx.x] = kend;
+  }
   double b_tmax = 0, b_a1 = 0, b_ref[TC_NORD] = {0}, b_max[TC_NORD] = {0}, b_r = 0, b_r2 = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N_pad; i += (long long)gridDim.x * blockDim.x) {
+  for (long long base = (long long)blockIdx.x * TC_PREP_THREADS; base < N_pad; base += (long long)gridDim.x * TC_PREP_THREADS) {
+    __syncthreads();     // the previous tile is consumed (and s_mu / s_U are visible)
+    const long long cnt = min((long long)TC_PREP_THREADS, N - base);
+    if (cnt > 0) {
+      const double* src = obs + (size_t)base * ncols;
+      // flat coalesced copy; (row, column) of element e advance by (128 / ncols, 128 % ncols) per step: no division
+      int row = threadIdx.x / ncols, col = threadIdx.x - row * ncols;
+      const int drow = TC_PREP_THREADS / ncols, dcol = TC_PREP_THREADS - drow * ncols;
+      for (int e = threadIdx.x; e < (int)cnt * ncols; e += TC_PREP_THREADS) {
+        s_tile[row * rs + col] = __ldg(src + e);
+        row += drow;
+        col += dcol;
+        if (col >= ncols) { col -= ncols; ++row; }
+      }
+    }
+    __syncthreads();
+    const long long i = base + threadIdx.x;
     float* o = coef + i;     // o[k * N_pad]
     if (i >= N) {
       for (int k = 0; k < TC_NCMAX; ++k) o[(size_t)k * N_pad] = 0.f;
       continue;
     }
-    const double* r = obs + (size_t)i * ncols;
+    const double* r = s_tile + threadIdx.x * rs;
     double eta = 0;
     for (int k = 0; k < d; ++k) eta += r[k] * s_mu[k];
     double t2 = 0;
-    for (int j = 0; j < p; ++j) {
-      double a = 0;
-      for (int k = 0; k < d; ++k) a += s_U[(size_t)j * d + k] * r[k];
-      t2 += a * a;
+    for (int j = 0; j < p4; j += 4) {
+      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      const int kend = s_kend[j >> 2];
+      for (int k = 0; k < kend; ++k) {
+        const double xk = r[k];
+        const double2 u01 = *reinterpret_cast<const double2*>(s_U + (size_t)k * p4 + j);
+        const double2 u23 = *reinterpret_cast<const double2*>(s_U + (size_t)k * p4 + j + 2);
+        a0 = fma(u01.x, xk, a0); a1 = fma(u01.y, xk, a1); a2 = fma(u23.x, xk, a2); a3 = fma(u23.y, xk, a3);
+      }
+      t2 += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
     }
     const double t = sqrt(t2);
     double c[TC_ORDER_MAX + 1];   // c[k], k = 3 .. TC_ORDER_MAX
@@ -849,7 +893,8 @@ static int ensure_data_state(jp_ctx* ctx, jp_data* data, int d) {
   JP_CUDA(jp_dmalloc(ctx, &s->d_sums, (size_t)(nE + 1) * 8));
   JP_CUDA(jp_dmalloc(ctx, &s->d_work, (size_t)s->glm_blocks * (nE + 1) * 8));
   JP_CUDA(jp_dmalloc(ctx, &s->d_bounds, (size_t)TC_PREP_BLOCKS * TC_NBOUND * 8));
-  tc_split_x_kernel<<<(unsigned)((s->N_pad * s->kp + 255) / 256), 256, 0, ctx->stream>>>(d, data->ncols, s->kp, s->N, s->N_pad,
+  const unsigned split_blocks = (unsigned)std::min<long long>((s->N_pad + TC_SPLIT_ROWS - 1) / TC_SPLIT_ROWS, (long long)ctx->sm_count * 32);
+  tc_split_x_kernel<<<split_blocks, dim3(s->kp, TC_SPLIT_ROWS), 0, ctx->stream>>>(d, data->ncols, s->kp, s->N, s->N_pad,
                                                                                   data->d_obs, s->d_xs);
   JP_CHECK_LAUNCH(ctx);
   JP_TRY(make_tensor_map(&s->tmA, s->d_xs, s->N_pad, s->kp, TC_OBS_TILE));
@@ -934,8 +979,10 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   JP_TRY(jp_glm_sums_device(ctx, data, d, post->d_mu, ds->d_sums, ds->d_work, ds->glm_blocks));
   // per-observation coefficients + bounds
   const double z_max = std::sqrt(post->grid->zmax2), z_ref = std::min(z_max, 6.0);
-  size_t sm_obs = (size_t)(d + d * p) * 8;
-  tc_obs_prep_kernel<<<TC_PREP_BLOCKS, 256, sm_obs, st>>>(data->family, d, p, data->ncols, data->N, ds->N_pad, data->d_obs,
+  const size_t sm_obs = (size_t)(((d + 1) & ~1) + d * ((p + 3) & ~3) + TC_PREP_THREADS * (data->ncols | 1)) * 8;
+  if (sm_obs > 48 * 1024)
+    JP_CUDA(cudaFuncSetAttribute(tc_obs_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_obs));
+  tc_obs_prep_kernel<<<TC_PREP_BLOCKS, TC_PREP_THREADS, sm_obs, st>>>(data->family, d, p, data->ncols, data->N, ds->N_pad, data->d_obs,
                                                           post->d_mu, post->d_U, z_ref, z_max, ds->d_coef, ds->d_bounds);
   JP_CHECK_LAUNCH(ctx);
   double* hb = ctx->h_pinned + 4096;   // away from the constants staged by jp_upload_fit_consts
