@@ -205,7 +205,8 @@ int jp_fit_path_used(const jp_posterior* post);
 /* a-priori error figures of the tensor-core path for the last fit that tried it (csrc/jp_glm_tc.cu,
  * jp_tc_choose_order): h_out8[0] = max |Delta eta| over (node, observation) pairs, [1] = truncation bound of the
  * link-remainder series at |z| <= 6, [2] = statistical rounding estimate, [3] = series coefficients used
- * (0 = bounds not met, FP64 kernel used), [4] = worst-case rounding bound; [5..7] reserved */
+ * (0 = bounds not met, FP64 kernel used), [4] = worst-case rounding bound, [5] = 1 when the coefficients are the
+ * economised ones (next odd / even order folded into the kept orders, tools/gen_fold.py); [6..7] reserved */
 int jp_fit_diagnostics(const jp_posterior* post, double* h_out8);
 
 /* ---------------------------------------------------------------------------------------------

@@ -5,86 +5,153 @@
 // GLM the Hessian is the closed form X' W X).  The same sums (X'(y - mu_hat), X' W X at the mode) are
 // what the tensor-core log-density path centres its expansion on (jp_glm_tc.cu).
 //
-// Layout: a block stages a tile of observation records in shared memory, computes the per-record
-// residual and weight once, then each thread owns a few entries of the packed (gradient, upper
-// Hessian) vector and accumulates them over the tile.  Per-block partials are combined in block
-// order by a second kernel, so the result is deterministic.
+// Layout: a block stages a tile of observation records in shared memory (coalesced loads), computes the
+// per-record residual and weight once, then updates X' W X as a register-blocked rank update: a thread owns
+// one BS x BS block of the upper block triangle and one slice of the tile's observations, so a record costs it
+// 2 BS + 1 shared-memory doubles for BS^2 + BS FP64 operations (the FP64 pipe, not shared-memory bandwidth,
+// bounds the loop).  Slices are summed in slice order at the end of the block, per-block partials in block
+// order by a second kernel, so the result is deterministic.  At N = 1e7, d = 30 the kernel streams the 2.5 GB
+// of records once; its floor is max(HBM time, N (d^2/2 + ~150) FP64 operations).
 #include <algorithm>
 #include <vector>
 #include "jp_common.cuh"
 
-#define JP_GLM_THREADS 256
-#define JP_GLM_TILE 128    // observations per tile
+#define JP_GLM_TILE 128    // observations per tile (upper bound: a tile holds slices x iterations <= 128)
 
-__global__ void __launch_bounds__(JP_GLM_THREADS)
+// BS = 4: 256 threads; BS = 8: 128 threads (64 FP64 accumulators = 128 registers per thread); two blocks per SM
+// either way, so that one block's record loads overlap the other's arithmetic
+template <int BS, int JP_GLM_THREADS>
+__global__ void __launch_bounds__(JP_GLM_THREADS, 2)
 jp_glm_partials_kernel(int family, int d, long long N, const double* __restrict__ obs, const double* __restrict__ beta,
                        int nE, double* __restrict__ part /* [gridDim.x][nE + 1] */) {
-  extern __shared__ double sh[];
+  extern __shared__ __align__(16) double sh[];
   const int ncols = d + 1;
-  double* tile = sh;                               // JP_GLM_TILE x ncols
-  double* res = tile + JP_GLM_TILE * ncols;        // JP_GLM_TILE
+  const int nb = (d + BS - 1) / BS, npairs = nb * (nb + 1) / 2;
+  const int rs = nb * BS + 2;                      // row stride: = 2 (mod 4) doubles -> conflict-free 16-byte loads
+  const int S = min(JP_GLM_THREADS / npairs, JP_GLM_TILE), iters = JP_GLM_TILE / S, T = S * iters;
+  double* tile = sh;                               // JP_GLM_TILE x rs (columns >= d stay zero)
+  double* res = tile + JP_GLM_TILE * rs;           // JP_GLM_TILE
   double* wgt = res + JP_GLM_TILE;                 // JP_GLM_TILE
   double* s_beta = wgt + JP_GLM_TILE;              // d
   __shared__ double red[33];
   for (int k = threadIdx.x; k < d; k += JP_GLM_THREADS) s_beta[k] = beta[k];
-  // entries owned by this thread: e = threadIdx.x + j * JP_GLM_THREADS; at most 9 for d = 64
-  double acc[9];
-  int er[9], ec[9];
+  for (int k = threadIdx.x; k < JP_GLM_TILE * rs; k += JP_GLM_THREADS) tile[k] = 0.0;
+  // this thread's block (br <= bc) of the upper block triangle and its observation slice
+  const int pair = threadIdx.x / S, slice = threadIdx.x - pair * S;
+  const bool active = pair < npairs;
+  int br = 0, bc = 0;
+  if (active) {
+    int t = pair;
+    while (t >= bc + 1) { t -= bc + 1; ++bc; }     // packed by block column, like the entries themselves
+    br = t;
+  }
+  const bool diag = active && br == bc;
+  double acc[BS][BS], gacc[BS];
 #pragma unroll
-  for (int j = 0; j < 9; ++j) {
-    acc[j] = 0.0;
-    int e = threadIdx.x + j * JP_GLM_THREADS;
-    er[j] = -1; ec[j] = -1;
-    if (e < d) {
-      er[j] = e; ec[j] = -2;                        // gradient entry
-    } else if (e < nE) {
-      int t = e - d, c = 0;                          // packed upper triangle, column by column
-      while (t >= c + 1) { t -= c + 1; ++c; }
-      er[j] = t; ec[j] = c;
-    }
+  for (int i = 0; i < BS; ++i) {
+    gacc[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < BS; ++j) acc[i][j] = 0.0;
   }
   double ll = 0.0;
-  for (long long base = (long long)blockIdx.x * JP_GLM_TILE; base < N; base += (long long)gridDim.x * JP_GLM_TILE) {
-    int cnt = (int)min((long long)JP_GLM_TILE, N - base);
-    __syncthreads();
-    const double* src = obs + (size_t)base * ncols;
-    for (int i = threadIdx.x; i < cnt * ncols; i += JP_GLM_THREADS) tile[i] = __ldg(src + i);
-    __syncthreads();
-    if (threadIdx.x < cnt) {
-      const double* r = tile + threadIdx.x * ncols;
-      double eta = 0;
-      for (int k = 0; k < d; ++k) eta += r[k] * s_beta[k];
-      double mu, wv;
-      if (family == JP_FAM_LOGISTIC) {
-        mu = 1.0 / (1.0 + exp(-eta));
-        wv = mu * (1.0 - mu);
-        ll += r[d] * eta - (fmax(eta, 0.0) + log1p(exp(-fabs(eta))));
-      } else {
-        mu = exp(eta);
-        wv = mu;
-        ll += r[d] * eta - mu;
+  for (long long base = (long long)blockIdx.x * T; base < N; base += (long long)gridDim.x * T) {
+    const int cnt = (int)min((long long)T, N - base);
+    __syncthreads();     // the previous tile is consumed (first pass: zero fill and s_beta are visible)
+    {
+      // flat coalesced copy of cnt records; (row, column) advance by (threads / ncols, threads % ncols) per step
+      const double* src = obs + (size_t)base * ncols;
+      int row = threadIdx.x / ncols, col = threadIdx.x - row * ncols;
+      const int drow = JP_GLM_THREADS / ncols, dcol = JP_GLM_THREADS - drow * ncols;
+      for (int e = threadIdx.x; e < cnt * ncols; e += JP_GLM_THREADS) {
+        const double v = __ldg(src + e);
+        if (col < d) tile[row * rs + col] = v; else res[row] = v;   // y parks in res until the residual replaces it
+        row += drow;
+        col += dcol;
+        if (col >= ncols) { col -= ncols; ++row; }
       }
-      res[threadIdx.x] = r[d] - mu;
-      wgt[threadIdx.x] = wv;
     }
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      if (er[j] < 0) continue;
-      double a = acc[j];
-      if (ec[j] == -2) {
-        for (int n = 0; n < cnt; ++n) a += res[n] * tile[n * ncols + er[j]];
-      } else {
-        for (int n = 0; n < cnt; ++n) a += wgt[n] * tile[n * ncols + er[j]] * tile[n * ncols + ec[j]];
+    for (int n = threadIdx.x; n < T; n += JP_GLM_THREADS) {
+      double rv = 0.0, wv = 0.0;
+      if (n < cnt) {
+        const double* r = tile + n * rs;
+        const double y = res[n];
+        double eta = 0;
+        for (int k = 0; k < d; ++k) eta += r[k] * s_beta[k];
+        double mu;
+        if (family == JP_FAM_LOGISTIC) {
+          mu = 1.0 / (1.0 + exp(-eta));
+          wv = mu * (1.0 - mu);
+          ll += y * eta - (fmax(eta, 0.0) + log1p(exp(-fabs(eta))));
+        } else {
+          mu = exp(eta);
+          wv = mu;
+          ll += y * eta - mu;
+        }
+        rv = y - mu;
       }
-      acc[j] = a;
+      res[n] = rv;     // records past the end of the data contribute nothing
+      wgt[n] = wv;
+    }
+    __syncthreads();
+    if (active) {
+      const double* xr = tile + br * BS;
+      const double* xc = tile + bc * BS;
+      for (int it = 0; it < iters; ++it) {
+        const int n = slice + it * S;
+        const double w = wgt[n];
+        double a[BS], b[BS];
+#pragma unroll
+        for (int i = 0; i < BS; i += 2) {
+          const double2 va = *reinterpret_cast<const double2*>(xr + n * rs + i);
+          const double2 vb = *reinterpret_cast<const double2*>(xc + n * rs + i);
+          a[i] = va.x; a[i + 1] = va.y;
+          b[i] = vb.x; b[i + 1] = vb.y;
+        }
+        if (diag) {
+          const double r = res[n];
+#pragma unroll
+          for (int i = 0; i < BS; ++i) gacc[i] = fma(r, a[i], gacc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+          const double wa = w * a[i];
+#pragma unroll
+          for (int j = 0; j < BS; ++j) acc[i][j] = fma(wa, b[j], acc[i][j]);
+        }
+      }
     }
   }
+  // slices -> block partial: one block pair at a time through shared memory (the tile is free now)
   double* o = part + (size_t)blockIdx.x * (nE + 1);
+  constexpr int NV = BS * BS + BS;
+  double* buf = tile;                              // [S][NV]
+  for (int pp = 0; pp < npairs; ++pp) {
+    __syncthreads();
+    if (active && pair == pp) {
+      double* w = buf + slice * NV;
 #pragma unroll
-  for (int j = 0; j < 9; ++j) {
-    int e = threadIdx.x + j * JP_GLM_THREADS;
-    if (e < nE) o[e] = acc[j];
+      for (int i = 0; i < BS; ++i) {
+#pragma unroll
+        for (int j = 0; j < BS; ++j) w[i * BS + j] = acc[i][j];
+        w[BS * BS + i] = gacc[i];
+      }
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < NV; v += JP_GLM_THREADS) {
+      int pc = 0, t = pp;
+      while (t >= pc + 1) { t -= pc + 1; ++pc; }
+      const int pr = t;
+      double sum = 0;
+      for (int sl = 0; sl < S; ++sl) sum += buf[sl * NV + v];
+      if (v < BS * BS) {
+        const int r = pr * BS + v / BS, c = pc * BS + v % BS;
+        if (r <= c && c < d) o[d + c * (c + 1) / 2 + r] = sum;     // packed upper triangle, column by column
+      } else if (pr == pc) {
+        const int r = pr * BS + (v - BS * BS);
+        if (r < d) o[r] = sum;                                     // gradient entry
+      }
+    }
   }
   ll = jp_block_sum(ll, red);
   if (threadIdx.x == 0) o[nE] = ll;
@@ -102,16 +169,28 @@ __global__ void __launch_bounds__(256) jp_glm_combine_kernel(int nblocks, int nE
 }
 
 // device-side entry used by both the C ABI and the TC path: packed sums into d_out[nE + 1]
+template <int BS, int JP_GLM_THREADS>
+static int launch_partials(jp_ctx* ctx, const jp_data* data, int d, const double* d_beta, double* d_work, int nblocks, int nE) {
+  const int nb = (d + BS - 1) / BS, npairs = nb * (nb + 1) / 2, rs = nb * BS + 2;
+  const int S = std::min(JP_GLM_THREADS / npairs, JP_GLM_TILE);
+  // the slice buffer of the final reduction reuses the tile
+  size_t tile_doubles = std::max<size_t>((size_t)JP_GLM_TILE * rs, (size_t)S * (BS * BS + BS));
+  size_t smem = (tile_doubles + 2 * JP_GLM_TILE + d) * sizeof(double);
+  if (smem > 48 * 1024)
+    JP_CUDA(cudaFuncSetAttribute(jp_glm_partials_kernel<BS, JP_GLM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  jp_glm_partials_kernel<BS, JP_GLM_THREADS><<<nblocks, JP_GLM_THREADS, smem, ctx->stream>>>(data->family, d, data->N, data->d_obs, d_beta, nE,
+                                                                               d_work);
+  JP_CHECK_LAUNCH(ctx);
+  return JP_OK;
+}
+
 int jp_glm_sums_device(jp_ctx* ctx, const jp_data* data, int d, const double* d_beta, double* d_out, double* d_work,
                        int nblocks) {
   int nE = d + d * (d + 1) / 2;
-  size_t smem = (size_t)(JP_GLM_TILE * (d + 1) + 2 * JP_GLM_TILE + d) * sizeof(double);
-  if (smem > 48 * 1024) {
-    JP_CUDA(cudaFuncSetAttribute(jp_glm_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
-  jp_glm_partials_kernel<<<nblocks, JP_GLM_THREADS, smem, ctx->stream>>>(data->family, d, data->N, data->d_obs, d_beta,
-                                                                           nE, d_work);
-  JP_CHECK_LAUNCH(ctx);
+  // 8 x 8 register blocks unless the padding to a multiple of 8 would waste more than it saves
+  const int st = (d > 16) ? (launch_partials<8, 128>)(ctx, data, d, d_beta, d_work, nblocks, nE)
+                          : (launch_partials<4, 256>)(ctx, data, d, d_beta, d_work, nblocks, nE);
+  JP_TRY(st);
   jp_glm_combine_kernel<<<(nE + 1 + 7) / 8, 256, 0, ctx->stream>>>(nblocks, nE + 1, d_work, d_out);
   JP_CHECK_LAUNCH(ctx);
   return JP_OK;
@@ -119,7 +198,7 @@ int jp_glm_sums_device(jp_ctx* ctx, const jp_data* data, int d, const double* d_
 
 int jp_glm_num_blocks(const jp_ctx* ctx, long long N) {
   long long tiles = (N + JP_GLM_TILE - 1) / JP_GLM_TILE;
-  return (int)std::max(1LL, std::min(tiles, (long long)ctx->sm_count * 4));
+  return (int)std::max(1LL, std::min(tiles, (long long)ctx->sm_count * 2));
 }
 
 extern "C" int jp_glm_grad_hess(jp_ctx* ctx, const jp_data* data, int d, const double* h_beta, double* h_g,

@@ -34,6 +34,7 @@
 #include <cstdlib>
 #include <vector>
 #include "jp_common.cuh"
+#include "jp_fold_tables.h"
 
 int jp_glm_sums_device(jp_ctx* ctx, const jp_data* data, int d, const double* d_beta, double* d_out, double* d_work,
                        int nblocks);
@@ -57,18 +58,23 @@ int jp_glm_num_blocks(const jp_ctx* ctx, long long N);
 #define TC_LDW 8                 // columns per tcgen05.ld of the epilogue (8 or 16)
 #endif
 #define TC_PREP_BLOCKS 592       // 4 per SM: 8 x 40 KB of staged records keep the FP64 pipe fed
-#define TC_NBOUND 14             // per-block bound partials, see tc_obs_prep_kernel
 #define TC_NORD 5                // series lengths NC = 4, 6, 8, 10, 12 (orders 6 .. 14)
+#define TC_NBOUND (14 + 2 * TC_NFOLD)   // per-block bound partials, see tc_obs_prep_kernel
+#define TC_COEF_ROWS (TC_NCMAX + 1)     // coefficient rows per observation + the row of t_i = |U' x_i|
 
 // derivative polynomials of softplus in s = sigmoid(eta): f_1 = s, f_{k+1} = f_k'(s) (s - s^2)
 __constant__ double c_sp_poly[TC_ORDER_MAX + 1][TC_ORDER_MAX + 2];
 __constant__ double c_inv_fact[TC_ORDER_MAX + 2];
+// economisation constants (jp_fold_tables.h): [0] odd kappa, [1] even kappa; eps / growth factors likewise
+__constant__ double c_fold_kappa[2][TC_NFOLD][5];
+__constant__ double c_fold_eps[2][TC_NFOLD];
+__constant__ double c_fold_grow[2][TC_NFOLD];
 
 struct TcDataState {
   int d = 0, kp = 0, ka = 0;
   long long N = 0, N_pad = 0;
   float* d_xs = nullptr;       // [N_pad][kp]  (x_hi | x_lo | x_hi | 0)
-  float* d_coef = nullptr;     // [TC_NCMAX][N_pad]: coefficient k of every observation, contiguous per 128-observation tile
+  float* d_coef = nullptr;     // [TC_COEF_ROWS][N_pad]: coefficient k of every observation, contiguous per 128-observation tile; last row t_i
   double* d_sums = nullptr;    // packed (g[d], upper H[d(d+1)/2], L_hat)
   double* d_work = nullptr;    // partials of the GLM sums
   double* d_bounds = nullptr;  // [TC_PREP_BLOCKS][TC_NBOUND]
@@ -239,6 +245,8 @@ __global__ void tc_split_x_kernel(int d, int ncols, int kp, long long N, long lo
 //   [0] max_i t_i   [1] sum |c_3| t^3   [2+j], [7+j] (j = 0..4 <-> NC = 4, 6, 8, 10, 12): truncation tail bounds of
 //   the series stopped at order NC + 2, summed over observations at |z| = z_ref and |z| = z_max
 //   [12] sum_i |R_i| and [13] sum_i R_i^2 at |z| = z_ref (majorants)
+//   [14+j], [14+TC_NFOLD+j] (j <-> NC = 4, 6, 8, 10): the same two bounds for the ECONOMISED series of NC coefficients
+//   (orders NC + 3 and NC + 4 folded into the kept ones over |D| <= t_i z_ref, tc_fold_kernel)
 #define TC_PREP_THREADS 128      // = observations per staged tile
 __global__ void __launch_bounds__(TC_PREP_THREADS)
 tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N_pad, const double* __restrict__ obs,
@@ -269,6 +277,7 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
     s_kend[threadIdx.x] = kend;
   }
   double b_tmax = 0, b_a1 = 0, b_ref[TC_NORD] = {0}, b_max[TC_NORD] = {0}, b_r = 0, b_r2 = 0;
+  double f_ref[TC_NFOLD] = {0}, f_max[TC_NFOLD] = {0};
   for (long long base = (long long)blockIdx.x * TC_PREP_THREADS; base < N_pad; base += (long long)gridDim.x * TC_PREP_THREADS) {
     __syncthreads();     // the previous tile is consumed (and s_mu / s_U are visible)
     const long long cnt = min((long long)TC_PREP_THREADS, N - base);
@@ -288,7 +297,7 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
     const long long i = base + threadIdx.x;
     float* o = coef + i;     // o[k * N_pad]
     if (i >= N) {
-      for (int k = 0; k < TC_NCMAX; ++k) o[(size_t)k * N_pad] = 0.f;
+      for (int k = 0; k < TC_COEF_ROWS; ++k) o[(size_t)k * N_pad] = 0.f;
       continue;
     }
     const double* r = s_tile + threadIdx.x * rs;
@@ -320,6 +329,7 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
       for (int k = 3; k <= TC_ORDER_MAX; ++k) c[k] = m * c_inv_fact[k];
     }
     for (int k = 0; k < TC_NCMAX; ++k) o[(size_t)k * N_pad] = (float)c[3 + k];
+    o[(size_t)TC_NCMAX * N_pad] = __double2float_ru(t);   // rounded up: the fold interval may only grow
     // bounds
     b_tmax = fmax(b_tmax, t);
     b_a1 += fabs(c[3]) * t * t * t;
@@ -348,6 +358,15 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
       const int K = 2 * j + 6;              // last order kept (NC = K - 2 coefficients); pr = tr^{K+1}
       b_ref[j] += fabs(c[K + 1]) * pr + fabs(c[K + 2]) * pr * tr * gr;
       b_max[j] += fabs(c[K + 1]) * pm + fabs(c[K + 2]) * pm * tm * gm;
+      if (j < TC_NFOLD) {
+        // economised: the two folded orders leave their minimax error (eps inside the fold interval, the growth
+        // factor x^n beyond it), the orders after them are dropped as before
+        const double r3 = pr * tr * tr, m3 = pm * tm * tm;   // t^{K+3}
+        f_ref[j] += fabs(c[K + 1]) * pr * c_fold_eps[0][j] + fabs(c[K + 2]) * pr * tr * c_fold_eps[1][j] +
+                    fabs(c[K + 3]) * r3 + fabs(c[K + 4]) * r3 * tr * gr;
+        f_max[j] += fabs(c[K + 1]) * pm * c_fold_grow[0][j] + fabs(c[K + 2]) * pm * tm * c_fold_grow[1][j] +
+                    fabs(c[K + 3]) * m3 + fabs(c[K + 4]) * m3 * tm * gm;
+      }
       pr *= tr * tr;
       pm *= tm * tm;
     }
@@ -367,6 +386,35 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
   if (threadIdx.x == 0) ob[12] = v;
   v = jp_block_sum(b_r2, red);
   if (threadIdx.x == 0) ob[13] = v;
+  for (int j = 0; j < TC_NFOLD; ++j) {
+    v = jp_block_sum(f_ref[j], red);
+    if (threadIdx.x == 0) ob[14 + j] = v;
+    v = jp_block_sum(f_max[j], red);
+    if (threadIdx.x == 0) ob[14 + TC_NFOLD + j] = v;
+  }
+}
+
+// Economisation of the chosen series length (once NC is known): per observation, with a = t_i z_ref,
+//   c_k' = c_k + kappa_k c_n a^(n-k),   n = NC + 3 for the odd orders k = 3, 5, .., NC + 1 (rows 0, 2, ..),
+//                                       n = NC + 4 for the even orders k = 4, 6, .., NC + 2 (rows 1, 3, ..)
+// (tools/gen_fold.py: x^n ~ sum_k kappa_k x^k on |x| <= 1 in the span the kernel can evaluate).  In place on the
+// first NC coefficient rows; streams (NC + 3) rows in and NC rows out, 4 bytes per observation and row.
+__global__ void __launch_bounds__(256)
+tc_fold_kernel(int NC, long long N_pad, double z_ref, float* __restrict__ coef) {
+  const int j = (NC - 4) >> 1, h = NC >> 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N_pad; i += (long long)gridDim.x * blockDim.x) {
+    float* o = coef + i;
+    const double a = (double)o[(size_t)TC_NCMAX * N_pad] * z_ref, a2 = a * a;
+    const double cn_o = o[(size_t)NC * N_pad], cn_e = o[(size_t)(NC + 1) * N_pad];
+    double pw = a2;                      // a^(NC - 2m), m descending from NC/2 - 1
+    for (int m = h - 1; m >= 0; --m) {
+      float* ro = o + (size_t)(2 * m) * N_pad;
+      float* re = o + (size_t)(2 * m + 1) * N_pad;
+      *ro = (float)((double)*ro + c_fold_kappa[0][j][m] * cn_o * pw);
+      *re = (float)((double)*re + c_fold_kappa[1][j][m] * cn_e * pw);
+      pw *= a2;
+    }
+  }
 }
 
 // Per node: delta = U z, theta = mu + delta (all transforms are the identity on this path) and the FP64
@@ -833,6 +881,18 @@ static int upload_tables() {
   }
   JP_CUDA(cudaMemcpyToSymbol(c_sp_poly, poly, sizeof poly));
   JP_CUDA(cudaMemcpyToSymbol(c_inv_fact, inv_fact, sizeof inv_fact));
+  double kappa[2][TC_NFOLD][5], eps[2][TC_NFOLD], grow[2][TC_NFOLD];
+  for (int j = 0; j < TC_NFOLD; ++j) {
+    for (int m = 0; m < 5; ++m) {
+      kappa[0][j][m] = k_fold_odd[j][m];
+      kappa[1][j][m] = k_fold_even[j][m];
+    }
+    eps[0][j] = k_fold_eps_odd[j]; eps[1][j] = k_fold_eps_even[j];
+    grow[0][j] = k_fold_grow_odd[j]; grow[1][j] = k_fold_grow_even[j];
+  }
+  JP_CUDA(cudaMemcpyToSymbol(c_fold_kappa, kappa, sizeof kappa));
+  JP_CUDA(cudaMemcpyToSymbol(c_fold_eps, eps, sizeof eps));
+  JP_CUDA(cudaMemcpyToSymbol(c_fold_grow, grow, sizeof grow));
   done = true;
   return JP_OK;
 }
@@ -889,7 +949,7 @@ static int ensure_data_state(jp_ctx* ctx, jp_data* data, int d) {
   const int nE = d + d * (d + 1) / 2;
   s->glm_blocks = jp_glm_num_blocks(ctx, data->N);
   JP_CUDA(jp_dmalloc(ctx, &s->d_xs, (size_t)s->N_pad * s->kp * sizeof(float)));
-  JP_CUDA(jp_dmalloc(ctx, &s->d_coef, (size_t)s->N_pad * TC_NCMAX * sizeof(float)));
+  JP_CUDA(jp_dmalloc(ctx, &s->d_coef, (size_t)s->N_pad * TC_COEF_ROWS * sizeof(float)));
   JP_CUDA(jp_dmalloc(ctx, &s->d_sums, (size_t)(nE + 1) * 8));
   JP_CUDA(jp_dmalloc(ctx, &s->d_work, (size_t)s->glm_blocks * (nE + 1) * 8));
   JP_CUDA(jp_dmalloc(ctx, &s->d_bounds, (size_t)TC_PREP_BLOCKS * TC_NBOUND * 8));
@@ -918,24 +978,37 @@ static int ensure_post_state(jp_posterior* post, int kp) {
 }
 
 // Order / eligibility decision from the reduced bounds (see tc_obs_prep_kernel).  Returns NC in {4, 6, .. 12}
-// or 0 when the series is not trustworthy for this (data, U, grid) and the FP64 kernel must be used.
+// or 0 when the series is not trustworthy for this (data, U, grid) and the FP64 kernel must be used; *fold says
+// whether the economised coefficients (tc_fold_kernel) are to be used for that NC.
 //   * series convergence (rigorous): max_i |Delta_i| <= t_max z_max must stay well inside the radius pi
-//   * truncation (rigorous): tail summed over ALL observations <= 1e-9 at |z| = z_ref = min(z_max, 6) and
-//     <= 1e-4 at z_max (nodes beyond |z| = 6 carry < e^-9 of the peak density, so 1e-4 relative on them is
-//     < 1e-8 of the largest weight)
+//   * truncation (rigorous): error of the evaluated polynomial summed over ALL observations <= 2.5e-8 at
+//     |z| <= z_ref = min(z_max, 6) (40 x below the 1e-6 tolerance of this path) and <= 1e-4 up to z_max (nodes
+//     beyond |z| = 6 carry < e^-9 of the peak density, so 1e-4 relative on them is < 1e-8 of the largest weight).
+//     The economised series of NC coefficients is tried before the plain Taylor truncation of the same length.
 //   * rounding (statistical): FP32 Horner and the 3xTF32 contraction perturb each R_i by ~2e-6 |R_i| with
 //     pseudo-random sign, so the log-density error is ~2e-6 sqrt(sum_i R_i^2); a factor 8 of margin is
 //     required below 2e-7.  (The worst case with every error aligned, 2e-6 sum_i |R_i|, is reported too.)
-static int jp_tc_choose_order(const double* b, double* err_trunc, double* err_round) {
+#define TC_TRUNC_REF 2.5e-8
+#define TC_TRUNC_MAX 1e-4
+static int jp_tc_choose_order(const double* b, double* err_trunc, double* err_round, int* fold) {
   const double tdelta = b[0];
+  *fold = 0;
   if (!(tdelta <= 2.0)) return 0;
   *err_round = 2e-6 * std::sqrt(b[13]);
   if (!(8.0 * *err_round <= 2e-7)) return 0;
-  for (int j = 0; j < TC_NORD; ++j)
-    if (b[2 + j] <= 1e-9 && b[7 + j] <= 1e-4) {
+  static const bool no_fold = getenv("JP_TC_NO_FOLD") != nullptr;   // A/B aid: plain Taylor truncation only
+  for (int j = 0; j < TC_NORD; ++j) {
+    // 1 + 1e-5: t_i is stored rounded up to FP32 for the fold, the interval grows by <= 1.2e-7 relative
+    if (!no_fold && j < TC_NFOLD && b[14 + j] * (1 + 1e-5) <= TC_TRUNC_REF && b[14 + TC_NFOLD + j] * (1 + 1e-5) <= TC_TRUNC_MAX) {
+      *err_trunc = b[14 + j] * (1 + 1e-5);
+      *fold = 1;
+      return 2 * j + 4;
+    }
+    if (b[2 + j] <= TC_TRUNC_REF && b[7 + j] <= TC_TRUNC_MAX) {
       *err_trunc = b[2 + j];
       return 2 * j + 4;
     }
+  }
   return 0;
 }
 
@@ -996,13 +1069,18 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   }
   b[0] *= z_max;
   double err_trunc = 0, err_round = 0;
-  const int NC = jp_tc_choose_order(b, &err_trunc, &err_round);
+  int fold = 0;
+  const int NC = jp_tc_choose_order(b, &err_trunc, &err_round, &fold);
   post->tc_bounds[0] = b[0]; post->tc_bounds[1] = err_trunc; post->tc_bounds[2] = err_round; post->tc_bounds[3] = NC;
-  post->tc_bounds[4] = 2e-6 * b[12];
+  post->tc_bounds[4] = 2e-6 * b[12]; post->tc_bounds[5] = fold;
   if (NC == 0) {
     jp_set_error("tensor-core path: series bounds not met (max |Delta| %.3g, rounding estimate %.3g, truncation bounds %.3g/%.3g "
                  "at order 14); use the FP64 path", b[0], 2e-6 * std::sqrt(b[13]), b[6], b[11]);
     return JP_ERR_UNSUPPORTED;
+  }
+  if (fold) {
+    tc_fold_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(NC, ds->N_pad, z_ref, ds->d_coef);
+    JP_CHECK_LAUNCH(ctx);
   }
   // node operand, theta, FP64 quadratic part
   size_t sm_node = (size_t)(d + d * p + d + d * d + 64 + 128 * d) * 8;

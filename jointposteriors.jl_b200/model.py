@@ -373,7 +373,7 @@ class JointPosterior:
         out = np.zeros(8)
         check(lib().jp_fit_diagnostics(self.handle, ptr(out)))
         return dict(max_delta_eta=out[0], truncation_bound=out[1], rounding_estimate=out[2], series_terms=int(out[3]),
-                    rounding_worst_case=out[4])
+                    rounding_worst_case=out[4], economised=bool(out[5]))
 
     @property
     def Theta(self):
