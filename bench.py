@@ -224,7 +224,7 @@ def run_product(args):
     from jointposteriors_jl_b200.model import Context, JointPosterior
     from jointposteriors_jl_b200 import _lib
     peaks = load_peaks()
-    wl = make_workload(jp, args.workload, world)
+    wl = make_workload(jp, args.workload, max(world, args.emulate_shard))
     data = wl["data"]
     obs, hyper = data.records()
     d = wl["d"]
@@ -253,11 +253,13 @@ def run_product(args):
     t_grid = e0.elapsed_time(e1)
     Mtot = int(jp.lib().jp_grid_size(grid))
     b, e = D.shard_bounds(Mtot, rank, world)
+    if args.emulate_shard > 1:     # diagnostic: the local work of rank 0 of W ranks (its node block, W x the observations)
+        b, e = D.shard_bounds(Mtot, 0, args.emulate_shard)
     post = JointPosterior(M, dd, grid, x, U, neg_min, path=path, node_range=(b, e))
     loc = D.CudaLocal(post)
     coords = list(range(d))
     N = obs.shape[0]
-    pairs = float(Mtot) * float(N)
+    pairs = float(Mtot if args.emulate_shard <= 1 else e - b) * float(N)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # 256 MiB > 126 MB L2
 
     def step_device():
@@ -400,7 +402,8 @@ def run_product(args):
                    ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
                    dtype="tf32x3+f64" if path_used == _lib.PATH_TC else "f64", data="synthetic",
                    config=dict(workload=wl["desc"], nodes=Mtot, obs=int(N), d=d, level=wl["level"],
-                               parallelism="node-sharded x%d" % world, path="tc" if path_used == _lib.PATH_TC else "fp64",
+                               parallelism="node-sharded x%d" % world if args.emulate_shard <= 1 else
+                               "DIAGNOSTIC: node block of rank 0 of %d on one GPU" % args.emulate_shard, path="tc" if path_used == _lib.PATH_TC else "fp64",
                                l2="256 MiB flush buffer written between timed iterations",
                                marginals="%d coordinate marginals per step (moments + 100-knot Grid CDF)" % d),
                    fit_ms=tot_fit_ms / args.steps, marginal_ms=tot_marg_ms / args.steps, grid_build_ms=t_grid,
@@ -435,6 +438,8 @@ def main():
     ap.add_argument("--workload", default="cfg3")
     ap.add_argument("--path", default="auto", choices=["auto", "fp64", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emulate-shard", type=int, default=1,
+                    help="diagnostic (1 GPU): run the local work of rank 0 of W ranks, no collectives; not a bench line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

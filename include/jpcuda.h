@@ -89,6 +89,10 @@ int jp_inv_chol(double* h_U, const double* h_H, int d);
 /* reduce_dimensions!  reference src/joint_posterior.jl:98-110 (max_rank = 0) and :120-134
  * (FixedRank{p}: max_rank = p).  h_out is d x d storage; *rank receives the kept column count. */
 int jp_reduce_dimensions(const double* h_H, int d, int max_rank, double* h_out, int* rank);
+/* reduce_dimensions!(M, H, LDR{g})  reference src/joint_posterior.jl:78-95,111-119: the leading admissible
+ * eigen directions (largest 1/lambda first) that carry the fraction g in (0,1) of the total variance.  The
+ * reference's `count` uses `total_energy` uninitialised (:84); zero-initialised here. */
+int jp_reduce_dimensions_ldr(const double* h_H, int d, double g, double* h_out, int* rank);
 /* deduce_scale!(..., Dynamic)  reference src/joint_posterior.jl:136-138 : Cholesky if H is positive
  * definite, else the eigen fallback.  *rank receives p; h_U is d x p column-major in d x d storage. */
 int jp_deduce_scale_dynamic(const double* h_H, int d, double* h_U, int* rank);

@@ -43,7 +43,7 @@ class FitArgs(C.Structure):
 # every symbol include/jpcuda.h declares (tests check that the .so exports exactly these)
 SYMBOLS = [
     "jp_last_error", "jp_version",
-    "jp_chol", "jp_try_chol", "jp_inv_upper", "jp_inv_chol", "jp_reduce_dimensions", "jp_deduce_scale_dynamic",
+    "jp_chol", "jp_try_chol", "jp_inv_upper", "jp_inv_chol", "jp_reduce_dimensions", "jp_reduce_dimensions_ldr", "jp_deduce_scale_dynamic",
     "jp_ctx_create", "jp_ctx_destroy", "jp_ctx_set_stream", "jp_ctx_sync", "jp_ctx_launch_count",
     "jp_ctx_last_kernel_ms",
     "jp_grid_get", "jp_grid_size", "jp_grid_dim", "jp_grid_build_stats", "jp_grid_download", "jp_rule_info",

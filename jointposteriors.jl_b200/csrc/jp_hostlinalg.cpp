@@ -192,6 +192,42 @@ int jp_reduce_dimensions(const double* H, int d, int max_rank, double* out, int*
   return JP_OK;
 }
 
+// reduce_dimensions!(M, H, LDR{g}), reference src/joint_posterior.jl:78-95,111-119: keep the leading (largest
+// variance 1/lambda) admissible eigen directions until they carry the fraction g of the total variance.  The
+// reference's `count` reads `total_energy` before defining it (:84, an UndefVarError); it is initialised to zero here.
+int jp_reduce_dimensions_ldr(const double* H, int d, double g, double* out, int* rank) {
+  if (!H || !out || !rank || d < 1 || !(g > 0.0 && g < 1.0)) {     // @assert 0.0 < g < 1.0 (:79)
+    jp_set_error("jp_reduce_dimensions_ldr: bad argument (need 0 < g < 1)");
+    return JP_ERR_BAD_ARG;
+  }
+  std::vector<double> lambda, vec;
+  symmetric_eigen(H, d, lambda, vec);
+  std::memset(out, 0, sizeof(double) * d * d);
+  int inadmissible = 0;
+  for (int i = 0; i < d; ++i)
+    if (1.0 / lambda[i] >= 1e11 || !(lambda[i] > 0.0)) ++inadmissible;   // :81 (non-positive eigenvalues too)
+  double total = 0.0;
+  for (int i = inadmissible; i < d; ++i) total += 1.0 / lambda[i];       // :83-85
+  const double limit = g * total;
+  int p = 0;
+  double cum = 0.0;
+  while (cum < limit && inadmissible + p < d) {                          // :89-93
+    cum += 1.0 / lambda[inadmissible + p];
+    ++p;
+  }
+  for (int c = 0; c < p; ++c) {                                          // :115-117
+    const int i = inadmissible + c;
+    const double s = std::sqrt(lambda[i]);
+    for (int k = 0; k < d; ++k) out[(size_t)c * d + k] = vec[(size_t)i * d + k] / s;
+  }
+  *rank = p;
+  if (p == 0) {
+    jp_set_error("jp_reduce_dimensions_ldr: no admissible eigen direction");
+    return JP_ERR_NOT_PD;
+  }
+  return JP_OK;
+}
+
 int jp_deduce_scale_dynamic(const double* H, int d, double* U, int* rank) {
   if (!H || !U || !rank || d < 1) {
     jp_set_error("jp_deduce_scale_dynamic: bad argument");

@@ -59,6 +59,17 @@ def reduce_dimensions(H, max_rank=0):
     return np.asfortranarray(out[:, :r.value])
 
 
+def reduce_dimensions_ldr(H, g):
+    """reduce_dimensions!(M, H, LDR{g}): leading eigen directions carrying the fraction g of the variance
+    (reference src/joint_posterior.jl:78-95,111-119)."""
+    H = colmajor(H)
+    d = H.shape[0]
+    out = np.zeros((d, d), order="F")
+    r = C.c_int()
+    check(lib().jp_reduce_dimensions_ldr(ptr(H), C.c_int(d), C.c_double(float(g)), ptr(out), C.byref(r)))
+    return np.asfortranarray(out[:, :r.value])
+
+
 def deduce_scale_dynamic(H):
     """deduce_scale!(M, H, Dynamic): Cholesky when possible, else eigen fallback (reference :136-138)."""
     H = colmajor(H)

@@ -64,6 +64,16 @@ class FixedRank:
         self.p = int(p)
 
 
+class LDR:
+    """Keep the leading eigen directions that carry the fraction g of the posterior variance
+    (reference src/joint_posterior.jl:78-95,111-119)."""
+
+    def __init__(self, g):
+        self.g = float(g)
+        if not 0.0 < self.g < 1.0:
+            raise ValueError("LDR: need 0 < g < 1")       # @assert, reference :79
+
+
 def default(build=None):
     """Default Smolyak level `default(B)` (reference src/joint_posterior.jl:177); the value lives in the
     absent SparseQuadratureGrids package -- 5 here, the level SURVEY/BASELINE quote configs on."""
@@ -299,6 +309,8 @@ def deduce_scale(M, H):
         return linalg.inv_chol(H)
     if isinstance(R, FixedRank):
         return linalg.reduce_dimensions(H, R.p)
+    if isinstance(R, LDR):
+        return linalg.reduce_dimensions_ldr(H, R.g)
     return linalg.deduce_scale_dynamic(H)
 
 

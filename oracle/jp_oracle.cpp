@@ -162,6 +162,36 @@ int orc_reduce_dimensions(const double* H, int d, int max_rank, double* out) {
   return g0;
 }
 
+// reference src/joint_posterior.jl:78-95 (count, LDR{g}) and :111-119 (reduce_dimensions!, LDR): with the
+// eigenvalues ascending, skip the inadmissible ones (1/lambda >= 1e11), then keep leading directions until their
+// cumulative 1/lambda reaches g x the admissible total.  `total_energy` is undefined at :84 in the reference
+// (latent UndefVarError); its evident initial value 0 is used.  Returns p; out is d x p column-major.
+int orc_reduce_dimensions_ldr(const double* H, int d, double g, double* out) {
+  std::vector<double> val, V;
+  jacobi_eig(H, d, val, V);
+  std::vector<double> inv_v(d);
+  int inadmissible = 0;
+  for (int i = 0; i < d; ++i) {
+    inv_v[i] = 1.0 / val[i];                                   // :80
+    if (inv_v[i] >= 1e11 || !(val[i] > 0.0)) ++inadmissible;   // :81
+  }
+  int ind_start = inadmissible;                                // :82 (0-based)
+  double total_energy = 0.0;
+  for (int i = ind_start; i < d; ++i) total_energy += inv_v[i];   // :83-85
+  double limit = g * total_energy, cumulative = 0.0;              // :86
+  int p = 0;
+  while (cumulative < limit && ind_start < d) {                   // :89-93
+    ++p;
+    cumulative += inv_v[ind_start];
+    ++ind_start;
+  }
+  for (int g0 = 0; g0 < p; ++g0) {                                // :115-117
+    int i = inadmissible + g0;
+    for (int k = 0; k < d; ++k) A_(out, k, g0, d) = A_(V, k, i, d) / std::sqrt(val[i]);
+  }
+  return p;
+}
+
 // reference src/joint_posterior.jl:136-138 (deduce_scale!, Dynamic): Cholesky when H is
 // positive definite, else the eigen fallback.  (`safe_inv_chol!` at :69-71 calls an undefined
 // `try_inv!`; the evident intent -- try_chol! then inv! -- is what is restated.)

@@ -98,6 +98,14 @@ def reduce_dimensions(H, max_rank=0):
     return np.asfortranarray(out[:, :p])
 
 
+def reduce_dimensions_ldr(H, g):
+    H = _colmajor(H)
+    d = H.shape[0]
+    out = np.zeros((d, d), order="F")
+    p = lib().orc_reduce_dimensions_ldr(_ptr(H), C.c_int(d), C.c_double(g), _ptr(out))
+    return np.asfortranarray(out[:, :p])
+
+
 def deduce_scale_dynamic(H):
     H = _colmajor(H)
     d = H.shape[0]

@@ -87,6 +87,11 @@ def test_reduce_dimensions_matches_oracle(jp, O):
         assert np.allclose(G @ G.T, Go @ Go.T, atol=1e-11)
     U = jp.deduce_scale_dynamic(H)
     assert U.shape == (6, 4)
+    for g in (0.5, 0.9, 0.97, 0.999):       # LDR{g}
+        G, Go = jp.reduce_dimensions_ldr(H, g), O.reduce_dimensions_ldr(H, g)
+        assert G.shape == Go.shape and np.allclose(G @ G.T, Go @ Go.T, atol=1e-11)
+    with pytest.raises(jp.JPError):
+        jp.reduce_dimensions_ldr(H, 1.5)
 
 
 def test_quantile_cdf_bit_exact_with_oracle(jp, O):

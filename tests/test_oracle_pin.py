@@ -150,6 +150,13 @@ def test_reduce_dimensions(O):
     assert O.reduce_dimensions(H, 2).shape == (5, 2)
     U = O.deduce_scale_dynamic(H)
     assert U.shape == (5, 3)
+    # LDR{g} (reference :78-95,111-119): variances 1/lambda of the admissible directions are 2, .5, 1/9 (total 2.611);
+    # g = 0.7 is reached by the first (2 / 2.611 = 0.766), g = 0.9 needs two, g = 0.99 all three
+    for g, p in ((0.7, 1), (0.9, 2), (0.99, 3)):
+        G = O.reduce_dimensions_ldr(H, g)
+        assert G.shape == (5, p)
+        kp = Q[:, 2:2 + p]
+        assert np.allclose(G @ G.T, (kp / lam[2:2 + p]) @ kp.T, atol=1e-10)
     Hpd = _spd(rng, 4)
     assert np.array_equal(O.deduce_scale_dynamic(Hpd), O.inv_chol(Hpd))
 
