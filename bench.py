@@ -285,8 +285,13 @@ def run_product(args):
     if rank == 0:
         sampler.start()
     fit_ms, marg_ms, step_ms, kern_in_step = [], [], [], []
+    tok = torch.zeros(1, device=dev)
     for _ in range(args.steps):
         flush.zero_()                      # evict the working set from L2 between timed iterations
+        if world > 1:
+            # line the ranks up before each timed step: without it a step's first collective also waits for the
+            # slowest rank's untimed flush / host bookkeeping, which is not part of the step
+            dist.all_reduce(tok)
         torch.cuda.synchronize(dev)
         a, bq, c = ev(), ev(), ev()
         a.record(stream)
@@ -360,7 +365,9 @@ def run_product(args):
     hdata._obs = obs_pinned.numpy()
 
     def step_e2e():
-        dde = ctx.upload(hdata)                                   # H2D of the observation records
+        # H2D of the observation records; with several ranks each uploads its 1/world row slice over PCIe and the
+        # slices are exchanged GPU->GPU (one NCCL all_gather over NVLink)
+        dde = ctx.upload(hdata) if world == 1 else ctx.upload_sharded(hdata)
         pe = JointPosterior(M, dde, grid, x, U, neg_min, path=path, node_range=(b, e))
         if world == 1:
             pe.evaluate()
@@ -392,7 +399,8 @@ def run_product(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.cpu()[0]) / args.steps
-    h2d = int(obs.nbytes + 8 * (d + d * U.shape[1]) + 4 * d)
+    rb, re_, _ = D.row_slice(obs.shape[0], rank, world)
+    h2d = int((re_ - rb) * obs.shape[1] * 8 + 8 * (d + d * U.shape[1]) + 4 * d)     # this rank's bytes (largest slice on rank 0)
     d2h = int(8 * (e - b) + d * 8 * (2 + 200))
     e2e = dict(value=pairs / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms)
 

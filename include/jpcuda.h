@@ -139,6 +139,11 @@ int jp_rule_info(int rule, int* levels, int* nmax, int* h_npts, double* h_nodes,
  *   NORMAL_LINEAR    (x_0..x_{p-1}, y)         hyper = (sd of beta prior, sd of sigma prior) */
 int jp_data_upload(jp_ctx* ctx, int family, long long N, int ncols, const double* h_obs, const double* h_hyper,
                    int n_hyper, jp_data** out);
+/* Same, for records that are ALREADY in the memory of ctx's GPU (e.g. row slices uploaded by each rank of a box and
+ * all-gathered over NVLink, SURVEY 8(e): "X broadcast GPU->GPU once per dataset").  The buffer is borrowed: it must
+ * stay valid until jp_data_free, work on it must be ordered on ctx's stream, and the library never frees it. */
+int jp_data_adopt_device(jp_ctx* ctx, int family, long long N, int ncols, const double* d_obs, const double* h_hyper,
+                         int n_hyper, jp_data** out);
 int jp_data_free(jp_data* data);
 
 /* GLM score and observed information at beta on the GPU (mode finding, upstream of the five

@@ -181,11 +181,35 @@ int jp_data_upload(jp_ctx* ctx, int family, long long N, int ncols, const double
   return JP_OK;
 }
 
+int jp_data_adopt_device(jp_ctx* ctx, int family, long long N, int ncols, const double* d_obs, const double* h_hyper,
+                         int n_hyper, jp_data** out) {
+  JP_REQUIRE(ctx && d_obs && out, "jp_data_adopt_device: null argument");
+  JP_REQUIRE(N >= 1 && ncols >= 1, "jp_data_adopt_device: empty data (N=%lld, ncols=%d)", N, ncols);
+  JP_REQUIRE(n_hyper >= 0 && n_hyper <= JP_MAX_HYPER, "jp_data_adopt_device: n_hyper=%d out of range", n_hyper);
+  JP_REQUIRE(jp_find_family(family) != nullptr, "jp_data_adopt_device: family %d is not registered", family);
+  cudaPointerAttributes attr;
+  JP_CUDA(cudaSetDevice(ctx->device));
+  cudaError_t e = cudaPointerGetAttributes(&attr, d_obs);
+  if (e != cudaSuccess || attr.type != cudaMemoryTypeDevice || attr.device != ctx->device) {
+    cudaGetLastError();
+    jp_set_error("jp_data_adopt_device: d_obs is not device memory of GPU %d", ctx->device);
+    return JP_ERR_BAD_ARG;
+  }
+  jp_data* dt = new (std::nothrow) jp_data();
+  if (!dt) return JP_ERR_ALLOC;
+  dt->ctx = ctx; dt->family = family; dt->N = N; dt->ncols = ncols; dt->n_hyper = n_hyper;
+  for (int i = 0; i < n_hyper; ++i) dt->hyper[i] = h_hyper[i];
+  dt->d_obs = const_cast<double*>(d_obs);
+  dt->owns_obs = false;
+  *out = dt;
+  return JP_OK;
+}
+
 int jp_data_free(jp_data* data) {
   if (!data) return JP_OK;
   cudaSetDevice(data->ctx->device);
   jp_tc_data_free(data);
-  jp_dfree(data->ctx, data->d_obs);
+  if (data->owns_obs) jp_dfree(data->ctx, data->d_obs);
   delete data;
   return JP_OK;
 }

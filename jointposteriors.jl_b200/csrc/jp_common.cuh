@@ -100,6 +100,7 @@ struct jp_data {
   long long N = 0;
   int ncols = 0;
   double* d_obs = nullptr;      // N x ncols row-major
+  bool owns_obs = true;         // false: d_obs belongs to the caller (jp_data_adopt_device)
   double hyper[JP_MAX_HYPER] = {0};
   int n_hyper = 0;
   void* tc_state = nullptr;     // per-data state of the GLM tensor-core path (jp_glm_tc.cu): the operand

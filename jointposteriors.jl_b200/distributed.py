@@ -50,6 +50,40 @@ def _all_gather(t, group):
     return out
 
 
+def row_slice(N, rank, world):
+    """Rows [begin, end) that `rank` uploads; every rank's slot holds ceil(N / world) rows (the last may be short)."""
+    n_loc = -(-int(N) // int(world))
+    return min(N, rank * n_loc), min(N, (rank + 1) * n_loc), n_loc
+
+
+def gather_rows(obs, device, group=None, gather=None, rank=None, world=None):
+    """All N x ncols records on `device`, this rank having copied only its own row slice from the host.
+
+    obs: the host array [N, ncols] (every rank can name all of it -- the generators are counter-based -- but only
+    obs[begin:end] is read here).  One all_gather_into_tensor moves the slices GPU->GPU (NCCL over NVLink on CUDA,
+    gloo in the CPU tests).  Returns a [world * n_loc, ncols] tensor whose first N rows are the records."""
+    import torch
+    import torch.distributed as dist
+    if world is None:
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank(group) if world > 1 else 0
+    N, ncols = obs.shape
+    b, e, n_loc = row_slice(N, rank, world)
+    mine = torch.empty((n_loc, ncols), dtype=torch.float64, device=device)
+    host = torch.from_numpy(obs[b:e]) if not isinstance(obs, torch.Tensor) else obs[b:e]
+    mine[:e - b].copy_(host, non_blocking=True)
+    if e - b < n_loc:
+        mine[e - b:].zero_()       # padding rows of a short last slice (never read: N bounds every kernel)
+    if world == 1:
+        return mine
+    if gather is not None:
+        return gather(mine, group).reshape(world * n_loc, ncols)
+    full = torch.empty((world * n_loc, ncols), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(full.view(-1), mine.view(-1), group=group)
+    return full
+
+
 def reference_knot_values(gathered, vmin, vmax):
     """The 100 value knots [K, 100]: end knots are the global extrema, interior knots are the values the
     device computed (slot 5 of every rank's candidates; all ranks derive them from the same (min, max))."""

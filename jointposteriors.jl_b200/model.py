@@ -123,17 +123,34 @@ class Context:
     def upload(self, data):
         return DeviceData(self, data)
 
+    def upload_sharded(self, data, group=None):
+        """Every rank of the box ends up with ALL observation records, but each uploads only its 1/world row slice
+        over PCIe; the slices are exchanged GPU->GPU by one all_gather (NCCL over NVLink).  See distributed.gather_rows."""
+        from . import distributed as D
+        import torch
+        obs, hyper = data.records()
+        dev = torch.device("cuda", self.device)
+        full = D.gather_rows(obs, dev, group)
+        return DeviceData(self, data, device_obs=full)
+
 
 class DeviceData:
     """Observations resident on the GPU (jp_data)."""
 
-    def __init__(self, ctx, data):
+    def __init__(self, ctx, data, device_obs=None):
         obs, hyper = data.records()
         obs = f64(obs)
         hyper = f64(hyper)
         h = C.c_void_p()
-        check(lib().jp_data_upload(ctx.handle, C.c_int(data.family), C.c_longlong(obs.shape[0]), C.c_int(obs.shape[1]),
-                                   ptr(obs), ptr(hyper), C.c_int(len(hyper)), C.byref(h)))
+        if device_obs is None:
+            check(lib().jp_data_upload(ctx.handle, C.c_int(data.family), C.c_longlong(obs.shape[0]), C.c_int(obs.shape[1]),
+                                       ptr(obs), ptr(hyper), C.c_int(len(hyper)), C.byref(h)))
+        else:
+            # a torch CUDA tensor holding (at least) the N x ncols records, borrowed by the library: keep it alive
+            self._device_obs = device_obs
+            check(lib().jp_data_adopt_device(ctx.handle, C.c_int(data.family), C.c_longlong(obs.shape[0]),
+                                             C.c_int(obs.shape[1]), C.c_void_p(device_obs.data_ptr()), ptr(hyper),
+                                             C.c_int(len(hyper)), C.byref(h)))
         self.ctx, self.handle, self.family = ctx, h, data.family
         self.N, self.ncols = obs.shape
         self.nbytes = obs.nbytes

@@ -88,7 +88,11 @@ def _worker(rank, world, port, a, w, values, q):
     loc = NumpyLocal(a[b:e], w[b:e], [v[b:e] for v in values], b, D)
     D.fit_sharded(loc)
     mu, sg, vn, wn = D.marginals_sharded(loc, list(range(len(values))))
-    q.put((rank, b, e, loc.density, mu, sg, vn, wn))
+    # row-sliced upload + all_gather (Context.upload_sharded): ragged N, every rank reassembles all records
+    obs = np.arange(float(1003 * 4)).reshape(1003, 4)
+    full = D.gather_rows(obs, torch.device("cpu"))
+    rows_ok = bool(full.shape[0] >= 1003 and np.array_equal(full[:1003].numpy(), obs))
+    q.put((rank, b, e, loc.density, mu, sg, vn, wn, rows_ok))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -116,19 +120,29 @@ def test_sharded_combine_matches_oracle(O, jp, world):
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
+    assert all(r[8] for r in res)
     dens = np.concatenate([r[3] for r in res])
     e = w * np.exp(a - a.max())
     assert np.allclose(dens, e / e.sum(), rtol=1e-13, atol=0)
     for r in res[1:]:                      # every rank holds bit-identical results
-        for x, y in zip(r[4:], res[0][4:]):
+        for x, y in zip(r[4:8], res[0][4:8]):
             assert np.array_equal(x, y, equal_nan=True)
-    _, _, _, _, mu, sg, vn, wn = res[0]
+    _, _, _, _, mu, sg, vn, wn, _ = res[0]
     for k, v in enumerate(values):
         m = O.marginal(v, dens)
         assert np.isclose(mu[k], m["mu"], rtol=1e-11, atol=1e-13)
         assert np.isclose(sg[k], m["sigma"], rtol=1e-10, equal_nan=True)
         assert np.allclose(vn[k], m["value_nodes"], rtol=1e-15, atol=1e-15)
         assert np.allclose(wn[k], m["weight_nodes"], rtol=1e-10, atol=1e-12), np.max(np.abs(wn[k] - m["weight_nodes"]))
+
+
+def test_row_slices(jp):
+    from jointposteriors_jl_b200.distributed import row_slice
+    for N, W in [(10, 3), (1003, 8), (8, 8), (5, 8), (100000, 1)]:
+        cuts = [row_slice(N, r, W) for r in range(W)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == N
+        assert all(cuts[i][1] == cuts[i + 1][0] for i in range(W - 1))
+        assert all(e - b <= n for b, e, n in cuts) and len({n for _, _, n in cuts}) == 1
 
 
 def test_shard_bounds(jp):

@@ -204,6 +204,30 @@ def test_gpu_mode_matches_cpu_mode(jp, O, gpu_ctx):
     assert np.allclose(x, xc, atol=1e-5) and abs(neg_min - fc) < 1e-8
 
 
+def test_adopted_device_records(jp, O, gpu_ctx):
+    """jp_data_adopt_device: records already on the GPU (what Context.upload_sharded builds from the NVLink all_gather)
+    give bit-identical results to jp_data_upload of the same host array; host pointers are refused."""
+    import torch
+    from jointposteriors_jl_b200.model import DeviceData
+    from jointposteriors_jl_b200 import distributed as D
+    name, family, code, obs, hyper = FAMILY_CASES[1]
+    data = _RawData(family, obs, hyper)
+    obs, hyper = data.records()
+    x, H, neg_min = _cpu_mode_for(O, family, code, obs, hyper)
+    U = O.inv_chol(2.0 * H)
+    M = _model_for(jp, code)
+    a = jp.fit(M, _upload(jp, gpu_ctx, family, obs, hyper), 4, path=jp.PATH_FP64, mode_result=(x, U, neg_min))
+    full = D.gather_rows(obs, torch.device("cuda", gpu_ctx.device), world=1, rank=0)
+    torch.cuda.synchronize()
+    dd = DeviceData(gpu_ctx, data, device_obs=full)
+    b = jp.fit(M, dd, 4, path=jp.PATH_FP64, mode_result=(x, U, neg_min))
+    assert np.array_equal(a.density, b.density) and np.array_equal(a.logdens, b.logdens)
+    h = C.c_void_p()
+    st = jp.lib().jp_data_adopt_device(gpu_ctx.handle, family, obs.shape[0], obs.shape[1], obs.ctypes.data_as(C.c_void_p),
+                                       hyper.ctypes.data_as(C.c_void_p), len(hyper), C.byref(h))
+    assert st == 1          # JP_ERR_BAD_ARG: a host pointer
+
+
 def test_glm_grad_hess(jp, O, gpu_ctx):
     for case in (1, 2):
         name, family, code, obs, hyper = FAMILY_CASES[case]
