@@ -384,14 +384,20 @@ def run_product(args):
         dde.free()
         return out
 
-    for _ in range(max(1, min(args.warmup, 3))):
+    # host-side transients (glibc raising its mmap threshold for the freshly allocated result arrays, the stream-ordered
+    # pool settling) decay over the first ~8 calls; the steady state is what is timed
+    e2e_warmup = max(args.warmup, 8)
+    for _ in range(e2e_warmup):
         step_e2e()
     barrier()
     a, c = ev(), ev()
     a.record(stream)
     t0 = time.perf_counter()
+    per_step = []
     for _ in range(args.steps):
-        step_e2e()
+        ts = time.perf_counter()
+        step_e2e()                      # ends with blocking D2H copies: the host clock sees the whole step
+        per_step.append((time.perf_counter() - ts) * 1e3)
     c.record(stream)
     barrier()
     e2e_wall = (time.perf_counter() - t0) * 1e3
@@ -402,7 +408,8 @@ def run_product(args):
     rb, re_, _ = D.row_slice(obs.shape[0], rank, world)
     h2d = int((re_ - rb) * obs.shape[1] * 8 + 8 * (d + d * U.shape[1]) + 4 * d)     # this rank's bytes (largest slice on rank 0)
     d2h = int(8 * (e - b) + d * 8 * (2 + 200))
-    e2e = dict(value=pairs / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms)
+    e2e = dict(value=pairs / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms,
+               warmup=e2e_warmup, per_step_ms=[round(v, 3) for v in per_step])
 
     if rank == 0:
         cpu = cpu_baseline(wl, (x, U, neg_min)) if world == 1 and not args.no_cpu_baseline else None
