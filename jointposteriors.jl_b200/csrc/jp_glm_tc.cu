@@ -27,7 +27,11 @@
 //               (thread = observation lane, column = node) in FP32 registers over all observation tiles of
 //               the item; per item one shuffle transpose-reduce + shared-memory combine in FP64.
 // 3xTF32: operand rows are [x_hi | x_lo | x_hi] and [d_hi | d_hi | d_lo] (TF32-representable FP32), so one
-// K = 3d contraction gives x_hi d_hi + x_lo d_hi + x_hi d_lo with FP32 accumulation in TMEM.
+// K = 3d contraction gives x_hi d_hi + x_lo d_hi + x_hi d_lo with FP32 accumulation in TMEM.  When that needs three
+// 128-byte K atoms (21 < d <= 32) the SPLIT layout is used instead: observation rows [x_hi | x_lo] with each part
+// padded to its own atom, pair rows [d_hi | d_hi | d_lo] likewise, and the third product re-reads the observation
+// row's FIRST atom from shared memory -- the streamed operand (the kernel is bound by L2 -> SM traffic of the
+// observation tiles there) shrinks by a third, the contraction is unchanged.
 #include <cuda.h>
 #include <algorithm>
 #include <cmath>
@@ -71,7 +75,8 @@ __constant__ double c_fold_eps[2][TC_NFOLD];
 __constant__ double c_fold_grow[2][TC_NFOLD];
 
 struct TcDataState {
-  int d = 0, kp = 0, ka = 0;
+  int d = 0, kp = 0, ka = 0;   // observation operand: row length (floats) and 128-byte atoms per row
+  int split = 0, kp_b = 0;     // split layout (see header) and the pair operand's row length
   long long N = 0, N_pad = 0;
   float* d_xs = nullptr;       // [N_pad][kp]  (x_hi | x_lo | x_hi | 0)
   float* d_coef = nullptr;     // [TC_COEF_ROWS][N_pad]: coefficient k of every observation, contiguous per 128-observation tile; last row t_i
@@ -223,20 +228,30 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // slab, so the stores of the [N_pad][kp] operand are coalesced, the three reads of a record hit L1, and no thread
 // divides.
 #define TC_SPLIT_ROWS 8
-__global__ void tc_split_x_kernel(int d, int ncols, int kp, long long N, long long N_pad, const double* __restrict__ obs,
-                                  float* __restrict__ xs) {
+#define TC_SPLIT_UNROLL 4        // independent record loads in flight per thread (Little: ~800 ns x 6.4 TB/s / 148 SMs)
+__global__ void tc_split_x_kernel(int d, int ncols, int kp, int split, long long N, long long N_pad,
+                                  const double* __restrict__ obs, float* __restrict__ xs) {
   const int c = threadIdx.x;                     // 0 .. kp - 1
-  const int part = (c >= 2 * d) ? 2 : (c >= d ? 1 : 0);
-  const int k = c - part * d;
-  const bool live = c < 3 * d;
-  for (long long i = (long long)blockIdx.x * TC_SPLIT_ROWS + threadIdx.y; i < N_pad; i += (long long)gridDim.x * TC_SPLIT_ROWS) {
-    float v = 0.f;
-    if (live && i < N) {
-      float hi, lo;
-      tf32_split(__ldg(obs + (size_t)i * ncols + k), hi, lo);
-      v = (part == 1) ? lo : hi;
+  // compact: [x_hi | x_lo | x_hi] back to back; split: x_hi in atom 0, x_lo in atom 1
+  const int part = split ? (c / TC_KATOM) : ((c >= 2 * d) ? 2 : (c >= d ? 1 : 0));
+  const int k = split ? (c % TC_KATOM) : (c - part * d);
+  const bool live = split ? (k < d) : (c < 3 * d);
+  const long long step = (long long)gridDim.x * TC_SPLIT_ROWS;
+  for (long long i0 = (long long)blockIdx.x * TC_SPLIT_ROWS + threadIdx.y; i0 < N_pad; i0 += step * TC_SPLIT_UNROLL) {
+    double x[TC_SPLIT_UNROLL];
+#pragma unroll
+    for (int u = 0; u < TC_SPLIT_UNROLL; ++u) {
+      const long long i = i0 + u * step;
+      x[u] = (live && i < N) ? __ldg(obs + (size_t)i * ncols + k) : 0.0;
     }
-    xs[(size_t)i * kp + c] = v;
+#pragma unroll
+    for (int u = 0; u < TC_SPLIT_UNROLL; ++u) {
+      const long long i = i0 + u * step;
+      if (i >= N_pad) break;
+      float hi, lo;
+      tf32_split(x[u], hi, lo);
+      xs[(size_t)i * kp + c] = (part == 1) ? lo : hi;      // rows past N and the padding columns are zero: split(0) = (0, 0)
+    }
   }
 }
 
@@ -423,7 +438,7 @@ tc_fold_kernel(int NC, long long N_pad, double z_ref, float* __restrict__ coef) 
 // thread -- or, when the local range starts on a second member, by its thread with the sign flipped
 // (delta(-z) = -delta(z) exactly: the sums below are sign-symmetric in IEEE arithmetic, and so is the TF32 split).
 __global__ void __launch_bounds__(128)
-tc_node_prep_kernel(int d, int p, int kp, int rule, long long M, long long m0, long long M_grid, long long j_lo,
+tc_node_prep_kernel(int d, int p, int kp, int seg, int rule, long long M, long long m0, long long M_grid, long long j_lo,
                     const uint8_t* __restrict__ idx, const double* __restrict__ znodes, const double* __restrict__ mu,
                     const double* __restrict__ U, const double* __restrict__ sums, double prior_sd,
                     double* __restrict__ theta, double* __restrict__ quad, float* __restrict__ ds) {
@@ -477,9 +492,9 @@ tc_node_prep_kernel(int d, int p, int kp, int rule, long long M, long long m0, l
     if (writes_row) {
       float hi, lo;
       tf32_split(dk, hi, lo);
-      o[k] = sgn * hi;
-      o[d + k] = sgn * hi;
-      o[2 * d + k] = sgn * lo;
+      o[k] = sgn * hi;              // seg = d (compact rows) or one K atom (split rows)
+      o[seg + k] = sgn * hi;
+      o[2 * seg + k] = sgn * lo;
     }
   }
   quad[m] = (L_hat + lin - 0.5 * qf) + prior;
@@ -507,7 +522,8 @@ __global__ void tc_finish_kernel(long long M, long long m0, long long j_lo, long
 
 // ------------------------------------------------------------------------------------ the tensor-core kernel
 struct TcKernelParams {
-  int ka;                 // 128-byte K atoms per operand row
+  int ka;                 // 128-byte K atoms per observation operand row
+  int kb;                 // ... per pair operand row (= products of one contraction); kb > ka: split layout
   int stages;             // observation-tile ring depth
   int nbbuf;              // pair-operand buffers (2: the next item's operand loads under the current item)
   int n_pair_tiles;
@@ -602,7 +618,7 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // carve-up (1024-byte aligned for the 128-byte swizzle): pair operands, observation ring, reduction buffer, barriers
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sB = base;                                              // nbbuf x ka x (96 x 128 B)
-  const uint32_t b_bytes = (uint32_t)P.ka * TC_PAIR_TILE * 128u;
+  const uint32_t b_bytes = (uint32_t)P.kb * TC_PAIR_TILE * 128u;
   const uint32_t sA = sB + (uint32_t)P.nbbuf * b_bytes;                  // stages x ka x (128 x 128 B)
   const uint32_t a_bytes = (uint32_t)P.ka * TC_OBS_TILE * 128u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -665,7 +681,7 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
         mbar_wait_relaxed(bar_bempty + 8u * bb, ((bphase >> bb) & 1u) ^ 1u);
         mbar_expect_tx(bar_bfull + 8u * bb, b_bytes);
-        for (int a = 0; a < P.ka; ++a)
+        for (int a = 0; a < P.kb; ++a)
           tma_load_2d(sB + (uint32_t)bb * b_bytes + (uint32_t)a * TC_PAIR_TILE * 128u, &tmB, bar_bfull + 8u * bb,
                       a * TC_KATOM, pair_tile * TC_PAIR_TILE);
         bphase ^= 1u << bb;
@@ -702,8 +718,10 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait_relaxed(bar_full + 8u * stage, phase);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC_TMEM_STRIDE;
-          for (int a = 0; a < P.ka; ++a) {
-            const uint32_t aA = sA + (uint32_t)stage * a_bytes + (uint32_t)a * TC_OBS_TILE * 128u;
+          for (int a = 0; a < P.kb; ++a) {
+            // split layout: the last product (x_hi . d_lo) takes the observation row's first atom again
+            const int a_obs = (a < P.ka) ? a : 0;
+            const uint32_t aA = sA + (uint32_t)stage * a_bytes + (uint32_t)a_obs * TC_OBS_TILE * 128u;
             const uint32_t aB = sB + (uint32_t)bb * b_bytes + (uint32_t)a * TC_PAIR_TILE * 128u;
 #pragma unroll
             for (int j = 0; j < 4; ++j)   // K = 8 tf32 = 32 bytes per instruction inside the 128-byte atom
@@ -942,8 +960,10 @@ static int ensure_data_state(jp_ctx* ctx, jp_data* data, int d) {
   TcDataState* s = new TcDataState();
   data->tc_state = s;
   s->d = d;
-  s->kp = ((3 * d + TC_KATOM - 1) / TC_KATOM) * TC_KATOM;
+  s->split = (3 * d > 2 * TC_KATOM) ? 1 : 0;     // three atoms compact -> two atoms split (d <= TC_KATOM is checked)
+  s->kp = s->split ? 2 * TC_KATOM : ((3 * d + TC_KATOM - 1) / TC_KATOM) * TC_KATOM;
   s->ka = s->kp / TC_KATOM;
+  s->kp_b = s->split ? 3 * TC_KATOM : s->kp;
   s->N = data->N;
   s->N_pad = ((data->N + TC_OBS_TILE - 1) / TC_OBS_TILE) * TC_OBS_TILE;
   const int nE = d + d * (d + 1) / 2;
@@ -954,7 +974,7 @@ static int ensure_data_state(jp_ctx* ctx, jp_data* data, int d) {
   JP_CUDA(jp_dmalloc(ctx, &s->d_work, (size_t)s->glm_blocks * (nE + 1) * 8));
   JP_CUDA(jp_dmalloc(ctx, &s->d_bounds, (size_t)TC_PREP_BLOCKS * TC_NBOUND * 8));
   const unsigned split_blocks = (unsigned)std::min<long long>((s->N_pad + TC_SPLIT_ROWS - 1) / TC_SPLIT_ROWS, (long long)ctx->sm_count * 32);
-  tc_split_x_kernel<<<split_blocks, dim3(s->kp, TC_SPLIT_ROWS), 0, ctx->stream>>>(d, data->ncols, s->kp, s->N, s->N_pad,
+  tc_split_x_kernel<<<split_blocks, dim3(s->kp, TC_SPLIT_ROWS), 0, ctx->stream>>>(d, data->ncols, s->kp, s->split, s->N, s->N_pad,
                                                                                   data->d_obs, s->d_xs);
   JP_CHECK_LAUNCH(ctx);
   JP_TRY(make_tensor_map(&s->tmA, s->d_xs, s->N_pad, s->kp, TC_OBS_TILE));
@@ -1044,7 +1064,7 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   JP_TRY(ensure_data_state(ctx, data, d));
   TcDataState* ds = static_cast<TcDataState*>(data->tc_state);
   JP_REQUIRE(ds->d == d, "tensor-core path: data was prepared for d=%d", ds->d);
-  JP_TRY(ensure_post_state(post, ds->kp));
+  JP_TRY(ensure_post_state(post, ds->kp_b));
   TcPostState* ps = static_cast<TcPostState*>(post->tc_state);
   JP_TRY(jp_upload_fit_consts(post, args));
   cudaStream_t st = ctx->stream;
@@ -1087,16 +1107,17 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   if (sm_node > 48 * 1024)
     JP_CUDA(cudaFuncSetAttribute(tc_node_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_node));
   tc_node_prep_kernel<<<(unsigned)((post->M + 127) / 128), 128, sm_node, st>>>(
-      d, p, ds->kp, post->grid->rule, post->M, post->m0, post->grid->M, ps->j_lo, post->grid->d_idx,
+      d, p, ds->kp_b, ds->split ? TC_KATOM : d, post->grid->rule, post->M, post->m0, post->grid->M, ps->j_lo, post->grid->d_idx,
       jp_rule_nodes_dev(post->grid->rule), post->d_mu, post->d_U, ds->d_sums, data->hyper[0], post->d_theta, ps->d_quad,
       ps->d_ds);
   JP_CHECK_LAUNCH(ctx);
   // work decomposition: node tiles x observation chunks on a persistent grid
   TcKernelParams kp;
   kp.ka = ds->ka;
+  kp.kb = ds->kp_b / TC_KATOM;
   kp.n_pair_tiles = (int)(ps->P_pad / TC_PAIR_TILE);
   kp.n_obs_tiles = (int)(ds->N_pad / TC_OBS_TILE);
-  const size_t b_bytes = (size_t)kp.ka * TC_PAIR_TILE * 128, a_bytes = (size_t)kp.ka * TC_OBS_TILE * 128;
+  const size_t b_bytes = (size_t)kp.kb * TC_PAIR_TILE * 128, a_bytes = (size_t)kp.ka * TC_OBS_TILE * 128;
   const size_t c_bytes = (size_t)NC * TC_OBS_TILE * 4;      // coefficient slot of one tile
   const size_t budget = 220 * 1024, misc = 1024 + 4 * TC_PAIR_TILE * 2 * 8 + 256 + TC_NBUF * c_bytes;
   // two pair-operand buffers unless that would push the observation ring below three stages

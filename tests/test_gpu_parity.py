@@ -456,8 +456,10 @@ def _glm_case(kind, seed, N, d, xscale=1.0):
 
 @pytest.mark.parametrize("kind,N,d,level,xscale", [("logistic", 50000, 6, 4, 1.0), ("poisson", 60000, 5, 4, 0.3),
                                                    ("logistic", 40000, 10, 4, 1.0), ("poisson", 100000, 20, 3, 0.3),
-                                                   ("logistic", 200000, 30, 3, 1.0), ("logistic", 30001, 3, 6, 1.0)],
-                         ids=["logit-d6", "pois-d5", "logit-d10", "pois-d20-2atoms", "logit-d30-3atoms", "logit-d3-ragged"])
+                                                   ("logistic", 200000, 30, 3, 1.0), ("logistic", 30001, 3, 6, 1.0),
+                                                   ("logistic", 60000, 22, 3, 1.0), ("poisson", 80000, 32, 3, 0.2)],
+                         ids=["logit-d6", "pois-d5", "logit-d10", "pois-d20-2atoms", "logit-d30-split", "logit-d3-ragged",
+                              "logit-d22-split", "pois-d32-split"])
 def test_tc_path_matches_oracle(jp, O, gpu_ctx, kind, N, d, level, xscale):
     """tcgen05 3xTF32 path vs the FP64 CPU oracle: normalised weights, moments, knots, quantiles <= 1e-6."""
     family, obs, hyper = _glm_case(kind, 100 + d, N, d, xscale)
