@@ -610,7 +610,8 @@ __device__ __forceinline__ float tc_transpose_reduce32(float* v, int lane) {
 }
 
 // MODE 0 is the product; 1 (no series arithmetic) and 2 (no TMEM loads) exist only to attribute time to the
-// two resources the epilogue contends for (JP_TC_DEBUG_MODE, profiling builds of bench.py only)
+// two resources the epilogue contends for, 3 and 4 repeat 0 and 2 with two extra (overwritten) K-atom products per
+// tile to measure how MMA time composes with epilogue time (JP_TC_DEBUG_MODE, profiling builds of bench.py only)
 template <int NC, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcKernelParams P) {
@@ -718,6 +719,11 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait_relaxed(bar_full + 8u * stage, phase);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC_TMEM_STRIDE;
+          if (MODE >= 3) {   // two dummy atom products, overwritten by the real contraction below
+            for (int r = 0; r < 8; ++r)
+              umma_tf32(d_tmem, umma_desc(sA + (uint32_t)stage * a_bytes + 32u * (r & 3)),
+                        umma_desc(sB + (uint32_t)bb * b_bytes + 32u * (r & 3)), idesc, 0u);
+          }
           for (int a = 0; a < P.kb; ++a) {
             // split layout: the last product (x_hi . d_lo) takes the observation row's first atom again
             const int a_obs = (a < P.ka) ? a : 0;
@@ -777,7 +783,7 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t(&nxt)[TC_LDW] = (c & 1) ? va : vb;
           tmem_ld_wait(cur);
           if (c + 1 < TC_COLS_PER_WARP / TC_LDW) {
-            if (MODE != 2) tmem_ld(nxt, taddr + (uint32_t)(TC_LDW * (c + 1)));
+            if (MODE != 2 && MODE != 4) tmem_ld(nxt, taddr + (uint32_t)(TC_LDW * (c + 1)));
           } else {
             // every tcgen05.ld of this tile has completed: hand the accumulator buffer back to the MMA issuer
             tc_fence_before();
@@ -787,7 +793,7 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               mbar_wait(bar_tfull + 8u * nbuf, (tphase >> nbuf) & 1u);
               tphase ^= 1u << nbuf;
               tc_fence_after();
-              if (MODE != 2) tmem_ld(nxt, lane_addr + (uint32_t)nbuf * TC_TMEM_STRIDE);
+              if (MODE != 2 && MODE != 4) tmem_ld(nxt, lane_addr + (uint32_t)nbuf * TC_TMEM_STRIDE);
               load_coef(cn);
             }
           }
@@ -1050,6 +1056,8 @@ static int launch_tc(jp_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB
   static const int mode = getenv("JP_TC_DEBUG_MODE") ? atoi(getenv("JP_TC_DEBUG_MODE")) : 0;
   if (mode == 1) return launch_tc_mode<NC, 1>(ctx, tmA, tmB, kp, smem);
   if (mode == 2) return launch_tc_mode<NC, 2>(ctx, tmA, tmB, kp, smem);
+  if (mode == 3) return launch_tc_mode<NC, 3>(ctx, tmA, tmB, kp, smem);
+  if (mode == 4) return launch_tc_mode<NC, 4>(ctx, tmA, tmB, kp, smem);
 #endif
   return launch_tc_mode<NC, 0>(ctx, tmA, tmB, kp, smem);
 }
