@@ -152,6 +152,15 @@ int jp_data_free(jp_data* data);
 int jp_glm_grad_hess(jp_ctx* ctx, const jp_data* data, int d, const double* h_beta, double* h_g, double* h_Hneg,
                      double* h_logpost);
 
+/* mode(M, data)  reference src/joint_posterior.jl:164-168 (optBFGS! + ForwardDiff Hessian there): the unconstrained
+ * posterior mode by Newton iterations driven from native host code, every function / derivative evaluation one
+ * batched GPU call.  glm != 0 (LOGISTIC / POISSON with unconstrained coefficients): analytic score and information
+ * (jp_glm_grad_hess); glm == 0: saddle-free Newton on Richardson finite differences of jp_log_density_points.
+ * h_x: in = start, out = mode; h_H: d x d Hessian of the NEGATIVE log-density at the mode (what `mode` doubles and
+ * hands to deduce_scale!, :167); *neg_min: the minimised objective (:166); *evals: GPU evaluations used. */
+int jp_mode(jp_ctx* ctx, const jp_data* data, int d, const int* h_transform, int glm, double* h_x, double* h_H,
+            double* neg_min, int* evals);
+
 /* Unconstrained log-density  log_density(transform(x), data) + log|J(x)|  at K arbitrary points: the
  * objective `mode` minimises (reference src/joint_posterior.jl:164-168, sign flipped, no neg_min),
  * evaluated by the same family plugins as the grid path.  h_x: K x d row-major; h_ld: K.  Blocking. */

@@ -16,6 +16,7 @@
 // result is deterministic.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include "jp_common.cuh"
 #include "jp_family.cuh"
 
@@ -379,13 +380,32 @@ int jp_log_density_points(jp_ctx* ctx, const jp_data* data, int d, const int* h_
   jp_posterior tmp;   // only ctx is used by the launcher
   tmp.ctx = ctx;
   int st = JP_OK;
-  cudaError_t e = jp_dmalloc(ctx, &d_x, (size_t)K * d * 8);
-  if (e == cudaSuccess) e = jp_dmalloc(ctx, &d_theta, (size_t)K * d * 8);
-  if (e == cudaSuccess) e = jp_dmalloc(ctx, &d_part, (size_t)K * (splits + 1) * 8);
-  if (e == cudaSuccess) e = jp_dmalloc(ctx, &d_out, (size_t)K * 8);
-  if (e == cudaSuccess) e = jp_dmalloc(ctx, &d_code, (size_t)d * 4);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_x, h_x, (size_t)K * d * 8, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_code, h_transform, (size_t)d * 4, cudaMemcpyHostToDevice, ctx->stream);
+  cudaError_t e = cudaSuccess;
+  // Small batches (the mode finder's finite-difference stencils: a few hundred points, called tens of times per fit)
+  // live in the context's persistent scratch and are staged through its pinned buffer: no allocation, no pageable copy.
+  const size_t code_dbl = ((size_t)d + 1) / 2, need_dev = (size_t)K * (2 * d + splits + 2) + code_dbl;
+  const size_t need_pin = (size_t)K * (d + 1) + code_dbl;
+  const bool small = need_dev <= JP_SCRATCH_DOUBLES && need_pin <= JP_PINNED_DOUBLES;
+  double* hp = ctx->h_pinned;
+  if (small) {
+    d_x = ctx->d_scratch;
+    d_theta = d_x + (size_t)K * d;
+    d_part = d_theta + (size_t)K * d;
+    d_out = d_part + (size_t)K * (splits + 1);
+    d_code = reinterpret_cast<int*>(d_out + K);
+    std::memcpy(hp, h_x, (size_t)K * d * 8);
+    std::memcpy(hp + (size_t)K * d, h_transform, (size_t)d * 4);
+    e = cudaMemcpyAsync(d_x, hp, (size_t)K * d * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_code, hp + (size_t)K * d, (size_t)d * 4, cudaMemcpyHostToDevice, ctx->stream);
+  } else {
+    e = jp_dmalloc(ctx, &d_x, (size_t)K * d * 8);
+    if (e == cudaSuccess) e = jp_dmalloc(ctx, &d_theta, (size_t)K * d * 8);
+    if (e == cudaSuccess) e = jp_dmalloc(ctx, &d_part, (size_t)K * (splits + 1) * 8);
+    if (e == cudaSuccess) e = jp_dmalloc(ctx, &d_out, (size_t)K * 8);
+    if (e == cudaSuccess) e = jp_dmalloc(ctx, &d_code, (size_t)d * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_x, h_x, (size_t)K * d * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_code, h_transform, (size_t)d * 4, cudaMemcpyHostToDevice, ctx->stream);
+  }
   if (e == cudaSuccess) {
     JpFitLaunchParams lp;
     lp.d = d; lp.p = 0; lp.ncols = data->ncols; lp.rule = 0;
@@ -400,10 +420,14 @@ int jp_log_density_points(jp_ctx* ctx, const jp_data* data, int d, const int* h_
       ctx->launches++;
       e = cudaGetLastError();
     }
-    if (st == JP_OK && e == cudaSuccess) e = cudaMemcpyAsync(h_ld, d_out, (size_t)K * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    double* h_dst = small ? hp + (size_t)K * d + code_dbl : h_ld;
+    if (st == JP_OK && e == cudaSuccess) e = cudaMemcpyAsync(h_dst, d_out, (size_t)K * 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (st == JP_OK && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (st == JP_OK && e == cudaSuccess && small) std::memcpy(h_ld, h_dst, (size_t)K * 8);
   }
-  jp_dfree(ctx, d_x); jp_dfree(ctx, d_theta); jp_dfree(ctx, d_part); jp_dfree(ctx, d_out); jp_dfree(ctx, d_code);
+  if (!small) {
+    jp_dfree(ctx, d_x); jp_dfree(ctx, d_theta); jp_dfree(ctx, d_part); jp_dfree(ctx, d_out); jp_dfree(ctx, d_code);
+  }
   if (st != JP_OK) return st;
   if (e != cudaSuccess) {
     jp_set_error("jp_log_density_points: %s", cudaGetErrorString(e));

@@ -13,6 +13,7 @@
 // order by a second kernel, so the result is deterministic.  At N = 1e7, d = 30 the kernel streams the 2.5 GB
 // of records once; its floor is max(HBM time, N (d^2/2 + ~150) FP64 operations).
 #include <algorithm>
+#include <cstring>
 #include <vector>
 #include "jp_common.cuh"
 
@@ -214,11 +215,14 @@ extern "C" int jp_glm_grad_hess(jp_ctx* ctx, const jp_data* data, int d, const d
   JP_CUDA(jp_dmalloc(ctx, &d_beta, sizeof(double) * d));
   JP_CUDA(jp_dmalloc(ctx, &d_out, sizeof(double) * (nE + 1)));
   JP_CUDA(jp_dmalloc(ctx, &d_work, sizeof(double) * (size_t)nb * (nE + 1)));
-  JP_CUDA(cudaMemcpyAsync(d_beta, h_beta, sizeof(double) * d, cudaMemcpyHostToDevice, ctx->stream));
+  // staged through the context's pinned buffer (a Newton iteration of the mode finder is one such call)
+  double* hp = ctx->h_pinned;
+  std::memcpy(hp, h_beta, sizeof(double) * d);
+  JP_CUDA(cudaMemcpyAsync(d_beta, hp, sizeof(double) * d, cudaMemcpyHostToDevice, ctx->stream));
   int st = jp_glm_sums_device(ctx, data, d, d_beta, d_out, d_work, nb);
-  std::vector<double> out(nE + 1);
+  double* out = hp + JP_MAX_D;     // nE + 1 <= 64 + 64 * 65 / 2 + 1 doubles
   if (st == JP_OK) {
-    cudaError_t e = cudaMemcpyAsync(out.data(), d_out, sizeof(double) * (nE + 1), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(out, d_out, sizeof(double) * (nE + 1), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
       jp_set_error("jp_glm_grad_hess: %s", cudaGetErrorString(e));

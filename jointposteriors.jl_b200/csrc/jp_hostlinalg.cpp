@@ -281,4 +281,246 @@ double jp_cdf(const double* wn, const double* vn, int n, double x) {
   return lerp_between(vn, wn, i, x);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// mode(M, data): reference src/joint_posterior.jl:164-168 (optBFGS! + ForwardDiff Hessian there).  Here: Newton
+// iterations whose every function / derivative evaluation is one batched GPU call, driven from native host code
+// (a Newton iteration costs one kernel round trip; the loop itself is d x d arithmetic).
+//   * GLM families with unconstrained coefficients: analytic score and information from jp_glm_grad_hess.
+//   * every other family: saddle-free Newton on Richardson (h, h/2) central differences of jp_log_density_points.
+//     The stencil is evaluated AT THE CANDIDATE x + t step, so its centre value decides the line search and its
+//     derivatives start the next iteration.  The Hessian's eigenvalues are replaced by their absolute values so
+//     that indefinite regions are descended; at a stationary point with negative curvature the iterate leaves
+//     along the most negative eigenvector.
+// h_x: in = start, out = mode (unconstrained); h_H: Hessian of the NEGATIVE log-density at the mode, d x d symmetric;
+// *neg_min: the minimised objective; *evals: batched GPU evaluations used.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct FdStencil {
+  int d = 0, n = 0;                 // n points per step size (without the centre)
+  std::vector<double> off;          // n x d offsets in units of h
+  explicit FdStencil(int d_) : d(d_) {
+    n = 2 * d + 2 * d * (d - 1);
+    off.assign((size_t)n * d, 0.0);
+    for (int i = 0; i < d; ++i) {
+      off[(size_t)(2 * i) * d + i] = 1.0;
+      off[(size_t)(2 * i + 1) * d + i] = -1.0;
+    }
+    int q = 2 * d;
+    static const double sg[4][2] = {{1, 1}, {1, -1}, {-1, 1}, {-1, -1}};
+    for (int i = 0; i < d; ++i)
+      for (int j = i + 1; j < d; ++j)
+        for (int k = 0; k < 4; ++k, ++q) {
+          off[(size_t)q * d + i] = sg[k][0];
+          off[(size_t)q * d + j] = sg[k][1];
+        }
+  }
+  // O(h^2) gradient / Hessian from the values f[0 .. n) on the stencil
+  void derivs(double f0, const double* f, double h, double* g, double* H) const {
+    for (int i = 0; i < d; ++i) {
+      const double fp = f[2 * i], fm = f[2 * i + 1];
+      g[i] = (fp - fm) / (2 * h);
+      H[(size_t)i * d + i] = (fp - 2 * f0 + fm) / (h * h);
+    }
+    int q = 2 * d;
+    for (int i = 0; i < d; ++i)
+      for (int j = i + 1; j < d; ++j, q += 4) {
+        const double v = (f[q] - f[q + 1] - f[q + 2] + f[q + 3]) / (4 * h * h);
+        H[(size_t)j * d + i] = H[(size_t)i * d + j] = v;
+      }
+  }
+};
+
+struct ModeProblem {
+  jp_ctx* ctx;
+  const jp_data* data;
+  int d;
+  const int* code;
+  int evals = 0;
+  FdStencil st;
+  std::vector<double> pts, val, g1, H1, g2, H2;
+  ModeProblem(jp_ctx* c, const jp_data* dt, int d_, const int* cd) : ctx(c), data(dt), d(d_), code(cd), st(d_) {
+    pts.resize((size_t)(1 + 2 * st.n) * d);
+    val.resize(1 + 2 * st.n);
+    g1.resize(d); g2.resize(d); H1.resize((size_t)d * d); H2.resize((size_t)d * d);
+  }
+  // negative log-density at K points
+  int values(const double* x, int K, double* f) {
+    int s = jp_log_density_points(ctx, data, d, code, K, x, f);
+    ++evals;
+    for (int k = 0; k < K; ++k) f[k] = -f[k];
+    return s;
+  }
+  // f(x) and O(h^4) derivatives from the stencils at h and h/2: one batched call
+  int richardson(const double* x, double h, double* f0, double* g, double* H) {
+    const int n = st.n;
+    for (int k = 0; k < d; ++k) pts[k] = x[k];
+    for (int s = 0; s < 2; ++s) {
+      const double hh = s ? h / 2 : h;
+      double* p = pts.data() + (size_t)(1 + s * n) * d;
+      for (int q = 0; q < n; ++q)
+        for (int k = 0; k < d; ++k) p[(size_t)q * d + k] = x[k] + hh * st.off[(size_t)q * d + k];
+    }
+    int s = values(pts.data(), 1 + 2 * n, val.data());
+    if (s != JP_OK) return s;
+    *f0 = val[0];
+    st.derivs(val[0], val.data() + 1, h, g1.data(), H1.data());
+    st.derivs(val[0], val.data() + 1 + n, h / 2, g2.data(), H2.data());
+    for (int k = 0; k < d; ++k) g[k] = (4 * g2[k] - g1[k]) / 3;
+    for (int k = 0; k < d * d; ++k) H[k] = (4 * H2[k] - H1[k]) / 3;
+    return JP_OK;
+  }
+};
+
+double max_abs(const double* v, int n) {
+  double m = 0;
+  for (int i = 0; i < n; ++i) m = std::fmax(m, std::fabs(v[i]));
+  return m;
+}
+
+int mode_generic(ModeProblem& P, double* x, double* H, double* fx_out, int iters) {
+  const int d = P.d;
+  const double h = 2e-3;
+  std::vector<double> g(d), step(d), xn(d), gn(d), Hn((size_t)d * d), lam, V, cands((size_t)4 * d), fc(4);
+  double fx;
+  int s = P.richardson(x, h, &fx, g.data(), H);
+  if (s != JP_OK) return s;
+  for (int it = 0; it < iters; ++it) {
+    symmetric_eigen(H, d, lam, V);                       // ascending; V[i * d + k] = component k of eigenvector i
+    double scale = 0;
+    for (int i = 0; i < d; ++i) scale = std::fmax(scale, std::fabs(lam[i]));
+    scale = std::fmax(scale, 1e-300);
+    const double gnorm = max_abs(g.data(), d);
+    if (lam[0] < -1e-8 * scale && gnorm < 1e-6 * scale) {
+      static const double sgn[4] = {1, 1, -1, -1}, tt[4] = {1.0, 0.25, 1.0, 0.25};
+      for (int c = 0; c < 4; ++c)
+        for (int k = 0; k < d; ++k) cands[(size_t)c * d + k] = x[k] + tt[c] * sgn[c] * V[k];
+      s = P.values(cands.data(), 4, fc.data());
+      if (s != JP_OK) return s;
+      int best = -1;
+      for (int c = 0; c < 4; ++c)
+        if (std::isfinite(fc[c]) && (best < 0 || fc[c] < fc[best])) best = c;
+      if (best < 0 || !(fc[best] < fx)) break;
+      for (int k = 0; k < d; ++k) x[k] = cands[(size_t)best * d + k];
+      s = P.richardson(x, h, &fx, g.data(), H);
+      if (s != JP_OK) return s;
+      continue;
+    }
+    // step = -V (V' g / |lambda|)
+    for (int k = 0; k < d; ++k) step[k] = 0;
+    for (int i = 0; i < d; ++i) {
+      double c = 0;
+      for (int k = 0; k < d; ++k) c += V[(size_t)i * d + k] * g[k];
+      c /= std::fmax(std::fabs(lam[i]), 1e-10 * scale);
+      for (int k = 0; k < d; ++k) step[k] -= V[(size_t)i * d + k] * c;
+    }
+    double nrm = max_abs(step.data(), d);
+    if (nrm > 10.0)
+      for (int k = 0; k < d; ++k) step[k] *= 10.0 / nrm;
+    if (lam[0] > 0 && max_abs(step.data(), d) < 1e-9 * (1 + max_abs(x, d))) break;   // below the finite-difference resolution
+    double t = 1.0, fn = 0;
+    bool ok = false;
+    while (t > 1e-8) {
+      for (int k = 0; k < d; ++k) xn[k] = x[k] + t * step[k];
+      s = P.richardson(xn.data(), h, &fn, gn.data(), Hn.data());
+      if (s != JP_OK) return s;
+      if (std::isfinite(fn) && fn <= fx + 1e-13 * (1 + std::fabs(fx))) {
+        ok = true;
+        break;
+      }
+      t *= 0.25;
+    }
+    if (!ok) break;
+    for (int k = 0; k < d; ++k) { x[k] = xn[k]; g[k] = gn[k]; }
+    std::memcpy(H, Hn.data(), sizeof(double) * d * d);
+    fx = fn;
+  }
+  *fx_out = fx;
+  return JP_OK;
+}
+
+// solve A y = b (A symmetric positive definite in practice; partial pivoting keeps it safe otherwise)
+bool solve_dense(std::vector<double> A, std::vector<double>& b, int d) {
+  for (int c = 0; c < d; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < d; ++r)
+      if (std::fabs(A[(size_t)c * d + r]) > std::fabs(A[(size_t)c * d + piv])) piv = r;
+    if (A[(size_t)c * d + piv] == 0.0) return false;
+    if (piv != c) {
+      for (int k = 0; k < d; ++k) std::swap(A[(size_t)k * d + c], A[(size_t)k * d + piv]);
+      std::swap(b[c], b[piv]);
+    }
+    for (int r = c + 1; r < d; ++r) {
+      const double f = A[(size_t)c * d + r] / A[(size_t)c * d + c];
+      if (f == 0.0) continue;
+      for (int k = c; k < d; ++k) A[(size_t)k * d + r] -= f * A[(size_t)k * d + c];
+      b[r] -= f * b[c];
+    }
+  }
+  for (int r = d - 1; r >= 0; --r) {
+    double v = b[r];
+    for (int k = r + 1; k < d; ++k) v -= A[(size_t)k * d + r] * b[k];
+    b[r] = v / A[(size_t)r * d + r];
+  }
+  return true;
+}
+
+int mode_glm(jp_ctx* ctx, const jp_data* data, int d, double* x, double* H, double* neg_min, int* evals, int iters) {
+  std::vector<double> g(d), g2(d), H2((size_t)d * d), step(d), xn(d);
+  double lp = 0, lp2 = 0;
+  int s = jp_glm_grad_hess(ctx, data, d, x, g.data(), H, &lp);
+  ++*evals;
+  if (s != JP_OK) return s;
+  for (int it = 0; it < iters; ++it) {
+    step = g;
+    if (!solve_dense(std::vector<double>(H, H + (size_t)d * d), step, d)) break;
+    double t = 1.0;
+    bool ok = false;
+    while (t > 1e-10) {
+      for (int k = 0; k < d; ++k) xn[k] = x[k] + t * step[k];
+      s = jp_glm_grad_hess(ctx, data, d, xn.data(), g2.data(), H2.data(), &lp2);
+      ++*evals;
+      if (s != JP_OK) return s;
+      if (std::isfinite(lp2) && lp2 >= lp - 1e-13 * std::fabs(lp)) {
+        ok = true;
+        break;
+      }
+      t *= 0.5;
+    }
+    if (!ok) break;
+    double moved = 0;
+    for (int k = 0; k < d; ++k) moved = std::fmax(moved, std::fabs(xn[k] - x[k]));
+    for (int k = 0; k < d; ++k) { x[k] = xn[k]; g[k] = g2[k]; }
+    std::memcpy(H, H2.data(), sizeof(double) * d * d);
+    lp = lp2;
+    if (moved < 1e-13 * (1 + max_abs(x, d))) break;
+  }
+  *neg_min = -lp;
+  return JP_OK;
+}
+}  // namespace
+
+int jp_mode(jp_ctx* ctx, const jp_data* data, int d, const int* h_transform, int glm, double* h_x, double* h_H,
+            double* neg_min, int* evals) {
+  if (!ctx || !data || !h_transform || !h_x || !h_H || !neg_min || d < 1 || d > 64) {
+    jp_set_error("jp_mode: bad argument");
+    return JP_ERR_BAD_ARG;
+  }
+  int n_eval = 0, s;
+  if (glm) {
+    for (int k = 0; k < d; ++k)
+      if (h_transform[k] != JP_T_REAL) {
+        jp_set_error("jp_mode: the GLM Newton iteration needs unconstrained coefficients (coordinate %d is constrained)", k);
+        return JP_ERR_BAD_ARG;
+      }
+    s = mode_glm(ctx, data, d, h_x, h_H, neg_min, &n_eval, 60);
+  } else {
+    ModeProblem P(ctx, data, d, h_transform);
+    s = mode_generic(P, h_x, h_H, neg_min, 100);
+    n_eval = P.evals;
+  }
+  if (evals) *evals = n_eval;
+  return s;
+}
+
 }  // extern "C"

@@ -214,109 +214,19 @@ def log_density_unc(M, ddata, X):
     return out
 
 
-def _fd_grad_hess(fbatch, x, h):
-    """Central finite-difference gradient and Hessian, O(h^2), all points in one GPU batch."""
-    d = len(x)
-    E = np.eye(d) * h
-    pts = [x]
-    for i in range(d):
-        pts += [x + E[i], x - E[i]]
-    pairs = [(i, j) for i in range(d) for j in range(i + 1, d)]
-    for i, j in pairs:
-        pts += [x + E[i] + E[j], x + E[i] - E[j], x - E[i] + E[j], x - E[i] - E[j]]
-    f = fbatch(np.array(pts))
-    f0 = f[0]
-    g = np.zeros(d)
-    H = np.zeros((d, d))
-    for i in range(d):
-        fp, fm = f[1 + 2 * i], f[2 + 2 * i]
-        g[i] = (fp - fm) / (2 * h)
-        H[i, i] = (fp - 2 * f0 + fm) / (h * h)
-    o = 1 + 2 * d
-    for q, (i, j) in enumerate(pairs):
-        a, b, c, e = f[o + 4 * q:o + 4 * q + 4]
-        H[i, j] = H[j, i] = (a - b - c + e) / (4 * h * h)
-    return f0, g, H
-
-
-def _richardson_grad_hess(fbatch, x, h=2e-3):
-    """O(h^4) derivatives from two central-difference evaluations."""
-    f0, g1, H1 = _fd_grad_hess(fbatch, x, h)
-    _, g2, H2 = _fd_grad_hess(fbatch, x, h / 2)
-    return f0, (4 * g2 - g1) / 3, (4 * H2 - H1) / 3
-
-
-def _newton_mode_generic(M, ddata, x0, iters=200):
-    """Saddle-free Newton on the GPU-evaluated negative log-density (derivatives by Richardson finite
-    differences, every stencil one batched jp_log_density_points call).  The Hessian's eigenvalues are
-    replaced by their absolute values so that indefinite regions are descended, and at a stationary
-    point with negative curvature the iterate leaves along the most negative eigenvector."""
-    f = lambda X: -log_density_unc(M, ddata, X)   # objective: negative log-density, as minimised by optBFGS!
-    x = np.array(x0, dtype=np.float64)
-    fx = f(x[None])[0]
-    for _ in range(iters):
-        _, g, H = _richardson_grad_hess(f, x)
-        lam, V = np.linalg.eigh(H)
-        scale = max(np.max(np.abs(lam)), 1e-300)
-        gnorm = np.max(np.abs(g))
-        if lam[0] < -1e-8 * scale and gnorm < 1e-6 * scale:
-            cands = [x + t * sgn * V[:, 0] for sgn in (1.0, -1.0) for t in (1.0, 0.25)]
-            fc = f(np.array(cands))
-            k = int(np.nanargmin(np.where(np.isfinite(fc), fc, np.inf)))
-            if not (np.isfinite(fc[k]) and fc[k] < fx):
-                break
-            x, fx = cands[k], fc[k]
-            continue
-        lam_mod = np.maximum(np.abs(lam), 1e-10 * scale)
-        step = -V @ ((V.T @ g) / lam_mod)
-        nrm = np.max(np.abs(step))
-        if nrm > 10.0:
-            step *= 10.0 / nrm
-        t, fn = 1.0, fx
-        while t > 1e-12:
-            fn = f((x + t * step)[None])[0]
-            if np.isfinite(fn) and fn <= fx:
-                break
-            t *= 0.5
-        if not (np.isfinite(fn) and fn <= fx):
-            break
-        x = x + t * step
-        done = abs(fx - fn) <= 1e-15 * (1 + abs(fx)) and np.max(np.abs(t * step)) < 1e-9 * (1 + np.max(np.abs(x)))
-        fx = fn
-        if done and lam[0] > 0:
-            break
-    fx, g, H = _richardson_grad_hess(f, x)
-    return x, H, fx
-
-
-def _newton_mode_glm(M, ddata, x0, iters=60):
+def _native_mode(M, ddata, x0, glm):
+    """jp_mode: the Newton iterations run in native host code inside libjpcuda (csrc/jp_hostlinalg.cpp), one batched
+    GPU evaluation per iteration -- analytic score / information for GLMs, saddle-free Newton on Richardson finite
+    differences of the plugin log-density otherwise."""
     d = M.d
-    L = lib()
-
-    def gh(beta):
-        g = np.zeros(d)
-        H = np.zeros((d, d), order="F")
-        lp = C.c_double()
-        beta = f64(beta)
-        check(L.jp_glm_grad_hess(ddata.ctx.handle, ddata.handle, C.c_int(d), ptr(beta), ptr(g), ptr(H), C.byref(lp)))
-        return lp.value, g, np.array(H)
-
     x = np.array(x0, dtype=np.float64)
-    lp, g, H = gh(x)
-    for _ in range(iters):
-        step = np.linalg.solve(H, g)
-        t = 1.0
-        while t > 1e-10:
-            lp2, g2, H2 = gh(x + t * step)
-            if np.isfinite(lp2) and lp2 >= lp - 1e-13 * abs(lp):
-                break
-            t *= 0.5
-        x = x + t * step
-        small = np.max(np.abs(t * step)) < 1e-13 * (1 + np.max(np.abs(x)))
-        lp, g, H = lp2, g2, H2
-        if small:
-            break
-    return x, H, -lp
+    H = np.zeros((d, d), order="F")
+    neg_min = C.c_double()
+    evals = C.c_int()
+    code = np.ascontiguousarray(M.transform, dtype=np.int32)
+    check(lib().jp_mode(ddata.ctx.handle, ddata.handle, C.c_int(d), ptr(code), C.c_int(1 if glm else 0), ptr(x), ptr(H),
+                        C.byref(neg_min), C.byref(evals)))
+    return x, np.array(H), neg_min.value
 
 
 def deduce_scale(M, H):
@@ -337,10 +247,8 @@ def mode(M, data, x0=None):
     ddata = _as_device_data(M, data)
     if x0 is None:
         x0 = np.zeros(M.d)
-    if ddata.family in (FAM_LOGISTIC, FAM_POISSON) and np.all(M.transform == 0):
-        x, H, neg_min = _newton_mode_glm(M, ddata, x0)
-    else:
-        x, H, neg_min = _newton_mode_generic(M, ddata, x0)
+    glm = ddata.family in (FAM_LOGISTIC, FAM_POISSON) and np.all(M.transform == 0)
+    x, H, neg_min = _native_mode(M, ddata, x0, glm)
     U = deduce_scale(M, M.hessian_scale * H)
     return x, U, neg_min
 

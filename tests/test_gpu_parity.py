@@ -202,6 +202,20 @@ def test_gpu_mode_matches_cpu_mode(jp, O, gpu_ctx):
     M = jp.Model((jp.ProbabilityVector(3),))
     x, U, neg_min = jp.mode(M, _upload(jp, gpu_ctx, 0, obs, hyper), x0=[0.2, -3.0, -2.0])
     assert np.allclose(x, xc, atol=1e-5) and abs(neg_min - fc) < 1e-8
+    # the default start (zeros) reaches the same mode; the native Newton loop reports its GPU evaluations
+    dd = _upload(jp, gpu_ctx, 0, obs, hyper)
+    x0, U0, f0 = jp.mode(M, dd)
+    assert np.allclose(x0, xc, atol=1e-5) and abs(f0 - fc) < 1e-8
+    code = np.ascontiguousarray(M.transform, dtype=np.int32)
+    xs, Hs = np.zeros(3), np.zeros((3, 3), order="F")
+    fmin, evals = C.c_double(), C.c_int()
+    assert jp.lib().jp_mode(gpu_ctx.handle, dd.handle, 3, code.ctypes.data_as(C.c_void_p), 0, xs.ctypes.data_as(C.c_void_p),
+                            Hs.ctypes.data_as(C.c_void_p), C.byref(fmin), C.byref(evals)) == 0
+    assert 3 <= evals.value <= 40 and np.allclose(Hs, Hc, rtol=1e-5, atol=1e-6) and np.allclose(Hs, Hs.T)
+    # the GLM iteration refuses constrained coordinates instead of ignoring the transform
+    bad = np.array([1, 0, 0], dtype=np.int32)
+    assert jp.lib().jp_mode(gpu_ctx.handle, dd.handle, 3, bad.ctypes.data_as(C.c_void_p), 1, xs.ctypes.data_as(C.c_void_p),
+                            Hs.ctypes.data_as(C.c_void_p), C.byref(fmin), C.byref(evals)) == 1
 
 
 def test_adopted_device_records(jp, O, gpu_ctx):
