@@ -44,11 +44,17 @@ typedef enum jp_status {
 enum { JP_RULE_GENZ_KEISTER = 0, JP_RULE_KRONROD_PATTERSON = 1 };
 /* constraint transforms (ConstrainedParameters RealVector / PositiveVector / ProbabilityVector,
  * reference src/JointPosteriors.jl:22-26, README.md:32,247-248) -- one code per unconstrained coordinate */
-enum { JP_T_REAL = 0, JP_T_POSITIVE = 1, JP_T_PROBABILITY = 2, JP_T_NONCENTRED = 3 };
+enum { JP_T_REAL = 0, JP_T_POSITIVE = 1, JP_T_PROBABILITY = 2, JP_T_NONCENTRED = 3, JP_T_SIMPLEX = 4 };
 /* JP_T_NONCENTRED couples coordinate k to two EARLIER constrained coordinates: theta_k = theta_loc + theta_scale * x_k,
  * log|J| += log(theta_scale); loc and scale travel in the code word (hierarchical models whose centred
  * parameterisation has no joint mode, e.g. eight schools).  Transforms are applied in coordinate order. */
 #define JP_T_NONCENTRED_CODE(loc, scale) (JP_T_NONCENTRED | ((loc) << 8) | ((scale) << 16))
+/* JP_T_SIMPLEX (ConstrainedParameters Simplex, reference src/JointPosteriors.jl:26): the n - 1 coordinates
+ * [first, first + len) are the first n - 1 components of a point of the n-simplex, the last one is implied:
+ *   theta_k = e^{x_k} / (1 + sum_j e^{x_j}),  theta_n = 1 / (1 + sum_j e^{x_j}),  log|J| = sum_{k=1..n} log theta_k
+ * (additive log-ratio map; det(diag(theta) - theta theta') = prod of all n components).  Every coordinate of the block
+ * carries the same code word. */
+#define JP_T_SIMPLEX_CODE(first, len) (JP_T_SIMPLEX | ((first) << 8) | ((len) << 16))
 #define JP_T_KIND(code) ((code) & 0xFF)
 #define JP_T_LOC(code) (((code) >> 8) & 0xFF)
 #define JP_T_SCALE(code) (((code) >> 16) & 0xFF)
@@ -58,7 +64,8 @@ enum {
   JP_FAM_LOGISTIC = 1,         /* logistic regression, N(0, s^2) prior */
   JP_FAM_POISSON = 2,          /* Poisson regression (log link), N(0, s^2) prior */
   JP_FAM_HIER_NORMAL = 3,      /* hierarchical normal ("eight schools") */
-  JP_FAM_NORMAL_LINEAR = 4     /* README Example 2 "HiWorld", reference README.md:245-258 */
+  JP_FAM_NORMAL_LINEAR = 4,    /* README Example 2 "HiWorld", reference README.md:245-258 */
+  JP_FAM_MULTINOMIAL = 5       /* category counts with a symmetric Dirichlet prior on a Simplex block */
 };
 /* log-density evaluation path of jp_fit */
 enum {
@@ -136,7 +143,8 @@ int jp_rule_info(int rule, int* levels, int* nmax, int* h_npts, double* h_nodes,
  *   BINOMIAL_MIXTURE (X, freq, NmX)            hyper = (a_m-1, b_m-1, a_p-1, b_p-1, a_tau-1, b_tau-1)
  *   LOGISTIC/POISSON (x_0..x_{d-1}, y)         hyper = (prior sd)
  *   HIER_NORMAL      (y_j, s_j)                hyper = (half-Cauchy scale of tau)
- *   NORMAL_LINEAR    (x_0..x_{p-1}, y)         hyper = (sd of beta prior, sd of sigma prior) */
+ *   NORMAL_LINEAR    (x_0..x_{p-1}, y)         hyper = (sd of beta prior, sd of sigma prior)
+ *   MULTINOMIAL      (count_k), one row per category, N = d + 1      hyper = (alpha - 1 of the Dirichlet prior) */
 int jp_data_upload(jp_ctx* ctx, int family, long long N, int ncols, const double* h_obs, const double* h_hyper,
                    int n_hyper, jp_data** out);
 /* Same, for records that are ALREADY in the memory of ctx's GPU (e.g. row slices uploaded by each rank of a box and

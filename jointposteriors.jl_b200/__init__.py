@@ -5,17 +5,18 @@ this package is the host-side mirror of the reference's Julia interface and bind
 ctypes.  There is no CPU fallback: importing works anywhere, computing needs a B200.
 """
 from ._lib import JPError, NotPositiveDefinite, PATH_AUTO, PATH_FP64, PATH_TC, lib
-from .data import (BinaryClassificationData, Data, HierNormalData, LogisticData, NormalLinearData, PoissonData)
+from .data import (BinaryClassificationData, Data, HierNormalData, LogisticData, MultinomialData, NormalLinearData,
+                   PoissonData)
 from .linalg import chol, deduce_scale_dynamic, inv_chol, inv_upper, reduce_dimensions, reduce_dimensions_ldr, try_chol
 from .marginals import Grid, cdf, marginal, marginals, quantile
 from .model import (Context, DeviceData, Dynamic, FixedRank, Full, LDR, GenzKeister, JointPosterior, JointPosteriorRaw,
                     KronrodPatterson, Model, Smolyak, SmolyakRaw, default, fit, log_density_unc, mode)
-from .params import NonCentredVector, PositiveVector, ProbabilityVector, RealVector, parameter
+from .params import NonCentredVector, PositiveVector, ProbabilityVector, RealVector, Simplex, parameter
 
 __all__ = [
     "Model", "fit", "marginal", "marginals", "mode", "quantile", "cdf", "Grid", "JointPosterior", "JointPosteriorRaw",
-    "parameter", "RealVector", "PositiveVector", "ProbabilityVector", "NonCentredVector", "Data", "BinaryClassificationData",
-    "LogisticData", "PoissonData", "HierNormalData", "NormalLinearData", "Smolyak", "SmolyakRaw", "GenzKeister",
+    "parameter", "RealVector", "PositiveVector", "ProbabilityVector", "Simplex", "NonCentredVector", "Data", "BinaryClassificationData",
+    "LogisticData", "PoissonData", "HierNormalData", "NormalLinearData", "MultinomialData", "Smolyak", "SmolyakRaw", "GenzKeister",
     "KronrodPatterson", "Dynamic", "Full", "FixedRank", "LDR", "default", "Context", "DeviceData", "chol", "try_chol",
     "inv_upper", "inv_chol", "reduce_dimensions", "reduce_dimensions_ldr", "deduce_scale_dynamic", "JPError", "NotPositiveDefinite",
     "PATH_AUTO", "PATH_FP64", "PATH_TC", "log_density_unc",

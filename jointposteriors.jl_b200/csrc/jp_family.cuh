@@ -140,6 +140,29 @@ struct FamNormalLinear {
   }
 };
 
+// category counts on a Simplex block: theta = first d = n - 1 components of a point of the n-simplex (the last is
+// 1 - sum); record (count_k), one per category; symmetric Dirichlet(alpha) prior, hyper[0] = alpha - 1.
+// The posterior is Dirichlet(alpha + counts) in closed form, which pins the simplex transform in the tests.
+struct FamMultinomial {
+  static constexpr int kId = JP_FAM_MULTINOMIAL;
+  static constexpr const char* kName = "multinomial";
+  static bool shape_ok(int d, int ncols, long long N) { return ncols == 1 && N == (long long)d + 1; }
+  template <int DPAD>
+  __device__ static double prior(const double (&t)[DPAD], int, long long, const double*) { return 0.0; }
+  template <int DPAD>
+  __device__ static double obs(const double (&t)[DPAD], int d, const double* r, long long n, const double* h) {
+    double tn = 0, rest = 1.0;
+#pragma unroll
+    for (int k = 0; k < DPAD; ++k)
+      if (k < d) {
+        rest -= t[k];
+        if (k == n) tn = t[k];
+      }
+    if (n >= d) tn = rest;
+    return (r[0] + h[0]) * log(tn);
+  }
+};
+
 // ------------------------------------------------------------------------------------ registry
 struct JpFitLaunchParams;   // defined in jp_fit.cu
 typedef int (*jp_family_launcher)(jp_posterior* post, const JpFitLaunchParams& lp);

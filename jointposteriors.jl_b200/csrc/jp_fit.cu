@@ -100,11 +100,38 @@ jp_fit_nodes_kernel(const JpFitLaunchParams P) {
       }
     }
     double lj = 0.0;
+    // simplex blocks first (each depends only on its own unconstrained coordinates): a run-time loop over block
+    // heads, compile-time indices into the register array inside
+#pragma unroll 1
+    for (int k0 = 0; k0 < P.d; ++k0) {
+      const int code = s_code[k0];
+      if (JP_T_KIND(code) != JP_T_SIMPLEX || JP_T_LOC(code) != k0) continue;
+      const int hi = k0 + JP_T_SCALE(code);
+      double mx = 0.0;                               // the implied last coordinate has x = 0
+#pragma unroll
+      for (int j = 0; j < DPAD; ++j)
+        if (j >= k0 && j < hi) mx = fmax(mx, th[j]);
+      double S = exp(-mx);
+#pragma unroll
+      for (int j = 0; j < DPAD; ++j)
+        if (j >= k0 && j < hi) S += exp(th[j] - mx);
+      const double logS = log(S);
+      lj += -mx - logS;                              // log of the implied last component
+#pragma unroll
+      for (int j = 0; j < DPAD; ++j)
+        if (j >= k0 && j < hi) {
+          const double l = th[j] - mx - logS;
+          lj += l;
+          th[j] = exp(l);
+        }
+    }
 #pragma unroll
     for (int k = 0; k < DPAD; ++k) {
       if (k < P.d) {
         const int code = s_code[k];
-        if (JP_T_KIND(code) == JP_T_NONCENTRED) {
+        if (JP_T_KIND(code) == JP_T_SIMPLEX) {
+          // transformed above
+        } else if (JP_T_KIND(code) == JP_T_NONCENTRED) {
           // theta_k = theta_loc + theta_scale * x_k with loc, scale < k already transformed; the register
           // array is searched with compile-time indices so that it never spills to local memory
           const int il = JP_T_LOC(code), is = JP_T_SCALE(code);
@@ -264,6 +291,7 @@ JP_REGISTER_FAMILY(FamLogistic)
 JP_REGISTER_FAMILY(FamPoisson)
 JP_REGISTER_FAMILY(FamHierNormal)
 JP_REGISTER_FAMILY(FamNormalLinear)
+JP_REGISTER_FAMILY(FamMultinomial)
 
 // ------------------------------------------------------------------------------------ host side
 int jp_upload_fit_consts(jp_posterior* post, const jp_fit_args* args) {
@@ -294,8 +322,15 @@ int jp_upload_fit_consts(jp_posterior* post, const jp_fit_args* args) {
 int jp_check_transform_codes(const char* who, const int* code, int d) {
   for (int k = 0; k < d; ++k) {
     int kind = JP_T_KIND(code[k]);
-    JP_REQUIRE(kind >= 0 && kind <= JP_T_NONCENTRED && (kind == JP_T_NONCENTRED || code[k] == kind),
+    JP_REQUIRE(kind >= 0 && kind <= JP_T_SIMPLEX && (kind >= JP_T_NONCENTRED || code[k] == kind),
                "%s: unknown transform code %d at coordinate %d", who, code[k], k);
+    if (kind == JP_T_SIMPLEX) {
+      const int first = JP_T_LOC(code[k]), len = JP_T_SCALE(code[k]);
+      JP_REQUIRE(len >= 1 && first <= k && k < first + len && first + len <= d && (code[k] >> 24) == 0,
+                 "%s: simplex coordinate %d lies outside its block [%d, %d)", who, k, first, first + len);
+      JP_REQUIRE(code[first] == code[k], "%s: simplex block [%d, %d) does not carry one code word (coordinate %d)", who, first,
+                 first + len, k);
+    }
     if (kind == JP_T_NONCENTRED)
       JP_REQUIRE(JP_T_LOC(code[k]) < k && JP_T_SCALE(code[k]) < k && (code[k] >> 24) == 0,
                  "%s: non-centred coordinate %d must refer to earlier coordinates (loc %d, scale %d)", who, k,

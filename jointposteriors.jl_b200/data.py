@@ -7,7 +7,7 @@ plugin reads.
 """
 import numpy as np
 
-FAM_BINOMIAL_MIXTURE, FAM_LOGISTIC, FAM_POISSON, FAM_HIER_NORMAL, FAM_NORMAL_LINEAR = range(5)
+FAM_BINOMIAL_MIXTURE, FAM_LOGISTIC, FAM_POISSON, FAM_HIER_NORMAL, FAM_NORMAL_LINEAR, FAM_MULTINOMIAL = range(6)
 
 
 class Data:
@@ -96,3 +96,20 @@ class NormalLinearData(Data):
     def records(self):
         obs = np.ascontiguousarray(np.concatenate([self.X, self.y[:, None]], axis=1))
         return obs, np.array([self.sd_beta, self.sd_sigma])
+
+
+class MultinomialData(Data):
+    """Category counts c_1..c_n with theta on the n-simplex (a Simplex(n) block) and a symmetric Dirichlet(alpha)
+    prior; the posterior is Dirichlet(alpha + c) in closed form, which is what pins the simplex transform."""
+    family = FAM_MULTINOMIAL
+
+    def __init__(self, counts, alpha=1.0):
+        self.counts = np.asarray(counts, dtype=np.float64)
+        if self.counts.ndim != 1 or self.counts.size < 2 or np.any(self.counts < 0):
+            raise ValueError("counts must be a 1-D array of at least two non-negative numbers")
+        self.alpha = float(alpha)
+        if self.alpha <= 0:
+            raise ValueError("alpha must be positive")
+
+    def records(self):
+        return np.ascontiguousarray(self.counts[:, None]), np.array([self.alpha - 1.0])

@@ -10,7 +10,7 @@ the per-coordinate transform codes of include/jpcuda.h and gives names to slices
 """
 import numpy as np
 
-T_REAL, T_POSITIVE, T_PROBABILITY, T_NONCENTRED = 0, 1, 2, 3
+T_REAL, T_POSITIVE, T_PROBABILITY, T_NONCENTRED, T_SIMPLEX = 0, 1, 2, 3, 4
 
 
 class _Block:
@@ -57,6 +57,24 @@ class NonCentredVector(_Block):
         return T_NONCENTRED | (self.loc << 8) | (self.scale << 16)
 
 
+class Simplex(_Block):
+    """A point of the n-simplex (ConstrainedParameters Simplex, reference src/JointPosteriors.jl:26): n - 1
+    unconstrained coordinates, theta_k = e^{x_k} / (1 + sum_j e^{x_j}) for the first n - 1 components, the last one
+    implied (1 - sum); log|J| = sum of the logs of all n components.  The block occupies n - 1 coordinates of Theta;
+    marginal functions see all n components (ParamView appends the implied one)."""
+    code = T_SIMPLEX
+
+    def __init__(self, n):
+        n = int(n)
+        if n < 2:
+            raise ValueError("a simplex has at least 2 components")
+        super().__init__(n - 1)
+        self.components = n
+
+    def __repr__(self):
+        return "Simplex(%d)" % self.components
+
+
 class parameter:
     """Base class for the struct API: subclasses list their blocks as class attributes, in order.
 
@@ -77,11 +95,19 @@ def blocks_of(spec):
         spec = (spec,)
     if isinstance(spec, (tuple, list)) and all(isinstance(b, _Block) for b in spec) and len(spec) > 0:
         return [("p%d" % (i + 1), b) for i, b in enumerate(spec)]
-    raise TypeError("model must be a parameter subclass or a tuple of RealVector/PositiveVector/ProbabilityVector/NonCentredVector")
+    raise TypeError("model must be a parameter subclass or a tuple of RealVector/PositiveVector/ProbabilityVector/Simplex/NonCentredVector")
 
 
 def transform_codes(blocks):
-    return np.concatenate([np.full(b.n, getattr(b, "code_word", b.code), dtype=np.int32) for _, b in blocks])
+    out, o = [], 0
+    for _, b in blocks:
+        if isinstance(b, Simplex):
+            word = T_SIMPLEX | (o << 8) | (b.n << 16)      # JP_T_SIMPLEX_CODE(first, len) of include/jpcuda.h
+        else:
+            word = getattr(b, "code_word", b.code)
+        out.append(np.full(b.n, word, dtype=np.int32))
+        o += b.n
+    return np.concatenate(out)
 
 
 class ParamView:
@@ -97,6 +123,8 @@ class ParamView:
         o = 0
         for name, b in blocks:
             v = theta[o:o + b.n]
+            if isinstance(b, Simplex):      # all n components: the implied last one is 1 - sum of the stored ones
+                v = np.concatenate([v, 1.0 - np.sum(v, axis=0, keepdims=True)], axis=0)
             setattr(self, name, v)
             self._names.append(name)
             self.blocks.append(v)

@@ -410,9 +410,29 @@ static inline double transform_one(int code, double x, double* lj) {
 
 // code 3 (kind in the low byte, loc in bits 8-15, scale in bits 16-23): non-centred coordinate
 //        theta_k = theta_loc + theta_scale * x_k, log|J| += log(theta_scale); loc, scale < k.
+// code 4 (kind, first coordinate of the block in bits 8-15, length n - 1 in bits 16-23): Simplex block (the type is
+//        exported at reference src/JointPosteriors.jl:26; its map lives in the absent ConstrainedParameters, so the
+//        additive log-ratio map is used): theta_k = e^{x_k} / (1 + sum e^{x_j}), implied last component
+//        1 / (1 + sum e^{x_j}), log|J| = sum of the logs of all n components.
 void orc_transform(const int* code, int d, const double* x, double* theta, double* logjac) {
   double lj = 0;
   for (int k = 0; k < d; ++k) {
+    if ((code[k] & 0xFF) == 4) {
+      int first = (code[k] >> 8) & 0xFF, len = (code[k] >> 16) & 0xFF;
+      if (k != first) continue;                 // the whole block is transformed at its head
+      double mx = 0;
+      for (int j = first; j < first + len; ++j) mx = std::max(mx, x[j]);
+      double S = std::exp(-mx);
+      for (int j = first; j < first + len; ++j) S += std::exp(x[j] - mx);
+      double logS = std::log(S);
+      lj += -mx - logS;
+      for (int j = first; j < first + len; ++j) {
+        double l = x[j] - mx - logS;
+        lj += l;
+        theta[j] = std::exp(l);
+      }
+      continue;
+    }
     if ((code[k] & 0xFF) == 3) {
       double loc = theta[(code[k] >> 8) & 0xFF], sc = theta[(code[k] >> 16) & 0xFF];
       theta[k] = loc + sc * x[k];
@@ -504,6 +524,15 @@ static double ld_linreg(const double* t, int d, const double* obs, long long N, 
   return lp;
 }
 
+// family 5: category counts on a Simplex block: theta = first d = n - 1 components (the last is 1 - sum), obs = one
+// count per category (N = n rows), symmetric Dirichlet(alpha) prior with hyper[0] = alpha - 1.
+static double ld_multinomial(const double* t, int d, const double* obs, long long N, const double* h) {
+  double rest = 1.0, lp = 0;
+  for (int k = 0; k < d; ++k) rest -= t[k];
+  for (long long n = 0; n < N; ++n) lp += (obs[n] + h[0]) * std::log(n < d ? t[n] : rest);
+  return lp;
+}
+
 double orc_log_density(int family, const double* theta, int d, const double* obs, long long N, const double* hyper) {
   switch (family) {
     case 0: return ld_binmix(theta, obs, N, hyper);
@@ -511,6 +540,7 @@ double orc_log_density(int family, const double* theta, int d, const double* obs
     case 2: return ld_poisson(theta, d, obs, N, hyper);
     case 3: return ld_hier(theta, d, obs, N, hyper);
     case 4: return ld_linreg(theta, d, obs, N, hyper);
+    case 5: return ld_multinomial(theta, d, obs, N, hyper);
   }
   return NAN;
 }

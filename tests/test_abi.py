@@ -133,6 +133,12 @@ def test_model_declaration_styles(jp):
     assert m3.d == 10 and list(m3.transform) == [0, 1] + [0] * 8 and m3.build.rule.rule_id == 1 and m3.build.raw
     with pytest.raises(TypeError):
         jp.Model(3)
+    # a Simplex(n) block takes n - 1 coordinates; its code word names the block's first coordinate and length
+    m4 = jp.Model((jp.RealVector(2), jp.Simplex(4), jp.PositiveVector(1)))
+    sx = 4 | (2 << 8) | (3 << 16)
+    assert m4.d == 6 and list(m4.transform) == [0, 0, sx, sx, sx, 1]
+    with pytest.raises(ValueError):
+        jp.Simplex(1)
 
 
 def test_coordinate_selector_detection(jp):
@@ -144,6 +150,10 @@ def test_coordinate_selector_detection(jp):
     assert probe_coordinate(lambda t: t.p3[1] - t.p3[0], m.blocks) is None
     m1 = jp.Model((jp.ProbabilityVector(3),))
     assert probe_coordinate(lambda p: p[0], m1.blocks) == 0
+    # Simplex: the stored components are coordinates, the implied last one is a host closure
+    m2 = jp.Model((jp.RealVector(1), jp.Simplex(3)))
+    assert probe_coordinate(lambda t: t.p2[1], m2.blocks) == 2
+    assert probe_coordinate(lambda t: t.p2[2], m2.blocks) is None
 
 
 def test_data_validation(jp):
@@ -155,3 +165,31 @@ def test_data_validation(jp):
         jp.LogisticData(np.zeros((4, 3)), np.zeros(5))
     obs, hyper = jp.BinaryClassificationData([0, 1], [2, 3], 9, βm=2, βp=2).records()
     assert obs.tolist() == [[0, 2, 9], [1, 3, 8]] and hyper.tolist() == [0, 1, 0, 1, 0, 0]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` runs on the host cores alone and prints ONE JSON line with the contract's keys."""
+    import json
+    import sys
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                                   "--warmup", "0"], text=True, stderr=subprocess.DEVNULL, timeout=600)
+    lines = [l for l in out.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
+              "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "node_x_obs_log_density_evals_per_sec" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_bench_product_arm_needs_a_gpu():
+    """Without a CUDA device the product arm refuses to run: there is no CPU fallback to time."""
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], text=True,
+                       capture_output=True, timeout=600)
+    assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)

@@ -72,6 +72,8 @@ def _family_cases():
     X = rng.standard_normal((100, 3))
     yv = X @ np.array([1.0, -2.0, 0.5]) + 0.7 * rng.standard_normal(100)
     yield "linreg", 4, [0, 0, 0, 1], np.column_stack([X, yv]), np.array([10.0, 1.0])
+    sx = 4 | (0 << 8) | (3 << 16)     # JP_T_SIMPLEX_CODE(first = 0, len = 3): a point of the 4-simplex
+    yield "multinomial", 5, [sx] * 3, np.array([[12.0], [7.0], [3.0], [18.0]]), np.array([0.0])
 
 
 FAMILY_CASES = list(_family_cases())
@@ -89,6 +91,8 @@ class _RawData:
 
 def _model_for(jp, code):
     blocks = []
+    if code and all(c & 0xFF == 4 for c in code):
+        return jp.Model((jp.Simplex(len(code) + 1),))
     for c in code:
         if c & 0xFF == 3:
             blocks.append(jp.NonCentredVector(1, loc=(c >> 8) & 0xFF, scale=(c >> 16) & 0xFF))
@@ -122,7 +126,7 @@ def _cpu_mode_for(O, family, code, obs, hyper):
     if family in (1, 2):
         beta, H, ll = O.glm_mode(family, obs, hyper, d)
         return beta, H, -ll
-    x0 = {0: [0.2, -3.0, -2.0], 3: [4.0, 1.0] + [0.0] * 8, 4: [0.0, 0.0, 0.0, 0.0]}[family]
+    x0 = {0: [0.2, -3.0, -2.0], 3: [4.0, 1.0] + [0.0] * 8, 4: [0.0, 0.0, 0.0, 0.0], 5: [0.0] * d}[family]
     return cpu_mode(O, family, code, obs, hyper, x0)
 
 
@@ -184,6 +188,32 @@ def test_cfg2_eight_schools(jp, O, gpu_ctx):
 def test_small_regressions_fp64(jp, O, gpu_ctx, case):
     name, family, code, obs, hyper = FAMILY_CASES[case]
     _check_fit_and_marginals(jp, O, gpu_ctx, family, code, obs, hyper, 0, 4)
+
+
+def test_simplex_block_against_dirichlet(jp, O, gpu_ctx):
+    """Simplex transform (north star stage 2; ConstrainedParameters Simplex, reference src/JointPosteriors.jl:26) on the
+    multinomial family: parity with the oracle, and the public API against the closed-form Dirichlet posterior."""
+    name, family, code, obs, hyper = FAMILY_CASES[5]
+    _check_fit_and_marginals(jp, O, gpu_ctx, family, code, obs, hyper, 0, 6)
+    counts = obs[:, 0]
+    M = jp.Model((jp.Simplex(4),))
+    post = jp.fit(M, jp.MultinomialData(counts, alpha=1.0), 7)            # GPU mode finder, level 7
+    a = counts + 1.0
+    A = a.sum()
+    ms = [jp.marginal(post, lambda p, k=k: p[k]) for k in range(4)]      # k = 3 is the implied last component
+    for k, m in enumerate(ms):
+        assert abs(m.mu - a[k] / A) < 1e-4 * a[k] / A
+        assert abs(m.sigma - np.sqrt(a[k] * (A - a[k]) / (A * A * (A + 1)))) < 2e-4 * m.sigma
+    th = post.Theta
+    assert np.all(th > 0) and np.all(th.sum(axis=0) < 1)
+    # a block that does not carry one code word, or that leaves [0, d), is refused
+    dd = gpu_ctx.upload(jp.MultinomialData(counts))
+    for bad in ([4 | (3 << 16), 4 | (2 << 16), 4 | (3 << 16)], [4 | (1 << 8) | (3 << 16)] * 3, [4 | (0 << 16)] * 3):
+        bad = np.array(bad, dtype=np.int32)
+        x, out = np.zeros((1, 3)), np.zeros(1)
+        st = jp.lib().jp_log_density_points(gpu_ctx.handle, dd.handle, 3, bad.ctypes.data_as(C.c_void_p), C.c_longlong(1),
+                                            x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        assert st == 1
 
 
 def test_gpu_mode_matches_cpu_mode(jp, O, gpu_ctx):

@@ -332,3 +332,33 @@ def test_level_beyond_rule_table(O):
     assert len(w) == 35 and abs(w.sum() - 1) < 1e-13
     idx, w = O.smolyak(0, 2, 11)
     assert len(w) == 35 * 35 and abs(w.sum() - 1) < 1e-12
+
+
+def test_simplex_transform_dirichlet_truth(O):
+    """Simplex block (additive log-ratio map) on category counts with a Dirichlet prior: the posterior is
+    Dirichlet(alpha + counts) in closed form, and the sparse-grid marginals converge to its moments -- an analytic pin
+    for the transform, its log-Jacobian and the implied last component."""
+    from conftest import cpu_mode
+    counts, alpha = np.array([12.0, 7.0, 3.0, 18.0]), 1.0
+    code = np.array([4 | (0 << 8) | (3 << 16)] * 3, dtype=np.int32)
+    obs, hyper = counts[:, None].copy(), np.array([alpha - 1.0])
+    th, lj = O.transform(code, np.array([0.3, -0.2, 1.1]))
+    assert np.isclose(lj, np.log(th).sum() + np.log(1 - th.sum()), rtol=1e-14) and 0 < th.sum() < 1
+    x, H, f = cpu_mode(O, 5, code, obs, hyper, np.zeros(3))
+    # the mode of the unconstrained density is the Dirichlet(alpha + c + 1) mode: theta_k = (a_k) / sum in ALR coordinates
+    a = counts + alpha
+    assert np.allclose(O.transform(code, x)[0], a[:3] / a.sum(), atol=1e-6)
+    A = a.sum()
+    mean, sd = a / A, np.sqrt(a * (A - a) / (A * A * (A + 1)))
+    U = O.inv_chol(2 * H)
+    errs = []
+    for L in (5, 7):
+        idx, w = O.smolyak(0, 3, L)
+        ref = O.eval_grid(0, 5, code, idx, w, x, U, f, obs, hyper)
+        t = ref["theta"]
+        vals = [t[0], t[1], t[2], 1 - t[0] - t[1] - t[2]]
+        ms = [O.marginal(v, ref["density"]) for v in vals]
+        errs.append((max(abs(m["mu"] - mean[k]) / mean[k] for k, m in enumerate(ms)),
+                     max(abs(m["sigma"] - sd[k]) / sd[k] for k, m in enumerate(ms))))
+    assert errs[0][0] < 2e-3 and errs[0][1] < 6e-3
+    assert errs[1][0] < 5e-5 and errs[1][1] < 1e-4
