@@ -163,6 +163,18 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                "r"(bytes), "r"(bar)
                : "memory");
 }
+// one lane of a converged warp (the same lane every time: the lowest)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -186,6 +198,23 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// The same with the descriptors given by their low words (the high word 0x40004040 -- SBO 1024 bytes, version 1,
+// 128-byte swizzle -- is a constant): the low word of a descriptor is affine in the shared-memory address,
+// lo(addr + off) = lo(addr) + (off >> 4), so the issuer advances it with one add per operand and instruction.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_tf32_lo(uint32_t tmem_d, uint32_t lo_a, uint32_t lo_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(lo_a), "r"(lo_b), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t (&v)[16], uint32_t taddr) {
@@ -534,7 +563,12 @@ struct TcKernelParams {
   const float* coef;      // [TC_NCMAX][N_pad]
   long long N_pad;
   double* part;           // [chunks][P][2]: even and odd part of the remainder sum of a pair
+  long long* dbg;         // profiling builds, MODE 5: per-tile clock64 stamps of CTA 0 ([6][TC_DBG_TILES]), else null
 };
+#define TC_DBG_TILES 2048
+// MODE 5 timeline rows: 0 producer issues the tile's TMA, 1 MMA issuer starts waiting for the tile's accumulator buffer,
+// 2 MMA issued, 3 epilogue warp 2 starts waiting for the tile's accumulator, 4 its wait returns
+#define TC_STAMP(row, n) do { if (MODE == 5 && P.dbg && blockIdx.x == 0 && (n) < TC_DBG_TILES) P.dbg[(row) * TC_DBG_TILES + (n)] = clock64(); } while (0)
 
 // Packed FP32 arithmetic (Blackwell FFMA2 / FMUL2): one instruction works on two adjacent pair columns, which
 // halves the issue slots of the epilogue (the FMA pipe itself retires 32 lanes x 2 per two cycles either way).
@@ -672,23 +706,33 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   const int n_items = P.n_pair_tiles * P.chunks;
+  // The producer and the issuer run their loops with the WHOLE warp converged and only predicate the asynchronous
+  // instructions on one elected lane: addresses, descriptors, ring indices and phases are then provably warp-uniform
+  // and live on the uniform datapath.  (Inside an `if (lane == 0)` region the compiler wraps every tcgen05.mma / TMA
+  // in an elect + R2UR + vote loop, ~100 cycles of dependent latency each: the issuer then needs a full tile time for
+  // its 4 .. 12 MMAs, runs in lockstep with the epilogue instead of TC_NBUF tiles ahead, and the MMA time shows up on
+  // the critical path -- measured with the MODE 5 timeline, profiles/r01_tc_attribution.txt.)
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0, bb = 0, cslot = 0;
-      uint32_t phase = 0, bphase = 0;   // bphase: bit b = parity of pair-operand buffer b
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int chunk = item / P.n_pair_tiles, pair_tile = item % P.n_pair_tiles;
-        const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
-        mbar_wait_relaxed(bar_bempty + 8u * bb, ((bphase >> bb) & 1u) ^ 1u);
+    const bool leader = elect_one();
+    int stage = 0, bb = 0, cslot = 0, ntile = 0;
+    uint32_t phase = 0, bphase = 0;   // bphase: bit b = parity of pair-operand buffer b
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int chunk = item / P.n_pair_tiles, pair_tile = item % P.n_pair_tiles;
+      const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
+      mbar_wait_relaxed(bar_bempty + 8u * bb, ((bphase >> bb) & 1u) ^ 1u);
+      if (leader) {
         mbar_expect_tx(bar_bfull + 8u * bb, b_bytes);
         for (int a = 0; a < P.kb; ++a)
           tma_load_2d(sB + (uint32_t)bb * b_bytes + (uint32_t)a * TC_PAIR_TILE * 128u, &tmB, bar_bfull + 8u * bb,
                       a * TC_KATOM, pair_tile * TC_PAIR_TILE);
-        bphase ^= 1u << bb;
-        if (++bb == P.nbbuf) bb = 0;
-        for (int t = t0; t < t1; ++t) {
-          mbar_wait_relaxed(bar_empty + 8u * stage, phase ^ 1);
+      }
+      bphase ^= 1u << bb;
+      if (++bb == P.nbbuf) bb = 0;
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait_relaxed(bar_empty + 8u * stage, phase ^ 1);
+        if (leader) {
+          TC_STAMP(0, ntile);
           mbar_expect_tx(bar_full + 8u * stage, a_bytes + c_bytes);
           for (int a = 0; a < P.ka; ++a)
             tma_load_2d(sA + (uint32_t)stage * a_bytes + (uint32_t)a * TC_OBS_TILE * 128u, &tmA, bar_full + 8u * stage,
@@ -697,52 +741,59 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int k = 0; k < NC; ++k)
             bulk_load_1d(sC + (uint32_t)cslot * c_bytes + (uint32_t)k * TC_OBS_TILE * 4u,
                          P.coef + (size_t)k * P.N_pad + (size_t)t * TC_OBS_TILE, TC_OBS_TILE * 4u, bar_full + 8u * stage);
-          if (++cslot == n_cslots) cslot = 0;
-          if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
+        ++ntile;
+        if (++cslot == n_cslots) cslot = 0;
+        if (++stage == P.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
-      // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 96 pairs, M = 128 observations
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_PAIR_TILE >> 3) << 17) |
-                             ((uint32_t)(TC_OBS_TILE >> 4) << 24);
-      int stage = 0, buf = 0, bb = 0;
-      uint32_t phase = 0, bphase = 0, tphase = 0;   // tphase: bit b = parity of accumulator buffer b
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int chunk = item / P.n_pair_tiles;
-        const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
-        mbar_wait_relaxed(bar_bfull + 8u * bb, (bphase >> bb) & 1u);
-        for (int t = t0; t < t1; ++t) {
-          mbar_wait_relaxed(bar_tempty + 8u * buf, ((tphase >> buf) & 1u) ^ 1u);
-          mbar_wait_relaxed(bar_full + 8u * stage, phase);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC_TMEM_STRIDE;
-          if (MODE >= 3) {   // two dummy atom products, overwritten by the real contraction below
-            for (int r = 0; r < 8; ++r)
-              umma_tf32(d_tmem, umma_desc(sA + (uint32_t)stage * a_bytes + 32u * (r & 3)),
-                        umma_desc(sB + (uint32_t)bb * b_bytes + 32u * (r & 3)), idesc, 0u);
+    const bool leader = elect_one();
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 96 pairs, M = 128 observations
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_PAIR_TILE >> 3) << 17) |
+                           ((uint32_t)(TC_OBS_TILE >> 4) << 24);
+    int stage = 0, buf = 0, bb = 0, ntile = 0;
+    uint32_t phase = 0, bphase = 0, tphase = 0;   // tphase: bit b = parity of accumulator buffer b
+    const uint32_t loA0 = umma_desc_lo(sA), loB0 = umma_desc_lo(sB), a_step = a_bytes >> 4, b_step = b_bytes >> 4;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int chunk = item / P.n_pair_tiles;
+      const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
+      mbar_wait_relaxed(bar_bfull + 8u * bb, (bphase >> bb) & 1u);
+      const uint32_t loB = loB0 + (uint32_t)bb * b_step;
+      for (int t = t0; t < t1; ++t) {
+        if (leader) TC_STAMP(1, ntile);
+        mbar_wait_relaxed(bar_tempty + 8u * buf, ((tphase >> buf) & 1u) ^ 1u);
+        if (leader) TC_STAMP(5, ntile);      // row 5: accumulator buffer free, now waiting for the observation tile
+        mbar_wait_relaxed(bar_full + 8u * stage, phase);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC_TMEM_STRIDE;
+        const uint32_t loA = loA0 + (uint32_t)stage * a_step;
+        if (leader) {
+          TC_STAMP(2, ntile);
+          if (MODE == 3 || MODE == 4) {   // two dummy atom products, overwritten by the real contraction below
+            for (int r = 0; r < 8; ++r) umma_tf32_lo(d_tmem, loA + 2u * (r & 3), loB + 2u * (r & 3), idesc, 0u);
           }
+#pragma unroll 1
           for (int a = 0; a < P.kb; ++a) {
             // split layout: the last product (x_hi . d_lo) takes the observation row's first atom again
-            const int a_obs = (a < P.ka) ? a : 0;
-            const uint32_t aA = sA + (uint32_t)stage * a_bytes + (uint32_t)a_obs * TC_OBS_TILE * 128u;
-            const uint32_t aB = sB + (uint32_t)bb * b_bytes + (uint32_t)a * TC_PAIR_TILE * 128u;
+            const uint32_t la = loA + ((a < P.ka) ? (uint32_t)a * (TC_OBS_TILE * 128u >> 4) : 0u);
+            const uint32_t lb = loB + (uint32_t)a * (TC_PAIR_TILE * 128u >> 4);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)   // K = 8 tf32 = 32 bytes per instruction inside the 128-byte atom
-              umma_tf32(d_tmem, umma_desc(aA + 32u * j), umma_desc(aB + 32u * j), idesc, (a | j) ? 1u : 0u);
+            for (int j = 0; j < 4; ++j)   // K = 8 tf32 = 32 bytes (2 descriptor units) per instruction inside the atom
+              umma_tf32_lo(d_tmem, la + 2u * j, lb + 2u * j, idesc, (a | j) ? 1u : 0u);
           }
           tc_commit(bar_empty + 8u * stage);        // frees the observation stage when the MMAs have read it
           tc_commit(bar_tfull + 8u * buf);          // publishes the accumulator buffer
-          tphase ^= 1u << buf;
-          if (++buf == TC_NBUF) buf = 0;
-          if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(bar_bempty + 8u * bb);            // pair operand may be overwritten once every MMA has retired
-        bphase ^= 1u << bb;
-        if (++bb == P.nbbuf) bb = 0;
+        ++ntile;
+        tphase ^= 1u << buf;
+        if (++buf == TC_NBUF) buf = 0;
+        if (++stage == P.stages) { stage = 0; phase ^= 1; }
       }
+      if (leader) tc_commit(bar_bempty + 8u * bb);  // pair operand may be overwritten once every MMA has retired
+      bphase ^= 1u << bb;
+      if (++bb == P.nbbuf) bb = 0;
     }
   } else {
     // ===================================================== epilogue warps
@@ -752,7 +803,7 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t accE[TC_COLS_PER_WARP / 2], accO[TC_COLS_PER_WARP / 2];   // FP32 sums, packed in pairs of adjacent columns
 #pragma unroll
     for (int j = 0; j < TC_COLS_PER_WARP / 2; ++j) accE[j] = accO[j] = 0ull;
-    int buf = 0, cslot = 0;
+    int buf = 0, cslot = 0, ntile = 0;
     uint32_t tphase = 0;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * TC_COLS_PER_WARP);
     const uint32_t coef_addr = sC + (uint32_t)(q * 32 + lane) * 4u;   // this thread's observation: tile row = TMEM lane
@@ -790,7 +841,9 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8u * buf);
             if (more) {
+              if (warp == 2 && lane == 0) TC_STAMP(3, ntile + 1);
               mbar_wait(bar_tfull + 8u * nbuf, (tphase >> nbuf) & 1u);
+              if (warp == 2 && lane == 0) TC_STAMP(4, ntile + 1);
               tphase ^= 1u << nbuf;
               tc_fence_after();
               if (MODE != 2 && MODE != 4) tmem_ld(nxt, lane_addr + (uint32_t)nbuf * TC_TMEM_STRIDE);
@@ -800,10 +853,13 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_accumulate<NC, MODE, TC_LDW>(cur, cc, accE + c * (TC_LDW / 2), accO + c * (TC_LDW / 2));
         }
         buf = nbuf;
+        ++ntile;
       };
       int t = t0;
       const bool odd = ((t1 - t0) & 1) != 0;
+      if (warp == 2 && lane == 0) TC_STAMP(3, ntile);
       mbar_wait(bar_tfull + 8u * buf, (tphase >> buf) & 1u);
+      if (warp == 2 && lane == 0) TC_STAMP(4, ntile);
       tphase ^= 1u << buf;
       tc_fence_after();
       tmem_ld(va, lane_addr + (uint32_t)buf * TC_TMEM_STRIDE);
@@ -1058,6 +1114,24 @@ static int launch_tc(jp_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB
   if (mode == 2) return launch_tc_mode<NC, 2>(ctx, tmA, tmB, kp, smem);
   if (mode == 3) return launch_tc_mode<NC, 3>(ctx, tmA, tmB, kp, smem);
   if (mode == 4) return launch_tc_mode<NC, 4>(ctx, tmA, tmB, kp, smem);
+  if (mode == 5) {   // per-tile timeline of CTA 0, dumped as 6 x TC_DBG_TILES int64 to $JP_TC_TIMELINE after every launch
+    static long long* d_dbg = nullptr;
+    if (!d_dbg) JP_CUDA(cudaMalloc(&d_dbg, sizeof(long long) * 6 * TC_DBG_TILES));
+    JP_CUDA(cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 6 * TC_DBG_TILES, ctx->stream));
+    TcKernelParams k2 = kp;
+    k2.dbg = d_dbg;
+    JP_TRY((launch_tc_mode<NC, 5>)(ctx, tmA, tmB, k2, smem));
+    std::vector<long long> h(6 * TC_DBG_TILES);
+    JP_CUDA(cudaMemcpyAsync(h.data(), d_dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    JP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (const char* path = getenv("JP_TC_TIMELINE")) {
+      if (FILE* f = fopen(path, "wb")) {
+        fwrite(h.data(), sizeof(long long), h.size(), f);
+        fclose(f);
+      }
+    }
+    return JP_OK;
+  }
 #endif
   return launch_tc_mode<NC, 0>(ctx, tmA, tmB, kp, smem);
 }
@@ -1163,6 +1237,7 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   kp.coef = ds->d_coef;
   kp.N_pad = ds->N_pad;
   kp.part = ps->d_part;
+  kp.dbg = nullptr;
   int stc;
   if (NC == 4) stc = launch_tc<4>(ctx, ds->tmA, ps->tmB, kp, smem);
   else if (NC == 6) stc = launch_tc<6>(ctx, ds->tmA, ps->tmB, kp, smem);
