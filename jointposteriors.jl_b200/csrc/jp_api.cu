@@ -275,6 +275,14 @@ int jp_fit_diagnostics(const jp_posterior* p, double* h_out8) {
 
 static int download(jp_posterior* p, const double* d_src, double* h_dst, size_t n) {
   JP_REQUIRE(p && h_dst, "jp_get_*: null argument");
+  // The caller's array is pageable (a Julia Vector / numpy array): results that fit the context's pinned buffer are
+  // DMA-ed there at PCIe speed and copied out by the host; larger ones take the driver's staged pageable path.
+  if (n <= JP_PINNED_DOUBLES) {
+    JP_CUDA(cudaMemcpyAsync(p->ctx->h_pinned, d_src, n * 8, cudaMemcpyDeviceToHost, p->ctx->stream));
+    JP_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    std::memcpy(h_dst, p->ctx->h_pinned, n * 8);
+    return JP_OK;
+  }
   JP_CUDA(cudaMemcpyAsync(h_dst, d_src, n * 8, cudaMemcpyDeviceToHost, p->ctx->stream));
   JP_CUDA(cudaStreamSynchronize(p->ctx->stream));
   return JP_OK;

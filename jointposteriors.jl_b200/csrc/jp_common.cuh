@@ -92,7 +92,7 @@ inline void jp_dfree(jp_ctx* ctx, const void* p) {
   if (p) cudaFreeAsync(const_cast<void*>(p), ctx->stream);
 }
 #define JP_SCRATCH_DOUBLES (1 << 16)
-#define JP_PINNED_DOUBLES (1 << 16)
+#define JP_PINNED_DOUBLES (1 << 18)   // 2 MB: result vectors of up to 262 144 nodes are downloaded through it
 
 struct jp_data {
   jp_ctx* ctx = nullptr;
