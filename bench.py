@@ -134,7 +134,8 @@ def run_reference(args):
     obs, hyper = data.records()
     d = wl["d"]
     fam = data.family
-    code = np.concatenate([np.full(b.n, b.code, dtype=np.int32) for b in wl["params"]])
+    from jointposteriors_jl_b200.params import blocks_of, transform_codes
+    code = transform_codes(blocks_of(wl["params"]))
     cores = O.num_threads()
     if fam in (1, 2):
         # mode on a subsample is enough to place the sample nodes (timing only)
