@@ -168,7 +168,7 @@ def run_reference(args):
     sample = "first %d of %d merged grid nodes x all %d observations per step (fit + %d coordinate marginals), %d threads" % (
         m_step, len(w), N, d, cores)
     out = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
-               higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
+               higher_is_better=True, scaling="weak" if args.workload == "cfg3" else "strong", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
                config=dict(workload=wl["desc"], sample=sample),
                cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind="port", sample=sample),
                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
@@ -453,7 +453,9 @@ def run_product(args):
     if rank == 0:
         cpu = cpu_baseline(wl, (x, U, neg_min)) if world == 1 and not args.no_cpu_baseline else None
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                   ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+                   ms_per_step=ms_per_step, higher_is_better=True,
+                   scaling="weak" if args.workload == "cfg3" else "strong",   # cfg3 grows N with the GPU count; cfg4/5 are fixed
+                   vs_baseline=None,
                    dtype="tf32x3+f64" if path_used == _lib.PATH_TC else "f64", data="synthetic",
                    config=dict(workload=wl["desc"], nodes=Mtot, obs=int(N), d=d, level=wl["level"],
                                parallelism="node-sharded x%d" % world if args.emulate_shard <= 1 else
