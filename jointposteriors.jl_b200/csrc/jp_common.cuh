@@ -208,6 +208,12 @@ __device__ __forceinline__ double jp_block_min(double v, double* smem) {
   __syncthreads();
   return smem[32];
 }
+// asynchronous global -> shared copies (LDGSTS): many bytes in flight per thread without register staging
+__device__ __forceinline__ void jp_cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void jp_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void jp_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // Multi-block reduction, second stage in the same launch: every block publishes its partial, the block that arrives
 // last (arrival counter, self-resetting) combines the partials in block order -- deterministic -- and writes the result.
 // Call with all threads after the block's partial has been written by thread 0; true in the last block only.

@@ -30,13 +30,16 @@ jp_glm_partials_kernel(int family, int d, long long N, const double* __restrict_
   const int nb = (d + BS - 1) / BS, npairs = nb * (nb + 1) / 2;
   const int rs = nb * BS + 2;                      // row stride: = 2 (mod 4) doubles -> conflict-free 16-byte loads
   const int S = min(JP_GLM_THREADS / npairs, JP_GLM_TILE), iters = JP_GLM_TILE / S, T = S * iters;
-  double* tile = sh;                               // JP_GLM_TILE x rs (columns >= d stay zero)
-  double* res = tile + JP_GLM_TILE * rs;           // JP_GLM_TILE
+  // two record tiles: the asynchronous copies (cp.async, 8 bytes each, no register staging) of tile i + 1 are in flight
+  // while tile i is consumed -- with a load -> store loop the kernel was bound by the latency of ~1 KB in flight per warp
+  double* tile0 = sh;                              // 2 x JP_GLM_TILE x rs (columns >= d stay zero)
+  double* ybuf0 = tile0 + 2 * JP_GLM_TILE * rs;    // 2 x JP_GLM_TILE: the responses of a tile
+  double* res = ybuf0 + 2 * JP_GLM_TILE;           // JP_GLM_TILE
   double* wgt = res + JP_GLM_TILE;                 // JP_GLM_TILE
   double* s_beta = wgt + JP_GLM_TILE;              // d
   __shared__ double red[33];
   for (int k = threadIdx.x; k < d; k += JP_GLM_THREADS) s_beta[k] = beta[k];
-  for (int k = threadIdx.x; k < JP_GLM_TILE * rs; k += JP_GLM_THREADS) tile[k] = 0.0;
+  for (int k = threadIdx.x; k < 2 * JP_GLM_TILE * rs; k += JP_GLM_THREADS) tile0[k] = 0.0;
   // this thread's block (br <= bc) of the upper block triangle and its observation slice
   const int pair = threadIdx.x / S, slice = threadIdx.x - pair * S;
   const bool active = pair < npairs;
@@ -55,28 +58,40 @@ jp_glm_partials_kernel(int family, int d, long long N, const double* __restrict_
     for (int j = 0; j < BS; ++j) acc[i][j] = 0.0;
   }
   double ll = 0.0;
-  for (long long base = (long long)blockIdx.x * T; base < N; base += (long long)gridDim.x * T) {
-    const int cnt = (int)min((long long)T, N - base);
-    __syncthreads();     // the previous tile is consumed (first pass: zero fill and s_beta are visible)
-    {
-      // flat coalesced copy of cnt records; (row, column) advance by (threads / ncols, threads % ncols) per step
+  // flat coalesced copy of a tile's records; (row, column) advance by (threads / ncols, threads % ncols) per step
+  auto issue_tile = [&](long long base, int b) {
+    if (base < N) {
+      const int cnt = (int)min((long long)T, N - base);
       const double* src = obs + (size_t)base * ncols;
+      double* tl = tile0 + (size_t)b * JP_GLM_TILE * rs;
+      double* yb = ybuf0 + b * JP_GLM_TILE;
       int row = threadIdx.x / ncols, col = threadIdx.x - row * ncols;
       const int drow = JP_GLM_THREADS / ncols, dcol = JP_GLM_THREADS - drow * ncols;
       for (int e = threadIdx.x; e < cnt * ncols; e += JP_GLM_THREADS) {
-        const double v = __ldg(src + e);
-        if (col < d) tile[row * rs + col] = v; else res[row] = v;   // y parks in res until the residual replaces it
+        jp_cp_async8((col < d) ? (tl + row * rs + col) : (yb + row), src + e);
         row += drow;
         col += dcol;
         if (col >= ncols) { col -= ncols; ++row; }
       }
     }
-    __syncthreads();
+    jp_cp_async_commit();
+  };
+  __syncthreads();       // the zero fill precedes the first asynchronous copies
+  const long long step = (long long)gridDim.x * T;
+  issue_tile((long long)blockIdx.x * T, 0);
+  int cur = 0;
+  for (long long base = (long long)blockIdx.x * T; base < N; base += step, cur ^= 1) {
+    const int cnt = (int)min((long long)T, N - base);
+    jp_cp_async_wait_all();
+    __syncthreads();     // tile `cur` has landed for every thread; the previous tile (in the other buffer) is consumed
+    issue_tile(base + step, cur ^ 1);
+    const double* tile = tile0 + (size_t)cur * JP_GLM_TILE * rs;
+    const double* yb = ybuf0 + cur * JP_GLM_TILE;
     for (int n = threadIdx.x; n < T; n += JP_GLM_THREADS) {
       double rv = 0.0, wv = 0.0;
       if (n < cnt) {
         const double* r = tile + n * rs;
-        const double y = res[n];
+        const double y = yb[n];
         double eta = 0;
         for (int k = 0; k < d; ++k) eta += r[k] * s_beta[k];
         double mu;
@@ -126,7 +141,8 @@ jp_glm_partials_kernel(int family, int d, long long N, const double* __restrict_
   // slices -> block partial: one block pair at a time through shared memory (the tile is free now)
   double* o = part + (size_t)blockIdx.x * (nE + 1);
   constexpr int NV = BS * BS + BS;
-  double* buf = tile;                              // [S][NV]
+  jp_cp_async_wait_all();
+  double* buf = tile0;                             // [S][NV]
   for (int pp = 0; pp < npairs; ++pp) {
     __syncthreads();
     if (active && pair == pp) {
@@ -175,8 +191,8 @@ static int launch_partials(jp_ctx* ctx, const jp_data* data, int d, const double
   const int nb = (d + BS - 1) / BS, npairs = nb * (nb + 1) / 2, rs = nb * BS + 2;
   const int S = std::min(JP_GLM_THREADS / npairs, JP_GLM_TILE);
   // the slice buffer of the final reduction reuses the tile
-  size_t tile_doubles = std::max<size_t>((size_t)JP_GLM_TILE * rs, (size_t)S * (BS * BS + BS));
-  size_t smem = (tile_doubles + 2 * JP_GLM_TILE + d) * sizeof(double);
+  size_t tile_doubles = std::max<size_t>((size_t)2 * JP_GLM_TILE * rs, (size_t)S * (BS * BS + BS));
+  size_t smem = (tile_doubles + 4 * JP_GLM_TILE + d) * sizeof(double);
   if (smem > 48 * 1024)
     JP_CUDA(cudaFuncSetAttribute(jp_glm_partials_kernel<BS, JP_GLM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   jp_glm_partials_kernel<BS, JP_GLM_THREADS><<<nblocks, JP_GLM_THREADS, smem, ctx->stream>>>(data->family, d, data->N, data->d_obs, d_beta, nE,

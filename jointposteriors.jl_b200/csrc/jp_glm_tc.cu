@@ -61,7 +61,7 @@ int jp_glm_num_blocks(const jp_ctx* ctx, long long N);
 #ifndef TC_LDW
 #define TC_LDW 8                 // columns per tcgen05.ld of the epilogue (8 or 16)
 #endif
-#define TC_PREP_BLOCKS 592       // 4 per SM: 8 x 40 KB of staged records keep the FP64 pipe fed
+#define TC_PREP_BLOCKS 444       // 3 per SM (two 32 KB record tiles each at d = 30)
 #define TC_NORD 5                // series lengths NC = 4, 6, 8, 10, 12 (orders 6 .. 14)
 #define TC_NBOUND (14 + 2 * TC_NFOLD)   // per-block bound partials, see tc_obs_prep_kernel
 #define TC_COEF_ROWS (TC_NCMAX + 1)     // coefficient rows per observation + the row of t_i = |U' x_i|
@@ -304,7 +304,7 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
   const int p4 = (p + 3) & ~3, rs = ncols | 1;
   double* s_mu = sh;                       // d
   double* s_U = sh + ((d + 1) & ~1);       // d x p4 row-major: s_U[k * p4 + j] = U[k + j * d]  (16-byte aligned rows)
-  double* s_tile = s_U + (size_t)d * p4;   // TC_PREP_THREADS x rs
+  double* s_tile = s_U + (size_t)d * p4;   // 2 x TC_PREP_THREADS x rs
   __shared__ double red[33];
   __shared__ int s_kend[16];               // per block of four columns of U: one past its last non-zero row
   for (int k = threadIdx.x; k < d; k += blockDim.x) s_mu[k] = mu[k];
@@ -322,29 +322,38 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
   }
   double b_tmax = 0, b_a1 = 0, b_ref[TC_NORD] = {0}, b_max[TC_NORD] = {0}, b_r = 0, b_r2 = 0;
   double f_ref[TC_NFOLD] = {0}, f_max[TC_NFOLD] = {0};
-  for (long long base = (long long)blockIdx.x * TC_PREP_THREADS; base < N_pad; base += (long long)gridDim.x * TC_PREP_THREADS) {
-    __syncthreads();     // the previous tile is consumed (and s_mu / s_U are visible)
+  // two record tiles: the asynchronous copies (cp.async) of the next tile are in flight while the current one is consumed
+  // flat coalesced copy; (row, column) of element e advance by (128 / ncols, 128 % ncols) per step: no division
+  auto issue_tile = [&](long long base, int b) {
     const long long cnt = min((long long)TC_PREP_THREADS, N - base);
     if (cnt > 0) {
       const double* src = obs + (size_t)base * ncols;
-      // flat coalesced copy; (row, column) of element e advance by (128 / ncols, 128 % ncols) per step: no division
+      double* tl = s_tile + (size_t)b * TC_PREP_THREADS * rs;
       int row = threadIdx.x / ncols, col = threadIdx.x - row * ncols;
       const int drow = TC_PREP_THREADS / ncols, dcol = TC_PREP_THREADS - drow * ncols;
       for (int e = threadIdx.x; e < (int)cnt * ncols; e += TC_PREP_THREADS) {
-        s_tile[row * rs + col] = __ldg(src + e);
+        jp_cp_async8(tl + row * rs + col, src + e);
         row += drow;
         col += dcol;
         if (col >= ncols) { col -= ncols; ++row; }
       }
     }
-    __syncthreads();
+    jp_cp_async_commit();
+  };
+  const long long step = (long long)gridDim.x * TC_PREP_THREADS;
+  issue_tile((long long)blockIdx.x * TC_PREP_THREADS, 0);
+  int cur = 0;
+  for (long long base = (long long)blockIdx.x * TC_PREP_THREADS; base < N_pad; base += step, cur ^= 1) {
+    jp_cp_async_wait_all();
+    __syncthreads();     // tile `cur` has landed; the previous tile is consumed (and s_mu / s_U are visible)
+    issue_tile(base + step, cur ^ 1);
     const long long i = base + threadIdx.x;
     float* o = coef + i;     // o[k * N_pad]
     if (i >= N) {
       for (int k = 0; k < TC_COEF_ROWS; ++k) o[(size_t)k * N_pad] = 0.f;
       continue;
     }
-    const double* r = s_tile + threadIdx.x * rs;
+    const double* r = s_tile + ((size_t)cur * TC_PREP_THREADS + threadIdx.x) * rs;
     double eta = 0;
     for (int k = 0; k < d; ++k) eta += r[k] * s_mu[k];
     double t2 = 0;
@@ -1154,7 +1163,7 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   JP_TRY(jp_glm_sums_device(ctx, data, d, post->d_mu, ds->d_sums, ds->d_work, ds->glm_blocks));
   // per-observation coefficients + bounds
   const double z_max = std::sqrt(post->grid->zmax2), z_ref = std::min(z_max, 6.0);
-  const size_t sm_obs = (size_t)(((d + 1) & ~1) + d * ((p + 3) & ~3) + TC_PREP_THREADS * (data->ncols | 1)) * 8;
+  const size_t sm_obs = (size_t)(((d + 1) & ~1) + d * ((p + 3) & ~3) + 2 * TC_PREP_THREADS * (data->ncols | 1)) * 8;
   if (sm_obs > 48 * 1024)
     JP_CUDA(cudaFuncSetAttribute(tc_obs_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_obs));
   tc_obs_prep_kernel<<<TC_PREP_BLOCKS, TC_PREP_THREADS, sm_obs, st>>>(data->family, d, p, data->ncols, data->N, ds->N_pad, data->d_obs,
