@@ -460,6 +460,7 @@ def run_product(args):
                    config=dict(workload=wl["desc"], nodes=Mtot, obs=int(N), d=d, level=wl["level"],
                                parallelism="node-sharded x%d" % world if args.emulate_shard <= 1 else
                                "DIAGNOSTIC: node block of rank 0 of %d on one GPU" % args.emulate_shard, path="tc" if path_used == _lib.PATH_TC else "fp64",
+                               prep=getattr(loc, "last_prep", "replicated") if world > 1 else "single",
                                l2="256 MiB flush buffer written between timed iterations",
                                marginals="%d coordinate marginals per step (moments + 100-knot Grid CDF)" % d),
                    fit_ms=tot_fit_ms / args.steps, marginal_ms=tot_marg_ms / args.steps, grid_build_ms=t_grid,

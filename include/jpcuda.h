@@ -218,6 +218,24 @@ int jp_fit_normalise(jp_posterior* post, const double* d_global_sum);
 int jp_fit_local_stats(jp_posterior* post, const jp_fit_args* args, double* d_stats);
 int jp_fit_normalise_gathered(jp_posterior* post, const double* d_gathered, int world, int rank);
 
+/* Node-sharded fit on the tensor-core path with its O(N) FP64 prep (X'WX sums, per-observation series coefficients)
+ * sharded by OBSERVATION: rank r prepares observation slice r only, so the work replicated on every rank stays
+ * O(N / world).  Sequence per fit (device buffers; collectives by the caller, on ctx's stream):
+ *   jp_fit_prep_local(post, args, rank, world, d_out[L])          L = jp_fit_prep_len(d); asynchronous
+ *   all_gather -> g[world][L]
+ *   jp_fit_prep_gathered(post, args, g, world, rank, &n_rows)     sums combined in rank order, series length decided
+ *                                                                 (one host sync), this rank's slice folded
+ *   jp_fit_coef_rows(post, &d_coef, &row_stride, &n_loc)          all_gather IN PLACE row k = 0 .. n_rows-1:
+ *                                                                 float d_coef[k*row_stride + r*n_loc .. + n_loc) from rank r
+ *   jp_fit_local_stats_prepared(post, args, d_out[2])             = jp_fit_local_stats without the prep
+ * JP_ERR_UNSUPPORTED from the first two calls (not a GLM / bounds not met) means: use jp_fit_local_stats. */
+int jp_fit_prep_len(int d);
+int jp_fit_prep_local(jp_posterior* post, const jp_fit_args* args, int rank, int world, double* d_out);
+int jp_fit_prep_gathered(jp_posterior* post, const jp_fit_args* args, const double* d_gathered, int world, int rank,
+                         int* n_rows);
+int jp_fit_coef_rows(jp_posterior* post, void** d_coef, long long* row_stride, long long* n_loc);
+int jp_fit_local_stats_prepared(jp_posterior* post, const jp_fit_args* args, double* d_stats);
+
 /* results to the host (blocking).  h_theta: d x M_local row-major (coordinate k of node m at
  * [k*M_local + m]); h_logdens: log-density + neg_min per node; h_density: normalised weights. */
 int jp_get_theta(jp_posterior* post, double* h_theta);

@@ -243,6 +243,13 @@ int jp_grid_build(jp_ctx* ctx, int rule, int d, int level, jp_grid* g);
 int jp_fit_fp64_launch(jp_posterior* post, const jp_fit_args* args);   // stages 2-3, generic plugin kernel
 int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args);     // stages 2-3, GLM tensor-core path
 bool jp_fit_tc_supported(const jp_posterior* post, const jp_fit_args* args);
+// the tensor-core path phase by phase (observation-sharded prep of a node-sharded fit)
+int jp_fit_tc_prep_len(int d);
+int jp_fit_tc_prep_local(jp_posterior* post, const jp_fit_args* args, int rank, int world, double* d_out);
+int jp_fit_tc_prep_gathered(jp_posterior* post, const jp_fit_args* args, const double* d_gathered, int world, int rank,
+                            int* n_rows);
+int jp_fit_tc_coef_rows(jp_posterior* post, float** d_coef, long long* row_stride, long long* n_loc);
+int jp_fit_tc_run_prepared(jp_posterior* post, const jp_fit_args* args);
 void jp_tc_data_free(jp_data* data);
 void jp_tc_post_free(jp_posterior* post);
 int jp_upload_fit_consts(jp_posterior* post, const jp_fit_args* args);   // mu_hat, U, transform codes -> device

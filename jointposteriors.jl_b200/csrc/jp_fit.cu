@@ -513,6 +513,39 @@ int jp_fit_local_stats(jp_posterior* post, const jp_fit_args* args, double* d_st
   return jp_fit_local_sum(post, d_stats, d_stats + 1);
 }
 
+// ---- node-sharded fit with the O(N) prep of the tensor-core path sharded by OBSERVATION (csrc/jp_glm_tc.cu)
+int jp_fit_prep_len(int d) { return jp_fit_tc_prep_len(d); }
+
+int jp_fit_prep_local(jp_posterior* post, const jp_fit_args* args, int rank, int world, double* d_out) {
+  JP_TRY(jp_fit_check_args(post, args));
+  JP_REQUIRE(args->path != JP_PATH_FP64, "jp_fit_prep_local: the sharded prep belongs to the tensor-core path");
+  return jp_fit_tc_prep_local(post, args, rank, world, d_out);
+}
+
+int jp_fit_prep_gathered(jp_posterior* post, const jp_fit_args* args, const double* d_gathered, int world, int rank,
+                         int* n_rows) {
+  JP_TRY(jp_fit_check_args(post, args));
+  return jp_fit_tc_prep_gathered(post, args, d_gathered, world, rank, n_rows);
+}
+
+int jp_fit_coef_rows(jp_posterior* post, void** d_coef, long long* row_stride, long long* n_loc) {
+  JP_REQUIRE(post && d_coef, "jp_fit_coef_rows: null argument");
+  float* p = nullptr;
+  JP_TRY(jp_fit_tc_coef_rows(post, &p, row_stride, n_loc));
+  *d_coef = p;
+  return JP_OK;
+}
+
+int jp_fit_local_stats_prepared(jp_posterior* post, const jp_fit_args* args, double* d_stats) {
+  JP_TRY(jp_fit_check_args(post, args));
+  JP_REQUIRE(d_stats, "jp_fit_local_stats_prepared: null output");
+  JP_TRY(jp_fit_tc_run_prepared(post, args));
+  jp_reduce_max_kernel<<<jp_red_blocks(post->M), 256, 0, post->ctx->stream>>>(post->d_a, post->M, post->ctx->d_bpart,
+                                                                              post->ctx->d_counters, d_stats);
+  JP_CHECK_LAUNCH(post->ctx);
+  return jp_fit_local_sum(post, d_stats, d_stats + 1);
+}
+
 int jp_fit_normalise_gathered(jp_posterior* post, const double* d_gathered, int world, int rank) {
   JP_REQUIRE(post && d_gathered && world >= 1 && rank >= 0 && rank < world, "jp_fit_normalise_gathered: bad argument");
   if (post->M == 0) return JP_OK;

@@ -42,6 +42,8 @@
 
 int jp_glm_sums_device(jp_ctx* ctx, const jp_data* data, int d, const double* d_beta, double* d_out, double* d_work,
                        int nblocks);
+int jp_glm_sums_device_range(jp_ctx* ctx, const jp_data* data, int d, const double* d_beta, double* d_out, double* d_work,
+                             int nblocks, long long o0, long long o1);
 int jp_glm_num_blocks(const jp_ctx* ctx, long long N);
 
 #define TC_OBS_TILE 128          // MMA M: observations per tile (TMEM lanes)
@@ -77,6 +79,8 @@ __constant__ double c_fold_grow[2][TC_NFOLD];
 struct TcDataState {
   int d = 0, kp = 0, ka = 0;   // observation operand: row length (floats) and 128-byte atoms per row
   int split = 0, kp_b = 0;     // split layout (see header) and the pair operand's row length
+  int world = 1;               // observation slices of the sharded prep (one per rank); N_pad = world * n_loc
+  long long n_loc = 0;         // observations per slice, a multiple of the tile
   long long N = 0, N_pad = 0;
   float* d_xs = nullptr;       // [N_pad][kp]  (x_hi | x_lo | x_hi | 0)
   float* d_coef = nullptr;     // [TC_COEF_ROWS][N_pad]: coefficient k of every observation, contiguous per 128-observation tile; last row t_i
@@ -295,7 +299,9 @@ __global__ void tc_split_x_kernel(int d, int ncols, int kp, int split, long long
 __global__ void __launch_bounds__(TC_PREP_THREADS)
 tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N_pad, const double* __restrict__ obs,
                    const double* __restrict__ mu, const double* __restrict__ U, double z_ref, double z_max,
-                   float* __restrict__ coef, double* __restrict__ bounds) {
+                   float* __restrict__ coef, long long coef_stride, double* __restrict__ bounds) {
+  // N, N_pad, obs, coef describe the slice of observations this launch covers (all of them on one GPU); coef_stride is
+  // the row stride of the whole coefficient array
   // HBM-bound streaming kernel (8 N (d + 1) bytes in, 48 N_pad out): a block copies a tile of 128 records to shared
   // memory with coalesced loads (row stride padded to an odd number of doubles: conflict-free column access), then a
   // thread owns one record.  t^2 = |U' x|^2 takes U four columns at a time (two 16-byte broadcast loads per record
@@ -348,9 +354,9 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
     __syncthreads();     // tile `cur` has landed; the previous tile is consumed (and s_mu / s_U are visible)
     issue_tile(base + step, cur ^ 1);
     const long long i = base + threadIdx.x;
-    float* o = coef + i;     // o[k * N_pad]
+    float* o = coef + i;     // o[k * coef_stride]
     if (i >= N) {
-      for (int k = 0; k < TC_COEF_ROWS; ++k) o[(size_t)k * N_pad] = 0.f;
+      for (int k = 0; k < TC_COEF_ROWS; ++k) o[(size_t)k * coef_stride] = 0.f;
       continue;
     }
     const double* r = s_tile + ((size_t)cur * TC_PREP_THREADS + threadIdx.x) * rs;
@@ -381,8 +387,8 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
       const double m = exp(eta);
       for (int k = 3; k <= TC_ORDER_MAX; ++k) c[k] = m * c_inv_fact[k];
     }
-    for (int k = 0; k < TC_NCMAX; ++k) o[(size_t)k * N_pad] = (float)c[3 + k];
-    o[(size_t)TC_NCMAX * N_pad] = __double2float_ru(t);   // rounded up: the fold interval may only grow
+    for (int k = 0; k < TC_NCMAX; ++k) o[(size_t)k * coef_stride] = (float)c[3 + k];
+    o[(size_t)TC_NCMAX * coef_stride] = __double2float_ru(t);   // rounded up: the fold interval may only grow
     // bounds
     b_tmax = fmax(b_tmax, t);
     b_a1 += fabs(c[3]) * t * t * t;
@@ -453,9 +459,10 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
 // (tools/gen_fold.py: x^n ~ sum_k kappa_k x^k on |x| <= 1 in the span the kernel can evaluate).  In place on the
 // first NC coefficient rows; streams (NC + 3) rows in and NC rows out, 4 bytes per observation and row.
 __global__ void __launch_bounds__(256)
-tc_fold_kernel(int NC, long long N_pad, double z_ref, float* __restrict__ coef) {
+tc_fold_kernel(int NC, long long n, long long N_pad, double z_ref, float* __restrict__ coef) {
   const int j = (NC - 4) >> 1, h = NC >> 1;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N_pad; i += (long long)gridDim.x * blockDim.x) {
+  // n observations starting at coef; N_pad is the row stride of the whole array
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float* o = coef + i;
     const double a = (double)o[(size_t)TC_NCMAX * N_pad] * z_ref, a2 = a * a;
     const double cn_o = o[(size_t)NC * N_pad], cn_e = o[(size_t)(NC + 1) * N_pad];
@@ -1026,7 +1033,8 @@ void jp_tc_post_free(jp_posterior* post) {
   post->tc_state = nullptr;
 }
 
-static int ensure_data_state(jp_ctx* ctx, jp_data* data, int d) {
+static int ensure_data_state(jp_ctx* ctx, jp_data* data, int d, int world) {
+  if (data->tc_state && static_cast<TcDataState*>(data->tc_state)->world != world) jp_tc_data_free(data);   // re-sliced
   if (data->tc_state) return JP_OK;
   TcDataState* s = new TcDataState();
   data->tc_state = s;
@@ -1036,7 +1044,11 @@ static int ensure_data_state(jp_ctx* ctx, jp_data* data, int d) {
   s->ka = s->kp / TC_KATOM;
   s->kp_b = s->split ? 3 * TC_KATOM : s->kp;
   s->N = data->N;
-  s->N_pad = ((data->N + TC_OBS_TILE - 1) / TC_OBS_TILE) * TC_OBS_TILE;
+  // observation slices of the sharded prep: world equal slices of whole tiles (the last ones may be short or empty)
+  s->world = world;
+  const long long tiles = (data->N + TC_OBS_TILE - 1) / TC_OBS_TILE;
+  s->n_loc = ((tiles + world - 1) / world) * TC_OBS_TILE;
+  s->N_pad = s->n_loc * world;
   const int nE = d + d * (d + 1) / 2;
   s->glm_blocks = jp_glm_num_blocks(ctx, data->N);
   JP_CUDA(jp_dmalloc(ctx, &s->d_xs, (size_t)s->N_pad * s->kp * sizeof(float)));
@@ -1145,39 +1157,46 @@ static int launch_tc(jp_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB
   return launch_tc_mode<NC, 0>(ctx, tmA, tmB, kp, smem);
 }
 
-int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
+// ---- the fit in pieces.  One GPU: setup, prep of all observations, decide, fold, run.  Several ranks (node-sharded
+// posterior, observations replicated): the O(N) FP64 prep is SHARDED BY OBSERVATION -- rank r prepares slice r, the
+// ranks exchange (sums, bounds) and then the coefficient rows -- so that the replicated work per rank stays O(N / world).
+static int tc_setup(jp_posterior* post, const jp_fit_args* args, int world) {
   jp_ctx* ctx = post->ctx;
   jp_data* data = const_cast<jp_data*>(post->data);
   if (!tc_static_ok(post, args)) return JP_ERR_UNSUPPORTED;
   JP_REQUIRE(post->grid->M % 2 == 1, "tensor-core path: the grid is not in mirror order (even node count %lld)", post->grid->M);
-  const int d = args->d, p = args->p;
   JP_TRY(upload_tables());
-  JP_TRY(ensure_data_state(ctx, data, d));
+  JP_TRY(ensure_data_state(ctx, data, args->d, world));
   TcDataState* ds = static_cast<TcDataState*>(data->tc_state);
-  JP_REQUIRE(ds->d == d, "tensor-core path: data was prepared for d=%d", ds->d);
+  JP_REQUIRE(ds->d == args->d, "tensor-core path: data was prepared for d=%d", ds->d);
   JP_TRY(ensure_post_state(post, ds->kp_b));
-  TcPostState* ps = static_cast<TcPostState*>(post->tc_state);
   JP_TRY(jp_upload_fit_consts(post, args));
-  cudaStream_t st = ctx->stream;
-  // FP64 sums at the centre: g, H, L_hat
-  JP_TRY(jp_glm_sums_device(ctx, data, d, post->d_mu, ds->d_sums, ds->d_work, ds->glm_blocks));
-  // per-observation coefficients + bounds
+  return JP_OK;
+}
+
+// FP64 sums (g, H, L_hat) over slice `rank` into d_sums, per-observation coefficients of the slice and the block
+// partials of the bounds into ds->d_bounds
+static int tc_prep_slice(jp_posterior* post, const jp_fit_args* args, int rank, double* d_sums) {
+  jp_ctx* ctx = post->ctx;
+  const jp_data* data = post->data;
+  TcDataState* ds = static_cast<TcDataState*>(data->tc_state);
+  const int d = args->d, p = args->p;
+  const long long o0 = std::min(data->N, (long long)rank * ds->n_loc), o1 = std::min(data->N, o0 + ds->n_loc);
+  JP_TRY(jp_glm_sums_device_range(ctx, data, d, post->d_mu, d_sums, ds->d_work, ds->glm_blocks, o0, o1));
   const double z_max = std::sqrt(post->grid->zmax2), z_ref = std::min(z_max, 6.0);
   const size_t sm_obs = (size_t)(((d + 1) & ~1) + d * ((p + 3) & ~3) + 2 * TC_PREP_THREADS * (data->ncols | 1)) * 8;
   if (sm_obs > 48 * 1024)
     JP_CUDA(cudaFuncSetAttribute(tc_obs_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_obs));
-  tc_obs_prep_kernel<<<TC_PREP_BLOCKS, TC_PREP_THREADS, sm_obs, st>>>(data->family, d, p, data->ncols, data->N, ds->N_pad, data->d_obs,
-                                                          post->d_mu, post->d_U, z_ref, z_max, ds->d_coef, ds->d_bounds);
+  tc_obs_prep_kernel<<<TC_PREP_BLOCKS, TC_PREP_THREADS, sm_obs, ctx->stream>>>(
+      data->family, d, p, data->ncols, o1 - o0, ds->n_loc, data->d_obs + (size_t)o0 * data->ncols, post->d_mu, post->d_U, z_ref,
+      z_max, ds->d_coef + (size_t)rank * ds->n_loc, ds->N_pad, ds->d_bounds);
   JP_CHECK_LAUNCH(ctx);
-  double* hb = ctx->h_pinned + 4096;   // away from the constants staged by jp_upload_fit_consts
-  JP_CUDA(cudaMemcpyAsync(hb, ds->d_bounds, (size_t)TC_PREP_BLOCKS * TC_NBOUND * 8, cudaMemcpyDeviceToHost, st));
-  JP_CUDA(cudaStreamSynchronize(st));
-  double b[TC_NBOUND] = {0};
-  for (int blk = 0; blk < TC_PREP_BLOCKS; ++blk) {
-    const double* o = hb + (size_t)blk * TC_NBOUND;
-    b[0] = std::max(b[0], o[0]);
-    for (int j = 1; j < TC_NBOUND; ++j) b[j] += o[j];
-  }
+  return JP_OK;
+}
+
+// series length from the reduced bounds b[TC_NBOUND] (b[0] still without the factor z_max); records the diagnostics
+static int tc_decide(jp_posterior* post, double* b, int* NC_out, int* fold_out) {
+  const double z_max = std::sqrt(post->grid->zmax2);
   b[0] *= z_max;
   double err_trunc = 0, err_round = 0;
   int fold = 0;
@@ -1189,11 +1208,28 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
                  "at order 14); use the FP64 path", b[0], 2e-6 * std::sqrt(b[13]), b[6], b[11]);
     return JP_ERR_UNSUPPORTED;
   }
-  if (fold) {
-    tc_fold_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(NC, ds->N_pad, z_ref, ds->d_coef);
-    JP_CHECK_LAUNCH(ctx);
-  }
-  // node operand, theta, FP64 quadratic part
+  *NC_out = NC;
+  *fold_out = fold;
+  return JP_OK;
+}
+
+static int tc_fold_slice(jp_posterior* post, int NC, int rank) {
+  jp_ctx* ctx = post->ctx;
+  TcDataState* ds = static_cast<TcDataState*>(post->data->tc_state);
+  const double z_max = std::sqrt(post->grid->zmax2), z_ref = std::min(z_max, 6.0);
+  tc_fold_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(NC, ds->n_loc, ds->N_pad, z_ref, ds->d_coef + (size_t)rank * ds->n_loc);
+  JP_CHECK_LAUNCH(ctx);
+  return JP_OK;
+}
+
+// node operand, theta, FP64 quadratic part, the tensor-core kernel and the per-node finish
+static int tc_run(jp_posterior* post, const jp_fit_args* args, int NC) {
+  jp_ctx* ctx = post->ctx;
+  const jp_data* data = post->data;
+  TcDataState* ds = static_cast<TcDataState*>(data->tc_state);
+  TcPostState* ps = static_cast<TcPostState*>(post->tc_state);
+  const int d = args->d, p = args->p;
+  cudaStream_t st = ctx->stream;
   size_t sm_node = (size_t)(d + d * p + d + d * d + 64 + 128 * d) * 8;
   if (sm_node > 48 * 1024)
     JP_CUDA(cudaFuncSetAttribute(tc_node_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_node));
@@ -1207,7 +1243,7 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   kp.ka = ds->ka;
   kp.kb = ds->kp_b / TC_KATOM;
   kp.n_pair_tiles = (int)(ps->P_pad / TC_PAIR_TILE);
-  kp.n_obs_tiles = (int)(ds->N_pad / TC_OBS_TILE);
+  kp.n_obs_tiles = (int)((ds->N + TC_OBS_TILE - 1) / TC_OBS_TILE);   // tiles past the data (slice padding) hold zeros: skipped
   const size_t b_bytes = (size_t)kp.kb * TC_PAIR_TILE * 128, a_bytes = (size_t)kp.ka * TC_OBS_TILE * 128;
   const size_t c_bytes = (size_t)NC * TC_OBS_TILE * 4;      // coefficient slot of one tile
   const size_t budget = 220 * 1024, misc = 1024 + 4 * TC_PAIR_TILE * 2 * 8 + 256 + TC_NBUF * c_bytes;
@@ -1260,4 +1296,105 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   JP_CHECK_LAUNCH(ctx);
   post->path_used = JP_PATH_TC;
   return JP_OK;
+}
+
+// bounds of the blocks of one prep launch -> b[TC_NBOUND] on the host ([0] a maximum, the rest sums in block order)
+static void tc_reduce_block_bounds(const double* hb, double* b) {
+  for (int j = 0; j < TC_NBOUND; ++j) b[j] = 0;
+  for (int blk = 0; blk < TC_PREP_BLOCKS; ++blk) {
+    const double* o = hb + (size_t)blk * TC_NBOUND;
+    b[0] = std::max(b[0], o[0]);
+    for (int j = 1; j < TC_NBOUND; ++j) b[j] += o[j];
+  }
+}
+
+int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
+  jp_ctx* ctx = post->ctx;
+  JP_TRY(tc_setup(post, args, 1));
+  TcDataState* ds = static_cast<TcDataState*>(post->data->tc_state);
+  JP_TRY(tc_prep_slice(post, args, 0, ds->d_sums));
+  double* hb = ctx->h_pinned + 4096;   // away from the constants staged by jp_upload_fit_consts
+  JP_CUDA(cudaMemcpyAsync(hb, ds->d_bounds, (size_t)TC_PREP_BLOCKS * TC_NBOUND * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  JP_CUDA(cudaStreamSynchronize(ctx->stream));
+  double b[TC_NBOUND];
+  tc_reduce_block_bounds(hb, b);
+  int NC = 0, fold = 0;
+  JP_TRY(tc_decide(post, b, &NC, &fold));
+  if (fold) JP_TRY(tc_fold_slice(post, NC, 0));
+  return tc_run(post, args, NC);
+}
+
+// ---- sharded prep, phase by phase (extern "C" wrappers in jp_fit.cu).  L = nE + 1 + TC_NBOUND doubles per rank.
+int jp_fit_tc_prep_len(int d) { return d + d * (d + 1) / 2 + 1 + TC_NBOUND; }
+
+// reduce the block partials of the bounds on the device (block order; [0] is a maximum)
+__global__ void tc_bounds_reduce_kernel(const double* __restrict__ blocks, double* __restrict__ out) {
+  const int j = threadIdx.x;
+  if (j >= TC_NBOUND) return;
+  double v = 0;
+  for (int blk = 0; blk < TC_PREP_BLOCKS; ++blk) {
+    const double o = blocks[(size_t)blk * TC_NBOUND + j];
+    v = (j == 0) ? fmax(v, o) : v + o;
+  }
+  out[j] = v;
+}
+
+// phase 1: this rank's observation slice -> d_out[L] = (local g, H, L_hat | local bounds); asynchronous
+int jp_fit_tc_prep_local(jp_posterior* post, const jp_fit_args* args, int rank, int world, double* d_out) {
+  JP_REQUIRE(world >= 1 && rank >= 0 && rank < world && d_out, "jp_fit_prep_local: bad rank / world / output");
+  JP_TRY(tc_setup(post, args, world));
+  TcDataState* ds = static_cast<TcDataState*>(post->data->tc_state);
+  const int nE1 = args->d + args->d * (args->d + 1) / 2 + 1;
+  JP_TRY(tc_prep_slice(post, args, rank, d_out));
+  tc_bounds_reduce_kernel<<<1, 32, 0, post->ctx->stream>>>(ds->d_bounds, d_out + nE1);
+  JP_CHECK_LAUNCH(post->ctx);
+  return JP_OK;
+}
+
+// phase 2: the gathered [world][L] buffer -> global sums (rank order, identical on every rank), the series length, the
+// fold of this rank's slice.  Blocks until the gathered buffer is on the host.  *n_rows = coefficient rows to exchange.
+int jp_fit_tc_prep_gathered(jp_posterior* post, const jp_fit_args* args, const double* d_gathered, int world, int rank,
+                            int* n_rows) {
+  jp_ctx* ctx = post->ctx;
+  TcDataState* ds = static_cast<TcDataState*>(post->data->tc_state);
+  JP_REQUIRE(ds && ds->world == world && d_gathered && n_rows, "jp_fit_prep_gathered: call jp_fit_prep_local first");
+  const int nE1 = args->d + args->d * (args->d + 1) / 2 + 1, L = nE1 + TC_NBOUND;
+  JP_REQUIRE((size_t)world * L + 4096 + L <= JP_PINNED_DOUBLES, "jp_fit_prep_gathered: world=%d too large", world);
+  double* hg = ctx->h_pinned + 4096;
+  JP_CUDA(cudaMemcpyAsync(hg, d_gathered, (size_t)world * L * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  JP_CUDA(cudaStreamSynchronize(ctx->stream));
+  double* hs = hg + (size_t)world * L;      // combined sums, staged for the upload
+  for (int e = 0; e < nE1; ++e) {
+    double v = 0;
+    for (int r = 0; r < world; ++r) v += hg[(size_t)r * L + e];
+    hs[e] = v;
+  }
+  double b[TC_NBOUND];
+  for (int j = 0; j < TC_NBOUND; ++j) {
+    double v = 0;
+    for (int r = 0; r < world; ++r) v = (j == 0) ? std::max(v, hg[(size_t)r * L + nE1 + j]) : v + hg[(size_t)r * L + nE1 + j];
+    b[j] = v;
+  }
+  JP_CUDA(cudaMemcpyAsync(ds->d_sums, hs, (size_t)nE1 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  int NC = 0, fold = 0;
+  JP_TRY(tc_decide(post, b, &NC, &fold));
+  if (fold) JP_TRY(tc_fold_slice(post, NC, rank));
+  *n_rows = NC;
+  return JP_OK;
+}
+
+// the coefficient array for the exchange: row k of rank r's slice is d_coef + k * row_stride + r * n_loc, n_loc floats
+int jp_fit_tc_coef_rows(jp_posterior* post, float** d_coef, long long* row_stride, long long* n_loc) {
+  TcDataState* ds = post && post->data ? static_cast<TcDataState*>(post->data->tc_state) : nullptr;
+  JP_REQUIRE(ds && d_coef && row_stride && n_loc, "jp_fit_coef_rows: call jp_fit_prep_local first");
+  *d_coef = ds->d_coef;
+  *row_stride = ds->N_pad;
+  *n_loc = ds->n_loc;
+  return JP_OK;
+}
+
+// phase 3 (after the rows are exchanged): stages 2-3 of this rank's node block
+int jp_fit_tc_run_prepared(jp_posterior* post, const jp_fit_args* args) {
+  JP_REQUIRE(post->tc_bounds[3] >= 4, "jp_fit_run_prepared: no series length has been decided (call the prep phases first)");
+  return tc_run(post, args, (int)post->tc_bounds[3]);
 }

@@ -7,6 +7,8 @@ and -- for the 100-knot Grid -- per-knot (mass below, predecessor, successor).  
 contiguous block of merged grid nodes and the ranks exchange only:
 
     fit        all_gather(local max m_r, local sum s_r relative to m_r)             one collective
+               tensor-core GLM path: its O(N) FP64 prep is sharded by OBSERVATION instead of being replicated --
+               all_gather(slice sums + bounds), then all_gather of the coefficient rows in place (fit_sharded)
     marginals  all_gather(K x 4 moments/extrema)  ;  all_gather(K x 98 x 6 knot candidates)
 
 Between the collectives the host does no arithmetic: the gathered buffers go straight back into the
@@ -164,6 +166,49 @@ class CudaLocal:
         check(lib().jp_fit_local_stats(self.jp.handle, C.byref(self.jp._args), C.c_void_p(out.data_ptr())))
         return out
 
+    # ---- observation-sharded prep of the tensor-core path (jp_fit_prep_*, include/jpcuda.h)
+    def prep_worthwhile(self):
+        """The sharded prep trades O(N (1 - 1/world)) replicated FP64 work (~0.3 ns per observation) for two more
+        collectives plus one all_gather per coefficient row (~0.25 ms at 2 GPUs): worth it from a few million
+        observations (BASELINE cfg5: 3.7 ms of prep per rank), a loss at cfg3 sizes.  JP_SHARDED_PREP_MIN_MB overrides
+        the record-size threshold."""
+        import os
+        return self.jp.data.nbytes >= float(os.environ.get("JP_SHARDED_PREP_MIN_MB", "512")) * 1e6
+
+    def fit_prep_local(self, rank, world):
+        """Slice sums and bounds of this rank's observation slice [L], or None when the posterior is not on the
+        tensor-core path (not a GLM, constrained coordinates, path forced to FP64)."""
+        L = int(lib().jp_fit_prep_len(C.c_int(self.jp._args.d)))
+        out = self._buf(L)
+        st = lib().jp_fit_prep_local(self.jp.handle, C.byref(self.jp._args), C.c_int(rank), C.c_int(world),
+                                     C.c_void_p(out.data_ptr()))
+        if st == 6:            # JP_ERR_UNSUPPORTED
+            return None
+        check(st)
+        return out
+
+    def fit_prep_gathered(self, g, rank):
+        """-> number of coefficient rows to exchange, or None when the series bounds are not met (use the FP64 kernel)."""
+        g = g.contiguous()
+        n_rows = C.c_int()
+        st = lib().jp_fit_prep_gathered(self.jp.handle, C.byref(self.jp._args), C.c_void_p(g.data_ptr()), C.c_int(g.shape[0]),
+                                        C.c_int(rank), C.byref(n_rows))
+        if st == 6:
+            return None
+        check(st)
+        return n_rows.value
+
+    def fit_coef_rows(self, n_rows):
+        """The first n_rows coefficient rows as torch views [n_rows][world * n_loc] of the library's buffer (float32)."""
+        ptr, stride, n_loc = C.c_void_p(), C.c_longlong(), C.c_longlong()
+        check(lib().jp_fit_coef_rows(self.jp.handle, C.byref(ptr), C.byref(stride), C.byref(n_loc)))
+        return _device_view_f32(self.torch, ptr.value, n_rows * stride.value, self.dev).view(n_rows, stride.value), n_loc.value
+
+    def fit_local_stats_prepared(self):
+        out = self._buf(2)
+        check(lib().jp_fit_local_stats_prepared(self.jp.handle, C.byref(self.jp._args), C.c_void_p(out.data_ptr())))
+        return out
+
     def fit_normalise_gathered(self, g, rank):
         g = g.contiguous()
         check(lib().jp_fit_normalise_gathered(self.jp.handle, C.c_void_p(g.data_ptr()), C.c_int(g.shape[0]), C.c_int(rank)))
@@ -216,19 +261,56 @@ class CudaLocal:
         return out
 
 
+def _device_view_f32(torch, ptr, numel, dev):
+    """A float32 torch tensor over `numel` elements of device memory owned by the library (no copy)."""
+    class _Ext:
+        pass
+    e = _Ext()
+    e.__cuda_array_interface__ = dict(shape=(int(numel),), typestr="<f4", data=(int(ptr), False), version=2)
+    return torch.as_tensor(e, device=dev)
+
+
 def _rank(group):
     import torch.distributed as dist
     return dist.get_rank(group)
 
 
-def fit_sharded(local, group=None, gather=None, rank=None):
-    """Normalise a node-sharded fit with one tiny all_gather of (local max, local sum).  `gather(t, group)` defaults
-    to torch.distributed all_gather; tests emulating several ranks inject their own.  The combine runs in rank
-    order on every rank, so all ranks derive bit-identical scalars."""
+def fit_sharded(local, group=None, gather=None, rank=None, world=None, gather_rows=None):
+    """Normalise a node-sharded fit.  `gather(t, group)` defaults to torch.distributed all_gather; tests emulating
+    several ranks inject their own.  Every combine runs in rank order on every rank: bit-identical scalars.
+
+    When the local phase offers it (tensor-core GLM path), the O(N) prep is sharded by observation first: one tiny
+    all_gather of (slice sums, bounds), then the chosen coefficient rows are all-gathered in place, row by row, inside
+    the library's buffer (`gather_rows(rows, n_loc, rank, group)`, default: torch all_gather_into_tensor on views)."""
     gather = gather or _all_gather
-    g = gather(local.fit_local_stats(), group)      # [world, 2]
-    local.fit_normalise_gathered(g, _rank(group) if rank is None else rank)
+    r = _rank(group) if rank is None else rank
+    if world is None:
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+    stats = None
+    prep = getattr(local, "fit_prep_local", None)
+    if prep is not None and world > 1 and local.prep_worthwhile():
+        mine = prep(r, world)
+        if mine is not None:
+            n_rows = local.fit_prep_gathered(gather(mine, group), r)
+            if n_rows is not None:
+                rows, n_loc = local.fit_coef_rows(n_rows)
+                (gather_rows or _all_gather_rows_inplace)(rows, n_loc, r, group)
+                stats = local.fit_local_stats_prepared()
+    local.last_prep = "sharded" if stats is not None else "replicated"      # which protocol this fit took (diagnostics)
+    if stats is None:
+        stats = local.fit_local_stats()
+    g = gather(stats, group)      # [world, 2]
+    local.fit_normalise_gathered(g, r)
     return g
+
+
+def _all_gather_rows_inplace(rows, n_loc, rank, group):
+    """rows: [n_rows][world * n_loc]; rank r owns columns [r * n_loc, (r + 1) * n_loc) of every row."""
+    import torch.distributed as dist
+    for k in range(rows.shape[0]):
+        row = rows[k]
+        dist.all_gather_into_tensor(row, row[rank * n_loc:(rank + 1) * n_loc], group=group)
 
 
 def marginals_sharded(local, coords, group=None, gather=None):

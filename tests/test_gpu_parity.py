@@ -581,6 +581,49 @@ def test_tc_sharded_equals_unsharded(jp, O, gpu_ctx):
         assert np.max(np.abs(sh.logdens - ld[b:e])) < 2e-8     # same arithmetic per node up to the chunking of the FP32 partial sums
 
 
+@pytest.mark.parametrize("world,N,level", [(2, 60000, 4), (3, 30001, 4), (5, 50000, 4)], ids=["w2", "w3-ragged", "w5"])
+def test_tc_observation_sharded_prep(jp, O, gpu_ctx, world, N, level):
+    """Node-sharded fit whose O(N) prep is sharded by observation (jp_fit_prep_local / _prep_gathered / _coef_rows /
+    _local_stats_prepared), `world` ranks emulated on one GPU -- every rank with its own copy of the records and its own
+    library state, collectives emulated by copies -- against the unsharded tensor-core fit and the oracle."""
+    import torch
+    from jointposteriors_jl_b200 import distributed as D
+    from jointposteriors_jl_b200.model import JointPosterior
+    d = 8 if N > 1000 else 3
+    family, obs, hyper = _glm_case("logistic", 9, N, d, 1.0)
+    code = [0] * d
+    x, H, neg_min = _cpu_mode_for(O, family, code, obs, hyper)
+    U = O.inv_chol(2.0 * H)
+    M = _model_for(jp, code)
+    full = jp.fit(M, _upload(jp, gpu_ctx, family, obs, hyper), level, path=jp.PATH_TC, mode_result=(x, U, neg_min))
+    grid = gpu_ctx.grid(0, d, level)
+    shards = [JointPosterior(M, _upload(jp, gpu_ctx, family, obs, hyper), grid, x, U, neg_min, path=jp.PATH_TC,
+                             node_range=D.shard_bounds(full.n_nodes, r, world)) for r in range(world)]
+    locs = [D.CudaLocal(sh) for sh in shards]
+    g = torch.stack([l.fit_prep_local(r, world) for r, l in enumerate(locs)]).contiguous()
+    n_rows = [l.fit_prep_gathered(g, r) for r, l in enumerate(locs)]
+    assert len(set(n_rows)) == 1 and n_rows[0] in (4, 6, 8, 10, 12)
+    views = [l.fit_coef_rows(n_rows[0]) for l in locs]
+    n_loc = views[0][1]
+    assert n_loc % 128 == 0 and views[0][0].shape[1] == world * n_loc
+    for src in range(world):                      # the in-place all_gather of the coefficient rows
+        for dst in range(world):
+            if dst != src:
+                views[dst][0][:, src * n_loc:(src + 1) * n_loc] = views[src][0][:, src * n_loc:(src + 1) * n_loc]
+    torch.cuda.synchronize()
+    gs = torch.stack([l.fit_local_stats_prepared() for l in locs]).contiguous()
+    for r, l in enumerate(locs):
+        l.fit_normalise_gathered(gs, r)
+    assert all(sh.path_used == jp.PATH_TC for sh in shards)
+    ld = np.concatenate([sh.logdens for sh in shards])
+    dens = np.concatenate([sh.density for sh in shards])
+    assert np.max(np.abs(ld - full.logdens)) < 1e-8 * max(1.0, np.max(np.abs(full.logdens)))
+    assert relerr(dens, full.density) < 1e-7
+    idx, w = O.smolyak(0, d, level)
+    ref = O.eval_grid(0, family, code, idx, w, x, U, neg_min, obs, hyper)
+    assert relerr(dens, ref["density"]) < TOLTC
+
+
 def test_cfg3_full_size_tc(jp, O, gpu_ctx):
     """BASELINE config 3 at full size on the tensor-core path vs the FP64 CUDA kernel and an oracle subsample."""
     from jointposteriors_jl_b200 import workloads
