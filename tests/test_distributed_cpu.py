@@ -73,6 +73,44 @@ class NumpyLocal:
         return tuple(x.numpy() for x in self.D.reference_combine(gm, gc))
 
 
+class NumpyPrepLocal(NumpyLocal):
+    """Adds the observation-sharded prep phases (same contract as CudaLocal.fit_prep_*): the 'prep' of this stand-in
+    is a per-observation coefficient c_i = 2 i + 1 and the slice sum of i, the node values a_m then get the global sum
+    and the dot of the gathered coefficients added -- so the fit only comes out right if every phase ran and every
+    rank saw every slice."""
+
+    def __init__(self, *args, n_obs=1000, world=1):
+        super().__init__(*args)
+        self.n_obs, self.world = n_obs, world
+        self.n_loc = -(-n_obs // world)
+        self.rows = self.t.zeros((2, world * self.n_loc), dtype=self.t.float32)
+        self.a0 = self.a.copy()
+
+    def prep_worthwhile(self):
+        return True
+
+    def fit_prep_local(self, rank, world):
+        lo, hi = min(self.n_obs, rank * self.n_loc), min(self.n_obs, (rank + 1) * self.n_loc)
+        i = np.arange(lo, hi, dtype=np.float64)
+        self.rows[0, lo:hi] = self.t.tensor(2 * i + 1, dtype=self.t.float32)
+        self.rows[1, lo:hi] = 1.0
+        return self._t([i.sum(), float(hi - lo), 0.0])
+
+    def fit_prep_gathered(self, g, rank):
+        self.total = float(g[:, 0].sum())
+        assert int(g[:, 1].sum()) == self.n_obs
+        return 2
+
+    def fit_coef_rows(self, n_rows):
+        return self.rows[:n_rows], self.n_loc
+
+    def fit_local_stats_prepared(self):
+        r = self.rows.numpy().astype(np.float64)
+        shift = 1e-6 * self.total + 1e-9 * float(r[0, :self.n_obs].sum()) + float(r[1, :self.n_obs].sum()) - self.n_obs
+        self.a = self.a0 + shift
+        return self.fit_local_stats()
+
+
 def _worker(rank, world, port, a, w, values, q):
     sys.path.insert(0, ROOT)
     import torch
@@ -88,6 +126,15 @@ def _worker(rank, world, port, a, w, values, q):
     loc = NumpyLocal(a[b:e], w[b:e], [v[b:e] for v in values], b, D)
     D.fit_sharded(loc)
     mu, sg, vn, wn = D.marginals_sharded(loc, list(range(len(values))))
+    # the fit again through the observation-sharded prep protocol (extra all_gather + in-place row gathers): a constant
+    # shift of every log-density leaves the normalised weights unchanged only if all ranks derived the SAME shift
+    ploc = NumpyPrepLocal(a[b:e], w[b:e], [v[b:e] for v in values], b, D, n_obs=1003, world=world)
+    D.fit_sharded(ploc)
+    assert ploc.last_prep == "sharded"
+    n = 1003
+    want = 1e-6 * (n * (n - 1) / 2) + 1e-9 * float(n * n)          # sum i, sum (2 i + 1) = n^2; the row of ones cancels n
+    assert abs((ploc.a - ploc.a0)[0] - want) < 1e-9 * max(1.0, abs(want)), ((ploc.a - ploc.a0)[0], want)
+    assert np.allclose(ploc.density, loc.density, rtol=1e-12, atol=0)
     # row-sliced upload + all_gather (Context.upload_sharded): ragged N, every rank reassembles all records
     obs = np.arange(float(1003 * 4)).reshape(1003, 4)
     full = D.gather_rows(obs, torch.device("cpu"))
