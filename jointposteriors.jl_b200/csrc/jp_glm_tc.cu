@@ -15,17 +15,23 @@
 // 1e-6 RELATIVE to R_i is ~1e-12 absolute per observation (see jp_tc_choose_order for the bounds that gate
 // the path; outside them the FP64 plugin kernel of jp_fit.cu is used).
 //
-// Kernel (one persistent CTA per SM, warp-specialised):
-//   warp 0      TMA producer: node-tile operand (128 nodes x K) once per work item, observation tiles
-//               (128 obs x K) through a ring of shared-memory stages; 128-byte swizzle, K-major
+// Kernel (one persistent CTA per SM, warp-specialised, 14 warps):
+//   warp 0      TMA producer: the mirror-pair operand (96 pairs x K) once per work item into one of two buffers,
+//               observation tiles (128 obs x K) plus their coefficient rows through a ring of shared-memory stages;
+//               128-byte swizzle, K-major
 //   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::tf32, M = 128 (observations on TMEM lanes),
-//               N = 128 (nodes on TMEM columns), K = 8 per instruction; four accumulator buffers in
-//               TMEM (4 x 128 columns); tcgen05.commit releases stages / publishes accumulators
-//   warps 2-9   epilogue: tcgen05.ld 16 columns at a time, R = D^3 (c3 + D (c4 + ...)) by Horner (packed
-//               FFMA2, two node columns per instruction) with the
-//               calling thread's own observation coefficients held in registers, accumulated per
-//               (thread = observation lane, column = node) in FP32 registers over all observation tiles of
-//               the item; per item one shuffle transpose-reduce + shared-memory combine in FP64.
+//               N = 96 (mirror pairs of grid nodes on TMEM columns), K = 8 per instruction; five accumulator buffers in
+//               TMEM (5 x 96 columns); tcgen05.commit releases stages / publishes accumulators.  Both warps run their
+//               loops converged and predicate the asynchronous instructions on one elected lane.
+//   warps 2-13  epilogue (3 per SM sub-partition, each one TMEM lane quarter x 32 columns): tcgen05.ld 8 columns at a
+//               time, software-pipelined across tiles; a column is a PAIR of nodes (z, -z): with D = x_i . delta(z),
+//               R_i(+-D) = E_i(D) +- O_i(D), E = D^4 (c4 + c6 D^2 + ..), O = D^3 (c3 + c5 D^2 + ..) in packed FFMA2 /
+//               FMUL2 (two columns per instruction, NC + 3 operations per column) with the thread's own observation
+//               coefficients from shared memory; accumulated per (thread = observation lane, column) in FP32
+//               registers over all observation tiles of the item; per item one shuffle transpose-reduce +
+//               shared-memory combine in FP64 into per-(chunk, pair) (E, O) partials.
+// The NC coefficients are the ECONOMISED ones when that passes the gate (tools/gen_fold.py, tc_fold_kernel): the next
+// odd / even Taylor order folded into the kept ones by its minimax approximation on the observation's own interval.
 // 3xTF32: operand rows are [x_hi | x_lo | x_hi] and [d_hi | d_hi | d_lo] (TF32-representable FP32), so one
 // K = 3d contraction gives x_hi d_hi + x_lo d_hi + x_hi d_lo with FP32 accumulation in TMEM.  When that needs three
 // 128-byte K atoms (21 < d <= 32) the SPLIT layout is used instead: observation rows [x_hi | x_lo] with each part

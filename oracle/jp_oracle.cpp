@@ -14,7 +14,8 @@
 //   (1) the reference's only numeric test, test/runtests.jl:69-70 (tau: mu 0.5504, sigma 0.077,
 //       quantiles [0.391 0.495 0.55 0.602 0.696] at rtol 10^-1.5) and the README prints
 //       (README.md:110-128), and
-//   (2) brute-force tensor Gauss-Legendre truth for the README model (tests/test_oracle_pin.py).
+//   (2) brute-force tensor Gauss-Legendre truth for the README model (tests/test_oracle_pin.py), and
+//   (3) the closed-form Dirichlet posterior of the multinomial family for the simplex transform.
 // Beyond that tolerance the Smolyak stages are "parity unpinned" (no upstream source exists to
 // compare against); DESIGN.md says the same.
 //

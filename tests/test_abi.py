@@ -193,3 +193,53 @@ def test_bench_product_arm_needs_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], text=True,
                        capture_output=True, timeout=600)
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_fold_tables_are_what_the_generator_produces():
+    """csrc/jp_fold_tables.h (economisation constants of the tensor-core series) is the output of tools/gen_fold.py:
+    constants agree to 1e-9, and the tabulated error bounds really bound the error of the tabulated constants."""
+    import sys
+    txt = open(os.path.join(ROOT, "jointposteriors.jl_b200", "csrc", "jp_fold_tables.h")).read()
+
+    def table(name, two_d):
+        body = txt[txt.index(name):]
+        body = body[body.index("{") + 1:body.index("};")]
+        vals = [float(v) for v in re.findall(r"[-+]?\d+\.?\d*(?:[eE][-+]?\d+)?", body)]
+        return np.array(vals).reshape(4, 5) if two_d else np.array(vals)
+
+    ko, ke = table("k_fold_odd[TC_NFOLD][5]", True), table("k_fold_even[TC_NFOLD][5]", True)
+    eo, ee = table("k_fold_eps_odd[TC_NFOLD]", False), table("k_fold_eps_even[TC_NFOLD]", False)
+    go, ge = table("k_fold_grow_odd[TC_NFOLD]", False), table("k_fold_grow_even[TC_NFOLD]", False)
+    x = np.linspace(0, 1, 200001)
+    for j, NC in enumerate((4, 6, 8, 10)):
+        odd = sum(ko[j][m] * x ** (3 + 2 * m) for m in range(NC // 2))
+        even = sum(ke[j][m] * x ** (4 + 2 * m) for m in range(NC // 2))
+        assert np.max(np.abs(x ** (NC + 3) - odd)) <= eo[j] and np.max(np.abs(x ** (NC + 4) - even)) <= ee[j]
+        assert abs(go[j] - (1 + np.abs(ko[j]).sum())) < 1e-5 and abs(ge[j] - (1 + np.abs(ke[j]).sum())) < 1e-5
+        assert np.all(ko[j][NC // 2:] == 0) and np.all(ke[j][NC // 2:] == 0)
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "tools", "gen_fold.py")], text=True, timeout=600)
+    new = np.array([float(v) for v in re.findall(r"[-+]?\d+\.\d+(?:[eE][-+]?\d+)?", out[out.index("k_fold_odd"):])])
+    old = np.array([float(v) for v in re.findall(r"[-+]?\d+\.\d+(?:[eE][-+]?\d+)?", txt[txt.index("k_fold_odd"):])])
+    assert new.shape == old.shape and np.allclose(new, old, rtol=1e-6, atol=1e-9)
+
+
+def test_rank_policies_in_deduce_scale(jp, O):
+    """deduce_scale!(M, H, R) for R = Dynamic / Full / FixedRank{p} / LDR{g} (reference src/joint_posterior.jl:136-144)."""
+    from jointposteriors_jl_b200 import model
+    rng = np.random.default_rng(2)
+    A = rng.standard_normal((5, 5))
+    H = A @ A.T + 0.1 * np.eye(5)
+
+    class FakeModel:
+        pass
+    m = FakeModel()
+    for rank, p in ((jp.Dynamic, 5), (jp.Full, 5), (jp.FixedRank(2), 2), (jp.LDR(0.5), None), (jp.LDR(0.999), None)):
+        m.rank = rank
+        U = model.deduce_scale(m, H)
+        assert U.shape[0] == 5 and (p is None or U.shape[1] == p)
+        if U.shape[1] == 5:
+            assert np.allclose(U @ U.T, np.linalg.inv(H), rtol=1e-9)
+    m.rank = jp.LDR(0.5)
+    assert model.deduce_scale(m, H).shape == O.reduce_dimensions_ldr(H, 0.5).shape
+    with pytest.raises(ValueError):
+        jp.LDR(1.0)
