@@ -423,15 +423,16 @@ int jp_log_density_points(jp_ctx* ctx, const jp_data* data, int d, const int* h_
   const bool small = need_dev <= JP_SCRATCH_DOUBLES && need_pin <= JP_PINNED_DOUBLES;
   double* hp = ctx->h_pinned;
   if (small) {
-    d_x = ctx->d_scratch;
-    d_theta = d_x + (size_t)K * d;
-    d_part = d_theta + (size_t)K * d;
-    d_out = d_part + (size_t)K * (splits + 1);
-    d_code = reinterpret_cast<int*>(d_out + K);
+    // Zero-copy: with unified addressing the pinned buffer is device-accessible at its host address, so the kernels read
+    // the (few KB of) points and codes straight from it and write the results back into it -- no copy calls, one
+    // launch pair and one synchronisation per evaluation (a Newton iteration of jp_mode is one such call).
     std::memcpy(hp, h_x, (size_t)K * d * 8);
     std::memcpy(hp + (size_t)K * d, h_transform, (size_t)d * 4);
-    e = cudaMemcpyAsync(d_x, hp, (size_t)K * d * 8, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_code, hp + (size_t)K * d, (size_t)d * 4, cudaMemcpyHostToDevice, ctx->stream);
+    d_x = hp;
+    d_code = reinterpret_cast<int*>(hp + (size_t)K * d);
+    d_out = hp + (size_t)K * d + code_dbl;
+    d_theta = ctx->d_scratch;
+    d_part = d_theta + (size_t)K * d;
   } else {
     e = jp_dmalloc(ctx, &d_x, (size_t)K * d * 8);
     if (e == cudaSuccess) e = jp_dmalloc(ctx, &d_theta, (size_t)K * d * 8);
@@ -455,10 +456,10 @@ int jp_log_density_points(jp_ctx* ctx, const jp_data* data, int d, const int* h_
       ctx->launches++;
       e = cudaGetLastError();
     }
-    double* h_dst = small ? hp + (size_t)K * d + code_dbl : h_ld;
-    if (st == JP_OK && e == cudaSuccess) e = cudaMemcpyAsync(h_dst, d_out, (size_t)K * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (st == JP_OK && e == cudaSuccess && !small)
+      e = cudaMemcpyAsync(h_ld, d_out, (size_t)K * 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (st == JP_OK && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (st == JP_OK && e == cudaSuccess && small) std::memcpy(h_ld, h_dst, (size_t)K * 8);
+    if (st == JP_OK && e == cudaSuccess && small) std::memcpy(h_ld, d_out, (size_t)K * 8);
   }
   if (!small) {
     jp_dfree(ctx, d_x); jp_dfree(ctx, d_theta); jp_dfree(ctx, d_part); jp_dfree(ctx, d_out); jp_dfree(ctx, d_code);
