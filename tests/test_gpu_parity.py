@@ -624,6 +624,30 @@ def test_tc_observation_sharded_prep(jp, O, gpu_ctx, world, N, level):
     assert relerr(dens, ref["density"]) < TOLTC
 
 
+@pytest.mark.parametrize("kind,N,d,level", [("logistic", 40000, 1, 5), ("logistic", 150000, 2, 7), ("poisson", 127, 2, 3),
+                                             ("logistic", 128, 3, 2), ("poisson", 129, 1, 2), ("logistic", 5000, 12, 2)],
+                         ids=["d1", "d2-L7", "N127", "N128", "N129", "d12-L2"])
+def test_auto_path_edge_shapes(jp, O, gpu_ctx, kind, N, d, level):
+    """Edge shapes through JP_PATH_AUTO: whatever the gate decides (tensor cores, or the FP64 kernel when the series
+    bounds are not met for so few observations), the result matches the FP64 kernel and the oracle."""
+    family, obs, hyper = _glm_case(kind, 300 + N % 1000 + d, N, d, 0.5)
+    code = [0] * d
+    x, H, neg_min = _cpu_mode_for(O, family, code, obs, hyper)
+    U = O.inv_chol(2.0 * H)
+    M = _model_for(jp, code)
+    dd = _upload(jp, gpu_ctx, family, obs, hyper)
+    auto = jp.fit(M, dd, level, mode_result=(x, U, neg_min))
+    f64 = jp.fit(M, dd, level, path=jp.PATH_FP64, mode_result=(x, U, neg_min))
+    assert auto.path_used in (jp.PATH_TC, jp.PATH_FP64) and auto.n_nodes == f64.n_nodes
+    tol = TOLTC if auto.path_used == jp.PATH_TC else TOL64
+    assert relerr(auto.density, f64.density) < tol
+    idx, w = O.smolyak(0, d, level)
+    ref = O.eval_grid(0, family, code, idx, w, x, U, neg_min, obs, hyper)
+    assert relerr(auto.density, ref["density"]) < tol
+    ms = jp.marginals(auto, list(range(d)))
+    assert all(np.isfinite(m.mu) and np.isfinite(jp.quantile(m, 0.5)) for m in ms)
+
+
 def test_cfg3_full_size_tc(jp, O, gpu_ctx):
     """BASELINE config 3 at full size on the tensor-core path vs the FP64 CUDA kernel and an oracle subsample."""
     from jointposteriors_jl_b200 import workloads
