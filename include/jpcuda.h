@@ -271,6 +271,14 @@ int jp_marginal_values(jp_posterior* post, int K, const double* h_values /* K x 
 int jp_marginal_sorted(jp_posterior* post, int k, double* h_sorted_values, double* h_sorted_weights,
                        double* h_cum_weights);
 
+/* update_MarginalBuffer! / Vandermonde! of the smooth-CDF path, reference src/marginal_posterior.jl:10-67 (the part
+ * of `marginal(jp, f, Normal)` that touches all M nodes; the 9-parameter fit of src/interp.jl:33-446 stays on the
+ * host and is not part of this library): for marginal k of the last jp_marginal_coords / _values call on an UNSHARDED
+ * posterior, the stable sort permutation (0-based node indices), the cumulative weights in sorted order, and the
+ * 10 x M column-major design matrix with column i = (1, z, z^2, .., z^9), z = (v_sorted[i] - mu) / sigma.  Blocking. */
+int jp_marginal_buffer(jp_posterior* post, int k, long long* h_ind, double* h_cum_weights, double* h_V, double* h_mu,
+                       double* h_sigma);
+
 /* The 100-knot Grid of the first K marginals of the last jp_marginal_* call recomputed from the explicit stable
  * sort + cumulative sum, exactly as the reference does it (src/interp.jl:21-31,448-457).  The default path above
  * gets the same knots from one binning pass without sorting; this entry point exists to cross-check it. */

@@ -53,7 +53,7 @@ SYMBOLS = [
     "jp_fit_prep_len", "jp_fit_prep_local", "jp_fit_prep_gathered", "jp_fit_coef_rows", "jp_fit_local_stats_prepared",
     "jp_get_theta", "jp_get_logdens", "jp_get_density", "jp_dev_theta", "jp_dev_density", "jp_fit_path_used",
     "jp_fit_diagnostics",
-    "jp_marginal_coords", "jp_marginal_values", "jp_marginal_sorted", "jp_marginal_knots_from_sort",
+    "jp_marginal_coords", "jp_marginal_values", "jp_marginal_sorted", "jp_marginal_buffer", "jp_marginal_knots_from_sort",
     "jp_marginal_local_moments", "jp_marginal_local_knots", "jp_marginal_local_knots_gathered",
     "jp_marginal_combine_gathered",
     "jp_quantile", "jp_cdf",

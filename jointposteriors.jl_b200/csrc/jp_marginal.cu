@@ -503,6 +503,30 @@ static int run_marginals(jp_posterior* post, int K, double* h_mu, double* h_sigm
 
 // explicit stable sort + cumulative weights of the K_last marginals of the last call (simultaneous_sort! +
 // cumsum, reference src/interp.jl:21-31); the knots computed from it (jp_knots_kernel) cross-check the bins
+// Vandermonde!(m, density, mu, sigma), reference src/marginal_posterior.jl:44-67: per sorted element the standardised
+// value z = (v - mu) / sigma and column (1, z, z^2, .., z^9) of the 10 x M design matrix of the smooth-CDF fit, with the
+// reference's own multiplication order; ind = the sort permutation as 0-based GLOBAL node indices.
+__global__ void jp_vandermonde_kernel(const double* __restrict__ sv, const uint32_t* __restrict__ perm, long long M, long long m0,
+                                      const double* __restrict__ mom, double* __restrict__ V, long long* __restrict__ ind) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const double mu = mom[0], sigma = sqrt(mom[1] - mom[0] * mom[0]);      // calc_mu_sigma, :79-86
+  const double z = (sv[i] - mu) / sigma;      // :52
+  const double z2 = z * z, z4 = z2 * z2;      // :53-54
+  double* o = V + (size_t)i * 10;
+  o[0] = 1.0;
+  o[1] = z;                                   // :55
+  o[2] = z2;
+  o[3] = z * z2;
+  o[4] = z4;
+  o[5] = z4 * z;
+  o[6] = z4 * z2;
+  o[7] = z4 * z2 * z;
+  o[8] = z4 * z4;                             // vi4^2
+  o[9] = z4 * z4 * z;
+  ind[i] = m0 + (long long)perm[i];
+}
+
 static int run_sort(jp_posterior* post) {
   jp_ctx* ctx = post->ctx;
   const long long M = post->M;
@@ -553,6 +577,39 @@ int jp_marginal_sorted(jp_posterior* post, int k, double* h_sv, double* h_sw, do
   if (h_sw) JP_CUDA(cudaMemcpyAsync(h_sw, post->d_sw + off, bytes, cudaMemcpyDeviceToHost, st));
   if (h_cw) JP_CUDA(cudaMemcpyAsync(h_cw, post->d_cw + off, bytes, cudaMemcpyDeviceToHost, st));
   JP_CUDA(cudaStreamSynchronize(st));
+  return JP_OK;
+}
+
+int jp_marginal_buffer(jp_posterior* post, int k, long long* h_ind, double* h_cum_w, double* h_V, double* h_mu,
+                       double* h_sigma) {
+  JP_REQUIRE(post && k >= 0 && k < post->K_last, "jp_marginal_buffer: marginal %d was not computed by the last call", k);
+  JP_REQUIRE(post->M == post->grid->M, "jp_marginal_buffer: the posterior holds a node shard (%lld of %lld nodes)", post->M,
+             post->grid->M);
+  jp_ctx* ctx = post->ctx;
+  if (!post->sorted_valid) JP_TRY(run_sort(post));      // 8 radix passes: the final permutation is back in d_perm_a
+  const long long M = post->M;
+  const size_t off = (size_t)k * M;
+  cudaStream_t st = ctx->stream;
+  double* d_V = nullptr;
+  long long* d_ind = nullptr;
+  JP_CUDA(jp_dmalloc(ctx, &d_V, (size_t)M * 10 * 8));
+  JP_CUDA(jp_dmalloc(ctx, &d_ind, (size_t)M * 8));
+  double* d_mom = ctx->d_scratch;                       // K x 4: sum w v, sum w v^2, min, max (calc_mu_sigma, :79-86)
+  JP_TRY(launch_moments(post, post->K_last, d_mom));
+  JP_CHECK_LAUNCH(ctx);
+  jp_vandermonde_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(post->d_sv + off, post->d_perm_a + off, M, post->m0,
+                                                                       d_mom + 4 * k, d_V, d_ind);
+  JP_CHECK_LAUNCH(ctx);
+  double ms[2];
+  if (h_V) JP_CUDA(cudaMemcpyAsync(h_V, d_V, (size_t)M * 10 * 8, cudaMemcpyDeviceToHost, st));
+  if (h_ind) JP_CUDA(cudaMemcpyAsync(h_ind, d_ind, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+  if (h_cum_w) JP_CUDA(cudaMemcpyAsync(h_cum_w, post->d_cw + off, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+  JP_CUDA(cudaMemcpyAsync(ms, d_mom + 4 * k, 16, cudaMemcpyDeviceToHost, st));
+  JP_CUDA(cudaStreamSynchronize(st));
+  jp_dfree(ctx, d_V);
+  jp_dfree(ctx, d_ind);
+  if (h_mu) *h_mu = ms[0];
+  if (h_sigma) *h_sigma = std::sqrt(ms[1] - ms[0] * ms[0]);
   return JP_OK;
 }
 

@@ -130,9 +130,32 @@ def marginals(jp, fs):
     return out
 
 
+class MarginalBuffer:
+    """What update_MarginalBuffer!(jp, f) leaves in the reference's MarginalBuffer (src/marginal_posterior.jl:10-67):
+    ind (stable sort permutation, 0-based node indices), w (cumulative weights in sorted order), V (10 x M, column i =
+    powers 0..9 of the standardised value), mu, sigma -- the node-touching input of the smooth-CDF fit."""
+
+    def __init__(self, ind, w, V, mu, sigma):
+        self.ind, self.w, self.V, self.mu, self.sigma = ind, w, V, mu, sigma
+        self.μ, self.σ = mu, sigma
+
+
+def marginal_buffer(jp, f):
+    """update_MarginalBuffer!(jp, f): evaluated on the GPU (sort, cumulative weights, Vandermonde columns).  The
+    9-parameter NestedPolyGLM fit that consumes it (reference src/interp.jl:33-446) is host code outside this library."""
+    marginals(jp, [f])                        # moments + value pointers of f on the device
+    M = jp.n_nodes
+    ind = np.zeros(M, dtype=np.int64)
+    w, V = np.zeros(M), np.zeros((M, 10))
+    mu, sg = C.c_double(), C.c_double()
+    check(lib().jp_marginal_buffer(jp.handle, C.c_int(0), ptr(ind), ptr(w), ptr(V), C.byref(mu), C.byref(sg)))
+    return MarginalBuffer(ind, w, V.T, mu.value, sg.value)
+
+
 def marginal(jp, f, kind=Grid):
     """marginal(jp, f[, Grid]) (reference src/marginal_posterior.jl:116-123)."""
     if kind is not Grid:
-        raise NotImplementedError("only the Grid CDF is on the accelerated path; the smooth NestedPolyGLM fit "
-                                  "(reference src/interp.jl:33-446) is out of scope (SURVEY section 8f)")
+        raise NotImplementedError("only the Grid CDF is built; for the smooth path the library provides the MarginalBuffer "
+                                  "(marginal_buffer(jp, f): sort, cumulative weights, Vandermonde matrix), the "
+                                  "NestedPolyGLM fit itself (reference src/interp.jl:33-446) is host code out of scope")
     return marginals(jp, [f])[0]

@@ -686,6 +686,37 @@ static double grid_interp(const double* x, const double* y, int i, double z) {
   return y[i - 2] + (z - x[i - 2]) * (y[i - 1] - y[i - 2]) / (x[i - 1] - x[i - 2]);
 }
 
+// update_MarginalBuffer! + calc_mu_sigma + Vandermonde!  (reference src/marginal_posterior.jl:10-16,44-67,79-86): the
+// node-touching part of the smooth-CDF path marginal(jp, f, Normal).  ind = sortperm(v) (stable, 0-based here), w =
+// cumulative weights in sorted order (sequential cumulative_w += d_i, :50-51), V = 10 x M column-major with column i =
+// (1, z, z^2, z z^2, z^4, z^4 z, z^4 z^2, z^4 z^2 z, (z^4)^2, (z^4)^2 z), z = (v - mu) / sigma (:52-64; row 1 is the
+// constant the MarginalBuffer constructor of the absent package provides).
+int orc_marginal_buffer(const double* values, const double* weights, long long M, long long* ind, double* cum_w, double* V,
+                        double* mu_out, double* sigma_out) {
+  double mu = 0, ex2 = 0;
+  for (long long i = 0; i < M; ++i) mu += values[i] * weights[i];                       // dot(x, w), :80
+  for (long long i = 0; i < M; ++i) ex2 += values[i] * values[i] * weights[i];          // :82-84
+  double sigma = std::sqrt(ex2 - mu * mu);                                              // :85
+  std::vector<long long> si(M);
+  std::iota(si.begin(), si.end(), 0LL);
+  std::stable_sort(si.begin(), si.end(), [&](long long a, long long b) { return values[a] < values[b]; });   // :45
+  double cumulative_w = 0;
+  for (long long i = 0; i < M; ++i) {
+    long long j = si[i];
+    cumulative_w += weights[j];                                                         // :50
+    cum_w[i] = cumulative_w;
+    ind[i] = j;
+    double v = (values[j] - mu) / sigma, v2 = v * v, v4 = v2 * v2;                      // :52-54
+    double* o = V + (size_t)i * 10;
+    o[0] = 1.0;
+    o[1] = v; o[2] = v2; o[3] = v * v2; o[4] = v4; o[5] = v4 * v; o[6] = v4 * v2; o[7] = v4 * v2 * v;   // :55-61
+    o[8] = v4 * v4; o[9] = v4 * v4 * v;                                                 // :62-63
+  }
+  *mu_out = mu;
+  *sigma_out = sigma;
+  return 0;
+}
+
 // marginal(jp, f) with the Grid CDF.  values/weights are the outputs of weights_values
 // (src/marginal_posterior.jl:98-115).  Outputs: mu, sigma (:120-121, no renormalisation, no
 // clamp), the 100 value/weight knots (interp.jl:448-457) and optionally the sorted arrays and

@@ -202,6 +202,17 @@ def marginal(values, weights, want_sorted=False):
     return out
 
 
+def marginal_buffer(values, weights):
+    values, weights = _d(values), _d(weights)
+    M = len(values)
+    ind = np.zeros(M, dtype=np.int64)
+    cw, V = np.zeros(M), np.zeros((M, 10))
+    mu, sg = C.c_double(), C.c_double()
+    lib().orc_marginal_buffer(_ptr(values), _ptr(weights), C.c_longlong(M), _ptr(ind), _ptr(cw), _ptr(V), C.byref(mu),
+                              C.byref(sg))
+    return dict(ind=ind, cum_weights=cw, V=V, mu=mu.value, sigma=sg.value)
+
+
 def quantile(weight_nodes, value_nodes, p):
     wn, vn = _d(weight_nodes), _d(value_nodes)
     return lib().orc_quantile(_ptr(wn), _ptr(vn), C.c_int(len(wn)), C.c_double(p))

@@ -307,6 +307,26 @@ def test_marginal_host_closures_and_sorted_arrays(jp, O, gpu_ctx):
     assert np.allclose(m.wv.cum_weights, mo["cum_weights"], rtol=1e-12, atol=1e-15)
 
 
+def test_marginal_buffer_matches_oracle(jp, O, gpu_ctx):
+    """jp_marginal_buffer (update_MarginalBuffer! / Vandermonde!, the GPU part of the smooth-CDF path) vs the oracle: same
+    stable permutation (ties!), cumulative weights and 10 x M design matrix; coordinate selector and host closure."""
+    obs, hyper = readme_records()
+    x, H, neg_min = cpu_mode(O, 0, [2, 2, 2], obs, hyper, [0.2, -3.0, -2.0])
+    U = O.inv_chol(2.0 * H)
+    M = jp.Model((jp.ProbabilityVector(3),))
+    post = jp.fit(M, _upload(jp, gpu_ctx, 0, obs, hyper), 6, path=jp.PATH_FP64, mode_result=(x, U, neg_min))
+    th, dens = post.Theta, post.density
+    for f, vals in ((lambda p: p[2], th[2]), (lambda p: p[1] - p[2], th[1] - th[2])):
+        b = jp.marginal_buffer(post, f)
+        o = O.marginal_buffer(vals, dens)
+        assert np.array_equal(b.ind, o["ind"])
+        assert np.allclose(b.w, o["cum_weights"], rtol=1e-12, atol=1e-15)
+        assert abs(b.mu - o["mu"]) < 1e-13 * abs(o["mu"]) + 1e-16 and abs(b.sigma - o["sigma"]) < 1e-11 * o["sigma"]
+        assert b.V.shape == (10, post.n_nodes) and np.allclose(b.V.T, o["V"], rtol=1e-9, atol=1e-12)
+    with pytest.raises(NotImplementedError):
+        jp.marginal(post, lambda p: p[0], kind="Normal")
+
+
 def test_sort_free_knots_match_explicit_sort(jp, O, gpu_ctx):
     """The default 100-knot Grid (one binning pass, no sort) equals the knots computed on the device from the explicit
     stable sort + cumulative sum (reference src/interp.jl:21-31,448-457) -- coordinate values (heavily tied),

@@ -362,3 +362,22 @@ def test_simplex_transform_dirichlet_truth(O):
                      max(abs(m["sigma"] - sd[k]) / sd[k] for k, m in enumerate(ms))))
     assert errs[0][0] < 2e-3 and errs[0][1] < 6e-3
     assert errs[1][0] < 5e-5 and errs[1][1] < 1e-4
+
+
+def test_marginal_buffer_restatement(O):
+    """orc_marginal_buffer (update_MarginalBuffer! / Vandermonde!, reference src/marginal_posterior.jl:10-67) against numpy:
+    stable sort with ties, sequential cumulative weights, powers of the standardised value."""
+    rng = np.random.default_rng(8)
+    M = 501
+    v = np.round(rng.standard_normal(M) * 3) / 3          # many ties
+    w = rng.random(M) - 0.1
+    w /= w.sum()
+    b = O.marginal_buffer(v, w)
+    order = np.argsort(v, kind="stable")
+    assert np.array_equal(b["ind"], order)
+    assert np.allclose(b["cum_weights"], np.cumsum(w[order]), rtol=1e-13, atol=1e-15)
+    mu = float(v @ w)
+    sigma = float(np.sqrt((v * v) @ w - mu * mu))
+    assert np.isclose(b["mu"], mu, rtol=1e-13) and np.isclose(b["sigma"], sigma, rtol=1e-12)
+    z = (v[order] - mu) / sigma
+    assert np.allclose(b["V"], np.stack([z ** k for k in range(10)], axis=1), rtol=1e-11, atol=1e-13)
