@@ -272,8 +272,7 @@ int jp_marginal_sorted(jp_posterior* post, int k, double* h_sorted_values, doubl
                        double* h_cum_weights);
 
 /* update_MarginalBuffer! / Vandermonde! of the smooth-CDF path, reference src/marginal_posterior.jl:10-67 (the part
- * of `marginal(jp, f, Normal)` that touches all M nodes; the 9-parameter fit of src/interp.jl:33-446 stays on the
- * host and is not part of this library): for marginal k of the last jp_marginal_coords / _values call on an UNSHARDED
+ * of `marginal(jp, f, Normal)` that touches all M nodes; jp_marginal_smooth below runs the 9-parameter fit on it): for marginal k of the last jp_marginal_coords / _values call on an UNSHARDED
  * posterior, the stable sort permutation (0-based node indices), the cumulative weights in sorted order, and the
  * 10 x M column-major design matrix with column i = (1, z, z^2, .., z^9), z = (v_sorted[i] - mu) / sigma.  Blocking. */
 int jp_marginal_buffer(jp_posterior* post, int k, long long* h_ind, double* h_cum_weights, double* h_V, double* h_mu,
@@ -314,6 +313,35 @@ int jp_marginal_combine_gathered(jp_posterior* post, int K, int world, const dou
  * Field order as in the reference: Grid(weights, values). */
 double jp_quantile(const double* h_weight_nodes, const double* h_value_nodes, int n, double p);
 double jp_cdf(const double* h_weight_nodes, const double* h_value_nodes, int n, double x);
+
+/* Smooth CDF of a marginal: marginal(jp, f, Normal) -> NestedPolyGLM, reference src/marginal_posterior.jl:124-129 and
+ * src/interp.jl:13-17 (struct: beta, theta, d = Normal(mu, sigma)), :377-384 (the fit).
+ *   F(x) = Phi(P(Q(z))), z = (x - mu) / sigma, Q(z) = z^3 + l z^2 + m z + n, P(y) = a y^3 + b y^2 + c y + d;
+ *   beta[0..9]  coefficients of P(Q(z)) in ascending powers of z        (update_ab!, src/interp.jl:203-235)
+ *   theta[0..6] = (a, c, b, d, m, l, n)                                 (update_bt!, src/interp.jl:193-199)
+ *   phi[0..8]   the unconstrained parameters the fit stopped at, objective = ntl_likelihood! there (src/interp.jl:108-111) */
+typedef struct jp_smooth_cdf {
+  double beta[10];
+  double theta[7];
+  double phi[9];
+  double mu, sigma;
+  double objective, grad_inf_norm;
+  int iterations, evaluations, converged;
+} jp_smooth_cdf;
+/* NestedPolyGLM(m, Normal(mu, sigma)) for marginal k of the last jp_marginal_coords / _values call on an UNSHARDED
+ * posterior: sort + design matrix on the device (as jp_marginal_buffer), then BFGS with a backtracking line search
+ * (src/interp.jl:380) where every evaluation of the objective and its score (ntl_likelihood! / ntscore!,
+ * src/interp.jl:81-111) is one kernel launch over all M nodes.  phi_init: 9 starting values or NULL (zeros; the
+ * reference's MarginalBuffer.init is in the absent LogDensities package); max_iter 0 = 1000 and g_tol 0 = 1e-8 (Optim's
+ * defaults).  Stopping at the iteration cap is not an error (converged = 0).  Blocking. */
+int jp_marginal_smooth(jp_posterior* post, int k, const double* phi_init, int max_iter, double g_tol, jp_smooth_cdf* out);
+/* ntl_likelihood! and ntscore! at a given phi (src/interp.jl:81-111) for marginal k; grad9 / beta10 / theta7 may be NULL. */
+int jp_smooth_objective(jp_posterior* post, int k, const double* phi, double* f, double* grad9, double* beta10,
+                        double* theta7);
+/* cdf / pdf / quantile of a fitted NestedPolyGLM: reference src/interp.jl:365-374 (host, no GPU). */
+double jp_smooth_cdf_eval(const jp_smooth_cdf* s, double x);
+double jp_smooth_pdf_eval(const jp_smooth_cdf* s, double x);
+double jp_smooth_quantile_eval(const jp_smooth_cdf* s, double p);
 
 #ifdef __cplusplus
 }

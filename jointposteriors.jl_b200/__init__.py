@@ -8,13 +8,14 @@ from ._lib import JPError, NotPositiveDefinite, PATH_AUTO, PATH_FP64, PATH_TC, l
 from .data import (BinaryClassificationData, Data, HierNormalData, LogisticData, MultinomialData, NormalLinearData,
                    PoissonData)
 from .linalg import chol, deduce_scale_dynamic, inv_chol, inv_upper, reduce_dimensions, reduce_dimensions_ldr, try_chol
-from .marginals import Grid, MarginalBuffer, cdf, marginal, marginal_buffer, marginals, quantile
+from .marginals import (Grid, MarginalBuffer, NestedPolyGLM, Normal, cdf, marginal, marginal_buffer, marginal_smooth, marginals,
+                        pdf, quantile)
 from .model import (Context, DeviceData, Dynamic, FixedRank, Full, LDR, GenzKeister, JointPosterior, JointPosteriorRaw,
                     KronrodPatterson, Model, Smolyak, SmolyakRaw, default, fit, log_density_unc, mode)
 from .params import NonCentredVector, PositiveVector, ProbabilityVector, RealVector, Simplex, parameter
 
 __all__ = [
-    "Model", "fit", "marginal", "marginals", "marginal_buffer", "MarginalBuffer", "mode", "quantile", "cdf", "Grid", "JointPosterior", "JointPosteriorRaw",
+    "Model", "fit", "marginal", "marginals", "marginal_buffer", "MarginalBuffer", "mode", "quantile", "cdf", "pdf", "Grid", "Normal", "NestedPolyGLM", "marginal_smooth", "JointPosterior", "JointPosteriorRaw",
     "parameter", "RealVector", "PositiveVector", "ProbabilityVector", "Simplex", "NonCentredVector", "Data", "BinaryClassificationData",
     "LogisticData", "PoissonData", "HierNormalData", "NormalLinearData", "MultinomialData", "Smolyak", "SmolyakRaw", "GenzKeister",
     "KronrodPatterson", "Dynamic", "Full", "FixedRank", "LDR", "default", "Context", "DeviceData", "chol", "try_chol",

@@ -40,6 +40,22 @@ class FitArgs(C.Structure):
     ]
 
 
+class SmoothCDF(C.Structure):
+    """jp_smooth_cdf of include/jpcuda.h."""
+    _fields_ = [
+        ("beta", C.c_double * 10),
+        ("theta", C.c_double * 7),
+        ("phi", C.c_double * 9),
+        ("mu", C.c_double),
+        ("sigma", C.c_double),
+        ("objective", C.c_double),
+        ("grad_inf_norm", C.c_double),
+        ("iterations", C.c_int),
+        ("evaluations", C.c_int),
+        ("converged", C.c_int),
+    ]
+
+
 # every symbol include/jpcuda.h declares (tests check that the .so exports exactly these)
 SYMBOLS = [
     "jp_last_error", "jp_version",
@@ -57,6 +73,7 @@ SYMBOLS = [
     "jp_marginal_local_moments", "jp_marginal_local_knots", "jp_marginal_local_knots_gathered",
     "jp_marginal_combine_gathered",
     "jp_quantile", "jp_cdf",
+    "jp_marginal_smooth", "jp_smooth_objective", "jp_smooth_cdf_eval", "jp_smooth_pdf_eval", "jp_smooth_quantile_eval",
 ]
 
 
@@ -80,6 +97,9 @@ def lib():
     L.jp_dev_density.restype = C.c_void_p
     for name in ("jp_quantile", "jp_cdf"):
         getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double]
+    for name in ("jp_smooth_cdf_eval", "jp_smooth_pdf_eval", "jp_smooth_quantile_eval"):
+        getattr(L, name).restype = C.c_double
+        getattr(L, name).argtypes = [C.c_void_p, C.c_double]
     _lib = L
     return L
 

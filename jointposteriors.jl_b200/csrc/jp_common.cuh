@@ -253,6 +253,7 @@ int jp_fit_tc_run_prepared(jp_posterior* post, const jp_fit_args* args);
 void jp_tc_data_free(jp_data* data);
 void jp_tc_post_free(jp_posterior* post);
 int jp_upload_fit_consts(jp_posterior* post, const jp_fit_args* args);   // mu_hat, U, transform codes -> device
+int jp_marginal_design_device(jp_posterior* post, int k, double** d_V, long long** d_ind, double* h_mu, double* h_sigma);   // jp_marginal.cu
 const double* jp_rule_nodes_dev(int rule);   // device copy of the master z-node table
 
 struct JpRule {

@@ -548,6 +548,38 @@ static int run_sort(jp_posterior* post) {
   return JP_OK;
 }
 
+// Device-resident design of the smooth-CDF fit for marginal k of the last call: sorts if needed, fills d_V (10 x M
+// column-major, caller frees with jp_dfree) and optionally the permutation; the cumulative weights are post->d_cw + k * M.
+int jp_marginal_design_device(jp_posterior* post, int k, double** d_V_out, long long** d_ind_out, double* h_mu, double* h_sigma) {
+  JP_REQUIRE(post && k >= 0 && k < post->K_last, "jp_marginal_buffer: marginal %d was not computed by the last call", k);
+  JP_REQUIRE(post->M == post->grid->M, "jp_marginal_buffer: the posterior holds a node shard (%lld of %lld nodes)", post->M,
+             post->grid->M);
+  jp_ctx* ctx = post->ctx;
+  if (!post->sorted_valid) JP_TRY(run_sort(post));      // 8 radix passes: the final permutation is back in d_perm_a
+  const long long M = post->M;
+  const size_t off = (size_t)k * M;
+  cudaStream_t st = ctx->stream;
+  double* d_V = nullptr;
+  long long* d_ind = nullptr;
+  JP_CUDA(jp_dmalloc(ctx, &d_V, (size_t)M * 10 * 8));
+  JP_CUDA(jp_dmalloc(ctx, &d_ind, (size_t)M * 8));
+  double* d_mom = ctx->d_scratch;                       // K x 4: sum w v, sum w v^2, min, max (calc_mu_sigma, :79-86)
+  JP_TRY(launch_moments(post, post->K_last, d_mom));
+  JP_CHECK_LAUNCH(ctx);
+  jp_vandermonde_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(post->d_sv + off, post->d_perm_a + off, M, post->m0,
+                                                                       d_mom + 4 * k, d_V, d_ind);
+  JP_CHECK_LAUNCH(ctx);
+  JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, d_mom + 4 * k, 16, cudaMemcpyDeviceToHost, st));
+  JP_CUDA(cudaStreamSynchronize(st));
+  const double m1 = ctx->h_pinned[0], m2 = ctx->h_pinned[1];
+  if (h_mu) *h_mu = m1;
+  if (h_sigma) *h_sigma = std::sqrt(m2 - m1 * m1);
+  *d_V_out = d_V;
+  if (d_ind_out) *d_ind_out = d_ind;
+  else jp_dfree(ctx, d_ind);
+  return JP_OK;
+}
+
 extern "C" {
 
 int jp_marginal_coords(jp_posterior* post, int K, const int* h_coords, double* h_mu, double* h_sigma,
@@ -582,34 +614,18 @@ int jp_marginal_sorted(jp_posterior* post, int k, double* h_sv, double* h_sw, do
 
 int jp_marginal_buffer(jp_posterior* post, int k, long long* h_ind, double* h_cum_w, double* h_V, double* h_mu,
                        double* h_sigma) {
-  JP_REQUIRE(post && k >= 0 && k < post->K_last, "jp_marginal_buffer: marginal %d was not computed by the last call", k);
-  JP_REQUIRE(post->M == post->grid->M, "jp_marginal_buffer: the posterior holds a node shard (%lld of %lld nodes)", post->M,
-             post->grid->M);
-  jp_ctx* ctx = post->ctx;
-  if (!post->sorted_valid) JP_TRY(run_sort(post));      // 8 radix passes: the final permutation is back in d_perm_a
-  const long long M = post->M;
-  const size_t off = (size_t)k * M;
-  cudaStream_t st = ctx->stream;
   double* d_V = nullptr;
   long long* d_ind = nullptr;
-  JP_CUDA(jp_dmalloc(ctx, &d_V, (size_t)M * 10 * 8));
-  JP_CUDA(jp_dmalloc(ctx, &d_ind, (size_t)M * 8));
-  double* d_mom = ctx->d_scratch;                       // K x 4: sum w v, sum w v^2, min, max (calc_mu_sigma, :79-86)
-  JP_TRY(launch_moments(post, post->K_last, d_mom));
-  JP_CHECK_LAUNCH(ctx);
-  jp_vandermonde_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(post->d_sv + off, post->d_perm_a + off, M, post->m0,
-                                                                       d_mom + 4 * k, d_V, d_ind);
-  JP_CHECK_LAUNCH(ctx);
-  double ms[2];
+  JP_TRY(jp_marginal_design_device(post, k, &d_V, &d_ind, h_mu, h_sigma));
+  jp_ctx* ctx = post->ctx;
+  const long long M = post->M;
+  cudaStream_t st = ctx->stream;
   if (h_V) JP_CUDA(cudaMemcpyAsync(h_V, d_V, (size_t)M * 10 * 8, cudaMemcpyDeviceToHost, st));
   if (h_ind) JP_CUDA(cudaMemcpyAsync(h_ind, d_ind, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
-  if (h_cum_w) JP_CUDA(cudaMemcpyAsync(h_cum_w, post->d_cw + off, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
-  JP_CUDA(cudaMemcpyAsync(ms, d_mom + 4 * k, 16, cudaMemcpyDeviceToHost, st));
+  if (h_cum_w) JP_CUDA(cudaMemcpyAsync(h_cum_w, post->d_cw + (size_t)k * M, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
   JP_CUDA(cudaStreamSynchronize(st));
   jp_dfree(ctx, d_V);
   jp_dfree(ctx, d_ind);
-  if (h_mu) *h_mu = ms[0];
-  if (h_sigma) *h_sigma = std::sqrt(ms[1] - ms[0] * ms[0]);
   return JP_OK;
 }
 

@@ -2,6 +2,8 @@
 Grid part of src/interp.jl.
 
     marginal(jp, f) -> marginal with fields wv, μ, σ, itp       reference src/marginal_posterior.jl:3-8,117-123
+    marginal(jp, f, Normal) -> the same with itp::NestedPolyGLM  reference src/marginal_posterior.jl:124-129,
+                                                                 src/interp.jl:13-17,365-384
     quantile(m, p), cdf(m, x)                                    reference src/marginal_posterior.jl:140-148,
                                                                  src/interp.jl:458-481
     show(m)                                                      reference src/marginal_posterior.jl:150-155
@@ -14,7 +16,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import GRID_KNOTS, check, f64, lib, ptr
+from ._lib import GRID_KNOTS, SmoothCDF, check, f64, lib, ptr
 from .params import probe_coordinate
 
 
@@ -63,25 +65,71 @@ class marginal_result:
     def cdf(self, x):
         return cdf(self, x)
 
+    def pdf(self, x):
+        return pdf(self, x)
+
     def __repr__(self):   # reference src/marginal_posterior.jl:150-155
         q = [quantile(self, p) for p in (.025, .25, .5, .75, .975)]
         return "Marginal parameter\nμ: %r\nσ: %r\nQuantiles: [%s]" % (self.mu, self.sigma, " ".join("%.6g" % v for v in q))
 
 
+class Normal:
+    """Tag of the smooth CDF family, as `Normal` in `marginal(jp, f, Normal)` (reference src/marginal_posterior.jl:124-129)."""
+
+
+class NestedPolyGLM:
+    """Smooth CDF Phi(P(Q((x - mu) / sigma))) with nested monotone cubics (reference struct, src/interp.jl:13-17: beta,
+    theta, d = Normal(mu, sigma)); fitted by the library (jp_marginal_smooth).  `info` holds the optimiser's report."""
+
+    def __init__(self, c):
+        self._c = c
+        self.beta, self.theta, self.phi = np.array(c.beta), np.array(c.theta), np.array(c.phi)
+        self.β, self.θ = self.beta, self.theta
+        self.mu, self.sigma = c.mu, c.sigma
+        self.info = dict(objective=c.objective, grad_inf_norm=c.grad_inf_norm, iterations=c.iterations,
+                         evaluations=c.evaluations, converged=bool(c.converged))
+
+    def _call(self, fn, x):
+        if np.ndim(x) > 0:
+            return np.array([fn(C.byref(self._c), float(v)) for v in np.ravel(x)]).reshape(np.shape(x))
+        return fn(C.byref(self._c), float(x))
+
+    def cdf(self, x):          # reference src/interp.jl:365-367
+        return self._call(lib().jp_smooth_cdf_eval, x)
+
+    def pdf(self, x):          # reference src/interp.jl:371-374
+        return self._call(lib().jp_smooth_pdf_eval, x)
+
+    def quantile(self, p):     # reference src/interp.jl:368-370
+        return self._call(lib().jp_smooth_quantile_eval, p)
+
+
 def quantile(m, p):
-    """quantile(::Grid, p) (reference src/interp.jl:467-478); vectorised over p."""
+    """quantile(::Grid, p) (reference src/interp.jl:467-478) / quantile(::NestedPolyGLM, p) (:368-370); vectorised over p."""
     itp = m.itp if isinstance(m, marginal_result) else m
+    if isinstance(itp, NestedPolyGLM):
+        return itp.quantile(p)
     if np.ndim(p) > 0:
         return np.array([quantile(itp, float(x)) for x in np.ravel(p)]).reshape(np.shape(p))
     return lib().jp_quantile(ptr(itp.weights), ptr(itp.values), C.c_int(len(itp.weights)), C.c_double(float(p)))
 
 
 def cdf(m, x):
-    """cdf(::Grid, x) (reference src/interp.jl:458-466); vectorised over x."""
+    """cdf(::Grid, x) (reference src/interp.jl:458-466) / cdf(::NestedPolyGLM, x) (:365-367); vectorised over x."""
     itp = m.itp if isinstance(m, marginal_result) else m
+    if isinstance(itp, NestedPolyGLM):
+        return itp.cdf(x)
     if np.ndim(x) > 0:
         return np.array([cdf(itp, float(v)) for v in np.ravel(x)]).reshape(np.shape(x))
     return lib().jp_cdf(ptr(itp.weights), ptr(itp.values), C.c_int(len(itp.weights)), C.c_double(float(x)))
+
+
+def pdf(m, x):
+    """pdf(m, x) (reference src/marginal_posterior.jl:143-145): defined for the smooth CDF (src/interp.jl:371-374)."""
+    itp = m.itp if isinstance(m, marginal_result) else m
+    if not isinstance(itp, NestedPolyGLM):
+        raise TypeError("pdf is defined for marginal(jp, f, Normal) only, as in the reference (a Grid has no pdf method)")
+    return itp.pdf(x)
 
 
 def _classify(jp, fs):
@@ -141,8 +189,8 @@ class MarginalBuffer:
 
 
 def marginal_buffer(jp, f):
-    """update_MarginalBuffer!(jp, f): evaluated on the GPU (sort, cumulative weights, Vandermonde columns).  The
-    9-parameter NestedPolyGLM fit that consumes it (reference src/interp.jl:33-446) is host code outside this library."""
+    """update_MarginalBuffer!(jp, f): evaluated on the GPU (sort, cumulative weights, Vandermonde columns); the download
+    is for inspection -- marginal(jp, f, Normal) consumes the same buffers on the device."""
     marginals(jp, [f])                        # moments + value pointers of f on the device
     M = jp.n_nodes
     ind = np.zeros(M, dtype=np.int64)
@@ -152,10 +200,24 @@ def marginal_buffer(jp, f):
     return MarginalBuffer(ind, w, V.T, mu.value, sg.value)
 
 
-def marginal(jp, f, kind=Grid):
-    """marginal(jp, f[, Grid]) (reference src/marginal_posterior.jl:116-123)."""
-    if kind is not Grid:
-        raise NotImplementedError("only the Grid CDF is built; for the smooth path the library provides the MarginalBuffer "
-                                  "(marginal_buffer(jp, f): sort, cumulative weights, Vandermonde matrix), the "
-                                  "NestedPolyGLM fit itself (reference src/interp.jl:33-446) is host code out of scope")
-    return marginals(jp, [f])[0]
+def marginal_smooth(jp, f, init=None, max_iter=0, g_tol=0.0):
+    """marginal(jp, f, Normal): update_MarginalBuffer! then NestedPolyGLM(m, Normal(mu, sigma)) (reference
+    src/marginal_posterior.jl:10-16,124-129; src/interp.jl:377-384), both in the library: the sort, cumulative weights,
+    design matrix and every objective / score evaluation of the BFGS iteration run on the GPU over all nodes."""
+    m = marginals(jp, [f])[0]                 # moments + value pointers of f on the device
+    c = SmoothCDF()
+    x0 = None if init is None else f64(init)
+    if x0 is not None and x0.shape != (9,):
+        raise ValueError("init: 9 unconstrained parameters expected")
+    check(lib().jp_marginal_smooth(jp.handle, C.c_int(0), ptr(x0), C.c_int(int(max_iter)), C.c_double(float(g_tol)),
+                                   C.byref(c)))
+    return marginal_result(jp, 0, c.mu, c.sigma, NestedPolyGLM(c))
+
+
+def marginal(jp, f, kind=Grid, **kw):
+    """marginal(jp, f[, Grid]) (reference src/marginal_posterior.jl:116-123) and marginal(jp, f, Normal) (:124-129)."""
+    if kind is Grid:
+        return marginals(jp, [f])[0]
+    if kind is Normal:
+        return marginal_smooth(jp, f, **kw)
+    raise NotImplementedError("Currently unsupported.")      # the reference throws the same for Gamma (:130-133)

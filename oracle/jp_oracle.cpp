@@ -823,6 +823,109 @@ double orc_glm_grad_hess(int family, const double* beta, int d, const double* ob
   return (double)ll;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Smooth CDF marginal(jp, f, Normal): the NestedPolyGLM objective and score, reference src/interp.jl:56-175 and :203-321.
+// CDF model: F(x) = Phi(P(Q(z))), z = (x - mu) / sigma, Q(z) = z^3 + l z^2 + m z + n (monotone: l^2 < 3m),
+// P(y) = a y^3 + b y^2 + c y + d (monotone: b^2 < 3ac); beta = the 10 coefficients of the composition (update_ab!, :203-235),
+// theta = (a, c, b, d, m, l, n) (update_bt!, :193-199).  Residuals delta_i = Phi(V_i . beta) - w_i against the cumulative
+// weights (calculate_common!, :56-64) enter a Gaussian likelihood with tridiagonal Toeplitz precision (1, -rho) / sigma2
+// (ToeplitzSymTriQuadForm!, :128-143; log_det_tstd, :147-156); the parameter log-Jacobian (:293-295) and phi_1^2 are added:
+//   f(phi) = (Q - logdet(rho, n) - 2 lj(phi) + phi_1^2) / n + phi_8                                 (ntl_likelihood!, :108-111)
+// The score follows ntscore! (:81-106); where the reference multiplies by its hand-tabulated 64-entry Jacobian alpha
+// (:236-289) and takes the log-determinant derivative by a complex step (:102), this restatement applies the chain rule of the
+// same maps analytically.  The 9 unconstrained parameters: phi = (log a, log c, logit-like b, d, log m, logit-like l, n,
+// log sigma2, logit 4 rho).
+static void smooth_coefficients(const double* phi, double* beta, double* theta, double* sigma2, double* rho,
+                                double* J /* 10 x 7 row-major: d beta / d phi_1..7, or null */) {
+  const double a = std::exp(phi[0]), c = std::exp(phi[1]);                       // :204-205
+  const double e3 = std::exp(phi[2]), t3 = (e3 - 1) / (e3 + 1);
+  const double sb = std::sqrt(3 * a * c), b = sb * t3;                           // :207
+  const double d = phi[3], m = std::exp(phi[4]);                                 // :208, :213
+  const double e6 = std::exp(phi[5]), t6 = (e6 - 1) / (e6 + 1);
+  const double sl = std::sqrt(3 * m), l = sl * t6;                               // :210
+  const double n = phi[6];
+  *sigma2 = std::exp(phi[7]);                                                    // :211
+  *rho = 1.0 / (4.0 * (1.0 + std::exp(-phi[8])));                                // :212
+  double q1[4] = {n, m, l, 1.0}, q2[7] = {0}, q3[10] = {0};
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) q2[i + j] += q1[i] * q1[j];
+  for (int i = 0; i < 7; ++i) for (int j = 0; j < 4; ++j) q3[i + j] += q2[i] * q1[j];
+  for (int k = 0; k < 10; ++k) beta[k] = a * q3[k] + (k < 7 ? b * q2[k] : 0.0) + (k < 4 ? c * q1[k] : 0.0);   // :224-233
+  beta[0] += d;
+  if (theta) { theta[0] = a; theta[1] = c; theta[2] = b; theta[3] = d; theta[4] = m; theta[5] = l; theta[6] = n; }   // :193-199
+  if (!J) return;
+  // P'(Q(z)) as a polynomial in z: the derivative of beta with respect to a coefficient z^j of Q is P'(Q) shifted by j
+  double g[7];
+  for (int k = 0; k < 7; ++k) g[k] = 3 * a * q2[k] + (k < 4 ? 2 * b * q1[k] : 0.0);
+  g[0] += c;
+  const double db3 = sb * 2 * e3 / ((e3 + 1) * (e3 + 1)), dl6 = sl * 2 * e6 / ((e6 + 1) * (e6 + 1));   // bt / lt of :234-235
+  for (int k = 0; k < 10; ++k) {
+    const double da = q3[k], dbk = k < 7 ? q2[k] : 0.0, dc = k < 4 ? q1[k] : 0.0;
+    const double dn = k < 7 ? g[k] : 0.0, dm = (k >= 1 && k < 8) ? g[k - 1] : 0.0, dl = (k >= 2 && k < 9) ? g[k - 2] : 0.0;
+    double* r = J + 7 * k;
+    r[0] = a * da + 0.5 * b * dbk;      // phi_1 = log a: b = sqrt(3ac) t3 moves with a
+    r[1] = c * dc + 0.5 * b * dbk;      // phi_2 = log c
+    r[2] = db3 * dbk;
+    r[3] = k == 0 ? 1.0 : 0.0;
+    r[4] = m * dm + 0.5 * l * dl;       // phi_5 = log m: l = sqrt(3m) t6 moves with m
+    r[5] = dl6 * dl;
+    r[6] = dn;
+  }
+}
+static double nlogit_lj(double x) { const double e = std::exp(x); return std::log(2 + e + 1 / e); }           // :318-321
+static double dnlogit_lj(double x) { const double e = std::exp(x), e2 = e * e; return (1 - e2) / (2 * e + e2 + 1); }   // :326-330
+
+int orc_smooth_objective(const double* V, const double* cw, long long M, const double* phi, double* f_out, double* grad9,
+                         double* beta_out, double* theta_out) {
+  double beta[10], theta[7], J[70], sigma2, rho;
+  smooth_coefficients(phi, beta, theta, &sigma2, &rho, J);
+  const double inv_sqrt2 = 1.0 / std::sqrt(2.0), inv_sqrt_2pi = std::pow(2 * M_PI, -0.5);
+  std::vector<double> delta(M), pdf(M);
+  for (long long i = 0; i < M; ++i) {
+    const double* v = V + (size_t)i * 10;
+    double eta = 0;
+    for (int k = 0; k < 10; ++k) eta += v[k] * beta[k];                          // At_mul_B!(V beta), :60
+    delta[i] = (1 + std::erf(eta * inv_sqrt2)) / 2 - cw[i];                      // :49-51, :61
+    pdf[i] = std::exp(-eta * eta / 2) * inv_sqrt_2pi;                            // :52-54
+  }
+  double d2 = 0, dc = 0, lag = 0;                                                // :128-139
+  for (long long i = 0; i < M; ++i) { d2 += delta[i] * delta[i]; dc += delta[i] * lag; lag = delta[i]; }
+  const double Q = (d2 - 2 * rho * dc) / sigma2;
+  // log_det_tstd (:147-156) and its derivative in rho (the reference takes it by a complex step, :102)
+  double out = 1, lag1 = 1, lag2 = 0, dout = 0, dlag1 = 0, dlag2 = 0;
+  const double r2 = rho * rho;
+  for (long long i = 0; i < M; ++i) {
+    out -= r2 * lag2;
+    dout -= 2 * rho * lag2 + r2 * dlag2;
+    lag2 = lag1; lag1 = out;
+    dlag2 = dlag1; dlag1 = dout;
+  }
+  const double logdet = std::log(out), dlogdet = dout / out;
+  const double lj = 3 * (phi[0] + phi[1] + phi[4]) / 2 - nlogit_lj(phi[2]) - nlogit_lj(phi[5]) + phi[7] - nlogit_lj(phi[8]);   // :293-295
+  if (f_out) *f_out = (Q - logdet - 2 * lj + phi[0] * phi[0]) / (double)M + phi[7];                                             // :108-111
+  if (beta_out) std::copy(beta, beta + 10, beta_out);
+  if (theta_out) std::copy(theta, theta + 7, theta_out);
+  if (!grad9) return 0;
+  double gb[10] = {0};
+  for (long long i = 0; i < M; ++i) {                                           // mul_tstd_x!, :66-76, then V (pdf .* z), :88-90
+    const double prev = i > 0 ? delta[i - 1] : 0.0, next = i + 1 < M ? delta[i + 1] : 0.0;
+    const double z = (delta[i] - rho * (prev + next)) * pdf[i];
+    const double* v = V + (size_t)i * 10;
+    for (int k = 0; k < 10; ++k) gb[k] += v[k] * z;
+  }
+  for (int k = 0; k < 10; ++k) gb[k] = 2 * gb[k] / sigma2;                      // :91-93
+  double g[9] = {0};
+  for (int j = 0; j < 7; ++j) for (int k = 0; k < 10; ++k) g[j] += J[7 * k + j] * gb[k];   // A_mul_B!(grad alpha, alpha, grad beta), :95
+  g[0] += 2 * phi[0];                                                           // :100
+  g[7] = -Q + (double)M;                                                        // :101 (Q[2] = -Q, :141)
+  const double er = std::exp(phi[8]);
+  g[8] = (-2 * dc / sigma2 - dlogdet) * (1 / (2 + er + 1 / er)) / 4;            // :102-103 (Q[3], :142; logit_lj, :322-325)
+  g[0] -= 3.0; g[1] -= 3.0; g[2] -= 2 * dnlogit_lj(phi[2]);                     // nlj_grad!, :296-305
+  g[4] -= 3.0; g[5] -= 2 * dnlogit_lj(phi[5]);
+  g[7] -= 2.0; g[8] -= 2 * dnlogit_lj(phi[8]);
+  for (int j = 0; j < 9; ++j) grad9[j] = g[j] / (double)M;                      // :105
+  return 0;
+}
+
 int orc_num_threads() { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"

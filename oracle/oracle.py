@@ -223,6 +223,78 @@ def cdf(weight_nodes, value_nodes, x):
     return lib().orc_cdf(_ptr(wn), _ptr(vn), C.c_int(len(wn)), C.c_double(x))
 
 
+# ---------------------------------------------------------------- smooth CDF (marginal(jp, f, Normal))
+SMOOTH_INIT = np.zeros(9)      # MarginalBuffer.init lives in the absent LogDensities; zeros: a = c = m = 1, b = l = n = d = 0
+
+
+def smooth_objective(V, cum_weights, phi, want_grad=True):
+    """ntl_likelihood! / ntscore!, reference src/interp.jl:81-111.  Returns f, grad[9], beta[10], theta[7]."""
+    V, cw, phi = _d(V), _d(cum_weights), _d(phi)
+    f = C.c_double()
+    g = np.zeros(9) if want_grad else None
+    beta, theta = np.zeros(10), np.zeros(7)
+    lib().orc_smooth_objective(_ptr(V), _ptr(cw), C.c_longlong(len(cw)), _ptr(phi), C.byref(f), _ptr(g), _ptr(beta),
+                               _ptr(theta))
+    return f.value, g, beta, theta
+
+
+def smooth_fit(V, cum_weights, mu, sigma, init=None, gtol=1e-8, maxiter=4000):
+    """NestedPolyGLM(m, Normal(mu, sigma)), reference src/interp.jl:377-384: BFGS on (f, score) from `init`.  The reference
+    uses Optim's BFGS with a backtracking line search; here scipy's (test side only)."""
+    from scipy.optimize import minimize
+
+    def fg(phi):
+        f, g, _, _ = smooth_objective(V, cum_weights, phi)
+        if not np.isfinite(f):
+            return 1e300, np.zeros(9)
+        return f, g
+
+    r = minimize(fg, SMOOTH_INIT.copy() if init is None else _d(init), jac=True, method="BFGS",
+                 options=dict(gtol=gtol, maxiter=maxiter))
+    f, g, beta, theta = smooth_objective(V, cum_weights, r.x)
+    return dict(phi=r.x, f=f, grad=g, beta=beta, theta=theta, mu=mu, sigma=sigma, iterations=r.nit)
+
+
+def smooth_cdf(fit, x):
+    """reference src/interp.jl:365-367 with polyexpreval (:338-346)."""
+    from scipy.special import erf
+    z = (x - fit["mu"]) / fit["sigma"]
+    b = fit["beta"]
+    zi, out = z, b[0] + z * b[1]
+    for i in range(2, len(b)):
+        zi = zi * z
+        out = out + zi * b[i]
+    return (1 + erf(out / np.sqrt(2))) / 2
+
+
+def smooth_pdf(fit, x):
+    """reference src/interp.jl:371-374 with d-polyexpreval (:348-361)."""
+    z = (x - fit["mu"]) / fit["sigma"]
+    b = fit["beta"]
+    fx, dfx, zi = b[0], 0.0, 1.0
+    for i in range(1, len(b)):
+        dfx = dfx + zi * i * b[i]
+        zi = zi * z
+        fx = fx + zi * b[i]
+    return np.exp(-fx * fx / 2) * (2 * np.pi) ** -0.5 * dfx / fit["sigma"]
+
+
+def _one_cubic_root(a, c, b, d):
+    """reference src/interp.jl:388-394 (argument order a, c, b, d as there)."""
+    D0 = b * b - 3 * a * c
+    D1 = 2 * b ** 3 - 9 * a * b * c + 27 * a * a * d
+    Cc = np.cbrt((D1 + np.sqrt(D1 * D1 - 4 * D0 ** 3)) / 2)
+    return -(b + Cc + D0 / Cc) / (3 * a)
+
+
+def smooth_quantile(fit, p):
+    """reference src/interp.jl:368-370 and nested_root (:402-405)."""
+    from scipy.special import erfinv
+    t = fit["theta"]
+    r1 = _one_cubic_root(t[0], t[1], t[2], t[3] - np.sqrt(2) * erfinv(2 * p - 1))
+    return _one_cubic_root(1.0, t[4], t[5], t[6] - r1) * fit["sigma"] + fit["mu"]
+
+
 # ---------------------------------------------------------------- GLM mode (test side)
 def glm_grad_hess(family, beta, obs, hyper):
     beta, obs, hyper = _d(beta), _d(obs), _d(hyper)

@@ -243,3 +243,25 @@ def test_rank_policies_in_deduce_scale(jp, O):
     assert model.deduce_scale(m, H).shape == O.reduce_dimensions_ldr(H, 0.5).shape
     with pytest.raises(ValueError):
         jp.LDR(1.0)
+
+
+def test_smooth_cdf_host_functions(jp, O):
+    """jp_smooth_cdf_eval / _pdf_eval / _quantile_eval (reference src/interp.jl:365-374) are host code: checked here against
+    the oracle's restatement for a NestedPolyGLM given by its coefficients, no GPU involved."""
+    from jointposteriors_jl_b200 import _lib
+    V = np.stack([np.linspace(-2, 2, 50) ** k for k in range(10)], 1)
+    phi = np.random.default_rng(0).standard_normal(9) * 0.4
+    _, _, beta, theta = O.smooth_objective(V, np.linspace(0, 1, 50), phi)
+    c = _lib.SmoothCDF()
+    c.beta[:], c.theta[:] = list(beta), list(theta)
+    c.mu, c.sigma = 0.3, 1.7
+    fit = dict(beta=beta, theta=theta, mu=0.3, sigma=1.7)
+    L = _lib.lib()
+    for p in (1e-5, 0.001, 0.025, 0.1, 0.3, 0.5, 0.7, 0.9, 0.975, 0.999, 1 - 1e-10):
+        q = L.jp_smooth_quantile_eval(C.byref(c), p)
+        assert abs(q - O.smooth_quantile(fit, p)) < 1e-12 * abs(q)
+        assert abs(L.jp_smooth_cdf_eval(C.byref(c), q) - p) < 1e-13
+    for x in (-3.0, 0.0, 0.3, 1.0, 4.0):
+        assert abs(L.jp_smooth_cdf_eval(C.byref(c), x) - O.smooth_cdf(fit, x)) < 1e-15
+        assert abs(L.jp_smooth_pdf_eval(C.byref(c), x) - O.smooth_pdf(fit, x)) <= 1e-14 * O.smooth_pdf(fit, x)
+    assert L.jp_smooth_quantile_eval(C.byref(c), 0.0) == -np.inf and L.jp_smooth_quantile_eval(C.byref(c), 1.0) == np.inf
