@@ -450,6 +450,18 @@ def run_product(args):
         if args.workload == "cfg1":
             api["published_reference_ms"] = 3.883
             api["published_source"] = "reference README.md:223-234 (BenchmarkTools median, fit + 3 marginals, unstated CPU)"
+        # marginal(jp, f, Normal): the smooth CDF of coordinate 0 (sort + design matrix + BFGS, one launch per evaluation)
+        pa = jp.fit(M, hdata, wl["level"], path=path)
+        jp.marginal(pa, 0, jp.Normal, max_iter=50)
+        t0 = time.perf_counter()
+        ms_ = jp.marginal(pa, 0, jp.Normal)
+        t_sm = (time.perf_counter() - t0) * 1e3
+        pa.free()
+        info = ms_.itp.info
+        api["smooth_cdf_marginal"] = dict(ms=t_sm, iterations=info["iterations"], evaluations=info["evaluations"],
+                                          us_per_evaluation=t_sm * 1e3 / max(1, info["evaluations"]), converged=info["converged"],
+                                          what="marginal(jp, f, Normal) of coordinate 0: stable sort, 10 x M design matrix, "
+                                               "BFGS (<= 1000 iterations) with every objective/score evaluation one launch over all nodes")
     if rank == 0:
         cpu = cpu_baseline(wl, (x, U, neg_min)) if world == 1 and not args.no_cpu_baseline else None
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
