@@ -758,3 +758,50 @@ def test_cfg3_full_size_tc(jp, O, gpu_ctx):
     mt, m6 = jp.marginals(tc, list(range(10))), jp.marginals(f64, list(range(10)))
     for a, b in zip(mt, m6):
         assert abs(a.mu - b.mu) <= TOLTC * max(abs(b.mu), 1e-3) and abs(a.sigma - b.sigma) <= 10 * TOLTC * b.sigma
+
+
+def _full_size_tc_vs_fp64(jp, O, gpu_ctx, wl, family, n_oracle):
+    """A BASELINE GLM configuration at full size: tensor-core path against the FP64 CUDA kernel on every node and against the
+    oracle on a node subsample (all observations), normalisation, and the marginals of every coordinate."""
+    data, d = wl["data"], wl["d"]
+    obs, hyper = data.records()
+    M = jp.Model(wl["params"])
+    dd = gpu_ctx.upload(data)
+    x, U, neg_min = jp.mode(M, dd)
+    tc = jp.fit(M, dd, wl["level"], path=jp.PATH_TC, mode_result=(x, U, neg_min))
+    assert tc.path_used == jp.PATH_TC
+    f64 = jp.fit(M, dd, wl["level"], path=jp.PATH_FP64, mode_result=(x, U, neg_min))
+    idx, w = O.smolyak(0, d, wl["level"])
+    assert tc.n_nodes == f64.n_nodes == len(w)
+    d64 = f64.density
+    assert relerr(tc.density, d64) < TOLTC
+    heavy = np.abs(d64) > 1e-6 * np.max(np.abs(d64))
+    assert np.max(np.abs(tc.logdens - f64.logdens)[heavy]) < TOLTC
+    assert abs(tc.density.sum() - 1.0) < 1e-12 and abs(d64.sum() - 1.0) < 1e-12
+    _, znodes, _ = O.rule_info(0)
+    order = np.argsort(-np.abs(d64))
+    pick = np.unique(np.concatenate([[0, 1, 2], order[:n_oracle - 5], order[len(order) // 2:len(order) // 2 + 2]]))
+    ld_ref = np.array([O.log_density_unc(family, [0] * d, x + U @ znodes[idx[m]], obs, hyper) + neg_min for m in pick])
+    scale = max(1.0, np.max(np.abs(ld_ref)))
+    assert np.max(np.abs(f64.logdens[pick] - ld_ref)) < 1e-9 * scale
+    hv = heavy[pick]
+    assert np.max(np.abs(tc.logdens[pick] - ld_ref)[hv]) < TOLTC
+    mt, m6 = jp.marginals(tc, list(range(d))), jp.marginals(f64, list(range(d)))
+    for a, b in zip(mt, m6):
+        assert abs(a.mu - b.mu) <= TOLTC * max(abs(b.mu), 1e-3) and abs(a.sigma - b.sigma) <= 10 * TOLTC * b.sigma
+        qa, qb = jp.quantile(a, PROBS5), jp.quantile(b, PROBS5)
+        assert np.max(np.abs(qa - qb)) <= 10 * TOLTC * max(b.sigma, 1e-12)
+    tc.free(); f64.free(); dd.free()
+
+
+def test_cfg4_full_size_tc(jp, O, gpu_ctx):
+    """BASELINE config 4 at full size (Poisson d=20, N=1e6, level 5 -> 189 161 nodes, 1.9e11 pairs)."""
+    from jointposteriors_jl_b200 import workloads
+    _full_size_tc_vs_fp64(jp, O, gpu_ctx, workloads.cfg4_poisson(), 2, 24)
+
+
+def test_cfg5_full_size_tc(jp, O, gpu_ctx):
+    """BASELINE config 5 at full size (logistic d=30, N=1e7, level 4 -> 45 201 nodes, 4.5e11 pairs, 2.5 GB of records; split
+    operand layout of the tensor-core kernel)."""
+    from jointposteriors_jl_b200 import workloads
+    _full_size_tc_vs_fp64(jp, O, gpu_ctx, workloads.cfg5_logistic(), 1, 10)
