@@ -94,6 +94,7 @@ struct TcDataState {
   double* d_work = nullptr;    // partials of the GLM sums
   double* d_bounds = nullptr;  // [TC_PREP_BLOCKS][TC_NBOUND]
   int glm_blocks = 0;
+  cudaEvent_t ev_bounds = nullptr;   // the bounds have reached the host (the fit waits on it, not on the whole stream)
   CUtensorMap tmA;
 };
 
@@ -1028,6 +1029,7 @@ void jp_tc_data_free(jp_data* data) {
   if (!s) return;
   jp_dfree(data->ctx, s->d_xs); jp_dfree(data->ctx, s->d_coef); jp_dfree(data->ctx, s->d_sums);
   jp_dfree(data->ctx, s->d_work); jp_dfree(data->ctx, s->d_bounds);
+  if (s->ev_bounds) cudaEventDestroy(s->ev_bounds);
   delete s;
   data->tc_state = nullptr;
 }
@@ -1044,6 +1046,7 @@ static int ensure_data_state(jp_ctx* ctx, jp_data* data, int d, int world) {
   if (data->tc_state) return JP_OK;
   TcDataState* s = new TcDataState();
   data->tc_state = s;
+  JP_CUDA(cudaEventCreateWithFlags(&s->ev_bounds, cudaEventDisableTiming));
   s->d = d;
   s->split = (3 * d > 2 * TC_KATOM) ? 1 : 0;     // three atoms compact -> two atoms split (d <= TC_KATOM is checked)
   s->kp = s->split ? 2 * TC_KATOM : ((3 * d + TC_KATOM - 1) / TC_KATOM) * TC_KATOM;
@@ -1228,8 +1231,9 @@ static int tc_fold_slice(jp_posterior* post, int NC, int rank) {
   return JP_OK;
 }
 
-// node operand, theta, FP64 quadratic part, the tensor-core kernel and the per-node finish
-static int tc_run(jp_posterior* post, const jp_fit_args* args, int NC) {
+// node operand, theta, FP64 quadratic part: independent of the series length, so the single-GPU fit queues it BEFORE it
+// waits for the bounds (the device works on it while the host decides)
+static int tc_node_prep(jp_posterior* post, const jp_fit_args* args) {
   jp_ctx* ctx = post->ctx;
   const jp_data* data = post->data;
   TcDataState* ds = static_cast<TcDataState*>(data->tc_state);
@@ -1244,6 +1248,16 @@ static int tc_run(jp_posterior* post, const jp_fit_args* args, int NC) {
       jp_rule_nodes_dev(post->grid->rule), post->d_mu, post->d_U, ds->d_sums, data->hyper[0], post->d_theta, ps->d_quad,
       ps->d_ds);
   JP_CHECK_LAUNCH(ctx);
+  return JP_OK;
+}
+
+// the tensor-core kernel and the per-node finish (after tc_node_prep)
+static int tc_run_kernel(jp_posterior* post, const jp_fit_args* args, int NC) {
+  jp_ctx* ctx = post->ctx;
+  const jp_data* data = post->data;
+  TcDataState* ds = static_cast<TcDataState*>(data->tc_state);
+  TcPostState* ps = static_cast<TcPostState*>(post->tc_state);
+  cudaStream_t st = ctx->stream;
   // work decomposition: node tiles x observation chunks on a persistent grid
   TcKernelParams kp;
   kp.ka = ds->ka;
@@ -1304,6 +1318,11 @@ static int tc_run(jp_posterior* post, const jp_fit_args* args, int NC) {
   return JP_OK;
 }
 
+static int tc_run(jp_posterior* post, const jp_fit_args* args, int NC) {
+  JP_TRY(tc_node_prep(post, args));
+  return tc_run_kernel(post, args, NC);
+}
+
 // bounds of the blocks of one prep launch -> b[TC_NBOUND] on the host ([0] a maximum, the rest sums in block order)
 static void tc_reduce_block_bounds(const double* hb, double* b) {
   for (int j = 0; j < TC_NBOUND; ++j) b[j] = 0;
@@ -1321,13 +1340,15 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   JP_TRY(tc_prep_slice(post, args, 0, ds->d_sums));
   double* hb = ctx->h_pinned + 4096;   // away from the constants staged by jp_upload_fit_consts
   JP_CUDA(cudaMemcpyAsync(hb, ds->d_bounds, (size_t)TC_PREP_BLOCKS * TC_NBOUND * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  JP_CUDA(cudaStreamSynchronize(ctx->stream));
+  JP_CUDA(cudaEventRecord(ds->ev_bounds, ctx->stream));
+  JP_TRY(tc_node_prep(post, args));                     // queued behind the copy: runs while the host waits and decides
+  JP_CUDA(cudaEventSynchronize(ds->ev_bounds));
   double b[TC_NBOUND];
   tc_reduce_block_bounds(hb, b);
   int NC = 0, fold = 0;
   JP_TRY(tc_decide(post, b, &NC, &fold));
   if (fold) JP_TRY(tc_fold_slice(post, NC, 0));
-  return tc_run(post, args, NC);
+  return tc_run_kernel(post, args, NC);
 }
 
 // ---- sharded prep, phase by phase (extern "C" wrappers in jp_fit.cu).  L = nE + 1 + TC_NBOUND doubles per rank.

@@ -231,22 +231,35 @@ jp_bins_kernel(const double* const* __restrict__ vptr, const double* __restrict_
       while (g > 0 && !(s_x[g] < vj)) --g;
       bin = g;
     }
-    // the lowest lane of every group of equal bins folds its group in lane order; the loop runs as many times as the
-    // largest group has members (all 32 only when the whole step falls into one bin)
+    // Every group of lanes with equal bins is folded into its lowest lane by a binary tree over the group's members:
+    // in each of five rounds the holders of even rank absorb the next holder above them (fixed order: reproducible).
+    // The minimum keeps the lower lane on ties, i.e. the lower node index.
     const unsigned peers = __match_any_sync(0xffffffffu, bin);
-    const bool leader = live && (peers & ((1u << lane) - 1)) == 0;
-    double sW = 0.0, mx = -INFINITY, mn = INFINITY, mi = INFINITY, mw = 0.0;
-    unsigned rest = leader ? peers : 0u;
-    while (__any_sync(0xffffffffu, rest != 0u)) {
-      const int s2 = rest ? (__ffs(rest) - 1) : lane;
-      const double vs = __shfl_sync(0xffffffffu, vj, s2), ws = __shfl_sync(0xffffffffu, wj, s2);
-      if (rest) {
-        sW += ws;
-        mx = fmax(mx, vs);
-        if (vs < mn) { mn = vs; mi = (double)(m0 + base + s2); mw = ws; }
-        rest &= rest - 1u;
+    const unsigned lt = (1u << lane) - 1u;
+    const bool leader = live && (peers & lt) == 0;
+    const bool ordinary = vj < INFINITY;                // NaN and +inf never become a minimum (nor did they in a serial fold)
+    double sW = wj, mx = fmax((double)-INFINITY, vj), mn = ordinary ? vj : (double)INFINITY;
+    int ml = ordinary ? lane : -1;                      // lane that holds the minimum
+    unsigned act = peers;                               // members of my group that still hold a partial
+#pragma unroll
+    for (int round = 0; round < 5; ++round) {
+      if (__all_sync(0xffffffffu, (act & (act - 1u)) == 0u)) break;      // every group is down to one holder
+      const unsigned above = act & ~(lt | (1u << lane));
+      const bool keep = ((act >> lane) & 1u) && (__popc(act & lt) & 1) == 0;
+      const int src = above ? (__ffs(above) - 1) : lane;
+      const double pW = __shfl_sync(0xffffffffu, sW, src), pmx = __shfl_sync(0xffffffffu, mx, src);
+      const double pmn = __shfl_sync(0xffffffffu, mn, src);
+      const int pml = __shfl_sync(0xffffffffu, ml, src);
+      if (keep && above) {
+        sW += pW;
+        mx = fmax(mx, pmx);
+        if (pmn < mn) { mn = pmn; ml = pml; }
       }
+      act = __ballot_sync(0xffffffffu, keep) & peers;
     }
+    const double mw_l = __shfl_sync(0xffffffffu, wj, max(ml, 0));
+    const double mw = ml >= 0 ? mw_l : 0.0;
+    const double mi = ml >= 0 ? (double)(m0 + base + ml) : INFINITY;
     if (leader) {
       double* bn = s_bin[warp][bin];
       bn[0] += sW;
@@ -272,26 +285,40 @@ jp_bins_kernel(const double* const* __restrict__ vptr, const double* __restrict_
 
 // one block per marginal: blocks -> bins -> knots.  FINAL: the 100-knot Grid + (mu, sigma) into mout;
 // otherwise the per-knot candidates (S, pred, succ, index, weight, x) for the cross-rank combine.
+#define JP_COMBINE_THREADS 512
 template <bool FINAL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(JP_COMBINE_THREADS)
 jp_bins_combine_kernel(const double* __restrict__ bins, int nblocks, const double* __restrict__ minmax, int minmax_stride,
                        int minmax_off, const double* __restrict__ mom, int mom_stride, double* __restrict__ out) {
   __shared__ double sb[JP_NBINS][JP_BIN_STRIDE];
+  __shared__ int s_argmin[JP_NBINS];
   __shared__ double sS[JP_GRID_KNOTS], sP[JP_GRID_KNOTS], sSucc[JP_GRID_KNOTS][3];
   const int k = blockIdx.x, t = threadIdx.x;
   const double vmin = minmax[(size_t)k * minmax_stride + minmax_off], vmax = minmax[(size_t)k * minmax_stride + minmax_off + 1];
-  if (t < JP_NBINS) {
-    double W = 0.0, mx = -INFINITY, mn = INFINITY, mi = INFINITY, mw = 0.0;
-    for (int b = 0; b < nblocks; ++b) {     // block order = ascending node index
-      const double* bn = bins + (((size_t)k * nblocks + b) * JP_NBINS + t) * JP_BIN_STRIDE;
-      W += bn[0];
-      mx = fmax(mx, bn[1]);
-      if (bn[2] < mn) { mn = bn[2]; mi = bn[3]; mw = bn[4]; }
+  // one thread per (bin, field): consecutive threads read consecutive doubles of a block's bin table; block order =
+  // ascending node index.  The index and weight of the minimum (fields 3, 4) are fetched from the block that won.
+  const int bin = t / JP_BIN_STRIDE, field = t % JP_BIN_STRIDE;
+  const double* col = bins + (size_t)k * nblocks * JP_NBINS * JP_BIN_STRIDE + t;
+  if (t < JP_NBINS * JP_BIN_STRIDE && field <= 2) {
+    double acc = field == 0 ? 0.0 : (field == 1 ? -INFINITY : INFINITY);
+    int arg = -1;
+#pragma unroll 4
+    for (int b = 0; b < nblocks; ++b) {
+      const double x = col[(size_t)b * JP_NBINS * JP_BIN_STRIDE];
+      if (field == 0) acc += x;
+      else if (field == 1) acc = fmax(acc, x);
+      else if (x < acc) { acc = x; arg = b; }
     }
-    sb[t][0] = W; sb[t][1] = mx; sb[t][2] = mn; sb[t][3] = mi; sb[t][4] = mw;
+    sb[bin][field] = acc;
+    if (field == 2) s_argmin[bin] = arg;
   }
   __syncthreads();
-  if (t == 0) {   // 99 bins: sequential prefix (mass, predecessor) and suffix (successor)
+  if (t < JP_NBINS * JP_BIN_STRIDE && field >= 3) {
+    const int arg = s_argmin[bin];
+    sb[bin][field] = arg >= 0 ? col[(size_t)arg * JP_NBINS * JP_BIN_STRIDE] : (field == 3 ? INFINITY : 0.0);
+  }
+  __syncthreads();
+  if (t == 0) {   // 99 bins: sequential prefix (mass, predecessor) ...
     double S = 0.0, pr = -INFINITY;
     for (int i = 1; i <= JP_NBINS - 1; ++i) {        // knot i reads bins 0 .. i-1
       S += sb[i - 1][0];
@@ -299,6 +326,7 @@ jp_bins_combine_kernel(const double* __restrict__ bins, int nblocks, const doubl
       sS[i] = S;
       sP[i] = pr;
     }
+  } else if (t == 32) {   // ... and, in another warp, suffix (successor)
     double mn = INFINITY, mi = INFINITY, mw = 0.0;
     for (int i = JP_NBINS - 1; i >= 1; --i) {        // knot i reads bins i .. 98; ties keep the lower bin's entry
       if (sb[i][2] <= mn && sb[i][2] < INFINITY) { mn = sb[i][2]; mi = sb[i][3]; mw = sb[i][4]; }
@@ -486,7 +514,7 @@ static int run_marginals(jp_posterior* post, int K, double* h_mu, double* h_sigm
   dim3 gb(post->bins_blocks, K);
   jp_bins_kernel<<<gb, JP_BIN_THREADS, 0, st>>>(post->d_vptr, post->d_density, M, post->m0, d_mom, 4, 2, post->d_bins);
   JP_CHECK_LAUNCH(ctx);
-  jp_bins_combine_kernel<true><<<K, 128, 0, st>>>(post->d_bins, post->bins_blocks, d_mom, 4, 2, d_mom, 4, post->d_mout);
+  jp_bins_combine_kernel<true><<<K, JP_COMBINE_THREADS, 0, st>>>(post->d_bins, post->bins_blocks, d_mom, 4, 2, d_mom, 4, post->d_mout);
   JP_CHECK_LAUNCH(ctx);
   JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, post->d_mout, (size_t)K * JP_MOUT_STRIDE * 8, cudaMemcpyDeviceToHost, st));
   JP_CUDA(cudaStreamSynchronize(st));
@@ -669,7 +697,7 @@ int jp_marginal_local_knots(jp_posterior* post, int K, const int* h_coords, cons
   jp_bins_kernel<<<gb, JP_BIN_THREADS, 0, post->ctx->stream>>>(post->d_vptr, post->d_density, post->M, post->m0, d_minmax, 2,
                                                                 0, post->d_bins);
   JP_CHECK_LAUNCH(post->ctx);
-  jp_bins_combine_kernel<false><<<K, 128, 0, post->ctx->stream>>>(post->d_bins, post->bins_blocks, d_minmax, 2, 0, nullptr, 0,
+  jp_bins_combine_kernel<false><<<K, JP_COMBINE_THREADS, 0, post->ctx->stream>>>(post->d_bins, post->bins_blocks, d_minmax, 2, 0, nullptr, 0,
                                                                    d_out);
   JP_CHECK_LAUNCH(post->ctx);
   post->K_last = K;

@@ -471,29 +471,41 @@ static double ld_binmix(const double* p, const double* obs, long long N, const d
   return lp;
 }
 // family 1: logistic regression, beta ~ N(0, hyper[0]^2); obs columns (x_0..x_{d-1}, y).
-static double ld_logistic(const double* b, int d, const double* obs, long long N, const double* h) {
-  double lp = 0;
+extern "C++" {
+template <class Acc>
+static double ld_logistic_t(const double* b, int d, const double* obs, long long N, const double* h) {
+  Acc lp = 0;
   for (int k = 0; k < d; ++k) lp += lpdf_normal(b[k], 0.0, h[0]);
   for (long long i = 0; i < N; ++i) {
     const double* r = obs + i * (d + 1);
-    double eta = 0;
-    for (int k = 0; k < d; ++k) eta += r[k] * b[k];
-    lp += r[d] * eta - softplus(eta);
+    Acc eta = 0;
+    for (int k = 0; k < d; ++k) eta += (Acc)r[k] * b[k];
+    lp += r[d] * eta - (Acc)softplus((double)eta);
   }
-  return lp;
+  return (double)lp;
+}
+}  // extern "C++"
+static double ld_logistic(const double* b, int d, const double* obs, long long N, const double* h) {
+  return ld_logistic_t<double>(b, d, obs, N, h);      // the plain loop a user's log_density(Theta, data) method runs
 }
 // family 2: Poisson regression (log link), beta ~ N(0, hyper[0]^2); the theta-independent
 // -lgamma(y+1) is omitted (it cancels in the normalisation, reference src/joint_posterior.jl:149).
-static double ld_poisson(const double* b, int d, const double* obs, long long N, const double* h) {
-  double lp = 0;
+extern "C++" {
+template <class Acc>
+static double ld_poisson_t(const double* b, int d, const double* obs, long long N, const double* h) {
+  Acc lp = 0;
   for (int k = 0; k < d; ++k) lp += lpdf_normal(b[k], 0.0, h[0]);
   for (long long i = 0; i < N; ++i) {
     const double* r = obs + i * (d + 1);
-    double eta = 0;
-    for (int k = 0; k < d; ++k) eta += r[k] * b[k];
-    lp += r[d] * eta - std::exp(eta);
+    Acc eta = 0;
+    for (int k = 0; k < d; ++k) eta += (Acc)r[k] * b[k];
+    lp += r[d] * eta - (Acc)std::exp((double)eta);
   }
-  return lp;
+  return (double)lp;
+}
+}  // extern "C++"
+static double ld_poisson(const double* b, int d, const double* obs, long long N, const double* h) {
+  return ld_poisson_t<double>(b, d, obs, N, h);
 }
 // family 3: hierarchical normal ("eight schools"): theta = (mu, tau, theta_1..theta_J), obs
 // columns (y_j, s_j); y_j ~ N(theta_j, s_j^2), theta_j ~ N(mu, tau^2), flat mu,
@@ -534,7 +546,14 @@ static double ld_multinomial(const double* t, int d, const double* obs, long lon
   return lp;
 }
 
+// orc_set_precise(1): the observation sums of the two GLM families are accumulated in 80-bit long double.  The default (0) is
+// the plain double loop a user's Julia log_density method runs -- that is what bench.py times -- but from N ~ 1e5 its own
+// rounding error (~1e-9 (N / 1e5)^1.5) exceeds the 1e-10 the FP64 CUDA path is held to, so the tests switch this on.
+static int g_precise = 0;
+void orc_set_precise(int on) { g_precise = on; }
 double orc_log_density(int family, const double* theta, int d, const double* obs, long long N, const double* hyper) {
+  if (g_precise && family == 1) return ld_logistic_t<long double>(theta, d, obs, N, hyper);
+  if (g_precise && family == 2) return ld_poisson_t<long double>(theta, d, obs, N, hyper);
   switch (family) {
     case 0: return ld_binmix(theta, obs, N, hyper);
     case 1: return ld_logistic(theta, d, obs, N, hyper);
@@ -554,6 +573,19 @@ double orc_log_density_unc(int family, const int* code, const double* x, int d, 
   double lj;
   orc_transform(code, d, x, th.data(), &lj);
   if (theta_out) std::memcpy(theta_out, th.data(), sizeof(double) * d);
+  return orc_log_density(family, th.data(), d, obs, N, hyper) + lj;
+}
+
+// The same with the observation sum of the two GLM families accumulated in 80-bit long double.  At N = 1e7 the plain double
+// loop above (what a user's Julia method does) carries ~1e-6 of rounding error in a sum of magnitude 5e6; the tests that hold
+// the CUDA paths to 1e-6 at that size use this entry point as the arbiter.
+double orc_log_density_unc_precise(int family, const int* code, const double* x, int d, const double* obs, long long N,
+                                   const double* hyper) {
+  std::vector<double> th(d);
+  double lj;
+  orc_transform(code, d, x, th.data(), &lj);
+  if (family == 1) return ld_logistic_t<long double>(th.data(), d, obs, N, hyper) + lj;
+  if (family == 2) return ld_poisson_t<long double>(th.data(), d, obs, N, hyper) + lj;
   return orc_log_density(family, th.data(), d, obs, N, hyper) + lj;
 }
 

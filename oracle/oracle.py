@@ -39,12 +39,18 @@ def lib():
         L = C.CDLL(so)
         L.orc_log_density.restype = C.c_double
         L.orc_log_density_unc.restype = C.c_double
+        L.orc_log_density_unc_precise.restype = C.c_double
         L.orc_quantile.restype = C.c_double
         L.orc_cdf.restype = C.c_double
         L.orc_glm_grad_hess.restype = C.c_double
         L.orc_smolyak_build.restype = C.c_longlong
         _LIB = L
     return _LIB
+
+
+def set_precise(on=True):
+    """Accumulate the observation sums of the GLM families in long double (tests); the default plain loop is what bench.py times."""
+    lib().orc_set_precise(C.c_int(1 if on else 0))
 
 
 def _d(a):
@@ -162,6 +168,14 @@ def log_density_unc(family, code, x, obs, hyper):
     x, obs, hyper = _d(x), _d(obs), _d(hyper)
     return lib().orc_log_density_unc(C.c_int(family), _ptr(code), _ptr(x), C.c_int(len(x)), _ptr(obs),
                                      C.c_longlong(obs.shape[0]), _ptr(hyper), None)
+
+
+def log_density_unc_precise(family, code, x, obs, hyper):
+    """log_density_unc with the observation sum of the GLM families in long double (arbiter at N = 1e7)."""
+    code = np.ascontiguousarray(code, dtype=np.int32)
+    x, obs, hyper = _d(x), _d(obs), _d(hyper)
+    return lib().orc_log_density_unc_precise(C.c_int(family), _ptr(code), _ptr(x), C.c_int(len(x)), _ptr(obs),
+                                             C.c_longlong(obs.shape[0]), _ptr(hyper))
 
 
 def eval_grid(rule, family, code, idx, w, mu_hat, U, neg_min, obs, hyper, m0=0, m1=None, threads=0, want_theta=True):

@@ -22,6 +22,7 @@ def O():
     """The CPU oracle (test infrastructure)."""
     from oracle import oracle
     oracle.build()
+    oracle.set_precise(True)      # exact observation sums for the GLM families: the arbiter, see oracle/jp_oracle.cpp
     return oracle
 
 
