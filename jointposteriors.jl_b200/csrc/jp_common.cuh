@@ -136,6 +136,7 @@ struct jp_posterior {
   int bins_blocks = 0;
   double* d_vals = nullptr;      // uploaded values K x M (host closures)
   const double** d_vptr = nullptr;  // K device pointers to the value columns
+  std::vector<const double*> vptr_host;   // what d_vptr holds (a repeated request skips the upload and its wait)
   double* d_bins = nullptr;      // [K][bins_blocks][99][5] per-block bins of the sort-free path
   uint32_t* d_perm_a = nullptr;  // K x M
   uint32_t* d_perm_b = nullptr;  // K x M

@@ -440,6 +440,7 @@ static int ensure_marginal_buffers(jp_posterior* post, int K) {
   jp_ctx* c = post->ctx;
   jp_dfree(c, (void*)post->d_vptr); jp_dfree(c, post->d_bins); jp_dfree(c, post->d_mout);
   post->d_vptr = nullptr; post->d_bins = nullptr; post->d_mout = nullptr;
+  post->vptr_host.clear();
   post->K_cap = 0;
   post->bins_blocks = bins_blocks_for(post->M);
   JP_CUDA(jp_dmalloc(c, (void**)&post->d_vptr, (size_t)K * sizeof(double*)));
@@ -484,17 +485,23 @@ static int set_value_pointers(jp_posterior* post, int K, const int* h_coords, co
   jp_ctx* ctx = post->ctx;
   JP_REQUIRE(K >= 1 && K <= 4096, "marginal: K=%d out of range", K);
   JP_REQUIRE((h_coords != nullptr) != (d_values != nullptr), "marginal: give exactly one of coords / values");
-  JP_CUDA(cudaStreamSynchronize(ctx->stream));   // pinned staging reuse
-  const double** hp = reinterpret_cast<const double**>(ctx->h_pinned);
+  std::vector<const double*> want((size_t)K);
   for (int k = 0; k < K; ++k) {
     if (h_coords) {
       JP_REQUIRE(h_coords[k] >= 0 && h_coords[k] < post->d, "marginal: coordinate %d out of range [0,%d)", h_coords[k], post->d);
-      hp[k] = post->d_theta + (size_t)h_coords[k] * post->M;
+      want[k] = post->d_theta + (size_t)h_coords[k] * post->M;
     } else {
-      hp[k] = d_values + (size_t)k * post->M;
+      want[k] = d_values + (size_t)k * post->M;
     }
   }
-  JP_CUDA(cudaMemcpyAsync((void*)post->d_vptr, hp, (size_t)K * sizeof(double*), cudaMemcpyHostToDevice, ctx->stream));
+  // the same columns as last time (every coordinate after each fit, say): the table on the device is already right
+  if (post->vptr_host.size() < (size_t)K || !std::equal(want.begin(), want.end(), post->vptr_host.begin())) {
+    JP_CUDA(cudaStreamSynchronize(ctx->stream));   // pinned staging reuse
+    const double** hp = reinterpret_cast<const double**>(ctx->h_pinned);
+    std::copy(want.begin(), want.end(), hp);
+    JP_CUDA(cudaMemcpyAsync((void*)post->d_vptr, hp, (size_t)K * sizeof(double*), cudaMemcpyHostToDevice, ctx->stream));
+    post->vptr_host = want;
+  }
   post->sorted_valid = false;
   post->K_last = 0;
   return JP_OK;

@@ -377,7 +377,8 @@ int jp_marginal_smooth(jp_posterior* post, int k, const double* phi_init, int ma
   double* d_V = nullptr;
   double mu, sigma;
   JP_TRY(jp_marginal_design_device(post, k, &d_V, nullptr, &mu, &sigma));
-  if (!(sigma > 0) || !std::isfinite(sigma)) {
+  // sigma^2 = E[v^2] - mu^2 is only known to ~1e-16 E[v^2]: below that the marginal is constant to working precision
+  if (!(sigma > 1e-7 * std::sqrt(sigma * sigma + mu * mu)) || !std::isfinite(sigma)) {
     jp_dfree(post->ctx, d_V);
     jp_set_error("jp_marginal_smooth: the marginal has no positive variance (sigma = %g)", sigma);
     return JP_ERR_BAD_ARG;

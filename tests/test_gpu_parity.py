@@ -464,6 +464,16 @@ def test_errors_are_statuses(jp, gpu_ctx):
     with pytest.raises(jp.JPError):            # reduced-rank U (d x p, p < d) must match the grid dimension
         from jointposteriors_jl_b200.model import JointPosterior
         JointPosterior(M, dd, gpu_ctx.grid(0, 3, 3), np.zeros(3), np.ones((3, 2)), 0.0)
+    # smooth CDF: a marginal without variance cannot be standardised; the marginal index must belong to the last batch
+    with pytest.raises(jp.JPError) as e:
+        jp.marginal(post, lambda p: 0.0 * p[0] + 2.0, jp.Normal)
+    assert e.value.status == 1 and "variance" in str(e.value)
+    jp.marginals(post, [0, 1])
+    from jointposteriors_jl_b200._lib import SmoothCDF
+    assert L.jp_marginal_smooth(post.handle, 2, None, 0, C.c_double(0.0), C.byref(SmoothCDF())) == 1
+    assert L.jp_marginal_smooth(post.handle, 1, None, -1, C.c_double(0.0), C.byref(SmoothCDF())) == 1
+    with pytest.raises(ValueError):
+        jp.marginal(post, 0, jp.Normal, init=np.zeros(5))
 
 
 def test_reduced_rank_scale(jp, O, gpu_ctx):

@@ -1,5 +1,7 @@
 #!/bin/bash
-TAG=${1:-r05g}
+# One gpurun call: all GPU tests, smoke, the default bench line and the (cold-cache) ncu launch list of the same bench command.
+# usage: tools/gpu_retry.sh 900 "bash tools/gpu_full.sh <tag>"
+TAG=${1:-full}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_gpu.txt 2>&1
 timeout 600 python -m pytest tests -q -m gpu -p no:cacheprovider --tb=short -s --durations=6 2>&1 | grep -v "^E    +" | tail -80 > gpurun_out/${TAG}_pytest.log
