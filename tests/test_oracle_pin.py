@@ -447,3 +447,25 @@ def test_smooth_runtests_assertions(O, readme_fit):
     b6 = _tau_buffer(O, readme_fit, 0, 6)
     fit6 = O.smooth_fit(b6["V"], b6["cum_weights"], b6["mu"], b6["sigma"], maxiter=1000)
     assert np.allclose([O.smooth_quantile(fit6, p) for p in PROBS], rt["tau"]["q"], rtol=0.035)
+
+
+def test_precise_observation_sums(O):
+    """orc_set_precise: the long-double observation sums of the GLM families (the arbiter of the full-size GPU tests) agree with
+    math.fsum to a few ulp; the reference-style plain double loop drifts by ~1e-9 (N / 1e5)^1.5."""
+    import math
+    from conftest import synth_glm
+    N, d = 200000, 8
+    X, y = synth_glm(3, N, d, "logistic", 1.0)
+    obs, hyper = np.column_stack([X, y]), np.array([10.0])
+    x = np.random.default_rng(0).standard_normal(d) * 0.3
+    eta = X @ x
+    terms = y * eta - np.logaddexp(0.0, eta)
+    exact = math.fsum(terms) + sum(-0.5 * (v / 10.0) ** 2 - math.log(10.0) - 0.5 * math.log(2 * math.pi) for v in x)
+    precise = O.log_density_unc_precise(1, [0] * d, x, obs, hyper)
+    O.set_precise(False)
+    try:
+        plain = O.log_density_unc(1, [0] * d, x, obs, hyper)
+    finally:
+        O.set_precise(True)
+    assert abs(precise - exact) <= 4 * np.spacing(abs(exact))
+    assert abs(plain - exact) < 1e-7 and abs(O.log_density_unc(1, [0] * d, x, obs, hyper) - precise) == 0.0
