@@ -50,7 +50,6 @@ __global__ void __launch_bounds__(JP_MOM_THREADS)
 jp_moments_kernel(const double* const* __restrict__ vptr, const double* __restrict__ w, long long M,
                   double* __restrict__ bpart /* [K][gridDim.x][4] */, unsigned int* __restrict__ counters /* [K] */,
                   double* __restrict__ out, int out_stride) {
-  __shared__ double sm[33];
   const int k = blockIdx.y;
   const double* v = vptr[k];
   const long long per = (M + gridDim.x - 1) / gridDim.x, b0 = (long long)blockIdx.x * per, b1 = min(M, b0 + per);
@@ -62,12 +61,21 @@ jp_moments_kernel(const double* const* __restrict__ vptr, const double* __restri
     mn = fmin(mn, x);
     mx = fmax(mx, x);
   }
-  s1 = jp_block_sum(s1, sm);
-  s2 = jp_block_sum(s2, sm);
-  mn = jp_block_min(mn, sm);
-  mx = jp_block_max(mx, sm);
+  // the four block reductions share one barrier: shuffle trees inside the warps, then thread 0 combines the warps in order
+  // (the same order, hence the same bits, as jp_block_sum / jp_block_min / jp_block_max)
+  __shared__ double sw[4][JP_MOM_THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  s1 = jp_warp_sum(s1);
+  s2 = jp_warp_sum(s2);
+  mn = jp_warp_min(mn);
+  mx = jp_warp_max(mx);
+  if (lane == 0) { sw[0][wid] = s1; sw[1][wid] = s2; sw[2][wid] = mn; sw[3][wid] = mx; }
+  __syncthreads();
   double* bp = bpart + (size_t)k * gridDim.x * 4;
   if (threadIdx.x == 0) {
+    s1 = 0; s2 = 0; mn = sw[2][0]; mx = sw[3][0];
+    for (int i = 0; i < JP_MOM_THREADS / 32; ++i) { s1 += sw[0][i]; s2 += sw[1][i]; }
+    for (int i = 1; i < JP_MOM_THREADS / 32; ++i) { mn = fmin(mn, sw[2][i]); mx = fmax(mx, sw[3][i]); }
     double* o = bp + (size_t)blockIdx.x * 4;
     o[0] = s1; o[1] = s2; o[2] = mn; o[3] = mx;
   }
@@ -302,7 +310,7 @@ jp_bins_combine_kernel(const double* __restrict__ bins, int nblocks, const doubl
   if (t < JP_NBINS * JP_BIN_STRIDE && field <= 2) {
     double acc = field == 0 ? 0.0 : (field == 1 ? -INFINITY : INFINITY);
     int arg = -1;
-#pragma unroll 4
+#pragma unroll 8
     for (int b = 0; b < nblocks; ++b) {
       const double x = col[(size_t)b * JP_NBINS * JP_BIN_STRIDE];
       if (field == 0) acc += x;
@@ -320,6 +328,7 @@ jp_bins_combine_kernel(const double* __restrict__ bins, int nblocks, const doubl
   __syncthreads();
   if (t == 0) {   // 99 bins: sequential prefix (mass, predecessor) ...
     double S = 0.0, pr = -INFINITY;
+#pragma unroll 7
     for (int i = 1; i <= JP_NBINS - 1; ++i) {        // knot i reads bins 0 .. i-1
       S += sb[i - 1][0];
       pr = fmax(pr, sb[i - 1][1]);
@@ -328,6 +337,7 @@ jp_bins_combine_kernel(const double* __restrict__ bins, int nblocks, const doubl
     }
   } else if (t == 32) {   // ... and, in another warp, suffix (successor)
     double mn = INFINITY, mi = INFINITY, mw = 0.0;
+#pragma unroll 7
     for (int i = JP_NBINS - 1; i >= 1; --i) {        // knot i reads bins i .. 98; ties keep the lower bin's entry
       if (sb[i][2] <= mn && sb[i][2] < INFINITY) { mn = sb[i][2]; mi = sb[i][3]; mw = sb[i][4]; }
       sSucc[i][0] = mn; sSucc[i][1] = mi; sSucc[i][2] = mw;
@@ -516,8 +526,7 @@ static int run_marginals(jp_posterior* post, int K, double* h_mu, double* h_sigm
   JP_REQUIRE((size_t)K * 4 <= JP_SCRATCH_DOUBLES, "marginal: K=%d too large for one call", K);
   cudaStream_t st = ctx->stream;
   double* d_mom = ctx->d_scratch;   // K x 4: sum w v, sum w v^2, min, max
-  JP_TRY(launch_moments(post, K, d_mom));
-  JP_CHECK_LAUNCH(ctx);
+  JP_TRY(launch_moments(post, K, d_mom));      // counts its own launch
   dim3 gb(post->bins_blocks, K);
   jp_bins_kernel<<<gb, JP_BIN_THREADS, 0, st>>>(post->d_vptr, post->d_density, M, post->m0, d_mom, 4, 2, post->d_bins);
   JP_CHECK_LAUNCH(ctx);
@@ -599,13 +608,24 @@ int jp_marginal_design_device(jp_posterior* post, int k, double** d_V_out, long 
   JP_CUDA(jp_dmalloc(ctx, &d_V, (size_t)M * 10 * 8));
   JP_CUDA(jp_dmalloc(ctx, &d_ind, (size_t)M * 8));
   double* d_mom = ctx->d_scratch;                       // K x 4: sum w v, sum w v^2, min, max (calc_mu_sigma, :79-86)
-  JP_TRY(launch_moments(post, post->K_last, d_mom));
-  JP_CHECK_LAUNCH(ctx);
-  jp_vandermonde_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(post->d_sv + off, post->d_perm_a + off, M, post->m0,
-                                                                       d_mom + 4 * k, d_V, d_ind);
-  JP_CHECK_LAUNCH(ctx);
-  JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, d_mom + 4 * k, 16, cudaMemcpyDeviceToHost, st));
-  JP_CUDA(cudaStreamSynchronize(st));
+  int status = launch_moments(post, post->K_last, d_mom);
+  if (status == JP_OK) {
+    jp_vandermonde_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(post->d_sv + off, post->d_perm_a + off, M, post->m0,
+                                                                         d_mom + 4 * k, d_V, d_ind);
+    ctx->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_pinned, d_mom + 4 * k, 16, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      jp_set_error("jp_marginal_buffer: %s", cudaGetErrorString(e));
+      status = JP_ERR_CUDA;
+    }
+  }
+  if (status != JP_OK) {      // the buffers go back to the pool on every path
+    jp_dfree(ctx, d_V);
+    jp_dfree(ctx, d_ind);
+    return status;
+  }
   const double m1 = ctx->h_pinned[0], m2 = ctx->h_pinned[1];
   if (h_mu) *h_mu = m1;
   if (h_sigma) *h_sigma = std::sqrt(m2 - m1 * m1);
@@ -670,8 +690,7 @@ int jp_marginal_knots_from_sort(jp_posterior* post, int K, double* h_value_nodes
   if (!post->sorted_valid) JP_TRY(run_sort(post));
   cudaStream_t st = ctx->stream;
   double* d_mom = ctx->d_scratch;
-  JP_TRY(launch_moments(post, K, d_mom));
-  JP_CHECK_LAUNCH(ctx);
+  JP_TRY(launch_moments(post, K, d_mom));      // counts its own launch
   jp_knots_kernel<<<K, 128, 0, st>>>(post->d_sv, post->d_cw, post->M, d_mom, 4, post->d_mout);
   JP_CHECK_LAUNCH(ctx);
   JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, post->d_mout, (size_t)K * JP_MOUT_STRIDE * 8, cudaMemcpyDeviceToHost, st));
@@ -688,8 +707,7 @@ int jp_marginal_local_moments(jp_posterior* post, int K, const int* h_coords, co
   JP_REQUIRE(post && d_out, "jp_marginal_local_moments: null argument");
   JP_TRY(ensure_marginal_buffers(post, K));
   JP_TRY(set_value_pointers(post, K, h_coords, d_values));
-  JP_TRY(launch_moments(post, K, d_out));
-  JP_CHECK_LAUNCH(post->ctx);
+  JP_TRY(launch_moments(post, K, d_out));      // counts its own launch
   post->K_last = K;
   return JP_OK;
 }
