@@ -16,6 +16,10 @@
 //       (README.md:110-128), and
 //   (2) brute-force tensor Gauss-Legendre truth for the README model (tests/test_oracle_pin.py), and
 //   (3) the closed-form Dirichlet posterior of the multinomial family for the simplex transform.
+//   (4) for the smooth CDF marginal(jp, f, Normal) (NestedPolyGLM objective / score, src/interp.jl:56-175,203-321, restated
+//       at the end of this file): the m_norm assertions of test/runtests.jl:49-51,60-64 at the reference's tolerance, an
+//       independent numpy restatement of the objective and central differences for the score.  The optimiser's starting point
+//       (MarginalBuffer.init) lives in the absent LogDensities package: zeros are used.
 // Beyond that tolerance the Smolyak stages are "parity unpinned" (no upstream source exists to
 // compare against); DESIGN.md says the same.
 //
