@@ -265,3 +265,26 @@ def test_smooth_cdf_host_functions(jp, O):
         assert abs(L.jp_smooth_cdf_eval(C.byref(c), x) - O.smooth_cdf(fit, x)) < 1e-15
         assert abs(L.jp_smooth_pdf_eval(C.byref(c), x) - O.smooth_pdf(fit, x)) <= 1e-14 * O.smooth_pdf(fit, x)
     assert L.jp_smooth_quantile_eval(C.byref(c), 0.0) == -np.inf and L.jp_smooth_quantile_eval(C.byref(c), 1.0) == np.inf
+
+
+def test_nested_poly_glm_host_mirror(jp, O):
+    """The Python mirror of the reference's NestedPolyGLM methods (cdf / pdf / quantile dispatch of src/marginal_posterior.jl:
+    140-148 onto src/interp.jl:365-374), vectorised, from a coefficient set -- host code only."""
+    from jointposteriors_jl_b200 import _lib
+    V = np.stack([np.linspace(-2, 2, 40) ** k for k in range(10)], 1)
+    phi = np.array([-0.3, 0.2, 0.4, 0.1, 0.3, -0.2, 0.05, -2.0, 0.5])
+    _, _, beta, theta = O.smooth_objective(V, np.linspace(0, 1, 40), phi)
+    c = _lib.SmoothCDF()
+    c.beta[:], c.theta[:], c.phi[:] = list(beta), list(theta), list(phi)
+    c.mu, c.sigma = -1.0, 0.5
+    itp = jp.NestedPolyGLM(c)
+    fit = dict(beta=beta, theta=theta, mu=-1.0, sigma=0.5)
+    ps = np.array([[0.025, 0.25], [0.5, 0.975]])
+    qs = jp.quantile(itp, ps)
+    assert qs.shape == ps.shape and np.all(np.diff(qs.ravel()) > 0)
+    assert np.allclose(qs, [[O.smooth_quantile(fit, p) for p in row] for row in ps], rtol=1e-13)
+    assert np.allclose(jp.cdf(itp, qs), ps, atol=1e-13)
+    assert np.allclose(jp.pdf(itp, qs), O.smooth_pdf(fit, qs), rtol=1e-13)
+    assert np.array_equal(itp.theta, theta) and np.array_equal(itp.β, beta)
+    with pytest.raises(TypeError):
+        jp.pdf(jp.Grid(np.linspace(0, 1, 100), np.linspace(0, 1, 100)), 0.5)      # a Grid has no pdf in the reference either
