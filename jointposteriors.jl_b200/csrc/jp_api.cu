@@ -67,6 +67,7 @@ int jp_ctx_destroy(jp_ctx* ctx) {
   jp_dfree(ctx, ctx->d_scratch); jp_dfree(ctx, ctx->d_counters); jp_dfree(ctx, ctx->d_bpart);
   cudaStreamSynchronize(ctx->stream);
   cudaFreeHost(ctx->h_pinned);
+  cudaFree(ctx->d_rule_nodes[0]); cudaFree(ctx->d_rule_nodes[1]);
   cudaEventDestroy(ctx->ev_k0);
   cudaEventDestroy(ctx->ev_k1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

@@ -45,6 +45,9 @@ void jp_set_error(const char* fmt, ...);
     }                                                                                              \
   } while (0)
 
+// every public entry point that launches work makes its context's GPU current first (several GPUs in one process)
+#define JP_ENTER_CTX(c) JP_CUDA(cudaSetDevice((c)->device))
+
 #define JP_TRY(expr)                                                                               \
   do {                                                                                             \
     int _s = (expr);                                                                               \
@@ -77,6 +80,10 @@ struct jp_ctx {
   double* h_pinned = nullptr;      // JP_PINNED_DOUBLES doubles
   unsigned int* d_counters = nullptr;   // JP_COUNTERS arrival counters of multi-block reductions (zero between kernels)
   double* d_bpart = nullptr;       // JP_BPART_DOUBLES per-block partials of those reductions
+  // __constant__ tables and the device copy of the master node tables are PER DEVICE: every context uploads its own
+  // (several GPUs in one process each get theirs; a second context on the same device re-uploads identical bytes)
+  bool rules_uploaded = false, fit_nodes_uploaded = false, tc_tables_uploaded = false;
+  double* d_rule_nodes[2] = {nullptr, nullptr};
 };
 #define JP_COUNTERS 1024
 #define JP_BPART_DOUBLES 4096
@@ -255,7 +262,7 @@ void jp_tc_data_free(jp_data* data);
 void jp_tc_post_free(jp_posterior* post);
 int jp_upload_fit_consts(jp_posterior* post, const jp_fit_args* args);   // mu_hat, U, transform codes -> device
 int jp_marginal_design_device(jp_posterior* post, int k, double** d_V, long long** d_ind, double* h_mu, double* h_sigma);   // jp_marginal.cu
-const double* jp_rule_nodes_dev(int rule);   // device copy of the master z-node table
+const double* jp_rule_nodes_dev(const jp_ctx* ctx, int rule);   // device copy of the master z-node table (this context's GPU)
 
 struct JpRule {
   int levels, nmax;

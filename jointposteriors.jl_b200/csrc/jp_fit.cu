@@ -43,7 +43,6 @@ struct JpFitLaunchParams {
 };
 
 __constant__ double c_fit_nodes[2][64];
-static bool g_fit_nodes_uploaded = false;
 
 __device__ __forceinline__ double jp_transform(int code, double x, double& lj) {
   if (code == JP_T_POSITIVE) {
@@ -304,14 +303,14 @@ JP_REGISTER_FAMILY(FamMultinomial)
 // ------------------------------------------------------------------------------------ host side
 int jp_upload_fit_consts(jp_posterior* post, const jp_fit_args* args) {
   jp_ctx* ctx = post->ctx;
-  if (!g_fit_nodes_uploaded) {
+  if (!ctx->fit_nodes_uploaded) {
     for (int r = 0; r < 2; ++r) {
       JpRule R = jp_get_rule(r);
       double nodes[64] = {0};
       for (int j = 0; j < R.nmax; ++j) nodes[j] = R.nodes[j];
       JP_CUDA(cudaMemcpyToSymbol(c_fit_nodes, nodes, sizeof nodes, sizeof(double) * 64 * r));
     }
-    g_fit_nodes_uploaded = true;
+    ctx->fit_nodes_uploaded = true;
   }
   // stage through pinned memory so the copies are truly asynchronous
   double* hp = ctx->h_pinned;
@@ -481,6 +480,8 @@ int jp_log_density_points(jp_ctx* ctx, const jp_data* data, int d, const int* h_
 }
 
 int jp_fit_local(jp_posterior* post, const jp_fit_args* args, double* d_local_max) {
+  JP_REQUIRE(post, "jp_fit_local: null posterior");
+  JP_ENTER_CTX(post->ctx);
   JP_TRY(jp_fit_check_args(post, args));
   JP_REQUIRE(d_local_max, "jp_fit_local: null output");
   // AUTO: GLM families take the tensor-core path when its a-priori error bounds hold for this
@@ -501,6 +502,7 @@ int jp_fit_local(jp_posterior* post, const jp_fit_args* args, double* d_local_ma
 
 int jp_fit_local_sum(jp_posterior* post, const double* d_global_max, double* d_local_sum) {
   JP_REQUIRE(post && d_global_max && d_local_sum, "jp_fit_local_sum: null argument");
+  JP_ENTER_CTX(post->ctx);
   jp_expw_sum_kernel<<<jp_red_blocks(post->M), 256, 0, post->ctx->stream>>>(post->M, post->m0, post->d_a, post->grid->d_w,
                                                                             d_global_max, post->d_density, post->ctx->d_bpart,
                                                                             post->ctx->d_counters, d_local_sum);
@@ -510,6 +512,7 @@ int jp_fit_local_sum(jp_posterior* post, const double* d_global_max, double* d_l
 
 int jp_fit_normalise(jp_posterior* post, const double* d_global_sum) {
   JP_REQUIRE(post && d_global_sum, "jp_fit_normalise: null argument");
+  JP_ENTER_CTX(post->ctx);
   unsigned gb = (unsigned)((post->M + 255) / 256);
   jp_scale_kernel<<<gb, 256, 0, post->ctx->stream>>>(post->M, post->d_density, d_global_sum);
   JP_CHECK_LAUNCH(post->ctx);
@@ -526,6 +529,8 @@ int jp_fit_local_stats(jp_posterior* post, const jp_fit_args* args, double* d_st
 int jp_fit_prep_len(int d) { return jp_fit_tc_prep_len(d); }
 
 int jp_fit_prep_local(jp_posterior* post, const jp_fit_args* args, int rank, int world, double* d_out) {
+  JP_REQUIRE(post, "jp_fit_prep_local: null posterior");
+  JP_ENTER_CTX(post->ctx);
   JP_TRY(jp_fit_check_args(post, args));
   JP_REQUIRE(args->path != JP_PATH_FP64, "jp_fit_prep_local: the sharded prep belongs to the tensor-core path");
   return jp_fit_tc_prep_local(post, args, rank, world, d_out);
@@ -533,6 +538,8 @@ int jp_fit_prep_local(jp_posterior* post, const jp_fit_args* args, int rank, int
 
 int jp_fit_prep_gathered(jp_posterior* post, const jp_fit_args* args, const double* d_gathered, int world, int rank,
                          int* n_rows) {
+  JP_REQUIRE(post, "jp_fit_prep_gathered: null posterior");
+  JP_ENTER_CTX(post->ctx);
   JP_TRY(jp_fit_check_args(post, args));
   return jp_fit_tc_prep_gathered(post, args, d_gathered, world, rank, n_rows);
 }
@@ -546,6 +553,8 @@ int jp_fit_coef_rows(jp_posterior* post, void** d_coef, long long* row_stride, l
 }
 
 int jp_fit_local_stats_prepared(jp_posterior* post, const jp_fit_args* args, double* d_stats) {
+  JP_REQUIRE(post, "jp_fit_local_stats_prepared: null posterior");
+  JP_ENTER_CTX(post->ctx);
   JP_TRY(jp_fit_check_args(post, args));
   JP_REQUIRE(d_stats, "jp_fit_local_stats_prepared: null output");
   JP_TRY(jp_fit_tc_run_prepared(post, args));
@@ -557,6 +566,7 @@ int jp_fit_local_stats_prepared(jp_posterior* post, const jp_fit_args* args, dou
 
 int jp_fit_normalise_gathered(jp_posterior* post, const double* d_gathered, int world, int rank) {
   JP_REQUIRE(post && d_gathered && world >= 1 && rank >= 0 && rank < world, "jp_fit_normalise_gathered: bad argument");
+  JP_ENTER_CTX(post->ctx);
   if (post->M == 0) return JP_OK;
   unsigned gb = (unsigned)((post->M + 255) / 256);
   jp_scale_gathered_kernel<<<gb, 256, 0, post->ctx->stream>>>(post->M, post->d_density, d_gathered, world, rank);
@@ -566,6 +576,7 @@ int jp_fit_normalise_gathered(jp_posterior* post, const double* d_gathered, int 
 
 int jp_fit(jp_posterior* post, const jp_fit_args* args) {
   JP_REQUIRE(post, "jp_fit: null posterior");
+  JP_ENTER_CTX(post->ctx);
   JP_TRY(jp_fit_local(post, args, post->d_stats));
   JP_TRY(jp_fit_local_sum(post, post->d_stats, post->d_stats + 1));
   JP_TRY(jp_fit_normalise(post, post->d_stats + 1));

@@ -69,6 +69,12 @@ int jp_glm_num_blocks(const jp_ctx* ctx, long long N);
 #ifndef TC_LDW
 #define TC_LDW 8                 // columns per tcgen05.ld of the epilogue (8 or 16)
 #endif
+#ifndef TC_EARLY_COEF
+#define TC_EARLY_COEF 0          // ... and loads that tile's coefficients right away when the peek succeeds
+#endif
+#ifndef TC_EARLY_PEEK
+#define TC_EARLY_PEEK 1          // epilogue peeks at the next tile's accumulator barrier one tile early
+#endif
 #define TC_PREP_BLOCKS 444       // 3 per SM (two 32 KB record tiles each at d = 30)
 #define TC_NORD 5                // series lengths NC = 4, 6, 8, 10, 12 (orders 6 .. 14)
 #define TC_NBOUND (14 + 2 * TC_NFOLD)   // per-block bound partials, see tc_obs_prep_kernel
@@ -134,6 +140,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking peek at a phase (the epilogue looks at the NEXT tile's accumulator barrier a tile early, so that the
+// barrier's read latency is off the critical path when the tile boundary comes)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
@@ -851,6 +872,15 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool more = t + 1 < t1;
         const int nbuf = (buf + 1 == TC_NBUF) ? 0 : buf + 1;
         const uint32_t taddr = lane_addr + (uint32_t)buf * TC_TMEM_STRIDE;
+#if TC_EARLY_PEEK
+        // The MMA issuer runs one to two tiles ahead: the next accumulator is normally complete when this tile starts.
+        // Peeking now (result in a register) takes the ~100-cycle barrier read off the tile boundary, where it used to
+        // sit in front of the last chunk's arithmetic in all three warps of the sub-partition at once.
+        const bool ready = more && mbar_test_wait(bar_tfull + 8u * nbuf, (tphase >> nbuf) & 1u);
+#else
+        const bool ready = false;
+#endif
+        if (TC_EARLY_COEF && ready) load_coef(cn);   // the tile's coefficient rows landed before its MMA was issued
 #pragma unroll
         for (int c = 0; c < TC_COLS_PER_WARP / TC_LDW; ++c) {
           uint32_t(&cur)[TC_LDW] = (c & 1) ? vb : va;
@@ -865,12 +895,12 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (lane == 0) mbar_arrive(bar_tempty + 8u * buf);
             if (more) {
               if (warp == 2 && lane == 0) TC_STAMP(3, ntile + 1);
-              mbar_wait(bar_tfull + 8u * nbuf, (tphase >> nbuf) & 1u);
+              if (!ready) mbar_wait(bar_tfull + 8u * nbuf, (tphase >> nbuf) & 1u);
               if (warp == 2 && lane == 0) TC_STAMP(4, ntile + 1);
               tphase ^= 1u << nbuf;
               tc_fence_after();
               if (MODE != 2 && MODE != 4) tmem_ld(nxt, lane_addr + (uint32_t)nbuf * TC_TMEM_STRIDE);
-              load_coef(cn);
+              if (!(TC_EARLY_COEF && ready)) load_coef(cn);
             }
           }
           tc_accumulate<NC, MODE, TC_LDW>(cur, cc, accE + c * (TC_LDW / 2), accO + c * (TC_LDW / 2));
@@ -958,9 +988,8 @@ static int make_tensor_map(CUtensorMap* map, float* base, long long rows, int kp
   return JP_OK;
 }
 
-static int upload_tables() {
-  static bool done = false;
-  if (done) return JP_OK;
+static int upload_tables(jp_ctx* ctx) {
+  if (ctx->tc_tables_uploaded) return JP_OK;
   double poly[TC_ORDER_MAX + 1][TC_ORDER_MAX + 2] = {{0}};
   double inv_fact[TC_ORDER_MAX + 2];
   // f_1 = s ; f_{k+1} = f_k'(s) (s - s^2), exact in integers (|coefficients| < 2^53 up to order 16)
@@ -996,7 +1025,7 @@ static int upload_tables() {
   JP_CUDA(cudaMemcpyToSymbol(c_fold_kappa, kappa, sizeof kappa));
   JP_CUDA(cudaMemcpyToSymbol(c_fold_eps, eps, sizeof eps));
   JP_CUDA(cudaMemcpyToSymbol(c_fold_grow, grow, sizeof grow));
-  done = true;
+  ctx->tc_tables_uploaded = true;
   return JP_OK;
 }
 
@@ -1174,7 +1203,7 @@ static int tc_setup(jp_posterior* post, const jp_fit_args* args, int world) {
   jp_data* data = const_cast<jp_data*>(post->data);
   if (!tc_static_ok(post, args)) return JP_ERR_UNSUPPORTED;
   JP_REQUIRE(post->grid->M % 2 == 1, "tensor-core path: the grid is not in mirror order (even node count %lld)", post->grid->M);
-  JP_TRY(upload_tables());
+  JP_TRY(upload_tables(ctx));
   JP_TRY(ensure_data_state(ctx, data, args->d, world));
   TcDataState* ds = static_cast<TcDataState*>(data->tc_state);
   JP_REQUIRE(ds->d == args->d, "tensor-core path: data was prepared for d=%d", ds->d);
@@ -1245,7 +1274,7 @@ static int tc_node_prep(jp_posterior* post, const jp_fit_args* args) {
     JP_CUDA(cudaFuncSetAttribute(tc_node_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_node));
   tc_node_prep_kernel<<<(unsigned)((post->M + 127) / 128), 128, sm_node, st>>>(
       d, p, ds->kp_b, ds->split ? TC_KATOM : d, post->grid->rule, post->M, post->m0, post->grid->M, ps->j_lo, post->grid->d_idx,
-      jp_rule_nodes_dev(post->grid->rule), post->d_mu, post->d_U, ds->d_sums, data->hyper[0], post->d_theta, ps->d_quad,
+      jp_rule_nodes_dev(ctx, post->grid->rule), post->d_mu, post->d_U, ds->d_sums, data->hyper[0], post->d_theta, ps->d_quad,
       ps->d_ds);
   JP_CHECK_LAUNCH(ctx);
   return JP_OK;

@@ -31,11 +31,9 @@ JpRule jp_get_rule(int rule) {
 __constant__ double c_rule_nodes[2][JP_RULE_NMAX];
 __constant__ double c_rule_weights[2][JP_RULE_LMAX][JP_RULE_NMAX];
 __constant__ int c_rule_npts[2][JP_RULE_LMAX];
-static double* g_rule_nodes_dev[2] = {nullptr, nullptr};
 
-static int upload_rules() {
-  static bool done = false;
-  if (done) return JP_OK;
+static int upload_rules(jp_ctx* ctx) {
+  if (ctx->rules_uploaded) return JP_OK;
   for (int r = 0; r < 2; ++r) {
     JpRule R = jp_get_rule(r);
     double nodes[JP_RULE_NMAX] = {0};
@@ -49,13 +47,13 @@ static int upload_rules() {
     JP_CUDA(cudaMemcpyToSymbol(c_rule_nodes, nodes, sizeof nodes, sizeof(double) * JP_RULE_NMAX * r));
     JP_CUDA(cudaMemcpyToSymbol(c_rule_weights, weights, sizeof weights, sizeof(double) * JP_RULE_LMAX * JP_RULE_NMAX * r));
     JP_CUDA(cudaMemcpyToSymbol(c_rule_npts, npts, sizeof npts, sizeof(int) * JP_RULE_LMAX * r));
-    JP_CUDA(cudaMalloc (&g_rule_nodes_dev[r], sizeof(double) * JP_RULE_NMAX));
-    JP_CUDA(cudaMemcpy(g_rule_nodes_dev[r], nodes, sizeof nodes, cudaMemcpyHostToDevice));
+    JP_CUDA(cudaMalloc(&ctx->d_rule_nodes[r], sizeof(double) * JP_RULE_NMAX));
+    JP_CUDA(cudaMemcpy(ctx->d_rule_nodes[r], nodes, sizeof nodes, cudaMemcpyHostToDevice));
   }
-  done = true;
+  ctx->rules_uploaded = true;
   return JP_OK;
 }
-const double* jp_rule_nodes_dev(int rule) { return g_rule_nodes_dev[rule ? 1 : 0]; }
+const double* jp_rule_nodes_dev(const jp_ctx* ctx, int rule) { return ctx->d_rule_nodes[rule ? 1 : 0]; }
 
 // ------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(1024) jp_radix_scan_kernel(uint32_t* __restrict__ hist, int nblocks) {
@@ -291,7 +289,7 @@ int jp_grid_build(jp_ctx* ctx, int rule, int d, int level, jp_grid* g) {
   JP_REQUIRE(rule == 0 || rule == 1, "jp_grid_get: unknown rule %d", rule);
   JP_REQUIRE(d >= 1 && d <= JP_MAX_D, "jp_grid_get: d_eff=%d out of range [1,%d]", d, JP_MAX_D);
   JP_REQUIRE(level >= 1 && level <= 32, "jp_grid_get: level=%d out of range", level);
-  JP_TRY(upload_rules());
+  JP_TRY(upload_rules(ctx));
   JpRule R = jp_get_rule(rule);
   const int cap = std::min(level, R.levels);
   const int q = level + d - 1;

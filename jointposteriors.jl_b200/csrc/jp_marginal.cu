@@ -596,6 +596,7 @@ static int run_sort(jp_posterior* post) {
 // column-major, caller frees with jp_dfree) and optionally the permutation; the cumulative weights are post->d_cw + k * M.
 int jp_marginal_design_device(jp_posterior* post, int k, double** d_V_out, long long** d_ind_out, double* h_mu, double* h_sigma) {
   JP_REQUIRE(post && k >= 0 && k < post->K_last, "jp_marginal_buffer: marginal %d was not computed by the last call", k);
+  JP_ENTER_CTX(post->ctx);
   JP_REQUIRE(post->M == post->grid->M, "jp_marginal_buffer: the posterior holds a node shard (%lld of %lld nodes)", post->M,
              post->grid->M);
   jp_ctx* ctx = post->ctx;
@@ -640,6 +641,7 @@ extern "C" {
 int jp_marginal_coords(jp_posterior* post, int K, const int* h_coords, double* h_mu, double* h_sigma,
                        double* h_value_nodes, double* h_weight_nodes) {
   JP_REQUIRE(post && h_coords, "jp_marginal_coords: null argument");
+  JP_ENTER_CTX(post->ctx);
   JP_TRY(ensure_marginal_buffers(post, K));
   JP_TRY(set_value_pointers(post, K, h_coords, nullptr));
   return run_marginals(post, K, h_mu, h_sigma, h_value_nodes, h_weight_nodes);
@@ -648,6 +650,7 @@ int jp_marginal_coords(jp_posterior* post, int K, const int* h_coords, double* h
 int jp_marginal_values(jp_posterior* post, int K, const double* h_values, double* h_mu, double* h_sigma,
                        double* h_value_nodes, double* h_weight_nodes) {
   JP_REQUIRE(post && h_values, "jp_marginal_values: null argument");
+  JP_ENTER_CTX(post->ctx);
   JP_TRY(ensure_marginal_buffers(post, K));
   JP_TRY(ensure_value_buffer(post, K));
   JP_CUDA(cudaMemcpyAsync(post->d_vals, h_values, (size_t)K * post->M * 8, cudaMemcpyHostToDevice, post->ctx->stream));
@@ -657,6 +660,7 @@ int jp_marginal_values(jp_posterior* post, int K, const double* h_values, double
 
 int jp_marginal_sorted(jp_posterior* post, int k, double* h_sv, double* h_sw, double* h_cw) {
   JP_REQUIRE(post && k >= 0 && k < post->K_last, "jp_marginal_sorted: marginal %d was not computed by the last call", k);
+  JP_ENTER_CTX(post->ctx);
   if (!post->sorted_valid) JP_TRY(run_sort(post));
   size_t off = (size_t)k * post->M, bytes = (size_t)post->M * 8;
   cudaStream_t st = post->ctx->stream;
@@ -686,6 +690,7 @@ int jp_marginal_buffer(jp_posterior* post, int k, long long* h_ind, double* h_cu
 
 int jp_marginal_knots_from_sort(jp_posterior* post, int K, double* h_value_nodes, double* h_weight_nodes) {
   JP_REQUIRE(post && K >= 1 && K <= post->K_last, "jp_marginal_knots_from_sort: no marginal batch of %d to sort", K);
+  JP_ENTER_CTX(post->ctx);
   jp_ctx* ctx = post->ctx;
   if (!post->sorted_valid) JP_TRY(run_sort(post));
   cudaStream_t st = ctx->stream;
@@ -705,6 +710,7 @@ int jp_marginal_knots_from_sort(jp_posterior* post, int K, double* h_value_nodes
 
 int jp_marginal_local_moments(jp_posterior* post, int K, const int* h_coords, const double* d_values, double* d_out) {
   JP_REQUIRE(post && d_out, "jp_marginal_local_moments: null argument");
+  JP_ENTER_CTX(post->ctx);
   JP_TRY(ensure_marginal_buffers(post, K));
   JP_TRY(set_value_pointers(post, K, h_coords, d_values));
   JP_TRY(launch_moments(post, K, d_out));      // counts its own launch
@@ -715,6 +721,7 @@ int jp_marginal_local_moments(jp_posterior* post, int K, const int* h_coords, co
 int jp_marginal_local_knots(jp_posterior* post, int K, const int* h_coords, const double* d_values,
                             const double* d_minmax, double* d_out) {
   JP_REQUIRE(post && d_minmax && d_out, "jp_marginal_local_knots: null argument");
+  JP_ENTER_CTX(post->ctx);
   JP_TRY(ensure_marginal_buffers(post, K));
   if (h_coords || d_values) JP_TRY(set_value_pointers(post, K, h_coords, d_values));
   else JP_REQUIRE(K == post->K_last, "jp_marginal_local_knots: no value columns given and the last call had %d, not %d", post->K_last, K);
@@ -732,6 +739,7 @@ int jp_marginal_local_knots(jp_posterior* post, int K, const int* h_coords, cons
 int jp_marginal_local_knots_gathered(jp_posterior* post, int K, const int* h_coords, const double* d_values,
                                      const double* d_gathered_moments, int world, double* d_out) {
   JP_REQUIRE(post && d_gathered_moments && d_out && world >= 1, "jp_marginal_local_knots_gathered: bad argument");
+  JP_ENTER_CTX(post->ctx);
   JP_REQUIRE((size_t)K * 2 <= JP_BPART_DOUBLES, "marginal: K=%d too large for one call", K);
   double* d_minmax = post->ctx->d_bpart;    // K x 2 (no reduction of this ctx is in flight: one stream)
   jp_minmax_gathered_kernel<<<(K + 127) / 128, 128, 0, post->ctx->stream>>>(d_gathered_moments, world, K, d_minmax);
@@ -742,6 +750,7 @@ int jp_marginal_local_knots_gathered(jp_posterior* post, int K, const int* h_coo
 int jp_marginal_combine_gathered(jp_posterior* post, int K, int world, const double* d_gathered_moments,
                                  const double* d_gathered_cands, double* h_mu, double* h_sigma, double* h_vn, double* h_wn) {
   JP_REQUIRE(post && d_gathered_moments && d_gathered_cands && world >= 1, "jp_marginal_combine_gathered: bad argument");
+  JP_ENTER_CTX(post->ctx);
   jp_ctx* ctx = post->ctx;
   JP_REQUIRE((size_t)K * JP_MOUT_STRIDE <= JP_PINNED_DOUBLES, "marginal: K=%d too large for one call", K);
   JP_TRY(ensure_marginal_buffers(post, K));

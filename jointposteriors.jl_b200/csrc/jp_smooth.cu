@@ -360,6 +360,7 @@ extern "C" {
 
 int jp_smooth_objective(jp_posterior* post, int k, const double* phi, double* f, double* grad9, double* beta10, double* theta7) {
   JP_REQUIRE(post && phi && f, "jp_smooth_objective: null argument");
+  JP_ENTER_CTX(post->ctx);
   double* d_V = nullptr;
   JP_TRY(jp_marginal_design_device(post, k, &d_V, nullptr, nullptr, nullptr));
   SmoothProblem P{post->ctx, d_V, post->d_cw + (size_t)k * post->M, post->M};
@@ -373,6 +374,7 @@ int jp_smooth_objective(jp_posterior* post, int k, const double* phi, double* f,
 
 int jp_marginal_smooth(jp_posterior* post, int k, const double* phi_init, int max_iter, double g_tol, jp_smooth_cdf* out) {
   JP_REQUIRE(post && out, "jp_marginal_smooth: null argument");
+  JP_ENTER_CTX(post->ctx);
   JP_REQUIRE(max_iter >= 0 && g_tol >= 0, "jp_marginal_smooth: negative iteration cap or tolerance");
   double* d_V = nullptr;
   double mu, sigma;

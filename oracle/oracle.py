@@ -30,11 +30,41 @@ def build(force=False):
     return so
 
 
+_FLAVOUR = "parity"   # "parity": -O2 -ffp-contract=off (tests); "fast": -O3 -march=native (bench.py's CPU baseline only)
+
+
+def build_fast():
+    """The CPU-baseline build SURVEY section 8d specifies (-O3 -march=native), compiled ON the machine that times it
+    (so `native` is that machine's ISA) into oracle/_fast/ (git-ignored).  The parity tests never use it: contraction
+    into FMAs changes rounding."""
+    out = os.path.join(_HERE, "_fast")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libjporacle_fast.so")
+    src = os.path.join(_HERE, "jp_oracle.cpp")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call([os.environ.get("CXX", "g++"), "-O3", "-march=native", "-pthread", "-fPIC", "-std=c++17",
+                               "-shared", "-o", so, src])
+    return so
+
+
+def use_fast():
+    """Switch this process to the -O3 -march=native build (bench.py only).  Returns the flags string for the report."""
+    global _LIB, _FLAVOUR
+    try:
+        build_fast()
+    except (OSError, subprocess.CalledProcessError):
+        return "-O2 -march=x86-64-v3 -ffp-contract=off (the -O3 -march=native build failed)"
+    _LIB, _FLAVOUR = None, "fast"
+    return "-O3 -march=native"
+
+
 def lib():
     global _LIB
     if _LIB is None:
         so = os.path.join(_HERE, "libjporacle.so")
-        if not os.path.exists(so):
+        if _FLAVOUR == "fast":
+            so = os.path.join(_HERE, "_fast", "libjporacle_fast.so")
+        elif not os.path.exists(so):
             build()
         L = C.CDLL(so)
         L.orc_log_density.restype = C.c_double
