@@ -96,7 +96,7 @@ def make_workload(jp, name, n_gpus):
     from jointposteriors_jl_b200 import workloads
     if name == "cfg3":
         wl = workloads.cfg3_logistic(N=100_000 * n_gpus)
-        desc = "BASELINE cfg3: logistic regression d=10, Smolyak level 6 (114985 nodes), %d synthetic obs (1e5 x n_gpus)" % (100_000 * n_gpus)
+        desc = "BASELINE cfg3: logistic regression d=10, Smolyak level 6 (115145 nodes), %d synthetic obs (1e5 x n_gpus)" % (100_000 * n_gpus)
     elif name == "cfg4":
         wl = workloads.cfg4_poisson(N=1_000_000 * max(1, n_gpus) // max(1, n_gpus))
         desc = "BASELINE cfg4: Poisson regression d=20, Smolyak level 5 (189161 nodes), 1e6 synthetic obs, node-sharded"

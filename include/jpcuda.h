@@ -133,8 +133,17 @@ int jp_grid_dim(const jp_grid* g);
 int jp_grid_build_stats(const jp_grid* g, long long* n_multi, long long* n_premerge);
 /* h_idx: M x d_eff row-major uint8 keys; h_w: M weights.  Either may be NULL. */
 int jp_grid_download(const jp_grid* g, uint8_t* h_idx, double* h_w);
-/* 1-D rule tables (master z-nodes, per-level weights) as compiled into the library */
+/* 1-D rule tables (master z-nodes, per-level weights BY MASTER INDEX, 0 for nodes a level does not use) as compiled
+ * into the library.  Genz-Keister: 1, 3, 9, 19, 35 points (nested) and the published 37-, 41-, 43-point members, which
+ * extend the 19-point rule; Kronrod-Patterson: 1 .. 63 points (nested).  (The rule family lives in the absent
+ * SparseQuadratureGrids package, reference test/runtests.jl:42.) */
 int jp_rule_info(int rule, int* levels, int* nmax, int* h_npts, double* h_nodes, double* h_weights);
+/* master indices of the nodes of 1-D level `level` (1-based) in generation order (h_index may be NULL); returns their
+ * number, or -1 for an unknown rule / level */
+int jp_rule_level_nodes(int rule, int level, int* h_index);
+/* highest 1-D level the build of this grid used: min(level, levels in the rule table).  A grid asked for a level past the
+ * table end is the combination formula over the capped index set, and this is how a caller finds out. */
+int jp_grid_level_cap(const jp_grid* g);
 
 /* ---------------------------------------------------------------------------------------------
  * Observations

@@ -62,7 +62,8 @@ SYMBOLS = [
     "jp_chol", "jp_try_chol", "jp_inv_upper", "jp_inv_chol", "jp_reduce_dimensions", "jp_reduce_dimensions_ldr", "jp_deduce_scale_dynamic",
     "jp_ctx_create", "jp_ctx_destroy", "jp_ctx_set_stream", "jp_ctx_sync", "jp_ctx_launch_count",
     "jp_ctx_last_kernel_ms",
-    "jp_grid_get", "jp_grid_size", "jp_grid_dim", "jp_grid_build_stats", "jp_grid_download", "jp_rule_info",
+    "jp_grid_get", "jp_grid_size", "jp_grid_dim", "jp_grid_build_stats", "jp_grid_download", "jp_rule_info", "jp_rule_level_nodes",
+    "jp_grid_level_cap",
     "jp_data_upload", "jp_data_adopt_device", "jp_data_free", "jp_glm_grad_hess", "jp_log_density_points", "jp_mode",
     "jp_posterior_create", "jp_posterior_free", "jp_posterior_size",
     "jp_fit", "jp_fit_local", "jp_fit_local_sum", "jp_fit_normalise", "jp_fit_local_stats", "jp_fit_normalise_gathered",

@@ -157,6 +157,18 @@ int jp_rule_info(int rule, int* levels, int* nmax, int* h_npts, double* h_nodes,
   return JP_OK;
 }
 
+int jp_rule_level_nodes(int rule, int level, int* h_index) {
+  if (rule != 0 && rule != 1) return -1;
+  JpRule R = jp_get_rule(rule);
+  if (level < 1 || level > R.levels) return -1;
+  const int n = R.npts[level - 1];
+  if (h_index)
+    for (int j = 0; j < n; ++j) h_index[j] = R.index[(size_t)(level - 1) * R.nmax + j];
+  return n;
+}
+
+int jp_grid_level_cap(const jp_grid* g) { return g ? std::min(g->level, jp_get_rule(g->rule).levels) : -1; }
+
 // ------------------------------------------------------------------------------------ data
 int jp_data_upload(jp_ctx* ctx, int family, long long N, int ncols, const double* h_obs, const double* h_hyper,
                    int n_hyper, jp_data** out) {

@@ -14,6 +14,7 @@
 #define JP_NUM_SMS_B200 148
 #define JP_MAX_D 64          // maximum number of unconstrained coordinates
 #define JP_MAX_HYPER 8
+#define JP_RULE_NMAX 128    // master 1-D nodes per rule family (Genz-Keister: 99, Kronrod-Patterson: 63)
 
 // ---------------------------------------------------------------------------- errors
 void jp_set_error(const char* fmt, ...);
@@ -268,6 +269,7 @@ struct JpRule {
   int levels, nmax;
   const int* npts;
   const double* nodes;
-  const double* weights;
+  const double* weights;         // [levels][nmax] by master index
+  const unsigned char* index;    // [levels][nmax]: master index of the pos-th node of a level
 };
 JpRule jp_get_rule(int rule);

@@ -42,7 +42,7 @@ struct JpFitLaunchParams {
   const double* xpts;          // non-null: explicit unconstrained points [M][d] instead of grid keys
 };
 
-__constant__ double c_fit_nodes[2][64];
+__constant__ double c_fit_nodes[2][JP_RULE_NMAX];
 
 __device__ __forceinline__ double jp_transform(int code, double x, double& lj) {
   if (code == JP_T_POSITIVE) {
@@ -306,9 +306,9 @@ int jp_upload_fit_consts(jp_posterior* post, const jp_fit_args* args) {
   if (!ctx->fit_nodes_uploaded) {
     for (int r = 0; r < 2; ++r) {
       JpRule R = jp_get_rule(r);
-      double nodes[64] = {0};
+      double nodes[JP_RULE_NMAX] = {0};
       for (int j = 0; j < R.nmax; ++j) nodes[j] = R.nodes[j];
-      JP_CUDA(cudaMemcpyToSymbol(c_fit_nodes, nodes, sizeof nodes, sizeof(double) * 64 * r));
+      JP_CUDA(cudaMemcpyToSymbol(c_fit_nodes, nodes, sizeof nodes, sizeof(double) * JP_RULE_NMAX * r));
     }
     ctx->fit_nodes_uploaded = true;
   }

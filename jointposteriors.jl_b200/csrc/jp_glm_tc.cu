@@ -69,6 +69,9 @@ int jp_glm_num_blocks(const jp_ctx* ctx, long long N);
 #ifndef TC_LDW
 #define TC_LDW 8                 // columns per tcgen05.ld of the epilogue (8 or 16)
 #endif
+#ifndef TC_EPI_V2
+#define TC_EPI_V2 0              // epilogue tile loop: 0 = two alternating coefficient sets (unrolled by two), 1 = one set
+#endif
 #ifndef TC_EARLY_COEF
 #define TC_EARLY_COEF 0          // ... and loads that tile's coefficients right away when the peek succeeds
 #endif
@@ -520,14 +523,14 @@ tc_node_prep_kernel(int d, int p, int kp, int seg, int rule, long long M, long l
   double* s_U = s_mu + d;             // d x p
   double* s_g = s_U + d * p;          // d
   double* s_H = s_g + d;              // d x d (full, symmetric)
-  double* s_z = s_H + d * d;          // 64
-  double* s_dl = s_z + 64;            // blockDim.x x d  (delta of each thread, strided by thread)
+  double* s_z = s_H + d * d;          // JP_RULE_NMAX
+  double* s_dl = s_z + JP_RULE_NMAX;  // blockDim.x x d  (delta of each thread, strided by thread)
   for (int k = threadIdx.x; k < d; k += blockDim.x) {
     s_mu[k] = mu[k];
     s_g[k] = sums[k];
   }
   for (int k = threadIdx.x; k < d * p; k += blockDim.x) s_U[k] = U[k];
-  for (int k = threadIdx.x; k < 64; k += blockDim.x) s_z[k] = znodes[k];
+  for (int k = threadIdx.x; k < JP_RULE_NMAX; k += blockDim.x) s_z[k] = znodes[k];
   for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
     int r = e % d, c = e / d;
     int rr = min(r, c), cc = max(r, c);
@@ -849,6 +852,9 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int j = 0; j < TC_COLS_PER_WARP / 2; ++j) accE[j] = accO[j] = 0ull;
     int buf = 0, cslot = 0, ntile = 0;
     uint32_t tphase = 0;
+#if TC_EPI_V2
+    uint32_t par = 0;               // parity of the current pass over the accumulator ring
+#endif
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * TC_COLS_PER_WARP);
     const uint32_t coef_addr = sC + (uint32_t)(q * 32 + lane) * 4u;   // this thread's observation: tile row = TMEM lane
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -908,6 +914,49 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         buf = nbuf;
         ++ntile;
       };
+#if TC_EPI_V2
+      // One tile body, one coefficient set: the next tile's coefficients are loaded into the same registers right
+      // after their last use (the loads land while the first chunk's squares are formed), and the accumulator ring is
+      // tracked by (buffer, parity of the ring pass) instead of a per-buffer phase mask.
+      {
+        float cc[NC];
+        mbar_wait(bar_tfull + 8u * buf, par);
+        tc_fence_after();
+        tmem_ld(va, lane_addr + (uint32_t)buf * TC_TMEM_STRIDE);
+        load_coef(cc);
+#pragma unroll 1
+        for (int t = t0; t < t1; ++t) {
+          const bool more = t + 1 < t1;
+          const bool wrap = buf + 1 == TC_NBUF;
+          const int nbuf = wrap ? 0 : buf + 1;
+          const uint32_t npar = wrap ? par ^ 1u : par;
+          const uint32_t taddr = lane_addr + (uint32_t)buf * TC_TMEM_STRIDE;
+          const bool ready = more && mbar_test_wait(bar_tfull + 8u * nbuf, npar);
+#pragma unroll
+          for (int c = 0; c < TC_COLS_PER_WARP / TC_LDW; ++c) {
+            uint32_t(&cur)[TC_LDW] = (c & 1) ? vb : va;
+            uint32_t(&nxt)[TC_LDW] = (c & 1) ? va : vb;
+            tmem_ld_wait(cur);
+            if (c + 1 < TC_COLS_PER_WARP / TC_LDW) {
+              tmem_ld(nxt, taddr + (uint32_t)(TC_LDW * (c + 1)));
+            } else {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_tempty + 8u * buf);
+              if (more) {
+                if (!ready) mbar_wait(bar_tfull + 8u * nbuf, npar);
+                tc_fence_after();
+                tmem_ld(nxt, lane_addr + (uint32_t)nbuf * TC_TMEM_STRIDE);
+              }
+            }
+            tc_accumulate<NC, MODE, TC_LDW>(cur, cc, accE + c * (TC_LDW / 2), accO + c * (TC_LDW / 2));
+          }
+          if (more) load_coef(cc);
+          buf = nbuf;
+          par = npar;
+        }
+      }
+#else
       int t = t0;
       const bool odd = ((t1 - t0) & 1) != 0;
       if (warp == 2 && lane == 0) TC_STAMP(3, ntile);
@@ -925,6 +974,7 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tile_step(t, ca, cb);
         tile_step(t + 1, cb, ca);
       }
+#endif
       // flush the item: sum over the 32 observation lanes by transpose-reduce, over the 4 lane quarters in
       // shared memory (FP64), one (even, odd) partial per (chunk, pair)
       {
@@ -1269,7 +1319,7 @@ static int tc_node_prep(jp_posterior* post, const jp_fit_args* args) {
   TcPostState* ps = static_cast<TcPostState*>(post->tc_state);
   const int d = args->d, p = args->p;
   cudaStream_t st = ctx->stream;
-  size_t sm_node = (size_t)(d + d * p + d + d * d + 64 + 128 * d) * 8;
+  size_t sm_node = (size_t)(d + d * p + d + d * d + JP_RULE_NMAX + 128 * d) * 8;
   if (sm_node > 48 * 1024)
     JP_CUDA(cudaFuncSetAttribute(tc_node_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_node));
   tc_node_prep_kernel<<<(unsigned)((post->M + 127) / 128), 128, sm_node, st>>>(

@@ -21,15 +21,17 @@
 
 JpRule jp_get_rule(int rule) {
   if (rule == JP_RULE_KRONROD_PATTERSON)
-    return JpRule{JP_KP_LEVELS, JP_KP_NMAX, jp_kp_npts, jp_kp_znodes, &jp_kp_weights[0][0]};
-  return JpRule{JP_GK_LEVELS, JP_GK_NMAX, jp_gk_npts, jp_gk_nodes, &jp_gk_weights[0][0]};
+    return JpRule{JP_KP_LEVELS, JP_KP_NMAX, jp_kp_npts, jp_kp_znodes, &jp_kp_weights[0][0], &jp_kp_index[0][0]};
+  return JpRule{JP_GK_LEVELS, JP_GK_NMAX, jp_gk_npts, jp_gk_nodes, &jp_gk_weights[0][0], &jp_gk_index[0][0]};
 }
 
 // rule tables in constant memory: [rule][...]
-#define JP_RULE_NMAX 64
 #define JP_RULE_LMAX 8
+static_assert(JP_GK_NMAX <= JP_RULE_NMAX && JP_KP_NMAX <= JP_RULE_NMAX, "master node table too small");
+static_assert(JP_GK_LEVELS <= JP_RULE_LMAX && JP_KP_LEVELS <= JP_RULE_LMAX, "level table too small");
 __constant__ double c_rule_nodes[2][JP_RULE_NMAX];
-__constant__ double c_rule_weights[2][JP_RULE_LMAX][JP_RULE_NMAX];
+__constant__ double c_rule_weights[2][JP_RULE_LMAX][JP_RULE_NMAX];   // by master index
+__constant__ unsigned char c_rule_index[2][JP_RULE_LMAX][JP_RULE_NMAX];   // position in a level -> master index
 __constant__ int c_rule_npts[2][JP_RULE_LMAX];
 
 static int upload_rules(jp_ctx* ctx) {
@@ -39,11 +41,16 @@ static int upload_rules(jp_ctx* ctx) {
     double nodes[JP_RULE_NMAX] = {0};
     double weights[JP_RULE_LMAX][JP_RULE_NMAX] = {{0}};
     int npts[JP_RULE_LMAX] = {0};
+    unsigned char index[JP_RULE_LMAX][JP_RULE_NMAX] = {{0}};
     for (int j = 0; j < R.nmax; ++j) nodes[j] = R.nodes[j];
     for (int l = 0; l < R.levels; ++l) {
       npts[l] = R.npts[l];
-      for (int j = 0; j < R.nmax; ++j) weights[l][j] = R.weights[(size_t)l * R.nmax + j];
+      for (int j = 0; j < R.nmax; ++j) {
+        weights[l][j] = R.weights[(size_t)l * R.nmax + j];
+        index[l][j] = R.index[(size_t)l * R.nmax + j];
+      }
     }
+    JP_CUDA(cudaMemcpyToSymbol(c_rule_index, index, sizeof index, sizeof(unsigned char) * JP_RULE_LMAX * JP_RULE_NMAX * r));
     JP_CUDA(cudaMemcpyToSymbol(c_rule_nodes, nodes, sizeof nodes, sizeof(double) * JP_RULE_NMAX * r));
     JP_CUDA(cudaMemcpyToSymbol(c_rule_weights, weights, sizeof weights, sizeof(double) * JP_RULE_LMAX * JP_RULE_NMAX * r));
     JP_CUDA(cudaMemcpyToSymbol(c_rule_npts, npts, sizeof npts, sizeof(int) * JP_RULE_LMAX * r));
@@ -182,7 +189,7 @@ __global__ void jp_expand_kernel(int d, int rule, unsigned long long n_mi, const
   uint8_t j[JP_MAX_D];
   for (int k = d - 1; k >= 0; --k) {
     unsigned np = (unsigned)c_rule_npts[rule][m[k] - 1];
-    j[k] = (uint8_t)(local % np);
+    j[k] = c_rule_index[rule][m[k] - 1][local % np];     // position in the level -> master index (the key byte)
     local /= np;
   }
   double w = coef[lo];

@@ -219,11 +219,23 @@ struct Rule {
   int levels, nmax;
   const int* npts;
   const double* nodes;    // z-space master nodes
-  const double* weights;  // [levels][nmax]
+  const double* weights;  // [levels][nmax], by MASTER index (0 for nodes a level does not use)
+  const unsigned char* index;   // [levels][nmax]: master index of the pos-th node of a level (a prefix for nested levels;
+                                // the 37/41/43-point Genz-Keister rules extend the 19-point rule, not the 35-point one)
 };
 static Rule get_rule(int rule_id) {
-  if (rule_id == 1) return Rule{JP_KP_LEVELS, JP_KP_NMAX, jp_kp_npts, jp_kp_znodes, &jp_kp_weights[0][0]};
-  return Rule{JP_GK_LEVELS, JP_GK_NMAX, jp_gk_npts, jp_gk_nodes, &jp_gk_weights[0][0]};
+  if (rule_id == 1) return Rule{JP_KP_LEVELS, JP_KP_NMAX, jp_kp_npts, jp_kp_znodes, &jp_kp_weights[0][0], &jp_kp_index[0][0]};
+  return Rule{JP_GK_LEVELS, JP_GK_NMAX, jp_gk_npts, jp_gk_nodes, &jp_gk_weights[0][0], &jp_gk_index[0][0]};
+}
+
+// master indices of the nodes of level `level` (1-based) in generation order; returns their number
+int orc_rule_level_nodes(int rule_id, int level, int* index) {
+  Rule r = get_rule(rule_id);
+  if (level < 1 || level > r.levels) return -1;
+  const int n = r.npts[level - 1];
+  if (index)
+    for (int j = 0; j < n; ++j) index[j] = r.index[(size_t)(level - 1) * r.nmax + j];
+  return n;
 }
 
 int orc_rule_info(int rule_id, int* levels, int* nmax, int* npts, double* nodes, double* weights) {
@@ -346,8 +358,9 @@ long long orc_smolyak_build(int rule_id, int d, int L, uint8_t* idx, double* w, 
     while (true) {
       double wt = S.coef[a];
       for (int k = 0; k < d; ++k) {
-        wt = wt * r.weights[(size_t)(mi[k] - 1) * r.nmax + j[k]];
-        key[k] = (uint8_t)j[k];
+        const uint8_t mj = r.index[(size_t)(mi[k] - 1) * r.nmax + j[k]];   // position in the level -> master index
+        wt = wt * r.weights[(size_t)(mi[k] - 1) * r.nmax + mj];
+        key[k] = mj;
       }
       auto it = acc.find(key);
       if (it == acc.end())

