@@ -232,17 +232,20 @@ int jp_fit_normalise_gathered(jp_posterior* post, const double* d_gathered, int 
  * O(N / world).  Sequence per fit (device buffers; collectives by the caller, on ctx's stream):
  *   jp_fit_prep_local(post, args, rank, world, d_out[L])          L = jp_fit_prep_len(d); asynchronous
  *   all_gather -> g[world][L]
- *   jp_fit_prep_gathered(post, args, g, world, rank, &n_rows)     sums combined in rank order, series length decided
- *                                                                 (one host sync), this rank's slice folded
- *   jp_fit_coef_rows(post, &d_coef, &row_stride, &n_loc)          all_gather IN PLACE row k = 0 .. n_rows-1:
- *                                                                 float d_coef[k*row_stride + r*n_loc .. + n_loc) from rank r
+ *   jp_fit_prep_gathered(post, args, g, world, rank, &n_rows)     sums and bounds combined in rank order ON THE DEVICE, this
+ *                                                                 rank's node operand queued, then the host reads the 22
+ *                                                                 combined bounds (the device is busy meanwhile), decides
+ *                                                                 the series length and folds this rank's slice
+ *   jp_fit_coef_slab(post, n_rows, &d_local, &d_all, &count)      ONE all_gather: every rank contributes `count` floats at
+ *                                                                 d_local (its first n_rows coefficient rows) and receives
+ *                                                                 float d_all[world][count]
  *   jp_fit_local_stats_prepared(post, args, d_out[2])             = jp_fit_local_stats without the prep
  * JP_ERR_UNSUPPORTED from the first two calls (not a GLM / bounds not met) means: use jp_fit_local_stats. */
 int jp_fit_prep_len(int d);
 int jp_fit_prep_local(jp_posterior* post, const jp_fit_args* args, int rank, int world, double* d_out);
 int jp_fit_prep_gathered(jp_posterior* post, const jp_fit_args* args, const double* d_gathered, int world, int rank,
                          int* n_rows);
-int jp_fit_coef_rows(jp_posterior* post, void** d_coef, long long* row_stride, long long* n_loc);
+int jp_fit_coef_slab(jp_posterior* post, int n_rows, void** d_local, void** d_all, long long* count);
 int jp_fit_local_stats_prepared(jp_posterior* post, const jp_fit_args* args, double* d_stats);
 
 /* results to the host (blocking).  h_theta: d x M_local row-major (coordinate k of node m at

@@ -67,7 +67,7 @@ SYMBOLS = [
     "jp_data_upload", "jp_data_adopt_device", "jp_data_free", "jp_glm_grad_hess", "jp_log_density_points", "jp_mode",
     "jp_posterior_create", "jp_posterior_free", "jp_posterior_size",
     "jp_fit", "jp_fit_local", "jp_fit_local_sum", "jp_fit_normalise", "jp_fit_local_stats", "jp_fit_normalise_gathered",
-    "jp_fit_prep_len", "jp_fit_prep_local", "jp_fit_prep_gathered", "jp_fit_coef_rows", "jp_fit_local_stats_prepared",
+    "jp_fit_prep_len", "jp_fit_prep_local", "jp_fit_prep_gathered", "jp_fit_coef_slab", "jp_fit_local_stats_prepared",
     "jp_get_theta", "jp_get_logdens", "jp_get_density", "jp_dev_theta", "jp_dev_density", "jp_fit_path_used",
     "jp_fit_diagnostics",
     "jp_marginal_coords", "jp_marginal_values", "jp_marginal_sorted", "jp_marginal_buffer", "jp_marginal_knots_from_sort",

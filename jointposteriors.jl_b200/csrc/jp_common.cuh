@@ -101,6 +101,12 @@ inline void jp_dfree(jp_ctx* ctx, const void* p) {
 }
 #define JP_SCRATCH_DOUBLES (1 << 16)
 #define JP_PINNED_DOUBLES (1 << 18)   // 2 MB: result vectors of up to 262 144 nodes are downloaded through it
+// Fixed sub-regions of the pinned staging buffer.  [0, JP_PINNED_CONSTS_END): the per-fit constants (mu d, U d x p, transform
+// codes d: at most 64 + 4096 + 32 doubles) staged by jp_upload_fit_consts; the bounds of the tensor-core path's a-priori gate
+// are read back behind them.  Host writes into the constants region wait for the event recorded after the last copy out of it.
+#define JP_PINNED_CONSTS_END 4352
+#define JP_PINNED_BOUNDS_OFF JP_PINNED_CONSTS_END
+static_assert(JP_MAX_D + JP_MAX_D * JP_MAX_D + JP_MAX_D / 2 + 1 <= JP_PINNED_CONSTS_END, "pinned constants region too small");
 
 struct jp_data {
   jp_ctx* ctx = nullptr;
@@ -257,7 +263,7 @@ int jp_fit_tc_prep_len(int d);
 int jp_fit_tc_prep_local(jp_posterior* post, const jp_fit_args* args, int rank, int world, double* d_out);
 int jp_fit_tc_prep_gathered(jp_posterior* post, const jp_fit_args* args, const double* d_gathered, int world, int rank,
                             int* n_rows);
-int jp_fit_tc_coef_rows(jp_posterior* post, float** d_coef, long long* row_stride, long long* n_loc);
+int jp_fit_tc_coef_slab(jp_posterior* post, int n_rows, float** d_local, float** d_all, long long* count);
 int jp_fit_tc_run_prepared(jp_posterior* post, const jp_fit_args* args);
 void jp_tc_data_free(jp_data* data);
 void jp_tc_post_free(jp_posterior* post);

@@ -544,11 +544,13 @@ int jp_fit_prep_gathered(jp_posterior* post, const jp_fit_args* args, const doub
   return jp_fit_tc_prep_gathered(post, args, d_gathered, world, rank, n_rows);
 }
 
-int jp_fit_coef_rows(jp_posterior* post, void** d_coef, long long* row_stride, long long* n_loc) {
-  JP_REQUIRE(post && d_coef, "jp_fit_coef_rows: null argument");
-  float* p = nullptr;
-  JP_TRY(jp_fit_tc_coef_rows(post, &p, row_stride, n_loc));
-  *d_coef = p;
+int jp_fit_coef_slab(jp_posterior* post, int n_rows, void** d_local, void** d_all, long long* count) {
+  JP_REQUIRE(post && d_local && d_all && count, "jp_fit_coef_slab: null argument");
+  JP_ENTER_CTX(post->ctx);
+  float *pl = nullptr, *pa = nullptr;
+  JP_TRY(jp_fit_tc_coef_slab(post, n_rows, &pl, &pa, count));
+  *d_local = pl;
+  *d_all = pa;
   return JP_OK;
 }
 

@@ -94,14 +94,18 @@ __constant__ double c_fold_grow[2][TC_NFOLD];
 struct TcDataState {
   int d = 0, kp = 0, ka = 0;   // observation operand: row length (floats) and 128-byte atoms per row
   int split = 0, kp_b = 0;     // split layout (see header) and the pair operand's row length
-  int world = 1;               // observation slices of the sharded prep (one per rank); N_pad = world * n_loc
+  int world = 1, rank = 0;     // observation slices of the sharded prep (one per rank) and the slice this rank prepares; N_pad = world * n_loc
   long long n_loc = 0;         // observations per slice, a multiple of the tile
   long long N = 0, N_pad = 0;
   float* d_xs = nullptr;       // [N_pad][kp]  (x_hi | x_lo | x_hi | 0)
-  float* d_coef = nullptr;     // [TC_COEF_ROWS][N_pad]: coefficient k of every observation, contiguous per 128-observation tile; last row t_i
+  float* d_coef = nullptr;     // [TC_COEF_ROWS][n_loc]: coefficient k of every observation of THIS rank's slice (all observations on
+                               // one GPU), contiguous per 128-observation tile; last row t_i
+  float* d_coef_all = nullptr; // world > 1: [world][nc_all][n_loc], the first nc_all rows of every rank's slab after ONE all_gather
+  int nc_all = 0;
   double* d_sums = nullptr;    // packed (g[d], upper H[d(d+1)/2], L_hat)
   double* d_work = nullptr;    // partials of the GLM sums
   double* d_bounds = nullptr;  // [TC_PREP_BLOCKS][TC_NBOUND]
+  double* d_comb = nullptr;    // [TC_NBOUND]: bounds combined over the ranks (sharded prep)
   int glm_blocks = 0;
   cudaEvent_t ev_bounds = nullptr;   // the bounds have reached the host (the fit waits on it, not on the whole stream)
   CUtensorMap tmA;
@@ -114,6 +118,7 @@ struct TcPostState {
   double* d_quad = nullptr;    // [M]
   double* d_part = nullptr;    // [part_chunks][P][2] per-chunk even / odd remainder sums
   int part_chunks = 0;
+  bool node_prep_queued = false;   // sharded prep: tc_node_prep already runs under the host's wait for the bounds
   CUtensorMap tmB;
 };
 
@@ -607,8 +612,10 @@ struct TcKernelParams {
   int tiles_per_chunk;
   int n_obs_tiles;
   long long P;            // local mirror pairs
-  const float* coef;      // [TC_NCMAX][N_pad]
-  long long N_pad;
+  const float* coef;      // coefficient row k of tile t: coef + slice * coef_slice_stride + k * coef_n_loc + (tile in slice) * 128,
+  long long coef_n_loc;   //   slice = t / tiles_per_slice (one GPU: a single slice = the slab itself)
+  long long coef_slice_stride;
+  int tiles_per_slice;
   double* part;           // [chunks][P][2]: even and odd part of the remainder sum of a pair
   long long* dbg;         // profiling builds, MODE 5: per-tile clock64 stamps of CTA 0 ([6][TC_DBG_TILES]), else null
 };
@@ -784,10 +791,12 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int a = 0; a < P.ka; ++a)
             tma_load_2d(sA + (uint32_t)stage * a_bytes + (uint32_t)a * TC_OBS_TILE * 128u, &tmA, bar_full + 8u * stage,
                         a * TC_KATOM, t * TC_OBS_TILE);
+          const int sl = t / P.tiles_per_slice;
+          const float* crow = P.coef + (size_t)sl * P.coef_slice_stride + (size_t)(t - sl * P.tiles_per_slice) * TC_OBS_TILE;
 #pragma unroll
           for (int k = 0; k < NC; ++k)
-            bulk_load_1d(sC + (uint32_t)cslot * c_bytes + (uint32_t)k * TC_OBS_TILE * 4u,
-                         P.coef + (size_t)k * P.N_pad + (size_t)t * TC_OBS_TILE, TC_OBS_TILE * 4u, bar_full + 8u * stage);
+            bulk_load_1d(sC + (uint32_t)cslot * c_bytes + (uint32_t)k * TC_OBS_TILE * 4u, crow + (size_t)k * P.coef_n_loc,
+                         TC_OBS_TILE * 4u, bar_full + 8u * stage);
         }
         ++ntile;
         if (++cslot == n_cslots) cslot = 0;
@@ -1106,8 +1115,8 @@ bool jp_fit_tc_supported(const jp_posterior* post, const jp_fit_args* args) { re
 void jp_tc_data_free(jp_data* data) {
   TcDataState* s = static_cast<TcDataState*>(data->tc_state);
   if (!s) return;
-  jp_dfree(data->ctx, s->d_xs); jp_dfree(data->ctx, s->d_coef); jp_dfree(data->ctx, s->d_sums);
-  jp_dfree(data->ctx, s->d_work); jp_dfree(data->ctx, s->d_bounds);
+  jp_dfree(data->ctx, s->d_xs); jp_dfree(data->ctx, s->d_coef); jp_dfree(data->ctx, s->d_coef_all); jp_dfree(data->ctx, s->d_sums);
+  jp_dfree(data->ctx, s->d_work); jp_dfree(data->ctx, s->d_bounds); jp_dfree(data->ctx, s->d_comb);
   if (s->ev_bounds) cudaEventDestroy(s->ev_bounds);
   delete s;
   data->tc_state = nullptr;
@@ -1120,8 +1129,11 @@ void jp_tc_post_free(jp_posterior* post) {
   post->tc_state = nullptr;
 }
 
-static int ensure_data_state(jp_ctx* ctx, jp_data* data, int d, int world) {
-  if (data->tc_state && static_cast<TcDataState*>(data->tc_state)->world != world) jp_tc_data_free(data);   // re-sliced
+static int ensure_data_state(jp_ctx* ctx, jp_data* data, int d, int world, int rank) {
+  if (data->tc_state) {
+    const TcDataState* o = static_cast<const TcDataState*>(data->tc_state);
+    if (o->world != world || o->rank != rank) jp_tc_data_free(data);   // re-sliced
+  }
   if (data->tc_state) return JP_OK;
   TcDataState* s = new TcDataState();
   data->tc_state = s;
@@ -1134,13 +1146,15 @@ static int ensure_data_state(jp_ctx* ctx, jp_data* data, int d, int world) {
   s->N = data->N;
   // observation slices of the sharded prep: world equal slices of whole tiles (the last ones may be short or empty)
   s->world = world;
+  s->rank = rank;
   const long long tiles = (data->N + TC_OBS_TILE - 1) / TC_OBS_TILE;
   s->n_loc = ((tiles + world - 1) / world) * TC_OBS_TILE;
   s->N_pad = s->n_loc * world;
   const int nE = d + d * (d + 1) / 2;
   s->glm_blocks = jp_glm_num_blocks(ctx, data->N);
   JP_CUDA(jp_dmalloc(ctx, &s->d_xs, (size_t)s->N_pad * s->kp * sizeof(float)));
-  JP_CUDA(jp_dmalloc(ctx, &s->d_coef, (size_t)s->N_pad * TC_COEF_ROWS * sizeof(float)));
+  JP_CUDA(jp_dmalloc(ctx, &s->d_coef, (size_t)s->n_loc * TC_COEF_ROWS * sizeof(float)));
+  JP_CUDA(jp_dmalloc(ctx, &s->d_comb, (size_t)TC_NBOUND * 8));
   JP_CUDA(jp_dmalloc(ctx, &s->d_sums, (size_t)(nE + 1) * 8));
   JP_CUDA(jp_dmalloc(ctx, &s->d_work, (size_t)s->glm_blocks * (nE + 1) * 8));
   JP_CUDA(jp_dmalloc(ctx, &s->d_bounds, (size_t)TC_PREP_BLOCKS * TC_NBOUND * 8));
@@ -1248,13 +1262,13 @@ static int launch_tc(jp_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB
 // ---- the fit in pieces.  One GPU: setup, prep of all observations, decide, fold, run.  Several ranks (node-sharded
 // posterior, observations replicated): the O(N) FP64 prep is SHARDED BY OBSERVATION -- rank r prepares slice r, the
 // ranks exchange (sums, bounds) and then the coefficient rows -- so that the replicated work per rank stays O(N / world).
-static int tc_setup(jp_posterior* post, const jp_fit_args* args, int world) {
+static int tc_setup(jp_posterior* post, const jp_fit_args* args, int world, int rank) {
   jp_ctx* ctx = post->ctx;
   jp_data* data = const_cast<jp_data*>(post->data);
   if (!tc_static_ok(post, args)) return JP_ERR_UNSUPPORTED;
   JP_REQUIRE(post->grid->M % 2 == 1, "tensor-core path: the grid is not in mirror order (even node count %lld)", post->grid->M);
   JP_TRY(upload_tables(ctx));
-  JP_TRY(ensure_data_state(ctx, data, args->d, world));
+  JP_TRY(ensure_data_state(ctx, data, args->d, world, rank));
   TcDataState* ds = static_cast<TcDataState*>(data->tc_state);
   JP_REQUIRE(ds->d == args->d, "tensor-core path: data was prepared for d=%d", ds->d);
   JP_TRY(ensure_post_state(post, ds->kp_b));
@@ -1277,7 +1291,7 @@ static int tc_prep_slice(jp_posterior* post, const jp_fit_args* args, int rank, 
     JP_CUDA(cudaFuncSetAttribute(tc_obs_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_obs));
   tc_obs_prep_kernel<<<TC_PREP_BLOCKS, TC_PREP_THREADS, sm_obs, ctx->stream>>>(
       data->family, d, p, data->ncols, o1 - o0, ds->n_loc, data->d_obs + (size_t)o0 * data->ncols, post->d_mu, post->d_U, z_ref,
-      z_max, ds->d_coef + (size_t)rank * ds->n_loc, ds->N_pad, ds->d_bounds);
+      z_max, ds->d_coef, ds->n_loc, ds->d_bounds);
   JP_CHECK_LAUNCH(ctx);
   return JP_OK;
 }
@@ -1301,11 +1315,11 @@ static int tc_decide(jp_posterior* post, double* b, int* NC_out, int* fold_out) 
   return JP_OK;
 }
 
-static int tc_fold_slice(jp_posterior* post, int NC, int rank) {
+static int tc_fold_slice(jp_posterior* post, int NC) {
   jp_ctx* ctx = post->ctx;
   TcDataState* ds = static_cast<TcDataState*>(post->data->tc_state);
   const double z_max = std::sqrt(post->grid->zmax2), z_ref = std::min(z_max, 6.0);
-  tc_fold_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(NC, ds->n_loc, ds->N_pad, z_ref, ds->d_coef + (size_t)rank * ds->n_loc);
+  tc_fold_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(NC, ds->n_loc, ds->n_loc, z_ref, ds->d_coef);
   JP_CHECK_LAUNCH(ctx);
   return JP_OK;
 }
@@ -1378,8 +1392,17 @@ static int tc_run_kernel(jp_posterior* post, const jp_fit_args* args, int NC) {
     ps->part_chunks = kp.chunks;
   }
   kp.P = ps->P;
-  kp.coef = ds->d_coef;
-  kp.N_pad = ds->N_pad;
+  if (ds->world > 1) {
+    JP_REQUIRE(ds->d_coef_all && ds->nc_all == NC, "tensor-core path: the coefficient rows of the other ranks have not been gathered "
+               "(jp_fit_coef_slab + one all_gather, then jp_fit_local_stats_prepared)");
+    kp.coef = ds->d_coef_all;
+    kp.coef_slice_stride = (long long)NC * ds->n_loc;
+  } else {
+    kp.coef = ds->d_coef;
+    kp.coef_slice_stride = 0;
+  }
+  kp.coef_n_loc = ds->n_loc;
+  kp.tiles_per_slice = (int)(ds->n_loc / TC_OBS_TILE);
   kp.part = ps->d_part;
   kp.dbg = nullptr;
   int stc;
@@ -1398,7 +1421,9 @@ static int tc_run_kernel(jp_posterior* post, const jp_fit_args* args, int NC) {
 }
 
 static int tc_run(jp_posterior* post, const jp_fit_args* args, int NC) {
-  JP_TRY(tc_node_prep(post, args));
+  TcPostState* ps = static_cast<TcPostState*>(post->tc_state);
+  if (!ps->node_prep_queued) JP_TRY(tc_node_prep(post, args));
+  ps->node_prep_queued = false;
   return tc_run_kernel(post, args, NC);
 }
 
@@ -1414,10 +1439,20 @@ static void tc_reduce_block_bounds(const double* hb, double* b) {
 
 int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   jp_ctx* ctx = post->ctx;
-  JP_TRY(tc_setup(post, args, 1));
+  JP_TRY(tc_setup(post, args, 1, 0));
   TcDataState* ds = static_cast<TcDataState*>(post->data->tc_state);
   JP_TRY(tc_prep_slice(post, args, 0, ds->d_sums));
-  double* hb = ctx->h_pinned + 4096;   // away from the constants staged by jp_upload_fit_consts
+  // diagnostic only (bench.py attribution of the host round trip): JP_TC_ASSUME=NC,fold skips the bounds read-back
+  static const char* assume = getenv("JP_TC_ASSUME");
+  if (assume) {
+    int nc = 4, fd = 1;
+    sscanf(assume, "%d,%d", &nc, &fd);
+    post->tc_bounds[3] = nc; post->tc_bounds[5] = fd;
+    JP_TRY(tc_node_prep(post, args));
+    if (fd) JP_TRY(tc_fold_slice(post, nc));
+    return tc_run_kernel(post, args, nc);
+  }
+  double* hb = ctx->h_pinned + JP_PINNED_BOUNDS_OFF;   // away from the constants staged by jp_upload_fit_consts
   JP_CUDA(cudaMemcpyAsync(hb, ds->d_bounds, (size_t)TC_PREP_BLOCKS * TC_NBOUND * 8, cudaMemcpyDeviceToHost, ctx->stream));
   JP_CUDA(cudaEventRecord(ds->ev_bounds, ctx->stream));
   JP_TRY(tc_node_prep(post, args));                     // queued behind the copy: runs while the host waits and decides
@@ -1426,7 +1461,7 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
   tc_reduce_block_bounds(hb, b);
   int NC = 0, fold = 0;
   JP_TRY(tc_decide(post, b, &NC, &fold));
-  if (fold) JP_TRY(tc_fold_slice(post, NC, 0));
+  if (fold) JP_TRY(tc_fold_slice(post, NC));
   return tc_run_kernel(post, args, NC);
 }
 
@@ -1448,7 +1483,7 @@ __global__ void tc_bounds_reduce_kernel(const double* __restrict__ blocks, doubl
 // phase 1: this rank's observation slice -> d_out[L] = (local g, H, L_hat | local bounds); asynchronous
 int jp_fit_tc_prep_local(jp_posterior* post, const jp_fit_args* args, int rank, int world, double* d_out) {
   JP_REQUIRE(world >= 1 && rank >= 0 && rank < world && d_out, "jp_fit_prep_local: bad rank / world / output");
-  JP_TRY(tc_setup(post, args, world));
+  JP_TRY(tc_setup(post, args, world, rank));
   TcDataState* ds = static_cast<TcDataState*>(post->data->tc_state);
   const int nE1 = args->d + args->d * (args->d + 1) / 2 + 1;
   JP_TRY(tc_prep_slice(post, args, rank, d_out));
@@ -1457,45 +1492,65 @@ int jp_fit_tc_prep_local(jp_posterior* post, const jp_fit_args* args, int rank, 
   return JP_OK;
 }
 
-// phase 2: the gathered [world][L] buffer -> global sums (rank order, identical on every rank), the series length, the
-// fold of this rank's slice.  Blocks until the gathered buffer is on the host.  *n_rows = coefficient rows to exchange.
+// gathered [world][L] -> global sums (g, H, L_hat) and bounds, combined in RANK ORDER on the device: every rank runs the same
+// kernel on the same gathered bits, so all ranks hold identical sums -- and no host arithmetic sits between the collectives
+__global__ void tc_combine_gathered_kernel(const double* __restrict__ g, int world, int L, int nE1, double* __restrict__ sums,
+                                           double* __restrict__ bounds) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < L; e += gridDim.x * blockDim.x) {
+    double v = 0;
+    if (e == nE1) {
+      for (int r = 0; r < world; ++r) v = fmax(v, g[(size_t)r * L + e]);     // [0] of the bounds is a maximum
+    } else {
+      for (int r = 0; r < world; ++r) v += g[(size_t)r * L + e];
+    }
+    if (e < nE1) sums[e] = v; else bounds[e - nE1] = v;
+  }
+}
+
+// phase 2: the gathered [world][L] buffer -> global sums on the device, the series length, the fold of this rank's slice.
+// The host needs the 22 combined bounds to pick the series length (it selects the kernel instantiation and the size of the
+// one collective that follows); the node operand / theta / quadratic part of this rank's node block (tc_node_prep, ~25 us)
+// is queued BEFORE the host waits, so the device works through the round trip.  *n_rows = coefficient rows to exchange.
 int jp_fit_tc_prep_gathered(jp_posterior* post, const jp_fit_args* args, const double* d_gathered, int world, int rank,
                             int* n_rows) {
   jp_ctx* ctx = post->ctx;
   TcDataState* ds = static_cast<TcDataState*>(post->data->tc_state);
-  JP_REQUIRE(ds && ds->world == world && d_gathered && n_rows, "jp_fit_prep_gathered: call jp_fit_prep_local first");
+  TcPostState* ps = static_cast<TcPostState*>(post->tc_state);
+  JP_REQUIRE(ds && ps && ds->world == world && ds->rank == rank && d_gathered && n_rows, "jp_fit_prep_gathered: call jp_fit_prep_local first");
   const int nE1 = args->d + args->d * (args->d + 1) / 2 + 1, L = nE1 + TC_NBOUND;
-  JP_REQUIRE((size_t)world * L + 4096 + L <= JP_PINNED_DOUBLES, "jp_fit_prep_gathered: world=%d too large", world);
-  double* hg = ctx->h_pinned + 4096;
-  JP_CUDA(cudaMemcpyAsync(hg, d_gathered, (size_t)world * L * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  JP_CUDA(cudaStreamSynchronize(ctx->stream));
-  double* hs = hg + (size_t)world * L;      // combined sums, staged for the upload
-  for (int e = 0; e < nE1; ++e) {
-    double v = 0;
-    for (int r = 0; r < world; ++r) v += hg[(size_t)r * L + e];
-    hs[e] = v;
-  }
+  tc_combine_gathered_kernel<<<(L + 127) / 128, 128, 0, ctx->stream>>>(d_gathered, world, L, nE1, ds->d_sums, ds->d_comb);
+  JP_CHECK_LAUNCH(ctx);
+  double* hb = ctx->h_pinned + JP_PINNED_BOUNDS_OFF;
+  JP_CUDA(cudaMemcpyAsync(hb, ds->d_comb, (size_t)TC_NBOUND * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  JP_CUDA(cudaEventRecord(ds->ev_bounds, ctx->stream));
+  JP_TRY(tc_node_prep(post, args));
+  ps->node_prep_queued = true;
+  JP_CUDA(cudaEventSynchronize(ds->ev_bounds));
   double b[TC_NBOUND];
-  for (int j = 0; j < TC_NBOUND; ++j) {
-    double v = 0;
-    for (int r = 0; r < world; ++r) v = (j == 0) ? std::max(v, hg[(size_t)r * L + nE1 + j]) : v + hg[(size_t)r * L + nE1 + j];
-    b[j] = v;
-  }
-  JP_CUDA(cudaMemcpyAsync(ds->d_sums, hs, (size_t)nE1 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  for (int j = 0; j < TC_NBOUND; ++j) b[j] = hb[j];
   int NC = 0, fold = 0;
   JP_TRY(tc_decide(post, b, &NC, &fold));
-  if (fold) JP_TRY(tc_fold_slice(post, NC, rank));
+  if (fold) JP_TRY(tc_fold_slice(post, NC));
   *n_rows = NC;
   return JP_OK;
 }
 
-// the coefficient array for the exchange: row k of rank r's slice is d_coef + k * row_stride + r * n_loc, n_loc floats
-int jp_fit_tc_coef_rows(jp_posterior* post, float** d_coef, long long* row_stride, long long* n_loc) {
+// The exchange of the coefficient rows is ONE all_gather: this rank contributes the first n_rows rows of its slab (contiguous,
+// n_rows x n_loc floats at *d_local) and receives everybody's into *d_all = [world][n_rows][n_loc].
+int jp_fit_tc_coef_slab(jp_posterior* post, int n_rows, float** d_local, float** d_all, long long* count) {
   TcDataState* ds = post && post->data ? static_cast<TcDataState*>(post->data->tc_state) : nullptr;
-  JP_REQUIRE(ds && d_coef && row_stride && n_loc, "jp_fit_coef_rows: call jp_fit_prep_local first");
-  *d_coef = ds->d_coef;
-  *row_stride = ds->N_pad;
-  *n_loc = ds->n_loc;
+  JP_REQUIRE(ds && d_local && d_all && count, "jp_fit_coef_slab: call jp_fit_prep_local first");
+  JP_REQUIRE(n_rows >= 1 && n_rows <= TC_NCMAX, "jp_fit_coef_slab: n_rows=%d out of range", n_rows);
+  if (ds->nc_all != n_rows || !ds->d_coef_all) {
+    jp_dfree(post->ctx, ds->d_coef_all);
+    ds->d_coef_all = nullptr;
+    ds->nc_all = 0;
+    JP_CUDA(jp_dmalloc(post->ctx, &ds->d_coef_all, (size_t)ds->world * n_rows * ds->n_loc * sizeof(float)));
+    ds->nc_all = n_rows;
+  }
+  *d_local = ds->d_coef;
+  *d_all = ds->d_coef_all;
+  *count = (long long)n_rows * ds->n_loc;
   return JP_OK;
 }
 

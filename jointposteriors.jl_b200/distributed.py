@@ -8,7 +8,7 @@ contiguous block of merged grid nodes and the ranks exchange only:
 
     fit        all_gather(local max m_r, local sum s_r relative to m_r)             one collective
                tensor-core GLM path: its O(N) FP64 prep is sharded by OBSERVATION instead of being replicated --
-               all_gather(slice sums + bounds), then all_gather of the coefficient rows in place (fit_sharded)
+               all_gather(slice sums + bounds), then ONE all_gather of the chosen coefficient rows (fit_sharded)
     marginals  all_gather(K x 4 moments/extrema)  ;  all_gather(K x 98 x 6 knot candidates)
 
 Between the collectives the host does no arithmetic: the gathered buffers go straight back into the
@@ -169,11 +169,11 @@ class CudaLocal:
     # ---- observation-sharded prep of the tensor-core path (jp_fit_prep_*, include/jpcuda.h)
     def prep_worthwhile(self):
         """The sharded prep trades O(N (1 - 1/world)) replicated FP64 work (~0.3 ns per observation) for two more
-        collectives plus one all_gather per coefficient row (~0.25 ms at 2 GPUs): worth it from a few million
-        observations (BASELINE cfg5: 3.7 ms of prep per rank), a loss at cfg3 sizes.  JP_SHARDED_PREP_MIN_MB overrides
-        the record-size threshold."""
+        collectives (slice sums + bounds, then ONE all_gather of the chosen coefficient rows), the host's read of the bounds
+        hidden under this rank's node prep: on whenever there are several ranks.  JP_SHARDED_PREP_MIN_MB (default 0) sets a
+        record-size threshold below which the prep stays replicated (A/B aid)."""
         import os
-        return self.jp.data.nbytes >= float(os.environ.get("JP_SHARDED_PREP_MIN_MB", "512")) * 1e6
+        return self.jp.data.nbytes >= float(os.environ.get("JP_SHARDED_PREP_MIN_MB", "0")) * 1e6
 
     def fit_prep_local(self, rank, world):
         """Slice sums and bounds of this rank's observation slice [L], or None when the posterior is not on the
@@ -198,11 +198,13 @@ class CudaLocal:
         check(st)
         return n_rows.value
 
-    def fit_coef_rows(self, n_rows):
-        """The first n_rows coefficient rows as torch views [n_rows][world * n_loc] of the library's buffer (float32)."""
-        ptr, stride, n_loc = C.c_void_p(), C.c_longlong(), C.c_longlong()
-        check(lib().jp_fit_coef_rows(self.jp.handle, C.byref(ptr), C.byref(stride), C.byref(n_loc)))
-        return _device_view_f32(self.torch, ptr.value, n_rows * stride.value, self.dev).view(n_rows, stride.value), n_loc.value
+    def fit_coef_slab(self, n_rows, world):
+        """(mine [count], everybody's [world, count]) as float32 torch views of the library's buffers: this rank's first
+        n_rows coefficient rows and the destination of the one all_gather that exchanges them."""
+        pl, pa, cnt = C.c_void_p(), C.c_void_p(), C.c_longlong()
+        check(lib().jp_fit_coef_slab(self.jp.handle, C.c_int(n_rows), C.byref(pl), C.byref(pa), C.byref(cnt)))
+        mine = _device_view_f32(self.torch, pl.value, cnt.value, self.dev)
+        return mine, _device_view_f32(self.torch, pa.value, world * cnt.value, self.dev).view(world, cnt.value)
 
     def fit_local_stats_prepared(self):
         out = self._buf(2)
@@ -275,13 +277,13 @@ def _rank(group):
     return dist.get_rank(group)
 
 
-def fit_sharded(local, group=None, gather=None, rank=None, world=None, gather_rows=None):
+def fit_sharded(local, group=None, gather=None, rank=None, world=None, gather_slab=None):
     """Normalise a node-sharded fit.  `gather(t, group)` defaults to torch.distributed all_gather; tests emulating
     several ranks inject their own.  Every combine runs in rank order on every rank: bit-identical scalars.
 
     When the local phase offers it (tensor-core GLM path), the O(N) prep is sharded by observation first: one tiny
-    all_gather of (slice sums, bounds), then the chosen coefficient rows are all-gathered in place, row by row, inside
-    the library's buffer (`gather_rows(rows, n_loc, rank, group)`, default: torch all_gather_into_tensor on views)."""
+    all_gather of (slice sums, bounds), then ONE all_gather of the chosen coefficient rows into the library's buffer
+    (`gather_slab(mine, everybody, group)`, default: torch all_gather_into_tensor on the views)."""
     gather = gather or _all_gather
     r = _rank(group) if rank is None else rank
     if world is None:
@@ -294,8 +296,8 @@ def fit_sharded(local, group=None, gather=None, rank=None, world=None, gather_ro
         if mine is not None:
             n_rows = local.fit_prep_gathered(gather(mine, group), r)
             if n_rows is not None:
-                rows, n_loc = local.fit_coef_rows(n_rows)
-                (gather_rows or _all_gather_rows_inplace)(rows, n_loc, r, group)
+                slab, everybody = local.fit_coef_slab(n_rows, world)
+                (gather_slab or _all_gather_slab)(slab, everybody, group)
                 stats = local.fit_local_stats_prepared()
     local.last_prep = "sharded" if stats is not None else "replicated"      # which protocol this fit took (diagnostics)
     if stats is None:
@@ -305,12 +307,10 @@ def fit_sharded(local, group=None, gather=None, rank=None, world=None, gather_ro
     return g
 
 
-def _all_gather_rows_inplace(rows, n_loc, rank, group):
-    """rows: [n_rows][world * n_loc]; rank r owns columns [r * n_loc, (r + 1) * n_loc) of every row."""
+def _all_gather_slab(mine, everybody, group):
+    """mine: [count] (this rank's coefficient rows), everybody: [world, count]."""
     import torch.distributed as dist
-    for k in range(rows.shape[0]):
-        row = rows[k]
-        dist.all_gather_into_tensor(row, row[rank * n_loc:(rank + 1) * n_loc], group=group)
+    dist.all_gather_into_tensor(everybody.view(-1), mine, group=group)
 
 
 def marginals_sharded(local, coords, group=None, gather=None):

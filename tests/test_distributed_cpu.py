@@ -83,7 +83,8 @@ class NumpyPrepLocal(NumpyLocal):
         super().__init__(*args)
         self.n_obs, self.world = n_obs, world
         self.n_loc = -(-n_obs // world)
-        self.rows = self.t.zeros((2, world * self.n_loc), dtype=self.t.float32)
+        self.rows = self.t.zeros((2, self.n_loc), dtype=self.t.float32)               # this rank's slab: [rows][n_loc]
+        self.all_rows = self.t.zeros((world, 2 * self.n_loc), dtype=self.t.float32)   # [world][rows * n_loc]
         self.a0 = self.a.copy()
 
     def prep_worthwhile(self):
@@ -92,8 +93,8 @@ class NumpyPrepLocal(NumpyLocal):
     def fit_prep_local(self, rank, world):
         lo, hi = min(self.n_obs, rank * self.n_loc), min(self.n_obs, (rank + 1) * self.n_loc)
         i = np.arange(lo, hi, dtype=np.float64)
-        self.rows[0, lo:hi] = self.t.tensor(2 * i + 1, dtype=self.t.float32)
-        self.rows[1, lo:hi] = 1.0
+        self.rows[0, :hi - lo] = self.t.tensor(2 * i + 1, dtype=self.t.float32)
+        self.rows[1, :hi - lo] = 1.0
         return self._t([i.sum(), float(hi - lo), 0.0])
 
     def fit_prep_gathered(self, g, rank):
@@ -101,12 +102,13 @@ class NumpyPrepLocal(NumpyLocal):
         assert int(g[:, 1].sum()) == self.n_obs
         return 2
 
-    def fit_coef_rows(self, n_rows):
-        return self.rows[:n_rows], self.n_loc
+    def fit_coef_slab(self, n_rows, world):
+        assert n_rows == 2 and world == self.world
+        return self.rows.view(-1), self.all_rows
 
     def fit_local_stats_prepared(self):
-        r = self.rows.numpy().astype(np.float64)
-        shift = 1e-6 * self.total + 1e-9 * float(r[0, :self.n_obs].sum()) + float(r[1, :self.n_obs].sum()) - self.n_obs
+        r = self.all_rows.numpy().astype(np.float64).reshape(self.world, 2, self.n_loc)
+        shift = 1e-6 * self.total + 1e-9 * float(r[:, 0].sum()) + float(r[:, 1].sum()) - self.n_obs
         self.a = self.a0 + shift
         return self.fit_local_stats()
 
@@ -126,7 +128,7 @@ def _worker(rank, world, port, a, w, values, q):
     loc = NumpyLocal(a[b:e], w[b:e], [v[b:e] for v in values], b, D)
     D.fit_sharded(loc)
     mu, sg, vn, wn = D.marginals_sharded(loc, list(range(len(values))))
-    # the fit again through the observation-sharded prep protocol (extra all_gather + in-place row gathers): a constant
+    # the fit again through the observation-sharded prep protocol (extra all_gather + ONE gather of the rows): a constant
     # shift of every log-density leaves the normalised weights unchanged only if all ranks derived the SAME shift
     ploc = NumpyPrepLocal(a[b:e], w[b:e], [v[b:e] for v in values], b, D, n_obs=1003, world=world)
     D.fit_sharded(ploc)

@@ -686,7 +686,7 @@ def test_tc_sharded_equals_unsharded(jp, O, gpu_ctx):
 
 @pytest.mark.parametrize("world,N,level", [(2, 60000, 4), (3, 30001, 4), (5, 50000, 4)], ids=["w2", "w3-ragged", "w5"])
 def test_tc_observation_sharded_prep(jp, O, gpu_ctx, world, N, level):
-    """Node-sharded fit whose O(N) prep is sharded by observation (jp_fit_prep_local / _prep_gathered / _coef_rows /
+    """Node-sharded fit whose O(N) prep is sharded by observation (jp_fit_prep_local / _prep_gathered / _coef_slab /
     _local_stats_prepared), `world` ranks emulated on one GPU -- every rank with its own copy of the records and its own
     library state, collectives emulated by copies -- against the unsharded tensor-core fit and the oracle."""
     import torch
@@ -706,13 +706,12 @@ def test_tc_observation_sharded_prep(jp, O, gpu_ctx, world, N, level):
     g = torch.stack([l.fit_prep_local(r, world) for r, l in enumerate(locs)]).contiguous()
     n_rows = [l.fit_prep_gathered(g, r) for r, l in enumerate(locs)]
     assert len(set(n_rows)) == 1 and n_rows[0] in (4, 6, 8, 10, 12)
-    views = [l.fit_coef_rows(n_rows[0]) for l in locs]
-    n_loc = views[0][1]
-    assert n_loc % 128 == 0 and views[0][0].shape[1] == world * n_loc
-    for src in range(world):                      # the in-place all_gather of the coefficient rows
+    views = [l.fit_coef_slab(n_rows[0], world) for l in locs]
+    count = views[0][0].numel()
+    assert count % (128 * n_rows[0]) == 0 and tuple(views[0][1].shape) == (world, count)
+    for src in range(world):                      # the ONE all_gather of the coefficient rows, emulated by copies
         for dst in range(world):
-            if dst != src:
-                views[dst][0][:, src * n_loc:(src + 1) * n_loc] = views[src][0][:, src * n_loc:(src + 1) * n_loc]
+            views[dst][1][src].copy_(views[src][0])
     torch.cuda.synchronize()
     gs = torch.stack([l.fit_local_stats_prepared() for l in locs]).contiguous()
     for r, l in enumerate(locs):
