@@ -128,6 +128,7 @@ def run_reference(args):
         return
     from oracle import oracle as O
     O.build()
+    cpu_flags = O.use_fast()     # the CPU path is timed from a -O3 -march=native build (compiled on this machine)
     jp = entry.load_package()
     wl = make_workload(jp, args.workload, args.gpus)
     data = wl["data"]
@@ -165,8 +166,8 @@ def run_reference(args):
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     val = m_step * N / (ms * 1e-3)
-    sample = "first %d of %d merged grid nodes x all %d observations per step (fit + %d coordinate marginals), %d threads" % (
-        m_step, len(w), N, d, cores)
+    sample = "first %d of %d merged grid nodes x all %d observations per step (fit + %d coordinate marginals), %d threads, oracle built %s" % (
+        m_step, len(w), N, d, cores, cpu_flags)
     out = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
                higher_is_better=True, scaling="weak" if args.workload == "cfg3" else "strong", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
                config=dict(workload=wl["desc"], sample=sample),
@@ -179,6 +180,7 @@ def run_reference(args):
 def cpu_baseline(wl, post_inputs, budget_s=12.0):
     from oracle import oracle as O
     O.build()
+    cpu_flags = O.use_fast()     # -O3 -march=native, compiled on this machine; the parity tests keep -O2 -ffp-contract=off
     data = wl["data"]
     obs, hyper = data.records()
     d, fam = wl["d"], data.family
@@ -200,9 +202,169 @@ def cpu_baseline(wl, post_inputs, budget_s=12.0):
     O.eval_grid(0, fam, code, idx, w, x, U, neg_min, obs, hyper, 0, m1, threads=1, want_theta=False)
     dt1 = time.perf_counter() - t1
     return dict(value=m * N / dt, unit=UNIT, cores=cores, kind="port",
-                sample="oracle eval_grid on the first %d of %d merged nodes x all %d observations, %d threads (%.1f s); "
-                       "1 thread (the reference is single-threaded): %.4g pairs/s on %d nodes" % (m, len(w), N, cores, dt, m1 * N / dt1, m1),
-                single_thread_value=m1 * N / dt1)
+                sample="oracle (%s) eval_grid on the first %d of %d merged nodes x all %d observations, %d threads (%.1f s); "
+                       "1 thread (the reference is single-threaded): %.4g pairs/s on %d nodes" % (cpu_flags, m, len(w), N, cores, dt, m1 * N / dt1, m1),
+                single_thread_value=m1 * N / dt1, flags=cpu_flags)
+
+
+def _boot_id():
+    try:
+        return open("/proc/sys/kernel/random/boot_id").read().strip()
+    except OSError:
+        return "unknown"
+
+
+STRONG_N1_PATHS = ("/tmp/jp_b200_strong_n1.json", os.path.join(ROOT, "gpurun_out", ".strong_n1.json"))
+
+
+def run_strong(jp, name, rank, world, dev, stream, steps, warmup):
+    """One of north_star's multi-GPU configurations at FIXED size on `world` ranks (strong scaling): device-resident
+    step time (fit + marginals of every coordinate, grid cached), the public sharded call, and -- several ranks -- whether the
+    sharded global knots / quantiles equal the unsharded ones computed on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from jointposteriors_jl_b200 import distributed as D
+    from jointposteriors_jl_b200.model import Context, JointPosterior
+    from jointposteriors_jl_b200 import _lib
+    wl = make_workload(jp, name, 1)
+    data, d = wl["data"], wl["d"]
+    obs, hyper = data.records()
+    ctx = Context.get(dev.index)
+    M = jp.Model(wl["params"], device=dev.index)
+    t0 = time.perf_counter()
+    dd = ctx.upload(data) if world == 1 else ctx.upload_sharded(data)
+    ctx.sync()
+    t_up = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    x, U, neg_min = jp.mode(M, dd)
+    t_mode = time.perf_counter() - t0
+    grid = ctx.grid(M.build.rule.rule_id, U.shape[1], wl["level"])
+    Mtot = int(jp.lib().jp_grid_size(grid))
+    b, e = D.shard_bounds(Mtot, rank, world)
+    post = JointPosterior(M, dd, grid, x, U, neg_min, node_range=(b, e))
+    loc = D.CudaLocal(post)
+    coords = list(range(d))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        if world == 1:
+            post.evaluate()
+            return jp.marginals(post, coords)
+        D.fit_sharded(loc)
+        return D.marginals_sharded(loc, coords)
+
+    for _ in range(warmup):
+        res = step()
+    tok = torch.zeros(1, device=dev)
+    ms, kms = [], []
+    for _ in range(steps):
+        flush.zero_()
+        if world > 1:
+            dist.all_reduce(tok)
+        torch.cuda.synchronize(dev)
+        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        res = step()
+        c.record(stream)
+        torch.cuda.synchronize(dev)
+        ms.append(a.elapsed_time(c))
+        kms.append(ctx.last_kernel_ms())
+    t = torch.tensor([float(np.sum(ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.cpu()[0]) / steps
+    pairs = float(Mtot) * float(obs.shape[0])
+    out = dict(workload=wl["desc"], n_gpus=world, nodes=Mtot, obs=int(obs.shape[0]), d=d, value=pairs / (ms_per_step * 1e-3), unit=UNIT,
+               ms_per_step=ms_per_step, kernel_ms=float(np.mean(kms)), steps=steps, warmup=warmup,
+               prep=getattr(loc, "last_prep", "replicated") if world > 1 else "single",
+               path="tc" if post.path_used == _lib.PATH_TC else "fp64", upload_ms=t_up * 1e3, mode_ms=t_mode * 1e3,
+               scaling="strong")
+    # the public call: fit_distributed(model, host data) + global marginals of every coordinate (fit(...) + marginals on one GPU)
+    hp = torch.from_numpy(obs).pin_memory()
+    hdata = type(data).__new__(type(data))
+    hdata.__dict__.update(data.__dict__)
+    hdata._obs = hp.numpy()
+
+    def api_call():
+        if world == 1:
+            pa = jp.fit(M, hdata, wl["level"])
+            ra = jp.marginals(pa, coords)
+        else:
+            pa = jp.fit_distributed(M, hdata, wl["level"])
+            ra = pa.marginals(coords)
+        pa.free()
+        return ra
+    api_call()
+    tt = []
+    for _ in range(3):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        api_call()
+        tt.append((time.perf_counter() - t0) * 1e3)
+    t = torch.tensor([float(np.median(tt))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out["api_fit_marginals_ms"] = float(t.cpu()[0])
+    out["api_what"] = "fit%s(model, pinned host data, level) incl. row-sharded upload, mode finder, + global marginals of all %d coordinates; median of 3, max over ranks" % (
+        "_distributed" if world > 1 else "", d)
+    # global weighted quantiles: sharded (two all_gathers of moments / knot candidates) against unsharded on rank 0
+    if world > 1:
+        mu, sg, vn, wn = res
+        flag = None
+        if rank == 0:
+            full = JointPosterior(M, dd, grid, x, U, neg_min)
+            full.evaluate()
+            mf = jp.marginals(full, coords)
+            qs = np.array([[jp.quantile(jp.Grid(wn[k], vn[k]), p) for p in (.025, .25, .5, .75, .975)] for k in range(d)])
+            qf = np.array([[jp.quantile(m, p) for p in (.025, .25, .5, .75, .975)] for m in mf])
+            sf = np.array([m.sigma for m in mf])
+            err = dict(mu=float(np.max(np.abs(mu - [m.mu for m in mf]) / np.maximum(np.abs([m.mu for m in mf]), 1e-3))),
+                       sigma=float(np.max(np.abs(sg - sf) / sf)),
+                       knot_weights=float(np.max(np.abs(wn - np.array([m.itp.weights for m in mf])))),
+                       quantiles_in_sigma=float(np.max(np.abs(qs - qf) / sf[:, None])))
+            flag = dict(equal=bool(max(err.values()) < 1e-9), max_err=err,
+                        what="sharded global (mu, sigma, 100-knot Grid, 5 quantiles) of all %d coordinates vs the unsharded fit on rank 0, tolerance 1e-9" % d)
+            full.free()
+        out["global_quantile_parity"] = flag
+    # efficiency against the 1-GPU figure of the same session (same boot of the same box), when there is one
+    if rank == 0:
+        if world == 1:
+            rec = {}
+            for pth in STRONG_N1_PATHS:
+                try:
+                    rec = json.load(open(pth))
+                    break
+                except (OSError, ValueError):
+                    pass
+            if rec.get("boot_id") != _boot_id():
+                rec = dict(boot_id=_boot_id())
+            rec[name] = dict(ms_per_step=ms_per_step, value=out["value"], when=time.time())
+            for pth in STRONG_N1_PATHS:
+                try:
+                    os.makedirs(os.path.dirname(pth), exist_ok=True)
+                    json.dump(rec, open(pth, "w"))
+                except OSError:
+                    pass
+        else:
+            out["vs_1gpu"] = None
+            for pth in STRONG_N1_PATHS:
+                try:
+                    rec = json.load(open(pth))
+                except (OSError, ValueError):
+                    continue
+                if rec.get("boot_id") == _boot_id() and name in rec:
+                    r1 = rec[name]
+                    out["vs_1gpu"] = dict(ms_per_step_1gpu=r1["ms_per_step"], speedup=r1["ms_per_step"] / ms_per_step,
+                                          efficiency=r1["ms_per_step"] / ms_per_step / world, age_s=time.time() - r1["when"],
+                                          source="1-GPU run of this bench in the same boot of this box (%s)" % pth)
+                    break
+    post.free()
+    dd.free()
+    del flush
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_product(args):
@@ -432,21 +594,31 @@ def run_product(args):
     # ---- the whole public call, mode finder included: fit(model, host data) + marginals of every coordinate, grid cached
     # (what the reference's README times for its Example 1: 3.883 ms median, README.md:223-234, unstated CPU)
     api = None
-    if world == 1 and args.emulate_shard <= 1:
+    if args.emulate_shard <= 1:
         def api_call():
-            pa = jp.fit(M, hdata, wl["level"], path=path)
-            ra = jp.marginals(pa, coords)
+            if world == 1:
+                pa = jp.fit(M, hdata, wl["level"], path=path)
+                ra = jp.marginals(pa, coords)
+            else:
+                pa = jp.fit_distributed(M, hdata, wl["level"], path=path)
+                ra = pa.marginals(coords)
             pa.free()
             return ra
         for _ in range(3):
             api_call()
         tt = []
         for _ in range(max(3, min(args.steps, 10))):
+            barrier()
             t0 = time.perf_counter()
             api_call()
             tt.append((time.perf_counter() - t0) * 1e3)
-        api = dict(ms_median=float(np.median(tt)), ms_min=float(np.min(tt)), calls=len(tt),
-                   what="fit(model, host data, level) incl. upload and mode finder + marginals of all %d coordinates" % d)
+        tm = torch.tensor([float(np.median(tt)), float(np.min(tt))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        api = dict(ms_median=float(tm.cpu()[0]), ms_min=float(tm.cpu()[1]), calls=len(tt), n_gpus=world,
+                   what="fit%s(model, host data, level) incl. upload and mode finder + marginals of all %d coordinates (max over ranks)" % (
+                       "_distributed" if world > 1 else "", d))
+    if api is not None and world == 1:
         if args.workload == "cfg1":
             api["published_reference_ms"] = 3.883
             api["published_source"] = "reference README.md:223-234 (BenchmarkTools median, fit + 3 marginals, unstated CPU)"
@@ -462,6 +634,17 @@ def run_product(args):
                                           us_per_evaluation=t_sm * 1e3 / max(1, info["evaluations"]), converged=info["converged"],
                                           what="marginal(jp, f, Normal) of coordinate 0: stable sort, 10 x M design matrix, "
                                                "BFGS (<= 1000 iterations) with every objective/score evaluation one launch over all nodes")
+    # ---- north_star's multi-GPU configurations at fixed size on these `world` ranks (strong scaling), beside the headline
+    strong = None
+    diag = post.diagnostics
+    if args.strong and args.strong != "none" and args.emulate_shard <= 1:
+        post.free()
+        dd.free()
+        del flush
+        torch.cuda.empty_cache()
+        strong = {}
+        for name in args.strong.split(","):
+            strong[name] = run_strong(jp, name, rank, world, dev, stream, steps=max(3, min(args.steps, 5)), warmup=3)
     if rank == 0:
         cpu = cpu_baseline(wl, (x, U, neg_min)) if world == 1 and not args.no_cpu_baseline else None
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -477,8 +660,10 @@ def run_product(args):
                                marginals="%d coordinate marginals per step (moments + 100-knot Grid CDF)" % d),
                    fit_ms=tot_fit_ms / args.steps, marginal_ms=tot_marg_ms / args.steps, grid_build_ms=t_grid,
                    mode_ms=t_mode * 1e3, upload_ms=t_up * 1e3, clocks=clocks, e2e=e2e, gpu_launches=int(launches),
-                   tc_diagnostics=post.diagnostics,
+                   tc_diagnostics=diag,
                    roofline=roof)
+        if strong:
+            out["strong"] = strong
         if cpu:
             out["cpu_baseline"] = cpu
         if api:
@@ -509,10 +694,14 @@ def main():
     ap.add_argument("--workload", default="cfg3")
     ap.add_argument("--path", default="auto", choices=["auto", "fp64", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", default="cfg5,cfg4",
+                    help="fixed-size configurations also run on these ranks and reported in the `strong` object ('none' to skip)")
     ap.add_argument("--emulate-shard", type=int, default=1,
                     help="diagnostic (1 GPU): run the local work of rank 0 of W ranks, no collectives; not a bench line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.workload != "cfg3":
+        args.strong = "none"        # the strong object accompanies the headline line only
     if args.impl == "reference":
         run_reference(args)
     else:

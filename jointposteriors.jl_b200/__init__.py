@@ -12,6 +12,7 @@ from .marginals import (Grid, MarginalBuffer, NestedPolyGLM, Normal, cdf, margin
                         pdf, quantile)
 from .model import (Context, DeviceData, Dynamic, FixedRank, Full, LDR, GenzKeister, JointPosterior, JointPosteriorRaw,
                     KronrodPatterson, Model, Smolyak, SmolyakRaw, default, fit, log_density_unc, mode)
+from .distributed import ShardedPosterior, fit_distributed
 from .params import NonCentredVector, PositiveVector, ProbabilityVector, RealVector, Simplex, parameter
 
 __all__ = [
@@ -20,5 +21,5 @@ __all__ = [
     "LogisticData", "PoissonData", "HierNormalData", "NormalLinearData", "MultinomialData", "Smolyak", "SmolyakRaw", "GenzKeister",
     "KronrodPatterson", "Dynamic", "Full", "FixedRank", "LDR", "default", "Context", "DeviceData", "chol", "try_chol",
     "inv_upper", "inv_chol", "reduce_dimensions", "reduce_dimensions_ldr", "deduce_scale_dynamic", "JPError", "NotPositiveDefinite",
-    "PATH_AUTO", "PATH_FP64", "PATH_TC", "log_density_unc",
+    "PATH_AUTO", "PATH_FP64", "PATH_TC", "log_density_unc", "fit_distributed", "ShardedPosterior",
 ]

@@ -45,6 +45,10 @@ int jp_ctx_create(int device, jp_ctx** out) {
   JP_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(unsigned int) * JP_COUNTERS, ctx->stream));
   JP_CUDA(jp_dmalloc(ctx, &ctx->d_bpart, sizeof(double) * JP_BPART_DOUBLES));
   JP_CUDA(cudaMallocHost(&ctx->h_pinned, sizeof(double) * JP_PINNED_DOUBLES));
+  JP_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+  JP_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  JP_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  JP_CUDA(cudaEventCreateWithFlags(&ctx->ev_pinned, cudaEventDisableTiming));
   JP_CUDA(cudaEventCreate(&ctx->ev_k0));
   JP_CUDA(cudaEventCreate(&ctx->ev_k1));
   *out = ctx;
@@ -68,6 +72,11 @@ int jp_ctx_destroy(jp_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaFreeHost(ctx->h_pinned);
   cudaFree(ctx->d_rule_nodes[0]); cudaFree(ctx->d_rule_nodes[1]);
+  cudaStreamSynchronize(ctx->side);
+  cudaStreamDestroy(ctx->side);
+  cudaEventDestroy(ctx->ev_fork);
+  cudaEventDestroy(ctx->ev_join);
+  cudaEventDestroy(ctx->ev_pinned);
   cudaEventDestroy(ctx->ev_k0);
   cudaEventDestroy(ctx->ev_k1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

@@ -83,6 +83,10 @@ struct jp_ctx {
   double* d_bpart = nullptr;       // JP_BPART_DOUBLES per-block partials of those reductions
   // __constant__ tables and the device copy of the master node tables are PER DEVICE: every context uploads its own
   // (several GPUs in one process each get theirs; a second context on the same device re-uploads identical bytes)
+  cudaStream_t side = nullptr;       // second stream of the context: independent O(N) prep kernels of a fit overlap on it
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_pinned = nullptr;   // recorded after the last asynchronous copy OUT of h_pinned (see jp_pinned_acquire)
+  bool pinned_busy = false;
   bool rules_uploaded = false, fit_nodes_uploaded = false, tc_tables_uploaded = false;
   double* d_rule_nodes[2] = {nullptr, nullptr};
 };
@@ -98,6 +102,18 @@ inline cudaError_t jp_dmalloc(jp_ctx* ctx, T** p, size_t bytes) {
 }
 inline void jp_dfree(jp_ctx* ctx, const void* p) {
   if (p) cudaFreeAsync(const_cast<void*>(p), ctx->stream);
+}
+// The pinned staging buffer is shared by every entry point of a context.  Before the HOST writes into it, wait until the last
+// asynchronous host-to-device copy that reads it has completed (an event, not a stream synchronisation: a fit queued behind
+// another fit only waits for that fit's three small uploads); after queueing copies out of it, publish them.
+inline cudaError_t jp_pinned_acquire(jp_ctx* ctx) {
+  if (!ctx->pinned_busy) return cudaSuccess;
+  ctx->pinned_busy = false;
+  return cudaEventSynchronize(ctx->ev_pinned);
+}
+inline cudaError_t jp_pinned_publish(jp_ctx* ctx) {
+  ctx->pinned_busy = true;
+  return cudaEventRecord(ctx->ev_pinned, ctx->stream);
 }
 #define JP_SCRATCH_DOUBLES (1 << 16)
 #define JP_PINNED_DOUBLES (1 << 18)   // 2 MB: result vectors of up to 262 144 nodes are downloaded through it
@@ -121,6 +137,19 @@ struct jp_data {
                                 // [x_hi | x_lo | x_hi] in TF32-representable FP32, its TMA map, per-obs coefficients
 };
 
+// what the per-node "finish" of a log-density launch needs (deferred into the fused stage-4 kernel, jp_fit.cu)
+struct JpFinish {
+  int path = 0;                   // JP_PATH_FP64 / JP_PATH_TC
+  int splits = 0;                 // FP64 path: observation splits; part [splits][M], lj_prior [M]
+  const double* part = nullptr;
+  const double* lj_prior = nullptr;
+  int chunks = 0;                 // TC path: observation chunks; tc_part [chunks][P][2] (even, odd), quad [M]
+  long long P = 0, j_lo = 0;
+  const double* tc_part = nullptr;
+  const double* quad = nullptr;
+  double neg_min = 0;
+};
+
 struct jp_posterior {
   jp_ctx* ctx = nullptr;
   const jp_grid* grid = nullptr;
@@ -128,6 +157,7 @@ struct jp_posterior {
   int d = 0, p = 0;
   long long m0 = 0, m1 = 0, M = 0;   // shard [m0, m1), M = m1 - m0
   int path_used = 0;
+  JpFinish fin;                  // pending finish of the last log-density launch (consumed by jp_stage4_launch)
   double* d_theta = nullptr;     // SoA constrained parameters [d][M]
   double* d_a = nullptr;         // log-density + neg_min + 0.5|z|^2
   double* d_logdens = nullptr;   // log-density + neg_min
@@ -255,8 +285,9 @@ __device__ __forceinline__ unsigned long long jp_sortable(double x) {
 
 // ---------------------------------------------------------------------------- internal entry points
 int jp_grid_build(jp_ctx* ctx, int rule, int d, int level, jp_grid* g);
-int jp_fit_fp64_launch(jp_posterior* post, const jp_fit_args* args);   // stages 2-3, generic plugin kernel
-int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args);     // stages 2-3, GLM tensor-core path
+// finish = false: the per-node finish (sum of the partials -> log-density) is left to the fused stage-4 kernel (post->fin)
+int jp_fit_fp64_launch(jp_posterior* post, const jp_fit_args* args, bool finish = true);   // stages 2-3, generic plugin kernel
+int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args, bool finish = true);     // stages 2-3, GLM tensor-core path
 bool jp_fit_tc_supported(const jp_posterior* post, const jp_fit_args* args);
 // the tensor-core path phase by phase (observation-sharded prep of a node-sharded fit)
 int jp_fit_tc_prep_len(int d);
@@ -264,7 +295,7 @@ int jp_fit_tc_prep_local(jp_posterior* post, const jp_fit_args* args, int rank, 
 int jp_fit_tc_prep_gathered(jp_posterior* post, const jp_fit_args* args, const double* d_gathered, int world, int rank,
                             int* n_rows);
 int jp_fit_tc_coef_slab(jp_posterior* post, int n_rows, float** d_local, float** d_all, long long* count);
-int jp_fit_tc_run_prepared(jp_posterior* post, const jp_fit_args* args);
+int jp_fit_tc_run_prepared(jp_posterior* post, const jp_fit_args* args, bool finish = true);
 void jp_tc_data_free(jp_data* data);
 void jp_tc_post_free(jp_posterior* post);
 int jp_upload_fit_consts(jp_posterior* post, const jp_fit_args* args);   // mu_hat, U, transform codes -> device

@@ -17,8 +17,10 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cooperative_groups.h>
 #include "jp_common.cuh"
 #include "jp_family.cuh"
+namespace cg = cooperative_groups;
 
 #define JP_FIT_THREADS 128
 #define JP_FIT_TILE_DOUBLES 4096     // shared-memory tile of observation records (32 KB)
@@ -251,6 +253,86 @@ __global__ void jp_scale_gathered_kernel(long long M, double* __restrict__ e, co
   e[m] = e[m] * exp(g[2 * rank] - mx) / S;
 }
 
+// Stage 4 in ONE cooperative launch (replaces finish + max + sum + scale = four launches of a few microseconds of work each,
+// whose launch gaps were a sixth of the cfg3 step): every block owns a contiguous slice of the node block and keeps it across
+// the phases (L1 / L2 resident), grid-wide barriers separate them:
+//   A  per node: log-density from the partials of the log-density kernel (the deferred "finish"), a = ld + |z|^2 / 2, block max
+//   B  global max (every block reduces the block maxima itself, same order -> same bits), e = w exp(a - max), block sums
+//   C  (one GPU) total in block order, density = e / total.  Several GPUs stop after B with (max, sum) for the all_gather.
+// Thread t of a block adds its elements in ascending order, blocks combine by the fixed tree of jp_block_sum, the block sums
+// are added in block order: bitwise reproducible for a given node count.
+#define JP_S4_THREADS 256
+struct Stage4Params {
+  long long M, m0;
+  JpFinish fin;
+  const double* hzz;
+  const double* w;
+  double* logdens;
+  double* a;
+  double* e;          // density
+  double* bmax;       // [gridDim.x]
+  double* bsum;       // [gridDim.x]
+  double* stats;      // [2]: max, sum
+  int normalise;
+};
+__global__ void __launch_bounds__(JP_S4_THREADS) jp_stage4_kernel(const Stage4Params P) {
+  __shared__ double sm[33];
+  cg::grid_group grid = cg::this_grid();
+  const long long per = (P.M + gridDim.x - 1) / gridDim.x, b0 = (long long)blockIdx.x * per, b1 = min(P.M, b0 + per);
+  // ---- A
+  double mx = -INFINITY;
+  for (long long m = b0 + threadIdx.x; m < b1; m += JP_S4_THREADS) {
+    double ld;
+    if (P.fin.path == JP_PATH_TC) {
+      const long long gm = P.m0 + m, j = ((gm + 1) >> 1) - P.fin.j_lo;
+      const double sgn = ((gm & 1) || gm == 0) ? 1.0 : -1.0;
+      double s = 0;
+      for (int c = 0; c < P.fin.chunks; ++c) {
+        const double2 eo = *reinterpret_cast<const double2*>(P.fin.tc_part + ((size_t)c * P.fin.P + j) * 2);
+        s += eo.x + sgn * eo.y;
+      }
+      ld = (P.fin.quad[m] - s) + P.fin.neg_min;
+    } else if (P.fin.path == JP_PATH_FP64) {
+      double s = 0;
+      for (int k = 0; k < P.fin.splits; ++k) s += P.fin.part[(size_t)k * P.M + m];
+      ld = (s + P.fin.lj_prior[m]) + P.fin.neg_min;
+    } else {
+      ld = P.logdens[m];      // already finished by the path's own kernel
+    }
+    const double a = ld + P.hzz[P.m0 + m];
+    if (P.fin.path != 0) P.logdens[m] = ld;
+    P.a[m] = a;
+    mx = fmax(mx, a);
+  }
+  mx = jp_block_max(mx, sm);
+  if (threadIdx.x == 0) P.bmax[blockIdx.x] = mx;
+  grid.sync();
+  // ---- B
+  double g = -INFINITY;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += JP_S4_THREADS) g = fmax(g, __ldcg(P.bmax + b));
+  g = jp_block_max(g, sm);
+  double s = 0;
+  for (long long m = b0 + threadIdx.x; m < b1; m += JP_S4_THREADS) {
+    const double v = P.w[P.m0 + m] * exp(P.a[m] - g);
+    P.e[m] = v;
+    s += v;
+  }
+  s = jp_block_sum(s, sm);
+  if (threadIdx.x == 0) P.bsum[blockIdx.x] = s;
+  grid.sync();
+  // ---- C
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(P.bsum + b);
+    sm[32] = t;
+    if (blockIdx.x == 0) { P.stats[0] = g; P.stats[1] = t; }
+  }
+  __syncthreads();
+  if (!P.normalise) return;
+  const double tot = sm[32];
+  for (long long m = b0 + threadIdx.x; m < b1; m += JP_S4_THREADS) P.e[m] = P.e[m] / tot;
+}
+
 // ------------------------------------------------------------------------------------ registry
 static JpFamilyEntry g_families[16];
 static int g_nfamilies = 0;
@@ -315,7 +397,7 @@ int jp_upload_fit_consts(jp_posterior* post, const jp_fit_args* args) {
   // stage through pinned memory so the copies are truly asynchronous
   double* hp = ctx->h_pinned;
   int d = args->d, p = args->p;
-  JP_CUDA(cudaStreamSynchronize(ctx->stream));   // pinned staging area is reused across calls
+  JP_CUDA(jp_pinned_acquire(ctx));               // the staging area is reused across calls
   for (int i = 0; i < d; ++i) hp[i] = args->h_mu_hat[i];
   for (int i = 0; i < d * p; ++i) hp[d + i] = args->h_U[i];
   int* hc = reinterpret_cast<int*>(hp + d + d * p);
@@ -323,6 +405,7 @@ int jp_upload_fit_consts(jp_posterior* post, const jp_fit_args* args) {
   JP_CUDA(cudaMemcpyAsync(post->d_mu, hp, sizeof(double) * d, cudaMemcpyHostToDevice, ctx->stream));
   JP_CUDA(cudaMemcpyAsync(post->d_U, hp + d, sizeof(double) * d * p, cudaMemcpyHostToDevice, ctx->stream));
   JP_CUDA(cudaMemcpyAsync(post->d_tcode, hc, sizeof(int) * d, cudaMemcpyHostToDevice, ctx->stream));
+  JP_CUDA(jp_pinned_publish(ctx));
   return JP_OK;
 }
 
@@ -355,7 +438,7 @@ int jp_fit_check_args(const jp_posterior* post, const jp_fit_args* args) {
   return JP_OK;
 }
 
-int jp_fit_fp64_launch(jp_posterior* post, const jp_fit_args* args) {
+int jp_fit_fp64_launch(jp_posterior* post, const jp_fit_args* args, bool finish) {
   jp_ctx* ctx = post->ctx;
   const jp_data* data = post->data;
   const JpFamilyEntry* fam = jp_find_family(data->family);
@@ -387,11 +470,17 @@ int jp_fit_fp64_launch(jp_posterior* post, const jp_fit_args* args) {
   lp.part = post->d_part;
   lp.lj_prior = post->d_part + (size_t)JP_POST_PART_SPLITS * post->M;
   JP_TRY(fam->launch(post, lp));
-  unsigned gb = (unsigned)((post->M + 255) / 256);
-  jp_fit_finish_kernel<<<gb, 256, 0, ctx->stream>>>(post->M, post->m0, splits, lp.part, lp.lj_prior,
-                                                     post->grid->d_hzz, args->neg_min, post->d_logdens, post->d_a);
-  JP_CHECK_LAUNCH(ctx);
   post->path_used = JP_PATH_FP64;
+  post->fin = JpFinish();
+  post->fin.path = JP_PATH_FP64; post->fin.splits = splits; post->fin.part = lp.part; post->fin.lj_prior = lp.lj_prior;
+  post->fin.neg_min = args->neg_min;
+  if (finish) {
+    unsigned gb = (unsigned)((post->M + 255) / 256);
+    jp_fit_finish_kernel<<<gb, 256, 0, ctx->stream>>>(post->M, post->m0, splits, lp.part, lp.lj_prior,
+                                                       post->grid->d_hzz, args->neg_min, post->d_logdens, post->d_a);
+    JP_CHECK_LAUNCH(ctx);
+    post->fin.path = 0;
+  }
   return JP_OK;
 }
 
@@ -402,6 +491,43 @@ __global__ void jp_points_finish_kernel(long long K, int splits, const double* _
   double s = 0;
   for (int k = 0; k < splits; ++k) s += part[(size_t)k * K + m];
   out[m] = s + lj_prior[m];
+}
+
+// stage 4 after a log-density launch made with finish = false; d_stats[2] receives (max, sum)
+static int jp_stage4_launch(jp_posterior* post, bool normalise, double* d_stats) {
+  jp_ctx* ctx = post->ctx;
+  Stage4Params P;
+  P.M = post->M; P.m0 = post->m0; P.fin = post->fin;
+  P.hzz = post->grid->d_hzz; P.w = post->grid->d_w;
+  P.logdens = post->d_logdens; P.a = post->d_a; P.e = post->d_density;
+  // one block per 512 nodes, at most two per SM (co-resident by a wide margin: 256 threads, 264 bytes of shared memory)
+  const int nb = (int)std::max<long long>(1, std::min<long long>(2LL * ctx->sm_count, (post->M + 511) / 512));
+  JP_REQUIRE(2 * nb <= JP_BPART_DOUBLES, "stage 4: %d blocks exceed the partial buffer", nb);
+  P.bmax = ctx->d_bpart; P.bsum = ctx->d_bpart + nb;
+  P.stats = d_stats;
+  P.normalise = normalise ? 1 : 0;
+  void* kargs[] = {(void*)&P};
+  JP_CUDA(cudaLaunchCooperativeKernel((const void*)jp_stage4_kernel, dim3(nb), dim3(JP_S4_THREADS), kargs, 0, ctx->stream));
+  JP_CHECK_LAUNCH(ctx);
+  post->fin.path = 0;
+  return JP_OK;
+}
+
+// stages 2-3 by the path the arguments select, the finish deferred to stage 4
+static int jp_fit_launch_path(jp_posterior* post, const jp_fit_args* args, bool finish) {
+  post->sorted_valid = false;      // the sorted arrays / marginals of an earlier fit no longer describe this posterior
+  post->K_last = 0;
+  // AUTO: GLM families take the tensor-core path when its a-priori error bounds hold for this
+  // (data, U, grid); otherwise, and for every other family, the FP64 plugin kernel runs.
+  int path = args->path;
+  if (path == JP_PATH_AUTO) path = jp_fit_tc_supported(post, args) ? JP_PATH_TC : JP_PATH_FP64;
+  if (path == JP_PATH_TC) {
+    int st = jp_fit_tc_launch(post, args, finish);
+    if (st == JP_ERR_UNSUPPORTED && args->path == JP_PATH_AUTO) path = JP_PATH_FP64;
+    else JP_TRY(st);
+  }
+  if (path == JP_PATH_FP64) JP_TRY(jp_fit_fp64_launch(post, args, finish));
+  return JP_OK;
 }
 
 extern "C" {
@@ -433,6 +559,8 @@ int jp_log_density_points(jp_ctx* ctx, const jp_data* data, int d, const int* h_
     // Zero-copy: with unified addressing the pinned buffer is device-accessible at its host address, so the kernels read
     // the (few KB of) points and codes straight from it and write the results back into it -- no copy calls, one
     // launch pair and one synchronisation per evaluation (a Newton iteration of jp_mode is one such call).
+    e = jp_pinned_acquire(ctx);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);    // zero-copy: no kernel of an earlier call may still read / write it
     std::memcpy(hp, h_x, (size_t)K * d * 8);
     std::memcpy(hp + (size_t)K * d, h_transform, (size_t)d * 4);
     d_x = hp;
@@ -484,16 +612,7 @@ int jp_fit_local(jp_posterior* post, const jp_fit_args* args, double* d_local_ma
   JP_ENTER_CTX(post->ctx);
   JP_TRY(jp_fit_check_args(post, args));
   JP_REQUIRE(d_local_max, "jp_fit_local: null output");
-  // AUTO: GLM families take the tensor-core path when its a-priori error bounds hold for this
-  // (data, U, grid); otherwise, and for every other family, the FP64 plugin kernel runs.
-  int path = args->path;
-  if (path == JP_PATH_AUTO) path = jp_fit_tc_supported(post, args) ? JP_PATH_TC : JP_PATH_FP64;
-  if (path == JP_PATH_TC) {
-    int st = jp_fit_tc_launch(post, args);
-    if (st == JP_ERR_UNSUPPORTED && args->path == JP_PATH_AUTO) path = JP_PATH_FP64;
-    else JP_TRY(st);
-  }
-  if (path == JP_PATH_FP64) JP_TRY(jp_fit_fp64_launch(post, args));
+  JP_TRY(jp_fit_launch_path(post, args, true));
   jp_reduce_max_kernel<<<jp_red_blocks(post->M), 256, 0, post->ctx->stream>>>(post->d_a, post->M, post->ctx->d_bpart,
                                                                               post->ctx->d_counters, d_local_max);
   JP_CHECK_LAUNCH(post->ctx);
@@ -520,9 +639,11 @@ int jp_fit_normalise(jp_posterior* post, const double* d_global_sum) {
 }
 
 int jp_fit_local_stats(jp_posterior* post, const jp_fit_args* args, double* d_stats) {
-  JP_REQUIRE(d_stats, "jp_fit_local_stats: null output");
-  JP_TRY(jp_fit_local(post, args, d_stats));
-  return jp_fit_local_sum(post, d_stats, d_stats + 1);
+  JP_REQUIRE(post && d_stats, "jp_fit_local_stats: null argument");
+  JP_ENTER_CTX(post->ctx);
+  JP_TRY(jp_fit_check_args(post, args));
+  JP_TRY(jp_fit_launch_path(post, args, false));
+  return jp_stage4_launch(post, false, d_stats);      // finish + local max + sum relative to it: one launch
 }
 
 // ---- node-sharded fit with the O(N) prep of the tensor-core path sharded by OBSERVATION (csrc/jp_glm_tc.cu)
@@ -559,11 +680,8 @@ int jp_fit_local_stats_prepared(jp_posterior* post, const jp_fit_args* args, dou
   JP_ENTER_CTX(post->ctx);
   JP_TRY(jp_fit_check_args(post, args));
   JP_REQUIRE(d_stats, "jp_fit_local_stats_prepared: null output");
-  JP_TRY(jp_fit_tc_run_prepared(post, args));
-  jp_reduce_max_kernel<<<jp_red_blocks(post->M), 256, 0, post->ctx->stream>>>(post->d_a, post->M, post->ctx->d_bpart,
-                                                                              post->ctx->d_counters, d_stats);
-  JP_CHECK_LAUNCH(post->ctx);
-  return jp_fit_local_sum(post, d_stats, d_stats + 1);
+  JP_TRY(jp_fit_tc_run_prepared(post, args, false));
+  return jp_stage4_launch(post, false, d_stats);
 }
 
 int jp_fit_normalise_gathered(jp_posterior* post, const double* d_gathered, int world, int rank) {
@@ -579,10 +697,9 @@ int jp_fit_normalise_gathered(jp_posterior* post, const double* d_gathered, int 
 int jp_fit(jp_posterior* post, const jp_fit_args* args) {
   JP_REQUIRE(post, "jp_fit: null posterior");
   JP_ENTER_CTX(post->ctx);
-  JP_TRY(jp_fit_local(post, args, post->d_stats));
-  JP_TRY(jp_fit_local_sum(post, post->d_stats, post->d_stats + 1));
-  JP_TRY(jp_fit_normalise(post, post->d_stats + 1));
-  return JP_OK;
+  JP_TRY(jp_fit_check_args(post, args));
+  JP_TRY(jp_fit_launch_path(post, args, false));
+  return jp_stage4_launch(post, true, post->d_stats);   // finish + max + sum + scale: one cooperative launch
 }
 
 }  // extern "C"

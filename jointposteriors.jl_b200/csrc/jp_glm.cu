@@ -236,6 +236,7 @@ extern "C" int jp_glm_grad_hess(jp_ctx* ctx, const jp_data* data, int d, const d
              "jp_glm_grad_hess: family %d is not a GLM", data->family);
   JP_REQUIRE(d >= 1 && d <= JP_MAX_D && data->ncols == d + 1, "jp_glm_grad_hess: d=%d does not match %d columns", d,
              data->ncols);
+  JP_ENTER_CTX(ctx);
   int nE = d + d * (d + 1) / 2;
   int nb = jp_glm_num_blocks(ctx, data->N);
   double *d_beta = nullptr, *d_out = nullptr, *d_work = nullptr;
@@ -244,6 +245,7 @@ extern "C" int jp_glm_grad_hess(jp_ctx* ctx, const jp_data* data, int d, const d
   JP_CUDA(jp_dmalloc(ctx, &d_work, sizeof(double) * (size_t)nb * (nE + 1)));
   // staged through the context's pinned buffer (a Newton iteration of the mode finder is one such call)
   double* hp = ctx->h_pinned;
+  JP_CUDA(jp_pinned_acquire(ctx));
   std::memcpy(hp, h_beta, sizeof(double) * d);
   JP_CUDA(cudaMemcpyAsync(d_beta, hp, sizeof(double) * d, cudaMemcpyHostToDevice, ctx->stream));
   int st = jp_glm_sums_device(ctx, data, d, d_beta, d_out, d_work, nb);

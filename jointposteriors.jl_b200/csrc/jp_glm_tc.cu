@@ -69,16 +69,11 @@ int jp_glm_num_blocks(const jp_ctx* ctx, long long N);
 #ifndef TC_LDW
 #define TC_LDW 8                 // columns per tcgen05.ld of the epilogue (8 or 16)
 #endif
-#ifndef TC_EPI_V2
-#define TC_EPI_V2 0              // epilogue tile loop: 0 = two alternating coefficient sets (unrolled by two), 1 = one set
-#endif
-#ifndef TC_EARLY_COEF
-#define TC_EARLY_COEF 0          // ... and loads that tile's coefficients right away when the peek succeeds
-#endif
 #ifndef TC_EARLY_PEEK
 #define TC_EARLY_PEEK 1          // epilogue peeks at the next tile's accumulator barrier one tile early
 #endif
-#define TC_PREP_BLOCKS 444       // 3 per SM (two 32 KB record tiles each at d = 30)
+#define TC_PREP_BLOCKS 444       // large N: 3 per SM (two 32 KB record tiles each at d = 30), every block streams many tiles
+#define TC_PREP_BLOCKS_MAX 1184  // small N: one block per 128-observation tile up to 8 per SM (a single round, no tile loop)
 #define TC_NORD 5                // series lengths NC = 4, 6, 8, 10, 12 (orders 6 .. 14)
 #define TC_NBOUND (14 + 2 * TC_NFOLD)   // per-block bound partials, see tc_obs_prep_kernel
 #define TC_COEF_ROWS (TC_NCMAX + 1)     // coefficient rows per observation + the row of t_i = |U' x_i|
@@ -104,7 +99,8 @@ struct TcDataState {
   int nc_all = 0;
   double* d_sums = nullptr;    // packed (g[d], upper H[d(d+1)/2], L_hat)
   double* d_work = nullptr;    // partials of the GLM sums
-  double* d_bounds = nullptr;  // [TC_PREP_BLOCKS][TC_NBOUND]
+  double* d_bounds = nullptr;  // [TC_PREP_BLOCKS_MAX][TC_NBOUND]
+  int prep_blocks = TC_PREP_BLOCKS;   // blocks of tc_obs_prep_kernel for a slice of n_loc observations
   double* d_comb = nullptr;    // [TC_NBOUND]: bounds combined over the ranks (sharded prep)
   int glm_blocks = 0;
   cudaEvent_t ev_bounds = nullptr;   // the bounds have reached the host (the fit waits on it, not on the whole stream)
@@ -354,12 +350,15 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
     const int k = e / p4, j = e - k * p4;
     s_U[e] = (j < p) ? U[(size_t)j * d + k] : 0.0;
   }
-  // the Cholesky scale matrix is upper triangular (reference src/joint_posterior.jl:56-76): its zero rows are skipped
+  // the Cholesky scale matrix is upper triangular (reference src/joint_posterior.jl:56-76): its zero rows are skipped.
+  // (Scanned from the shared copy: forty dependent global loads by a handful of threads used to open every block.)
+  __syncthreads();
   if (threadIdx.x < p4 / 4) {
     int kend = 0;
-    for (int k = 0; k < d; ++k)
-      for (int j = 4 * threadIdx.x; j < min(p, 4 * (int)threadIdx.x + 4); ++j)
-        if (U[(size_t)j * d + k] != 0.0) kend = k + 1;
+    for (int k = 0; k < d; ++k) {
+      const double* u = s_U + (size_t)k * p4 + 4 * threadIdx.x;
+      if (u[0] != 0.0 || u[1] != 0.0 || u[2] != 0.0 || u[3] != 0.0) kend = k + 1;
+    }
     s_kend[threadIdx.x] = kend;
   }
   double b_tmax = 0, b_a1 = 0, b_ref[TC_NORD] = {0}, b_max[TC_NORD] = {0}, b_r = 0, b_r2 = 0;
@@ -543,42 +542,55 @@ tc_node_prep_kernel(int d, int p, int kp, int seg, int rule, long long M, long l
   }
   __syncthreads();
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
   double* dl = s_dl + threadIdx.x;       // dl[k * blockDim.x]
-  for (int k = 0; k < d; ++k) dl[k * blockDim.x] = 0.0;
-  for (int j = 0; j < p; ++j) {
-    int key = idx[(size_t)j * M_grid + (m0 + m)];
-    if (key != 0) {
-      double z = s_z[key];
-      for (int k = 0; k < d; ++k) dl[k * blockDim.x] += s_U[(size_t)j * d + k] * z;   // same order as the FP64 path
+  if (m < M) {
+    for (int k = 0; k < d; ++k) dl[k * blockDim.x] = 0.0;
+    for (int j = 0; j < p; ++j) {
+      int key = idx[(size_t)j * M_grid + (m0 + m)];
+      if (key != 0) {
+        double z = s_z[key];
+        for (int k = 0; k < d; ++k) dl[k * blockDim.x] += s_U[(size_t)j * d + k] * z;   // same order as the FP64 path
+      }
+    }
+    const double L_hat = sums[d + d * (d + 1) / 2];
+    double lin = 0, qf = 0, prior = 0;
+    for (int k = 0; k < d; ++k) {
+      const double dk = dl[k * blockDim.x];
+      const double th = s_mu[k] + dk;
+      theta[(size_t)k * M + m] = th;
+      lin += s_g[k] * dk;
+      double hk = 0;
+      for (int l = 0; l < d; ++l) hk += s_H[(size_t)k * d + l] * dl[l * blockDim.x];
+      qf += dk * hk;
+      const double zz = th / prior_sd;
+      prior += -0.5 * zz * zz - log(prior_sd) - 0.5 * 1.8378770664093454835606594728112;
+    }
+    quad[m] = (L_hat + lin - 0.5 * qf) + prior;
+  }
+  // The pair operand rows, written by WHOLE WARPS: a row is kp floats (one to three 128-byte lines), lane c takes column
+  // c, c + 32, ..; one store instruction is one coalesced line.  (One thread writing its own row cost 3 d scattered
+  // 4-byte stores per node, eight times the bytes in 32-byte sectors.)  Warp w serves the nodes of its own 32 threads.
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w0 = threadIdx.x & ~31;
+  for (int r = w0; r < w0 + 32; ++r) {
+    const long long mr = (long long)blockIdx.x * blockDim.x + r;
+    if (mr >= M) break;
+    const long long gm = m0 + mr;
+    const bool first_member = (gm & 1) || gm == 0;
+    if (!(first_member || mr == 0)) continue;      // a second member writes only when the local range starts on it
+    const float sgn = first_member ? 1.f : -1.f;
+    float* o = ds + (size_t)(((gm + 1) >> 1) - j_lo) * kp;
+    for (int c = lane; c < kp; c += 32) {
+      const int part = c / seg, k = c - part * seg;          // seg = d (compact rows) or one K atom (split rows)
+      float v = 0.f;
+      if (part < 3 && k < d) {
+        float hi, lo;
+        tf32_split(s_dl[(size_t)k * blockDim.x + r], hi, lo);
+        v = sgn * (part == 2 ? lo : hi);
+      }
+      o[c] = v;
     }
   }
-  const double L_hat = sums[d + d * (d + 1) / 2];
-  double lin = 0, qf = 0, prior = 0;
-  const long long gm = m0 + m;
-  const bool first_member = (gm & 1) || gm == 0;
-  const bool writes_row = first_member || m == 0;
-  const float sgn = first_member ? 1.f : -1.f;
-  float* o = ds + (size_t)(((gm + 1) >> 1) - j_lo) * kp;
-  for (int k = 0; k < d; ++k) {
-    const double dk = dl[k * blockDim.x];
-    const double th = s_mu[k] + dk;
-    theta[(size_t)k * M + m] = th;
-    lin += s_g[k] * dk;
-    double hk = 0;
-    for (int l = 0; l < d; ++l) hk += s_H[(size_t)k * d + l] * dl[l * blockDim.x];
-    qf += dk * hk;
-    const double zz = th / prior_sd;
-    prior += -0.5 * zz * zz - log(prior_sd) - 0.5 * 1.8378770664093454835606594728112;
-    if (writes_row) {
-      float hi, lo;
-      tf32_split(dk, hi, lo);
-      o[k] = sgn * hi;              // seg = d (compact rows) or one K atom (split rows)
-      o[seg + k] = sgn * hi;
-      o[2 * seg + k] = sgn * lo;
-    }
-  }
-  quad[m] = (L_hat + lin - 0.5 * qf) + prior;
 }
 
 // ld = quad - sum_c (E[c] +- O[c]) + neg_min ; a = ld + |z|^2/2.  The first member of a mirror pair takes E + O,
@@ -861,9 +873,6 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int j = 0; j < TC_COLS_PER_WARP / 2; ++j) accE[j] = accO[j] = 0ull;
     int buf = 0, cslot = 0, ntile = 0;
     uint32_t tphase = 0;
-#if TC_EPI_V2
-    uint32_t par = 0;               // parity of the current pass over the accumulator ring
-#endif
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * TC_COLS_PER_WARP);
     const uint32_t coef_addr = sC + (uint32_t)(q * 32 + lane) * 4u;   // this thread's observation: tile row = TMEM lane
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -895,7 +904,6 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #else
         const bool ready = false;
 #endif
-        if (TC_EARLY_COEF && ready) load_coef(cn);   // the tile's coefficient rows landed before its MMA was issued
 #pragma unroll
         for (int c = 0; c < TC_COLS_PER_WARP / TC_LDW; ++c) {
           uint32_t(&cur)[TC_LDW] = (c & 1) ? vb : va;
@@ -915,7 +923,7 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tphase ^= 1u << nbuf;
               tc_fence_after();
               if (MODE != 2 && MODE != 4) tmem_ld(nxt, lane_addr + (uint32_t)nbuf * TC_TMEM_STRIDE);
-              if (!(TC_EARLY_COEF && ready)) load_coef(cn);
+              load_coef(cn);
             }
           }
           tc_accumulate<NC, MODE, TC_LDW>(cur, cc, accE + c * (TC_LDW / 2), accO + c * (TC_LDW / 2));
@@ -923,49 +931,6 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         buf = nbuf;
         ++ntile;
       };
-#if TC_EPI_V2
-      // One tile body, one coefficient set: the next tile's coefficients are loaded into the same registers right
-      // after their last use (the loads land while the first chunk's squares are formed), and the accumulator ring is
-      // tracked by (buffer, parity of the ring pass) instead of a per-buffer phase mask.
-      {
-        float cc[NC];
-        mbar_wait(bar_tfull + 8u * buf, par);
-        tc_fence_after();
-        tmem_ld(va, lane_addr + (uint32_t)buf * TC_TMEM_STRIDE);
-        load_coef(cc);
-#pragma unroll 1
-        for (int t = t0; t < t1; ++t) {
-          const bool more = t + 1 < t1;
-          const bool wrap = buf + 1 == TC_NBUF;
-          const int nbuf = wrap ? 0 : buf + 1;
-          const uint32_t npar = wrap ? par ^ 1u : par;
-          const uint32_t taddr = lane_addr + (uint32_t)buf * TC_TMEM_STRIDE;
-          const bool ready = more && mbar_test_wait(bar_tfull + 8u * nbuf, npar);
-#pragma unroll
-          for (int c = 0; c < TC_COLS_PER_WARP / TC_LDW; ++c) {
-            uint32_t(&cur)[TC_LDW] = (c & 1) ? vb : va;
-            uint32_t(&nxt)[TC_LDW] = (c & 1) ? va : vb;
-            tmem_ld_wait(cur);
-            if (c + 1 < TC_COLS_PER_WARP / TC_LDW) {
-              tmem_ld(nxt, taddr + (uint32_t)(TC_LDW * (c + 1)));
-            } else {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar_tempty + 8u * buf);
-              if (more) {
-                if (!ready) mbar_wait(bar_tfull + 8u * nbuf, npar);
-                tc_fence_after();
-                tmem_ld(nxt, lane_addr + (uint32_t)nbuf * TC_TMEM_STRIDE);
-              }
-            }
-            tc_accumulate<NC, MODE, TC_LDW>(cur, cc, accE + c * (TC_LDW / 2), accO + c * (TC_LDW / 2));
-          }
-          if (more) load_coef(cc);
-          buf = nbuf;
-          par = npar;
-        }
-      }
-#else
       int t = t0;
       const bool odd = ((t1 - t0) & 1) != 0;
       if (warp == 2 && lane == 0) TC_STAMP(3, ntile);
@@ -983,7 +948,6 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tile_step(t, ca, cb);
         tile_step(t + 1, cb, ca);
       }
-#endif
       // flush the item: sum over the 32 observation lanes by transpose-reduce, over the 4 lane quarters in
       // shared memory (FP64), one (even, odd) partial per (chunk, pair)
       {
@@ -1157,7 +1121,11 @@ static int ensure_data_state(jp_ctx* ctx, jp_data* data, int d, int world, int r
   JP_CUDA(jp_dmalloc(ctx, &s->d_comb, (size_t)TC_NBOUND * 8));
   JP_CUDA(jp_dmalloc(ctx, &s->d_sums, (size_t)(nE + 1) * 8));
   JP_CUDA(jp_dmalloc(ctx, &s->d_work, (size_t)s->glm_blocks * (nE + 1) * 8));
-  JP_CUDA(jp_dmalloc(ctx, &s->d_bounds, (size_t)TC_PREP_BLOCKS * TC_NBOUND * 8));
+  JP_CUDA(jp_dmalloc(ctx, &s->d_bounds, (size_t)TC_PREP_BLOCKS_MAX * TC_NBOUND * 8));
+  {
+    const long long slice_tiles = s->n_loc / TC_OBS_TILE;
+    s->prep_blocks = (int)(slice_tiles <= TC_PREP_BLOCKS_MAX ? std::max<long long>(1, slice_tiles) : TC_PREP_BLOCKS);
+  }
   const unsigned split_blocks = (unsigned)std::min<long long>((s->N_pad + TC_SPLIT_ROWS - 1) / TC_SPLIT_ROWS, (long long)ctx->sm_count * 32);
   tc_split_x_kernel<<<split_blocks, dim3(s->kp, TC_SPLIT_ROWS), 0, ctx->stream>>>(d, data->ncols, s->kp, s->split, s->N, s->N_pad,
                                                                                   data->d_obs, s->d_xs);
@@ -1284,15 +1252,27 @@ static int tc_prep_slice(jp_posterior* post, const jp_fit_args* args, int rank, 
   TcDataState* ds = static_cast<TcDataState*>(data->tc_state);
   const int d = args->d, p = args->p;
   const long long o0 = std::min(data->N, (long long)rank * ds->n_loc), o1 = std::min(data->N, o0 + ds->n_loc);
-  JP_TRY(jp_glm_sums_device_range(ctx, data, d, post->d_mu, d_sums, ds->d_work, ds->glm_blocks, o0, o1));
+  // The two O(N) passes over the slice are independent (sums g, H, L_hat | per-observation coefficients and bounds): the
+  // coefficient pass runs on the context's side stream, forked here; the caller joins (tc_join_side) before anything reads
+  // its results on the main stream.
+  JP_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  JP_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
   const double z_max = std::sqrt(post->grid->zmax2), z_ref = std::min(z_max, 6.0);
   const size_t sm_obs = (size_t)(((d + 1) & ~1) + d * ((p + 3) & ~3) + 2 * TC_PREP_THREADS * (data->ncols | 1)) * 8;
   if (sm_obs > 48 * 1024)
     JP_CUDA(cudaFuncSetAttribute(tc_obs_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_obs));
-  tc_obs_prep_kernel<<<TC_PREP_BLOCKS, TC_PREP_THREADS, sm_obs, ctx->stream>>>(
+  tc_obs_prep_kernel<<<ds->prep_blocks, TC_PREP_THREADS, sm_obs, ctx->side>>>(
       data->family, d, p, data->ncols, o1 - o0, ds->n_loc, data->d_obs + (size_t)o0 * data->ncols, post->d_mu, post->d_U, z_ref,
       z_max, ds->d_coef, ds->n_loc, ds->d_bounds);
   JP_CHECK_LAUNCH(ctx);
+  JP_TRY(jp_glm_sums_device_range(ctx, data, d, post->d_mu, d_sums, ds->d_work, ds->glm_blocks, o0, o1));
+  return JP_OK;
+}
+
+// the main stream waits for everything queued on the side stream so far
+static int tc_join_side(jp_ctx* ctx) {
+  JP_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
+  JP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
   return JP_OK;
 }
 
@@ -1345,7 +1325,7 @@ static int tc_node_prep(jp_posterior* post, const jp_fit_args* args) {
 }
 
 // the tensor-core kernel and the per-node finish (after tc_node_prep)
-static int tc_run_kernel(jp_posterior* post, const jp_fit_args* args, int NC) {
+static int tc_run_kernel(jp_posterior* post, const jp_fit_args* args, int NC, bool finish) {
   jp_ctx* ctx = post->ctx;
   const jp_data* data = post->data;
   TcDataState* ds = static_cast<TcDataState*>(data->tc_state);
@@ -1412,32 +1392,40 @@ static int tc_run_kernel(jp_posterior* post, const jp_fit_args* args, int NC) {
   else if (NC == 10) stc = launch_tc<10>(ctx, ds->tmA, ps->tmB, kp, smem);
   else stc = launch_tc<12>(ctx, ds->tmA, ps->tmB, kp, smem);
   JP_TRY(stc);
-  tc_finish_kernel<<<(unsigned)((post->M + 255) / 256), 256, 0, st>>>(post->M, post->m0, ps->j_lo, ps->P, kp.chunks, ps->d_part, ps->d_quad,
-                                                                       post->grid->d_hzz, args->neg_min, post->d_logdens,
-                                                                       post->d_a);
-  JP_CHECK_LAUNCH(ctx);
   post->path_used = JP_PATH_TC;
+  post->fin = JpFinish();
+  post->fin.path = JP_PATH_TC; post->fin.chunks = kp.chunks; post->fin.P = ps->P; post->fin.j_lo = ps->j_lo;
+  post->fin.tc_part = ps->d_part; post->fin.quad = ps->d_quad; post->fin.neg_min = args->neg_min;
+  if (finish) {
+    tc_finish_kernel<<<(unsigned)((post->M + 255) / 256), 256, 0, st>>>(post->M, post->m0, ps->j_lo, ps->P, kp.chunks, ps->d_part,
+                                                                         ps->d_quad, post->grid->d_hzz, args->neg_min, post->d_logdens,
+                                                                         post->d_a);
+    JP_CHECK_LAUNCH(ctx);
+    post->fin.path = 0;
+  }
   return JP_OK;
 }
 
-static int tc_run(jp_posterior* post, const jp_fit_args* args, int NC) {
+static int tc_run(jp_posterior* post, const jp_fit_args* args, int NC, bool finish) {
   TcPostState* ps = static_cast<TcPostState*>(post->tc_state);
   if (!ps->node_prep_queued) JP_TRY(tc_node_prep(post, args));
   ps->node_prep_queued = false;
-  return tc_run_kernel(post, args, NC);
+  return tc_run_kernel(post, args, NC, finish);
 }
 
-// bounds of the blocks of one prep launch -> b[TC_NBOUND] on the host ([0] a maximum, the rest sums in block order)
-static void tc_reduce_block_bounds(const double* hb, double* b) {
-  for (int j = 0; j < TC_NBOUND; ++j) b[j] = 0;
-  for (int blk = 0; blk < TC_PREP_BLOCKS; ++blk) {
-    const double* o = hb + (size_t)blk * TC_NBOUND;
-    b[0] = std::max(b[0], o[0]);
-    for (int j = 1; j < TC_NBOUND; ++j) b[j] += o[j];
+// reduce the block partials of the bounds on the device (block order; [0] is a maximum)
+__global__ void tc_bounds_reduce_kernel(const double* __restrict__ blocks, int nblocks, double* __restrict__ out) {
+  const int j = threadIdx.x;
+  if (j >= TC_NBOUND) return;
+  double v = 0;
+  for (int blk = 0; blk < nblocks; ++blk) {
+    const double o = blocks[(size_t)blk * TC_NBOUND + j];
+    v = (j == 0) ? fmax(v, o) : v + o;
   }
+  out[j] = v;
 }
 
-int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
+int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args, bool finish) {
   jp_ctx* ctx = post->ctx;
   JP_TRY(tc_setup(post, args, 1, 0));
   TcDataState* ds = static_cast<TcDataState*>(post->data->tc_state);
@@ -1449,36 +1437,31 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args) {
     sscanf(assume, "%d,%d", &nc, &fd);
     post->tc_bounds[3] = nc; post->tc_bounds[5] = fd;
     JP_TRY(tc_node_prep(post, args));
+    JP_TRY(tc_join_side(ctx));
     if (fd) JP_TRY(tc_fold_slice(post, nc));
-    return tc_run_kernel(post, args, nc);
+    return tc_run_kernel(post, args, nc, finish);
   }
+  // side stream: block bounds -> 22 numbers -> pinned host memory; main stream meanwhile: sums, then the node operand
+  // (tc_node_prep needs g, H only).  The host's wait for the bounds is hidden under both (measured: skipping it with
+  // JP_TC_ASSUME changes the fit time by < 5 us).
   double* hb = ctx->h_pinned + JP_PINNED_BOUNDS_OFF;   // away from the constants staged by jp_upload_fit_consts
-  JP_CUDA(cudaMemcpyAsync(hb, ds->d_bounds, (size_t)TC_PREP_BLOCKS * TC_NBOUND * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  JP_CUDA(cudaEventRecord(ds->ev_bounds, ctx->stream));
-  JP_TRY(tc_node_prep(post, args));                     // queued behind the copy: runs while the host waits and decides
+  tc_bounds_reduce_kernel<<<1, 32, 0, ctx->side>>>(ds->d_bounds, ds->prep_blocks, ds->d_comb);
+  JP_CHECK_LAUNCH(ctx);
+  JP_CUDA(cudaMemcpyAsync(hb, ds->d_comb, (size_t)TC_NBOUND * 8, cudaMemcpyDeviceToHost, ctx->side));
+  JP_CUDA(cudaEventRecord(ds->ev_bounds, ctx->side));
+  JP_TRY(tc_node_prep(post, args));
   JP_CUDA(cudaEventSynchronize(ds->ev_bounds));
+  JP_TRY(tc_join_side(ctx));
   double b[TC_NBOUND];
-  tc_reduce_block_bounds(hb, b);
+  for (int j = 0; j < TC_NBOUND; ++j) b[j] = hb[j];
   int NC = 0, fold = 0;
   JP_TRY(tc_decide(post, b, &NC, &fold));
   if (fold) JP_TRY(tc_fold_slice(post, NC));
-  return tc_run_kernel(post, args, NC);
+  return tc_run_kernel(post, args, NC, finish);
 }
 
 // ---- sharded prep, phase by phase (extern "C" wrappers in jp_fit.cu).  L = nE + 1 + TC_NBOUND doubles per rank.
 int jp_fit_tc_prep_len(int d) { return d + d * (d + 1) / 2 + 1 + TC_NBOUND; }
-
-// reduce the block partials of the bounds on the device (block order; [0] is a maximum)
-__global__ void tc_bounds_reduce_kernel(const double* __restrict__ blocks, double* __restrict__ out) {
-  const int j = threadIdx.x;
-  if (j >= TC_NBOUND) return;
-  double v = 0;
-  for (int blk = 0; blk < TC_PREP_BLOCKS; ++blk) {
-    const double o = blocks[(size_t)blk * TC_NBOUND + j];
-    v = (j == 0) ? fmax(v, o) : v + o;
-  }
-  out[j] = v;
-}
 
 // phase 1: this rank's observation slice -> d_out[L] = (local g, H, L_hat | local bounds); asynchronous
 int jp_fit_tc_prep_local(jp_posterior* post, const jp_fit_args* args, int rank, int world, double* d_out) {
@@ -1487,8 +1470,9 @@ int jp_fit_tc_prep_local(jp_posterior* post, const jp_fit_args* args, int rank, 
   TcDataState* ds = static_cast<TcDataState*>(post->data->tc_state);
   const int nE1 = args->d + args->d * (args->d + 1) / 2 + 1;
   JP_TRY(tc_prep_slice(post, args, rank, d_out));
-  tc_bounds_reduce_kernel<<<1, 32, 0, post->ctx->stream>>>(ds->d_bounds, d_out + nE1);
+  tc_bounds_reduce_kernel<<<1, 32, 0, post->ctx->side>>>(ds->d_bounds, ds->prep_blocks, d_out + nE1);
   JP_CHECK_LAUNCH(post->ctx);
+  JP_TRY(tc_join_side(post->ctx));      // the caller's collective reads d_out on the main stream
   return JP_OK;
 }
 
@@ -1555,7 +1539,7 @@ int jp_fit_tc_coef_slab(jp_posterior* post, int n_rows, float** d_local, float**
 }
 
 // phase 3 (after the rows are exchanged): stages 2-3 of this rank's node block
-int jp_fit_tc_run_prepared(jp_posterior* post, const jp_fit_args* args) {
+int jp_fit_tc_run_prepared(jp_posterior* post, const jp_fit_args* args, bool finish) {
   JP_REQUIRE(post->tc_bounds[3] >= 4, "jp_fit_run_prepared: no series length has been decided (call the prep phases first)");
-  return tc_run(post, args, (int)post->tc_bounds[3]);
+  return tc_run(post, args, (int)post->tc_bounds[3], finish);
 }

@@ -506,10 +506,11 @@ static int set_value_pointers(jp_posterior* post, int K, const int* h_coords, co
   }
   // the same columns as last time (every coordinate after each fit, say): the table on the device is already right
   if (post->vptr_host.size() < (size_t)K || !std::equal(want.begin(), want.end(), post->vptr_host.begin())) {
-    JP_CUDA(cudaStreamSynchronize(ctx->stream));   // pinned staging reuse
+    JP_CUDA(jp_pinned_acquire(ctx));
     const double** hp = reinterpret_cast<const double**>(ctx->h_pinned);
     std::copy(want.begin(), want.end(), hp);
     JP_CUDA(cudaMemcpyAsync((void*)post->d_vptr, hp, (size_t)K * sizeof(double*), cudaMemcpyHostToDevice, ctx->stream));
+    JP_CUDA(jp_pinned_publish(ctx));
     post->vptr_host = want;
   }
   post->sorted_valid = false;

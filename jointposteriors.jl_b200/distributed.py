@@ -320,3 +320,64 @@ def marginals_sharded(local, coords, group=None, gather=None):
     gm = gather(local.moments(coords), group)                   # [world, K, 4] = (sum w v, sum w v^2, min, max)
     gc = gather(local.knots_gathered(coords, gm), group)        # [world, K, 98, 6]
     return local.combine_gathered(gm, gc)
+
+
+# ----------------------------------------------------------------------------- the public multi-GPU call
+class ShardedPosterior:
+    """Result of `fit_distributed`: this rank's block of the joint posterior (reference struct JointPosterior,
+    src/joint_posterior.jl:2-8, restricted to the nodes [begin, end)) plus what is needed to answer `marginal` globally.
+    Every rank holds bit-identical global scalars, moments, knots and quantiles."""
+
+    def __init__(self, post, local, group, bounds, prep):
+        self.post, self.local, self.group, self.bounds, self.prep = post, local, group, bounds, prep
+        self.M, self.mu_hat, self.U = post.M, post.mu_hat, post.U
+
+    @property
+    def density(self):
+        """This rank's block of the normalised weights (global normalisation)."""
+        return self.post.density
+
+    @property
+    def Theta(self):
+        return self.post.Theta
+
+    def marginals(self, coords):
+        """Global marginal(jp, f) of coordinate selectors: two all_gathers per batch, no global sort."""
+        from .marginals import Grid, marginal_result
+        coords = [int(c) for c in coords]
+        mu, sg, vn, wn = marginals_sharded(self.local, coords, self.group)
+        return [marginal_result(None, j, mu[j], sg[j], Grid(wn[j].copy(), vn[j].copy())) for j in range(len(coords))]
+
+    def marginal(self, k):
+        return self.marginals([k])[0]
+
+    def free(self):
+        self.post.free()
+
+
+def fit_distributed(M, data, n=None, group=None, path=None, mode_result=None):
+    """fit(M, data[, n]) (reference src/joint_posterior.jl:177-188) with the grid nodes sharded over the ranks of `group`
+    (one process per GPU, torch.distributed initialised by the caller): row-sharded upload + NVLink all_gather of the
+    records, the mode on every rank (deterministic: identical everywhere), this rank's node block through stages 2-3, the
+    global normalisation through one all_gather (plus the two of the observation-sharded tensor-core prep)."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    from .model import DeviceData, JointPosterior, colmajor, default, mode
+    ctx = M.ctx
+    dev = torch.device("cuda", ctx.device)
+    ctx.use_stream(torch.cuda.current_stream(dev).cuda_stream)      # collectives and kernels on one stream
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    ddata = data if isinstance(data, DeviceData) else ctx.upload_sharded(data, group)
+    if n is None:
+        n = default(M.build)
+    mu_hat, U, neg_min = mode(M, ddata) if mode_result is None else mode_result
+    U = colmajor(U)
+    grid = ctx.grid(M.build.rule.rule_id, U.shape[1], int(n))
+    Mtot = int(lib().jp_grid_size(grid))
+    b, e = shard_bounds(Mtot, rank, world)
+    post = JointPosterior(M, ddata, grid, mu_hat, U, neg_min, path=_lib.PATH_AUTO if path is None else path, node_range=(b, e))
+    local = CudaLocal(post)
+    fit_sharded(local, group)
+    return ShardedPosterior(post, local, group, (b, e), getattr(local, "last_prep", "replicated"))

@@ -130,6 +130,8 @@ class Context:
         import torch
         obs, hyper = data.records()
         dev = torch.device("cuda", self.device)
+        # the gather runs on torch's current stream; the library's kernels must be ordered behind it
+        self.use_stream(torch.cuda.current_stream(dev).cuda_stream)
         full = D.gather_rows(obs, dev, group)
         return DeviceData(self, data, device_obs=full)
 

@@ -4,7 +4,7 @@ TAG=$1; A=$2; B=$3; shift 3
 mkdir -p gpurun_out
 for L in $A $B; do
   n=$(basename $L .so)
-  JPCUDA_LIB=$PWD/$L timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/${TAG}_$n.json 2> gpurun_out/${TAG}_$n.err
+  JPCUDA_LIB=$PWD/$L timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --strong none "$@" > gpurun_out/${TAG}_$n.json 2> gpurun_out/${TAG}_$n.err
   echo "$n exit $?"; tail -2 gpurun_out/${TAG}_$n.err
   python - <<PY
 import json

@@ -4,7 +4,7 @@ TAG=$1; ARGS=$2; shift 2
 mkdir -p gpurun_out
 for L in "$@"; do
   n=$(basename $L .so)
-  JPCUDA_LIB=$PWD/$L timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline $ARGS > gpurun_out/${TAG}_$n.json 2> gpurun_out/${TAG}_$n.err
+  JPCUDA_LIB=$PWD/$L timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --strong none $ARGS > gpurun_out/${TAG}_$n.json 2> gpurun_out/${TAG}_$n.err
   echo "$n exit $?"; tail -2 gpurun_out/${TAG}_$n.err
   python - <<PY
 import json

@@ -12,7 +12,7 @@ timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 
 echo "bench exit $?" >> gpurun_out/${TAG}_bench.err
 tail -5 gpurun_out/${TAG}_pytest.log; cat gpurun_out/${TAG}_smoke.log | tail -5; cat gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err
 if [ "${NCU:-0}" = "1" ]; then
-  BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --path ${NCU_PATH:-auto}"
+  BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --strong none --path ${NCU_PATH:-auto}"
   $BENCH > gpurun_out/${TAG}_ncu_plain.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv $BENCH > gpurun_out/${TAG}_ncu_list.log 2>&1
   echo "ncu list exit $?"
