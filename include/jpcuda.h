@@ -115,6 +115,11 @@ int jp_ctx_set_stream(jp_ctx* ctx, void* cuda_stream);
 int jp_ctx_sync(jp_ctx* ctx);
 /* number of kernels this ctx has launched since creation (for bench.py's gpu_launches) */
 long long jp_ctx_launch_count(const jp_ctx* ctx);
+/* Stage tracing: jp_ctx_trace(ctx, 1) clears the trace and makes the entry points record CUDA events at their phase
+ * boundaries (on the stream the phase runs on); jp_ctx_trace_dump synchronises and writes one "name<TAB>microseconds since
+ * the first mark" line per event into buf.  jp_ctx_trace(ctx, 0) switches it off.  Diagnostic; not thread-safe. */
+int jp_ctx_trace(jp_ctx* ctx, int on);
+int jp_ctx_trace_dump(jp_ctx* ctx, char* buf, int len);
 /* device time (CUDA events on the ctx stream) of the most recent launch of the dominant kernel of the path:
  * the node x observation log-density kernel of jp_fit (FP64 plugin kernel or tcgen05 GLM kernel).  Blocking. */
 int jp_ctx_last_kernel_ms(jp_ctx* ctx, float* ms);

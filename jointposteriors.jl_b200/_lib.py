@@ -61,7 +61,7 @@ SYMBOLS = [
     "jp_last_error", "jp_version",
     "jp_chol", "jp_try_chol", "jp_inv_upper", "jp_inv_chol", "jp_reduce_dimensions", "jp_reduce_dimensions_ldr", "jp_deduce_scale_dynamic",
     "jp_ctx_create", "jp_ctx_destroy", "jp_ctx_set_stream", "jp_ctx_sync", "jp_ctx_launch_count",
-    "jp_ctx_last_kernel_ms",
+    "jp_ctx_last_kernel_ms", "jp_ctx_trace", "jp_ctx_trace_dump",
     "jp_grid_get", "jp_grid_size", "jp_grid_dim", "jp_grid_build_stats", "jp_grid_download", "jp_rule_info", "jp_rule_level_nodes",
     "jp_grid_level_cap",
     "jp_data_upload", "jp_data_adopt_device", "jp_data_free", "jp_glm_grad_hess", "jp_log_density_points", "jp_mode",

@@ -46,6 +46,8 @@ int jp_ctx_create(int device, jp_ctx** out) {
   JP_CUDA(jp_dmalloc(ctx, &ctx->d_bpart, sizeof(double) * JP_BPART_DOUBLES));
   JP_CUDA(cudaMallocHost(&ctx->h_pinned, sizeof(double) * JP_PINNED_DOUBLES));
   JP_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+  JP_CUDA(cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking));
+  JP_CUDA(cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming));
   JP_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   JP_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   JP_CUDA(cudaEventCreateWithFlags(&ctx->ev_pinned, cudaEventDisableTiming));
@@ -74,6 +76,9 @@ int jp_ctx_destroy(jp_ctx* ctx) {
   cudaFree(ctx->d_rule_nodes[0]); cudaFree(ctx->d_rule_nodes[1]);
   cudaStreamSynchronize(ctx->side);
   cudaStreamDestroy(ctx->side);
+  cudaStreamSynchronize(ctx->side2);
+  cudaStreamDestroy(ctx->side2);
+  cudaEventDestroy(ctx->ev_join2);
   cudaEventDestroy(ctx->ev_fork);
   cudaEventDestroy(ctx->ev_join);
   cudaEventDestroy(ctx->ev_pinned);
@@ -100,6 +105,34 @@ int jp_ctx_sync(jp_ctx* ctx) {
 }
 
 long long jp_ctx_launch_count(const jp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int jp_ctx_trace(jp_ctx* ctx, int on) {
+  JP_REQUIRE(ctx, "jp_ctx_trace: null ctx");
+  for (auto& m : ctx->trace.marks) cudaEventDestroy(m.second);
+  ctx->trace.marks.clear();
+  ctx->trace.on = on != 0;
+  return JP_OK;
+}
+
+int jp_ctx_trace_dump(jp_ctx* ctx, char* buf, int len) {
+  JP_REQUIRE(ctx && buf && len > 0, "jp_ctx_trace_dump: bad argument");
+  JP_CUDA(cudaStreamSynchronize(ctx->stream));
+  JP_CUDA(cudaStreamSynchronize(ctx->side));
+  JP_CUDA(cudaStreamSynchronize(ctx->side2));
+  int pos = 0;
+  buf[0] = 0;
+  for (size_t i = 0; i < ctx->trace.marks.size(); ++i) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->trace.marks[0].second, ctx->trace.marks[i].second) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    int n = snprintf(buf + pos, (size_t)(len - pos), "%s\t%.1f\n", ctx->trace.marks[i].first, ms * 1e3);
+    if (n < 0 || n >= len - pos) break;
+    pos += n;
+  }
+  return JP_OK;
+}
 
 int jp_ctx_last_kernel_ms(jp_ctx* ctx, float* ms) {
   JP_REQUIRE(ctx && ms, "jp_ctx_last_kernel_ms: null argument");
@@ -281,6 +314,7 @@ int jp_posterior_free(jp_posterior* p) {
   jp_dfree(c, p->d_stats); jp_dfree(c, p->d_mu); jp_dfree(c, p->d_U); jp_dfree(c, p->d_tcode); jp_tc_post_free(p);
   jp_dfree(c, p->d_vals); jp_dfree(c, p->d_bins); jp_dfree(c, (void*)p->d_vptr); jp_dfree(c, p->d_perm_a); jp_dfree(c, p->d_perm_b); jp_dfree(c, p->d_hist);
   jp_dfree(c, p->d_sv); jp_dfree(c, p->d_sw); jp_dfree(c, p->d_cw); jp_dfree(c, p->d_mout);
+  jp_dfree(c, p->d_cmom); jp_dfree(c, p->d_coords);
   delete p;
   return JP_OK;
 }

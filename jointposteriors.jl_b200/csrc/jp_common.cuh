@@ -67,8 +67,16 @@ struct jp_grid {
   double zmax2 = 0;           // max_m |z_m|^2
 };
 
+// Stage tracing (the reference has none): when switched on (jp_ctx_trace), entry points drop CUDA events
+// at their phase boundaries on whichever stream the phase runs on; jp_ctx_trace_dump turns them into a timeline.
+struct JpTrace {
+  bool on = false;
+  std::vector<std::pair<const char*, cudaEvent_t>> marks;
+};
+
 struct jp_ctx {
   int device = 0;
+  JpTrace trace;
   int sm_count = JP_NUM_SMS_B200;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -83,8 +91,9 @@ struct jp_ctx {
   double* d_bpart = nullptr;       // JP_BPART_DOUBLES per-block partials of those reductions
   // __constant__ tables and the device copy of the master node tables are PER DEVICE: every context uploads its own
   // (several GPUs in one process each get theirs; a second context on the same device re-uploads identical bytes)
-  cudaStream_t side = nullptr;       // second stream of the context: independent O(N) prep kernels of a fit overlap on it
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t side = nullptr, side2 = nullptr;   // further streams of the context: the independent O(N) passes of a fit's
+                                                  // preparation overlap on them (forked from / joined into `stream`)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
   cudaEvent_t ev_pinned = nullptr;   // recorded after the last asynchronous copy OUT of h_pinned (see jp_pinned_acquire)
   bool pinned_busy = false;
   bool rules_uploaded = false, fit_nodes_uploaded = false, tc_tables_uploaded = false;
@@ -115,6 +124,15 @@ inline cudaError_t jp_pinned_publish(jp_ctx* ctx) {
   ctx->pinned_busy = true;
   return cudaEventRecord(ctx->ev_pinned, ctx->stream);
 }
+inline void jp_trace_mark(jp_ctx* ctx, const char* name, cudaStream_t st) {
+  if (!ctx->trace.on) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  ctx->trace.marks.emplace_back(name, e);
+}
+#define JP_MARK(ctx, name) jp_trace_mark((ctx), (name), (ctx)->stream)
+#define JP_MARK_SIDE(ctx, name) jp_trace_mark((ctx), (name), (ctx)->side)
 #define JP_SCRATCH_DOUBLES (1 << 16)
 #define JP_PINNED_DOUBLES (1 << 18)   // 2 MB: result vectors of up to 262 144 nodes are downloaded through it
 // Fixed sub-regions of the pinned staging buffer.  [0, JP_PINNED_CONSTS_END): the per-fit constants (mu d, U d x p, transform
@@ -164,6 +182,13 @@ struct jp_posterior {
   double* d_density = nullptr;   // normalised weights
   double* d_part = nullptr;      // (JP_POST_PART_SPLITS + 1) x M doubles, see below
   double* d_stats = nullptr;     // [0]=max, [1]=sum (device scalars for the single-GPU path)
+  // per stage-4 block and coordinate: (sum w theta, sum w theta^2, min theta, max theta), left by the fused stage-4 kernel of a
+  // single-GPU fit; coordinate marginals then need ONE launch (jp_marginal_onepass_kernel)
+  double* d_cmom = nullptr;
+  int cmom_blocks = 0, cmom_cap = 0;
+  bool cmom_valid = false;
+  int* d_coords = nullptr;       // coordinates of the last one-pass marginal batch on the device
+  std::vector<int> coords_host;
   void* tc_state = nullptr;      // TC path: node operand, tensor map, quadratic part (jp_glm_tc.cu)
   double tc_bounds[8] = {0};     // TC path diagnostics of the last fit: max|Delta|, truncation bound, rounding
                                  // estimate, series coefficients used, worst-case rounding bound

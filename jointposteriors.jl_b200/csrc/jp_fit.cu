@@ -274,7 +274,13 @@ struct Stage4Params {
   double* bsum;       // [gridDim.x]
   double* stats;      // [2]: max, sum
   int normalise;
+  // single-GPU fits also leave the per-block, per-coordinate (sum w theta, sum w theta^2, min, max) for stage 5
+  const double* theta;   // [d][M]
+  int d;
+  double* cmom;          // [gridDim.x][d][4] or null
 };
+// per-coordinate block reduction of two values per thread: warp shuffles, one barrier, warps combined in warp order
+#define JP_S4_WARPS (JP_S4_THREADS / 32)
 __global__ void __launch_bounds__(JP_S4_THREADS) jp_stage4_kernel(const Stage4Params P) {
   __shared__ double sm[33];
   cg::grid_group grid = cg::this_grid();
@@ -306,6 +312,29 @@ __global__ void __launch_bounds__(JP_S4_THREADS) jp_stage4_kernel(const Stage4Pa
   }
   mx = jp_block_max(mx, sm);
   if (threadIdx.x == 0) P.bmax[blockIdx.x] = mx;
+  __shared__ double s_co[2][JP_S4_WARPS][JP_MAX_D];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (P.cmom) {      // extrema of every coordinate over this block's slice (they do not depend on the weights)
+    for (int k = 0; k < P.d; ++k) {
+      const double* th = P.theta + (size_t)k * P.M;
+      double mn = INFINITY, mxk = -INFINITY;
+      for (long long m = b0 + threadIdx.x; m < b1; m += JP_S4_THREADS) {
+        const double v = th[m];
+        mn = fmin(mn, v);
+        mxk = fmax(mxk, v);
+      }
+      mn = jp_warp_min(mn);
+      mxk = jp_warp_max(mxk);
+      if (lane == 0) { s_co[0][wid][k] = mn; s_co[1][wid][k] = mxk; }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < P.d; k += JP_S4_THREADS) {
+      double mn = s_co[0][0][k], mxk = s_co[1][0][k];
+      for (int i = 1; i < JP_S4_WARPS; ++i) { mn = fmin(mn, s_co[0][i][k]); mxk = fmax(mxk, s_co[1][i][k]); }
+      double* o = P.cmom + ((size_t)blockIdx.x * P.d + k) * 4;
+      o[2] = mn; o[3] = mxk;
+    }
+  }
   grid.sync();
   // ---- B
   double g = -INFINITY;
@@ -331,6 +360,27 @@ __global__ void __launch_bounds__(JP_S4_THREADS) jp_stage4_kernel(const Stage4Pa
   if (!P.normalise) return;
   const double tot = sm[32];
   for (long long m = b0 + threadIdx.x; m < b1; m += JP_S4_THREADS) P.e[m] = P.e[m] / tot;
+  if (!P.cmom) return;
+  // weighted moments of every coordinate over this block's slice (each thread re-reads the weights it just wrote)
+  for (int k = 0; k < P.d; ++k) {
+    const double* th = P.theta + (size_t)k * P.M;
+    double s1 = 0, s2 = 0;
+    for (long long m = b0 + threadIdx.x; m < b1; m += JP_S4_THREADS) {
+      const double v = th[m], wv = P.e[m];
+      s1 += wv * v;
+      s2 += wv * (v * v);
+    }
+    s1 = jp_warp_sum(s1);
+    s2 = jp_warp_sum(s2);
+    if (lane == 0) { s_co[0][wid][k] = s1; s_co[1][wid][k] = s2; }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < P.d; k += JP_S4_THREADS) {
+    double s1 = 0, s2 = 0;
+    for (int i = 0; i < JP_S4_WARPS; ++i) { s1 += s_co[0][i][k]; s2 += s_co[1][i][k]; }
+    double* o = P.cmom + ((size_t)blockIdx.x * P.d + k) * 4;
+    o[0] = s1; o[1] = s2;
+  }
 }
 
 // ------------------------------------------------------------------------------------ registry
@@ -500,15 +550,36 @@ static int jp_stage4_launch(jp_posterior* post, bool normalise, double* d_stats)
   P.M = post->M; P.m0 = post->m0; P.fin = post->fin;
   P.hzz = post->grid->d_hzz; P.w = post->grid->d_w;
   P.logdens = post->d_logdens; P.a = post->d_a; P.e = post->d_density;
-  // one block per 512 nodes, at most two per SM (co-resident by a wide margin: 256 threads, 264 bytes of shared memory)
-  const int nb = (int)std::max<long long>(1, std::min<long long>(2LL * ctx->sm_count, (post->M + 511) / 512));
+  // one node per thread up to six blocks per SM (the phases are latency chains: parallelism, not bytes, is what they need);
+  // co-resident by a wide margin (256 threads, 8 KB of shared memory)
+  static int per_sm = 0;      // co-resident blocks per SM of this kernel (a property of the build, not of the device instance)
+  if (per_sm == 0) {
+    JP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jp_stage4_kernel, JP_S4_THREADS, 0));
+    per_sm = std::max(1, std::min(per_sm, 6));
+  }
+  const int nb = (int)std::max<long long>(1, std::min<long long>((long long)per_sm * ctx->sm_count, (post->M + JP_S4_THREADS - 1) / JP_S4_THREADS));
   JP_REQUIRE(2 * nb <= JP_BPART_DOUBLES, "stage 4: %d blocks exceed the partial buffer", nb);
   P.bmax = ctx->d_bpart; P.bsum = ctx->d_bpart + nb;
   P.stats = d_stats;
   P.normalise = normalise ? 1 : 0;
+  P.theta = post->d_theta; P.d = post->d; P.cmom = nullptr;
+  post->cmom_valid = false;
+  if (normalise && post->M >= 2) {
+    if (nb > post->cmom_cap) {
+      jp_dfree(ctx, post->d_cmom);
+      post->d_cmom = nullptr;
+      post->cmom_cap = 0;
+      JP_CUDA(jp_dmalloc(ctx, &post->d_cmom, (size_t)nb * post->d * 4 * 8));
+      post->cmom_cap = nb;
+    }
+    P.cmom = post->d_cmom;
+    post->cmom_blocks = nb;
+    post->cmom_valid = true;
+  }
   void* kargs[] = {(void*)&P};
   JP_CUDA(cudaLaunchCooperativeKernel((const void*)jp_stage4_kernel, dim3(nb), dim3(JP_S4_THREADS), kargs, 0, ctx->stream));
   JP_CHECK_LAUNCH(ctx);
+  JP_MARK(ctx, "fit:stage4");
   post->fin.path = 0;
   return JP_OK;
 }
@@ -517,6 +588,7 @@ static int jp_stage4_launch(jp_posterior* post, bool normalise, double* d_stats)
 static int jp_fit_launch_path(jp_posterior* post, const jp_fit_args* args, bool finish) {
   post->sorted_valid = false;      // the sorted arrays / marginals of an earlier fit no longer describe this posterior
   post->K_last = 0;
+  post->cmom_valid = false;
   // AUTO: GLM families take the tensor-core path when its a-priori error bounds hold for this
   // (data, U, grid); otherwise, and for every other family, the FP64 plugin kernel runs.
   int path = args->path;

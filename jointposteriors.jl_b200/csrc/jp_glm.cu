@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(256) jp_glm_combine_kernel(int nblocks, int nE
 
 // device-side entry used by both the C ABI and the TC path: packed sums into d_out[nE + 1]
 template <int BS, int JP_GLM_THREADS>
-static int launch_partials(jp_ctx* ctx, const jp_data* data, int d, const double* d_beta, double* d_work, int nblocks, int nE,
-                           long long o0, long long o1) {
+static int launch_partials(jp_ctx* ctx, cudaStream_t stream, const jp_data* data, int d, const double* d_beta, double* d_work,
+                           int nblocks, int nE, long long o0, long long o1) {
   const int nb = (d + BS - 1) / BS, npairs = nb * (nb + 1) / 2, rs = nb * BS + 2;
   const int S = std::min(JP_GLM_THREADS / npairs, JP_GLM_TILE);
   // the slice buffer of the final reduction reuses the tiles
@@ -196,27 +196,31 @@ static int launch_partials(jp_ctx* ctx, const jp_data* data, int d, const double
   size_t smem = (tile_doubles + 4 * JP_GLM_TILE + d) * sizeof(double);
   if (smem > 48 * 1024)
     JP_CUDA(cudaFuncSetAttribute(jp_glm_partials_kernel<BS, JP_GLM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  jp_glm_partials_kernel<BS, JP_GLM_THREADS><<<nblocks, JP_GLM_THREADS, smem, ctx->stream>>>(
+  jp_glm_partials_kernel<BS, JP_GLM_THREADS><<<nblocks, JP_GLM_THREADS, smem, stream>>>(
       data->family, d, o1 - o0, data->d_obs + (size_t)o0 * data->ncols, d_beta, nE, d_work);
   JP_CHECK_LAUNCH(ctx);
   return JP_OK;
 }
 
 // sums over the observation rows [o0, o1) (the whole data set: 0, N)
-int jp_glm_sums_device_range(jp_ctx* ctx, const jp_data* data, int d, const double* d_beta, double* d_out, double* d_work,
-                             int nblocks, long long o0, long long o1) {
+int jp_glm_sums_device_range_on(jp_ctx* ctx, cudaStream_t stream, const jp_data* data, int d, const double* d_beta, double* d_out,
+                                double* d_work, int nblocks, long long o0, long long o1) {
   int nE = d + d * (d + 1) / 2;
   if (o1 <= o0) {      // an empty slice (more ranks than observation tiles) contributes zeros
-    JP_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * (nE + 1), ctx->stream));
+    JP_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * (nE + 1), stream));
     return JP_OK;
   }
   // 8 x 8 register blocks unless the padding to a multiple of 8 would waste more than it saves
-  const int st = (d > 16) ? (launch_partials<8, 128>)(ctx, data, d, d_beta, d_work, nblocks, nE, o0, o1)
-                          : (launch_partials<4, 256>)(ctx, data, d, d_beta, d_work, nblocks, nE, o0, o1);
+  const int st = (d > 16) ? (launch_partials<8, 128>)(ctx, stream, data, d, d_beta, d_work, nblocks, nE, o0, o1)
+                          : (launch_partials<4, 256>)(ctx, stream, data, d, d_beta, d_work, nblocks, nE, o0, o1);
   JP_TRY(st);
-  jp_glm_combine_kernel<<<(nE + 1 + 7) / 8, 256, 0, ctx->stream>>>(nblocks, nE + 1, d_work, d_out);
+  jp_glm_combine_kernel<<<(nE + 1 + 7) / 8, 256, 0, stream>>>(nblocks, nE + 1, d_work, d_out);
   JP_CHECK_LAUNCH(ctx);
   return JP_OK;
+}
+int jp_glm_sums_device_range(jp_ctx* ctx, const jp_data* data, int d, const double* d_beta, double* d_out, double* d_work,
+                             int nblocks, long long o0, long long o1) {
+  return jp_glm_sums_device_range_on(ctx, ctx->stream, data, d, d_beta, d_out, d_work, nblocks, o0, o1);
 }
 
 int jp_glm_sums_device(jp_ctx* ctx, const jp_data* data, int d, const double* d_beta, double* d_out, double* d_work,

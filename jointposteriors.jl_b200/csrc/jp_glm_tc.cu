@@ -48,8 +48,8 @@
 
 int jp_glm_sums_device(jp_ctx* ctx, const jp_data* data, int d, const double* d_beta, double* d_out, double* d_work,
                        int nblocks);
-int jp_glm_sums_device_range(jp_ctx* ctx, const jp_data* data, int d, const double* d_beta, double* d_out, double* d_work,
-                             int nblocks, long long o0, long long o1);
+int jp_glm_sums_device_range_on(jp_ctx* ctx, cudaStream_t stream, const jp_data* data, int d, const double* d_beta, double* d_out,
+                                double* d_work, int nblocks, long long o0, long long o1);
 int jp_glm_num_blocks(const jp_ctx* ctx, long long N);
 
 #define TC_OBS_TILE 128          // MMA M: observations per tile (TMEM lanes)
@@ -512,11 +512,14 @@ tc_fold_kernel(int NC, long long n, long long N_pad, double z_ref, float* __rest
   }
 }
 
-// Per node: delta = U z, theta = mu + delta (all transforms are the identity on this path) and the FP64
-// quadratic part  L_hat + g.delta - 1/2 delta' H delta + prior(theta).  Per mirror pair (grid nodes 2j-1, 2j; pair 0
-// is the origin): the operand row [d_hi | d_hi | d_lo | 0] of the pair's FIRST member, written by that node's
-// thread -- or, when the local range starts on a second member, by its thread with the sign flipped
-// (delta(-z) = -delta(z) exactly: the sums below are sign-symmetric in IEEE arithmetic, and so is the TF32 split).
+// Per node: delta = U z, theta = mu + delta (all transforms are the identity on this path), in two kernels that run on
+// different streams (both rebuild delta from the integer keys; it costs a few FMAs per non-zero coordinate):
+//   PART 0  theta, and per mirror pair (grid nodes 2j-1, 2j; pair 0 is the origin) the operand row [d_hi | d_hi | d_lo | 0] of
+//           the pair's FIRST member -- or, when the local range starts on a second member, of that member with the sign flipped
+//           (delta(-z) = -delta(z) exactly: the sums are sign-symmetric in IEEE arithmetic, and so is the TF32 split).
+//           Needs (mu, U) only: runs while the O(N) passes over the observations are still in flight.
+//   PART 1  the FP64 quadratic part  L_hat + g.delta - 1/2 delta' H delta + prior(theta): needs the sums (g, H, L_hat).
+template <int PART>
 __global__ void __launch_bounds__(128)
 tc_node_prep_kernel(int d, int p, int kp, int seg, int rule, long long M, long long m0, long long M_grid, long long j_lo,
                     const uint8_t* __restrict__ idx, const double* __restrict__ znodes, const double* __restrict__ mu,
@@ -531,15 +534,16 @@ tc_node_prep_kernel(int d, int p, int kp, int seg, int rule, long long M, long l
   double* s_dl = s_z + JP_RULE_NMAX;  // blockDim.x x d  (delta of each thread, strided by thread)
   for (int k = threadIdx.x; k < d; k += blockDim.x) {
     s_mu[k] = mu[k];
-    s_g[k] = sums[k];
+    if (PART == 1) s_g[k] = sums[k];
   }
   for (int k = threadIdx.x; k < d * p; k += blockDim.x) s_U[k] = U[k];
   for (int k = threadIdx.x; k < JP_RULE_NMAX; k += blockDim.x) s_z[k] = znodes[k];
-  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
-    int r = e % d, c = e / d;
-    int rr = min(r, c), cc = max(r, c);
-    s_H[e] = sums[d + cc * (cc + 1) / 2 + rr];     // packed upper triangle, column by column
-  }
+  if (PART == 1)
+    for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+      int r = e % d, c = e / d;
+      int rr = min(r, c), cc = max(r, c);
+      s_H[e] = sums[d + cc * (cc + 1) / 2 + rr];     // packed upper triangle, column by column
+    }
   __syncthreads();
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double* dl = s_dl + threadIdx.x;       // dl[k * blockDim.x]
@@ -552,21 +556,25 @@ tc_node_prep_kernel(int d, int p, int kp, int seg, int rule, long long M, long l
         for (int k = 0; k < d; ++k) dl[k * blockDim.x] += s_U[(size_t)j * d + k] * z;   // same order as the FP64 path
       }
     }
-    const double L_hat = sums[d + d * (d + 1) / 2];
-    double lin = 0, qf = 0, prior = 0;
-    for (int k = 0; k < d; ++k) {
-      const double dk = dl[k * blockDim.x];
-      const double th = s_mu[k] + dk;
-      theta[(size_t)k * M + m] = th;
-      lin += s_g[k] * dk;
-      double hk = 0;
-      for (int l = 0; l < d; ++l) hk += s_H[(size_t)k * d + l] * dl[l * blockDim.x];
-      qf += dk * hk;
-      const double zz = th / prior_sd;
-      prior += -0.5 * zz * zz - log(prior_sd) - 0.5 * 1.8378770664093454835606594728112;
+    if (PART == 0) {
+      for (int k = 0; k < d; ++k) theta[(size_t)k * M + m] = s_mu[k] + dl[k * blockDim.x];
+    } else {
+      const double L_hat = sums[d + d * (d + 1) / 2];
+      double lin = 0, qf = 0, prior = 0;
+      for (int k = 0; k < d; ++k) {
+        const double dk = dl[k * blockDim.x];
+        const double th = s_mu[k] + dk;
+        lin += s_g[k] * dk;
+        double hk = 0;
+        for (int l = 0; l < d; ++l) hk += s_H[(size_t)k * d + l] * dl[l * blockDim.x];
+        qf += dk * hk;
+        const double zz = th / prior_sd;
+        prior += -0.5 * zz * zz - log(prior_sd) - 0.5 * 1.8378770664093454835606594728112;
+      }
+      quad[m] = (L_hat + lin - 0.5 * qf) + prior;
     }
-    quad[m] = (L_hat + lin - 0.5 * qf) + prior;
   }
+  if (PART == 1) return;
   // The pair operand rows, written by WHOLE WARPS: a row is kp floats (one to three 128-byte lines), lane c takes column
   // c, c + 32, ..; one store instruction is one coalesced line.  (One thread writing its own row cost 3 d scattered
   // 4-byte stores per node, eight times the bytes in 32-byte sectors.)  Warp w serves the nodes of its own 32 threads.
@@ -1252,11 +1260,13 @@ static int tc_prep_slice(jp_posterior* post, const jp_fit_args* args, int rank, 
   TcDataState* ds = static_cast<TcDataState*>(data->tc_state);
   const int d = args->d, p = args->p;
   const long long o0 = std::min(data->N, (long long)rank * ds->n_loc), o1 = std::min(data->N, o0 + ds->n_loc);
-  // The two O(N) passes over the slice are independent (sums g, H, L_hat | per-observation coefficients and bounds): the
-  // coefficient pass runs on the context's side stream, forked here; the caller joins (tc_join_side) before anything reads
-  // its results on the main stream.
+  // The two O(N) passes over the slice are independent of each other (sums g, H, L_hat | per-observation coefficients and
+  // bounds) and of the node operand: the coefficient pass runs on the context's stream `side`, the sums on `side2`, both
+  // forked here; the main stream stays free for the node operand.  The caller joins (tc_join_side) before anything reads
+  // their results on the main stream.
   JP_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
   JP_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+  JP_CUDA(cudaStreamWaitEvent(ctx->side2, ctx->ev_fork, 0));
   const double z_max = std::sqrt(post->grid->zmax2), z_ref = std::min(z_max, 6.0);
   const size_t sm_obs = (size_t)(((d + 1) & ~1) + d * ((p + 3) & ~3) + 2 * TC_PREP_THREADS * (data->ncols | 1)) * 8;
   if (sm_obs > 48 * 1024)
@@ -1265,14 +1275,16 @@ static int tc_prep_slice(jp_posterior* post, const jp_fit_args* args, int rank, 
       data->family, d, p, data->ncols, o1 - o0, ds->n_loc, data->d_obs + (size_t)o0 * data->ncols, post->d_mu, post->d_U, z_ref,
       z_max, ds->d_coef, ds->n_loc, ds->d_bounds);
   JP_CHECK_LAUNCH(ctx);
-  JP_TRY(jp_glm_sums_device_range(ctx, data, d, post->d_mu, d_sums, ds->d_work, ds->glm_blocks, o0, o1));
+  JP_TRY(jp_glm_sums_device_range_on(ctx, ctx->side2, data, d, post->d_mu, d_sums, ds->d_work, ds->glm_blocks, o0, o1));
   return JP_OK;
 }
 
-// the main stream waits for everything queued on the side stream so far
+// the main stream waits for everything queued on the two side streams so far
 static int tc_join_side(jp_ctx* ctx) {
   JP_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
   JP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  JP_CUDA(cudaEventRecord(ctx->ev_join2, ctx->side2));
+  JP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));
   return JP_OK;
 }
 
@@ -1306,23 +1318,27 @@ static int tc_fold_slice(jp_posterior* post, int NC) {
 
 // node operand, theta, FP64 quadratic part: independent of the series length, so the single-GPU fit queues it BEFORE it
 // waits for the bounds (the device works on it while the host decides)
-static int tc_node_prep(jp_posterior* post, const jp_fit_args* args) {
+template <int PART>
+static int tc_node_prep_part(jp_posterior* post, const jp_fit_args* args, cudaStream_t st) {
   jp_ctx* ctx = post->ctx;
   const jp_data* data = post->data;
   TcDataState* ds = static_cast<TcDataState*>(data->tc_state);
   TcPostState* ps = static_cast<TcPostState*>(post->tc_state);
   const int d = args->d, p = args->p;
-  cudaStream_t st = ctx->stream;
   size_t sm_node = (size_t)(d + d * p + d + d * d + JP_RULE_NMAX + 128 * d) * 8;
   if (sm_node > 48 * 1024)
-    JP_CUDA(cudaFuncSetAttribute(tc_node_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_node));
-  tc_node_prep_kernel<<<(unsigned)((post->M + 127) / 128), 128, sm_node, st>>>(
+    JP_CUDA(cudaFuncSetAttribute(tc_node_prep_kernel<PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_node));
+  tc_node_prep_kernel<PART><<<(unsigned)((post->M + 127) / 128), 128, sm_node, st>>>(
       d, p, ds->kp_b, ds->split ? TC_KATOM : d, post->grid->rule, post->M, post->m0, post->grid->M, ps->j_lo, post->grid->d_idx,
       jp_rule_nodes_dev(ctx, post->grid->rule), post->d_mu, post->d_U, ds->d_sums, data->hyper[0], post->d_theta, ps->d_quad,
       ps->d_ds);
   JP_CHECK_LAUNCH(ctx);
   return JP_OK;
 }
+// theta + pair operand on the main stream (needs mu, U only)
+static int tc_node_operand(jp_posterior* post, const jp_fit_args* args) { return tc_node_prep_part<0>(post, args, post->ctx->stream); }
+// the quadratic part on `st`, behind the sums it needs
+static int tc_node_quad(jp_posterior* post, const jp_fit_args* args, cudaStream_t st) { return tc_node_prep_part<1>(post, args, st); }
 
 // the tensor-core kernel and the per-node finish (after tc_node_prep)
 static int tc_run_kernel(jp_posterior* post, const jp_fit_args* args, int NC, bool finish) {
@@ -1392,6 +1408,7 @@ static int tc_run_kernel(jp_posterior* post, const jp_fit_args* args, int NC, bo
   else if (NC == 10) stc = launch_tc<10>(ctx, ds->tmA, ps->tmB, kp, smem);
   else stc = launch_tc<12>(ctx, ds->tmA, ps->tmB, kp, smem);
   JP_TRY(stc);
+  JP_MARK(ctx, "fit:tc_kernel");
   post->path_used = JP_PATH_TC;
   post->fin = JpFinish();
   post->fin.path = JP_PATH_TC; post->fin.chunks = kp.chunks; post->fin.P = ps->P; post->fin.j_lo = ps->j_lo;
@@ -1408,48 +1425,61 @@ static int tc_run_kernel(jp_posterior* post, const jp_fit_args* args, int NC, bo
 
 static int tc_run(jp_posterior* post, const jp_fit_args* args, int NC, bool finish) {
   TcPostState* ps = static_cast<TcPostState*>(post->tc_state);
-  if (!ps->node_prep_queued) JP_TRY(tc_node_prep(post, args));
+  if (!ps->node_prep_queued) {
+    JP_TRY(tc_node_operand(post, args));
+    JP_TRY(tc_node_quad(post, args, post->ctx->stream));
+  }
   ps->node_prep_queued = false;
   return tc_run_kernel(post, args, NC, finish);
 }
 
-// reduce the block partials of the bounds on the device (block order; [0] is a maximum)
-__global__ void tc_bounds_reduce_kernel(const double* __restrict__ blocks, int nblocks, double* __restrict__ out) {
-  const int j = threadIdx.x;
-  if (j >= TC_NBOUND) return;
+// reduce the block partials of the bounds on the device: one warp per bound, lane l adds blocks l, l + 32, .. in ascending
+// order, then the fixed shuffle tree (deterministic); [0] is a maximum.  Launch with TC_NBOUND warps.
+__global__ void __launch_bounds__(32 * TC_NBOUND) tc_bounds_reduce_kernel(const double* __restrict__ blocks, int nblocks,
+                                                                          double* __restrict__ out) {
+  const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double v = 0;
-  for (int blk = 0; blk < nblocks; ++blk) {
+  for (int blk = lane; blk < nblocks; blk += 32) {
     const double o = blocks[(size_t)blk * TC_NBOUND + j];
     v = (j == 0) ? fmax(v, o) : v + o;
   }
-  out[j] = v;
+  v = (j == 0) ? jp_warp_max(v) : jp_warp_sum(v);
+  if (lane == 0) out[j] = v;
 }
 
 int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args, bool finish) {
   jp_ctx* ctx = post->ctx;
+  JP_MARK(ctx, "fit:start");
   JP_TRY(tc_setup(post, args, 1, 0));
+  JP_MARK(ctx, "fit:setup+consts");
   TcDataState* ds = static_cast<TcDataState*>(post->data->tc_state);
   JP_TRY(tc_prep_slice(post, args, 0, ds->d_sums));
+  jp_trace_mark(ctx, "fit:glm_sums(side2)", ctx->side2);
+  JP_MARK_SIDE(ctx, "fit:obs_prep(side)");
+  JP_TRY(tc_node_quad(post, args, ctx->side2));       // behind the sums on their stream
+  jp_trace_mark(ctx, "fit:node_quad(side2)", ctx->side2);
   // diagnostic only (bench.py attribution of the host round trip): JP_TC_ASSUME=NC,fold skips the bounds read-back
   static const char* assume = getenv("JP_TC_ASSUME");
   if (assume) {
     int nc = 4, fd = 1;
     sscanf(assume, "%d,%d", &nc, &fd);
     post->tc_bounds[3] = nc; post->tc_bounds[5] = fd;
-    JP_TRY(tc_node_prep(post, args));
+    JP_TRY(tc_node_operand(post, args));
     JP_TRY(tc_join_side(ctx));
     if (fd) JP_TRY(tc_fold_slice(post, nc));
     return tc_run_kernel(post, args, nc, finish);
   }
-  // side stream: block bounds -> 22 numbers -> pinned host memory; main stream meanwhile: sums, then the node operand
-  // (tc_node_prep needs g, H only).  The host's wait for the bounds is hidden under both (measured: skipping it with
-  // JP_TC_ASSUME changes the fit time by < 5 us).
+  // `side`: block bounds -> 22 numbers -> pinned host memory; `side2`: sums, then the quadratic part of every node; main
+  // stream: theta and the pair operand.  The host's wait for the bounds is hidden under the three (measured: skipping it
+  // with JP_TC_ASSUME changes the fit time by < 5 us).
   double* hb = ctx->h_pinned + JP_PINNED_BOUNDS_OFF;   // away from the constants staged by jp_upload_fit_consts
-  tc_bounds_reduce_kernel<<<1, 32, 0, ctx->side>>>(ds->d_bounds, ds->prep_blocks, ds->d_comb);
+  tc_bounds_reduce_kernel<<<1, 32 * TC_NBOUND, 0, ctx->side>>>(ds->d_bounds, ds->prep_blocks, ds->d_comb);
   JP_CHECK_LAUNCH(ctx);
   JP_CUDA(cudaMemcpyAsync(hb, ds->d_comb, (size_t)TC_NBOUND * 8, cudaMemcpyDeviceToHost, ctx->side));
   JP_CUDA(cudaEventRecord(ds->ev_bounds, ctx->side));
-  JP_TRY(tc_node_prep(post, args));
+  JP_MARK_SIDE(ctx, "fit:bounds_d2h(side)");
+  JP_TRY(tc_node_operand(post, args));
+  JP_MARK(ctx, "fit:node_operand");
   JP_CUDA(cudaEventSynchronize(ds->ev_bounds));
   JP_TRY(tc_join_side(ctx));
   double b[TC_NBOUND];
@@ -1457,6 +1487,7 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args, bool finish) {
   int NC = 0, fold = 0;
   JP_TRY(tc_decide(post, b, &NC, &fold));
   if (fold) JP_TRY(tc_fold_slice(post, NC));
+  JP_MARK(ctx, "fit:host_decision+fold");
   return tc_run_kernel(post, args, NC, finish);
 }
 
@@ -1470,8 +1501,9 @@ int jp_fit_tc_prep_local(jp_posterior* post, const jp_fit_args* args, int rank, 
   TcDataState* ds = static_cast<TcDataState*>(post->data->tc_state);
   const int nE1 = args->d + args->d * (args->d + 1) / 2 + 1;
   JP_TRY(tc_prep_slice(post, args, rank, d_out));
-  tc_bounds_reduce_kernel<<<1, 32, 0, post->ctx->side>>>(ds->d_bounds, ds->prep_blocks, d_out + nE1);
+  tc_bounds_reduce_kernel<<<1, 32 * TC_NBOUND, 0, post->ctx->side>>>(ds->d_bounds, ds->prep_blocks, d_out + nE1);
   JP_CHECK_LAUNCH(post->ctx);
+  JP_TRY(tc_node_operand(post, args));  // theta and the pair operand of this rank's node block, under the O(N) passes
   JP_TRY(tc_join_side(post->ctx));      // the caller's collective reads d_out on the main stream
   return JP_OK;
 }
@@ -1507,7 +1539,7 @@ int jp_fit_tc_prep_gathered(jp_posterior* post, const jp_fit_args* args, const d
   double* hb = ctx->h_pinned + JP_PINNED_BOUNDS_OFF;
   JP_CUDA(cudaMemcpyAsync(hb, ds->d_comb, (size_t)TC_NBOUND * 8, cudaMemcpyDeviceToHost, ctx->stream));
   JP_CUDA(cudaEventRecord(ds->ev_bounds, ctx->stream));
-  JP_TRY(tc_node_prep(post, args));
+  JP_TRY(tc_node_quad(post, args, ctx->stream));      // needs the combined sums; the operand was queued by jp_fit_prep_local
   ps->node_prep_queued = true;
   JP_CUDA(cudaEventSynchronize(ds->ev_bounds));
   double b[TC_NBOUND];

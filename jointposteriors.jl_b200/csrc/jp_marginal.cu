@@ -206,16 +206,13 @@ jp_knots_kernel(const double* __restrict__ sv, const double* __restrict__ cw, lo
 #define JP_BIN_WARPS (JP_BIN_THREADS / 32)
 #define JP_BIN_STRIDE 5                  // per bin: W, max, min, index of min (as double), weight at min
 
-__global__ void __launch_bounds__(JP_BIN_THREADS)
-jp_bins_kernel(const double* const* __restrict__ vptr, const double* __restrict__ w, long long M, long long m0,
-               const double* __restrict__ minmax, int minmax_stride, int minmax_off,
-               double* __restrict__ out /* [K][gridDim.x][JP_NBINS][JP_BIN_STRIDE] */) {
-  __shared__ double s_x[JP_GRID_KNOTS];
-  __shared__ double s_bin[JP_BIN_WARPS][JP_NBINS][JP_BIN_STRIDE];
-  const int k = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const double* v = vptr[k];
-  const double vmin = minmax[(size_t)k * minmax_stride + minmax_off], vmax = minmax[(size_t)k * minmax_stride + minmax_off + 1];
-  for (int i = threadIdx.x; i < JP_GRID_KNOTS; i += JP_BIN_THREADS) s_x[i] = jp_knot_value(vmin, vmax, i);
+// The binning pass of one block over its slice of marginal k (all JP_BIN_THREADS threads): fills s_bin and writes the block's
+// bin table to `o`.  s_x holds the 100 knots of [vmin, vmax].
+typedef double JpBinTable[JP_BIN_WARPS][JP_NBINS][JP_BIN_STRIDE];
+__device__ __forceinline__ void jp_bin_slice(const double* __restrict__ v, const double* __restrict__ w, long long M, long long m0,
+                                             double vmin, double vmax, const double* s_x, JpBinTable& s_bin, double* __restrict__ o,
+                                             double* mom_s1 = nullptr, double* mom_s2 = nullptr) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < JP_BIN_WARPS * JP_NBINS; i += JP_BIN_THREADS) {
     double* bn = &s_bin[0][0][0] + (size_t)i * JP_BIN_STRIDE;
     bn[0] = 0.0; bn[1] = -INFINITY; bn[2] = INFINITY; bn[3] = INFINITY; bn[4] = 0.0;
@@ -227,10 +224,15 @@ jp_bins_kernel(const double* const* __restrict__ vptr, const double* __restrict_
   const long long per_warp = ((per_block + JP_BIN_WARPS - 1) / JP_BIN_WARPS + 31) / 32 * 32;
   const long long w0 = b0 + (long long)warp * per_warp, w1 = min(b1, w0 + per_warp);
   const double scale = (vmax > vmin) ? (double)(JP_GRID_KNOTS - 1) / (vmax - vmin) : 0.0;
+  double t1 = 0, t2 = 0;      // this lane's share of sum w v, sum w v^2 (only when the caller asks for the moments)
   for (long long base = w0; base < w1; base += 32) {
     const long long j = base + lane;
     const bool live = j < w1;
     double vj = live ? v[j] : 0.0, wj = live ? w[j] : 0.0;
+    if (mom_s1) {
+      t1 += wj * vj;
+      t2 += wj * (vj * vj);
+    }
     int bin = -1;
     if (live) {
       int g = (int)floor((vj - vmin) * scale);          // guess, then make exact against the knot table
@@ -276,8 +278,11 @@ jp_bins_kernel(const double* const* __restrict__ vptr, const double* __restrict_
     }
     __syncwarp();
   }
+  if (mom_s1) {
+    *mom_s1 = t1;
+    *mom_s2 = t2;
+  }
   __syncthreads();
-  double* o = out + ((size_t)k * gridDim.x + blockIdx.x) * JP_NBINS * JP_BIN_STRIDE;
   for (int bq = threadIdx.x; bq < JP_NBINS; bq += JP_BIN_THREADS) {
     double W = 0.0, mx = -INFINITY, mn = INFINITY, mi = INFINITY, mw = 0.0;
     for (int ww = 0; ww < JP_BIN_WARPS; ++ww) {
@@ -291,86 +296,160 @@ jp_bins_kernel(const double* const* __restrict__ vptr, const double* __restrict_
   }
 }
 
-// one block per marginal: blocks -> bins -> knots.  FINAL: the 100-knot Grid + (mu, sigma) into mout;
-// otherwise the per-knot candidates (S, pred, succ, index, weight, x) for the cross-rank combine.
-#define JP_COMBINE_THREADS 512
-template <bool FINAL>
-__global__ void __launch_bounds__(JP_COMBINE_THREADS)
-jp_bins_combine_kernel(const double* __restrict__ bins, int nblocks, const double* __restrict__ minmax, int minmax_stride,
-                       int minmax_off, const double* __restrict__ mom, int mom_stride, double* __restrict__ out) {
-  __shared__ double sb[JP_NBINS][JP_BIN_STRIDE];
-  __shared__ int s_argmin[JP_NBINS];
-  __shared__ double sS[JP_GRID_KNOTS], sP[JP_GRID_KNOTS], sSucc[JP_GRID_KNOTS][3];
-  const int k = blockIdx.x, t = threadIdx.x;
+__global__ void __launch_bounds__(JP_BIN_THREADS)
+jp_bins_kernel(const double* const* __restrict__ vptr, const double* __restrict__ w, long long M, long long m0,
+               const double* __restrict__ minmax, int minmax_stride, int minmax_off,
+               double* __restrict__ out /* [K][gridDim.x][JP_NBINS][JP_BIN_STRIDE] */) {
+  __shared__ double s_x[JP_GRID_KNOTS];
+  __shared__ JpBinTable s_bin;
+  const int k = blockIdx.y;
   const double vmin = minmax[(size_t)k * minmax_stride + minmax_off], vmax = minmax[(size_t)k * minmax_stride + minmax_off + 1];
+  for (int i = threadIdx.x; i < JP_GRID_KNOTS; i += JP_BIN_THREADS) s_x[i] = jp_knot_value(vmin, vmax, i);
+  jp_bin_slice(vptr[k], w, M, m0, vmin, vmax, s_x, s_bin, out + ((size_t)k * gridDim.x + blockIdx.x) * JP_NBINS * JP_BIN_STRIDE);
+}
+
+// blocks -> bins -> knots of one marginal, by all threads of a block (any block size >= 64).  FINAL: the 100-knot Grid +
+// (mu, sigma) into `out` (one JP_MOUT_STRIDE record); otherwise the per-knot candidates (S, pred, succ, index, weight, x)
+// for the cross-rank combine.
+#define JP_COMBINE_THREADS 512
+struct JpCombineSmem {
+  double sb[JP_NBINS][JP_BIN_STRIDE];
+  int argmin[JP_NBINS];
+  double sS[JP_GRID_KNOTS], sP[JP_GRID_KNOTS], sSucc[JP_GRID_KNOTS][3];
+};
+template <bool FINAL>
+__device__ __forceinline__ void jp_combine_bins(JpCombineSmem& S, const double* __restrict__ bins_k, int nblocks, double vmin, double vmax,
+                                                double s1, double s2, double* __restrict__ out) {
+  const int nt = blockDim.x;
   // one thread per (bin, field): consecutive threads read consecutive doubles of a block's bin table; block order =
   // ascending node index.  The index and weight of the minimum (fields 3, 4) are fetched from the block that won.
-  const int bin = t / JP_BIN_STRIDE, field = t % JP_BIN_STRIDE;
-  const double* col = bins + (size_t)k * nblocks * JP_NBINS * JP_BIN_STRIDE + t;
-  if (t < JP_NBINS * JP_BIN_STRIDE && field <= 2) {
+  for (int t = threadIdx.x; t < JP_NBINS * JP_BIN_STRIDE; t += nt) {
+    const int bin = t / JP_BIN_STRIDE, field = t % JP_BIN_STRIDE;
+    if (field > 2) continue;
+    const double* col = bins_k + t;
     double acc = field == 0 ? 0.0 : (field == 1 ? -INFINITY : INFINITY);
     int arg = -1;
 #pragma unroll 8
     for (int b = 0; b < nblocks; ++b) {
-      const double x = col[(size_t)b * JP_NBINS * JP_BIN_STRIDE];
+      const double x = __ldcg(col + (size_t)b * JP_NBINS * JP_BIN_STRIDE);
       if (field == 0) acc += x;
       else if (field == 1) acc = fmax(acc, x);
       else if (x < acc) { acc = x; arg = b; }
     }
-    sb[bin][field] = acc;
-    if (field == 2) s_argmin[bin] = arg;
+    S.sb[bin][field] = acc;
+    if (field == 2) S.argmin[bin] = arg;
   }
   __syncthreads();
-  if (t < JP_NBINS * JP_BIN_STRIDE && field >= 3) {
-    const int arg = s_argmin[bin];
-    sb[bin][field] = arg >= 0 ? col[(size_t)arg * JP_NBINS * JP_BIN_STRIDE] : (field == 3 ? INFINITY : 0.0);
+  for (int t = threadIdx.x; t < JP_NBINS * JP_BIN_STRIDE; t += nt) {
+    const int bin = t / JP_BIN_STRIDE, field = t % JP_BIN_STRIDE;
+    if (field < 3) continue;
+    const int arg = S.argmin[bin];
+    S.sb[bin][field] = arg >= 0 ? __ldcg(bins_k + t + (size_t)arg * JP_NBINS * JP_BIN_STRIDE) : (field == 3 ? INFINITY : 0.0);
   }
   __syncthreads();
-  if (t == 0) {   // 99 bins: sequential prefix (mass, predecessor) ...
-    double S = 0.0, pr = -INFINITY;
+  if (threadIdx.x == 0) {   // 99 bins: sequential prefix (mass, predecessor) ...
+    double Sm = 0.0, pr = -INFINITY;
 #pragma unroll 7
     for (int i = 1; i <= JP_NBINS - 1; ++i) {        // knot i reads bins 0 .. i-1
-      S += sb[i - 1][0];
-      pr = fmax(pr, sb[i - 1][1]);
-      sS[i] = S;
-      sP[i] = pr;
+      Sm += S.sb[i - 1][0];
+      pr = fmax(pr, S.sb[i - 1][1]);
+      S.sS[i] = Sm;
+      S.sP[i] = pr;
     }
-  } else if (t == 32) {   // ... and, in another warp, suffix (successor)
+  } else if (threadIdx.x == 32) {   // ... and, in another warp, suffix (successor)
     double mn = INFINITY, mi = INFINITY, mw = 0.0;
 #pragma unroll 7
     for (int i = JP_NBINS - 1; i >= 1; --i) {        // knot i reads bins i .. 98; ties keep the lower bin's entry
-      if (sb[i][2] <= mn && sb[i][2] < INFINITY) { mn = sb[i][2]; mi = sb[i][3]; mw = sb[i][4]; }
-      sSucc[i][0] = mn; sSucc[i][1] = mi; sSucc[i][2] = mw;
+      if (S.sb[i][2] <= mn && S.sb[i][2] < INFINITY) { mn = S.sb[i][2]; mi = S.sb[i][3]; mw = S.sb[i][4]; }
+      S.sSucc[i][0] = mn; S.sSucc[i][1] = mi; S.sSucc[i][2] = mw;
     }
   }
   __syncthreads();
   if (FINAL) {
-    double* o = out + (size_t)k * JP_MOUT_STRIDE;
-    if (t == 0) {
-      double s1 = mom[(size_t)k * mom_stride + 0], s2 = mom[(size_t)k * mom_stride + 1];
-      o[0] = s1;
-      o[1] = sqrt(s2 - s1 * s1);      // no clamp: a negative argument gives NaN, as in the reference
-      o[2 + 2 * JP_GRID_KNOTS] = vmin;
-      o[3 + 2 * JP_GRID_KNOTS] = vmax;
+    if (threadIdx.x == 0) {
+      out[0] = s1;
+      out[1] = sqrt(s2 - s1 * s1);      // no clamp: a negative argument gives NaN, as in the reference
+      out[2 + 2 * JP_GRID_KNOTS] = vmin;
+      out[3 + 2 * JP_GRID_KNOTS] = vmax;
     }
-    if (t < JP_GRID_KNOTS) {
+    for (int t = threadIdx.x; t < JP_GRID_KNOTS; t += nt) {
       const double x = jp_knot_value(vmin, vmax, t);
-      o[2 + t] = x;
+      out[2 + t] = x;
       double wn;
       if (t == 0) wn = 0.0;                              // interp.jl:451
       else if (t == JP_GRID_KNOTS - 1) wn = 1.0;         // interp.jl:452
       else {
-        const double k0 = sP[t], k1 = sSucc[t][0], c0 = sS[t], c1 = sS[t] + sSucc[t][2];
+        const double k0 = S.sP[t], k1 = S.sSucc[t][0], c0 = S.sS[t], c1 = S.sS[t] + S.sSucc[t][2];
         const double fx = (x - k0) / (k1 - k0);
         wn = c0 * (1.0 - fx) + c1 * fx;
       }
-      o[2 + JP_GRID_KNOTS + t] = wn;
+      out[2 + JP_GRID_KNOTS + t] = wn;
     }
-  } else if (t >= 1 && t <= JP_GRID_KNOTS - 2) {
-    double* o = out + ((size_t)k * (JP_GRID_KNOTS - 2) + (t - 1)) * 6;
-    o[0] = sS[t]; o[1] = sP[t]; o[2] = sSucc[t][0]; o[3] = sSucc[t][1]; o[4] = sSucc[t][2];
-    o[5] = jp_knot_value(vmin, vmax, t);
+  } else {
+    for (int t = 1 + threadIdx.x; t <= JP_GRID_KNOTS - 2; t += nt) {
+      double* o = out + (size_t)(t - 1) * 6;
+      o[0] = S.sS[t]; o[1] = S.sP[t]; o[2] = S.sSucc[t][0]; o[3] = S.sSucc[t][1]; o[4] = S.sSucc[t][2];
+      o[5] = jp_knot_value(vmin, vmax, t);
+    }
   }
+}
+
+template <bool FINAL>
+__global__ void __launch_bounds__(JP_COMBINE_THREADS)
+jp_bins_combine_kernel(const double* __restrict__ bins, int nblocks, const double* __restrict__ minmax, int minmax_stride,
+                       int minmax_off, const double* __restrict__ mom, int mom_stride, double* __restrict__ out) {
+  __shared__ JpCombineSmem S;
+  const int k = blockIdx.x;
+  const double vmin = minmax[(size_t)k * minmax_stride + minmax_off], vmax = minmax[(size_t)k * minmax_stride + minmax_off + 1];
+  const double s1 = FINAL ? mom[(size_t)k * mom_stride + 0] : 0.0, s2 = FINAL ? mom[(size_t)k * mom_stride + 1] : 0.0;
+  jp_combine_bins<FINAL>(S, bins + (size_t)k * nblocks * JP_NBINS * JP_BIN_STRIDE, nblocks, vmin, vmax, s1, s2,
+                         out + (FINAL ? (size_t)k * JP_MOUT_STRIDE : (size_t)k * (JP_GRID_KNOTS - 2) * 6));
+}
+
+// ---- single-GPU default path after a fit: ONE launch per batch of coordinate marginals.  Stage 4 (jp_fit.cu) leaves, per
+// stage-4 block and coordinate, (sum w theta, sum w theta^2, min theta, max theta): every block here combines the extrema of
+// its coordinate itself (block order), bins its slice, and the last block of a marginal to finish (arrival counter) turns the
+// block tables into the 100-knot Grid -- no separate moments pass, no second and third launch.
+__global__ void __launch_bounds__(JP_BIN_THREADS)
+jp_marginal_onepass_kernel(const int* __restrict__ coords, const double* __restrict__ theta, const double* __restrict__ w, long long M,
+                           long long m0, const double* __restrict__ cmom /* [nb4][d][4] */, int nb4, int d,
+                           double* __restrict__ bins /* [K][gridDim.x][JP_NBINS][JP_BIN_STRIDE] */, unsigned int* __restrict__ counters,
+                           double* __restrict__ mout) {
+  __shared__ double s_x[JP_GRID_KNOTS];
+  __shared__ union U { JpBinTable bin; JpCombineSmem comb; U() {} } sh;
+  __shared__ double s_red[4][JP_BIN_WARPS];
+  __shared__ double s_mm[4];
+  const int k = blockIdx.y, c = coords[k], lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // extrema and moments of coordinate c from the stage-4 block partials, in block order
+  {
+    double mn = INFINITY, mx = -INFINITY;
+    for (int b = threadIdx.x; b < nb4; b += JP_BIN_THREADS) {
+      const double* q = cmom + ((size_t)b * d + c) * 4;
+      mn = fmin(mn, __ldcg(q + 2));
+      mx = fmax(mx, __ldcg(q + 3));
+    }
+    mn = jp_warp_min(mn);
+    mx = jp_warp_max(mx);
+    if (lane == 0) { s_red[2][wid] = mn; s_red[3][wid] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mn = s_red[2][0]; mx = s_red[3][0];
+      for (int i = 1; i < JP_BIN_WARPS; ++i) { mn = fmin(mn, s_red[2][i]); mx = fmax(mx, s_red[3][i]); }
+      double s1 = 0, s2 = 0;
+      for (int b = 0; b < nb4; ++b) {
+        const double* q = cmom + ((size_t)b * d + c) * 4;
+        s1 += __ldcg(q); s2 += __ldcg(q + 1);
+      }
+      s_mm[0] = s1; s_mm[1] = s2; s_mm[2] = mn; s_mm[3] = mx;
+    }
+    __syncthreads();
+  }
+  const double vmin = s_mm[2], vmax = s_mm[3];
+  for (int i = threadIdx.x; i < JP_GRID_KNOTS; i += JP_BIN_THREADS) s_x[i] = jp_knot_value(vmin, vmax, i);
+  double* bins_k = bins + (size_t)k * gridDim.x * JP_NBINS * JP_BIN_STRIDE;
+  jp_bin_slice(theta + (size_t)c * M, w, M, m0, vmin, vmax, s_x, sh.bin, bins_k + (size_t)blockIdx.x * JP_NBINS * JP_BIN_STRIDE);
+  if (!jp_last_block(counters + k, gridDim.x)) return;
+  jp_combine_bins<true>(sh.comb, bins_k, gridDim.x, vmin, vmax, s_mm[0], s_mm[1], mout + (size_t)k * JP_MOUT_STRIDE);
 }
 
 // ---- cross-rank combine on the device (node-sharded posterior): gathered moments [world][K][4], candidates
@@ -527,12 +606,56 @@ static int run_marginals(jp_posterior* post, int K, double* h_mu, double* h_sigm
   JP_REQUIRE((size_t)K * 4 <= JP_SCRATCH_DOUBLES, "marginal: K=%d too large for one call", K);
   cudaStream_t st = ctx->stream;
   double* d_mom = ctx->d_scratch;   // K x 4: sum w v, sum w v^2, min, max
+  JP_MARK(ctx, "marginals:start");
   JP_TRY(launch_moments(post, K, d_mom));      // counts its own launch
+  JP_MARK(ctx, "marginals:moments");
   dim3 gb(post->bins_blocks, K);
   jp_bins_kernel<<<gb, JP_BIN_THREADS, 0, st>>>(post->d_vptr, post->d_density, M, post->m0, d_mom, 4, 2, post->d_bins);
   JP_CHECK_LAUNCH(ctx);
+  JP_MARK(ctx, "marginals:bins");
   jp_bins_combine_kernel<true><<<K, JP_COMBINE_THREADS, 0, st>>>(post->d_bins, post->bins_blocks, d_mom, 4, 2, d_mom, 4, post->d_mout);
   JP_CHECK_LAUNCH(ctx);
+  JP_MARK(ctx, "marginals:combine");
+  JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, post->d_mout, (size_t)K * JP_MOUT_STRIDE * 8, cudaMemcpyDeviceToHost, st));
+  JP_MARK(ctx, "marginals:d2h");
+  JP_CUDA(cudaStreamSynchronize(st));
+  for (int k = 0; k < K; ++k) {
+    const double* o = ctx->h_pinned + (size_t)k * JP_MOUT_STRIDE;
+    if (h_mu) h_mu[k] = o[0];
+    if (h_sigma) h_sigma[k] = o[1];
+    if (h_vn) std::copy(o + 2, o + 2 + JP_GRID_KNOTS, h_vn + (size_t)k * JP_GRID_KNOTS);
+    if (h_wn) std::copy(o + 2 + JP_GRID_KNOTS, o + 2 + 2 * JP_GRID_KNOTS, h_wn + (size_t)k * JP_GRID_KNOTS);
+  }
+  post->K_last = K;
+  return JP_OK;
+}
+
+// coordinate marginals right after a single-GPU fit: the moments and extrema come from stage 4, one launch does the rest
+static int run_marginals_onepass(jp_posterior* post, int K, const int* h_coords, double* h_mu, double* h_sigma, double* h_vn,
+                                 double* h_wn) {
+  jp_ctx* ctx = post->ctx;
+  const long long M = post->M;
+  JP_REQUIRE(M >= 2, "marginal: need at least 2 nodes");
+  JP_REQUIRE((size_t)K * JP_MOUT_STRIDE <= JP_PINNED_DOUBLES && K <= JP_COUNTERS, "marginal: K=%d too large for one call", K);
+  cudaStream_t st = ctx->stream;
+  if (post->coords_host.size() != (size_t)K || !std::equal(h_coords, h_coords + K, post->coords_host.begin())) {
+    jp_dfree(ctx, post->d_coords);
+    post->d_coords = nullptr;
+    post->coords_host.clear();
+    JP_CUDA(jp_dmalloc(ctx, &post->d_coords, (size_t)K * sizeof(int)));
+    JP_CUDA(jp_pinned_acquire(ctx));
+    int* hp = reinterpret_cast<int*>(ctx->h_pinned);
+    std::copy(h_coords, h_coords + K, hp);
+    JP_CUDA(cudaMemcpyAsync(post->d_coords, hp, (size_t)K * sizeof(int), cudaMemcpyHostToDevice, st));
+    JP_CUDA(jp_pinned_publish(ctx));
+    post->coords_host.assign(h_coords, h_coords + K);
+  }
+  JP_MARK(ctx, "marginals:start");
+  dim3 gb(post->bins_blocks, K);
+  jp_marginal_onepass_kernel<<<gb, JP_BIN_THREADS, 0, st>>>(post->d_coords, post->d_theta, post->d_density, M, post->m0, post->d_cmom,
+                                                            post->cmom_blocks, post->d, post->d_bins, ctx->d_counters, post->d_mout);
+  JP_CHECK_LAUNCH(ctx);
+  JP_MARK(ctx, "marginals:onepass");
   JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, post->d_mout, (size_t)K * JP_MOUT_STRIDE * 8, cudaMemcpyDeviceToHost, st));
   JP_CUDA(cudaStreamSynchronize(st));
   for (int k = 0; k < K; ++k) {
@@ -645,6 +768,8 @@ int jp_marginal_coords(jp_posterior* post, int K, const int* h_coords, double* h
   JP_ENTER_CTX(post->ctx);
   JP_TRY(ensure_marginal_buffers(post, K));
   JP_TRY(set_value_pointers(post, K, h_coords, nullptr));
+  static const bool no_onepass = getenv("JP_NO_ONEPASS") != nullptr;      // A/B aid: the three-launch path
+  if (post->cmom_valid && !no_onepass) return run_marginals_onepass(post, K, h_coords, h_mu, h_sigma, h_value_nodes, h_weight_nodes);
   return run_marginals(post, K, h_mu, h_sigma, h_value_nodes, h_weight_nodes);
 }
 

@@ -115,6 +115,20 @@ class Context:
         check(lib().jp_ctx_last_kernel_ms(self.handle, C.byref(ms)))
         return float(ms.value)
 
+    def trace(self, on=True):
+        """Start (and clear) / stop the stage trace of this context (jp_ctx_trace)."""
+        check(lib().jp_ctx_trace(self.handle, C.c_int(1 if on else 0)))
+
+    def trace_dump(self):
+        """[(name, microseconds since the first mark)] of the events recorded since trace(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        check(lib().jp_ctx_trace_dump(self.handle, buf, C.c_int(len(buf))))
+        out = []
+        for line in buf.value.decode().splitlines():
+            name, us = line.split("\t")
+            out.append((name, float(us)))
+        return out
+
     def grid(self, rule_id, d_eff, level):
         g = C.c_void_p()
         check(lib().jp_grid_get(self.handle, C.c_int(rule_id), C.c_int(d_eff), C.c_int(level), C.byref(g)))
