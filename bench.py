@@ -544,24 +544,38 @@ def run_product(args):
     hdata.__dict__.update(data.__dict__)
     hdata._obs = obs_pinned.numpy()
 
+    phases = {}      # host clock at the phase boundaries of a step (no synchronisation added: the calls that block are the
+                     # marginals' result download and the density download)
+
     def step_e2e():
         # H2D of the observation records; with several ranks each uploads its 1/world row slice over PCIe and the
         # slices are exchanged GPU->GPU (one NCCL all_gather over NVLink)
+        t_ = [time.perf_counter()]
         dde = ctx.upload(hdata) if world == 1 else ctx.upload_sharded(hdata)
+        t_.append(time.perf_counter())
         pe = JointPosterior(M, dde, grid, x, U, neg_min, path=path, node_range=(b, e))
+        t_.append(time.perf_counter())
         if world == 1:
             pe.evaluate()
+            t_.append(time.perf_counter())
             res = jp.marginals(pe, coords)                        # D2H of mu, sigma, 2 x 100 knots per coordinate
+            t_.append(time.perf_counter())
             dens = pe.density                                     # D2H of the normalised weights
             out = (res[0].mu, float(dens[0]))
         else:
             le = D.CudaLocal(pe)
             D.fit_sharded(le)
+            t_.append(time.perf_counter())
             mu, sg, vn, wn = D.marginals_sharded(le, coords)
+            t_.append(time.perf_counter())
             dens = pe.density
             out = (float(mu[0]), float(sg[0]), vn, wn, float(dens[0]))
+        t_.append(time.perf_counter())
         pe.free()
         dde.free()
+        t_.append(time.perf_counter())
+        for nm, a_, b_ in zip(("upload_call", "posterior_create", "fit_enqueue", "marginals_blocking", "density_d2h", "free"), t_[:-1], t_[1:]):
+            phases.setdefault(nm, []).append((b_ - a_) * 1e3)
         return out
 
     # host-side transients (glibc raising its mmap threshold for the freshly allocated result arrays, the stream-ordered
@@ -571,6 +585,7 @@ def run_product(args):
         step_e2e()
     barrier()
     a, c = ev(), ev()
+    phases.clear()
     a.record(stream)
     t0 = time.perf_counter()
     per_step = []
@@ -589,7 +604,8 @@ def run_product(args):
     h2d = int((re_ - rb) * obs.shape[1] * 8 + 8 * (d + d * U.shape[1]) + 4 * d)     # this rank's bytes (largest slice on rank 0)
     d2h = int(8 * (e - b) + d * 8 * (2 + 200))
     e2e = dict(value=pairs / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms,
-               warmup=e2e_warmup, per_step_ms=[round(v, 3) for v in per_step])
+               warmup=e2e_warmup, per_step_ms=[round(v, 3) for v in per_step],
+               host_phases_ms={k: round(float(np.median(v)), 4) for k, v in phases.items()})
 
     # ---- the whole public call, mode finder included: fit(model, host data) + marginals of every coordinate, grid cached
     # (what the reference's README times for its Example 1: 3.883 ms median, README.md:223-234, unstated CPU)

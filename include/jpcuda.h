@@ -37,7 +37,8 @@ typedef enum jp_status {
   JP_ERR_CUDA = 3,
   JP_ERR_NO_DEVICE = 4,
   JP_ERR_ALLOC = 5,
-  JP_ERR_UNSUPPORTED = 6
+  JP_ERR_UNSUPPORTED = 6,
+  JP_ERR_COMM = 7         /* a peer rank never reached the matching exchange (jp_comm_status) */
 } jp_status;
 
 /* quadrature rule families (SparseQuadratureGrids.GenzKeister / KronrodPatterson, reference test/runtests.jl:42) */
@@ -78,6 +79,7 @@ typedef struct jp_ctx jp_ctx;
 typedef struct jp_grid jp_grid;
 typedef struct jp_data jp_data;
 typedef struct jp_posterior jp_posterior;
+typedef struct jp_comm jp_comm;
 
 const char* jp_last_error(void);
 int jp_version(void);
@@ -252,6 +254,42 @@ int jp_fit_prep_gathered(jp_posterior* post, const jp_fit_args* args, const doub
                          int* n_rows);
 int jp_fit_coef_slab(jp_posterior* post, int n_rows, void** d_local, void** d_all, long long* count);
 int jp_fit_local_stats_prepared(jp_posterior* post, const jp_fit_args* args, double* d_stats);
+
+/* ---- The node-sharded path with its exchanges INSIDE the library, over NVLink peer memory (csrc/jp_comm.cu).
+ * SURVEY 8b sketched jp_ctx_create(n_gpus); the sharding keeps one process (and one jp_ctx) per GPU, and a jp_comm joins
+ * the ranks of one box.  Every rank owns a mailbox in its GPU's memory; peers map it through CUDA IPC and the library's
+ * kernels store their payloads and a sequence flag straight into it (no NCCL call, no host synchronisation between the
+ * phases).  The host moves ONE 64-byte handle per rank, once, by whatever it has (MPI, sockets, a file, torch.distributed):
+ *   jp_comm_create(ctx, rank, world, bulk_bytes, &comm)   bulk_bytes: room for the coefficient rows of the tensor-core
+ *                                                         path, 4 bytes x 12 rows x observations rounded up to 128 x world
+ *                                                         (0: GLM fits then keep their O(N) prep replicated)
+ *   jp_comm_ipc_handle(comm, h[64])  --  all ranks exchange their handles  --  jp_comm_connect_ipc(comm, handles[world][64])
+ *   (one process driving several contexts, e.g. tests: jp_comm_connect_local(comm, comms[world]))
+ * Every rank must then issue the same sequence of jp_*_p2p calls.  jp_comm_status synchronises the stream and reports a
+ * peer that never arrived (JP_ERR_COMM after JP_COMM_TIMEOUT_S seconds, default 60). */
+int jp_comm_create(jp_ctx* ctx, int rank, int world, long long bulk_bytes, jp_comm** out);
+int jp_comm_ipc_handle(jp_comm* comm, void* handle64);
+int jp_comm_connect_ipc(jp_comm* comm, const void* handles);
+int jp_comm_connect_local(jp_comm* comm, jp_comm* const* comms);
+long long jp_comm_bulk_bytes(const jp_comm* comm);
+int jp_comm_status(jp_comm* comm);
+int jp_comm_destroy(jp_comm* comm);
+/* all_gather of n doubles per rank (device buffers, asynchronous): d_out[world][n] */
+int jp_comm_all_gather(jp_comm* comm, const double* d_src, int n, double* d_out);
+/* jp_fit on this rank's node block with a global normalisation: stages 2-4 of eval_grid! (reference
+ * src/joint_posterior.jl:180,186) as ONE asynchronous queue per rank.  Tensor-core GLM path: observation-sharded FP64 prep,
+ * exchange of (sums, bounds), series length decided ON THE DEVICE (every instantiation of the kernel is launched and all
+ * but the chosen one exit at once), coefficient rows pushed into the peers' bulk regions, kernel, local (max, sum),
+ * exchange, scale.  Other families / JP_PATH_FP64: plugin kernel, (max, sum), exchange, scale.  When the a-priori bounds of
+ * the tensor-core path do not hold, the first blocking call on the posterior (jp_get_*, jp_marginal_coords_p2p,
+ * jp_fit_p2p_check) returns JP_ERR_UNSUPPORTED on EVERY rank (they see the same bits): call again with JP_PATH_FP64. */
+int jp_fit_p2p(jp_posterior* post, const jp_fit_args* args, jp_comm* comm);
+int jp_fit_p2p_check(jp_posterior* post);
+/* marginal(jp, f) of K coordinates of the node-sharded posterior, globally: moments, exchange, knot candidates, exchange,
+ * combine in rank order (every rank gets identical bits); results to the host (blocking).  Reference
+ * src/marginal_posterior.jl:117-123, src/interp.jl:448-457. */
+int jp_marginal_coords_p2p(jp_posterior* post, jp_comm* comm, int K, const int* h_coords, double* h_mu, double* h_sigma,
+                           double* h_value_nodes, double* h_weight_nodes);
 
 /* results to the host (blocking).  h_theta: d x M_local row-major (coordinate k of node m at
  * [k*M_local + m]); h_logdens: log-density + neg_min per node; h_density: normalised weights. */

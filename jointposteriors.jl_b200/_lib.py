@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.environ.get("JPCUDA_LIB") or os.path.join(_HERE, "libjpcuda.so")
 _lib = None
 
-JP_OK, JP_ERR_BAD_ARG, JP_ERR_NOT_PD, JP_ERR_CUDA, JP_ERR_NO_DEVICE, JP_ERR_ALLOC, JP_ERR_UNSUPPORTED = range(7)
+JP_OK, JP_ERR_BAD_ARG, JP_ERR_NOT_PD, JP_ERR_CUDA, JP_ERR_NO_DEVICE, JP_ERR_ALLOC, JP_ERR_UNSUPPORTED, JP_ERR_COMM = range(8)
 PATH_AUTO, PATH_FP64, PATH_TC = 0, 1, 2
 GRID_KNOTS = 100
 
@@ -68,6 +68,8 @@ SYMBOLS = [
     "jp_posterior_create", "jp_posterior_free", "jp_posterior_size",
     "jp_fit", "jp_fit_local", "jp_fit_local_sum", "jp_fit_normalise", "jp_fit_local_stats", "jp_fit_normalise_gathered",
     "jp_fit_prep_len", "jp_fit_prep_local", "jp_fit_prep_gathered", "jp_fit_coef_slab", "jp_fit_local_stats_prepared",
+    "jp_comm_create", "jp_comm_ipc_handle", "jp_comm_connect_ipc", "jp_comm_connect_local", "jp_comm_bulk_bytes", "jp_comm_status",
+    "jp_comm_destroy", "jp_comm_all_gather", "jp_fit_p2p", "jp_fit_p2p_check", "jp_marginal_coords_p2p",
     "jp_get_theta", "jp_get_logdens", "jp_get_density", "jp_dev_theta", "jp_dev_density", "jp_fit_path_used",
     "jp_fit_diagnostics",
     "jp_marginal_coords", "jp_marginal_values", "jp_marginal_sorted", "jp_marginal_buffer", "jp_marginal_knots_from_sort",
@@ -92,6 +94,7 @@ def lib():
     L.jp_grid_size.restype = C.c_longlong
     L.jp_posterior_size.restype = C.c_longlong
     L.jp_ctx_launch_count.restype = C.c_longlong
+    L.jp_comm_bulk_bytes.restype = C.c_longlong
     L.jp_quantile.restype = C.c_double
     L.jp_cdf.restype = C.c_double
     L.jp_dev_theta.restype = C.c_void_p

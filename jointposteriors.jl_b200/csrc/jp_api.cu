@@ -314,7 +314,7 @@ int jp_posterior_free(jp_posterior* p) {
   jp_dfree(c, p->d_stats); jp_dfree(c, p->d_mu); jp_dfree(c, p->d_U); jp_dfree(c, p->d_tcode); jp_tc_post_free(p);
   jp_dfree(c, p->d_vals); jp_dfree(c, p->d_bins); jp_dfree(c, (void*)p->d_vptr); jp_dfree(c, p->d_perm_a); jp_dfree(c, p->d_perm_b); jp_dfree(c, p->d_hist);
   jp_dfree(c, p->d_sv); jp_dfree(c, p->d_sw); jp_dfree(c, p->d_cw); jp_dfree(c, p->d_mout);
-  jp_dfree(c, p->d_cmom); jp_dfree(c, p->d_coords);
+  jp_dfree(c, p->d_cmom); jp_dfree(c, p->d_coords); jp_dfree(c, p->d_cand);
   delete p;
   return JP_OK;
 }
@@ -325,6 +325,7 @@ const double* jp_dev_density(const jp_posterior* p) { return p ? p->d_density : 
 int jp_fit_path_used(const jp_posterior* p) { return p ? p->path_used : 0; }
 int jp_fit_diagnostics(const jp_posterior* p, double* h_out8) {
   JP_REQUIRE(p && h_out8, "jp_fit_diagnostics: null argument");
+  jp_fit_tc_verify(const_cast<jp_posterior*>(p));      // a device-side decision not yet read back (blocks once)
   for (int i = 0; i < 8; ++i) h_out8[i] = p->tc_bounds[i];
   return JP_OK;
 }
@@ -333,15 +334,17 @@ static int download(jp_posterior* p, const double* d_src, double* h_dst, size_t 
   JP_REQUIRE(p && h_dst, "jp_get_*: null argument");
   // The caller's array is pageable (a Julia Vector / numpy array): results that fit the context's pinned buffer are
   // DMA-ed there at PCIe speed and copied out by the host; larger ones take the driver's staged pageable path.
+  JP_CUDA(cudaSetDevice(p->ctx->device));
   if (n <= JP_PINNED_DOUBLES) {
+    JP_CUDA(jp_pinned_acquire(p->ctx));      // no earlier host-to-device copy may still be reading the staging buffer
     JP_CUDA(cudaMemcpyAsync(p->ctx->h_pinned, d_src, n * 8, cudaMemcpyDeviceToHost, p->ctx->stream));
     JP_CUDA(cudaStreamSynchronize(p->ctx->stream));
     std::memcpy(h_dst, p->ctx->h_pinned, n * 8);
-    return JP_OK;
+    return jp_fit_tc_verify(p);
   }
   JP_CUDA(cudaMemcpyAsync(h_dst, d_src, n * 8, cudaMemcpyDeviceToHost, p->ctx->stream));
   JP_CUDA(cudaStreamSynchronize(p->ctx->stream));
-  return JP_OK;
+  return jp_fit_tc_verify(p);
 }
 int jp_get_theta(jp_posterior* p, double* h) { return download(p, p ? p->d_theta : nullptr, h, p ? (size_t)p->M * p->d : 0); }
 int jp_get_logdens(jp_posterior* p, double* h) { return download(p, p ? p->d_logdens : nullptr, h, p ? (size_t)p->M : 0); }

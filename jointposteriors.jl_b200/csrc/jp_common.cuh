@@ -214,6 +214,8 @@ struct jp_posterior {
   double* d_sw = nullptr;        // sorted weights K x M
   double* d_cw = nullptr;        // cumulative weights K x M
   double* d_mout = nullptr;      // K x (2 + 200 + 2) results
+  double* d_cand = nullptr;      // K x 98 x 6 knot candidates on their way to the peers (jp_marginal_coords_p2p)
+  int K_cap_cand = 0;
 };
 #define JP_POST_PART_SPLITS 32   // d_part holds [splits <= 32][M] observation partial sums + [M] (lj + prior)
 
@@ -308,6 +310,76 @@ __device__ __forceinline__ unsigned long long jp_sortable(double x) {
 }
 #endif
 
+// ---------------------------------------------------------------------------- in-library exchange over NVLink peer memory
+// One MAILBOX per rank (plain cudaMalloc memory, exported through CUDA IPC and mapped by every peer): small per-channel
+// slots that the peers WRITE into with ordinary stores over NVLink, one 8-byte flag per (channel, parity, sender) that
+// carries the sequence number of the exchange, and a bulk region for the coefficient rows of the tensor-core path.  An
+// exchange is one kernel: block p copies this rank's payload into peer p's slot, publishes it (fence.sys + st.release.sys of
+// the sequence number) and then waits for peer p's payload to arrive in the own mailbox (ld.acquire.sys).  No NCCL, no host
+// round trip; slots alternate by sequence parity, and every consumer of a slot precedes the rank's next send on that channel
+// in stream order, so a sender can never overwrite data its peer still reads.
+#define JP_COMM_MAX_WORLD 8
+enum { JP_CH_PREP = 0, JP_CH_STATS, JP_CH_MOM, JP_CH_KNOTS, JP_CH_BULK, JP_CH_USER, JP_COMM_NCHAN };
+#define JP_COMM_HEADER_BYTES 4096      // error word + flags
+#define JP_COMM_KMAX 64                // marginals per exchange of the knot candidates
+struct JpCommDev {                     // what the kernels need, by value
+  unsigned char* const* peer;          // device array [world]: mailbox base of every rank as mapped HERE (own one at [rank])
+  unsigned char* self;
+  int rank, world;
+  long long timeout_ns;
+};
+struct jp_comm {
+  jp_ctx* ctx = nullptr;
+  int rank = 0, world = 1;
+  unsigned char* mailbox = nullptr;
+  size_t bytes = 0, bulk_off = 0, bulk_bytes = 0;
+  unsigned char* peer_h[JP_COMM_MAX_WORLD] = {nullptr};
+  bool ipc_opened[JP_COMM_MAX_WORLD] = {false};
+  bool connected = false;
+  unsigned char** d_peer = nullptr;
+  unsigned long long seq[JP_COMM_NCHAN] = {0};
+  size_t data_off[JP_COMM_NCHAN][2] = {{0}};
+  size_t cap_doubles[JP_COMM_NCHAN] = {0};     // capacity of one (channel, parity) region, all ranks together
+  unsigned int* d_counter = nullptr;           // arrival counter of the bulk push
+  long long timeout_ns = 60000000000ll;
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long* jp_comm_flag(unsigned char* mailbox, int chan, int parity, int sender) {
+  return reinterpret_cast<unsigned long long*>(mailbox + 64) + ((size_t)(chan * 2 + parity) * JP_COMM_MAX_WORLD + sender);
+}
+__device__ __forceinline__ void jp_st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long jp_ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ long long jp_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until the flag carries `seq` (or a later exchange's number); on timeout record the channel in the mailbox's error word
+__device__ __forceinline__ void jp_comm_wait_flag(const JpCommDev& c, int chan, int parity, int sender, unsigned long long seq) {
+  const unsigned long long* f = jp_comm_flag(c.self, chan, parity, sender);
+  const long long t0 = jp_globaltimer();
+  while (jp_ld_acquire_sys(f) < seq) {
+    __nanosleep(64);
+    if (jp_globaltimer() - t0 > c.timeout_ns) {
+      atomicExch(reinterpret_cast<int*>(c.self), 1 + chan + 16 * sender);
+      break;
+    }
+  }
+}
+#endif
+JpCommDev jp_comm_dev(const jp_comm* c);
+// all_gather of n doubles per rank on channel `chan` (stream-ordered, asynchronous): *d_gathered = [world][n] in the own mailbox
+int jp_comm_exchange(jp_comm* c, int chan, const double* d_src, int n, const double** d_gathered);
+// the bulk region (coefficient rows): its flags follow the same sequence protocol on JP_CH_BULK, single-buffered
+int jp_comm_bulk_begin(jp_comm* c, unsigned long long* seq);                 // next sequence number of the bulk channel
+int jp_comm_wait(jp_comm* c, int chan, int parity, unsigned long long seq);  // one tiny kernel: all senders' flags >= seq
+
 // ---------------------------------------------------------------------------- internal entry points
 int jp_grid_build(jp_ctx* ctx, int rule, int d, int level, jp_grid* g);
 // finish = false: the per-node finish (sum of the partials -> log-density) is left to the fused stage-4 kernel (post->fin)
@@ -321,6 +393,8 @@ int jp_fit_tc_prep_gathered(jp_posterior* post, const jp_fit_args* args, const d
                             int* n_rows);
 int jp_fit_tc_coef_slab(jp_posterior* post, int n_rows, float** d_local, float** d_all, long long* count);
 int jp_fit_tc_run_prepared(jp_posterior* post, const jp_fit_args* args, bool finish = true);
+int jp_fit_tc_launch_dev(jp_posterior* post, const jp_fit_args* args, jp_comm* comm);   // device-side series-length decision
+int jp_fit_tc_verify(jp_posterior* post);      // read that decision back (first blocking call after the fit)
 void jp_tc_data_free(jp_data* data);
 void jp_tc_post_free(jp_posterior* post);
 int jp_upload_fit_consts(jp_posterior* post, const jp_fit_args* args);   // mu_hat, U, transform codes -> device

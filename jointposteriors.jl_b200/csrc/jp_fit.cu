@@ -231,11 +231,10 @@ __global__ void __launch_bounds__(256) jp_expw_sum_kernel(long long M, long long
   s = jp_block_sum(s, sm);
   if (threadIdx.x == 0) bpart[blockIdx.x] = s;
   if (!jp_last_block(counter, gridDim.x)) return;
-  if (threadIdx.x == 0) {
-    double t = 0;
-    for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(bpart + b);
-    out[0] = t;
-  }
+  double t = 0;      // thread t takes blocks t, t + 256, .. in ascending order, then the fixed tree
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += 256) t += __ldcg(bpart + b);
+  t = jp_block_sum(t, sm);
+  if (threadIdx.x == 0) out[0] = t;
 }
 __global__ void jp_scale_kernel(long long M, double* __restrict__ e, const double* __restrict__ gsum) {
   long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -312,29 +311,7 @@ __global__ void __launch_bounds__(JP_S4_THREADS) jp_stage4_kernel(const Stage4Pa
   }
   mx = jp_block_max(mx, sm);
   if (threadIdx.x == 0) P.bmax[blockIdx.x] = mx;
-  __shared__ double s_co[2][JP_S4_WARPS][JP_MAX_D];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (P.cmom) {      // extrema of every coordinate over this block's slice (they do not depend on the weights)
-    for (int k = 0; k < P.d; ++k) {
-      const double* th = P.theta + (size_t)k * P.M;
-      double mn = INFINITY, mxk = -INFINITY;
-      for (long long m = b0 + threadIdx.x; m < b1; m += JP_S4_THREADS) {
-        const double v = th[m];
-        mn = fmin(mn, v);
-        mxk = fmax(mxk, v);
-      }
-      mn = jp_warp_min(mn);
-      mxk = jp_warp_max(mxk);
-      if (lane == 0) { s_co[0][wid][k] = mn; s_co[1][wid][k] = mxk; }
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < P.d; k += JP_S4_THREADS) {
-      double mn = s_co[0][0][k], mxk = s_co[1][0][k];
-      for (int i = 1; i < JP_S4_WARPS; ++i) { mn = fmin(mn, s_co[0][i][k]); mxk = fmax(mxk, s_co[1][i][k]); }
-      double* o = P.cmom + ((size_t)blockIdx.x * P.d + k) * 4;
-      o[2] = mn; o[3] = mxk;
-    }
-  }
   grid.sync();
   // ---- B
   double g = -INFINITY;
@@ -349,37 +326,39 @@ __global__ void __launch_bounds__(JP_S4_THREADS) jp_stage4_kernel(const Stage4Pa
   s = jp_block_sum(s, sm);
   if (threadIdx.x == 0) P.bsum[blockIdx.x] = s;
   grid.sync();
-  // ---- C
-  if (threadIdx.x == 0) {
-    double t = 0;
-    for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(P.bsum + b);
-    sm[32] = t;
-    if (blockIdx.x == 0) { P.stats[0] = g; P.stats[1] = t; }
-  }
-  __syncthreads();
+  // ---- C: every block adds the block sums itself, all threads loading (thread t takes blocks t, t + 256, .. in ascending
+  // order, then the fixed tree of jp_block_sum: the same bits in every block; one thread walking the few hundred L2-resident
+  // partials alone cost ~35 us of dependent load latency per launch)
+  double tot = 0;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += JP_S4_THREADS) tot += __ldcg(P.bsum + b);
+  tot = jp_block_sum(tot, sm);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { P.stats[0] = g; P.stats[1] = tot; }
   if (!P.normalise) return;
-  const double tot = sm[32];
   for (long long m = b0 + threadIdx.x; m < b1; m += JP_S4_THREADS) P.e[m] = P.e[m] / tot;
   if (!P.cmom) return;
-  // weighted moments of every coordinate over this block's slice (each thread re-reads the weights it just wrote)
-  for (int k = 0; k < P.d; ++k) {
+  // Per-coordinate (sum w theta, sum w theta^2, min theta, max theta) over this block's slice, for stage 5: WARP w takes
+  // coordinates w, w + 8, ..; its lanes walk the slice of the coordinate's column (coalesced; the weights were just written by
+  // this block), then one shuffle tree per quantity -- the warp's result is the block's, no shared memory, no barrier per
+  // coordinate.  (One butterfly per thread-owned node and coordinate cost 8.5 M of this kernel's 13 M warp instructions.)
+  __syncthreads();
+  for (int k = wid; k < P.d; k += JP_S4_WARPS) {
     const double* th = P.theta + (size_t)k * P.M;
-    double s1 = 0, s2 = 0;
-    for (long long m = b0 + threadIdx.x; m < b1; m += JP_S4_THREADS) {
+    double s1 = 0, s2 = 0, mn = INFINITY, mxk = -INFINITY;
+    for (long long m = b0 + lane; m < b1; m += 32) {
       const double v = th[m], wv = P.e[m];
       s1 += wv * v;
       s2 += wv * (v * v);
+      mn = fmin(mn, v);
+      mxk = fmax(mxk, v);
     }
     s1 = jp_warp_sum(s1);
     s2 = jp_warp_sum(s2);
-    if (lane == 0) { s_co[0][wid][k] = s1; s_co[1][wid][k] = s2; }
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < P.d; k += JP_S4_THREADS) {
-    double s1 = 0, s2 = 0;
-    for (int i = 0; i < JP_S4_WARPS; ++i) { s1 += s_co[0][i][k]; s2 += s_co[1][i][k]; }
-    double* o = P.cmom + ((size_t)blockIdx.x * P.d + k) * 4;
-    o[0] = s1; o[1] = s2;
+    mn = jp_warp_min(mn);
+    mxk = jp_warp_max(mxk);
+    if (lane == 0) {
+      double* o = P.cmom + ((size_t)blockIdx.x * P.d + k) * 4;
+      o[0] = s1; o[1] = s2; o[2] = mn; o[3] = mxk;
+    }
   }
 }
 
@@ -764,6 +743,39 @@ int jp_fit_normalise_gathered(jp_posterior* post, const double* d_gathered, int 
   jp_scale_gathered_kernel<<<gb, 256, 0, post->ctx->stream>>>(post->M, post->d_density, d_gathered, world, rank);
   JP_CHECK_LAUNCH(post->ctx);
   return JP_OK;
+}
+
+// The node-sharded fit with the exchanges inside the library (csrc/jp_comm.cu): one asynchronous queue per rank.
+int jp_fit_p2p(jp_posterior* post, const jp_fit_args* args, jp_comm* comm) {
+  JP_REQUIRE(post && comm, "jp_fit_p2p: null argument");
+  JP_REQUIRE(comm->ctx == post->ctx, "jp_fit_p2p: the communicator belongs to another context");
+  JP_ENTER_CTX(post->ctx);
+  JP_TRY(jp_fit_check_args(post, args));
+  post->sorted_valid = false;
+  post->K_last = 0;
+  post->cmom_valid = false;
+  int path = args->path;
+  if (path == JP_PATH_AUTO) path = jp_fit_tc_supported(post, args) ? JP_PATH_TC : JP_PATH_FP64;
+  if (path == JP_PATH_TC) JP_TRY(jp_fit_tc_launch_dev(post, args, comm));
+  else JP_TRY(jp_fit_fp64_launch(post, args, false));
+  if (comm->world == 1) return jp_stage4_launch(post, true, post->d_stats);
+  JP_TRY(jp_stage4_launch(post, false, post->d_stats));      // finish + local max + sum relative to it
+  const double* g = nullptr;
+  JP_TRY(jp_comm_exchange(comm, JP_CH_STATS, post->d_stats, 2, &g));
+  if (post->M > 0) {
+    jp_scale_gathered_kernel<<<(unsigned)((post->M + 255) / 256), 256, 0, post->ctx->stream>>>(post->M, post->d_density, g, comm->world,
+                                                                                              comm->rank);
+    JP_CHECK_LAUNCH(post->ctx);
+  }
+  JP_MARK(post->ctx, "fit:normalised");
+  return JP_OK;
+}
+
+int jp_fit_p2p_check(jp_posterior* post) {
+  JP_REQUIRE(post, "jp_fit_p2p_check: null posterior");
+  JP_ENTER_CTX(post->ctx);
+  JP_CUDA(cudaStreamSynchronize(post->ctx->stream));
+  return jp_fit_tc_verify(post);
 }
 
 int jp_fit(jp_posterior* post, const jp_fit_args* args) {

@@ -102,9 +102,17 @@ struct TcDataState {
   double* d_bounds = nullptr;  // [TC_PREP_BLOCKS_MAX][TC_NBOUND]
   int prep_blocks = TC_PREP_BLOCKS;   // blocks of tc_obs_prep_kernel for a slice of n_loc observations
   double* d_comb = nullptr;    // [TC_NBOUND]: bounds combined over the ranks (sharded prep)
+  double* d_loc = nullptr;     // [L]: this rank's (slice sums | slice bounds) on their way to the peers (jp_fit_p2p)
   int glm_blocks = 0;
   cudaEvent_t ev_bounds = nullptr;   // the bounds have reached the host (the fit waits on it, not on the whole stream)
   CUtensorMap tmA;
+};
+
+// what tc_decide_kernel leaves: the series length (0: bounds not met), whether the economised coefficients are used, and the
+// diagnostics the host-side decision records in post->tc_bounds
+struct TcDecision {
+  int NC, fold, pad0, pad1;
+  double diag[6];
 };
 
 struct TcPostState {
@@ -115,8 +123,11 @@ struct TcPostState {
   double* d_part = nullptr;    // [part_chunks][P][2] per-chunk even / odd remainder sums
   int part_chunks = 0;
   bool node_prep_queued = false;   // sharded prep: tc_node_prep already runs under the host's wait for the bounds
+  TcDecision* d_dec = nullptr;   // series length decided on the device (jp_fit_tc_launch_dev)
+  bool dec_pending = false;        // ... and not yet read back by the host
   CUtensorMap tmB;
 };
+
 
 // ------------------------------------------------------------------------------------ small device helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -493,8 +504,7 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
 //                                       n = NC + 4 for the even orders k = 4, 6, .., NC + 2 (rows 1, 3, ..)
 // (tools/gen_fold.py: x^n ~ sum_k kappa_k x^k on |x| <= 1 in the span the kernel can evaluate).  In place on the
 // first NC coefficient rows; streams (NC + 3) rows in and NC rows out, 4 bytes per observation and row.
-__global__ void __launch_bounds__(256)
-tc_fold_kernel(int NC, long long n, long long N_pad, double z_ref, float* __restrict__ coef) {
+__device__ __forceinline__ void tc_fold_body(int NC, long long n, long long N_pad, double z_ref, float* __restrict__ coef) {
   const int j = (NC - 4) >> 1, h = NC >> 1;
   // n observations starting at coef; N_pad is the row stride of the whole array
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -510,6 +520,16 @@ tc_fold_kernel(int NC, long long n, long long N_pad, double z_ref, float* __rest
       pw *= a2;
     }
   }
+}
+__global__ void __launch_bounds__(256)
+tc_fold_kernel(int NC, long long n, long long N_pad, double z_ref, float* __restrict__ coef) {
+  tc_fold_body(NC, n, N_pad, z_ref, coef);
+}
+// the same with the series length (and whether to fold at all) read from the device-side decision
+__global__ void __launch_bounds__(256)
+tc_fold_dev_kernel(const TcDecision* __restrict__ dec, long long n, long long N_pad, double z_ref, float* __restrict__ coef) {
+  if (dec->NC < 4 || !dec->fold) return;
+  tc_fold_body(dec->NC, n, N_pad, z_ref, coef);
 }
 
 // Per node: delta = U z, theta = mu + delta (all transforms are the identity on this path), in two kernels that run on
@@ -637,6 +657,7 @@ struct TcKernelParams {
   long long coef_slice_stride;
   int tiles_per_slice;
   double* part;           // [chunks][P][2]: even and odd part of the remainder sum of a pair
+  const int* nc_sel;      // non-null: the series length chosen on the device; an instantiation with another NC exits at once
   long long* dbg;         // profiling builds, MODE 5: per-tile clock64 stamps of CTA 0 ([6][TC_DBG_TILES]), else null
 };
 #define TC_DBG_TILES 2048
@@ -724,6 +745,7 @@ template <int NC, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcKernelParams P) {
   extern __shared__ uint8_t smem_raw[];
+  if (P.nc_sel != nullptr && *P.nc_sel != NC) return;   // device-side series-length decision: uniform over the grid
   // carve-up (1024-byte aligned for the 128-byte swizzle): pair operands, observation ring, reduction buffer, barriers
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sB = base;                                              // nbbuf x ka x (96 x 128 B)
@@ -1088,7 +1110,7 @@ void jp_tc_data_free(jp_data* data) {
   TcDataState* s = static_cast<TcDataState*>(data->tc_state);
   if (!s) return;
   jp_dfree(data->ctx, s->d_xs); jp_dfree(data->ctx, s->d_coef); jp_dfree(data->ctx, s->d_coef_all); jp_dfree(data->ctx, s->d_sums);
-  jp_dfree(data->ctx, s->d_work); jp_dfree(data->ctx, s->d_bounds); jp_dfree(data->ctx, s->d_comb);
+  jp_dfree(data->ctx, s->d_work); jp_dfree(data->ctx, s->d_bounds); jp_dfree(data->ctx, s->d_comb); jp_dfree(data->ctx, s->d_loc);
   if (s->ev_bounds) cudaEventDestroy(s->ev_bounds);
   delete s;
   data->tc_state = nullptr;
@@ -1096,7 +1118,7 @@ void jp_tc_data_free(jp_data* data) {
 void jp_tc_post_free(jp_posterior* post) {
   TcPostState* s = static_cast<TcPostState*>(post->tc_state);
   if (!s) return;
-  jp_dfree(post->ctx, s->d_ds); jp_dfree(post->ctx, s->d_quad); jp_dfree(post->ctx, s->d_part);
+  jp_dfree(post->ctx, s->d_ds); jp_dfree(post->ctx, s->d_quad); jp_dfree(post->ctx, s->d_part); jp_dfree(post->ctx, s->d_dec);
   delete s;
   post->tc_state = nullptr;
 }
@@ -1197,10 +1219,12 @@ template <int NC, int MODE>
 static int launch_tc_mode(jp_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcKernelParams& kp, size_t smem) {
   JP_CUDA(cudaFuncSetAttribute(jp_glm_tc_kernel<NC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = std::min(ctx->sm_count, kp.n_pair_tiles * kp.chunks);
-  cudaEventRecord(ctx->ev_k0, ctx->stream);
+  if (!kp.nc_sel) cudaEventRecord(ctx->ev_k0, ctx->stream);      // guarded launches are bracketed as a group by the caller
   jp_glm_tc_kernel<NC, MODE><<<grid, TC_THREADS, smem, ctx->stream>>>(tmA, tmB, kp);
-  cudaEventRecord(ctx->ev_k1, ctx->stream);
-  ctx->ev_valid = true;
+  if (!kp.nc_sel) {
+    cudaEventRecord(ctx->ev_k1, ctx->stream);
+    ctx->ev_valid = true;
+  }
   JP_CHECK_LAUNCH(ctx);
   return JP_OK;
 }
@@ -1341,7 +1365,8 @@ static int tc_node_operand(jp_posterior* post, const jp_fit_args* args) { return
 static int tc_node_quad(jp_posterior* post, const jp_fit_args* args, cudaStream_t st) { return tc_node_prep_part<1>(post, args, st); }
 
 // the tensor-core kernel and the per-node finish (after tc_node_prep)
-static int tc_run_kernel(jp_posterior* post, const jp_fit_args* args, int NC, bool finish) {
+static int tc_run_kernel(jp_posterior* post, const jp_fit_args* args, int NC, bool finish, const int* nc_sel = nullptr,
+                         const float* coef_gathered = nullptr) {
   jp_ctx* ctx = post->ctx;
   const jp_data* data = post->data;
   TcDataState* ds = static_cast<TcDataState*>(data->tc_state);
@@ -1388,7 +1413,10 @@ static int tc_run_kernel(jp_posterior* post, const jp_fit_args* args, int NC, bo
     ps->part_chunks = kp.chunks;
   }
   kp.P = ps->P;
-  if (ds->world > 1) {
+  if (ds->world > 1 && coef_gathered) {      // [world][NC][n_loc] in the mailbox's bulk region (jp_fit_p2p)
+    kp.coef = coef_gathered;
+    kp.coef_slice_stride = (long long)NC * ds->n_loc;
+  } else if (ds->world > 1) {
     JP_REQUIRE(ds->d_coef_all && ds->nc_all == NC, "tensor-core path: the coefficient rows of the other ranks have not been gathered "
                "(jp_fit_coef_slab + one all_gather, then jp_fit_local_stats_prepared)");
     kp.coef = ds->d_coef_all;
@@ -1400,6 +1428,7 @@ static int tc_run_kernel(jp_posterior* post, const jp_fit_args* args, int NC, bo
   kp.coef_n_loc = ds->n_loc;
   kp.tiles_per_slice = (int)(ds->n_loc / TC_OBS_TILE);
   kp.part = ps->d_part;
+  kp.nc_sel = nc_sel;
   kp.dbg = nullptr;
   int stc;
   if (NC == 4) stc = launch_tc<4>(ctx, ds->tmA, ps->tmB, kp, smem);
@@ -1450,6 +1479,8 @@ __global__ void __launch_bounds__(32 * TC_NBOUND) tc_bounds_reduce_kernel(const 
 int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args, bool finish) {
   jp_ctx* ctx = post->ctx;
   JP_MARK(ctx, "fit:start");
+  static const bool dev_decision = getenv("JP_TC_DEVICE_DECISION") != nullptr;   // A/B aid: no host round trip inside the fit
+  if (dev_decision && !finish) return jp_fit_tc_launch_dev(post, args, nullptr);
   JP_TRY(tc_setup(post, args, 1, 0));
   JP_MARK(ctx, "fit:setup+consts");
   TcDataState* ds = static_cast<TcDataState*>(post->data->tc_state);
@@ -1575,3 +1606,135 @@ int jp_fit_tc_run_prepared(jp_posterior* post, const jp_fit_args* args, bool fin
   JP_REQUIRE(post->tc_bounds[3] >= 4, "jp_fit_run_prepared: no series length has been decided (call the prep phases first)");
   return tc_run(post, args, (int)post->tc_bounds[3], finish);
 }
+
+// ---- the whole tensor-core fit as ONE asynchronous queue: series length decided on the device ------------------------------
+// (jp_fit_p2p on every rank of a node-sharded fit; one GPU with JP_TC_DEVICE_DECISION=1 or under stream capture)
+__global__ void tc_decide_kernel(const double* __restrict__ comb, double z_max, int no_fold, TcDecision* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // jp_tc_choose_order / tc_decide, statement by statement
+  const double tdelta = comb[0] * z_max;
+  const double err_round = 2e-6 * sqrt(comb[13]);
+  double err_trunc = 0;
+  int NC = 0, fold = 0;
+  if (tdelta <= 2.0 && 8.0 * err_round <= 2e-7) {
+    for (int j = 0; j < TC_NORD && NC == 0; ++j) {
+      if (!no_fold && j < TC_NFOLD && comb[14 + j] * (1 + 1e-5) <= TC_TRUNC_REF && comb[14 + TC_NFOLD + j] * (1 + 1e-5) <= TC_TRUNC_MAX) {
+        err_trunc = comb[14 + j] * (1 + 1e-5);
+        fold = 1;
+        NC = 2 * j + 4;
+      } else if (comb[2 + j] <= TC_TRUNC_REF && comb[7 + j] <= TC_TRUNC_MAX) {
+        err_trunc = comb[2 + j];
+        NC = 2 * j + 4;
+      }
+    }
+  }
+  out->NC = NC; out->fold = fold; out->pad0 = out->pad1 = 0;
+  out->diag[0] = tdelta; out->diag[1] = err_trunc; out->diag[2] = err_round; out->diag[3] = NC;
+  out->diag[4] = 2e-6 * comb[12]; out->diag[5] = fold;
+}
+
+// This rank's first NC coefficient rows (contiguous in its slab) into slot `rank` of every peer's bulk region
+// [world][NC][n_loc], 16 bytes per store over NVLink; the block that finishes last raises this rank's flag on every peer.
+__global__ void __launch_bounds__(256)
+tc_coef_push_kernel(const JpCommDev c, const TcDecision* __restrict__ dec, const float* __restrict__ coef, long long n_loc,
+                    size_t bulk_off, unsigned int* __restrict__ counter, unsigned long long seq) {
+  const int NC = dec->NC;
+  const long long count4 = (long long)NC * n_loc / 4;      // n_loc is a multiple of the 128-observation tile
+  const float4* src = reinterpret_cast<const float4*>(coef);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    for (int p = 0; p < c.world; ++p) reinterpret_cast<float4*>(c.peer[p] + bulk_off)[(long long)c.rank * count4 + i] = v;
+  }
+  __shared__ unsigned int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned int t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1u);
+    if (s_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (s_last && (int)threadIdx.x < c.world) {
+    __threadfence_system();
+    jp_st_release_sys(jp_comm_flag(c.peer[threadIdx.x], JP_CH_BULK, 0, c.rank), seq);
+  }
+}
+
+int jp_fit_tc_launch_dev(jp_posterior* post, const jp_fit_args* args, jp_comm* comm) {
+  jp_ctx* ctx = post->ctx;
+  const int world = comm ? comm->world : 1, rank = comm ? comm->rank : 0;
+  JP_MARK(ctx, "fit:start");
+  JP_TRY(tc_setup(post, args, world, rank));
+  TcDataState* ds = static_cast<TcDataState*>(post->data->tc_state);
+  TcPostState* ps = static_cast<TcPostState*>(post->tc_state);
+  const int d = args->d, nE1 = d + d * (d + 1) / 2 + 1, L = nE1 + TC_NBOUND;
+  if (!ps->d_dec) JP_CUDA(jp_dmalloc(ctx, &ps->d_dec, sizeof(TcDecision)));
+  if (world > 1) {
+    if (!ds->d_loc) JP_CUDA(jp_dmalloc(ctx, &ds->d_loc, (size_t)L * 8));
+    const size_t need = (size_t)world * TC_NCMAX * (size_t)ds->n_loc * sizeof(float);
+    JP_REQUIRE(comm->bulk_bytes >= need, "jp_fit_p2p: the communicator's bulk region holds %zu bytes, the coefficient rows of %lld "
+               "observations on %d ranks may need %zu (jp_comm_create)", comm->bulk_bytes, ds->N, world, need);
+  }
+  const double z_max = std::sqrt(post->grid->zmax2), z_ref = std::min(z_max, 6.0);
+  // side: coefficients + bounds of this rank's slice; side2: its sums (one GPU: then the quadratic part); main: node operand
+  JP_TRY(tc_prep_slice(post, args, rank, world > 1 ? ds->d_loc : ds->d_sums));
+  tc_bounds_reduce_kernel<<<1, 32 * TC_NBOUND, 0, ctx->side>>>(ds->d_bounds, ds->prep_blocks, world > 1 ? ds->d_loc + nE1 : ds->d_comb);
+  JP_CHECK_LAUNCH(ctx);
+  if (world == 1) JP_TRY(tc_node_quad(post, args, ctx->side2));
+  JP_TRY(tc_node_operand(post, args));
+  JP_TRY(tc_join_side(ctx));
+  JP_MARK(ctx, "fit:prep_joined");
+  if (world > 1) {
+    const double* g = nullptr;
+    JP_TRY(jp_comm_exchange(comm, JP_CH_PREP, ds->d_loc, L, &g));
+    tc_combine_gathered_kernel<<<(L + 127) / 128, 128, 0, ctx->stream>>>(g, world, L, nE1, ds->d_sums, ds->d_comb);
+    JP_CHECK_LAUNCH(ctx);
+    JP_MARK(ctx, "fit:prep_exchanged");
+    JP_TRY(tc_node_quad(post, args, ctx->stream));
+  }
+  static const bool no_fold = getenv("JP_TC_NO_FOLD") != nullptr;
+  tc_decide_kernel<<<1, 32, 0, ctx->stream>>>(ds->d_comb, z_max, no_fold ? 1 : 0, ps->d_dec);
+  JP_CHECK_LAUNCH(ctx);
+  tc_fold_dev_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ps->d_dec, ds->n_loc, ds->n_loc, z_ref, ds->d_coef);
+  JP_CHECK_LAUNCH(ctx);
+  const float* coef_gathered = nullptr;
+  if (world > 1) {
+    unsigned long long seq = 0;
+    JP_TRY(jp_comm_bulk_begin(comm, &seq));
+    const int pb = (int)std::max<long long>(1, std::min<long long>(2LL * ctx->sm_count, ds->n_loc / 256));
+    tc_coef_push_kernel<<<pb, 256, 0, ctx->stream>>>(jp_comm_dev(comm), ps->d_dec, ds->d_coef, ds->n_loc, comm->bulk_off,
+                                                     comm->d_counter, seq);
+    JP_CHECK_LAUNCH(ctx);
+    JP_TRY(jp_comm_wait(comm, JP_CH_BULK, 0, seq));
+    coef_gathered = reinterpret_cast<const float*>(comm->mailbox + comm->bulk_off);
+    JP_MARK(ctx, "fit:coef_exchanged");
+  }
+  // every instantiation is queued; the four the device did not choose return before touching anything
+  JP_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
+  for (int NC = 4; NC <= TC_NCMAX; NC += 2) JP_TRY(tc_run_kernel(post, args, NC, false, &ps->d_dec->NC, coef_gathered));
+  JP_CUDA(cudaEventRecord(ctx->ev_k1, ctx->stream));
+  ctx->ev_valid = true;
+  ps->dec_pending = true;
+  post->tc_bounds[3] = -1;       // not known to the host until jp_fit_tc_verify
+  return JP_OK;
+}
+
+// The host reads the device's decision at its first blocking call after the fit (the result downloads synchronise anyway).
+// JP_ERR_UNSUPPORTED: the bounds were not met and no instantiation ran -- the results of this fit are garbage.
+int jp_fit_tc_verify(jp_posterior* post) {
+  TcPostState* ps = post ? static_cast<TcPostState*>(post->tc_state) : nullptr;
+  if (!ps || !ps->dec_pending) return JP_OK;
+  ps->dec_pending = false;
+  TcDecision dec;
+  JP_CUDA(cudaStreamSynchronize(post->ctx->stream));
+  JP_CUDA(cudaMemcpy(&dec, ps->d_dec, sizeof dec, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 6; ++i) post->tc_bounds[i] = dec.diag[i];
+  if (dec.NC == 0) {
+    post->path_used = 0;
+    jp_set_error("tensor-core path: series bounds not met (max |Delta| %.3g, rounding estimate %.3g); use the FP64 path",
+                 dec.diag[0], dec.diag[2]);
+    return JP_ERR_UNSUPPORTED;
+  }
+  return JP_OK;
+}
+

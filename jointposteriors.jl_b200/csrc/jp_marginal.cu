@@ -80,14 +80,20 @@ jp_moments_kernel(const double* const* __restrict__ vptr, const double* __restri
     o[0] = s1; o[1] = s2; o[2] = mn; o[3] = mx;
   }
   if (!jp_last_block(counters + k, gridDim.x)) return;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {      // warp 0: lane l takes blocks l, l + 32, .. in ascending order, then the fixed shuffle tree
     s1 = 0; s2 = 0; mn = INFINITY; mx = -INFINITY;
-    for (int b = 0; b < (int)gridDim.x; ++b) {
+    for (int b = lane; b < (int)gridDim.x; b += 32) {
       s1 += __ldcg(bp + 4 * b); s2 += __ldcg(bp + 4 * b + 1);
       mn = fmin(mn, __ldcg(bp + 4 * b + 2)); mx = fmax(mx, __ldcg(bp + 4 * b + 3));
     }
-    double* o = out + (size_t)k * out_stride;
-    o[0] = s1; o[1] = s2; o[2] = mn; o[3] = mx;
+    s1 = jp_warp_sum(s1);
+    s2 = jp_warp_sum(s2);
+    mn = jp_warp_min(mn);
+    mx = jp_warp_max(mx);
+    if (lane == 0) {
+      double* o = out + (size_t)k * out_stride;
+      o[0] = s1; o[1] = s2; o[2] = mn; o[3] = mx;
+    }
   }
 }
 
@@ -422,23 +428,27 @@ jp_marginal_onepass_kernel(const int* __restrict__ coords, const double* __restr
   const int k = blockIdx.y, c = coords[k], lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   // extrema and moments of coordinate c from the stage-4 block partials, in block order
   {
-    double mn = INFINITY, mx = -INFINITY;
+    // all threads load (thread t takes stage-4 blocks t, t + 256, .. in ascending order), fixed shuffle tree, warps in warp
+    // order: reproducible, and no single thread walks the L2-resident partials alone
+    double mn = INFINITY, mx = -INFINITY, s1 = 0, s2 = 0;
     for (int b = threadIdx.x; b < nb4; b += JP_BIN_THREADS) {
-      const double* q = cmom + ((size_t)b * d + c) * 4;
-      mn = fmin(mn, __ldcg(q + 2));
-      mx = fmax(mx, __ldcg(q + 3));
+      const double2* q = reinterpret_cast<const double2*>(cmom + ((size_t)b * d + c) * 4);
+      const double2 s12 = __ldcg(q), mm = __ldcg(q + 1);
+      s1 += s12.x; s2 += s12.y;
+      mn = fmin(mn, mm.x);
+      mx = fmax(mx, mm.y);
     }
     mn = jp_warp_min(mn);
     mx = jp_warp_max(mx);
-    if (lane == 0) { s_red[2][wid] = mn; s_red[3][wid] = mx; }
+    s1 = jp_warp_sum(s1);
+    s2 = jp_warp_sum(s2);
+    if (lane == 0) { s_red[0][wid] = s1; s_red[1][wid] = s2; s_red[2][wid] = mn; s_red[3][wid] = mx; }
     __syncthreads();
     if (threadIdx.x == 0) {
-      mn = s_red[2][0]; mx = s_red[3][0];
-      for (int i = 1; i < JP_BIN_WARPS; ++i) { mn = fmin(mn, s_red[2][i]); mx = fmax(mx, s_red[3][i]); }
-      double s1 = 0, s2 = 0;
-      for (int b = 0; b < nb4; ++b) {
-        const double* q = cmom + ((size_t)b * d + c) * 4;
-        s1 += __ldcg(q); s2 += __ldcg(q + 1);
+      s1 = s_red[0][0]; s2 = s_red[1][0]; mn = s_red[2][0]; mx = s_red[3][0];
+      for (int i = 1; i < JP_BIN_WARPS; ++i) {
+        s1 += s_red[0][i]; s2 += s_red[1][i];
+        mn = fmin(mn, s_red[2][i]); mx = fmax(mx, s_red[3][i]);
       }
       s_mm[0] = s1; s_mm[1] = s2; s_mm[2] = mn; s_mm[3] = mx;
     }
@@ -619,6 +629,7 @@ static int run_marginals(jp_posterior* post, int K, double* h_mu, double* h_sigm
   JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, post->d_mout, (size_t)K * JP_MOUT_STRIDE * 8, cudaMemcpyDeviceToHost, st));
   JP_MARK(ctx, "marginals:d2h");
   JP_CUDA(cudaStreamSynchronize(st));
+  JP_TRY(jp_fit_tc_verify(post));      // a series length decided on the device is read back here (no-op otherwise)
   for (int k = 0; k < K; ++k) {
     const double* o = ctx->h_pinned + (size_t)k * JP_MOUT_STRIDE;
     if (h_mu) h_mu[k] = o[0];
@@ -658,6 +669,7 @@ static int run_marginals_onepass(jp_posterior* post, int K, const int* h_coords,
   JP_MARK(ctx, "marginals:onepass");
   JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, post->d_mout, (size_t)K * JP_MOUT_STRIDE * 8, cudaMemcpyDeviceToHost, st));
   JP_CUDA(cudaStreamSynchronize(st));
+  JP_TRY(jp_fit_tc_verify(post));      // a series length decided on the device is read back here (no-op otherwise)
   for (int k = 0; k < K; ++k) {
     const double* o = ctx->h_pinned + (size_t)k * JP_MOUT_STRIDE;
     if (h_mu) h_mu[k] = o[0];
@@ -885,12 +897,70 @@ int jp_marginal_combine_gathered(jp_posterior* post, int K, int world, const dou
   JP_CHECK_LAUNCH(ctx);
   JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, post->d_mout, (size_t)K * JP_MOUT_STRIDE * 8, cudaMemcpyDeviceToHost, st));
   JP_CUDA(cudaStreamSynchronize(st));
+  JP_TRY(jp_fit_tc_verify(post));      // a series length decided on the device is read back here (no-op otherwise)
   for (int k = 0; k < K; ++k) {
     const double* o = ctx->h_pinned + (size_t)k * JP_MOUT_STRIDE;
     if (h_mu) h_mu[k] = o[0];
     if (h_sigma) h_sigma[k] = o[1];
     if (h_vn) std::copy(o + 2, o + 2 + JP_GRID_KNOTS, h_vn + (size_t)k * JP_GRID_KNOTS);
     if (h_wn) std::copy(o + 2 + JP_GRID_KNOTS, o + 2 + 2 * JP_GRID_KNOTS, h_wn + (size_t)k * JP_GRID_KNOTS);
+  }
+  return JP_OK;
+}
+
+// marginal(jp, f) of K coordinates of a node-sharded posterior with the two exchanges inside the library (csrc/jp_comm.cu):
+// local moments -> exchange -> knot candidates against the global extrema -> exchange -> combine in rank order -> host
+int jp_marginal_coords_p2p(jp_posterior* post, jp_comm* comm, int K, const int* h_coords, double* h_mu, double* h_sigma,
+                           double* h_vn, double* h_wn) {
+  JP_REQUIRE(post && comm && h_coords, "jp_marginal_coords_p2p: null argument");
+  JP_REQUIRE(comm->ctx == post->ctx, "jp_marginal_coords_p2p: the communicator belongs to another context");
+  JP_REQUIRE(K >= 1, "jp_marginal_coords_p2p: K=%d", K);
+  JP_ENTER_CTX(post->ctx);
+  jp_ctx* ctx = post->ctx;
+  cudaStream_t st = ctx->stream;
+  const int world = comm->world;
+  for (int k0 = 0; k0 < K; k0 += JP_COMM_KMAX) {       // batches of at most JP_COMM_KMAX marginals per exchange
+    const int Kb = std::min(JP_COMM_KMAX, K - k0);
+    JP_REQUIRE(post->M >= 1, "marginal: this rank owns no node");
+    JP_TRY(ensure_marginal_buffers(post, Kb));
+    JP_TRY(set_value_pointers(post, Kb, h_coords + k0, nullptr));
+    if (Kb > post->K_cap_cand) {
+      jp_dfree(ctx, post->d_cand);
+      post->d_cand = nullptr;
+      post->K_cap_cand = 0;
+      JP_CUDA(jp_dmalloc(ctx, &post->d_cand, (size_t)Kb * (JP_GRID_KNOTS - 2) * 6 * 8));
+      post->K_cap_cand = Kb;
+    }
+    JP_MARK(ctx, "marginals:start");
+    double* d_mom = ctx->d_scratch;
+    JP_TRY(launch_moments(post, Kb, d_mom));
+    const double *gm = nullptr, *gc = nullptr;
+    JP_TRY(jp_comm_exchange(comm, JP_CH_MOM, d_mom, Kb * 4, &gm));
+    JP_MARK(ctx, "marginals:moments_exchanged");
+    double* d_minmax = ctx->d_bpart;
+    jp_minmax_gathered_kernel<<<(Kb + 127) / 128, 128, 0, st>>>(gm, world, Kb, d_minmax);
+    JP_CHECK_LAUNCH(ctx);
+    dim3 gb(post->bins_blocks, Kb);
+    jp_bins_kernel<<<gb, JP_BIN_THREADS, 0, st>>>(post->d_vptr, post->d_density, post->M, post->m0, d_minmax, 2, 0, post->d_bins);
+    JP_CHECK_LAUNCH(ctx);
+    jp_bins_combine_kernel<false><<<Kb, JP_COMBINE_THREADS, 0, st>>>(post->d_bins, post->bins_blocks, d_minmax, 2, 0, nullptr, 0, post->d_cand);
+    JP_CHECK_LAUNCH(ctx);
+    JP_TRY(jp_comm_exchange(comm, JP_CH_KNOTS, post->d_cand, Kb * (JP_GRID_KNOTS - 2) * 6, &gc));
+    JP_MARK(ctx, "marginals:knots_exchanged");
+    jp_combine_gathered_kernel<<<Kb, 128, 0, st>>>(gm, gc, world, Kb, post->d_mout);
+    JP_CHECK_LAUNCH(ctx);
+    JP_CUDA(jp_pinned_acquire(ctx));
+    JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, post->d_mout, (size_t)Kb * JP_MOUT_STRIDE * 8, cudaMemcpyDeviceToHost, st));
+    JP_CUDA(cudaStreamSynchronize(st));
+    JP_TRY(jp_fit_tc_verify(post));
+    for (int k = 0; k < Kb; ++k) {
+      const double* o = ctx->h_pinned + (size_t)k * JP_MOUT_STRIDE;
+      if (h_mu) h_mu[k0 + k] = o[0];
+      if (h_sigma) h_sigma[k0 + k] = o[1];
+      if (h_vn) std::copy(o + 2, o + 2 + JP_GRID_KNOTS, h_vn + (size_t)(k0 + k) * JP_GRID_KNOTS);
+      if (h_wn) std::copy(o + 2 + JP_GRID_KNOTS, o + 2 + 2 * JP_GRID_KNOTS, h_wn + (size_t)(k0 + k) * JP_GRID_KNOTS);
+    }
+    post->K_last = Kb;
   }
   return JP_OK;
 }

@@ -147,15 +147,116 @@ def reference_combine(gm, gc):
     return mu, sigma, vn, wn
 
 
-class CudaLocal:
-    """Local phases of one rank through the C ABI, on torch's current CUDA stream."""
+def bulk_bytes_for(N, world):
+    """Bytes of a communicator's bulk region that the coefficient rows of N observations may need on `world` ranks
+    (12 rows of 4-byte coefficients per observation, slices of whole 128-observation tiles; include/jpcuda.h)."""
+    tiles = -(-int(N) // 128)
+    n_loc = -(-tiles // int(world)) * 128
+    return int(world) * 12 * n_loc * 4
 
-    def __init__(self, jp):
+
+class Comm:
+    """jp_comm: this rank's mailbox plus the mapped mailboxes of its peers (csrc/jp_comm.cu).  The 64-byte IPC handles are
+    exchanged ONCE through `exchange(bytes) -> [bytes] * world` (default: torch.distributed.all_gather_object); every
+    data-path exchange afterwards is a kernel of the library storing into peer memory over NVLink."""
+
+    def __init__(self, ctx, rank, world, bulk_bytes=0, group=None, exchange=None):
+        h = C.c_void_p()
+        check(lib().jp_comm_create(ctx.handle, C.c_int(rank), C.c_int(world), C.c_longlong(int(bulk_bytes)), C.byref(h)))
+        self.handle, self.ctx, self.rank, self.world, self.group = h, ctx, int(rank), int(world), group
+        if world > 1:
+            buf = (C.c_ubyte * 64)()
+            check(lib().jp_comm_ipc_handle(h, buf))
+            if exchange is None:
+                import torch.distributed as dist
+
+                def exchange(mine):
+                    out = [None] * world
+                    dist.all_gather_object(out, mine, group=group)
+                    return out
+            handles = exchange(bytes(buf))
+            blob = b"".join(handles)
+            if len(blob) != 64 * world:
+                raise ValueError("Comm: expected %d handles of 64 bytes" % world)
+            check(lib().jp_comm_connect_ipc(h, C.c_char_p(blob)))
+
+    @property
+    def bulk_bytes(self):
+        return int(lib().jp_comm_bulk_bytes(self.handle))
+
+    def status(self):
+        """Synchronise the stream and raise if a peer never reached a matching exchange."""
+        check(lib().jp_comm_status(self.handle))
+
+    def all_gather(self, t):
+        """[world, n] from every rank's float64 device tensor of n elements (asynchronous on the context's stream)."""
+        import torch
+        t = t.contiguous().view(-1)
+        out = torch.empty((self.world, t.numel()), dtype=torch.float64, device=t.device)
+        check(lib().jp_comm_all_gather(self.handle, C.c_void_p(t.data_ptr()), C.c_int(t.numel()), C.c_void_p(out.data_ptr())))
+        return out
+
+    def destroy(self):
+        if getattr(self, "handle", None):
+            lib().jp_comm_destroy(self.handle)
+            self.handle = None
+
+
+def comm_for(ctx, N, group=None):
+    """The context's communicator over `group`, created (collectively) on first use and re-created when a data set needs a
+    larger bulk region.  None when torch.distributed is not initialised, the group has one rank, or JP_NO_P2P is set."""
+    import os
+    import torch.distributed as dist
+    if os.environ.get("JP_NO_P2P") or not (dist.is_available() and dist.is_initialized()):
+        return None
+    world = dist.get_world_size(group)
+    if world < 2 or world > 8:
+        return None
+    need = bulk_bytes_for(N, world)
+    cache = ctx.__dict__.setdefault("_comms", {})
+    key = id(group) if group is not None else 0
+    c = cache.get(key)
+    if c is None or c.bulk_bytes < need:
+        if c is not None:
+            c.destroy()
+        c = Comm(ctx, dist.get_rank(group), world, need, group)
+        cache[key] = c
+    return c
+
+
+class CudaLocal:
+    """Local phases of one rank through the C ABI, on torch's current CUDA stream.  With a `comm` (jp_comm) the whole
+    sharded fit and the global marginals are ONE library call each (exchanges over NVLink peer memory inside the library);
+    without, the phase calls below are driven with torch.distributed collectives in between."""
+
+    def __init__(self, jp, comm="auto", group=None):
         import torch
         self.jp = jp
         self.torch = torch
         self.dev = torch.device("cuda", jp.ctx.device)
         jp.ctx.use_stream(torch.cuda.current_stream(self.dev).cuda_stream)
+        self.comm = comm_for(jp.ctx, jp.data.N, group) if isinstance(comm, str) else comm
+
+    # ---- exchanges inside the library (jp_fit_p2p / jp_marginal_coords_p2p)
+    def fit_p2p(self):
+        check(lib().jp_fit_p2p(self.jp.handle, C.byref(self.jp._args), self.comm.handle))
+        self.jp._theta = self.jp._density = None
+
+    def marginals_p2p(self, coords):
+        cs = np.ascontiguousarray(coords, dtype=np.int32)
+        K = len(cs)
+        mu, sg = np.zeros(K), np.zeros(K)
+        vn, wn = np.zeros((K, GRID_KNOTS)), np.zeros((K, GRID_KNOTS))
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        args = (self.jp.handle, self.comm.handle, C.c_int(K), p(cs), p(mu), p(sg), p(vn), p(wn))
+        st = lib().jp_marginal_coords_p2p(*args)
+        if st == 6 and self.jp._args.path == 0:
+            # the tensor-core bounds did not hold (every rank sees the same decision): refit on the FP64 path, once
+            self.jp._args.path = 1
+            self.fit_p2p()
+            st = lib().jp_marginal_coords_p2p(*args)
+        check(st)
+        return mu, sg, vn, wn
 
     def _buf(self, *shape):
         return self.torch.empty(shape, dtype=self.torch.float64, device=self.dev)
@@ -284,6 +385,10 @@ def fit_sharded(local, group=None, gather=None, rank=None, world=None, gather_sl
     When the local phase offers it (tensor-core GLM path), the O(N) prep is sharded by observation first: one tiny
     all_gather of (slice sums, bounds), then ONE all_gather of the chosen coefficient rows into the library's buffer
     (`gather_slab(mine, everybody, group)`, default: torch all_gather_into_tensor on the views)."""
+    if getattr(local, "comm", None) is not None:        # exchanges inside the library: one call, no collective from here
+        local.fit_p2p()
+        local.last_prep = "sharded-p2p"
+        return None
     gather = gather or _all_gather
     r = _rank(group) if rank is None else rank
     if world is None:
@@ -316,6 +421,8 @@ def _all_gather_slab(mine, everybody, group):
 def marginals_sharded(local, coords, group=None, gather=None):
     """Global (mu, sigma, value_nodes, weight_nodes) for K coordinate marginals of a node-sharded posterior:
     two all_gathers per batch, no global sort, no host arithmetic in between."""
+    if getattr(local, "comm", None) is not None:
+        return local.marginals_p2p(coords)
     gather = gather or _all_gather
     gm = gather(local.moments(coords), group)                   # [world, K, 4] = (sum w v, sum w v^2, min, max)
     gc = gather(local.knots_gathered(coords, gm), group)        # [world, K, 98, 6]
@@ -378,6 +485,6 @@ def fit_distributed(M, data, n=None, group=None, path=None, mode_result=None):
     Mtot = int(lib().jp_grid_size(grid))
     b, e = shard_bounds(Mtot, rank, world)
     post = JointPosterior(M, ddata, grid, mu_hat, U, neg_min, path=_lib.PATH_AUTO if path is None else path, node_range=(b, e))
-    local = CudaLocal(post)
+    local = CudaLocal(post, group=group)
     fit_sharded(local, group)
     return ShardedPosterior(post, local, group, (b, e), getattr(local, "last_prep", "replicated"))

@@ -6,6 +6,13 @@ import sys
 import numpy as np
 import pytest
 
+# one hardware queue per stream: the tests that emulate several ranks on one GPU run spinning exchange kernels of one rank
+# beside the kernels of another, which must never share a queue (set before CUDA initialises)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+os.environ.setdefault("JP_COMM_TIMEOUT_S", "20")
+# ... and no kernel may be loaded lazily while another rank's exchange kernel spins: loading synchronises the context
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

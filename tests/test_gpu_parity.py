@@ -726,6 +726,146 @@ def test_tc_observation_sharded_prep(jp, O, gpu_ctx, world, N, level):
     assert relerr(dens, ref["density"]) < TOLTC
 
 
+def test_device_side_series_decision(jp, O, gpu_ctx):
+    """jp_fit_p2p on a one-rank communicator: the whole tensor-core fit as one asynchronous queue, the series length chosen
+    by tc_decide_kernel and every kernel instantiation launched (all but one exit at once) -- same bits as jp_fit, whose
+    host reads the bounds back and launches one instantiation."""
+    from jointposteriors_jl_b200 import distributed as D
+    from jointposteriors_jl_b200.model import JointPosterior
+    for kind, N, d, level, xs in (("logistic", 50000, 6, 4, 1.0), ("poisson", 60000, 5, 4, 0.3)):
+        family, obs, hyper = _glm_case(kind, 9, N, d, xs)
+        code = [0] * d
+        x, H, neg_min = _cpu_mode_for(O, family, code, obs, hyper)
+        U = O.inv_chol(2.0 * H)
+        M = _model_for(jp, code)
+        dd = _upload(jp, gpu_ctx, family, obs, hyper)
+        full = jp.fit(M, dd, level, path=jp.PATH_TC, mode_result=(x, U, neg_min))
+        grid = gpu_ctx.grid(0, d, level)
+        comm = D.Comm(gpu_ctx, 0, 1)
+        sh = JointPosterior(M, dd, grid, x, U, neg_min, path=jp.PATH_AUTO)
+        loc = D.CudaLocal(sh, comm=comm)
+        D.fit_sharded(loc)
+        assert loc.last_prep == "sharded-p2p"
+        mu, sg, vn, wn = D.marginals_sharded(loc, list(range(d)))
+        assert sh.path_used == jp.PATH_TC
+        assert sh.diagnostics["series_terms"] == full.diagnostics["series_terms"]
+        assert sh.diagnostics["economised"] == full.diagnostics["economised"]
+        assert np.array_equal(sh.logdens, full.logdens)
+        assert np.array_equal(sh.density, full.density)
+        ms = jp.marginals(full, list(range(d)))
+        assert np.max(np.abs(mu - [m.mu for m in ms])) < 1e-13
+        assert np.max(np.abs(wn - np.array([m.itp.weights for m in ms]))) < 1e-12
+        comm.status()
+        comm.destroy()
+    # bounds not met (huge prior scale spreads the nodes): the device decides NC = 0, no instantiation runs, the first
+    # blocking call reports it and the sharded call refits on the FP64 path
+    family, obs, hyper = _glm_case("logistic", 5, 500, 4)       # the case of test_tc_path_gating
+    code = [0] * 4
+    x, H, neg_min = _cpu_mode_for(O, family, code, obs, hyper)
+    U = O.inv_chol(2.0 * H)
+    M = _model_for(jp, code)
+    dd = _upload(jp, gpu_ctx, family, obs, hyper)
+    grid = gpu_ctx.grid(0, 4, 5)
+    comm = D.Comm(gpu_ctx, 0, 1)
+    sh = JointPosterior(M, dd, grid, x, U, neg_min, path=jp.PATH_AUTO)
+    loc = D.CudaLocal(sh, comm=comm)
+    D.fit_sharded(loc)
+    with pytest.raises(jp.JPError) as e:
+        sh.density
+    assert e.value.status == 6 and "series bounds" in str(e.value)
+    D.fit_sharded(loc)
+    mu, sg, vn, wn = D.marginals_sharded(loc, [0, 1, 2, 3])
+    assert sh.path_used == jp.PATH_FP64
+    ref = jp.fit(M, dd, 5, path=jp.PATH_FP64, mode_result=(x, U, neg_min))
+    assert relerr(sh.density, ref.density) < 1e-12
+    comm.destroy()
+
+
+@pytest.mark.parametrize("world,N,level,kind", [(2, 60000, 4, "logistic"), (3, 30001, 4, "logistic"), (2, 500, 5, "binmix")],
+                         ids=["w2-tc", "w3-tc-ragged", "w2-fp64"])
+def test_p2p_sharded_ranks_on_one_gpu(jp, O, gpu_ctx, world, N, level, kind):
+    """The node-sharded fit + global marginals with every exchange inside the library (jp_fit_p2p / jp_marginal_coords_p2p:
+    stores into the peers' mailboxes, sequence flags, spinning waits): `world` ranks emulated on ONE GPU -- a context, a
+    stream set, a copy of the records and a communicator each, mailboxes connected by pointer (jp_comm_connect_local), one
+    host thread per rank -- against the unsharded fit and the oracle."""
+    import threading
+    from jointposteriors_jl_b200 import distributed as D
+    from jointposteriors_jl_b200.model import Context, JointPosterior
+    import ctypes as C
+    if kind == "binmix":
+        obs, hyper = readme_records()
+        family, code, d, tol = 0, [2, 2, 2], 3, TOL64
+    else:
+        d = 8 if N > 1000 else 3
+        family, obs, hyper = _glm_case(kind, 9, N, d, 1.0)
+        code, tol = [0] * d, TOLTC
+    x, H, neg_min = _cpu_mode_for(O, family, code, obs, hyper)
+    U = O.inv_chol(2.0 * H)
+    M = _model_for(jp, code)
+    full = jp.fit(M, _upload(jp, gpu_ctx, family, obs, hyper), level, mode_result=(x, U, neg_min))
+    mfull = jp.marginals(full, list(range(d)))
+    ctxs = [Context(0) for _ in range(world)]
+    comms = [D.Comm.__new__(D.Comm) for _ in range(world)]
+    for r, (cx, cm) in enumerate(zip(ctxs, comms)):
+        h = C.c_void_p()
+        jp._lib.check(jp.lib().jp_comm_create(cx.handle, C.c_int(r), C.c_int(world), C.c_longlong(D.bulk_bytes_for(len(obs), world)), C.byref(h)))
+        cm.handle, cm.ctx, cm.rank, cm.world, cm.group = h, cx, r, world, None
+    arr = (C.c_void_p * world)(*[cm.handle for cm in comms])
+    for cm in comms:
+        jp._lib.check(jp.lib().jp_comm_connect_local(cm.handle, arr))
+    out, errs = [None] * world, []
+    # Everything that synchronises the whole device (grid build, table uploads of a new context) happens BEFORE the ranks
+    # run side by side: inside a single process such a call would wait for another rank's spinning exchange kernel, which
+    # in turn waits for this rank.  (One process per GPU -- the real deployment -- has no such coupling.)
+    shards = []
+    for r, cx in enumerate(ctxs):
+        Mr = jp.Model(M.params)
+        dd = _upload(jp, cx, family, obs, hyper)
+        grid = cx.grid(0, d, level)
+        sh = JointPosterior(Mr, dd, grid, x, U, neg_min, node_range=D.shard_bounds(full.n_nodes, r, world))
+        sh.evaluate()
+        sh.density
+        shards.append(sh)
+
+    def rank_main(r):
+        try:
+            sh = shards[r]
+            loc = D.CudaLocal.__new__(D.CudaLocal)
+            loc.jp, loc.comm = sh, comms[r]
+            for rep in range(2):              # twice: slot parities, sequence numbers, the single-buffered bulk region
+                D.fit_sharded(loc)
+                res = D.marginals_sharded(loc, list(range(d)))
+            comms[r].status()
+            out[r] = (sh.logdens, sh.density, res, sh.path_used)
+        except Exception as e:      # noqa: BLE001
+            errs.append((r, repr(e)))
+
+    th = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    assert not errs, errs
+    assert all(o is not None for o in out), "a rank did not finish (exchange timed out?)"
+    ld = np.concatenate([o[0] for o in out])
+    dens = np.concatenate([o[1] for o in out])
+    assert all(o[3] == full.path_used for o in out)
+    assert np.max(np.abs(ld - full.logdens)) < 1e-8 * max(1.0, np.max(np.abs(full.logdens)))
+    assert relerr(dens, full.density) < 1e-7
+    for r in range(1, world):      # every rank holds bit-identical global results
+        for a, b in zip(out[0][2], out[r][2]):
+            assert np.array_equal(a, b)
+    mu, sg, vn, wn = out[0][2]
+    assert np.max(np.abs(mu - [m.mu for m in mfull])) < 1e-9
+    assert np.max(np.abs(sg - [m.sigma for m in mfull]) / np.array([m.sigma for m in mfull])) < 1e-7
+    assert np.max(np.abs(wn - np.array([m.itp.weights for m in mfull]))) < 1e-7
+    idx, w = O.smolyak(0, d, level)
+    ref = O.eval_grid(0, family, code, idx, w, x, U, neg_min, obs, hyper)
+    assert relerr(dens, ref["density"]) < tol
+    for cm in comms:
+        cm.destroy()
+
+
 @pytest.mark.parametrize("kind,N,d,level", [("logistic", 40000, 1, 5), ("logistic", 150000, 2, 7), ("poisson", 127, 2, 3),
                                              ("logistic", 128, 3, 2), ("poisson", 129, 1, 2), ("logistic", 5000, 12, 2)],
                          ids=["d1", "d2-L7", "N127", "N128", "N129", "d12-L2"])
