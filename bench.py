@@ -400,13 +400,28 @@ def run_product(args):
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
+    # Several ranks, GLM workload: OBSERVATION sharding (default) -- every rank uploads and keeps its N / world rows only and
+    # evaluates ALL nodes on them; the ranks exchange slice sums / bounds and per-pair partial sums inside the library
+    # (NVLink peer memory) and each ends up with the complete posterior.  --shard nodes: the node-sharded protocol instead
+    # (each rank a node block, all observations on every rank).
+    obs_mode = world > 1 and args.shard == "obs" and args.emulate_shard <= 1 and D.glm_obs_shardable(M, data) and path != _lib.PATH_FP64
+    comm = None
+    rows = D.row_slice(obs.shape[0], rank, world)[:2]
     # ---- one-time setup: data upload, mode, grid build (timed, reported, not part of the step)
     t0 = time.perf_counter()
-    dd = ctx.upload(data)
+    if obs_mode:
+        from jointposteriors_jl_b200.model import DeviceData
+        dd = DeviceData(ctx, data, rows=rows)
+    else:
+        dd = ctx.upload(data)
     ctx.sync()
     t_up = time.perf_counter() - t0
+    if obs_mode:
+        comm = D.comm_for(ctx, 0, None, min_bulk=1 << 24)
+        if comm is None:
+            raise SystemExit("bench.py: --shard obs needs the in-library exchanges (JP_NO_P2P is set?)")
     t0 = time.perf_counter()
-    x, U, neg_min = jp.mode(M, dd)
+    x, U, neg_min = D.mode_p2p(M, dd, comm) if obs_mode else jp.mode(M, dd)
     t_mode = time.perf_counter() - t0
     e0, e1 = ev(), ev()
     e0.record(stream)
@@ -418,8 +433,16 @@ def run_product(args):
     b, e = D.shard_bounds(Mtot, rank, world)
     if args.emulate_shard > 1:     # diagnostic: the local work of rank 0 of W ranks (its node block, W x the observations)
         b, e = D.shard_bounds(Mtot, 0, args.emulate_shard)
-    post = JointPosterior(M, dd, grid, x, U, neg_min, path=path, node_range=(b, e))
-    loc = D.CudaLocal(post)
+    if obs_mode:
+        b, e = 0, Mtot
+        if comm.bulk_bytes < D.bulk_bytes_obs(Mtot, world):
+            comm = D.comm_for(ctx, 0, None, min_bulk=D.bulk_bytes_obs(Mtot, world))
+        post = JointPosterior(M, dd, grid, x, U, neg_min, path=path)
+        sp = D.ObsShardedPosterior(post, comm, rows)
+        loc = None
+    else:
+        post = JointPosterior(M, dd, grid, x, U, neg_min, path=path, node_range=(b, e))
+        loc = D.CudaLocal(post)
     coords = list(range(d))
     N = obs.shape[0]
     pairs = float(Mtot if args.emulate_shard <= 1 else e - b) * float(N)
@@ -430,6 +453,9 @@ def run_product(args):
             post.evaluate()
             res = jp.marginals(post, coords)
             return res[0].mu
+        if obs_mode:
+            sp.refit()
+            return sp.marginals(coords)[0].mu
         D.fit_sharded(loc)
         mu, sg, vn, wn = D.marginals_sharded(loc, coords)
         return float(mu[0])
@@ -462,6 +488,10 @@ def run_product(args):
             post.evaluate()
             bq.record(stream)
             jp.marginals(post, coords)
+        elif obs_mode:
+            sp.refit()
+            bq.record(stream)
+            sp.marginals(coords)
         else:
             D.fit_sharded(loc)
             bq.record(stream)
@@ -484,7 +514,8 @@ def run_product(args):
     # from the CUDA events the library records around it on its stream
     kms = float(np.mean(kern_in_step))
     path_used = post.path_used
-    local_pairs = float(e - b) * float(N)
+    local_pairs = float(e - b) * float(N if not obs_mode else rows[1] - rows[0])
+    n_local_obs = N if not obs_mode else rows[1] - rows[0]
     if path_used == _lib.PATH_TC:
         flops = 2.0 * d * local_pairs
         tf32_peak = peaks["bf16_tflops"] / 2.0
@@ -495,7 +526,7 @@ def run_product(args):
                          "see the epilogue / tile_model objects and DESIGN.md" % (
                              int(round(3 * 32 * ((d * 3 + 31) // 32) / (3.0 * d))), peaks["source"]))
     else:
-        nbytes = 8.0 * N * (d + 1) + 8.0 * (e - b) * (d + 1)
+        nbytes = 8.0 * n_local_obs * (d + 1) + 8.0 * (e - b) * (d + 1)
         roof = dict(bound="hbm", achieved=nbytes / (kms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
                     frac=nbytes / (kms * 1e-3) / 1e9 / peaks["hbm_gbs"], traffic=None,
                     note="FP64 plugin kernel: compulsory bytes 8N(d+1)+8M(d+1); the kernel is FP64-ALU bound "
@@ -516,7 +547,7 @@ def run_product(args):
         # MMA occupies the tensor pipe for 48 cycles per K = 8 instruction (128 x 96 / 256, same guide), 4 per 128-byte K
         # atom product.  The three resources overlap, so the floor of a tile is their maximum.
         atoms = 1 if 3 * d <= 32 else (2 if 3 * d <= 64 else 3)
-        tiles_per_sm = np.ceil(N / 128.0) * np.ceil(((e - b + 1) // 2 + 1) / 96.0) / 148.0
+        tiles_per_sm = np.ceil(n_local_obs / 128.0) * np.ceil(((e - b + 1) // 2 + 1) / 96.0) / 148.0
         cyc = kms * 1e-3 * clk * 1e6 / tiles_per_sm
         fma_cyc = 3 * 2 * 16 * (nc + 3)
         floor = max(768.0, 192.0 * atoms, float(fma_cyc))
@@ -551,11 +582,21 @@ def run_product(args):
         # H2D of the observation records; with several ranks each uploads its 1/world row slice over PCIe and the
         # slices are exchanged GPU->GPU (one NCCL all_gather over NVLink)
         t_ = [time.perf_counter()]
-        dde = ctx.upload(hdata) if world == 1 else ctx.upload_sharded(hdata)
+        if obs_mode:
+            dde = DeviceData(ctx, hdata, rows=rows)          # this rank's rows only: no replication of X, no row exchange
+        else:
+            dde = ctx.upload(hdata) if world == 1 else ctx.upload_sharded(hdata)
         t_.append(time.perf_counter())
         pe = JointPosterior(M, dde, grid, x, U, neg_min, path=path, node_range=(b, e))
         t_.append(time.perf_counter())
-        if world == 1:
+        if obs_mode:
+            spe = D.ObsShardedPosterior(pe, comm, rows).refit()
+            t_.append(time.perf_counter())
+            res = spe.marginals(coords)
+            t_.append(time.perf_counter())
+            dens = pe.density if rank == 0 else None          # every rank holds the same complete posterior: one download
+            out = (res[0].mu, float(dens[0]) if rank == 0 else 0.0)
+        elif world == 1:
             pe.evaluate()
             t_.append(time.perf_counter())
             res = jp.marginals(pe, coords)                        # D2H of mu, sigma, 2 x 100 knots per coordinate
@@ -602,7 +643,7 @@ def run_product(args):
     e2e_ms = float(t.cpu()[0]) / args.steps
     rb, re_, _ = D.row_slice(obs.shape[0], rank, world)
     h2d = int((re_ - rb) * obs.shape[1] * 8 + 8 * (d + d * U.shape[1]) + 4 * d)     # this rank's bytes (largest slice on rank 0)
-    d2h = int(8 * (e - b) + d * 8 * (2 + 200))
+    d2h = int(8 * (e - b) + d * 8 * (2 + 200))                                       # rank 0 (obs mode: the whole density there)
     e2e = dict(value=pairs / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms,
                warmup=e2e_warmup, per_step_ms=[round(v, 3) for v in per_step],
                host_phases_ms={k: round(float(np.median(v)), 4) for k, v in phases.items()})
@@ -616,7 +657,7 @@ def run_product(args):
                 pa = jp.fit(M, hdata, wl["level"], path=path)
                 ra = jp.marginals(pa, coords)
             else:
-                pa = jp.fit_distributed(M, hdata, wl["level"], path=path)
+                pa = jp.fit_distributed(M, hdata, wl["level"], path=path, shard="obs" if obs_mode else "nodes")
                 ra = pa.marginals(coords)
             pa.free()
             return ra
@@ -669,9 +710,10 @@ def run_product(args):
                    vs_baseline=None,
                    dtype="tf32x3+f64" if path_used == _lib.PATH_TC else "f64", data="synthetic",
                    config=dict(workload=wl["desc"], nodes=Mtot, obs=int(N), d=d, level=wl["level"],
-                               parallelism="node-sharded x%d" % world if args.emulate_shard <= 1 else
+                               parallelism=("observation-sharded x%d (every rank: all nodes x its N / %d rows)" % (world, world) if obs_mode
+                                            else "node-sharded x%d" % world) if args.emulate_shard <= 1 else
                                "DIAGNOSTIC: node block of rank 0 of %d on one GPU" % args.emulate_shard, path="tc" if path_used == _lib.PATH_TC else "fp64",
-                               prep=getattr(loc, "last_prep", "replicated") if world > 1 else "single",
+                               prep=("observation-sharded-p2p" if obs_mode else getattr(loc, "last_prep", "replicated")) if world > 1 else "single",
                                l2="256 MiB flush buffer written between timed iterations",
                                marginals="%d coordinate marginals per step (moments + 100-knot Grid CDF)" % d),
                    fit_ms=tot_fit_ms / args.steps, marginal_ms=tot_marg_ms / args.steps, grid_build_ms=t_grid,
@@ -712,6 +754,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strong", default="cfg5,cfg4",
                     help="fixed-size configurations also run on these ranks and reported in the `strong` object ('none' to skip)")
+    ap.add_argument("--shard", default="obs", choices=["obs", "nodes"],
+                    help="several ranks, GLM workload: shard the observations (default) or the grid nodes")
     ap.add_argument("--emulate-shard", type=int, default=1,
                     help="diagnostic (1 GPU): run the local work of rank 0 of W ranks, no collectives; not a bench line")
     args = ap.parse_args()

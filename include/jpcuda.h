@@ -205,6 +205,10 @@ typedef struct jp_fit_args {
   int path;                     /* JP_PATH_* */
   long long node_begin;         /* node shard [node_begin, node_end) of the merged grid owned by */
   long long node_end;           /*   this ctx; (0, -1) = all nodes */
+  int raw;                      /* 1: RawBuild (src/joint_posterior.jl:183-188): the result keeps the UNCONSTRAINED node
+                                 *    coordinates x = mu_hat + U z (the reference's grid.cache, jp_get_cache); the constrained
+                                 *    parameters are constructed on the device whenever a marginal or jp_get_theta needs them
+                                 *    (update!(Theta), src/marginal_posterior.jl:86-90,106-115).  0: CacheBuild (Theta stored) */
 } jp_fit_args;
 
 /* allocate the device-resident result (Theta SoA [d][M_local], density, work buffers) */
@@ -285,6 +289,17 @@ int jp_comm_all_gather(jp_comm* comm, const double* d_src, int n, double* d_out)
  * jp_fit_p2p_check) returns JP_ERR_UNSUPPORTED on EVERY rank (they see the same bits): call again with JP_PATH_FP64. */
 int jp_fit_p2p(jp_posterior* post, const jp_fit_args* args, jp_comm* comm);
 int jp_fit_p2p_check(jp_posterior* post);
+/* OBSERVATION sharding (SURVEY 8e "alternative worth benchmarking"; the natural decomposition when N grows with the GPU
+ * count): every rank uploads and keeps ITS rows only (jp_data of N / world observations, no replication of X), the
+ * posterior handle covers ALL grid nodes.  Tensor-core GLM path only: the ranks exchange the slice sums and bounds, decide
+ * the series length on the device, run the kernel over (all nodes) x (own observations), push their per-pair partial sums to
+ * every peer and finish in rank order -- every rank then holds the complete, bit-identical posterior, so jp_marginal_coords
+ * and the jp_get_* downloads work on it as after jp_fit and stage 5 needs no exchange.  bulk_bytes of the communicator:
+ * 16 bytes x ceil(nodes / 2 + 1) x world.  JP_ERR_UNSUPPORTED: not a GLM / constrained coordinates -- shard the nodes.
+ * jp_mode_p2p: the Newton iteration of jp_mode on row-sharded GLM data, its sums added over the ranks inside the library. */
+int jp_fit_p2p_obs(jp_posterior* post, const jp_fit_args* args, jp_comm* comm);
+int jp_mode_p2p(jp_ctx* ctx, const jp_data* data, jp_comm* comm, int d, const int* h_transform, double* h_x, double* h_H,
+                double* neg_min, int* evals);
 /* marginal(jp, f) of K coordinates of the node-sharded posterior, globally: moments, exchange, knot candidates, exchange,
  * combine in rank order (every rank gets identical bits); results to the host (blocking).  Reference
  * src/marginal_posterior.jl:117-123, src/interp.jl:448-457. */
@@ -294,6 +309,9 @@ int jp_marginal_coords_p2p(jp_posterior* post, jp_comm* comm, int K, const int* 
 /* results to the host (blocking).  h_theta: d x M_local row-major (coordinate k of node m at
  * [k*M_local + m]); h_logdens: log-density + neg_min per node; h_density: normalised weights. */
 int jp_get_theta(jp_posterior* post, double* h_theta);
+/* RawBuild results only: the d x M_local unconstrained node matrix (row-major like h_theta), the `cache` field of the
+ * reference's raw grid (src/marginal_posterior.jl:69,107) */
+int jp_get_cache(jp_posterior* post, double* h_x);
 int jp_get_logdens(jp_posterior* post, double* h_logdens);
 int jp_get_density(jp_posterior* post, double* h_density);
 /* device views for zero-copy consumers (valid until jp_posterior_free) */

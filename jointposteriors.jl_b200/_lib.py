@@ -37,6 +37,7 @@ class FitArgs(C.Structure):
         ("path", C.c_int),
         ("node_begin", C.c_longlong),
         ("node_end", C.c_longlong),
+        ("raw", C.c_int),
     ]
 
 
@@ -70,6 +71,7 @@ SYMBOLS = [
     "jp_fit_prep_len", "jp_fit_prep_local", "jp_fit_prep_gathered", "jp_fit_coef_slab", "jp_fit_local_stats_prepared",
     "jp_comm_create", "jp_comm_ipc_handle", "jp_comm_connect_ipc", "jp_comm_connect_local", "jp_comm_bulk_bytes", "jp_comm_status",
     "jp_comm_destroy", "jp_comm_all_gather", "jp_fit_p2p", "jp_fit_p2p_check", "jp_marginal_coords_p2p",
+    "jp_fit_p2p_obs", "jp_mode_p2p", "jp_get_cache",
     "jp_get_theta", "jp_get_logdens", "jp_get_density", "jp_dev_theta", "jp_dev_density", "jp_fit_path_used",
     "jp_fit_diagnostics",
     "jp_marginal_coords", "jp_marginal_values", "jp_marginal_sorted", "jp_marginal_buffer", "jp_marginal_knots_from_sort",

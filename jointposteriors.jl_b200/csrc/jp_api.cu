@@ -346,7 +346,23 @@ static int download(jp_posterior* p, const double* d_src, double* h_dst, size_t 
   JP_CUDA(cudaStreamSynchronize(p->ctx->stream));
   return jp_fit_tc_verify(p);
 }
-int jp_get_theta(jp_posterior* p, double* h) { return download(p, p ? p->d_theta : nullptr, h, p ? (size_t)p->M * p->d : 0); }
+int jp_get_theta(jp_posterior* p, double* h) {
+  JP_REQUIRE(p && h, "jp_get_theta: null argument");
+  if (!p->raw) return download(p, p->d_theta, h, (size_t)p->M * p->d);
+  // RawBuild: construct every coordinate from the unconstrained cache into a temporary, then download
+  JP_CUDA(cudaSetDevice(p->ctx->device));
+  double* tmp = nullptr;
+  JP_CUDA(jp_dmalloc(p->ctx, &tmp, (size_t)p->M * p->d * 8));
+  int st = jp_construct_columns(p, p->d, nullptr, tmp);
+  if (st == JP_OK) st = download(p, tmp, h, (size_t)p->M * p->d);
+  jp_dfree(p->ctx, tmp);
+  return st;
+}
+int jp_get_cache(jp_posterior* p, double* h) {
+  JP_REQUIRE(p && h, "jp_get_cache: null argument");
+  JP_REQUIRE(p->raw, "jp_get_cache: the posterior was not fitted as a RawBuild (jp_fit_args.raw)");
+  return download(p, p->d_theta, h, (size_t)p->M * p->d);
+}
 int jp_get_logdens(jp_posterior* p, double* h) { return download(p, p ? p->d_logdens : nullptr, h, p ? (size_t)p->M : 0); }
 int jp_get_density(jp_posterior* p, double* h) { return download(p, p ? p->d_density : nullptr, h, p ? (size_t)p->M : 0); }
 

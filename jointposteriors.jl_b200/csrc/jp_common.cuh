@@ -175,6 +175,8 @@ struct jp_posterior {
   int d = 0, p = 0;
   long long m0 = 0, m1 = 0, M = 0;   // shard [m0, m1), M = m1 - m0
   int path_used = 0;
+  std::vector<int> tcode_host;   // transform codes of the last fit (host copy)
+  bool raw = false;              // RawBuild: d_theta holds the UNCONSTRAINED node coordinates (the reference's grid.cache)
   JpFinish fin;                  // pending finish of the last log-density launch (consumed by jp_stage4_launch)
   double* d_theta = nullptr;     // SoA constrained parameters [d][M]
   double* d_a = nullptr;         // log-density + neg_min + 0.5|z|^2
@@ -393,10 +395,13 @@ int jp_fit_tc_prep_gathered(jp_posterior* post, const jp_fit_args* args, const d
                             int* n_rows);
 int jp_fit_tc_coef_slab(jp_posterior* post, int n_rows, float** d_local, float** d_all, long long* count);
 int jp_fit_tc_run_prepared(jp_posterior* post, const jp_fit_args* args, bool finish = true);
-int jp_fit_tc_launch_dev(jp_posterior* post, const jp_fit_args* args, jp_comm* comm);   // device-side series-length decision
+int jp_fit_tc_launch_dev(jp_posterior* post, const jp_fit_args* args, jp_comm* comm, int obs_sharded);   // device-side series-length decision
 int jp_fit_tc_verify(jp_posterior* post);      // read that decision back (first blocking call after the fit)
 void jp_tc_data_free(jp_data* data);
 void jp_tc_post_free(jp_posterior* post);
+int jp_construct_columns(jp_posterior* post, int K, const int* d_coords, double* d_out);   // RawBuild: constrained columns from the cache
+int jp_glm_grad_hess_comm(jp_ctx* ctx, const jp_data* data, jp_comm* comm, int d, const double* h_beta, double* h_g, double* h_Hneg,
+                          double* h_logpost);
 int jp_upload_fit_consts(jp_posterior* post, const jp_fit_args* args);   // mu_hat, U, transform codes -> device
 int jp_marginal_design_device(jp_posterior* post, int k, double** d_V, long long** d_ind, double* h_mu, double* h_sigma);   // jp_marginal.cu
 const double* jp_rule_nodes_dev(const jp_ctx* ctx, int rule);   // device copy of the master z-node table (this context's GPU)

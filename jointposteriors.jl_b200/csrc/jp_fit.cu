@@ -42,6 +42,7 @@ struct JpFitLaunchParams {
   double* lj_prior;            // [M]: log-Jacobian + prior(theta)
   double* part;                // [splits][M] observation sums
   const double* xpts;          // non-null: explicit unconstrained points [M][d] instead of grid keys
+  int raw;                     // RawBuild: theta receives the unconstrained coordinates
 };
 
 __constant__ double c_fit_nodes[2][JP_RULE_NMAX];
@@ -57,6 +58,62 @@ __device__ __forceinline__ double jp_transform(int code, double x, double& lj) {
     return 1.0 / (1.0 + exp(-x));
   }
   return x;
+}
+
+// construct / update! of ConstrainedParameters (reference src/joint_posterior.jl:148,152): unconstrained -> constrained in
+// place (register array, compile-time indices), returns log|J|.  Simplex blocks first, then coordinate by coordinate.
+template <int DPAD>
+__device__ __forceinline__ double jp_construct(double (&th)[DPAD], int d, const int* s_code) {
+  double lj = 0.0;
+  // simplex blocks first (each depends only on its own unconstrained coordinates): a run-time loop over block
+  // heads, compile-time indices into the register array inside
+#pragma unroll 1
+  for (int k0 = 0; k0 < d; ++k0) {
+    const int code = s_code[k0];
+    if (JP_T_KIND(code) != JP_T_SIMPLEX || JP_T_LOC(code) != k0) continue;
+    const int hi = k0 + JP_T_SCALE(code);
+    double mx = 0.0;                               // the implied last coordinate has x = 0
+#pragma unroll
+    for (int j = 0; j < DPAD; ++j)
+      if (j >= k0 && j < hi) mx = fmax(mx, th[j]);
+    double S = exp(-mx);
+#pragma unroll
+    for (int j = 0; j < DPAD; ++j)
+      if (j >= k0 && j < hi) S += exp(th[j] - mx);
+    const double logS = log(S);
+    lj += -mx - logS;                              // log of the implied last component
+#pragma unroll
+    for (int j = 0; j < DPAD; ++j)
+      if (j >= k0 && j < hi) {
+        const double l = th[j] - mx - logS;
+        lj += l;
+        th[j] = exp(l);
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < DPAD; ++k) {
+    if (k < d) {
+      const int code = s_code[k];
+      if (JP_T_KIND(code) == JP_T_SIMPLEX) {
+        // transformed above
+      } else if (JP_T_KIND(code) == JP_T_NONCENTRED) {
+        // theta_k = theta_loc + theta_scale * x_k with loc, scale < k already transformed; the register
+        // array is searched with compile-time indices so that it never spills to local memory
+        const int il = JP_T_LOC(code), is = JP_T_SCALE(code);
+        double loc = 0.0, sc = 1.0;
+#pragma unroll
+        for (int j = 0; j < k; ++j) {
+          if (j == il) loc = th[j];
+          if (j == is) sc = th[j];
+        }
+        th[k] = fma(sc, th[k], loc);
+        lj += log(sc);
+      } else {
+        th[k] = jp_transform(code, th[k], lj);
+      }
+    }
+  }
+  return lj;
 }
 
 template <class F, int DPAD>
@@ -100,59 +157,19 @@ jp_fit_nodes_kernel(const JpFitLaunchParams P) {
           if (k < P.d) th[k] += s_U[j * P.d + k] * z;
       }
     }
-    double lj = 0.0;
-    // simplex blocks first (each depends only on its own unconstrained coordinates): a run-time loop over block
-    // heads, compile-time indices into the register array inside
-#pragma unroll 1
-    for (int k0 = 0; k0 < P.d; ++k0) {
-      const int code = s_code[k0];
-      if (JP_T_KIND(code) != JP_T_SIMPLEX || JP_T_LOC(code) != k0) continue;
-      const int hi = k0 + JP_T_SCALE(code);
-      double mx = 0.0;                               // the implied last coordinate has x = 0
-#pragma unroll
-      for (int j = 0; j < DPAD; ++j)
-        if (j >= k0 && j < hi) mx = fmax(mx, th[j]);
-      double S = exp(-mx);
-#pragma unroll
-      for (int j = 0; j < DPAD; ++j)
-        if (j >= k0 && j < hi) S += exp(th[j] - mx);
-      const double logS = log(S);
-      lj += -mx - logS;                              // log of the implied last component
-#pragma unroll
-      for (int j = 0; j < DPAD; ++j)
-        if (j >= k0 && j < hi) {
-          const double l = th[j] - mx - logS;
-          lj += l;
-          th[j] = exp(l);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < DPAD; ++k) {
-      if (k < P.d) {
-        const int code = s_code[k];
-        if (JP_T_KIND(code) == JP_T_SIMPLEX) {
-          // transformed above
-        } else if (JP_T_KIND(code) == JP_T_NONCENTRED) {
-          // theta_k = theta_loc + theta_scale * x_k with loc, scale < k already transformed; the register
-          // array is searched with compile-time indices so that it never spills to local memory
-          const int il = JP_T_LOC(code), is = JP_T_SCALE(code);
-          double loc = 0.0, sc = 1.0;
-#pragma unroll
-          for (int j = 0; j < k; ++j) {
-            if (j == il) loc = th[j];
-            if (j == is) sc = th[j];
-          }
-          th[k] = fma(sc, th[k], loc);
-          lj += log(sc);
-        } else {
-          th[k] = jp_transform(code, th[k], lj);
-        }
-      }
-    }
-    if (blockIdx.y == 0) {
+    // RawBuild (reference src/joint_posterior.jl:183-188): the result keeps the UNCONSTRAINED node (the grid's `cache`)
+    if (P.raw && blockIdx.y == 0) {
 #pragma unroll
       for (int k = 0; k < DPAD; ++k)
         if (k < P.d) P.theta[(size_t)k * P.M + m] = th[k];
+    }
+    const double lj = jp_construct<DPAD>(th, P.d, s_code);
+    if (blockIdx.y == 0) {
+      if (!P.raw) {
+#pragma unroll
+        for (int k = 0; k < DPAD; ++k)
+          if (k < P.d) P.theta[(size_t)k * P.M + m] = th[k];
+      }
       ljp = lj + F::template prior<DPAD>(th, P.d, P.N, P.hyper);
       P.lj_prior[m] = ljp;
     }
@@ -362,6 +379,41 @@ __global__ void __launch_bounds__(JP_S4_THREADS) jp_stage4_kernel(const Stage4Pa
   }
 }
 
+// RawBuild consumers (reference src/marginal_posterior.jl:68-77,106-115: update!(Theta) on every column of grid.cache before
+// f is evaluated): constrained coordinates `coords` (null: all d) of every node from the unconstrained cache x[d][M].
+template <int DPAD>
+__global__ void __launch_bounds__(128) jp_construct_kernel(int d, long long M, const int* __restrict__ tcode, const double* __restrict__ x,
+                                                           int K, const int* __restrict__ coords, double* __restrict__ out) {
+  __shared__ int s_code[JP_MAX_D];
+  for (int i = threadIdx.x; i < d; i += blockDim.x) s_code[i] = tcode[i];
+  __syncthreads();
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  double th[DPAD];
+#pragma unroll
+  for (int k = 0; k < DPAD; ++k) th[k] = (k < d) ? x[(size_t)k * M + m] : 0.0;
+  jp_construct<DPAD>(th, d, s_code);
+  for (int j = 0; j < K; ++j) {
+    const int c = coords ? coords[j] : j;
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < DPAD; ++k)
+      if (k == c) v = th[k];
+    out[(size_t)j * M + m] = v;
+  }
+}
+
+int jp_construct_columns(jp_posterior* post, int K, const int* d_coords, double* d_out) {
+  jp_ctx* ctx = post->ctx;
+  const unsigned gb = (unsigned)((post->M + 127) / 128);
+  if (post->d <= 16)
+    jp_construct_kernel<16><<<gb, 128, 0, ctx->stream>>>(post->d, post->M, post->d_tcode, post->d_theta, K, d_coords, d_out);
+  else
+    jp_construct_kernel<JP_MAX_D><<<gb, 128, 0, ctx->stream>>>(post->d, post->M, post->d_tcode, post->d_theta, K, d_coords, d_out);
+  JP_CHECK_LAUNCH(ctx);
+  return JP_OK;
+}
+
 // ------------------------------------------------------------------------------------ registry
 static JpFamilyEntry g_families[16];
 static int g_nfamilies = 0;
@@ -431,6 +483,7 @@ int jp_upload_fit_consts(jp_posterior* post, const jp_fit_args* args) {
   for (int i = 0; i < d * p; ++i) hp[d + i] = args->h_U[i];
   int* hc = reinterpret_cast<int*>(hp + d + d * p);
   for (int i = 0; i < d; ++i) hc[i] = args->h_transform[i];
+  post->tcode_host.assign(args->h_transform, args->h_transform + d);
   JP_CUDA(cudaMemcpyAsync(post->d_mu, hp, sizeof(double) * d, cudaMemcpyHostToDevice, ctx->stream));
   JP_CUDA(cudaMemcpyAsync(post->d_U, hp + d, sizeof(double) * d * p, cudaMemcpyHostToDevice, ctx->stream));
   JP_CUDA(cudaMemcpyAsync(post->d_tcode, hc, sizeof(int) * d, cudaMemcpyHostToDevice, ctx->stream));
@@ -464,6 +517,7 @@ int jp_fit_check_args(const jp_posterior* post, const jp_fit_args* args) {
              args->d, args->p, post->d, post->p);
   JP_REQUIRE(args->h_transform && args->h_mu_hat && args->h_U, "jp_fit: null host array");
   JP_TRY(jp_check_transform_codes("jp_fit", args->h_transform, args->d));
+  const_cast<jp_posterior*>(post)->raw = args->raw != 0;
   return JP_OK;
 }
 
@@ -496,6 +550,7 @@ int jp_fit_fp64_launch(jp_posterior* post, const jp_fit_args* args, bool finish)
   // round the split length to whole tiles so tiles never straddle a split boundary unevenly
   lp.obs_per_split = ((lp.obs_per_split + tile_obs - 1) / tile_obs) * tile_obs;
   lp.xpts = nullptr;
+  lp.raw = post->raw ? 1 : 0;
   lp.part = post->d_part;
   lp.lj_prior = post->d_part + (size_t)JP_POST_PART_SPLITS * post->M;
   JP_TRY(fam->launch(post, lp));
@@ -543,7 +598,7 @@ static int jp_stage4_launch(jp_posterior* post, bool normalise, double* d_stats)
   P.normalise = normalise ? 1 : 0;
   P.theta = post->d_theta; P.d = post->d; P.cmom = nullptr;
   post->cmom_valid = false;
-  if (normalise && post->M >= 2) {
+  if (normalise && post->M >= 2 && !post->raw) {      // (a RawBuild's theta array holds unconstrained coordinates)
     if (nb > post->cmom_cap) {
       jp_dfree(ctx, post->d_cmom);
       post->d_cmom = nullptr;
@@ -635,7 +690,7 @@ int jp_log_density_points(jp_ctx* ctx, const jp_data* data, int d, const int* h_
     lp.idx = nullptr; lp.mu = nullptr; lp.U = nullptr; lp.tcode = d_code; lp.obs = data->d_obs;
     for (int i = 0; i < JP_MAX_HYPER; ++i) lp.hyper[i] = data->hyper[i];
     lp.theta = d_theta; lp.splits = splits; lp.obs_per_split = data->N;
-    lp.part = d_part; lp.lj_prior = d_part + (size_t)splits * K; lp.xpts = d_x;
+    lp.part = d_part; lp.lj_prior = d_part + (size_t)splits * K; lp.xpts = d_x; lp.raw = 0;
     st = fam->launch(&tmp, lp);
     if (st == JP_OK) {
       jp_points_finish_kernel<<<(unsigned)((K + 255) / 256), 256, 0, ctx->stream>>>(K, splits, lp.part, lp.lj_prior, d_out);
@@ -756,7 +811,7 @@ int jp_fit_p2p(jp_posterior* post, const jp_fit_args* args, jp_comm* comm) {
   post->cmom_valid = false;
   int path = args->path;
   if (path == JP_PATH_AUTO) path = jp_fit_tc_supported(post, args) ? JP_PATH_TC : JP_PATH_FP64;
-  if (path == JP_PATH_TC) JP_TRY(jp_fit_tc_launch_dev(post, args, comm));
+  if (path == JP_PATH_TC) JP_TRY(jp_fit_tc_launch_dev(post, args, comm, 0));
   else JP_TRY(jp_fit_fp64_launch(post, args, false));
   if (comm->world == 1) return jp_stage4_launch(post, true, post->d_stats);
   JP_TRY(jp_stage4_launch(post, false, post->d_stats));      // finish + local max + sum relative to it
@@ -769,6 +824,28 @@ int jp_fit_p2p(jp_posterior* post, const jp_fit_args* args, jp_comm* comm) {
   }
   JP_MARK(post->ctx, "fit:normalised");
   return JP_OK;
+}
+
+// OBSERVATION-sharded fit (the alternative to node sharding): `post` covers ALL grid nodes, its data handle holds
+// only this rank's observations.  Tensor-core GLM path only (the remainder sums are additive over observations).  Every
+// rank ends up with the complete, bit-identical posterior: stage 5 needs no exchange at all.
+int jp_fit_p2p_obs(jp_posterior* post, const jp_fit_args* args, jp_comm* comm) {
+  JP_REQUIRE(post && comm, "jp_fit_p2p_obs: null argument");
+  JP_REQUIRE(comm->ctx == post->ctx, "jp_fit_p2p_obs: the communicator belongs to another context");
+  JP_ENTER_CTX(post->ctx);
+  JP_TRY(jp_fit_check_args(post, args));
+  JP_REQUIRE(post->m0 == 0 && post->M == post->grid->M, "jp_fit_p2p_obs: the posterior must cover all %lld grid nodes (it is the "
+             "observations that are sharded)", post->grid->M);
+  if (args->path == JP_PATH_FP64 || !jp_fit_tc_supported(post, args)) {
+    jp_set_error("jp_fit_p2p_obs: observation sharding needs the tensor-core GLM path (family %d, path %d); shard the nodes instead "
+                 "(jp_fit_p2p)", post->data->family, args->path);
+    return JP_ERR_UNSUPPORTED;
+  }
+  post->sorted_valid = false;
+  post->K_last = 0;
+  post->cmom_valid = false;
+  JP_TRY(jp_fit_tc_launch_dev(post, args, comm, 1));
+  return jp_stage4_launch(post, true, post->d_stats);
 }
 
 int jp_fit_p2p_check(jp_posterior* post) {

@@ -233,8 +233,19 @@ int jp_glm_num_blocks(const jp_ctx* ctx, long long N) {
   return (int)std::max(1LL, std::min(tiles, (long long)ctx->sm_count * 2));
 }
 
-extern "C" int jp_glm_grad_hess(jp_ctx* ctx, const jp_data* data, int d, const double* h_beta, double* h_g,
-                                double* h_Hneg, double* h_logpost) {
+// sum over the ranks of a gathered [world][n] buffer, in rank order (the same bits on every rank)
+__global__ void jp_sum_gathered_kernel(const double* __restrict__ g, int world, int n, double* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double v = 0;
+  for (int r = 0; r < world; ++r) v += g[(size_t)r * n + e];
+  out[e] = v;
+}
+
+// comm != null: `data` holds this rank's observations only; the sums are exchanged and added in rank order, so every rank
+// gets the score / information of ALL observations (jp_mode_p2p, observation-sharded fits)
+int jp_glm_grad_hess_comm(jp_ctx* ctx, const jp_data* data, jp_comm* comm, int d, const double* h_beta, double* h_g,
+                          double* h_Hneg, double* h_logpost) {
   JP_REQUIRE(ctx && data && h_beta, "jp_glm_grad_hess: null argument");
   JP_REQUIRE(data->family == JP_FAM_LOGISTIC || data->family == JP_FAM_POISSON,
              "jp_glm_grad_hess: family %d is not a GLM", data->family);
@@ -253,6 +264,14 @@ extern "C" int jp_glm_grad_hess(jp_ctx* ctx, const jp_data* data, int d, const d
   std::memcpy(hp, h_beta, sizeof(double) * d);
   JP_CUDA(cudaMemcpyAsync(d_beta, hp, sizeof(double) * d, cudaMemcpyHostToDevice, ctx->stream));
   int st = jp_glm_sums_device(ctx, data, d, d_beta, d_out, d_work, nb);
+  if (st == JP_OK && comm && comm->world > 1) {
+    const double* g = nullptr;
+    st = jp_comm_exchange(comm, JP_CH_USER, d_out, nE + 1, &g);
+    if (st == JP_OK) {
+      jp_sum_gathered_kernel<<<(nE + 1 + 127) / 128, 128, 0, ctx->stream>>>(g, comm->world, nE + 1, d_out);
+      ctx->launches++;
+    }
+  }
   double* out = hp + JP_MAX_D;     // nE + 1 <= 64 + 64 * 65 / 2 + 1 doubles
   if (st == JP_OK) {
     cudaError_t e = cudaMemcpyAsync(out, d_out, sizeof(double) * (nE + 1), cudaMemcpyDeviceToHost, ctx->stream);
@@ -283,4 +302,9 @@ extern "C" int jp_glm_grad_hess(jp_ctx* ctx, const jp_data* data, int d, const d
   }
   if (h_logpost) *h_logpost = lp;
   return JP_OK;
+}
+
+extern "C" int jp_glm_grad_hess(jp_ctx* ctx, const jp_data* data, int d, const double* h_beta, double* h_g, double* h_Hneg,
+                                double* h_logpost) {
+  return jp_glm_grad_hess_comm(ctx, data, nullptr, d, h_beta, h_g, h_Hneg, h_logpost);
 }

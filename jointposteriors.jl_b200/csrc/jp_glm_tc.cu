@@ -742,10 +742,8 @@ __device__ __forceinline__ float tc_transpose_reduce32(float* v, int lane) {
 // two resources the epilogue contends for, 3 and 4 repeat 0 and 2 with two extra (overwritten) K-atom products per
 // tile to measure how MMA time composes with epilogue time (JP_TC_DEBUG_MODE, profiling builds of bench.py only)
 template <int NC, int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcKernelParams P) {
+__device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcKernelParams& P) {
   extern __shared__ uint8_t smem_raw[];
-  if (P.nc_sel != nullptr && *P.nc_sel != NC) return;   // device-side series-length decision: uniform over the grid
   // carve-up (1024-byte aligned for the 128-byte swizzle): pair operands, observation ring, reduction buffer, barriers
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sB = base;                                              // nbbuf x ka x (96 x 128 B)
@@ -834,7 +832,9 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_2d(sA + (uint32_t)stage * a_bytes + (uint32_t)a * TC_OBS_TILE * 128u, &tmA, bar_full + 8u * stage,
                         a * TC_KATOM, t * TC_OBS_TILE);
           const int sl = t / P.tiles_per_slice;
-          const float* crow = P.coef + (size_t)sl * P.coef_slice_stride + (size_t)(t - sl * P.tiles_per_slice) * TC_OBS_TILE;
+          // gathered rows are laid out [slice][NC][n_loc] with the series length actually in use (= this body's NC)
+          const size_t slice_stride = P.coef_slice_stride ? (size_t)NC * (size_t)P.coef_n_loc : 0;
+          const float* crow = P.coef + (size_t)sl * slice_stride + (size_t)(t - sl * P.tiles_per_slice) * TC_OBS_TILE;
 #pragma unroll
           for (int k = 0; k < NC; ++k)
             bulk_load_1d(sC + (uint32_t)cslot * c_bytes + (uint32_t)k * TC_OBS_TILE * 4u, crow + (size_t)k * P.coef_n_loc,
@@ -1009,6 +1009,25 @@ jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
+}
+
+template <int NC, int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+jp_glm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcKernelParams P) {
+  if (P.nc_sel != nullptr && *P.nc_sel != NC) return;   // device-side series-length decision: uniform over the grid
+  tc_kernel_body<NC, MODE>(tmA, tmB, P);
+}
+
+// Device-side decision, second launch: whichever of the longer series (NC = 6 .. 12) the device chose -- ONE launch instead
+// of four that exit at once (an empty launch of this 448-thread, 150+ KB kernel costs ~6 us).  Its ring geometry is the one
+// computed for NC = 12 (the largest coefficient slots), valid for the shorter series too.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+jp_glm_tc_rest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcKernelParams P) {
+  const int nc = *P.nc_sel;
+  if (nc == 6) tc_kernel_body<6, 0>(tmA, tmB, P);
+  else if (nc == 8) tc_kernel_body<8, 0>(tmA, tmB, P);
+  else if (nc == 10) tc_kernel_body<10, 0>(tmA, tmB, P);
+  else if (nc == 12) tc_kernel_body<12, 0>(tmA, tmB, P);
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -1366,7 +1385,9 @@ static int tc_node_quad(jp_posterior* post, const jp_fit_args* args, cudaStream_
 
 // the tensor-core kernel and the per-node finish (after tc_node_prep)
 static int tc_run_kernel(jp_posterior* post, const jp_fit_args* args, int NC, bool finish, const int* nc_sel = nullptr,
-                         const float* coef_gathered = nullptr) {
+                         const float* coef_gathered = nullptr, bool rest = false) {
+  // rest: the single launch that serves NC = 6 .. 12 under a device-side decision (geometry of NC = TC_NCMAX; the
+  // coefficient slice stride of the gathered rows is NC-dependent and read from the decision by the kernel)
   jp_ctx* ctx = post->ctx;
   const jp_data* data = post->data;
   TcDataState* ds = static_cast<TcDataState*>(data->tc_state);
@@ -1431,7 +1452,12 @@ static int tc_run_kernel(jp_posterior* post, const jp_fit_args* args, int NC, bo
   kp.nc_sel = nc_sel;
   kp.dbg = nullptr;
   int stc;
-  if (NC == 4) stc = launch_tc<4>(ctx, ds->tmA, ps->tmB, kp, smem);
+  if (rest) {
+    JP_CUDA(cudaFuncSetAttribute(jp_glm_tc_rest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jp_glm_tc_rest_kernel<<<std::min(ctx->sm_count, kp.n_pair_tiles * kp.chunks), TC_THREADS, smem, ctx->stream>>>(ds->tmA, ps->tmB, kp);
+    JP_CHECK_LAUNCH(ctx);
+    stc = JP_OK;
+  } else if (NC == 4) stc = launch_tc<4>(ctx, ds->tmA, ps->tmB, kp, smem);
   else if (NC == 6) stc = launch_tc<6>(ctx, ds->tmA, ps->tmB, kp, smem);
   else if (NC == 8) stc = launch_tc<8>(ctx, ds->tmA, ps->tmB, kp, smem);
   else if (NC == 10) stc = launch_tc<10>(ctx, ds->tmA, ps->tmB, kp, smem);
@@ -1480,7 +1506,7 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args, bool finish) {
   jp_ctx* ctx = post->ctx;
   JP_MARK(ctx, "fit:start");
   static const bool dev_decision = getenv("JP_TC_DEVICE_DECISION") != nullptr;   // A/B aid: no host round trip inside the fit
-  if (dev_decision && !finish) return jp_fit_tc_launch_dev(post, args, nullptr);
+  if (dev_decision && !finish) return jp_fit_tc_launch_dev(post, args, nullptr, 0);
   JP_TRY(tc_setup(post, args, 1, 0));
   JP_MARK(ctx, "fit:setup+consts");
   TcDataState* ds = static_cast<TcDataState*>(post->data->tc_state);
@@ -1660,24 +1686,59 @@ tc_coef_push_kernel(const JpCommDev c, const TcDecision* __restrict__ dec, const
   }
 }
 
-int jp_fit_tc_launch_dev(jp_posterior* post, const jp_fit_args* args, jp_comm* comm) {
+// Observation-sharded fit: every rank's partial (E, O) sums over ITS observations, summed over the chunks, into slot `rank`
+// of every peer's bulk region [world][P][2]; the per-node finish then adds the slots in rank order (JpFinish with
+// chunks = world), so every rank holds bit-identical log-densities of ALL nodes.
+__global__ void __launch_bounds__(256)
+tc_part_push_kernel(const JpCommDev c, const double* __restrict__ part, int chunks, long long P, size_t bulk_off,
+                    unsigned int* __restrict__ counter, unsigned long long seq) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < P; j += (long long)gridDim.x * blockDim.x) {
+    double2 sum = make_double2(0.0, 0.0);
+    for (int ch = 0; ch < chunks; ++ch) {
+      const double2 eo = *reinterpret_cast<const double2*>(part + ((size_t)ch * P + j) * 2);
+      sum.x += eo.x;
+      sum.y += eo.y;
+    }
+    for (int p = 0; p < c.world; ++p) reinterpret_cast<double2*>(c.peer[p] + bulk_off)[(long long)c.rank * P + j] = sum;
+  }
+  __shared__ unsigned int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned int t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1u);
+    if (s_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (s_last && (int)threadIdx.x < c.world) {
+    __threadfence_system();
+    jp_st_release_sys(jp_comm_flag(c.peer[threadIdx.x], JP_CH_BULK, 0, c.rank), seq);
+  }
+}
+
+// obs_sharded = 0: NODE sharding -- the posterior is this rank's node block, the data handle holds ALL observations, the O(N)
+//   prep is sharded by observation slice and the coefficient rows are exchanged.
+// obs_sharded = 1: OBSERVATION sharding -- the data handle holds this rank's observations only, the posterior
+//   covers ALL nodes; the ranks exchange the (sums, bounds) and the per-pair partial sums, nothing else.
+int jp_fit_tc_launch_dev(jp_posterior* post, const jp_fit_args* args, jp_comm* comm, int obs_sharded) {
   jp_ctx* ctx = post->ctx;
   const int world = comm ? comm->world : 1, rank = comm ? comm->rank : 0;
+  const bool obs = obs_sharded && world > 1;
   JP_MARK(ctx, "fit:start");
-  JP_TRY(tc_setup(post, args, world, rank));
+  JP_TRY(tc_setup(post, args, obs ? 1 : world, obs ? 0 : rank));
   TcDataState* ds = static_cast<TcDataState*>(post->data->tc_state);
   TcPostState* ps = static_cast<TcPostState*>(post->tc_state);
   const int d = args->d, nE1 = d + d * (d + 1) / 2 + 1, L = nE1 + TC_NBOUND;
   if (!ps->d_dec) JP_CUDA(jp_dmalloc(ctx, &ps->d_dec, sizeof(TcDecision)));
   if (world > 1) {
     if (!ds->d_loc) JP_CUDA(jp_dmalloc(ctx, &ds->d_loc, (size_t)L * 8));
-    const size_t need = (size_t)world * TC_NCMAX * (size_t)ds->n_loc * sizeof(float);
-    JP_REQUIRE(comm->bulk_bytes >= need, "jp_fit_p2p: the communicator's bulk region holds %zu bytes, the coefficient rows of %lld "
-               "observations on %d ranks may need %zu (jp_comm_create)", comm->bulk_bytes, ds->N, world, need);
+    const size_t need = obs ? (size_t)world * (size_t)ps->P * 16 : (size_t)world * TC_NCMAX * (size_t)ds->n_loc * sizeof(float);
+    JP_REQUIRE(comm->bulk_bytes >= need, "jp_fit_p2p: the communicator's bulk region holds %zu bytes, this fit (%lld observations, %lld "
+               "nodes, %d ranks) may need %zu (jp_comm_create)", comm->bulk_bytes, ds->N, post->M, world, need);
   }
   const double z_max = std::sqrt(post->grid->zmax2), z_ref = std::min(z_max, 6.0);
-  // side: coefficients + bounds of this rank's slice; side2: its sums (one GPU: then the quadratic part); main: node operand
-  JP_TRY(tc_prep_slice(post, args, rank, world > 1 ? ds->d_loc : ds->d_sums));
+  // side: coefficients + bounds of this rank's observations; side2: their sums (one GPU: then the quadratic part); main: node operand
+  JP_TRY(tc_prep_slice(post, args, obs ? 0 : rank, world > 1 ? ds->d_loc : ds->d_sums));
   tc_bounds_reduce_kernel<<<1, 32 * TC_NBOUND, 0, ctx->side>>>(ds->d_bounds, ds->prep_blocks, world > 1 ? ds->d_loc + nE1 : ds->d_comb);
   JP_CHECK_LAUNCH(ctx);
   if (world == 1) JP_TRY(tc_node_quad(post, args, ctx->side2));
@@ -1690,7 +1751,11 @@ int jp_fit_tc_launch_dev(jp_posterior* post, const jp_fit_args* args, jp_comm* c
     tc_combine_gathered_kernel<<<(L + 127) / 128, 128, 0, ctx->stream>>>(g, world, L, nE1, ds->d_sums, ds->d_comb);
     JP_CHECK_LAUNCH(ctx);
     JP_MARK(ctx, "fit:prep_exchanged");
-    JP_TRY(tc_node_quad(post, args, ctx->stream));
+    // the quadratic part of every node needs the combined sums only: on side2, beside the decision / fold / coefficient push
+    JP_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    JP_CUDA(cudaStreamWaitEvent(ctx->side2, ctx->ev_fork, 0));
+    JP_TRY(tc_node_quad(post, args, ctx->side2));
+    JP_CUDA(cudaEventRecord(ctx->ev_join2, ctx->side2));
   }
   static const bool no_fold = getenv("JP_TC_NO_FOLD") != nullptr;
   tc_decide_kernel<<<1, 32, 0, ctx->stream>>>(ds->d_comb, z_max, no_fold ? 1 : 0, ps->d_dec);
@@ -1698,7 +1763,7 @@ int jp_fit_tc_launch_dev(jp_posterior* post, const jp_fit_args* args, jp_comm* c
   tc_fold_dev_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ps->d_dec, ds->n_loc, ds->n_loc, z_ref, ds->d_coef);
   JP_CHECK_LAUNCH(ctx);
   const float* coef_gathered = nullptr;
-  if (world > 1) {
+  if (world > 1 && !obs) {
     unsigned long long seq = 0;
     JP_TRY(jp_comm_bulk_begin(comm, &seq));
     const int pb = (int)std::max<long long>(1, std::min<long long>(2LL * ctx->sm_count, ds->n_loc / 256));
@@ -1709,11 +1774,26 @@ int jp_fit_tc_launch_dev(jp_posterior* post, const jp_fit_args* args, jp_comm* c
     coef_gathered = reinterpret_cast<const float*>(comm->mailbox + comm->bulk_off);
     JP_MARK(ctx, "fit:coef_exchanged");
   }
-  // every instantiation is queued; the four the device did not choose return before touching anything
+  if (world > 1) JP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));      // the quadratic part (stage 4 reads it)
+  // two launches: the shortest series (the usual choice) and one kernel for all longer ones; whichever the device did not
+  // choose returns before touching anything
   JP_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
-  for (int NC = 4; NC <= TC_NCMAX; NC += 2) JP_TRY(tc_run_kernel(post, args, NC, false, &ps->d_dec->NC, coef_gathered));
+  JP_TRY(tc_run_kernel(post, args, 4, false, &ps->d_dec->NC, coef_gathered));
+  JP_TRY(tc_run_kernel(post, args, TC_NCMAX, false, &ps->d_dec->NC, coef_gathered, true));
   JP_CUDA(cudaEventRecord(ctx->ev_k1, ctx->stream));
   ctx->ev_valid = true;
+  if (obs) {
+    unsigned long long seq = 0;
+    JP_TRY(jp_comm_bulk_begin(comm, &seq));
+    const int pb = (int)std::max<long long>(1, std::min<long long>(2LL * ctx->sm_count, (ps->P + 255) / 256));
+    tc_part_push_kernel<<<pb, 256, 0, ctx->stream>>>(jp_comm_dev(comm), ps->d_part, post->fin.chunks, ps->P, comm->bulk_off,
+                                                     comm->d_counter, seq);
+    JP_CHECK_LAUNCH(ctx);
+    JP_TRY(jp_comm_wait(comm, JP_CH_BULK, 0, seq));
+    post->fin.chunks = world;       // the finish adds the ranks' slots in rank order
+    post->fin.tc_part = reinterpret_cast<const double*>(comm->mailbox + comm->bulk_off);
+    JP_MARK(ctx, "fit:partials_exchanged");
+  }
   ps->dec_pending = true;
   post->tc_bounds[3] = -1;       // not known to the host until jp_fit_tc_verify
   return JP_OK;

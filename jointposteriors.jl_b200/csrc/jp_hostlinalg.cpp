@@ -8,6 +8,9 @@
 #include <vector>
 
 #include "../../include/jpcuda.h"
+// score / information sums of a GLM, optionally added over the ranks of a communicator (csrc/jp_glm.cu)
+int jp_glm_grad_hess_comm(jp_ctx* ctx, const jp_data* data, jp_comm* comm, int d, const double* h_beta, double* h_g, double* h_Hneg,
+                          double* h_logpost);
 
 static thread_local char g_err[1024] = "";
 
@@ -465,10 +468,10 @@ bool solve_dense(std::vector<double> A, std::vector<double>& b, int d) {
   return true;
 }
 
-int mode_glm(jp_ctx* ctx, const jp_data* data, int d, double* x, double* H, double* neg_min, int* evals, int iters) {
+int mode_glm(jp_ctx* ctx, const jp_data* data, jp_comm* comm, int d, double* x, double* H, double* neg_min, int* evals, int iters) {
   std::vector<double> g(d), g2(d), H2((size_t)d * d), step(d), xn(d);
   double lp = 0, lp2 = 0;
-  int s = jp_glm_grad_hess(ctx, data, d, x, g.data(), H, &lp);
+  int s = jp_glm_grad_hess_comm(ctx, data, comm, d, x, g.data(), H, &lp);
   ++*evals;
   if (s != JP_OK) return s;
   for (int it = 0; it < iters; ++it) {
@@ -478,7 +481,7 @@ int mode_glm(jp_ctx* ctx, const jp_data* data, int d, double* x, double* H, doub
     bool ok = false;
     while (t > 1e-10) {
       for (int k = 0; k < d; ++k) xn[k] = x[k] + t * step[k];
-      s = jp_glm_grad_hess(ctx, data, d, xn.data(), g2.data(), H2.data(), &lp2);
+      s = jp_glm_grad_hess_comm(ctx, data, comm, d, xn.data(), g2.data(), H2.data(), &lp2);
       ++*evals;
       if (s != JP_OK) return s;
       if (std::isfinite(lp2) && lp2 >= lp - 1e-13 * std::fabs(lp)) {
@@ -513,12 +516,32 @@ int jp_mode(jp_ctx* ctx, const jp_data* data, int d, const int* h_transform, int
         jp_set_error("jp_mode: the GLM Newton iteration needs unconstrained coefficients (coordinate %d is constrained)", k);
         return JP_ERR_BAD_ARG;
       }
-    s = mode_glm(ctx, data, d, h_x, h_H, neg_min, &n_eval, 60);
+    s = mode_glm(ctx, data, nullptr, d, h_x, h_H, neg_min, &n_eval, 60);
   } else {
     ModeProblem P(ctx, data, d, h_transform);
     s = mode_generic(P, h_x, h_H, neg_min, 100);
     n_eval = P.evals;
   }
+  if (evals) *evals = n_eval;
+  return s;
+}
+
+// jp_mode for a GLM whose observations are sharded over the ranks of `comm` (data = this rank's rows): the Newton iteration of
+// jp_mode with every score / information evaluation summed over the ranks in rank order inside the library -- all ranks walk
+// the same iterates and return bit-identical (x, H, neg_min).  Reference src/joint_posterior.jl:164-168.
+int jp_mode_p2p(jp_ctx* ctx, const jp_data* data, jp_comm* comm, int d, const int* h_transform, double* h_x, double* h_H,
+                double* neg_min, int* evals) {
+  if (!ctx || !data || !comm || !h_transform || !h_x || !h_H || !neg_min || d < 1 || d > 64) {
+    jp_set_error("jp_mode_p2p: bad argument");
+    return JP_ERR_BAD_ARG;
+  }
+  for (int k = 0; k < d; ++k)
+    if (h_transform[k] != JP_T_REAL) {
+      jp_set_error("jp_mode_p2p: the GLM Newton iteration needs unconstrained coefficients (coordinate %d is constrained)", k);
+      return JP_ERR_BAD_ARG;
+    }
+  int n_eval = 0;
+  const int s = mode_glm(ctx, data, comm, d, h_x, h_H, neg_min, &n_eval, 60);
   if (evals) *evals = n_eval;
   return s;
 }

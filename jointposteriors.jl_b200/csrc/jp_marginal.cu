@@ -585,6 +585,30 @@ static int set_value_pointers(jp_posterior* post, int K, const int* h_coords, co
   JP_REQUIRE(K >= 1 && K <= 4096, "marginal: K=%d out of range", K);
   JP_REQUIRE((h_coords != nullptr) != (d_values != nullptr), "marginal: give exactly one of coords / values");
   std::vector<const double*> want((size_t)K);
+  if (h_coords && post->raw) {
+    // RawBuild: d_theta is the unconstrained cache.  Identity coordinates are their own columns; as soon as one requested
+    // coordinate is constrained, the K columns are constructed on the device (update!(Theta) of the reference,
+    // src/marginal_posterior.jl:86-90) into the value buffer and used from there.
+    bool constrained = false;
+    for (int k = 0; k < K; ++k) {
+      JP_REQUIRE(h_coords[k] >= 0 && h_coords[k] < post->d, "marginal: coordinate %d out of range [0,%d)", h_coords[k], post->d);
+      constrained = constrained || post->tcode_host[(size_t)h_coords[k]] != JP_T_REAL;
+    }
+    if (constrained) {
+      JP_TRY(ensure_value_buffer(post, K));
+      int* d_c = nullptr;
+      JP_CUDA(jp_dmalloc(ctx, &d_c, (size_t)K * sizeof(int)));
+      JP_CUDA(jp_pinned_acquire(ctx));
+      int* hc = reinterpret_cast<int*>(ctx->h_pinned);
+      std::copy(h_coords, h_coords + K, hc);
+      JP_CUDA(cudaMemcpyAsync(d_c, hc, (size_t)K * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      JP_CUDA(jp_pinned_publish(ctx));
+      JP_TRY(jp_construct_columns(post, K, d_c, post->d_vals));
+      jp_dfree(ctx, d_c);
+      h_coords = nullptr;
+      d_values = post->d_vals;
+    }
+  }
   for (int k = 0; k < K; ++k) {
     if (h_coords) {
       JP_REQUIRE(h_coords[k] >= 0 && h_coords[k] < post->d, "marginal: coordinate %d out of range [0,%d)", h_coords[k], post->d);

@@ -202,7 +202,12 @@ class Comm:
             self.handle = None
 
 
-def comm_for(ctx, N, group=None):
+def bulk_bytes_obs(nodes, world):
+    """Bulk bytes of an observation-sharded fit: one (even, odd) partial sum per mirror pair of nodes and rank."""
+    return int(world) * ((int(nodes) >> 1) + 1) * 16
+
+
+def comm_for(ctx, N, group=None, min_bulk=0):
     """The context's communicator over `group`, created (collectively) on first use and re-created when a data set needs a
     larger bulk region.  None when torch.distributed is not initialised, the group has one rank, or JP_NO_P2P is set."""
     import os
@@ -212,7 +217,7 @@ def comm_for(ctx, N, group=None):
     world = dist.get_world_size(group)
     if world < 2 or world > 8:
         return None
-    need = bulk_bytes_for(N, world)
+    need = max(bulk_bytes_for(N, world), int(min_bulk))
     cache = ctx.__dict__.setdefault("_comms", {})
     key = id(group) if group is not None else 0
     c = cache.get(key)
@@ -429,6 +434,91 @@ def marginals_sharded(local, coords, group=None, gather=None):
     return local.combine_gathered(gm, gc)
 
 
+# ----------------------------------------------------------------------------- observation sharding
+def mode_p2p(M, ddata, comm, x0=None):
+    """mode(M, data) (reference src/joint_posterior.jl:164-168) of a GLM whose rows are sharded over the ranks of `comm`:
+    jp_mode_p2p, every rank returns the same bits."""
+    from .model import deduce_scale
+    d = M.d
+    x = np.zeros(d) if x0 is None else np.array(x0, dtype=np.float64)
+    H = np.zeros((d, d), order="F")
+    neg_min, evals = C.c_double(), C.c_int()
+    code = np.ascontiguousarray(M.transform, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    check(lib().jp_mode_p2p(ddata.ctx.handle, ddata.handle, comm.handle, C.c_int(d), p(code), p(x), p(H), C.byref(neg_min),
+                            C.byref(evals)))
+    return x, deduce_scale(M, M.hessian_scale * np.array(H)), neg_min.value
+
+
+class ObsShardedPosterior:
+    """Result of an OBSERVATION-sharded fit: this rank uploaded and holds only its rows, but -- the remainder sums of the
+    tensor-core GLM path being additive over observations -- it ends up with the complete joint posterior (all nodes,
+    bit-identical on every rank), so marginals, quantiles and downloads are those of a single-GPU JointPosterior."""
+
+    def __init__(self, post, comm, rows):
+        self.post, self.comm, self.rows, self.prep = post, comm, rows, "observation-sharded-p2p"
+        self.M, self.mu_hat, self.U = post.M, post.mu_hat, post.U
+
+    def refit(self):
+        check(lib().jp_fit_p2p_obs(self.post.handle, C.byref(self.post._args), self.comm.handle))
+        self.post._theta = self.post._density = None
+        self.post._theta_gen += 1
+        return self
+
+    density = property(lambda self: self.post.density)
+    Theta = property(lambda self: self.post.Theta)
+
+    def marginals(self, coords):
+        from .marginals import marginals
+        return marginals(self.post, [int(c) for c in coords])
+
+    def marginal(self, k):
+        return self.marginals([k])[0]
+
+    def free(self):
+        self.post.free()
+
+
+def glm_obs_shardable(M, data):
+    from .data import FAM_LOGISTIC, FAM_POISSON
+    return data.family in (FAM_LOGISTIC, FAM_POISSON) and bool(np.all(M.transform == 0)) and M.d <= 32
+
+
+def fit_obs_sharded(M, data, n=None, group=None, mode_result=None, ddata=None, comm=None):
+    """fit(M, data[, n]) with the OBSERVATIONS sharded over the ranks of `group` (GLM families on the tensor-core path):
+    this rank uploads rows [b, e) only; mode, series-length decision and the exchange of the per-pair partial sums happen
+    inside the library over NVLink peer memory.  Raises JPError(status 6) when the a-priori bounds of the tensor-core path
+    fail at the first blocking call (use fit_distributed(..., shard="nodes") then)."""
+    import torch
+    import torch.distributed as dist
+    from .model import DeviceData, JointPosterior, colmajor, default
+    ctx = M.ctx
+    dev = torch.device("cuda", ctx.device)
+    ctx.use_stream(torch.cuda.current_stream(dev).cuda_stream)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if n is None:
+        n = default(M.build)
+    N = data.records()[0].shape[0] if ddata is None else None
+    if ddata is None:
+        b, e, _ = row_slice(N, rank, world)
+        ddata = DeviceData(ctx, data, rows=(b, e))
+        rows = (b, e)
+    else:
+        rows = None
+    if comm is None:
+        comm = comm_for(ctx, 0, group, min_bulk=1 << 22)
+    if comm is None:
+        raise RuntimeError("fit_obs_sharded needs an initialised torch.distributed group of 2..8 ranks (and JP_NO_P2P unset)")
+    mu_hat, U, neg_min = mode_p2p(M, ddata, comm) if mode_result is None else mode_result
+    U = colmajor(U)
+    grid = ctx.grid(M.build.rule.rule_id, U.shape[1], int(n))
+    Mtot = int(lib().jp_grid_size(grid))
+    if comm.bulk_bytes < bulk_bytes_obs(Mtot, world):
+        comm = comm_for(ctx, 0, group, min_bulk=bulk_bytes_obs(Mtot, world))
+    post = JointPosterior(M, ddata, grid, mu_hat, U, neg_min)
+    return ObsShardedPosterior(post, comm, rows).refit()
+
+
 # ----------------------------------------------------------------------------- the public multi-GPU call
 class ShardedPosterior:
     """Result of `fit_distributed`: this rank's block of the joint posterior (reference struct JointPosterior,
@@ -462,7 +552,7 @@ class ShardedPosterior:
         self.post.free()
 
 
-def fit_distributed(M, data, n=None, group=None, path=None, mode_result=None):
+def fit_distributed(M, data, n=None, group=None, path=None, mode_result=None, shard="nodes"):
     """fit(M, data[, n]) (reference src/joint_posterior.jl:177-188) with the grid nodes sharded over the ranks of `group`
     (one process per GPU, torch.distributed initialised by the caller): row-sharded upload + NVLink all_gather of the
     records, the mode on every rank (deterministic: identical everywhere), this rank's node block through stages 2-3, the
@@ -472,6 +562,9 @@ def fit_distributed(M, data, n=None, group=None, path=None, mode_result=None):
     from . import _lib
     from .model import DeviceData, JointPosterior, colmajor, default, mode
     ctx = M.ctx
+    if shard == "obs" or (shard == "auto" and not isinstance(data, DeviceData) and glm_obs_shardable(M, data)
+                          and comm_for(ctx, 0, group, min_bulk=1 << 22) is not None):
+        return fit_obs_sharded(M, data, n, group, mode_result)
     dev = torch.device("cuda", ctx.device)
     ctx.use_stream(torch.cuda.current_stream(dev).cuda_stream)      # collectives and kernels on one stream
     world = dist.get_world_size(group)

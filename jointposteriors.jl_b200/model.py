@@ -153,8 +153,10 @@ class Context:
 class DeviceData:
     """Observations resident on the GPU (jp_data)."""
 
-    def __init__(self, ctx, data, device_obs=None):
+    def __init__(self, ctx, data, device_obs=None, rows=None):
         obs, hyper = data.records()
+        if rows is not None:             # this rank's observation slice only (observation-sharded fits)
+            obs = obs[int(rows[0]):int(rows[1])]
         obs = f64(obs)
         hyper = f64(hyper)
         h = C.c_void_p()
@@ -277,7 +279,7 @@ class JointPosterior:
     access), density (normalised, signed weights), μ_hat / mu_hat, U.
     """
 
-    def __init__(self, M, ddata, grid, mu_hat, U, neg_min, path=_lib.PATH_AUTO, node_range=None):
+    def __init__(self, M, ddata, grid, mu_hat, U, neg_min, path=_lib.PATH_AUTO, node_range=None, raw=False):
         self.M = M
         self.data = ddata
         self.grid = grid
@@ -296,11 +298,13 @@ class JointPosterior:
         a.neg_min = self.neg_min
         a.path = int(path)
         a.node_begin, a.node_end = (0, -1) if node_range is None else node_range
+        a.raw = 1 if raw else 0
         h = C.c_void_p()
         check(lib().jp_posterior_create(self.ctx.handle, grid, ddata.handle, C.byref(a), C.byref(h)))
         self.handle = h
         self.n_nodes = int(lib().jp_posterior_size(h))
         self._theta = self._density = None
+        self._theta_gen = 0
 
     def update(self, mu_hat, U, neg_min):
         """Re-point the posterior at a new (mu_hat, U, neg_min) of the same shape (buffers are reused)."""
@@ -314,6 +318,7 @@ class JointPosterior:
         """Stages 2-4 on the GPU (asynchronous)."""
         check(lib().jp_fit(self.handle, C.byref(self._args)))
         self._theta = self._density = None
+        self._theta_gen += 1
         return self
 
     @property
@@ -370,7 +375,39 @@ class JointPosterior:
             pass
 
 
-JointPosteriorRaw = JointPosterior   # RawBuild keeps the same device-resident result here
+class _RawGrid:
+    """The `grid` field of the reference's JointPosteriorRaw (src/joint_posterior.jl:9-14): `cache` = the d x M matrix of
+    UNCONSTRAINED node coordinates mu_hat + U z (src/marginal_posterior.jl:69,107), `density` = the normalised weights."""
+
+    def __init__(self, jp):
+        self._jp = jp
+        self._cache = None
+
+    @property
+    def cache(self):
+        if self._cache is None or self._jp._theta_gen != self._gen:
+            out = np.zeros((self._jp._args.d, self._jp.n_nodes))
+            check(lib().jp_get_cache(self._jp.handle, ptr(out)))
+            self._cache, self._gen = out, self._jp._theta_gen
+        return self._cache
+
+    _gen = -1
+
+    @property
+    def density(self):
+        return self._jp.density
+
+
+class JointPosteriorRaw(JointPosterior):
+    """Result of fit for a RawBuild model (`Model(params, SmolyakRaw[rule])`; reference struct JointPosteriorRaw,
+    src/joint_posterior.jl:9-14,183-188): fields M, grid (.cache, .density), mu_hat, U.  The device keeps the unconstrained
+    node matrix; the constrained parameters a marginal function needs are constructed from it on the device at every call
+    (update!(Theta) per node, src/marginal_posterior.jl:86-90,106-115), never stored."""
+
+    def __init__(self, M, ddata, grid, mu_hat, U, neg_min, path=_lib.PATH_AUTO, node_range=None):
+        super().__init__(M, ddata, grid, mu_hat, U, neg_min, path=path, node_range=node_range, raw=True)
+        self.grid_handle = self.grid
+        self.grid = _RawGrid(self)
 
 
 def fit(M, data, n=None, path=_lib.PATH_AUTO, mode_result=None):
@@ -382,6 +419,7 @@ def fit(M, data, n=None, path=_lib.PATH_AUTO, mode_result=None):
     mu_hat, U, neg_min = mode(M, ddata) if mode_result is None else mode_result
     U = colmajor(U)
     grid = M.ctx.grid(M.build.rule.rule_id, U.shape[1], int(n))   # cache key: (rule, rank, level), cf. index() :157-162
-    jp = JointPosterior(M, ddata, grid, mu_hat, U, neg_min, path=path)
+    cls = JointPosteriorRaw if M.build.raw else JointPosterior      # RawBuild / CacheBuild dispatch of the reference's two fit methods
+    jp = cls(M, ddata, grid, mu_hat, U, neg_min, path=path)
     jp.evaluate()
     return jp

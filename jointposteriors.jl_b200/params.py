@@ -136,25 +136,44 @@ class ParamView:
         return self.blocks[i]
 
 
-def probe_coordinate(f, blocks):
-    """Return the flat coordinate index if f(Theta) merely selects one coordinate, else None.
+class _Tracer:
+    """Stand-in for one constrained coordinate while a marginal function is probed.  It supports NO arithmetic, comparison or
+    conversion: a function that does anything to a parameter except hand it back raises and is treated as a general closure."""
+    __slots__ = ("index",)
 
-    f is evaluated on three fixed pseudo-random parameter vectors; it is a pure selector of coordinate k
-    exactly when its result is bit-identical to entry k of every probe (any arithmetic breaks that)."""
-    d = sum(b.n for _, b in blocks)
-    rng = np.random.Generator(np.random.Philox(key=0x5E1EC7))
-    found = None
-    for _ in range(3):
-        v = rng.random(d) + 0.25
-        try:
-            r = f(ParamView(blocks, v))
-            r = np.asarray(r, dtype=np.float64)
-        except Exception:
-            return None
-        if r.size != 1:
-            return None
-        hits = np.nonzero(v == r.reshape(-1)[0])[0]
-        if len(hits) != 1 or (found is not None and hits[0] != found):
-            return None
-        found = int(hits[0])
-    return found
+    def __init__(self, index):
+        self.index = index
+
+    def __array__(self, *a, **k):      # numpy must not silently turn it into a number either
+        raise TypeError("not a number")
+
+
+def probe_coordinate(f, blocks):
+    """Return the flat coordinate index if f(Theta) merely SELECTS one coordinate, else None.
+
+    f is called once on a ParamView-like object whose entries are opaque tracer objects: only a function that returns one
+    of them untouched is a selector (and its marginal is then a zero-copy column of the Theta array on the device).  Any
+    arithmetic, comparison (`abs`, `max(p[0], 0)`, `np.clip`, a branch on the value ...) fails on a tracer, so such an f is
+    evaluated on the host at every node, as the reference does for every f (src/marginal_posterior.jl:98-105)."""
+    view = ParamView.__new__(ParamView)
+    view._names, view.blocks = [], []
+    o = 0
+    for name, b in blocks:
+        v = np.empty(b.n + (1 if isinstance(b, Simplex) else 0), dtype=object)
+        for i in range(b.n):
+            v[i] = _Tracer(o + i)
+        if isinstance(b, Simplex):
+            v[b.n] = _Tracer(None)      # the implied last component is not a stored coordinate
+        setattr(view, name, v)
+        view._names.append(name)
+        view.blocks.append(v)
+        o += b.n
+    try:
+        r = f(view)
+    except Exception:
+        return None
+    if isinstance(r, np.ndarray) and r.dtype == object and r.size == 1:
+        r = r.reshape(-1)[0]
+    if isinstance(r, _Tracer) and r.index is not None:
+        return int(r.index)
+    return None

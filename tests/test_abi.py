@@ -148,6 +148,10 @@ def test_coordinate_selector_detection(jp):
     assert probe_coordinate(lambda t: t.p2[0], m.blocks) == 1
     assert probe_coordinate(lambda t: t.p3[4] * 2, m.blocks) is None
     assert probe_coordinate(lambda t: t.p3[1] - t.p3[0], m.blocks) is None
+    # functions that are the identity on part of the range are NOT selectors (reference evaluates f at every node)
+    for g in (lambda t: abs(t.p2[0]), lambda t: max(t.p2[0], 0), lambda t: np.clip(t.p2[0], 0, 2),
+              lambda t: t.p2[0] if t.p2[0] > 0 else -t.p2[0], lambda t: float(t.p2[0]), lambda t: t.p2[0] + 0.0):
+        assert probe_coordinate(g, m.blocks) is None
     m1 = jp.Model((jp.ProbabilityVector(3),))
     assert probe_coordinate(lambda p: p[0], m1.blocks) == 0
     # Simplex: the stored components are coordinates, the implied last one is a host closure

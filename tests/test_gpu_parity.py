@@ -131,7 +131,7 @@ def _cpu_mode_for(O, family, code, obs, hyper):
     if family in (1, 2):
         beta, H, ll = O.glm_mode(family, obs, hyper, d)
         return beta, H, -ll
-    x0 = {0: [0.2, -3.0, -2.0], 3: [4.0, 1.0] + [0.0] * 8, 4: [0.0, 0.0, 0.0, 0.0], 5: [0.0] * d}[family]
+    x0 = {0: [0.2, -3.0, -2.0], 3: [4.0, 1.0] + [0.0] * 8, 4: [0.0] * d, 5: [0.0] * d}[family]
     return cpu_mode(O, family, code, obs, hyper, x0)
 
 
@@ -312,6 +312,22 @@ def test_marginal_host_closures_and_sorted_arrays(jp, O, gpu_ctx):
     assert np.array_equal(m.wv.values, mo["sorted_values"])
     assert np.array_equal(m.wv.weights, mo["sorted_weights"])
     assert np.allclose(m.wv.cum_weights, mo["cum_weights"], rtol=1e-12, atol=1e-15)
+
+
+def test_marginal_of_abs_is_not_the_coordinate(jp, O, gpu_ctx):
+    """A function that is the identity on part of its range (abs) must be evaluated at every node, as the reference does
+    (src/marginal_posterior.jl:98-105), not mistaken for a coordinate selector: posterior of a coefficient straddling 0."""
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((40, 2))
+    yv = X @ np.array([1.0, 0.0]) + rng.standard_normal(40)
+    obs, hyper = np.column_stack([X, yv]), np.array([10.0, 1.0])
+    post, ref = _check_fit_and_marginals(jp, O, gpu_ctx, 4, [0, 0, 1], obs, hyper, 0, 5)
+    th = ref["theta"]
+    assert th[1].min() < 0 < th[1].max()
+    m_abs, m_id = jp.marginals(post, [lambda t: abs(t[1]), lambda t: t[1]])
+    mo = O.marginal(np.abs(th[1]), ref["density"])
+    assert abs(m_abs.mu - mo["mu"]) < 1e-10 and abs(m_abs.sigma - mo["sigma"]) < 1e-9
+    assert m_abs.mu > abs(m_id.mu) + 0.01 and m_abs.itp.values[0] >= 0.0
 
 
 def test_marginal_buffer_matches_oracle(jp, O, gpu_ctx):
@@ -732,7 +748,8 @@ def test_device_side_series_decision(jp, O, gpu_ctx):
     host reads the bounds back and launches one instantiation."""
     from jointposteriors_jl_b200 import distributed as D
     from jointposteriors_jl_b200.model import JointPosterior
-    for kind, N, d, level, xs in (("logistic", 50000, 6, 4, 1.0), ("poisson", 60000, 5, 4, 0.3)):
+    seen = set()
+    for kind, N, d, level, xs in (("logistic", 50000, 6, 4, 1.0), ("poisson", 60000, 5, 4, 0.3), ("logistic", 20000, 6, 5, 1.0)):
         family, obs, hyper = _glm_case(kind, 9, N, d, xs)
         code = [0] * d
         x, H, neg_min = _cpu_mode_for(O, family, code, obs, hyper)
@@ -749,6 +766,8 @@ def test_device_side_series_decision(jp, O, gpu_ctx):
         mu, sg, vn, wn = D.marginals_sharded(loc, list(range(d)))
         assert sh.path_used == jp.PATH_TC
         assert sh.diagnostics["series_terms"] == full.diagnostics["series_terms"]
+        seen.add(int(sh.diagnostics["series_terms"]))
+        print("device-side decision:", kind, N, d, level, "-> NC", sh.diagnostics["series_terms"], "economised", sh.diagnostics["economised"])
         assert sh.diagnostics["economised"] == full.diagnostics["economised"]
         assert np.array_equal(sh.logdens, full.logdens)
         assert np.array_equal(sh.density, full.density)
@@ -757,6 +776,7 @@ def test_device_side_series_decision(jp, O, gpu_ctx):
         assert np.max(np.abs(wn - np.array([m.itp.weights for m in ms]))) < 1e-12
         comm.status()
         comm.destroy()
+    assert 4 in seen and max(seen) > 4, seen      # both launches of the device-decided path ran a real series (NC = 4 | the rest kernel)
     # bounds not met (huge prior scale spreads the nodes): the device decides NC = 0, no instantiation runs, the first
     # blocking call reports it and the sharded call refits on the FP64 path
     family, obs, hyper = _glm_case("logistic", 5, 500, 4)       # the case of test_tc_path_gating
@@ -781,8 +801,8 @@ def test_device_side_series_decision(jp, O, gpu_ctx):
     comm.destroy()
 
 
-@pytest.mark.parametrize("world,N,level,kind", [(2, 60000, 4, "logistic"), (3, 30001, 4, "logistic"), (2, 500, 5, "binmix")],
-                         ids=["w2-tc", "w3-tc-ragged", "w2-fp64"])
+@pytest.mark.parametrize("world,N,level,kind", [(2, 60000, 4, "logistic"), (3, 30001, 4, "logistic"), (2, 30000, 5, "logistic"),
+                                                (2, 500, 5, "binmix")], ids=["w2-tc", "w3-tc-ragged", "w2-tc-nc6", "w2-fp64"])
 def test_p2p_sharded_ranks_on_one_gpu(jp, O, gpu_ctx, world, N, level, kind):
     """The node-sharded fit + global marginals with every exchange inside the library (jp_fit_p2p / jp_marginal_coords_p2p:
     stores into the peers' mailboxes, sequence flags, spinning waits): `world` ranks emulated on ONE GPU -- a context, a
@@ -850,6 +870,8 @@ def test_p2p_sharded_ranks_on_one_gpu(jp, O, gpu_ctx, world, N, level, kind):
     ld = np.concatenate([o[0] for o in out])
     dens = np.concatenate([o[1] for o in out])
     assert all(o[3] == full.path_used for o in out)
+    if level == 5 and kind == "logistic":
+        assert full.diagnostics["series_terms"] == 6      # the gathered rows go through the kernel that serves NC = 6 .. 12
     assert np.max(np.abs(ld - full.logdens)) < 1e-8 * max(1.0, np.max(np.abs(full.logdens)))
     assert relerr(dens, full.density) < 1e-7
     for r in range(1, world):      # every rank holds bit-identical global results
@@ -864,6 +886,132 @@ def test_p2p_sharded_ranks_on_one_gpu(jp, O, gpu_ctx, world, N, level, kind):
     assert relerr(dens, ref["density"]) < tol
     for cm in comms:
         cm.destroy()
+
+
+@pytest.mark.parametrize("world,N,kind", [(2, 60000, "logistic"), (3, 30001, "poisson")], ids=["w2", "w3-ragged"])
+def test_p2p_observation_sharded_ranks_on_one_gpu(jp, O, gpu_ctx, world, N, kind):
+    """OBSERVATION sharding (jp_fit_p2p_obs, jp_mode_p2p): every emulated rank holds only its rows and a posterior over ALL
+    nodes; the ranks exchange slice sums / bounds and per-pair partial sums inside the library.  Every rank must end up with
+    the complete posterior -- bit-identical across ranks, equal to the unsharded fit and the oracle within the tolerance of
+    the tensor-core path -- and the distributed Newton iteration with the mode of the whole data set."""
+    import threading
+    import ctypes as C
+    from jointposteriors_jl_b200 import distributed as D
+    from jointposteriors_jl_b200.model import Context, DeviceData, JointPosterior
+    d, level = 6, 4
+    family, obs, hyper = _glm_case(kind, 11, N, d, 1.0 if kind == "logistic" else 0.3)
+    code = [0] * d
+    M = _model_for(jp, code)
+    dfull = _upload(jp, gpu_ctx, family, obs, hyper)
+    x, U, neg_min = jp.mode(M, dfull)
+    full = jp.fit(M, dfull, level, path=jp.PATH_TC, mode_result=(x, U, neg_min))
+    mfull = jp.marginals(full, list(range(d)))
+    ctxs = [Context(0) for _ in range(world)]
+    comms = [D.Comm.__new__(D.Comm) for _ in range(world)]
+    for r, (cx, cm) in enumerate(zip(ctxs, comms)):
+        h = C.c_void_p()
+        jp._lib.check(jp.lib().jp_comm_create(cx.handle, C.c_int(r), C.c_int(world), C.c_longlong(D.bulk_bytes_obs(full.n_nodes, world)), C.byref(h)))
+        cm.handle, cm.ctx, cm.rank, cm.world, cm.group = h, cx, r, world, None
+    arr = (C.c_void_p * world)(*[cm.handle for cm in comms])
+    for cm in comms:
+        jp._lib.check(jp.lib().jp_comm_connect_local(cm.handle, arr))
+    raw = _RawData(family, obs, hyper)
+    from jointposteriors_jl_b200.data import Data
+    raw.__class__ = type("RawData", (Data,), dict(records=_RawData.records, family=family))
+    slices, posts = [], []
+    for r, cx in enumerate(ctxs):          # device-wide synchronising work before the ranks run side by side
+        b, e, _ = D.row_slice(len(obs), r, world)
+        dd = DeviceData(cx, raw, rows=(b, e))
+        assert dd.N == e - b
+        grid = cx.grid(0, d, level)
+        sh = JointPosterior(jp.Model(M.params), dd, grid, x, U, neg_min)
+        sh.evaluate()
+        sh.density
+        slices.append(dd)
+        posts.append(sh)
+    out, errs = [None] * world, []
+
+    def rank_main(r):
+        try:
+            mr = D.mode_p2p(M, slices[r], comms[r])
+            res = None
+            for rep in range(2):
+                sp = D.ObsShardedPosterior(posts[r], comms[r], None).refit()
+                res = sp.marginals(list(range(d)))
+            comms[r].status()
+            out[r] = (posts[r].logdens, posts[r].density, res, mr, posts[r].path_used)
+        except Exception as e:      # noqa: BLE001
+            errs.append((r, repr(e)))
+
+    th = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    assert not errs, errs
+    assert all(o is not None for o in out), "a rank did not finish (exchange timed out?)"
+    for r in range(1, world):          # bit-identical on every rank
+        assert np.array_equal(out[r][0], out[0][0]) and np.array_equal(out[r][1], out[0][1])
+        assert all(np.array_equal(a, b) for a, b in zip(out[r][3], out[0][3]))
+    ld, dens, ms, mr, path_used = out[0]
+    assert path_used == jp.PATH_TC
+    assert np.max(np.abs(mr[0] - x)) < 1e-9 and abs(mr[2] - neg_min) < 1e-8 * abs(neg_min) and np.max(np.abs(mr[1] - U)) < 1e-9
+    assert np.max(np.abs(ld - full.logdens)) < 1e-8 * max(1.0, np.max(np.abs(full.logdens)))
+    assert relerr(dens, full.density) < 1e-7
+    assert np.max(np.abs(np.array([m.mu for m in ms]) - [m.mu for m in mfull])) < 1e-9
+    assert np.max(np.abs(np.array([m.itp.weights for m in ms]) - np.array([m.itp.weights for m in mfull]))) < 1e-7
+    idx, w = O.smolyak(0, d, level)
+    ref = O.eval_grid(0, family, code, idx, w, x, U, neg_min, obs, hyper)
+    assert relerr(dens, ref["density"]) < TOLTC
+    for cm in comms:
+        cm.destroy()
+
+
+def test_raw_build_result(jp, O, gpu_ctx):
+    """RawBuild (reference src/joint_posterior.jl:9-14,183-188; consumers src/marginal_posterior.jl:68-77,106-115):
+    fit(Model(params, SmolyakRaw[rule])) keeps the d x M UNCONSTRAINED node cache; Theta and the marginals are constructed
+    from it on the device and must equal the CacheBuild fit of the same model."""
+    obs, hyper = readme_records()
+    x, H, neg_min = _cpu_mode_for(O, 0, [2, 2, 2], obs, hyper)
+    U = O.inv_chol(2.0 * H)
+    dd = _upload(jp, gpu_ctx, 0, obs, hyper)
+    Mc = jp.Model((jp.ProbabilityVector(3),), jp.Smolyak[jp.KronrodPatterson])
+    Mr = jp.Model((jp.ProbabilityVector(3),), jp.SmolyakRaw[jp.KronrodPatterson])
+    pc = jp.fit(Mc, dd, 6, mode_result=(x, U, neg_min))
+    pr = jp.fit(Mr, dd, 6, mode_result=(x, U, neg_min))
+    assert isinstance(pr, jp.JointPosteriorRaw) and not isinstance(pc, jp.JointPosteriorRaw)
+    idx, w = O.smolyak(1, 3, 6)
+    ref = O.eval_grid(1, 0, [2, 2, 2], idx, w, x, U, neg_min, obs, hyper)
+    cache = pr.grid.cache
+    assert cache.shape == (3, pr.n_nodes)
+    assert np.max(np.abs(1 / (1 + np.exp(-cache)) - ref["theta"])) < 1e-14      # the cache is unconstrained: logistic(cache) = Theta
+    assert np.array_equal(pr.grid.density, pr.density) and relerr(pr.density, ref["density"]) < TOL64
+    assert np.array_equal(pr.density, pc.density)
+    assert np.max(np.abs(pr.Theta - pc.Theta)) < 1e-15
+    fs = [0, 2, lambda p: p[1] - p[2], lambda p: p[0]]
+    for a, b in zip(jp.marginals(pr, fs), jp.marginals(pc, fs)):
+        assert abs(a.mu - b.mu) < 1e-14 and abs(a.sigma - b.sigma) < 1e-13
+        assert np.max(np.abs(a.itp.weights - b.itp.weights)) < 1e-13 and np.max(np.abs(a.itp.values - b.itp.values)) < 1e-14
+    with pytest.raises(jp.JPError):
+        import ctypes as C
+        jp._lib.check(jp.lib().jp_get_cache(pc.handle, jp._lib.ptr(np.zeros((3, pc.n_nodes)))))
+    # a model with an identity block: its coordinates are zero-copy columns of the cache, the constrained ones are constructed
+    ys = np.array([28, 8, -3, 7, -1, 1, 18, 12.0])
+    ss = np.array([15, 10, 16, 11, 9, 11, 10, 18.0])
+    nc = 3 | (0 << 8) | (1 << 16)
+    code = [0, 1] + [nc] * 8
+    ob2, hy2 = np.column_stack([ys, ss]), np.array([25.0])
+    x2, H2, nm2 = _cpu_mode_for(O, 3, code, ob2, hy2)
+    U2 = O.inv_chol(2.0 * H2)
+    d2 = _upload(jp, gpu_ctx, 3, ob2, hy2)
+    Mc2 = _model_for(jp, code)
+    Mr2 = _model_for(jp, code)
+    Mr2.build = jp.SmolyakRaw(jp.GenzKeister)
+    pc2 = jp.fit(Mc2, d2, 4, mode_result=(x2, U2, nm2))
+    pr2 = jp.fit(Mr2, d2, 4, mode_result=(x2, U2, nm2))
+    assert np.max(np.abs(pr2.Theta - pc2.Theta)) < 1e-13 and np.array_equal(pr2.density, pc2.density)
+    for a, b in zip(jp.marginals(pr2, list(range(10))), jp.marginals(pc2, list(range(10)))):
+        assert abs(a.mu - b.mu) < 1e-12 and np.max(np.abs(a.itp.weights - b.itp.weights)) < 1e-12
 
 
 @pytest.mark.parametrize("kind,N,d,level", [("logistic", 40000, 1, 5), ("logistic", 150000, 2, 7), ("poisson", 127, 2, 3),
