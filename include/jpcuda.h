@@ -45,7 +45,7 @@ typedef enum jp_status {
 enum { JP_RULE_GENZ_KEISTER = 0, JP_RULE_KRONROD_PATTERSON = 1 };
 /* constraint transforms (ConstrainedParameters RealVector / PositiveVector / ProbabilityVector,
  * reference src/JointPosteriors.jl:22-26, README.md:32,247-248) -- one code per unconstrained coordinate */
-enum { JP_T_REAL = 0, JP_T_POSITIVE = 1, JP_T_PROBABILITY = 2, JP_T_NONCENTRED = 3, JP_T_SIMPLEX = 4 };
+enum { JP_T_REAL = 0, JP_T_POSITIVE = 1, JP_T_PROBABILITY = 2, JP_T_NONCENTRED = 3, JP_T_SIMPLEX = 4, JP_T_COVMAT = 5 };
 /* JP_T_NONCENTRED couples coordinate k to two EARLIER constrained coordinates: theta_k = theta_loc + theta_scale * x_k,
  * log|J| += log(theta_scale); loc and scale travel in the code word (hierarchical models whose centred
  * parameterisation has no joint mode, e.g. eight schools).  Transforms are applied in coordinate order. */
@@ -56,6 +56,11 @@ enum { JP_T_REAL = 0, JP_T_POSITIVE = 1, JP_T_PROBABILITY = 2, JP_T_NONCENTRED =
  * (additive log-ratio map; det(diag(theta) - theta theta') = prod of all n components).  Every coordinate of the block
  * carries the same code word. */
 #define JP_T_SIMPLEX_CODE(first, len) (JP_T_SIMPLEX | ((first) << 8) | ((len) << 16))
+/* JP_T_COVMAT (ConstrainedParameters CovarianceMatrix, reference src/JointPosteriors.jl:22): the p (p + 1) / 2 coordinates
+ * [first, first + len) hold the lower triangle of a p x p matrix row by row, (0,0), (1,0), (1,1), (2,0), ..  Unconstrained:
+ * the log-Cholesky factor (L_ii = exp(x_ii), L_ij = x_ij for i > j); constrained: the lower triangle of Sigma = L L' in the
+ * same order; log|J| = p log 2 + sum_{i=0}^{p-1} (p - i + 1) x_ii.  Every coordinate of the block carries the same code word. */
+#define JP_T_COVMAT_CODE(first, len) (JP_T_COVMAT | ((first) << 8) | ((len) << 16))
 #define JP_T_KIND(code) ((code) & 0xFF)
 #define JP_T_LOC(code) (((code) >> 8) & 0xFF)
 #define JP_T_SCALE(code) (((code) >> 16) & 0xFF)
@@ -66,7 +71,9 @@ enum {
   JP_FAM_POISSON = 2,          /* Poisson regression (log link), N(0, s^2) prior */
   JP_FAM_HIER_NORMAL = 3,      /* hierarchical normal ("eight schools") */
   JP_FAM_NORMAL_LINEAR = 4,    /* README Example 2 "HiWorld", reference README.md:245-258 */
-  JP_FAM_MULTINOMIAL = 5       /* category counts with a symmetric Dirichlet prior on a Simplex block */
+  JP_FAM_MULTINOMIAL = 5,      /* category counts with a symmetric Dirichlet prior on a Simplex block */
+  JP_FAM_MVN_COV = 6,          /* zero-mean multivariate normal, inverse-Wishart prior, on a CovarianceMatrix block */
+  JP_FAM_ANOVA2 = 7            /* balanced two-factor random-effects ANOVA, README Example 3 (reference README.md:416-470) */
 };
 /* log-density evaluation path of jp_fit */
 enum {

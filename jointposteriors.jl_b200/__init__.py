@@ -5,15 +5,15 @@ this package is the host-side mirror of the reference's Julia interface and bind
 ctypes.  There is no CPU fallback: importing works anywhere, computing needs a B200.
 """
 from ._lib import JPError, NotPositiveDefinite, PATH_AUTO, PATH_FP64, PATH_TC, lib
-from .data import (BinaryClassificationData, Data, HierNormalData, LogisticData, MultinomialData, NormalLinearData,
-                   PoissonData)
+from .data import (BinaryClassificationData, Data, HierNormalData, LogisticData, MultinomialData, MvNormalCovData,
+                   NormalLinearData, PoissonData, TwoFactorANOVAData)
 from .linalg import chol, deduce_scale_dynamic, inv_chol, inv_upper, reduce_dimensions, reduce_dimensions_ldr, try_chol
 from .marginals import (Grid, MarginalBuffer, NestedPolyGLM, Normal, cdf, marginal, marginal_buffer, marginal_smooth, marginals,
                         pdf, quantile)
 from .model import (Context, DeviceData, Dynamic, FixedRank, Full, LDR, GenzKeister, JointPosterior, JointPosteriorRaw,
                     KronrodPatterson, Model, Smolyak, SmolyakRaw, default, fit, log_density_unc, mode)
-from .distributed import ShardedPosterior, fit_distributed
-from .params import NonCentredVector, PositiveVector, ProbabilityVector, RealVector, Simplex, parameter
+from .distributed import Comm, ObsShardedPosterior, ShardedPosterior, fit_distributed, fit_obs_sharded, mode_p2p
+from .params import CovarianceMatrix, NonCentredVector, PositiveVector, ProbabilityVector, RealVector, Simplex, parameter
 
 __all__ = [
     "Model", "fit", "marginal", "marginals", "marginal_buffer", "MarginalBuffer", "mode", "quantile", "cdf", "pdf", "Grid", "Normal", "NestedPolyGLM", "marginal_smooth", "JointPosterior", "JointPosteriorRaw",
@@ -21,5 +21,6 @@ __all__ = [
     "LogisticData", "PoissonData", "HierNormalData", "NormalLinearData", "MultinomialData", "Smolyak", "SmolyakRaw", "GenzKeister",
     "KronrodPatterson", "Dynamic", "Full", "FixedRank", "LDR", "default", "Context", "DeviceData", "chol", "try_chol",
     "inv_upper", "inv_chol", "reduce_dimensions", "reduce_dimensions_ldr", "deduce_scale_dynamic", "JPError", "NotPositiveDefinite",
-    "PATH_AUTO", "PATH_FP64", "PATH_TC", "log_density_unc", "fit_distributed", "ShardedPosterior",
+    "PATH_AUTO", "PATH_FP64", "PATH_TC", "log_density_unc", "fit_distributed", "ShardedPosterior", "ObsShardedPosterior",
+    "fit_obs_sharded", "mode_p2p", "Comm", "CovarianceMatrix", "MvNormalCovData", "TwoFactorANOVAData",
 ]

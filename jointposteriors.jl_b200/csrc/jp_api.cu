@@ -335,8 +335,9 @@ static int download(jp_posterior* p, const double* d_src, double* h_dst, size_t 
   // The caller's array is pageable (a Julia Vector / numpy array): results that fit the context's pinned buffer are
   // DMA-ed there at PCIe speed and copied out by the host; larger ones take the driver's staged pageable path.
   JP_CUDA(cudaSetDevice(p->ctx->device));
-  if (n <= JP_PINNED_DOUBLES) {
+  if (n <= JP_PINNED_DOUBLES - JP_PINNED_TAIL_DOUBLES) {
     JP_CUDA(jp_pinned_acquire(p->ctx));      // no earlier host-to-device copy may still be reading the staging buffer
+    JP_TRY(jp_fit_tc_verify_prefetch(p));
     JP_CUDA(cudaMemcpyAsync(p->ctx->h_pinned, d_src, n * 8, cudaMemcpyDeviceToHost, p->ctx->stream));
     JP_CUDA(cudaStreamSynchronize(p->ctx->stream));
     std::memcpy(h_dst, p->ctx->h_pinned, n * 8);

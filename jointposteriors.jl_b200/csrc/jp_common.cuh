@@ -134,6 +134,7 @@ inline void jp_trace_mark(jp_ctx* ctx, const char* name, cudaStream_t st) {
 #define JP_MARK(ctx, name) jp_trace_mark((ctx), (name), (ctx)->stream)
 #define JP_MARK_SIDE(ctx, name) jp_trace_mark((ctx), (name), (ctx)->side)
 #define JP_SCRATCH_DOUBLES (1 << 16)
+#define JP_PINNED_TAIL_DOUBLES 16      // last doubles of the pinned buffer: the device-side series decision on its way to the host
 #define JP_PINNED_DOUBLES (1 << 18)   // 2 MB: result vectors of up to 262 144 nodes are downloaded through it
 // Fixed sub-regions of the pinned staging buffer.  [0, JP_PINNED_CONSTS_END): the per-fit constants (mu d, U d x p, transform
 // codes d: at most 64 + 4096 + 32 doubles) staged by jp_upload_fit_consts; the bounds of the tensor-core path's a-priori gate
@@ -396,6 +397,7 @@ int jp_fit_tc_prep_gathered(jp_posterior* post, const jp_fit_args* args, const d
 int jp_fit_tc_coef_slab(jp_posterior* post, int n_rows, float** d_local, float** d_all, long long* count);
 int jp_fit_tc_run_prepared(jp_posterior* post, const jp_fit_args* args, bool finish = true);
 int jp_fit_tc_launch_dev(jp_posterior* post, const jp_fit_args* args, jp_comm* comm, int obs_sharded);   // device-side series-length decision
+int jp_fit_tc_verify_prefetch(jp_posterior* post);   // queue the read-back in front of the caller's own synchronisation
 int jp_fit_tc_verify(jp_posterior* post);      // read that decision back (first blocking call after the fit)
 void jp_tc_data_free(jp_data* data);
 void jp_tc_post_free(jp_posterior* post);

@@ -163,6 +163,99 @@ struct FamMultinomial {
   }
 };
 
+// zero-mean multivariate normal with unknown covariance on a CovarianceMatrix block, inverse-Wishart(nu0, psi0 I) prior
+// (lpdf_InverseWishart is among the reference's exports, src/JointPosteriors.jl:36): theta = lower triangle of Sigma row by
+// row; the records are the p rows of the scatter matrix S = sum y y' (sufficient statistic); hyper = (n_obs, nu0, psi0).
+//   log p = -(n + nu0 + p + 1) / 2 log|Sigma| - 1/2 tr((S + psi0 I) Sigma^-1):   Sigma | y ~ inverse-Wishart(nu0 + n, S + psi0 I)
+// Every call factorises Sigma again (p <= 10, p records): this family exists to pin the transform, not for speed.
+struct FamMvnCov {
+  static constexpr int kId = JP_FAM_MVN_COV;
+  static constexpr const char* kName = "mvn_cov";
+  static constexpr int kPmax = 10;
+  static bool shape_ok(int d, int ncols, long long N) { return N >= 1 && N <= kPmax && ncols == (int)N && d == (int)(N * (N + 1) / 2); }
+  // Cholesky factor C (packed lower triangle) of Sigma; returns log|Sigma|
+  template <int DPAD>
+  __device__ static double factor(const double (&t)[DPAD], int p, double* C) {
+    const int len = p * (p + 1) / 2;
+#pragma unroll
+    for (int j = 0; j < DPAD; ++j)
+      if (j < len) C[j] = t[j];
+    double logdet = 0;
+    for (int i = 0; i < p; ++i)
+      for (int j = 0; j <= i; ++j) {
+        double v = C[i * (i + 1) / 2 + j];
+        for (int k = 0; k < j; ++k) v -= C[i * (i + 1) / 2 + k] * C[j * (j + 1) / 2 + k];
+        if (i == j) {
+          v = sqrt(v);
+          logdet += 2.0 * log(v);
+        } else {
+          v /= C[j * (j + 1) / 2 + j];
+        }
+        C[i * (i + 1) / 2 + j] = v;
+      }
+    return logdet;
+  }
+  template <int DPAD>
+  __device__ static double prior(const double (&t)[DPAD], int, long long N, const double* h) {
+    double C[kPmax * (kPmax + 1) / 2];
+    const int p = (int)N;
+    return -0.5 * (h[0] + h[1] + p + 1) * factor<DPAD>(t, p, C);
+  }
+  template <int DPAD>
+  __device__ static double obs(const double (&t)[DPAD], int d, const double* r, long long n, const double* h) {
+    // row n of Sigma^-1 against row n of S + psi0 I:  Sigma^-1 e_n by two triangular solves
+    double C[kPmax * (kPmax + 1) / 2], y[kPmax];
+    int p = 0;
+    while ((p + 1) * (p + 2) / 2 <= d) ++p;
+    factor<DPAD>(t, p, C);
+    for (int i = 0; i < p; ++i) {            // C y = e_n
+      double v = (i == (int)n) ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) v -= C[i * (i + 1) / 2 + k] * y[k];
+      y[i] = v / C[i * (i + 1) / 2 + i];
+    }
+    for (int i = p - 1; i >= 0; --i) {       // C' x = y
+      double v = y[i];
+      for (int k = i + 1; k < p; ++k) v -= C[k * (k + 1) / 2 + i] * y[k];
+      y[i] = v / C[i * (i + 1) / 2 + i];
+    }
+    double row = 0;
+    for (int j = 0; j < p; ++j) row += y[j] * (r[j] + (j == (int)n ? h[2] : 0.0));
+    return -0.5 * row;
+  }
+};
+
+// balanced two-factor random-effects ANOVA with the random effects integrated out (README Example 3, reference
+// README.md:416-470; `TF_RE_ANOVA` of the absent LogDensities package): theta = (mu, s2_P, s2_O, s2_PO, s2_R); records
+// (SS_k, df_k) for parts, operators, interaction, error and (grand mean, P O R); hyper = (P, O, R, folded-Cauchy scale of
+// the operator standard deviation).  Expected mean squares and the variance of the grand mean as in oracle/jp_oracle.cpp.
+struct FamAnova2 {
+  static constexpr int kId = JP_FAM_ANOVA2;
+  static constexpr const char* kName = "anova2";
+  static bool shape_ok(int d, int ncols, long long N) { return d == 5 && ncols == 2 && N == 5; }
+  template <int DPAD>
+  __device__ static double lambda(const double (&t)[DPAD], int k, const double* h) {
+    const double base = t[4] + h[2] * t[3];
+    if (k == 0) return base + h[1] * h[2] * t[1];
+    if (k == 1) return base + h[0] * h[2] * t[2];
+    if (k == 2) return base;
+    return t[4];
+  }
+  template <int DPAD>
+  __device__ static double prior(const double (&t)[DPAD], int, long long, const double* h) {
+    const double so = sqrt(t[2]) / h[3];
+    return -log1p(so * so) - 0.5 * log(t[2]);
+  }
+  template <int DPAD>
+  __device__ static double obs(const double (&t)[DPAD], int, const double* r, long long n, const double* h) {
+    if (n < 4) {
+      const double lam = lambda<DPAD>(t, (int)n, h);
+      return -0.5 * r[1] * log(lam) - 0.5 * r[0] / lam;
+    }
+    const double vm = (lambda<DPAD>(t, 0, h) + lambda<DPAD>(t, 1, h) - lambda<DPAD>(t, 2, h)) / r[1];
+    return -0.5 * log(vm) - 0.5 * (r[0] - t[0]) * (r[0] - t[0]) / vm;
+  }
+};
+
 // ------------------------------------------------------------------------------------ registry
 struct JpFitLaunchParams;   // defined in jp_fit.cu
 typedef int (*jp_family_launcher)(jp_posterior* post, const JpFitLaunchParams& lp);

@@ -24,6 +24,7 @@ namespace cg = cooperative_groups;
 
 #define JP_FIT_THREADS 128
 #define JP_FIT_TILE_DOUBLES 4096     // shared-memory tile of observation records (32 KB)
+#define JP_COVMAT_MAX_LEN 55          // lower triangle of a 10 x 10 covariance matrix (JP_MAX_D = 64 coordinates in all)
 
 struct JpFitLaunchParams {
   int d, p, ncols, rule;
@@ -90,11 +91,41 @@ __device__ __forceinline__ double jp_construct(double (&th)[DPAD], int d, const 
         th[j] = exp(l);
       }
   }
+  // covariance-matrix blocks: Sigma = L L' from the log-Cholesky coordinates.  The block is copied to a small local array
+  // (run-time indices; only models that declare such a block ever execute this loop body).
+#pragma unroll 1
+  for (int k0 = 0; k0 < d; ++k0) {
+    const int code = s_code[k0];
+    if (JP_T_KIND(code) != JP_T_COVMAT || JP_T_LOC(code) != k0) continue;
+    const int len = JP_T_SCALE(code);
+    int p = 0;
+    while ((p + 1) * (p + 2) / 2 <= len) ++p;
+    double Lm[JP_COVMAT_MAX_LEN];
+#pragma unroll
+    for (int j = 0; j < DPAD; ++j)
+      if (j >= k0 && j < k0 + len) Lm[j - k0] = th[j];
+    for (int i = 0; i < p; ++i) {
+      const int e = i * (i + 1) / 2 + i;
+      lj += (p - i + 1) * Lm[e];
+      Lm[e] = exp(Lm[e]);
+    }
+    lj += p * 0.69314718055994530942;
+    double Sg[JP_COVMAT_MAX_LEN];
+    for (int i = 0, e = 0; i < p; ++i)
+      for (int j = 0; j <= i; ++j, ++e) {
+        double v = 0;
+        for (int k = 0; k <= j; ++k) v += Lm[i * (i + 1) / 2 + k] * Lm[j * (j + 1) / 2 + k];
+        Sg[e] = v;
+      }
+#pragma unroll
+    for (int j = 0; j < DPAD; ++j)
+      if (j >= k0 && j < k0 + len) th[j] = Sg[j - k0];
+  }
 #pragma unroll
   for (int k = 0; k < DPAD; ++k) {
     if (k < d) {
       const int code = s_code[k];
-      if (JP_T_KIND(code) == JP_T_SIMPLEX) {
+      if (JP_T_KIND(code) == JP_T_SIMPLEX || JP_T_KIND(code) == JP_T_COVMAT) {
         // transformed above
       } else if (JP_T_KIND(code) == JP_T_NONCENTRED) {
         // theta_k = theta_loc + theta_scale * x_k with loc, scale < k already transformed; the register
@@ -462,6 +493,8 @@ JP_REGISTER_FAMILY(FamPoisson)
 JP_REGISTER_FAMILY(FamHierNormal)
 JP_REGISTER_FAMILY(FamNormalLinear)
 JP_REGISTER_FAMILY(FamMultinomial)
+JP_REGISTER_FAMILY(FamMvnCov)
+JP_REGISTER_FAMILY(FamAnova2)
 
 // ------------------------------------------------------------------------------------ host side
 int jp_upload_fit_consts(jp_posterior* post, const jp_fit_args* args) {
@@ -494,8 +527,18 @@ int jp_upload_fit_consts(jp_posterior* post, const jp_fit_args* args) {
 int jp_check_transform_codes(const char* who, const int* code, int d) {
   for (int k = 0; k < d; ++k) {
     int kind = JP_T_KIND(code[k]);
-    JP_REQUIRE(kind >= 0 && kind <= JP_T_SIMPLEX && (kind >= JP_T_NONCENTRED || code[k] == kind),
+    JP_REQUIRE(kind >= 0 && kind <= JP_T_COVMAT && (kind >= JP_T_NONCENTRED || code[k] == kind),
                "%s: unknown transform code %d at coordinate %d", who, code[k], k);
+    if (kind == JP_T_COVMAT) {
+      const int first = JP_T_LOC(code[k]), len = JP_T_SCALE(code[k]);
+      int p = 0;
+      while ((p + 1) * (p + 2) / 2 <= len) ++p;
+      JP_REQUIRE(len >= 1 && len <= JP_COVMAT_MAX_LEN && p * (p + 1) / 2 == len && first <= k && k < first + len && first + len <= d &&
+                 (code[k] >> 24) == 0, "%s: covariance-matrix coordinate %d: block [%d, %d) is not the lower triangle of a p x p matrix, p <= 10",
+                 who, k, first, first + len);
+      JP_REQUIRE(code[first] == code[k], "%s: covariance-matrix block [%d, %d) does not carry one code word (coordinate %d)", who, first,
+                 first + len, k);
+    }
     if (kind == JP_T_SIMPLEX) {
       const int first = JP_T_LOC(code[k]), len = JP_T_SCALE(code[k]);
       JP_REQUIRE(len >= 1 && first <= k && k < first + len && first + len <= d && (code[k] >> 24) == 0,

@@ -42,6 +42,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #include "jp_common.cuh"
 #include "jp_fold_tables.h"
@@ -125,6 +126,7 @@ struct TcPostState {
   bool node_prep_queued = false;   // sharded prep: tc_node_prep already runs under the host's wait for the bounds
   TcDecision* d_dec = nullptr;   // series length decided on the device (jp_fit_tc_launch_dev)
   bool dec_pending = false;        // ... and not yet read back by the host
+  bool dec_prefetched = false;     // ... its copy into the pinned tail is queued (jp_fit_tc_verify_prefetch)
   CUtensorMap tmB;
 };
 
@@ -1795,19 +1797,37 @@ int jp_fit_tc_launch_dev(jp_posterior* post, const jp_fit_args* args, jp_comm* c
     JP_MARK(ctx, "fit:partials_exchanged");
   }
   ps->dec_pending = true;
+  ps->dec_prefetched = false;
   post->tc_bounds[3] = -1;       // not known to the host until jp_fit_tc_verify
   return JP_OK;
 }
 
 // The host reads the device's decision at its first blocking call after the fit (the result downloads synchronise anyway).
 // JP_ERR_UNSUPPORTED: the bounds were not met and no instantiation ran -- the results of this fit are garbage.
+// Queue the read-back behind whatever the caller is about to synchronise on (the decision then rides in the same wait as
+// the results: no second synchronisation, no pageable copy).  The slot is the tail of the context's pinned buffer.
+int jp_fit_tc_verify_prefetch(jp_posterior* post) {
+  TcPostState* ps = post ? static_cast<TcPostState*>(post->tc_state) : nullptr;
+  if (!ps || !ps->dec_pending || ps->dec_prefetched) return JP_OK;
+  static_assert(sizeof(TcDecision) <= JP_PINNED_TAIL_DOUBLES * 8, "decision record does not fit the pinned tail");
+  JP_CUDA(cudaMemcpyAsync(post->ctx->h_pinned + (JP_PINNED_DOUBLES - JP_PINNED_TAIL_DOUBLES), ps->d_dec, sizeof(TcDecision),
+                          cudaMemcpyDeviceToHost, post->ctx->stream));
+  ps->dec_prefetched = true;
+  return JP_OK;
+}
+
 int jp_fit_tc_verify(jp_posterior* post) {
   TcPostState* ps = post ? static_cast<TcPostState*>(post->tc_state) : nullptr;
   if (!ps || !ps->dec_pending) return JP_OK;
   ps->dec_pending = false;
   TcDecision dec;
-  JP_CUDA(cudaStreamSynchronize(post->ctx->stream));
-  JP_CUDA(cudaMemcpy(&dec, ps->d_dec, sizeof dec, cudaMemcpyDeviceToHost));
+  if (ps->dec_prefetched) {      // the caller has synchronised the stream since jp_fit_tc_verify_prefetch
+    ps->dec_prefetched = false;
+    std::memcpy(&dec, post->ctx->h_pinned + (JP_PINNED_DOUBLES - JP_PINNED_TAIL_DOUBLES), sizeof dec);
+  } else {
+    JP_CUDA(cudaStreamSynchronize(post->ctx->stream));
+    JP_CUDA(cudaMemcpy(&dec, ps->d_dec, sizeof dec, cudaMemcpyDeviceToHost));
+  }
   for (int i = 0; i < 6; ++i) post->tc_bounds[i] = dec.diag[i];
   if (dec.NC == 0) {
     post->path_used = 0;

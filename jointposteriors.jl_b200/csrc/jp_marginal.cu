@@ -636,7 +636,7 @@ static int run_marginals(jp_posterior* post, int K, double* h_mu, double* h_sigm
   jp_ctx* ctx = post->ctx;
   const long long M = post->M;
   JP_REQUIRE(M >= 2, "marginal: need at least 2 nodes");
-  JP_REQUIRE((size_t)K * JP_MOUT_STRIDE <= JP_PINNED_DOUBLES, "marginal: K=%d too large for one call", K);
+  JP_REQUIRE((size_t)K * JP_MOUT_STRIDE <= JP_PINNED_DOUBLES - JP_PINNED_TAIL_DOUBLES, "marginal: K=%d too large for one call", K);
   JP_REQUIRE((size_t)K * 4 <= JP_SCRATCH_DOUBLES, "marginal: K=%d too large for one call", K);
   cudaStream_t st = ctx->stream;
   double* d_mom = ctx->d_scratch;   // K x 4: sum w v, sum w v^2, min, max
@@ -652,6 +652,7 @@ static int run_marginals(jp_posterior* post, int K, double* h_mu, double* h_sigm
   JP_MARK(ctx, "marginals:combine");
   JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, post->d_mout, (size_t)K * JP_MOUT_STRIDE * 8, cudaMemcpyDeviceToHost, st));
   JP_MARK(ctx, "marginals:d2h");
+  JP_TRY(jp_fit_tc_verify_prefetch(post));
   JP_CUDA(cudaStreamSynchronize(st));
   JP_TRY(jp_fit_tc_verify(post));      // a series length decided on the device is read back here (no-op otherwise)
   for (int k = 0; k < K; ++k) {
@@ -671,7 +672,7 @@ static int run_marginals_onepass(jp_posterior* post, int K, const int* h_coords,
   jp_ctx* ctx = post->ctx;
   const long long M = post->M;
   JP_REQUIRE(M >= 2, "marginal: need at least 2 nodes");
-  JP_REQUIRE((size_t)K * JP_MOUT_STRIDE <= JP_PINNED_DOUBLES && K <= JP_COUNTERS, "marginal: K=%d too large for one call", K);
+  JP_REQUIRE((size_t)K * JP_MOUT_STRIDE <= JP_PINNED_DOUBLES - JP_PINNED_TAIL_DOUBLES && K <= JP_COUNTERS, "marginal: K=%d too large for one call", K);
   cudaStream_t st = ctx->stream;
   if (post->coords_host.size() != (size_t)K || !std::equal(h_coords, h_coords + K, post->coords_host.begin())) {
     jp_dfree(ctx, post->d_coords);
@@ -692,6 +693,7 @@ static int run_marginals_onepass(jp_posterior* post, int K, const int* h_coords,
   JP_CHECK_LAUNCH(ctx);
   JP_MARK(ctx, "marginals:onepass");
   JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, post->d_mout, (size_t)K * JP_MOUT_STRIDE * 8, cudaMemcpyDeviceToHost, st));
+  JP_TRY(jp_fit_tc_verify_prefetch(post));
   JP_CUDA(cudaStreamSynchronize(st));
   JP_TRY(jp_fit_tc_verify(post));      // a series length decided on the device is read back here (no-op otherwise)
   for (int k = 0; k < K; ++k) {
@@ -914,12 +916,13 @@ int jp_marginal_combine_gathered(jp_posterior* post, int K, int world, const dou
   JP_REQUIRE(post && d_gathered_moments && d_gathered_cands && world >= 1, "jp_marginal_combine_gathered: bad argument");
   JP_ENTER_CTX(post->ctx);
   jp_ctx* ctx = post->ctx;
-  JP_REQUIRE((size_t)K * JP_MOUT_STRIDE <= JP_PINNED_DOUBLES, "marginal: K=%d too large for one call", K);
+  JP_REQUIRE((size_t)K * JP_MOUT_STRIDE <= JP_PINNED_DOUBLES - JP_PINNED_TAIL_DOUBLES, "marginal: K=%d too large for one call", K);
   JP_TRY(ensure_marginal_buffers(post, K));
   cudaStream_t st = ctx->stream;
   jp_combine_gathered_kernel<<<K, 128, 0, st>>>(d_gathered_moments, d_gathered_cands, world, K, post->d_mout);
   JP_CHECK_LAUNCH(ctx);
   JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, post->d_mout, (size_t)K * JP_MOUT_STRIDE * 8, cudaMemcpyDeviceToHost, st));
+  JP_TRY(jp_fit_tc_verify_prefetch(post));
   JP_CUDA(cudaStreamSynchronize(st));
   JP_TRY(jp_fit_tc_verify(post));      // a series length decided on the device is read back here (no-op otherwise)
   for (int k = 0; k < K; ++k) {
@@ -975,6 +978,7 @@ int jp_marginal_coords_p2p(jp_posterior* post, jp_comm* comm, int K, const int* 
     JP_CHECK_LAUNCH(ctx);
     JP_CUDA(jp_pinned_acquire(ctx));
     JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, post->d_mout, (size_t)Kb * JP_MOUT_STRIDE * 8, cudaMemcpyDeviceToHost, st));
+    JP_TRY(jp_fit_tc_verify_prefetch(post));
     JP_CUDA(cudaStreamSynchronize(st));
     JP_TRY(jp_fit_tc_verify(post));
     for (int k = 0; k < Kb; ++k) {

@@ -7,7 +7,7 @@ plugin reads.
 """
 import numpy as np
 
-FAM_BINOMIAL_MIXTURE, FAM_LOGISTIC, FAM_POISSON, FAM_HIER_NORMAL, FAM_NORMAL_LINEAR, FAM_MULTINOMIAL = range(6)
+FAM_BINOMIAL_MIXTURE, FAM_LOGISTIC, FAM_POISSON, FAM_HIER_NORMAL, FAM_NORMAL_LINEAR, FAM_MULTINOMIAL, FAM_MVN_COV, FAM_ANOVA2 = range(8)
 
 
 class Data:
@@ -113,3 +113,66 @@ class MultinomialData(Data):
 
     def records(self):
         return np.ascontiguousarray(self.counts[:, None]), np.array([self.alpha - 1.0])
+
+
+class MvNormalCovData(Data):
+    """Zero-mean multivariate normal observations y_i in R^p with unknown covariance Sigma (a CovarianceMatrix(p) block) and
+    an inverse-Wishart(nu0, psi0 I) prior (lpdf_InverseWishart: reference src/JointPosteriors.jl:36).  The records are the p
+    rows of the scatter matrix S = sum_i y_i y_i' (sufficient statistic); the posterior is inverse-Wishart(nu0 + n, S + psi0 I)
+    in closed form, which is what pins the covariance-matrix transform."""
+    family = FAM_MVN_COV
+
+    def __init__(self, Y, nu0=None, psi0=1.0):
+        Y = np.asarray(Y, dtype=np.float64)
+        if Y.ndim != 2 or Y.shape[0] < 1 or not 1 <= Y.shape[1] <= 10:
+            raise ValueError("Y must be n x p with 1 <= p <= 10")
+        self.n, self.p = Y.shape
+        self.S = Y.T @ Y
+        self.nu0 = float(self.p + 2 if nu0 is None else nu0)
+        self.psi0 = float(psi0)
+
+    def records(self):
+        return np.ascontiguousarray(self.S), np.array([float(self.n), self.nu0, self.psi0])
+
+    def posterior_mean(self):
+        """E[Sigma | y] of the inverse-Wishart posterior."""
+        return (self.S + self.psi0 * np.eye(self.p)) / (self.nu0 + self.n - self.p - 1)
+
+
+class TwoFactorANOVAData(Data):
+    """Balanced two-factor random-effects ANOVA (README Example 3, reference README.md:416-470: `TF_RE_ANOVA_Data(y, yp, yo)`
+    of the absent LogDensities package): y[i] measured on part yp[i] by operator yo[i], R replicates per cell.  Parameters
+    (mu, s2_P, s2_O, s2_PO, s2_R) = RealVector(1) + PositiveVector(4); the random effects are integrated out, the records are
+    the four ANOVA sums of squares with their degrees of freedom and the grand mean; folded-Cauchy(cauchy_scale) prior on the
+    operator standard deviation, improper flat priors elsewhere (as the README describes the model)."""
+    family = FAM_ANOVA2
+
+    def __init__(self, y, yp, yo, cauchy_scale=20.0):
+        y = np.asarray(y, dtype=np.float64)
+        yp = np.asarray(yp, dtype=np.int64)
+        yo = np.asarray(yo, dtype=np.int64)
+        if not (y.ndim == yp.ndim == yo.ndim == 1 and len(y) == len(yp) == len(yo) and len(y) > 0):
+            raise ValueError("y, yp, yo must be 1-D arrays of equal length")
+        ps, os_ = np.unique(yp), np.unique(yo)
+        P, Oo = len(ps), len(os_)
+        cells = np.zeros((P, Oo))
+        counts = np.zeros((P, Oo), dtype=np.int64)
+        pi, oi = np.searchsorted(ps, yp), np.searchsorted(os_, yo)
+        np.add.at(cells, (pi, oi), y)
+        np.add.at(counts, (pi, oi), 1)
+        R = int(counts[0, 0])
+        if R < 2 or np.any(counts != R) or P < 2 or Oo < 2:
+            raise ValueError("TwoFactorANOVAData needs a balanced design with >= 2 parts, operators and replicates")
+        cm = cells / R
+        gm = cm.mean()
+        pm, om = cm.mean(axis=1), cm.mean(axis=0)
+        ss_p = Oo * R * float(np.sum((pm - gm) ** 2))
+        ss_o = P * R * float(np.sum((om - gm) ** 2))
+        ss_po = R * float(np.sum((cm - pm[:, None] - om[None, :] + gm) ** 2))
+        ss_e = float(np.sum((y - cm[pi, oi]) ** 2))
+        self.P, self.O, self.R, self.cauchy_scale = P, Oo, R, float(cauchy_scale)
+        self._obs = np.array([[ss_p, P - 1.0], [ss_o, Oo - 1.0], [ss_po, (P - 1.0) * (Oo - 1.0)], [ss_e, P * Oo * (R - 1.0)],
+                              [gm, float(P * Oo * R)]])
+
+    def records(self):
+        return self._obs, np.array([float(self.P), float(self.O), float(self.R), self.cauchy_scale])

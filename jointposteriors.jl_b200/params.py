@@ -10,7 +10,7 @@ the per-coordinate transform codes of include/jpcuda.h and gives names to slices
 """
 import numpy as np
 
-T_REAL, T_POSITIVE, T_PROBABILITY, T_NONCENTRED, T_SIMPLEX = 0, 1, 2, 3, 4
+T_REAL, T_POSITIVE, T_PROBABILITY, T_NONCENTRED, T_SIMPLEX, T_COVMAT = 0, 1, 2, 3, 4, 5
 
 
 class _Block:
@@ -75,6 +75,31 @@ class Simplex(_Block):
         return "Simplex(%d)" % self.components
 
 
+class CovarianceMatrix(_Block):
+    """A p x p covariance matrix (ConstrainedParameters CovarianceMatrix, reference src/JointPosteriors.jl:22):
+    p (p + 1) / 2 unconstrained coordinates = the log-Cholesky factor (lower triangle row by row, diagonal on the log scale);
+    constrained = the lower triangle of Sigma = L L' in the same order; log|J| = p log 2 + sum_i (p - i + 1) x_ii.
+    Marginal functions receive the full symmetric p x p matrix (ParamView expands the triangle)."""
+    code = T_COVMAT
+
+    def __init__(self, p):
+        p = int(p)
+        if p < 1 or p > 10:
+            raise ValueError("CovarianceMatrix: 1 <= p <= 10")
+        super().__init__(p * (p + 1) // 2)
+        self.p = p
+
+    def __repr__(self):
+        return "CovarianceMatrix(%d)" % self.p
+
+
+def tril_index(p):
+    """(rows, cols) of the packed lower triangle, row by row: (0,0), (1,0), (1,1), (2,0), .."""
+    r = np.array([i for i in range(p) for j in range(i + 1)])
+    c = np.array([j for i in range(p) for j in range(i + 1)])
+    return r, c
+
+
 class parameter:
     """Base class for the struct API: subclasses list their blocks as class attributes, in order.
 
@@ -95,7 +120,7 @@ def blocks_of(spec):
         spec = (spec,)
     if isinstance(spec, (tuple, list)) and all(isinstance(b, _Block) for b in spec) and len(spec) > 0:
         return [("p%d" % (i + 1), b) for i, b in enumerate(spec)]
-    raise TypeError("model must be a parameter subclass or a tuple of RealVector/PositiveVector/ProbabilityVector/Simplex/NonCentredVector")
+    raise TypeError("model must be a parameter subclass or a tuple of RealVector/PositiveVector/ProbabilityVector/Simplex/CovarianceMatrix/NonCentredVector")
 
 
 def transform_codes(blocks):
@@ -103,6 +128,8 @@ def transform_codes(blocks):
     for _, b in blocks:
         if isinstance(b, Simplex):
             word = T_SIMPLEX | (o << 8) | (b.n << 16)      # JP_T_SIMPLEX_CODE(first, len) of include/jpcuda.h
+        elif isinstance(b, CovarianceMatrix):
+            word = T_COVMAT | (o << 8) | (b.n << 16)       # JP_T_COVMAT_CODE(first, len)
         else:
             word = getattr(b, "code_word", b.code)
         out.append(np.full(b.n, word, dtype=np.int32))
@@ -125,6 +152,12 @@ class ParamView:
             v = theta[o:o + b.n]
             if isinstance(b, Simplex):      # all n components: the implied last one is 1 - sum of the stored ones
                 v = np.concatenate([v, 1.0 - np.sum(v, axis=0, keepdims=True)], axis=0)
+            if isinstance(b, CovarianceMatrix):      # the symmetric p x p matrix (x nodes) from its stored lower triangle
+                r, c = tril_index(b.p)
+                full = np.zeros((b.p, b.p) + v.shape[1:], dtype=v.dtype)
+                full[r, c] = v
+                full[c, r] = v
+                v = full
             setattr(self, name, v)
             self._names.append(name)
             self.blocks.append(v)
@@ -164,6 +197,12 @@ def probe_coordinate(f, blocks):
             v[i] = _Tracer(o + i)
         if isinstance(b, Simplex):
             v[b.n] = _Tracer(None)      # the implied last component is not a stored coordinate
+        if isinstance(b, CovarianceMatrix):      # Sigma[i, j] and Sigma[j, i] are the same stored coordinate
+            r, c = tril_index(b.p)
+            full = np.empty((b.p, b.p), dtype=object)
+            full[r, c] = v
+            full[c, r] = v
+            v = full
         setattr(view, name, v)
         view._names.append(name)
         view.blocks.append(v)

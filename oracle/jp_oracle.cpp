@@ -432,9 +432,41 @@ static inline double transform_one(int code, double x, double* lj) {
 //        exported at reference src/JointPosteriors.jl:26; its map lives in the absent ConstrainedParameters, so the
 //        additive log-ratio map is used): theta_k = e^{x_k} / (1 + sum e^{x_j}), implied last component
 //        1 / (1 + sum e^{x_j}), log|J| = sum of the logs of all n components.
+// code 5 (kind, first coordinate in bits 8-15, length p (p + 1) / 2 in bits 16-23): CovarianceMatrix block (exported at
+//        reference src/JointPosteriors.jl:22; map in the absent ConstrainedParameters, so the log-Cholesky map is used --
+//        parity unpinned upstream, pinned here on the closed-form inverse-Wishart posterior): the block holds the lower
+//        triangle row by row, (0,0), (1,0), (1,1), (2,0), ..; L_ii = exp(x_ii), L_ij = x_ij (i > j), Sigma = L L',
+//        theta = the lower triangle of Sigma in the same order, log|J| = p log 2 + sum_i (p - i + 1) x_ii (i = 0 .. p-1).
+static void transform_covmat(const double* x, int len, double* theta, double* lj) {
+  int p = 0;
+  while ((p + 1) * (p + 2) / 2 <= len) ++p;
+  std::vector<double> L((size_t)p * p, 0.0);
+  for (int i = 0, e = 0; i < p; ++i)
+    for (int j = 0; j <= i; ++j, ++e) {
+      if (i == j) {
+        L[(size_t)i * p + j] = std::exp(x[e]);
+        *lj += (p - i + 1) * x[e];
+      } else {
+        L[(size_t)i * p + j] = x[e];
+      }
+    }
+  *lj += p * std::log(2.0);
+  for (int i = 0, e = 0; i < p; ++i)
+    for (int j = 0; j <= i; ++j, ++e) {
+      double v = 0;
+      for (int k = 0; k <= j; ++k) v += L[(size_t)i * p + k] * L[(size_t)j * p + k];
+      theta[e] = v;
+    }
+}
+
 void orc_transform(const int* code, int d, const double* x, double* theta, double* logjac) {
   double lj = 0;
   for (int k = 0; k < d; ++k) {
+    if ((code[k] & 0xFF) == 5) {
+      int first = (code[k] >> 8) & 0xFF, len = (code[k] >> 16) & 0xFF;
+      if (k == first) transform_covmat(x + first, len, theta + first, &lj);
+      continue;
+    }
     if ((code[k] & 0xFF) == 4) {
       int first = (code[k] >> 8) & 0xFF, len = (code[k] >> 16) & 0xFF;
       if (k != first) continue;                 // the whole block is transformed at its head
@@ -563,6 +595,68 @@ static double ld_multinomial(const double* t, int d, const double* obs, long lon
   return lp;
 }
 
+// family 6: zero-mean multivariate normal with unknown covariance on a CovarianceMatrix block, inverse-Wishart(nu0, psi0 I)
+// prior (lpdf_InverseWishart is among the reference's exports, src/JointPosteriors.jl:36).  theta = lower triangle of Sigma
+// (p (p + 1) / 2 entries, row by row); obs = the p rows of the scatter matrix S = sum_i y_i y_i' (sufficient statistic);
+// hyper = (n_obs, nu0, psi0).  log p(Sigma | y) = -(n + nu0 + p + 1) / 2 log|Sigma| - 1/2 tr((S + psi0 I) Sigma^-1) + const,
+// i.e. Sigma | y ~ inverse-Wishart(nu0 + n, S + psi0 I) in closed form: the analytic anchor of the transform.
+static double ld_mvn_cov(const double* t, int d, const double* obs, long long N, const double* h) {
+  const int p = (int)N;
+  std::vector<double> C((size_t)p * p, 0.0), Inv((size_t)p * p, 0.0);
+  for (int i = 0, e = 0; i < p; ++i)      // Cholesky of Sigma from its packed lower triangle
+    for (int j = 0; j <= i; ++j, ++e) {
+      double v = t[e];
+      for (int k = 0; k < j; ++k) v -= C[(size_t)i * p + k] * C[(size_t)j * p + k];
+      C[(size_t)i * p + j] = (i == j) ? std::sqrt(v) : v / C[(size_t)j * p + j];
+    }
+  double logdet = 0;
+  for (int i = 0; i < p; ++i) logdet += 2.0 * std::log(C[(size_t)i * p + i]);
+  // Sigma^-1 = C^-T C^-1: invert the triangular factor column by column
+  std::vector<double> Ci((size_t)p * p, 0.0);
+  for (int c = 0; c < p; ++c) {
+    Ci[(size_t)c * p + c] = 1.0 / C[(size_t)c * p + c];
+    for (int i = c + 1; i < p; ++i) {
+      double v = 0;
+      for (int k = c; k < i; ++k) v -= C[(size_t)i * p + k] * Ci[(size_t)k * p + c];
+      Ci[(size_t)i * p + c] = v / C[(size_t)i * p + i];
+    }
+  }
+  for (int i = 0; i < p; ++i)
+    for (int j = 0; j < p; ++j) {
+      double v = 0;
+      for (int k = std::max(i, j); k < p; ++k) v += Ci[(size_t)k * p + i] * Ci[(size_t)k * p + j];
+      Inv[(size_t)i * p + j] = v;
+    }
+  double lp = -0.5 * (h[0] + h[1] + p + 1) * logdet;
+  for (int n = 0; n < p; ++n) {
+    double row = 0;
+    for (int j = 0; j < p; ++j) row += Inv[(size_t)n * p + j] * (obs[(size_t)n * p + j] + (j == n ? h[2] : 0.0));
+    lp += -0.5 * row;
+  }
+  (void)d;
+  return lp;
+}
+
+// family 7: balanced two-factor random-effects ANOVA (the model of README Example 3, reference README.md:416-470: parts x
+// operators x replicates, `TF_RE_ANOVA` of the absent LogDensities package; marginal likelihood with the random effects
+// integrated out).  theta = (mu, s2_P, s2_O, s2_PO, s2_R); obs rows (SS_k, df_k) for k = parts, operators, interaction, error
+// and a fifth row (grand mean, P O R); hyper = (P, O, R, scale of the folded-Cauchy prior on the operator standard deviation;
+// improper flat priors elsewhere, as the README states).  The four sums of squares are independent lambda_k chi2(df_k) with
+// the expected mean squares lambda_P = s2_R + R s2_PO + O R s2_P, lambda_O = s2_R + R s2_PO + P R s2_O,
+// lambda_PO = s2_R + R s2_PO, lambda_E = s2_R, and the grand mean is N(mu, (lambda_P + lambda_O - lambda_PO) / (P O R)).
+static double ld_anova2(const double* t, int d, const double* obs, long long N, const double* h) {
+  const double P = h[0], Oo = h[1], R = h[2];
+  const double lam[4] = {t[4] + R * t[3] + Oo * R * t[1], t[4] + R * t[3] + P * R * t[2], t[4] + R * t[3], t[4]};
+  double lp = 0;
+  for (int k = 0; k < 4; ++k) lp += -0.5 * obs[2 * k + 1] * std::log(lam[k]) - 0.5 * obs[2 * k] / lam[k];
+  const double vm = (lam[0] + lam[1] - lam[2]) / obs[9];
+  lp += -0.5 * std::log(vm) - 0.5 * (obs[8] - t[0]) * (obs[8] - t[0]) / vm;
+  const double so = std::sqrt(t[2]) / h[3];
+  lp += -std::log1p(so * so) - 0.5 * std::log(t[2]);      // folded Cauchy on the sd, expressed on the variance scale
+  (void)d; (void)N;
+  return lp;
+}
+
 // orc_set_precise(1): the observation sums of the two GLM families are accumulated in 80-bit long double.  The default (0) is
 // the plain double loop a user's Julia log_density method runs -- that is what bench.py times -- but from N ~ 1e5 its own
 // rounding error (~1e-9 (N / 1e5)^1.5) exceeds the 1e-10 the FP64 CUDA path is held to, so the tests switch this on.
@@ -578,6 +672,8 @@ double orc_log_density(int family, const double* theta, int d, const double* obs
     case 3: return ld_hier(theta, d, obs, N, hyper);
     case 4: return ld_linreg(theta, d, obs, N, hyper);
     case 5: return ld_multinomial(theta, d, obs, N, hyper);
+    case 6: return ld_mvn_cov(theta, d, obs, N, hyper);
+    case 7: return ld_anova2(theta, d, obs, N, hyper);
   }
   return NAN;
 }

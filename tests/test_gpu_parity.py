@@ -79,6 +79,10 @@ def _family_cases():
     yield "linreg", 4, [0, 0, 0, 1], np.column_stack([X, yv]), np.array([10.0, 1.0])
     sx = 4 | (0 << 8) | (3 << 16)     # JP_T_SIMPLEX_CODE(first = 0, len = 3): a point of the 4-simplex
     yield "multinomial", 5, [sx] * 3, np.array([[12.0], [7.0], [3.0], [18.0]]), np.array([0.0])
+    cv = 5 | (0 << 8) | (3 << 16)     # JP_T_COVMAT_CODE(first = 0, len = 3): a 2 x 2 covariance matrix
+    Y = np.random.default_rng(3).multivariate_normal(np.zeros(2), [[2.0, 0.6], [0.6, 0.5]], size=40)
+    yield "mvncov", 6, [cv] * 3, np.ascontiguousarray(Y.T @ Y), np.array([40.0, 4.0, 1.0])
+    yield "anova2", 7, [0, 1, 1, 1, 1], np.array([[310.0, 3.0], [9.5, 2.0], [2.1, 6.0], [1.3, 12.0], [15.2, 24.0]]), np.array([4.0, 3.0, 2.0, 20.0])
 
 
 FAMILY_CASES = list(_family_cases())
@@ -98,6 +102,11 @@ def _model_for(jp, code):
     blocks = []
     if code and all(c & 0xFF == 4 for c in code):
         return jp.Model((jp.Simplex(len(code) + 1),))
+    if code and all(c & 0xFF == 5 for c in code):
+        p = 0
+        while (p + 1) * (p + 2) // 2 <= len(code):
+            p += 1
+        return jp.Model((jp.CovarianceMatrix(p),))
     for c in code:
         if c & 0xFF == 3:
             blocks.append(jp.NonCentredVector(1, loc=(c >> 8) & 0xFF, scale=(c >> 16) & 0xFF))
@@ -131,7 +140,7 @@ def _cpu_mode_for(O, family, code, obs, hyper):
     if family in (1, 2):
         beta, H, ll = O.glm_mode(family, obs, hyper, d)
         return beta, H, -ll
-    x0 = {0: [0.2, -3.0, -2.0], 3: [4.0, 1.0] + [0.0] * 8, 4: [0.0] * d, 5: [0.0] * d}[family]
+    x0 = {0: [0.2, -3.0, -2.0], 3: [4.0, 1.0] + [0.0] * 8, 4: [0.0] * d, 5: [0.0] * d, 6: [0.0] * d, 7: [15.0, 3.0, 0.5, -1.0, -2.0]}[family]
     return cpu_mode(O, family, code, obs, hyper, x0)
 
 
@@ -195,6 +204,34 @@ def test_cfg2_eight_schools(jp, O, gpu_ctx):
 def test_small_regressions_fp64(jp, O, gpu_ctx, case):
     name, family, code, obs, hyper = FAMILY_CASES[case]
     _check_fit_and_marginals(jp, O, gpu_ctx, family, code, obs, hyper, 0, 4)
+
+
+@pytest.mark.parametrize("case", [6, 7], ids=["mvncov", "anova2"])
+def test_covariance_matrix_and_anova_families(jp, O, gpu_ctx, case):
+    """CovarianceMatrix transform (north star stage 2; reference src/JointPosteriors.jl:22) through the fused node kernel and
+    the two families that use the new blocks, end to end against the oracle; the multivariate normal / inverse-Wishart model
+    also against its closed-form posterior mean, the ANOVA model (README Example 3) through the README's own marginal
+    function rGT (a host closure over the variance components)."""
+    name, family, code, obs, hyper = FAMILY_CASES[case]
+    post, ref = _check_fit_and_marginals(jp, O, gpu_ctx, family, code, obs, hyper, 0, 6 if case == 6 else 5)
+    if case == 6:
+        n, nu0, psi0 = hyper
+        mean = (obs + psi0 * np.eye(2)) / (nu0 + n - 2 - 1)
+        ms = jp.marginals(post, [lambda t: t[0, 0], lambda t: t[1, 0], lambda t: t[0, 1], lambda t: t[1, 1],
+                                 lambda t: t[1, 0] / np.sqrt(t[0, 0] * t[1, 1])])
+        assert abs(ms[0].mu - mean[0, 0]) < 2e-3 * mean[0, 0] and abs(ms[3].mu - mean[1, 1]) < 2e-3 * mean[1, 1]
+        assert abs(ms[1].mu - mean[1, 0]) < 2e-3 * abs(mean[1, 0]) and ms[1].mu == ms[2].mu     # Sigma[1,0] and Sigma[0,1]: one coordinate
+        assert -1 < ms[4].itp.values[0] and ms[4].itp.values[-1] < 1                               # correlation (host closure)
+    else:
+        def rGT(t):      # reference README.md:447-451
+            g = t.p3[0] + t.p4[0] + t.p5[0]
+            return np.sqrt(g / (g + t.p2[0]))
+        m = jp.marginal(post, rGT)
+        th = ref["theta"]
+        g = th[2] + th[3] + th[4]
+        mo = O.marginal(np.sqrt(g / (g + th[1])), ref["density"])
+        assert abs(m.mu - mo["mu"]) < 1e-10 and abs(m.sigma - mo["sigma"]) < 1e-9
+        assert 0 < m.mu < 1 and "Marginal parameter" in repr(m)
 
 
 def test_simplex_block_against_dirichlet(jp, O, gpu_ctx):

@@ -389,6 +389,83 @@ def test_simplex_transform_dirichlet_truth(O):
     assert errs[1][0] < 5e-5 and errs[1][1] < 1e-4
 
 
+def test_covariance_matrix_transform_inverse_wishart_truth(O):
+    """CovarianceMatrix block (log-Cholesky map): the log-Jacobian against finite differences of the map, and -- zero-mean
+    multivariate normal data with an inverse-Wishart prior -- the closed-form inverse-Wishart posterior: the sparse-grid
+    marginals of the entries of Sigma converge to (S + psi0 I) / (nu0 + n - p - 1) and to the analytic variances."""
+    from conftest import cpu_mode
+    p = 2
+    code = np.array([5 | (0 << 8) | (3 << 16)] * 3, dtype=np.int32)
+    x0 = np.array([0.3, -0.7, 0.2])
+    th, lj = O.transform(code, x0)
+    L = np.array([[np.exp(x0[0]), 0.0], [x0[1], np.exp(x0[2])]])
+    Sg = L @ L.T
+    assert np.allclose(th, [Sg[0, 0], Sg[1, 0], Sg[1, 1]], rtol=1e-15)
+    J = np.zeros((3, 3))
+    for k in range(3):
+        e = np.zeros(3); e[k] = 1e-6
+        J[:, k] = (O.transform(code, x0 + e)[0] - O.transform(code, x0 - e)[0]) / 2e-6
+    assert np.isclose(lj, np.log(abs(np.linalg.det(J))), rtol=1e-8)
+    rng = np.random.default_rng(3)
+    n, nu0, psi0 = 40, 4.0, 1.0
+    Y = rng.multivariate_normal(np.zeros(p), [[2.0, 0.6], [0.6, 0.5]], size=n)
+    S = Y.T @ Y
+    obs, hyper = np.ascontiguousarray(S), np.array([float(n), nu0, psi0])
+    # the family's density against the inverse-Wishart log-density written out with numpy
+    Psi, nu = S + psi0 * np.eye(p), nu0 + n
+    lp = lambda M: -0.5 * (nu + p + 1) * np.linalg.slogdet(M)[1] - 0.5 * np.trace(Psi @ np.linalg.inv(M))
+    A = np.array([[1.7, 0.3], [0.3, 0.9]])
+    B = np.array([[2.5, -0.4], [-0.4, 0.6]])
+    tri = lambda M: np.array([M[0, 0], M[1, 0], M[1, 1]])
+    assert np.isclose(O.log_density(6, tri(A), obs, hyper) - O.log_density(6, tri(B), obs, hyper), lp(A) - lp(B), rtol=1e-12)
+    x, H, f = cpu_mode(O, 6, code, obs, hyper, np.zeros(3))
+    U = O.inv_chol(2 * H)
+    mean = Psi / (nu - p - 1)
+    # Var(Sigma_ii) = 2 Psi_ii^2 / ((nu - p - 1)^2 (nu - p - 3)) for an inverse-Wishart
+    sd_diag = np.sqrt(2 * np.diag(Psi) ** 2 / ((nu - p - 1) ** 2 * (nu - p - 3)))
+    errs = []
+    for Lv in (5, 7):
+        idx, w = O.smolyak(0, 3, Lv)
+        ref = O.eval_grid(0, 6, code, idx, w, x, U, f, obs, hyper)
+        t = ref["theta"]
+        ms = [O.marginal(t[k], ref["density"]) for k in range(3)]
+        errs.append((max(abs(ms[0]["mu"] - mean[0, 0]) / mean[0, 0], abs(ms[1]["mu"] - mean[1, 0]) / abs(mean[1, 0]),
+                         abs(ms[2]["mu"] - mean[1, 1]) / mean[1, 1]),
+                     max(abs(ms[0]["sigma"] - sd_diag[0]) / sd_diag[0], abs(ms[2]["sigma"] - sd_diag[1]) / sd_diag[1])))
+    assert errs[0][0] < 5e-3 and errs[0][1] < 3e-2, errs
+    assert errs[1][0] < 2e-4 and errs[1][1] < 2e-3, errs
+
+
+def test_anova_sufficient_statistics_against_full_likelihood(O):
+    """Family 7 (balanced two-factor random-effects ANOVA, README Example 3): the marginal likelihood written on the four sums
+    of squares and the grand mean equals -- up to a parameter-free constant -- the multivariate normal density of all the
+    observations with the random effects integrated out, V = s2_P Z_P Z_P' + s2_O Z_O Z_O' + s2_PO Z_PO Z_PO' + s2_R I."""
+    import __graft_entry__ as entry
+    jp = entry.load_package()
+    rng = np.random.default_rng(12)
+    P, Oo, R = 4, 3, 2
+    yp = np.repeat(np.arange(P), Oo * R)
+    yo = np.tile(np.repeat(np.arange(Oo), R), P)
+    y = 15 + rng.normal(0, 3, P)[yp] + rng.normal(0, 0.8, Oo)[yo] + rng.normal(0, 0.5, (P, Oo))[yp, yo] + rng.normal(0, 0.3, P * Oo * R)
+    data = jp.TwoFactorANOVAData(y, yp + 1, yo + 1, cauchy_scale=20.0)
+    obs, hyper = data.records()
+    n = len(y)
+    Zp = (yp[:, None] == np.arange(P)[None]).astype(float)
+    Zo = (yo[:, None] == np.arange(Oo)[None]).astype(float)
+    cell = yp * Oo + yo
+    Zc = (cell[:, None] == np.arange(P * Oo)[None]).astype(float)
+
+    def full(th):
+        mu, vP, vO, vPO, vR = th
+        V = vP * Zp @ Zp.T + vO * Zo @ Zo.T + vPO * Zc @ Zc.T + vR * np.eye(n)
+        r = y - mu
+        prior = -np.log1p(vO / 20.0 ** 2) - 0.5 * np.log(vO)
+        return -0.5 * np.linalg.slogdet(V)[1] - 0.5 * r @ np.linalg.solve(V, r) + prior
+    a = np.array([14.0, 8.0, 0.7, 0.2, 0.1])
+    b = np.array([16.5, 3.0, 1.9, 0.6, 0.05])
+    assert np.isclose(O.log_density(7, a, obs, hyper) - O.log_density(7, b, obs, hyper), full(a) - full(b), rtol=1e-10)
+
+
 def test_marginal_buffer_restatement(O):
     """orc_marginal_buffer (update_MarginalBuffer! / Vandermonde!, reference src/marginal_posterior.jl:10-67) against numpy:
     stable sort with ties, sequential cumulative weights, powers of the standardised value."""

@@ -20,13 +20,24 @@ wl = workloads.cfg3_logistic(N=100_000 * world) if name == "cfg3" else workloads
 ctx = Context.get(lr)
 ctx.use_stream(torch.cuda.current_stream(dev).cuda_stream)
 M = jp.Model(wl["params"], device=lr)
-dd = ctx.upload(wl["data"])
-x, U, neg_min = jp.mode(M, dd)
-grid = ctx.grid(0, U.shape[1], wl["level"])
-Mtot = int(jp.lib().jp_grid_size(grid))
-post = JointPosterior(M, dd, grid, x, U, neg_min, node_range=D.shard_bounds(Mtot, rank, world))
-loc = D.CudaLocal(post)
+obs_mode = os.environ.get("SHARD", "nodes") == "obs"
 coords = list(range(wl["d"]))
+if obs_mode:
+    from jointposteriors_jl_b200.model import DeviceData
+    N = wl["data"].records()[0].shape[0]
+    dd = DeviceData(ctx, wl["data"], rows=D.row_slice(N, rank, world)[:2])
+    comm = D.comm_for(ctx, 0, None, min_bulk=1 << 24)
+    x, U, neg_min = D.mode_p2p(M, dd, comm)
+    grid = ctx.grid(0, U.shape[1], wl["level"])
+    post = JointPosterior(M, dd, grid, x, U, neg_min)
+    sp = D.ObsShardedPosterior(post, comm, None)
+else:
+    dd = ctx.upload(wl["data"])
+    x, U, neg_min = jp.mode(M, dd)
+    grid = ctx.grid(0, U.shape[1], wl["level"])
+    Mtot = int(jp.lib().jp_grid_size(grid))
+    post = JointPosterior(M, dd, grid, x, U, neg_min, node_range=D.shard_bounds(Mtot, rank, world))
+    loc = D.CudaLocal(post)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 tok = torch.zeros(1, device=dev)
 for it in range(6):
@@ -34,12 +45,16 @@ for it in range(6):
     dist.all_reduce(tok)
     torch.cuda.synchronize()
     ctx.trace(True)
-    D.fit_sharded(loc)
-    D.marginals_sharded(loc, coords)
+    if obs_mode:
+        sp.refit()
+        sp.marginals(coords)
+    else:
+        D.fit_sharded(loc)
+        D.marginals_sharded(loc, coords)
     tr = ctx.trace_dump()
     ctx.trace(False)
 if rank == 0:
-    print("%s on %d ranks, rank 0: last of 6 steps (L2 flushed before each), prep %s" % (name, world, loc.last_prep))
+    print("%s on %d ranks, rank 0: last of 6 steps (L2 flushed before each), prep %s" % (name, world, "observation-sharded-p2p" if obs_mode else loc.last_prep))
     for nm, us in tr:
         print("  %-30s %9.1f us" % (nm, us))
 dist.barrier()
