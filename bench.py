@@ -681,16 +681,21 @@ def run_product(args):
             api["published_source"] = "reference README.md:223-234 (BenchmarkTools median, fit + 3 marginals, unstated CPU)"
         # marginal(jp, f, Normal): the smooth CDF of coordinate 0 (sort + design matrix + BFGS, one launch per evaluation)
         pa = jp.fit(M, hdata, wl["level"], path=path)
-        jp.marginal(pa, 0, jp.Normal, max_iter=50)
+        jp.marginal(pa, 1, jp.Normal, max_iter=5)        # warm the kernels on another coordinate
         t0 = time.perf_counter()
-        ms_ = jp.marginal(pa, 0, jp.Normal)
+        ms_ = jp.marginal(pa, 0, jp.Normal)               # first call for this function: sort + design matrix + fit
         t_sm = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        ms2 = jp.marginal(pa, 0, jp.Normal)               # again: the design kept on the device is reused (M.MarginalBuffers)
+        t_sm2 = (time.perf_counter() - t0) * 1e3
         pa.free()
         info = ms_.itp.info
-        api["smooth_cdf_marginal"] = dict(ms=t_sm, iterations=info["iterations"], evaluations=info["evaluations"],
+        api["smooth_cdf_marginal"] = dict(ms=t_sm, ms_repeat=t_sm2, buffer_reused=bool(ms2.buffer_reused), iterations=info["iterations"],
+                                          evaluations=info["evaluations"], grad_inf_norm=info["grad_inf_norm"],
                                           us_per_evaluation=t_sm * 1e3 / max(1, info["evaluations"]), converged=info["converged"],
-                                          what="marginal(jp, f, Normal) of coordinate 0: stable sort, 10 x M design matrix, "
-                                               "BFGS (<= 1000 iterations) with every objective/score evaluation one launch over all nodes")
+                                          criterion=info["criterion"],
+                                          what="marginal(jp, f, Normal) of coordinate 0: stable sort, 10 x M design matrix, damped Newton on "
+                                               "the 9 parameters (score at phi and its 9 forward-difference neighbours = ONE launch over all nodes)")
     # ---- north_star's multi-GPU configurations at fixed size on these `world` ranks (strong scaling), beside the headline
     strong = None
     diag = post.diagnostics

@@ -409,12 +409,23 @@ typedef struct jp_smooth_cdf {
   int iterations, evaluations, converged;
 } jp_smooth_cdf;
 /* NestedPolyGLM(m, Normal(mu, sigma)) for marginal k of the last jp_marginal_coords / _values call on an UNSHARDED
- * posterior: sort + design matrix on the device (as jp_marginal_buffer), then BFGS with a backtracking line search
- * (src/interp.jl:380) where every evaluation of the objective and its score (ntl_likelihood! / ntscore!,
- * src/interp.jl:81-111) is one kernel launch over all M nodes.  phi_init: 9 starting values or NULL (zeros; the
- * reference's MarginalBuffer.init is in the absent LogDensities package); max_iter 0 = 1000 and g_tol 0 = 1e-8 (Optim's
- * defaults).  Stopping at the iteration cap is not an error (converged = 0).  Blocking. */
+ * posterior: sort + design matrix on the device (as jp_marginal_buffer), then the minimisation of ntl_likelihood!
+ * (src/interp.jl:81-111): a short BFGS phase with a backtracking line search (the optimiser the reference asks of Optim,
+ * :380; one kernel launch over all M nodes per objective / score evaluation) followed by a saddle-free trust-region Newton
+ * iteration whose Hessian comes from ONE batched launch (the score at phi and at its nine forward-difference neighbours).
+ * phi_init: 9 starting values or NULL (zeros; the reference's MarginalBuffer.init is in the absent LogDensities package);
+ * max_iter 0 = 300 iterations in all, g_tol 0 = 1e-8 (Optim's default).  converged: 1 = the score's infinity norm is below
+ * g_tol; 2 = the decrease a full Newton step predicts is below 1e-8 max(1, |objective|) (the objective's curvatures span ten
+ * orders of magnitude, the infinity norm of the score does not reach 1e-8 with any optimiser); 0 = stopped at
+ * the iteration cap (not an error).  JP_SMOOTH_BFGS=1 in the environment: BFGS only, max_iter 0 = 1000.  Blocking. */
 int jp_marginal_smooth(jp_posterior* post, int k, const double* phi_init, int max_iter, double g_tol, jp_smooth_cdf* out);
+/* The same with the per-function buffer cache of the reference (`get!(() -> MarginalBuffer(n), M.MarginalBuffers, f)`,
+ * src/marginal_posterior.jl:10,71): `key` names the marginal function (the host keeps one key per f); the sorted design matrix
+ * and cumulative weights built for a key since the last fit of `post` are kept on the device (up to 4 functions) and a
+ * repeated call reuses them -- no sort, no Vandermonde pass (*cache_hit = 1).  k < 0 only looks the key up: on a miss nothing
+ * is computed and *cache_hit = 0; k >= 0 names the marginal of the last jp_marginal_* call that provides the values. */
+int jp_marginal_smooth_keyed(jp_posterior* post, int k, long long key, const double* phi_init, int max_iter, double g_tol,
+                             jp_smooth_cdf* out, int* cache_hit);
 /* ntl_likelihood! and ntscore! at a given phi (src/interp.jl:81-111) for marginal k; grad9 / beta10 / theta7 may be NULL. */
 int jp_smooth_objective(jp_posterior* post, int k, const double* phi, double* f, double* grad9, double* beta10,
                         double* theta7);

@@ -78,7 +78,7 @@ SYMBOLS = [
     "jp_marginal_local_moments", "jp_marginal_local_knots", "jp_marginal_local_knots_gathered",
     "jp_marginal_combine_gathered",
     "jp_quantile", "jp_cdf",
-    "jp_marginal_smooth", "jp_smooth_objective", "jp_smooth_cdf_eval", "jp_smooth_pdf_eval", "jp_smooth_quantile_eval",
+    "jp_marginal_smooth", "jp_marginal_smooth_keyed", "jp_smooth_objective", "jp_smooth_cdf_eval", "jp_smooth_pdf_eval", "jp_smooth_quantile_eval",
 ]
 
 

@@ -315,6 +315,7 @@ int jp_posterior_free(jp_posterior* p) {
   jp_dfree(c, p->d_vals); jp_dfree(c, p->d_bins); jp_dfree(c, (void*)p->d_vptr); jp_dfree(c, p->d_perm_a); jp_dfree(c, p->d_perm_b); jp_dfree(c, p->d_hist);
   jp_dfree(c, p->d_sv); jp_dfree(c, p->d_sw); jp_dfree(c, p->d_cw); jp_dfree(c, p->d_mout);
   jp_dfree(c, p->d_cmom); jp_dfree(c, p->d_coords); jp_dfree(c, p->d_cand);
+  for (auto& e : p->design_cache) { jp_dfree(c, e.d_V); jp_dfree(c, e.d_cw); }
   delete p;
   return JP_OK;
 }

@@ -169,6 +169,16 @@ struct JpFinish {
   double neg_min = 0;
 };
 
+// one cached smooth-CDF design (jp_marginal_smooth_keyed): sorted design matrix and cumulative weights of one marginal function
+struct JpDesignCache {
+  long long key, gen;
+  double* d_V;
+  double* d_cw;
+  double mu, sigma;
+  long long stamp;
+};
+#define JP_DESIGN_CACHE 4
+
 struct jp_posterior {
   jp_ctx* ctx = nullptr;
   const jp_grid* grid = nullptr;
@@ -177,6 +187,9 @@ struct jp_posterior {
   long long m0 = 0, m1 = 0, M = 0;   // shard [m0, m1), M = m1 - m0
   int path_used = 0;
   std::vector<int> tcode_host;   // transform codes of the last fit (host copy)
+  long long fit_gen = 0;         // counts the fits of this posterior: what was derived from an earlier fit is stale
+  long long cache_clock = 0;
+  std::vector<JpDesignCache> design_cache;
   bool raw = false;              // RawBuild: d_theta holds the UNCONSTRAINED node coordinates (the reference's grid.cache)
   JpFinish fin;                  // pending finish of the last log-density launch (consumed by jp_stage4_launch)
   double* d_theta = nullptr;     // SoA constrained parameters [d][M]

@@ -561,6 +561,7 @@ int jp_fit_check_args(const jp_posterior* post, const jp_fit_args* args) {
   JP_REQUIRE(args->h_transform && args->h_mu_hat && args->h_U, "jp_fit: null host array");
   JP_TRY(jp_check_transform_codes("jp_fit", args->h_transform, args->d));
   const_cast<jp_posterior*>(post)->raw = args->raw != 0;
+  const_cast<jp_posterior*>(post)->fit_gen += 1;
   return JP_OK;
 }
 

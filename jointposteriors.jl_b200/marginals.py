@@ -87,7 +87,8 @@ class NestedPolyGLM:
         self.β, self.θ = self.beta, self.theta
         self.mu, self.sigma = c.mu, c.sigma
         self.info = dict(objective=c.objective, grad_inf_norm=c.grad_inf_norm, iterations=c.iterations,
-                         evaluations=c.evaluations, converged=bool(c.converged))
+                         evaluations=c.evaluations, converged=bool(c.converged),
+                         criterion={0: None, 1: "g_tol", 2: "newton_decrement"}.get(int(c.converged)))
 
     def _call(self, fn, x):
         if np.ndim(x) > 0:
@@ -204,14 +205,24 @@ def marginal_smooth(jp, f, init=None, max_iter=0, g_tol=0.0):
     """marginal(jp, f, Normal): update_MarginalBuffer! then NestedPolyGLM(m, Normal(mu, sigma)) (reference
     src/marginal_posterior.jl:10-16,124-129; src/interp.jl:377-384), both in the library: the sort, cumulative weights,
     design matrix and every objective / score evaluation of the BFGS iteration run on the GPU over all nodes."""
-    m = marginals(jp, [f])[0]                 # moments + value pointers of f on the device
     c = SmoothCDF()
     x0 = None if init is None else f64(init)
     if x0 is not None and x0.shape != (9,):
         raise ValueError("init: 9 unconstrained parameters expected")
-    check(lib().jp_marginal_smooth(jp.handle, C.c_int(0), ptr(x0), C.c_int(int(max_iter)), C.c_double(float(g_tol)),
-                                   C.byref(c)))
-    return marginal_result(jp, 0, c.mu, c.sigma, NestedPolyGLM(c))
+    # M.MarginalBuffers: one entry per marginal function, as `get!(..., jp.M.MarginalBuffers, f)` of the reference
+    # (src/marginal_posterior.jl:10,71); the entry is the key under which the library keeps f's sorted design on the device
+    table = jp.M.__dict__.setdefault("MarginalBuffers", {})
+    fk = ("coord", int(f)) if isinstance(f, (int, np.integer)) else f
+    key = table.setdefault(fk, len(table) + 1)
+    hit = C.c_int(0)
+    args = (ptr(x0), C.c_int(int(max_iter)), C.c_double(float(g_tol)), C.byref(c), C.byref(hit))
+    check(lib().jp_marginal_smooth_keyed(jp.handle, C.c_int(-1), C.c_longlong(key), *args))      # a design kept since the last fit?
+    if not hit.value:
+        marginals(jp, [f])                        # moments + value pointers of f on the device
+        check(lib().jp_marginal_smooth_keyed(jp.handle, C.c_int(0), C.c_longlong(key), *args))
+    res = marginal_result(jp if not hit.value else None, 0, c.mu, c.sigma, NestedPolyGLM(c))
+    res.buffer_reused = bool(hit.value)
+    return res
 
 
 def marginal(jp, f, kind=Grid, **kw):
