@@ -522,7 +522,7 @@ def run_product(args):
         roof = dict(bound="tensor", achieved=flops / (kms * 1e-3) / 1e12, peak=tf32_peak, unit="TFLOP/s",
                     frac=flops / (kms * 1e-3) / 1e12 / tf32_peak, traffic=None,
                     note="algorithmic 2*d flops per pair (issued 3xTF32 on K padded to 32: %dx more); peak = measured bf16/2 "
-                         "(TF32 dense is half the bf16 rate), %s; the kernel is bound by its FP32 epilogue (issue slots) and the TMEM read rate, "
+                         "(TF32 dense is half the bf16 rate), %s; the kernel is bound by the FMA pipe of its FP32 series epilogue, "
                          "see the epilogue / tile_model objects and DESIGN.md" % (
                              int(round(3 * 32 * ((d * 3 + 31) // 32) / (3.0 * d))), peaks["source"]))
     else:
@@ -541,22 +541,24 @@ def run_product(args):
                                 note="the kernel's true limiter: (NC + 3) / 2 = %.1f FP32 FMA-pipe instructions per (node, observation) "
                                      "pair (even / odd split of the link remainder series shared by a mirror pair of grid nodes) "
                                      "against 148 SMs x 128 lanes x SM clock" % ops)
-        # Per tile (128 observations x 96 mirror pairs) and SM: the epilogue reads the 48 KB accumulator out of TMEM
-        # (tcgen05.ld: 64 B / cycle / SM in /opt/skills/guides/B300_MICROARCH.md -> 768 cycles), issues 112 packed FP32
-        # operations per warp on 3 warps per sub-partition (2 cycles each on the FMA pipe -> 672 cycles at NC = 4), and the
-        # MMA occupies the tensor pipe for 48 cycles per K = 8 instruction (128 x 96 / 256, same guide), 4 per 128-byte K
-        # atom product.  The three resources overlap, so the floor of a tile is their maximum.
+        # Per tile (128 observations x 96 mirror pairs) and SM the epilogue (3 warps per sub-partition) issues 16 (NC + 3) packed
+        # FP32 operations per warp, 2 FMA-pipe cycles each (measured: tools/ubench/ffma2.cu, profiles/r01_ubench_ffma2.txt) ->
+        # 672 cycles at NC = 4; it reads the 48 KB accumulator out of TMEM, measured on B200 at 320-430 B / cycle / SM with 12
+        # warps (tools/ubench/tmem_ld.cu, profiles/r02_ubench_tmem_ld.txt; x8 loads, 4 in flight: 357) -> ~140 cycles; the MMA
+        # occupies the tensor pipe for 48 cycles per K = 8 instruction (128 x 96 / 256), 4 per 128-byte K atom product.  The
+        # three resources overlap, so the floor of a tile is their maximum: the FMA pipe.
         atoms = 1 if 3 * d <= 32 else (2 if 3 * d <= 64 else 3)
         tiles_per_sm = np.ceil(n_local_obs / 128.0) * np.ceil(((e - b + 1) // 2 + 1) / 96.0) / 148.0
         cyc = kms * 1e-3 * clk * 1e6 / tiles_per_sm
         fma_cyc = 3 * 2 * 16 * (nc + 3)
-        floor = max(768.0, 192.0 * atoms, float(fma_cyc))
-        roof["tile_model"] = dict(cycles_per_tile=cyc, tmem_read_cycles=768.0, mma_cycles=192.0 * atoms, fma_cycles=float(fma_cyc),
+        tmem_cyc = 128 * 96 * 4 / 357.0
+        floor = max(tmem_cyc, 192.0 * atoms, float(fma_cyc))
+        roof["tile_model"] = dict(cycles_per_tile=cyc, tmem_read_cycles=tmem_cyc, mma_cycles=192.0 * atoms, fma_cycles=float(fma_cyc),
                                   floor_cycles=floor, frac=floor / cyc,
-                                  tmem_read_gbs=4.0 * local_pairs / 2.0 / (kms * 1e-3) / 1e9, tmem_read_peak_gbs=148 * 64 * clk * 1e6 / 1e9,
-                                  note="floor = max(TMEM read of the 48 KB accumulator at 64 B/cycle/SM, FMA-pipe cycles of the "
-                                       "packed series, tensor-pipe cycles of the 3xTF32 contraction); TMEM / MMA constants from "
-                                       "B300_MICROARCH.md, not re-measured on B200; DESIGN.md section 4")
+                                  tmem_read_gbs=4.0 * local_pairs / 2.0 / (kms * 1e-3) / 1e9, tmem_read_peak_gbs=148 * 357 * clk * 1e6 / 1e9,
+                                  note="floor = max(FMA-pipe cycles of the packed series, TMEM read of the 48 KB accumulator at the "
+                                       "357 B/cycle/SM measured on B200 (profiles/r02_ubench_tmem_ld.txt; the 64 B/cycle of "
+                                       "B300_MICROARCH.md does not hold here), tensor-pipe cycles of the 3xTF32 contraction); DESIGN.md section 4")
     roof["kernel"] = "jp_glm_tc_kernel" if path_used == _lib.PATH_TC else "jp_fit_nodes_kernel"
     try:   # DRAM traffic of the same kernel on the same workload from the committed ncu capture (per launch)
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("%s:%s" % (args.workload, roof["kernel"]))

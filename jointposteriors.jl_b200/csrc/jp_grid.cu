@@ -63,29 +63,108 @@ static int upload_rules(jp_ctx* ctx) {
 const double* jp_rule_nodes_dev(const jp_ctx* ctx, int rule) { return ctx->d_rule_nodes[rule ? 1 : 0]; }
 
 // ------------------------------------------------------------------------------------ kernels
-__global__ void __launch_bounds__(1024) jp_radix_scan_kernel(uint32_t* __restrict__ hist, int nblocks) {
-  __shared__ uint32_t tot[1024];
-  uint32_t* h = hist + (size_t)blockIdx.x * JP_SORT_BINS * nblocks;
-  const int len = JP_SORT_BINS * nblocks;
-  const int chunk = (len + 1023) / 1024;
-  const int b = threadIdx.x * chunk, e = min(b + chunk, len);
+// In-place exclusive scan of `len` 32-bit counts by ONE block of 32 warps: warp w owns the contiguous chunk w and walks it 32
+// entries at a time (coalesced), first for its total, then -- after the 32 totals are scanned -- again with a running carry
+// and a shuffle scan per step.  (One thread per chunk, each walking its own entries with strided loads, cost 29 us per radix
+// pass at the BASELINE grids.)
+__device__ __forceinline__ void jp_block_scan_u32(uint32_t* __restrict__ h, int len) {
+  __shared__ uint32_t s_tot[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int chunk = (((len + 31) / 32) + 31) & ~31;          // per warp, a multiple of 32
+  const int b = w * chunk, e = min(b + chunk, len);
   uint32_t s = 0;
-  for (int i = b; i < e; ++i) s += h[i];
-  tot[threadIdx.x] = s;
+  for (int i = b + lane; i < e; i += 32) s += h[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) s_tot[w] = s;
   __syncthreads();
-  // Hillis-Steele inclusive scan over the 1024 chunk totals
-  for (int o = 1; o < 1024; o <<= 1) {
-    uint32_t v = (threadIdx.x >= o) ? tot[threadIdx.x - o] : 0u;
-    __syncthreads();
-    tot[threadIdx.x] += v;
-    __syncthreads();
+  if (w == 0) {
+    uint32_t v = s_tot[lane], x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += u;
+    }
+    s_tot[lane] = x - v;                                     // exclusive prefix of the warp totals
   }
-  uint32_t run = tot[threadIdx.x] - s;
-  for (int i = b; i < e; ++i) {
-    uint32_t v = h[i];
-    h[i] = run;
-    run += v;
+  __syncthreads();
+  uint32_t run = s_tot[w];
+  for (int i0 = b; i0 < e; i0 += 32) {
+    const int i = i0 + lane;
+    const uint32_t v = (i < e) ? h[i] : 0u;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += u;
+    }
+    if (i < e) h[i] = run + x - v;
+    run += __shfl_sync(0xffffffffu, x, 31);
   }
+}
+__global__ void __launch_bounds__(1024) jp_radix_scan_kernel(uint32_t* __restrict__ hist, int nblocks) {
+  jp_block_scan_u32(hist + (size_t)blockIdx.x * JP_SORT_BINS * nblocks, JP_SORT_BINS * nblocks);
+}
+
+// Multi-block exclusive scan of n 32-bit values (head flags -> segment ids), three small launches: tile sums, scan of the tile
+// sums (one block, above), tile-local scan + offset.  out[n] receives the total.
+#define JP_SCAN_TILE 4096
+__global__ void __launch_bounds__(256) jp_scan_tile_sums_kernel(const uint32_t* __restrict__ in, unsigned long long n,
+                                                                uint32_t* __restrict__ tsum) {
+  __shared__ uint32_t sw[8];
+  const unsigned long long base = (unsigned long long)blockIdx.x * JP_SCAN_TILE;
+  uint32_t s = 0;
+  for (int j = threadIdx.x; j < JP_SCAN_TILE; j += 256) {
+    const unsigned long long i = base + j;
+    if (i < n) s += in[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int i = 0; i < 8; ++i) t += sw[i];
+    tsum[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(1024) jp_scan_tile_offsets_kernel(uint32_t* __restrict__ tsum, int ntiles) {
+  // exclusive scan of the tile sums in place; the grand total goes behind them
+  uint32_t last = (ntiles > 0) ? tsum[ntiles - 1] : 0u;
+  __syncthreads();
+  jp_block_scan_u32(tsum, ntiles);
+  __syncthreads();
+  if (threadIdx.x == 0) tsum[ntiles] = (ntiles > 0) ? tsum[ntiles - 1] + last : 0u;
+}
+__global__ void __launch_bounds__(256) jp_scan_apply_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                            unsigned long long n, const uint32_t* __restrict__ toff, int ntiles) {
+  // thread t owns 16 consecutive values of the tile (a 64-byte line): local sums, block scan of the 256 thread sums, write
+  __shared__ uint32_t s_w[8];
+  const unsigned long long base = (unsigned long long)blockIdx.x * JP_SCAN_TILE + (unsigned long long)threadIdx.x * 16;
+  uint32_t v[16], s = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    v[j] = (base + j < n) ? in[base + j] : 0u;
+    s += v[j];
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t x = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t u = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += u;
+  }
+  if (lane == 31) s_w[w] = x;
+  __syncthreads();
+  uint32_t wbase = 0;
+  for (int i = 0; i < w; ++i) wbase += s_w[i];
+  uint32_t run = toff[blockIdx.x] + wbase + x - s;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (base + j < n) out[base + j] = run;
+    run += v[j];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = toff[ntiles];
 }
 
 __global__ void jp_iota_kernel(uint32_t* __restrict__ perm, long long n, long long stride) {
@@ -236,31 +315,6 @@ __global__ void jp_heads_kernel(int d, unsigned long long P, const uint8_t* __re
   head[i] = h;
 }
 
-// single-block exclusive scan of 32-bit flags -> segment ids; total to out[n]
-__global__ void __launch_bounds__(1024) jp_scan32_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                                                         unsigned long long n) {
-  __shared__ uint32_t tot[1024];
-  unsigned long long chunk = (n + 1023) / 1024;
-  unsigned long long b = threadIdx.x * chunk, e = min(b + chunk, n);
-  uint32_t s = 0;
-  for (unsigned long long i = b; i < e; ++i) s += in[i];
-  tot[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    uint32_t v = (threadIdx.x >= o) ? tot[threadIdx.x - o] : 0u;
-    __syncthreads();
-    tot[threadIdx.x] += v;
-    __syncthreads();
-  }
-  uint32_t run = tot[threadIdx.x] - s;
-  for (unsigned long long i = b; i < e; ++i) {
-    uint32_t v = in[i];
-    out[i] = run;
-    run += v;
-  }
-  if (threadIdx.x == 1023) out[n] = tot[1023];
-}
-
 // seg_start[seg] = sorted position of the head of segment seg
 __global__ void jp_segstart_kernel(unsigned long long P, const uint32_t* __restrict__ head,
                                    const uint32_t* __restrict__ segid, uint32_t* __restrict__ seg_start) {
@@ -275,10 +329,45 @@ __global__ void jp_merge_kernel(int d, int rule, unsigned long long P, long long
                                 const uint32_t* __restrict__ seg_start, uint8_t* __restrict__ idx,
                                 double* __restrict__ w, double* __restrict__ hzz) {
   long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  unsigned long long b = seg_start[m], e = (m + 1 < M) ? seg_start[m + 1] : P;
-  double s = wt[perm[b]];
-  for (unsigned long long i = b + 1; i < e; ++i) s = __dadd_rn(s, wt[perm[i]]);
+  const bool live = m < M;
+  unsigned long long b = 0, e = 0;
+  if (live) {
+    b = seg_start[m];
+    e = (m + 1 < M) ? seg_start[m + 1] : P;
+  }
+  // Runs longer than 32 (the origin collects one point of every multi-index: thousands) are summed by the whole warp: the 32
+  // lanes gather 32 weights at once, lane 0's order of additions is unchanged (position order = generation order, the sum
+  // is bit-identical to the sequential loop), only the load latency is no longer paid once per element.
+  const int lane = threadIdx.x & 31;
+  unsigned longmask = __ballot_sync(0xffffffffu, live && (e - b) > 32);
+  double s = 0;
+  bool done = false;
+  while (longmask) {
+    const int src_lane = __ffs(longmask) - 1;
+    longmask &= longmask - 1;
+    const unsigned long long lb = __shfl_sync(0xffffffffu, b, src_lane), le = __shfl_sync(0xffffffffu, e, src_lane);
+    double acc = 0;
+    bool first = true;
+    for (unsigned long long i0 = lb; i0 < le; i0 += 32) {
+      const unsigned long long i = i0 + lane;
+      const double v = (i < le) ? wt[perm[i]] : 0.0;
+      const int cnt = (int)min(32ull, le - i0);
+      for (int j = 0; j < cnt; ++j) {
+        const double vj = __shfl_sync(0xffffffffu, v, j);
+        acc = first ? vj : __dadd_rn(acc, vj);
+        first = false;
+      }
+    }
+    if (lane == src_lane) {
+      s = acc;
+      done = true;
+    }
+  }
+  if (!live) return;
+  if (!done) {
+    s = wt[perm[b]];
+    for (unsigned long long i = b + 1; i < e; ++i) s = __dadd_rn(s, wt[perm[i]]);
+  }
   w[m] = s;
   uint32_t src = perm[b];
   double zz = 0;
@@ -289,6 +378,15 @@ __global__ void jp_merge_kernel(int d, int rule, unsigned long long P, long long
     zz += z * z;
   }
   hzz[m] = 0.5 * zz;
+}
+
+// max of a positive array by one block (the grid's largest |z|^2 / 2)
+__global__ void __launch_bounds__(1024) jp_grid_max_kernel(const double* __restrict__ v, long long n, double* __restrict__ out) {
+  __shared__ double sm[33];
+  double m = 0;
+  for (long long i = threadIdx.x; i < n; i += 1024) m = fmax(m, v[i]);
+  m = jp_block_max(m, sm);
+  if (threadIdx.x == 0) out[0] = m;
 }
 
 // ------------------------------------------------------------------------------------ host driver
@@ -365,6 +463,8 @@ int jp_grid_build(jp_ctx* ctx, int rule, int d, int level, jp_grid* g) {
   JP_CUDA(jp_dmalloc(ctx, &d_hist, (size_t)JP_SORT_BINS * nb * 4));
   JP_CUDA(jp_dmalloc(ctx, &d_head, Ptot * 4));
   JP_CUDA(jp_dmalloc(ctx, &d_seg, (Ptot + 1) * 4));
+  uint32_t* d_tsum = nullptr;
+  JP_CUDA(jp_dmalloc(ctx, &d_tsum, ((Ptot + JP_SCAN_TILE - 1) / JP_SCAN_TILE + 2) * 4));
   unsigned gp = (unsigned)((Ptot + 255) / 256);
   jp_expand_kernel<<<gp, 256, 0, st>>>(d, rule, n_mi, d_mi, d_coef, d_off, Ptot, d_keys, d_flip, d_wt);
   JP_CHECK_LAUNCH(ctx);
@@ -383,8 +483,15 @@ int jp_grid_build(jp_ctx* ctx, int rule, int d, int level, jp_grid* g) {
   }
   jp_heads_kernel<<<gp, 256, 0, st>>>(d, Ptot, d_keys, pin, d_head);
   JP_CHECK_LAUNCH(ctx);
-  jp_scan32_kernel<<<1, 1024, 0, st>>>(d_head, d_seg, Ptot);
-  JP_CHECK_LAUNCH(ctx);
+  {
+    const int ntiles = (int)((Ptot + JP_SCAN_TILE - 1) / JP_SCAN_TILE);
+    jp_scan_tile_sums_kernel<<<ntiles, 256, 0, st>>>(d_head, Ptot, d_tsum);
+    JP_CHECK_LAUNCH(ctx);
+    jp_scan_tile_offsets_kernel<<<1, 1024, 0, st>>>(d_tsum, ntiles);
+    JP_CHECK_LAUNCH(ctx);
+    jp_scan_apply_kernel<<<ntiles, 256, 0, st>>>(d_head, d_seg, Ptot, d_tsum, ntiles);
+    JP_CHECK_LAUNCH(ctx);
+  }
   uint32_t M32 = 0;
   JP_CUDA(cudaMemcpyAsync(&M32, d_seg + Ptot, 4, cudaMemcpyDeviceToHost, st));
   JP_CUDA(cudaStreamSynchronize(st));
@@ -403,15 +510,16 @@ int jp_grid_build(jp_ctx* ctx, int rule, int d, int level, jp_grid* g) {
   // sit at most at the largest node of the highest 1-D level in use, but the sum constraint couples
   // them; read it back from the device table instead of bounding it.
   {
-    std::vector<double> hz((size_t)M);
-    JP_CUDA(cudaMemcpy(hz.data(), g->d_hzz, (size_t)M * 8, cudaMemcpyDeviceToHost));
+    jp_grid_max_kernel<<<1, 1024, 0, st>>>(g->d_hzz, M, ctx->d_scratch);
+    JP_CHECK_LAUNCH(ctx);
     double mx = 0;
-    for (double v : hz) mx = std::max(mx, 2.0 * v);
-    g->zmax2 = mx;
+    JP_CUDA(cudaMemcpyAsync(&mx, ctx->d_scratch, 8, cudaMemcpyDeviceToHost, st));
+    JP_CUDA(cudaStreamSynchronize(st));
+    g->zmax2 = 2.0 * mx;
   }
   g->ctx = ctx; g->rule = rule; g->d = d; g->level = level; g->M = M;
   jp_dfree(ctx, d_comp); jp_dfree(ctx, d_mi); jp_dfree(ctx, d_coef); jp_dfree(ctx, d_npts); jp_dfree(ctx, d_off);
   jp_dfree(ctx, d_keys); jp_dfree(ctx, d_flip); jp_dfree(ctx, d_wt); jp_dfree(ctx, d_pa); jp_dfree(ctx, d_pb); jp_dfree(ctx, d_hist);
-  jp_dfree(ctx, d_head); jp_dfree(ctx, d_seg); jp_dfree(ctx, d_start);
+  jp_dfree(ctx, d_head); jp_dfree(ctx, d_seg); jp_dfree(ctx, d_start); jp_dfree(ctx, d_tsum);
   return JP_OK;
 }
