@@ -561,7 +561,7 @@ def run_product(args):
                                        "B300_MICROARCH.md does not hold here), tensor-pipe cycles of the 3xTF32 contraction); DESIGN.md section 4")
     roof["kernel"] = "jp_glm_tc_kernel" if path_used == _lib.PATH_TC else "jp_fit_nodes_kernel"
     try:   # DRAM traffic of the same kernel on the same workload from the committed ncu capture (per launch)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("%s:%s" % (args.workload, roof["kernel"]))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get("%s:%s" % (args.workload, roof["kernel"]))
         if tr and world == 1:
             roof["traffic"] = tr["dram_bytes"]
             roof["traffic_source"] = tr["source"]
