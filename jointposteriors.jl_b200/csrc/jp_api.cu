@@ -6,6 +6,32 @@
 #include "jp_common.cuh"
 #include "jp_family.cuh"
 
+// queue the download of the normalised weights on the context's `side` stream, behind everything queued on the main stream so far
+int jp_density_prefetch(jp_posterior* p) {
+  jp_ctx* ctx = p->ctx;
+  const size_t n = (size_t)p->M;
+  if (n == 0 || n > ((size_t)1 << 24)) return JP_OK;                         // (128 MB of pinned memory at most)
+  if (n > ctx->h_density_cap) {
+    if (ctx->h_density) {
+      JP_CUDA(cudaEventSynchronize(ctx->ev_density));
+      JP_CUDA(cudaFreeHost(ctx->h_density));
+      ctx->h_density = nullptr;
+      ctx->h_density_cap = 0;
+    }
+    JP_CUDA(cudaMallocHost(&ctx->h_density, n * 8));
+    ctx->h_density_cap = n;
+  }
+  ctx->h_density_owner = nullptr;
+  JP_CUDA(cudaEventRecord(ctx->ev_stage4, ctx->stream));
+  JP_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_stage4, 0));
+  JP_CUDA(cudaMemcpyAsync(ctx->h_density, p->d_density, n * 8, cudaMemcpyDeviceToHost, ctx->side));
+  JP_CUDA(cudaEventRecord(ctx->ev_density, ctx->side));
+  ctx->h_density_owner = p;
+  ctx->h_density_gen = p->fit_gen;
+  return JP_OK;
+}
+
+
 extern "C" {
 
 int jp_ctx_create(int device, jp_ctx** out) {
@@ -51,6 +77,8 @@ int jp_ctx_create(int device, jp_ctx** out) {
   JP_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   JP_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   JP_CUDA(cudaEventCreateWithFlags(&ctx->ev_pinned, cudaEventDisableTiming));
+  JP_CUDA(cudaEventCreateWithFlags(&ctx->ev_density, cudaEventDisableTiming));
+  JP_CUDA(cudaEventCreateWithFlags(&ctx->ev_stage4, cudaEventDisableTiming));
   JP_CUDA(cudaEventCreate(&ctx->ev_k0));
   JP_CUDA(cudaEventCreate(&ctx->ev_k1));
   *out = ctx;
@@ -73,6 +101,9 @@ int jp_ctx_destroy(jp_ctx* ctx) {
   jp_dfree(ctx, ctx->d_scratch); jp_dfree(ctx, ctx->d_counters); jp_dfree(ctx, ctx->d_bpart);
   cudaStreamSynchronize(ctx->stream);
   cudaFreeHost(ctx->h_pinned);
+  if (ctx->h_density) cudaFreeHost(ctx->h_density);
+  cudaEventDestroy(ctx->ev_density);
+  cudaEventDestroy(ctx->ev_stage4);
   cudaFree(ctx->d_rule_nodes[0]); cudaFree(ctx->d_rule_nodes[1]);
   cudaStreamSynchronize(ctx->side);
   cudaStreamDestroy(ctx->side);
@@ -310,6 +341,10 @@ int jp_posterior_free(jp_posterior* p) {
   if (!p) return JP_OK;
   cudaSetDevice(p->ctx->device);
   jp_ctx* c = p->ctx;   // stream-ordered frees: work already queued on the ctx stream still sees the buffers
+  if (c->h_density_owner == p) {      // a queued download of this posterior's weights must finish before its buffer is reused
+    c->h_density_owner = nullptr;
+    cudaStreamWaitEvent(c->stream, c->ev_density, 0);
+  }
   jp_dfree(c, p->d_theta); jp_dfree(c, p->d_a); jp_dfree(c, p->d_logdens); jp_dfree(c, p->d_density); jp_dfree(c, p->d_part);
   jp_dfree(c, p->d_stats); jp_dfree(c, p->d_mu); jp_dfree(c, p->d_U); jp_dfree(c, p->d_tcode); jp_tc_post_free(p);
   jp_dfree(c, p->d_vals); jp_dfree(c, p->d_bins); jp_dfree(c, (void*)p->d_vptr); jp_dfree(c, p->d_perm_a); jp_dfree(c, p->d_perm_b); jp_dfree(c, p->d_hist);
@@ -366,6 +401,16 @@ int jp_get_cache(jp_posterior* p, double* h) {
   return download(p, p->d_theta, h, (size_t)p->M * p->d);
 }
 int jp_get_logdens(jp_posterior* p, double* h) { return download(p, p ? p->d_logdens : nullptr, h, p ? (size_t)p->M : 0); }
-int jp_get_density(jp_posterior* p, double* h) { return download(p, p ? p->d_density : nullptr, h, p ? (size_t)p->M : 0); }
+int jp_get_density(jp_posterior* p, double* h) {
+  JP_REQUIRE(p && h, "jp_get_density: null argument");
+  jp_ctx* ctx = p->ctx;
+  if (ctx->h_density_owner == p && ctx->h_density_gen == p->fit_gen) {      // queued by jp_fit behind stage 4
+    JP_CUDA(cudaSetDevice(ctx->device));
+    JP_CUDA(cudaEventSynchronize(ctx->ev_density));
+    std::memcpy(h, ctx->h_density, (size_t)p->M * 8);
+    return jp_fit_tc_verify(p);
+  }
+  return download(p, p->d_density, h, (size_t)p->M);
+}
 
 }  // extern "C"

@@ -96,6 +96,14 @@ struct jp_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
   cudaEvent_t ev_pinned = nullptr;   // recorded after the last asynchronous copy OUT of h_pinned (see jp_pinned_acquire)
   bool pinned_busy = false;
+  // The reference's fit returns `density` as a host vector: jp_fit queues its download on `side` right behind stage 4, into this
+  // pinned buffer, so that it overlaps whatever the caller does next on the device (the marginals); jp_get_density then only waits
+  // for that copy.  One buffer per context: valid for the posterior / fit generation recorded beside it.
+  double* h_density = nullptr;
+  size_t h_density_cap = 0;
+  const void* h_density_owner = nullptr;
+  long long h_density_gen = -1;
+  cudaEvent_t ev_density = nullptr, ev_stage4 = nullptr;
   bool rules_uploaded = false, fit_nodes_uploaded = false, tc_tables_uploaded = false;
   double* d_rule_nodes[2] = {nullptr, nullptr};
 };
@@ -417,6 +425,7 @@ void jp_tc_post_free(jp_posterior* post);
 int jp_construct_columns(jp_posterior* post, int K, const int* d_coords, double* d_out);   // RawBuild: constrained columns from the cache
 int jp_glm_grad_hess_comm(jp_ctx* ctx, const jp_data* data, jp_comm* comm, int d, const double* h_beta, double* h_g, double* h_Hneg,
                           double* h_logpost);
+int jp_density_prefetch(jp_posterior* post);      // queue the download of the normalised weights behind stage 4 (jp_api.cu)
 int jp_upload_fit_consts(jp_posterior* post, const jp_fit_args* args);   // mu_hat, U, transform codes -> device
 int jp_marginal_design_device(jp_posterior* post, int k, double** d_V, long long** d_ind, double* h_mu, double* h_sigma);   // jp_marginal.cu
 const double* jp_rule_nodes_dev(const jp_ctx* ctx, int rule);   // device copy of the master z-node table (this context's GPU)

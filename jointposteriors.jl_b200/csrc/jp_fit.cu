@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <cooperative_groups.h>
 #include "jp_common.cuh"
 #include "jp_family.cuh"
@@ -904,7 +905,11 @@ int jp_fit(jp_posterior* post, const jp_fit_args* args) {
   JP_ENTER_CTX(post->ctx);
   JP_TRY(jp_fit_check_args(post, args));
   JP_TRY(jp_fit_launch_path(post, args, false));
-  return jp_stage4_launch(post, true, post->d_stats);   // finish + max + sum + scale: one cooperative launch
+  JP_TRY(jp_stage4_launch(post, true, post->d_stats));   // finish + max + sum + scale: one cooperative launch
+  // `density` is a host vector in the reference's result (src/joint_posterior.jl:5,181): its download starts now, beside
+  // whatever follows on the main stream
+  static const bool no_prefetch = getenv("JP_NO_DENSITY_PREFETCH") != nullptr;
+  return no_prefetch ? JP_OK : jp_density_prefetch(post);
 }
 
 }  // extern "C"
