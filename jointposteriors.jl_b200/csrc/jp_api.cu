@@ -325,9 +325,12 @@ int jp_posterior_create(jp_ctx* ctx, const jp_grid* g, const jp_data* data, cons
   A((void**)&p->d_density, M * 8);
   A((void**)&p->d_part, M * (JP_POST_PART_SPLITS + 1) * 8);
   A((void**)&p->d_stats, 16 * 8);
-  A((void**)&p->d_mu, (size_t)p->d * 8);
-  A((void**)&p->d_U, (size_t)p->d * p->p * 8);
-  A((void**)&p->d_tcode, (size_t)p->d * 4);
+  // the per-fit constants (mu_hat d, U d x p, transform codes d) share ONE block: one host-to-device copy per fit
+  A((void**)&p->d_mu, (size_t)(p->d + p->d * p->p) * 8 + (size_t)p->d * 4);
+  if (e == cudaSuccess) {
+    p->d_U = p->d_mu + p->d;
+    p->d_tcode = reinterpret_cast<int*>(p->d_U + (size_t)p->d * p->p);
+  }
   if (e != cudaSuccess) {
     jp_set_error("jp_posterior_create: %s", cudaGetErrorString(e));
     jp_posterior_free(p);
@@ -346,7 +349,7 @@ int jp_posterior_free(jp_posterior* p) {
     cudaStreamWaitEvent(c->stream, c->ev_density, 0);
   }
   jp_dfree(c, p->d_theta); jp_dfree(c, p->d_a); jp_dfree(c, p->d_logdens); jp_dfree(c, p->d_density); jp_dfree(c, p->d_part);
-  jp_dfree(c, p->d_stats); jp_dfree(c, p->d_mu); jp_dfree(c, p->d_U); jp_dfree(c, p->d_tcode); jp_tc_post_free(p);
+  jp_dfree(c, p->d_stats); jp_dfree(c, p->d_mu); jp_tc_post_free(p);      // d_U, d_tcode live in d_mu's block
   jp_dfree(c, p->d_vals); jp_dfree(c, p->d_bins); jp_dfree(c, (void*)p->d_vptr); jp_dfree(c, p->d_perm_a); jp_dfree(c, p->d_perm_b); jp_dfree(c, p->d_hist);
   jp_dfree(c, p->d_sv); jp_dfree(c, p->d_sw); jp_dfree(c, p->d_cw); jp_dfree(c, p->d_mout);
   jp_dfree(c, p->d_cmom); jp_dfree(c, p->d_coords); jp_dfree(c, p->d_cand);

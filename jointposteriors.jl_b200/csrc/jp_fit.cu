@@ -518,9 +518,8 @@ int jp_upload_fit_consts(jp_posterior* post, const jp_fit_args* args) {
   int* hc = reinterpret_cast<int*>(hp + d + d * p);
   for (int i = 0; i < d; ++i) hc[i] = args->h_transform[i];
   post->tcode_host.assign(args->h_transform, args->h_transform + d);
-  JP_CUDA(cudaMemcpyAsync(post->d_mu, hp, sizeof(double) * d, cudaMemcpyHostToDevice, ctx->stream));
-  JP_CUDA(cudaMemcpyAsync(post->d_U, hp + d, sizeof(double) * d * p, cudaMemcpyHostToDevice, ctx->stream));
-  JP_CUDA(cudaMemcpyAsync(post->d_tcode, hc, sizeof(int) * d, cudaMemcpyHostToDevice, ctx->stream));
+  // one copy: the device block of jp_posterior_create has the staging area's layout (mu | U | codes)
+  JP_CUDA(cudaMemcpyAsync(post->d_mu, hp, sizeof(double) * (d + d * p) + sizeof(int) * d, cudaMemcpyHostToDevice, ctx->stream));
   JP_CUDA(jp_pinned_publish(ctx));
   return JP_OK;
 }

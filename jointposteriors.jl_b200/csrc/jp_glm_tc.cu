@@ -1299,7 +1299,8 @@ static int tc_setup(jp_posterior* post, const jp_fit_args* args, int world, int 
 
 // FP64 sums (g, H, L_hat) over slice `rank` into d_sums, per-observation coefficients of the slice and the block
 // partials of the bounds into ds->d_bounds
-static int tc_prep_slice(jp_posterior* post, const jp_fit_args* args, int rank, double* d_sums) {
+// what: 1 = fork + coefficient pass (`side`), 2 = sums (`side2`; after a call with 1), 3 = both
+static int tc_prep_slice(jp_posterior* post, const jp_fit_args* args, int rank, double* d_sums, int what = 3) {
   jp_ctx* ctx = post->ctx;
   const jp_data* data = post->data;
   TcDataState* ds = static_cast<TcDataState*>(data->tc_state);
@@ -1309,18 +1310,20 @@ static int tc_prep_slice(jp_posterior* post, const jp_fit_args* args, int rank, 
   // bounds) and of the node operand: the coefficient pass runs on the context's stream `side`, the sums on `side2`, both
   // forked here; the main stream stays free for the node operand.  The caller joins (tc_join_side) before anything reads
   // their results on the main stream.
-  JP_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
-  JP_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-  JP_CUDA(cudaStreamWaitEvent(ctx->side2, ctx->ev_fork, 0));
-  const double z_max = std::sqrt(post->grid->zmax2), z_ref = std::min(z_max, 6.0);
-  const size_t sm_obs = (size_t)(((d + 1) & ~1) + d * ((p + 3) & ~3) + 2 * TC_PREP_THREADS * (data->ncols | 1)) * 8;
-  if (sm_obs > 48 * 1024)
-    JP_CUDA(cudaFuncSetAttribute(tc_obs_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_obs));
-  tc_obs_prep_kernel<<<ds->prep_blocks, TC_PREP_THREADS, sm_obs, ctx->side>>>(
-      data->family, d, p, data->ncols, o1 - o0, ds->n_loc, data->d_obs + (size_t)o0 * data->ncols, post->d_mu, post->d_U, z_ref,
-      z_max, ds->d_coef, ds->n_loc, ds->d_bounds);
-  JP_CHECK_LAUNCH(ctx);
-  JP_TRY(jp_glm_sums_device_range_on(ctx, ctx->side2, data, d, post->d_mu, d_sums, ds->d_work, ds->glm_blocks, o0, o1));
+  if (what & 1) {
+    JP_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    JP_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    JP_CUDA(cudaStreamWaitEvent(ctx->side2, ctx->ev_fork, 0));
+    const double z_max = std::sqrt(post->grid->zmax2), z_ref = std::min(z_max, 6.0);
+    const size_t sm_obs = (size_t)(((d + 1) & ~1) + d * ((p + 3) & ~3) + 2 * TC_PREP_THREADS * (data->ncols | 1)) * 8;
+    if (sm_obs > 48 * 1024)
+      JP_CUDA(cudaFuncSetAttribute(tc_obs_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_obs));
+    tc_obs_prep_kernel<<<ds->prep_blocks, TC_PREP_THREADS, sm_obs, ctx->side>>>(
+        data->family, d, p, data->ncols, o1 - o0, ds->n_loc, data->d_obs + (size_t)o0 * data->ncols, post->d_mu, post->d_U, z_ref,
+        z_max, ds->d_coef, ds->n_loc, ds->d_bounds);
+    JP_CHECK_LAUNCH(ctx);
+  }
+  if (what & 2) JP_TRY(jp_glm_sums_device_range_on(ctx, ctx->side2, data, d, post->d_mu, d_sums, ds->d_work, ds->glm_blocks, o0, o1));
   return JP_OK;
 }
 
@@ -1329,6 +1332,19 @@ static int tc_join_side(jp_ctx* ctx) {
   JP_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
   JP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
   JP_CUDA(cudaEventRecord(ctx->ev_join2, ctx->side2));
+  JP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));
+  return JP_OK;
+}
+// The contraction kernel needs the coefficient pass (`side`) only; the sums and the FP64 quadratic part of every node (`side2`)
+// are read by the finish / stage 4 BEHIND the kernel, so the main stream picks them up there (tc_join_quad) and the kernel's
+// start no longer waits for the sums -> quadratic-part chain.
+static int tc_join_coef(jp_ctx* ctx) {
+  JP_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
+  JP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  JP_CUDA(cudaEventRecord(ctx->ev_join2, ctx->side2));       // waited for behind the kernel
+  return JP_OK;
+}
+static int tc_join_quad(jp_ctx* ctx) {
   JP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));
   return JP_OK;
 }
@@ -1387,7 +1403,7 @@ static int tc_node_quad(jp_posterior* post, const jp_fit_args* args, cudaStream_
 
 // the tensor-core kernel and the per-node finish (after tc_node_prep)
 static int tc_run_kernel(jp_posterior* post, const jp_fit_args* args, int NC, bool finish, const int* nc_sel = nullptr,
-                         const float* coef_gathered = nullptr, bool rest = false) {
+                         const float* coef_gathered = nullptr, bool rest = false, bool join_quad = false) {
   // rest: the single launch that serves NC = 6 .. 12 under a device-side decision (geometry of NC = TC_NCMAX; the
   // coefficient slice stride of the gathered rows is NC-dependent and read from the decision by the kernel)
   jp_ctx* ctx = post->ctx;
@@ -1466,6 +1482,7 @@ static int tc_run_kernel(jp_posterior* post, const jp_fit_args* args, int NC, bo
   else stc = launch_tc<12>(ctx, ds->tmA, ps->tmB, kp, smem);
   JP_TRY(stc);
   JP_MARK(ctx, "fit:tc_kernel");
+  if (join_quad) JP_TRY(tc_join_quad(ctx));      // the finish / stage 4 read the quadratic part
   post->path_used = JP_PATH_TC;
   post->fin = JpFinish();
   post->fin.path = JP_PATH_TC; post->fin.chunks = kp.chunks; post->fin.P = ps->P; post->fin.j_lo = ps->j_lo;
@@ -1512,17 +1529,14 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args, bool finish) {
   JP_TRY(tc_setup(post, args, 1, 0));
   JP_MARK(ctx, "fit:setup+consts");
   TcDataState* ds = static_cast<TcDataState*>(post->data->tc_state);
-  JP_TRY(tc_prep_slice(post, args, 0, ds->d_sums));
-  jp_trace_mark(ctx, "fit:glm_sums(side2)", ctx->side2);
-  JP_MARK_SIDE(ctx, "fit:obs_prep(side)");
-  JP_TRY(tc_node_quad(post, args, ctx->side2));       // behind the sums on their stream
-  jp_trace_mark(ctx, "fit:node_quad(side2)", ctx->side2);
   // diagnostic only (bench.py attribution of the host round trip): JP_TC_ASSUME=NC,fold skips the bounds read-back
   static const char* assume = getenv("JP_TC_ASSUME");
   if (assume) {
     int nc = 4, fd = 1;
     sscanf(assume, "%d,%d", &nc, &fd);
     post->tc_bounds[3] = nc; post->tc_bounds[5] = fd;
+    JP_TRY(tc_prep_slice(post, args, 0, ds->d_sums));
+    JP_TRY(tc_node_quad(post, args, ctx->side2));
     JP_TRY(tc_node_operand(post, args));
     JP_TRY(tc_join_side(ctx));
     if (fd) JP_TRY(tc_fold_slice(post, nc));
@@ -1531,7 +1545,11 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args, bool finish) {
   // `side`: block bounds -> 22 numbers -> pinned host memory; `side2`: sums, then the quadratic part of every node; main
   // stream: theta and the pair operand.  The host's wait for the bounds is hidden under the three (measured: skipping it
   // with JP_TC_ASSUME changes the fit time by < 5 us).
+  // Enqueue order = urgency: the chain the kernel's start hangs on first (coefficient pass -> bounds -> host), then the node
+  // operand (needed by the kernel), last the sums and the quadratic part (needed behind the kernel only).
   double* hb = ctx->h_pinned + JP_PINNED_BOUNDS_OFF;   // away from the constants staged by jp_upload_fit_consts
+  JP_TRY(tc_prep_slice(post, args, 0, ds->d_sums, 1));
+  JP_MARK_SIDE(ctx, "fit:obs_prep(side)");
   tc_bounds_reduce_kernel<<<1, 32 * TC_NBOUND, 0, ctx->side>>>(ds->d_bounds, ds->prep_blocks, ds->d_comb);
   JP_CHECK_LAUNCH(ctx);
   JP_CUDA(cudaMemcpyAsync(hb, ds->d_comb, (size_t)TC_NBOUND * 8, cudaMemcpyDeviceToHost, ctx->side));
@@ -1539,15 +1557,23 @@ int jp_fit_tc_launch(jp_posterior* post, const jp_fit_args* args, bool finish) {
   JP_MARK_SIDE(ctx, "fit:bounds_d2h(side)");
   JP_TRY(tc_node_operand(post, args));
   JP_MARK(ctx, "fit:node_operand");
+  JP_TRY(tc_prep_slice(post, args, 0, ds->d_sums, 2));
+  jp_trace_mark(ctx, "fit:glm_sums(side2)", ctx->side2);
+  JP_TRY(tc_node_quad(post, args, ctx->side2));       // behind the sums on their stream
+  jp_trace_mark(ctx, "fit:node_quad(side2)", ctx->side2);
   JP_CUDA(cudaEventSynchronize(ds->ev_bounds));
-  JP_TRY(tc_join_side(ctx));
+  JP_TRY(tc_join_coef(ctx));
   double b[TC_NBOUND];
   for (int j = 0; j < TC_NBOUND; ++j) b[j] = hb[j];
   int NC = 0, fold = 0;
-  JP_TRY(tc_decide(post, b, &NC, &fold));
+  const int st_dec = tc_decide(post, b, &NC, &fold);
+  if (st_dec != JP_OK) {
+    tc_join_quad(ctx);      // leave no work of this fit un-joined behind an error return
+    return st_dec;
+  }
   if (fold) JP_TRY(tc_fold_slice(post, NC));
   JP_MARK(ctx, "fit:host_decision+fold");
-  return tc_run_kernel(post, args, NC, finish);
+  return tc_run_kernel(post, args, NC, finish, nullptr, nullptr, false, true);
 }
 
 // ---- sharded prep, phase by phase (extern "C" wrappers in jp_fit.cu).  L = nE + 1 + TC_NBOUND doubles per rank.
@@ -1745,7 +1771,8 @@ int jp_fit_tc_launch_dev(jp_posterior* post, const jp_fit_args* args, jp_comm* c
   JP_CHECK_LAUNCH(ctx);
   if (world == 1) JP_TRY(tc_node_quad(post, args, ctx->side2));
   JP_TRY(tc_node_operand(post, args));
-  JP_TRY(tc_join_side(ctx));
+  if (world == 1) JP_TRY(tc_join_coef(ctx));      // the quadratic part is joined behind the kernel
+  else JP_TRY(tc_join_side(ctx));
   JP_MARK(ctx, "fit:prep_joined");
   if (world > 1) {
     const double* g = nullptr;
@@ -1776,7 +1803,6 @@ int jp_fit_tc_launch_dev(jp_posterior* post, const jp_fit_args* args, jp_comm* c
     coef_gathered = reinterpret_cast<const float*>(comm->mailbox + comm->bulk_off);
     JP_MARK(ctx, "fit:coef_exchanged");
   }
-  if (world > 1) JP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));      // the quadratic part (stage 4 reads it)
   // two launches: the shortest series (the usual choice) and one kernel for all longer ones; whichever the device did not
   // choose returns before touching anything
   JP_CUDA(cudaEventRecord(ctx->ev_k0, ctx->stream));
@@ -1784,6 +1810,7 @@ int jp_fit_tc_launch_dev(jp_posterior* post, const jp_fit_args* args, jp_comm* c
   JP_TRY(tc_run_kernel(post, args, TC_NCMAX, false, &ps->d_dec->NC, coef_gathered, true));
   JP_CUDA(cudaEventRecord(ctx->ev_k1, ctx->stream));
   ctx->ev_valid = true;
+  JP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));      // the quadratic part, computed beside the kernel (stage 4 reads it)
   if (obs) {
     unsigned long long seq = 0;
     JP_TRY(jp_comm_bulk_begin(comm, &seq));
