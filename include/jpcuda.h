@@ -191,6 +191,11 @@ int jp_glm_grad_hess(jp_ctx* ctx, const jp_data* data, int d, const double* h_be
  * hands to deduce_scale!, :167); *neg_min: the minimised objective (:166); *evals: GPU evaluations used. */
 int jp_mode(jp_ctx* ctx, const jp_data* data, int d, const int* h_transform, int glm, double* h_x, double* h_H,
             double* neg_min, int* evals);
+/* How the last jp_mode / jp_mode_p2p call of the calling thread ended: infinity norm of the gradient of the negative
+ * log-density at the returned point, iterations used, converged = 1 when the search stopped on its own criterion, 0 at the
+ * iteration cap or after a failed line search (the point is still returned: a grid centred beside the mode is a worse
+ * quadrature, not an error -- the host decides whether to warn). */
+int jp_mode_report(double* grad_inf_norm, int* iterations, int* converged);
 
 /* Unconstrained log-density  log_density(transform(x), data) + log|J(x)|  at K arbitrary points: the
  * objective `mode` minimises (reference src/joint_posterior.jl:164-168, sign flipped, no neg_min),

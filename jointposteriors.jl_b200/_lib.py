@@ -65,7 +65,7 @@ SYMBOLS = [
     "jp_ctx_last_kernel_ms", "jp_ctx_trace", "jp_ctx_trace_dump",
     "jp_grid_get", "jp_grid_size", "jp_grid_dim", "jp_grid_build_stats", "jp_grid_download", "jp_rule_info", "jp_rule_level_nodes",
     "jp_grid_level_cap",
-    "jp_data_upload", "jp_data_adopt_device", "jp_data_free", "jp_glm_grad_hess", "jp_log_density_points", "jp_mode",
+    "jp_data_upload", "jp_data_adopt_device", "jp_data_free", "jp_glm_grad_hess", "jp_log_density_points", "jp_mode", "jp_mode_report",
     "jp_posterior_create", "jp_posterior_free", "jp_posterior_size",
     "jp_fit", "jp_fit_local", "jp_fit_local_sum", "jp_fit_normalise", "jp_fit_local_stats", "jp_fit_normalise_gathered",
     "jp_fit_prep_len", "jp_fit_prep_local", "jp_fit_prep_gathered", "jp_fit_coef_slab", "jp_fit_local_stats_prepared",

@@ -381,14 +381,23 @@ double max_abs(const double* v, int n) {
   return m;
 }
 
+// what the last mode search of this thread ended with (jp_mode_report): infinity norm of the gradient of the negative
+// log-density at the returned point, and whether the iteration stopped on its own criterion rather than at the cap / a failed
+// line search
+thread_local double g_mode_grad = 0.0;
+thread_local int g_mode_converged = 0, g_mode_iterations = 0;
+
 int mode_generic(ModeProblem& P, double* x, double* H, double* fx_out, int iters) {
   const int d = P.d;
   const double h = 2e-3;
   std::vector<double> g(d), step(d), xn(d), gn(d), Hn((size_t)d * d), lam, V, cands((size_t)4 * d), fc(4);
   double fx;
+  g_mode_converged = 0;
+  g_mode_iterations = 0;
   int s = P.richardson(x, h, &fx, g.data(), H);
   if (s != JP_OK) return s;
   for (int it = 0; it < iters; ++it) {
+    g_mode_iterations = it + 1;
     symmetric_eigen(H, d, lam, V);                       // ascending; V[i * d + k] = component k of eigenvector i
     double scale = 0;
     for (int i = 0; i < d; ++i) scale = std::fmax(scale, std::fabs(lam[i]));
@@ -420,7 +429,10 @@ int mode_generic(ModeProblem& P, double* x, double* H, double* fx_out, int iters
     double nrm = max_abs(step.data(), d);
     if (nrm > 10.0)
       for (int k = 0; k < d; ++k) step[k] *= 10.0 / nrm;
-    if (lam[0] > 0 && max_abs(step.data(), d) < 1e-9 * (1 + max_abs(x, d))) break;   // below the finite-difference resolution
+    if (lam[0] > 0 && max_abs(step.data(), d) < 1e-9 * (1 + max_abs(x, d))) {         // below the finite-difference resolution
+      g_mode_converged = 1;
+      break;
+    }
     double t = 1.0, fn = 0;
     bool ok = false;
     while (t > 1e-8) {
@@ -439,6 +451,10 @@ int mode_generic(ModeProblem& P, double* x, double* H, double* fx_out, int iters
     fx = fn;
   }
   *fx_out = fx;
+  g_mode_grad = max_abs(g.data(), d);
+  // a line search that finds no further decrease at the resolution of the finite differences, with a gradient that is tiny next
+  // to the objective, is the normal way this iteration ends
+  if (!g_mode_converged && g_mode_grad <= 1e-5 * (1 + std::fabs(fx))) g_mode_converged = 1;
   return JP_OK;
 }
 
@@ -474,7 +490,10 @@ int mode_glm(jp_ctx* ctx, const jp_data* data, jp_comm* comm, int d, double* x, 
   int s = jp_glm_grad_hess_comm(ctx, data, comm, d, x, g.data(), H, &lp);
   ++*evals;
   if (s != JP_OK) return s;
+  g_mode_converged = 0;
+  g_mode_iterations = 0;
   for (int it = 0; it < iters; ++it) {
+    g_mode_iterations = it + 1;
     step = g;
     if (!solve_dense(std::vector<double>(H, H + (size_t)d * d), step, d)) break;
     double t = 1.0;
@@ -496,8 +515,15 @@ int mode_glm(jp_ctx* ctx, const jp_data* data, jp_comm* comm, int d, double* x, 
     for (int k = 0; k < d; ++k) { x[k] = xn[k]; g[k] = g2[k]; }
     std::memcpy(H, H2.data(), sizeof(double) * d * d);
     lp = lp2;
-    if (moved < 1e-13 * (1 + max_abs(x, d))) break;
+    if (moved < 1e-13 * (1 + max_abs(x, d))) {
+      g_mode_converged = 1;
+      break;
+    }
   }
+  g_mode_grad = max_abs(g.data(), d);
+  // a Newton step that no longer moves the log-posterior (failed line search at the resolution of the sums) with a gradient that
+  // is tiny next to the curvature is a converged fit as well
+  if (!g_mode_converged && g_mode_grad <= 1e-6 * (1 + std::fabs(lp))) g_mode_converged = 1;
   *neg_min = -lp;
   return JP_OK;
 }
@@ -544,6 +570,17 @@ int jp_mode_p2p(jp_ctx* ctx, const jp_data* data, jp_comm* comm, int d, const in
   const int s = mode_glm(ctx, data, comm, d, h_x, h_H, neg_min, &n_eval, 60);
   if (evals) *evals = n_eval;
   return s;
+}
+
+// How the last jp_mode / jp_mode_p2p call of the calling thread ended: infinity norm of the gradient of the negative log-density
+// at the returned point, iterations used, and whether the search stopped on its own criterion (1) or at the iteration cap / a
+// failed line search (0) -- the reference's Optim call reports the same through its result object, and a grid centred on a
+// point that is not the mode is a worse quadrature, not an error.
+int jp_mode_report(double* grad_inf_norm, int* iterations, int* converged) {
+  if (grad_inf_norm) *grad_inf_norm = g_mode_grad;
+  if (iterations) *iterations = g_mode_iterations;
+  if (converged) *converged = g_mode_converged;
+  return JP_OK;
 }
 
 }  // extern "C"

@@ -447,6 +447,8 @@ def mode_p2p(M, ddata, comm, x0=None):
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     check(lib().jp_mode_p2p(ddata.ctx.handle, ddata.handle, comm.handle, C.c_int(d), p(code), p(x), p(H), C.byref(neg_min),
                             C.byref(evals)))
+    from .model import _warn_unless_converged
+    _warn_unless_converged("mode_p2p")
     return x, deduce_scale(M, M.hessian_scale * np.array(H)), neg_min.value
 
 

@@ -40,6 +40,7 @@ class marginal_result:
 
     def __init__(self, jp, k, mu, sigma, itp):
         self._jp, self._k = jp, k
+        self._batch = getattr(jp, "_marginal_batch", 0) if jp is not None else 0
         self.mu, self.sigma, self.itp = float(mu), float(sigma), itp
         self._wv = None
 
@@ -53,6 +54,9 @@ class marginal_result:
         if self._wv is None:
             if self._jp is None:
                 raise RuntimeError("sorted weights/values are not available for this marginal")
+            if getattr(self._jp, "_marginal_batch", 0) != self._batch:
+                raise RuntimeError("the sorted weights/values of this marginal were replaced by a later marginal / fit call on "
+                                   "the same posterior; ask for `wv` before the next call (or compute the marginal again)")
             M = self._jp.n_nodes
             sv, sw, cw = np.zeros(M), np.zeros(M), np.zeros(M)
             check(lib().jp_marginal_sorted(self._jp.handle, C.c_int(self._k), ptr(sv), ptr(sw), ptr(cw)))
@@ -152,6 +156,7 @@ def marginals(jp, fs):
     """Batched marginal(jp, f) for a list of functions: one library call per kind (device / host)."""
     fs = list(fs)
     out = [None] * len(fs)
+    jp._marginal_batch = getattr(jp, "_marginal_batch", 0) + 1      # results of earlier batches lose their device-side sorted arrays
     coords, host = _classify(jp, fs)
     L = lib()
     if coords:

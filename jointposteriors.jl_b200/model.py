@@ -244,7 +244,19 @@ def _native_mode(M, ddata, x0, glm):
     code = np.ascontiguousarray(M.transform, dtype=np.int32)
     check(lib().jp_mode(ddata.ctx.handle, ddata.handle, C.c_int(d), ptr(code), C.c_int(1 if glm else 0), ptr(x), ptr(H),
                         C.byref(neg_min), C.byref(evals)))
+    _warn_unless_converged("mode")
     return x, np.array(H), neg_min.value
+
+
+def _warn_unless_converged(who):
+    """jp_mode_report: a search that stopped at its iteration cap or after a failed line search still returns its last point;
+    say so instead of silently centring the grid there."""
+    import warnings
+    g, it, ok = C.c_double(), C.c_int(), C.c_int()
+    lib().jp_mode_report(C.byref(g), C.byref(it), C.byref(ok))
+    if not ok.value:
+        warnings.warn("%s: the mode search did not converge (%d iterations, gradient infinity norm %.3g); the grid is centred on "
+                      "its last point" % (who, it.value, g.value), RuntimeWarning, stacklevel=3)
 
 
 def deduce_scale(M, H):
@@ -319,6 +331,7 @@ class JointPosterior:
         check(lib().jp_fit(self.handle, C.byref(self._args)))
         self._theta = self._density = None
         self._theta_gen += 1
+        self._marginal_batch = getattr(self, "_marginal_batch", 0) + 1
         return self
 
     @property
