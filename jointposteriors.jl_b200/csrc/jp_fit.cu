@@ -857,7 +857,10 @@ int jp_fit_p2p(jp_posterior* post, const jp_fit_args* args, jp_comm* comm) {
   if (path == JP_PATH_AUTO) path = jp_fit_tc_supported(post, args) ? JP_PATH_TC : JP_PATH_FP64;
   if (path == JP_PATH_TC) JP_TRY(jp_fit_tc_launch_dev(post, args, comm, 0));
   else JP_TRY(jp_fit_fp64_launch(post, args, false));
-  if (comm->world == 1) return jp_stage4_launch(post, true, post->d_stats);
+  if (comm->world == 1) {
+    JP_TRY(jp_stage4_launch(post, true, post->d_stats));
+    return getenv("JP_NO_DENSITY_PREFETCH") ? JP_OK : jp_density_prefetch(post);
+  }
   JP_TRY(jp_stage4_launch(post, false, post->d_stats));      // finish + local max + sum relative to it
   const double* g = nullptr;
   JP_TRY(jp_comm_exchange(comm, JP_CH_STATS, post->d_stats, 2, &g));
@@ -867,7 +870,7 @@ int jp_fit_p2p(jp_posterior* post, const jp_fit_args* args, jp_comm* comm) {
     JP_CHECK_LAUNCH(post->ctx);
   }
   JP_MARK(post->ctx, "fit:normalised");
-  return JP_OK;
+  return getenv("JP_NO_DENSITY_PREFETCH") ? JP_OK : jp_density_prefetch(post);
 }
 
 // OBSERVATION-sharded fit (the alternative to node sharding): `post` covers ALL grid nodes, its data handle holds
@@ -889,7 +892,8 @@ int jp_fit_p2p_obs(jp_posterior* post, const jp_fit_args* args, jp_comm* comm) {
   post->K_last = 0;
   post->cmom_valid = false;
   JP_TRY(jp_fit_tc_launch_dev(post, args, comm, 1));
-  return jp_stage4_launch(post, true, post->d_stats);
+  JP_TRY(jp_stage4_launch(post, true, post->d_stats));
+  return getenv("JP_NO_DENSITY_PREFETCH") ? JP_OK : jp_density_prefetch(post);      // as jp_fit: the weights start their way to the host
 }
 
 int jp_fit_p2p_check(jp_posterior* post) {
