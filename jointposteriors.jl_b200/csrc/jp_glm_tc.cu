@@ -44,6 +44,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <type_traits>
 #include "jp_common.cuh"
 #include "jp_fold_tables.h"
 
@@ -56,7 +57,14 @@ int jp_glm_num_blocks(const jp_ctx* ctx, long long N);
 #define TC_OBS_TILE 128          // MMA M: observations per tile (TMEM lanes)
 #define TC_PAIR_TILE 96          // MMA N: mirror pairs of grid nodes per tile (TMEM columns)
 #define TC_TMEM_STRIDE 96        // columns between accumulator buffers
+#ifndef TC_RING_UNROLL
+#define TC_RING_UNROLL 1         // epilogue tile loop unrolled over the accumulator ring (compile-time buffer indices)
+#endif
+#if TC_RING_UNROLL
+#define TC_NBUF 4                // accumulator buffers in TMEM (4 x 96 of the 512 columns): a power of two, see the epilogue
+#else
 #define TC_NBUF 5                // accumulator buffers in TMEM (5 x 96 of the 512 columns)
+#endif
 #define TC_COLS_PER_WARP 32      // each epilogue warp owns one lane quarter x one third of the pair columns
 #define TC_EPI_WARPS (4 * TC_PAIR_TILE / TC_COLS_PER_WARP)   // 12: three per SM sub-partition
 #define TC_KATOM 32              // fp32 elements per 128-byte swizzle atom
@@ -757,7 +765,11 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
   // its TMA load until the epilogue has consumed its accumulator, i.e. across the observation ring AND the TMEM
   // buffers, hence stages + TC_NBUF slots (a slot is reused only after empty[stage] of a tile `stages` later,
   // which the MMA issuer signals after waiting for tempty of a tile TC_NBUF earlier still)
+#if TC_RING_UNROLL
+  const int n_cslots = ((P.stages + TC_NBUF + 3) / 4) * 4;      // whole groups of four (the epilogue's unrolled ring)
+#else
   const int n_cslots = P.stages + TC_NBUF;
+#endif
   const uint32_t c_bytes = (uint32_t)NC * TC_OBS_TILE * 4u;
   const uint32_t sC = sA + (uint32_t)P.stages * a_bytes;
   double* red = reinterpret_cast<double*>(gen + (size_t)P.nbbuf * b_bytes + (size_t)P.stages * a_bytes +
@@ -897,6 +909,122 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
     }
   } else {
     // ===================================================== epilogue warps
+#if TC_RING_UNROLL
+    // The accumulator ring has FOUR buffers and the tile loop is unrolled by four, entered at the buffer the CTA's running tile
+    // count points at (Duff's device): TMEM addresses, barrier addresses and the coefficient-set ping-pong are compile-time in
+    // every copy of the step, the phase parity flips and the coefficient-slot group advances once per round of four tiles.
+    // (With five buffers and run-time ring indices the step carried ~20 uniform-datapath instructions per tile and warp; every
+    // one of them costs an issue slot the packed FP32 operations cannot hide.)
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int h = (warp - 2) >> 2;           // column third handled by this warp
+    const int et = threadIdx.x - 64;         // 0 .. TC_EPI_THREADS - 1
+    uint64_t accE[TC_COLS_PER_WARP / 2], accO[TC_COLS_PER_WARP / 2];   // FP32 sums, packed in pairs of adjacent columns
+#pragma unroll
+    for (int j = 0; j < TC_COLS_PER_WARP / 2; ++j) accE[j] = accO[j] = 0ull;
+    int ntile = 0;                           // tiles this CTA has consumed: buffer = ntile & 3, round parity = (ntile >> 2) & 1
+    uint32_t par = 0;                        // phase parity of the current round of accumulator buffers
+    uint32_t cgrp = 0;                       // byte offset of the current group of four coefficient slots
+    const uint32_t cgrp_end = (uint32_t)(n_cslots / 4) * 4u * c_bytes;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * TC_COLS_PER_WARP);
+    const uint32_t coef_addr = sC + (uint32_t)(q * 32 + lane) * 4u;   // this thread's observation: tile row = TMEM lane
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int chunk = item / P.n_pair_tiles, pair_tile = item % P.n_pair_tiles;
+      const int t0 = chunk * P.tiles_per_chunk, t1 = min(P.n_obs_tiles, t0 + P.tiles_per_chunk);
+      uint32_t va[TC_LDW], vb[TC_LDW];
+      float ca[NC], cb[NC];
+      auto load_coef = [&](float (&dst)[NC], uint32_t slot_addr) {
+#pragma unroll
+        for (int k = 0; k < NC; ++k)
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dst[k]) : "r"(slot_addr + (uint32_t)k * TC_OBS_TILE * 4u));
+      };
+      int t = t0;
+      // one tile in accumulator buffer B (compile-time); cc = its coefficients, cn receives the next tile's
+      auto tile_step = [&](auto Bc, const float (&cc)[NC], float (&cn)[NC]) {
+        constexpr int B = decltype(Bc)::value, NB = (B + 1) & 3;
+        const bool more = t + 1 < t1;
+        const uint32_t taddr = lane_addr + (uint32_t)(B * TC_TMEM_STRIDE);
+        const uint32_t npar = (B == 3) ? (par ^ 1u) : par;                     // parity of the next tile's phase
+        const uint32_t ncg = (B == 3) ? ((cgrp + 4u * c_bytes == cgrp_end) ? 0u : cgrp + 4u * c_bytes) : cgrp;
+#if TC_EARLY_PEEK
+        const bool ready = more && mbar_test_wait(bar_tfull + 8u * NB, npar);
+#else
+        const bool ready = false;
+#endif
+#pragma unroll
+        for (int c = 0; c < TC_COLS_PER_WARP / TC_LDW; ++c) {
+          uint32_t(&cur)[TC_LDW] = (c & 1) ? vb : va;
+          uint32_t(&nxt)[TC_LDW] = (c & 1) ? va : vb;
+          tmem_ld_wait(cur);
+          if (c + 1 < TC_COLS_PER_WARP / TC_LDW) {
+            if (MODE != 2 && MODE != 4) tmem_ld(nxt, taddr + (uint32_t)(TC_LDW * (c + 1)));
+          } else {
+            // every tcgen05.ld of this tile has completed: hand the accumulator buffer back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8u * B);
+            if (more) {
+              if (warp == 2 && lane == 0) TC_STAMP(3, ntile + 1);
+              if (!ready) mbar_wait(bar_tfull + 8u * NB, npar);
+              if (warp == 2 && lane == 0) TC_STAMP(4, ntile + 1);
+              tc_fence_after();
+              if (MODE != 2 && MODE != 4) tmem_ld(nxt, lane_addr + (uint32_t)(NB * TC_TMEM_STRIDE));
+              load_coef(cn, coef_addr + ncg + (uint32_t)NB * c_bytes);
+            }
+          }
+          tc_accumulate<NC, MODE, TC_LDW>(cur, cc, accE + c * (TC_LDW / 2), accO + c * (TC_LDW / 2));
+        }
+        if (B == 3) {
+          par ^= 1u;
+          cgrp = ncg;
+        }
+        ++ntile;
+        ++t;
+      };
+      // first tile of the item
+      {
+        const int b0 = ntile & 3;
+        if (warp == 2 && lane == 0) TC_STAMP(3, ntile);
+        mbar_wait(bar_tfull + 8u * b0, par);
+        if (warp == 2 && lane == 0) TC_STAMP(4, ntile);
+        tc_fence_after();
+        tmem_ld(va, lane_addr + (uint32_t)(b0 * TC_TMEM_STRIDE));
+        if (b0 & 1) load_coef(cb, coef_addr + cgrp + (uint32_t)b0 * c_bytes);
+        else load_coef(ca, coef_addr + cgrp + (uint32_t)b0 * c_bytes);
+        switch (b0) {
+          for (;;) {
+            case 0: tile_step(std::integral_constant<int, 0>(), ca, cb); if (t == t1) break;
+            case 1: tile_step(std::integral_constant<int, 1>(), cb, ca); if (t == t1) break;
+            case 2: tile_step(std::integral_constant<int, 2>(), ca, cb); if (t == t1) break;
+            case 3: tile_step(std::integral_constant<int, 3>(), cb, ca); if (t == t1) break;
+          }
+        }
+      }
+      // flush the item: sum over the 32 observation lanes by transpose-reduce, over the 4 lane quarters in
+      // shared memory (FP64), one (even, odd) partial per (chunk, pair)
+      {
+        float col[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f32x2_unpack(accE[j], col[2 * j], col[2 * j + 1]);
+        const float sE = tc_transpose_reduce32(col, lane);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f32x2_unpack(accO[j], col[2 * j], col[2 * j + 1]);
+        const float sO = tc_transpose_reduce32(col, lane);
+        double* r = red + ((size_t)q * TC_PAIR_TILE + h * TC_COLS_PER_WARP + lane) * 2;
+        r[0] = (double)sE;
+        r[1] = (double)sO;
+      }
+      epi_bar_sync();
+      if (et < 2 * TC_PAIR_TILE) {
+        const double s = (red[et] + red[2 * TC_PAIR_TILE + et]) + (red[4 * TC_PAIR_TILE + et] + red[6 * TC_PAIR_TILE + et]);
+        const long long pair = (long long)pair_tile * TC_PAIR_TILE + (et >> 1);
+        if (pair < P.P) P.part[((size_t)chunk * P.P + pair) * 2 + (et & 1)] = s;
+      }
+      epi_bar_sync();
+#pragma unroll
+      for (int j = 0; j < TC_COLS_PER_WARP / 2; ++j) accE[j] = accO[j] = 0ull;
+    }
+  }
+#else
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int h = (warp - 2) >> 2;           // column third handled by this warp
     const int et = threadIdx.x - 64;         // 0 .. TC_EPI_THREADS - 1
@@ -1005,6 +1133,7 @@ __device__ __forceinline__ void tc_kernel_body(const CUtensorMap& tmA, const CUt
       for (int j = 0; j < TC_COLS_PER_WARP / 2; ++j) accE[j] = accO[j] = 0ull;
     }
   }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -1419,7 +1548,7 @@ static int tc_run_kernel(jp_posterior* post, const jp_fit_args* args, int NC, bo
   kp.n_obs_tiles = (int)((ds->N + TC_OBS_TILE - 1) / TC_OBS_TILE);   // tiles past the data (slice padding) hold zeros: skipped
   const size_t b_bytes = (size_t)kp.kb * TC_PAIR_TILE * 128, a_bytes = (size_t)kp.ka * TC_OBS_TILE * 128;
   const size_t c_bytes = (size_t)NC * TC_OBS_TILE * 4;      // coefficient slot of one tile
-  const size_t budget = 220 * 1024, misc = 1024 + 4 * TC_PAIR_TILE * 2 * 8 + 256 + TC_NBUF * c_bytes;
+  const size_t budget = 220 * 1024, misc = 1024 + 4 * TC_PAIR_TILE * 2 * 8 + 256 + (TC_NBUF + 3) * c_bytes;   // (+3: slot count rounded up to a multiple of four)
   // two pair-operand buffers unless that would push the observation ring below three stages
   kp.nbbuf = ((budget - misc - 2 * b_bytes) / (a_bytes + c_bytes) >= 3) ? 2 : 1;
   const size_t fixed = misc + (size_t)kp.nbbuf * b_bytes;

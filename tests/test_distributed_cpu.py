@@ -204,3 +204,36 @@ def test_shard_bounds(jp):
         assert max(sizes) - min(sizes) <= 2
         # interior cuts are odd: a mirror pair of nodes (2j-1, 2j) never straddles two ranks
         assert all(b % 2 == 1 or b in (0, M) for b, _ in cuts[1:])
+
+
+def test_sharding_geometry_of_the_in_library_exchanges():
+    """Host-side geometry of the jp_comm protocols (no GPU): row slices cover the observations exactly once, the bulk-region sizes
+    bound what the kernels store (12 coefficient rows of whole 128-observation tiles per rank for node sharding, one (even, odd)
+    pair per mirror pair of nodes and rank for observation sharding), and GLM models are recognised for observation sharding."""
+    import __graft_entry__ as entry
+    jp = entry.load_package()
+    from jointposteriors_jl_b200 import distributed as D
+    for N, world in ((100000, 8), (30001, 3), (7, 4), (128, 2)):
+        cover = []
+        for r in range(world):
+            b, e, n_loc = D.row_slice(N, r, world)
+            assert 0 <= b <= e <= N and e - b <= n_loc
+            cover.extend(range(b, e))
+        assert cover == list(range(N))
+        tiles = -(-N // 128)
+        n_loc_tiles = -(-tiles // world)
+        assert D.bulk_bytes_for(N, world) == world * 12 * n_loc_tiles * 128 * 4
+        assert D.bulk_bytes_for(N, world) >= 12 * 4 * N                      # room for every observation's 12 coefficients
+    for M in (495, 115145, 189161):
+        assert D.bulk_bytes_obs(M, 8) == 8 * ((M >> 1) + 1) * 16            # pairs (z, -z) plus the origin
+    X = np.ones((10, 3))
+    y = np.zeros(10)
+    assert D.glm_obs_shardable(jp.Model((jp.RealVector(3),)), jp.LogisticData(X, y))
+    assert D.glm_obs_shardable(jp.Model((jp.RealVector(3),)), jp.PoissonData(X, y))
+    assert not D.glm_obs_shardable(jp.Model((jp.RealVector(2), jp.PositiveVector(1))), jp.NormalLinearData(X[:, :2], y))
+    assert not D.glm_obs_shardable(jp.Model((jp.RealVector(2), jp.PositiveVector(1))), jp.LogisticData(X, y))
+    # mirror pairs never straddle a node cut
+    for M, world in ((115145, 8), (495, 3), (45201, 8)):
+        cuts = [D.shard_bounds(M, r, world) for r in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == M and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+        assert all(c[0] % 2 == 1 or c[0] == 0 for c in cuts)
