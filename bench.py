@@ -11,9 +11,12 @@ src/joint_posterior.jl:157-162; the grid build and the mode finder are timed onc
   value  whole-job (node x obs pairs) / s with observations resident in HBM, CUDA-event timed, max over ranks
   e2e    same metric through the public API with HOST buffers: jp_data_upload of the observation records
          (H2D), fit, marginals, and the D2H of the results, all inside the timed region
-Multi-GPU (torchrun, one rank per GPU): WEAK scaling -- the grid nodes are sharded across ranks and the
-observation count grows with the rank count (N_obs = n_gpus x base), so per-GPU work is fixed; the only
-collectives are the tiny all_gathers of jointposteriors.jl_b200/distributed.py.
+Multi-GPU (torchrun, one rank per GPU): WEAK scaling -- the observation count grows with the rank count (N_obs = n_gpus x
+base) and the OBSERVATIONS are sharded (--shard obs, default: every rank keeps its rows and evaluates all nodes on them) or the
+grid nodes (--shard nodes); per-GPU work is fixed either way.  The exchanges are kernels of the library that store into the
+peers' memory over NVLink (csrc/jp_comm.cu); JP_NO_P2P=1 runs the node-sharded protocol with NCCL all_gathers through
+torch.distributed instead.  The `strong` object of the line runs north_star's fixed-size configs (cfg5, cfg4) node-sharded on
+the same ranks.
 """
 import argparse
 import json
