@@ -571,3 +571,64 @@ def test_precise_observation_sums(O):
         O.set_precise(True)
     assert abs(precise - exact) <= 4 * np.spacing(abs(exact))
     assert abs(plain - exact) < 1e-7 and abs(O.log_density_unc(1, [0] * d, x, obs, hyper) - precise) == 0.0
+
+
+def test_normal_linear_d10_against_semi_analytic_truth(O):
+    """An independent anchor for stages 1-4 at d = 10 (the dimension of BASELINE config 3): README Example 2's normal linear model
+    (reference README.md:245-258) with 9 coefficients and sigma.  Given sigma the coefficient posterior is Gaussian in closed form,
+    so E[beta], Var[beta] and the moments of sigma follow from ONE 1-D integral over sigma (done here by dense Gauss-Legendre
+    quadrature of the closed-form marginal likelihood) -- no sparse grid, no sampling.  The oracle's level-5 / level-6 Smolyak
+    posteriors must converge to it."""
+    from conftest import cpu_mode
+    rng = np.random.default_rng(17)
+    n, p = 60, 9
+    X = rng.standard_normal((n, p))
+    X[:, 0] = 1.0
+    beta_true = rng.standard_normal(p) * 0.5
+    y = X @ beta_true + 0.8 * rng.standard_normal(n)
+    sd_b, sd_s = 10.0, 1.0
+    obs, hyper = np.ascontiguousarray(np.column_stack([X, y])), np.array([sd_b, sd_s])
+    code = np.array([0] * p + [1], dtype=np.int32)
+    # ---- semi-analytic truth: integrate over sigma
+    XtX, Xty, yty = X.T @ X, X.T @ y, y @ y
+
+    def given_sigma(s):
+        A = XtX / s ** 2 + np.eye(p) / sd_b ** 2            # posterior precision of beta | sigma
+        L = np.linalg.cholesky(A)
+        m = np.linalg.solve(A, Xty / s ** 2)
+        # log marginal likelihood of y given sigma (beta integrated out) + log prior of sigma (normal(0, sd_s) on sigma > 0)
+        lml = -n * np.log(s) - 0.5 * yty / s ** 2 + 0.5 * (Xty / s ** 2) @ m - np.sum(np.log(np.diag(L))) - 0.5 * (s / sd_s) ** 2
+        return lml, m, np.linalg.inv(A)
+    gx, gw = np.polynomial.legendre.leggauss(400)
+    lo, hi = 0.3, 2.5
+    ss = 0.5 * (hi - lo) * gx + 0.5 * (hi + lo)
+    ww = 0.5 * (hi - lo) * gw
+    vals = [given_sigma(s) for s in ss]
+    l = np.array([v[0] for v in vals])
+    wt = ww * np.exp(l - l.max())
+    wt /= wt.sum()
+    assert wt[0] < 1e-12 and wt[-1] < 1e-12                   # the sigma range holds the whole posterior
+    Eb = sum(w * v[1] for w, v in zip(wt, vals))
+    Ebb = sum(w * (v[2] + np.outer(v[1], v[1])) for w, v in zip(wt, vals))
+    sd_beta = np.sqrt(np.diag(Ebb) - Eb ** 2)
+    Es, Ess = np.sum(wt * ss), np.sum(wt * ss ** 2)
+    # ---- the oracle's sparse-grid posterior
+    x0 = np.concatenate([np.linalg.lstsq(X, y, rcond=None)[0], [np.log(0.8)]])
+    x, H, f = cpu_mode(O, 4, code, obs, hyper, x0)
+    U = O.inv_chol(2 * H)
+    errs = []
+    for Lv in (5, 6):
+        idx, w = O.smolyak(0, p + 1, Lv)
+        ref = O.eval_grid(0, 4, code, idx, w, x, U, f, obs, hyper, want_theta=True)
+        t, dens = ref["theta"], ref["density"]
+        mu = np.array([O.marginal(t[k], dens)["mu"] for k in range(p + 1)])
+        sg = np.array([O.marginal(t[k], dens)["sigma"] for k in range(p + 1)])
+        errs.append((np.max(np.abs(mu[:p] - Eb) / sd_beta), abs(mu[p] - Es) / Es, np.max(np.abs(sg[:p] - sd_beta) / sd_beta),
+                     abs(sg[p] - np.sqrt(Ess - Es ** 2)) / np.sqrt(Ess - Es ** 2)))
+    print("normal linear d=10: (mean beta in sd, mean sigma, sd beta, sd sigma) rel. errors at levels 5, 6:", errs)
+    # the coefficients (near-Gaussian directions) are resolved to a fraction of a per cent of their posterior sd; sigma, whose
+    # posterior is skewed and couples with every coefficient's curvature, converges slowly at these levels -- the behaviour the
+    # reference's README reports for its own sparse-grid quantiles (README.md:404-405) -- but it does converge
+    assert errs[0][0] < 1e-3 and errs[1][0] < 1e-3
+    assert errs[0][2] < 0.25 and errs[1][2] < 0.8 * errs[0][2]             # second moments carry sigma's uncertainty: slower
+    assert errs[0][1] < 0.08 and errs[1][1] < 0.8 * errs[0][1] and errs[0][3] < 0.3 and errs[1][3] < 0.8 * errs[0][3]
