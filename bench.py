@@ -409,6 +409,21 @@ def run_product(args):
     # (each rank a node block, all observations on every rank).
     obs_mode = world > 1 and args.shard == "obs" and args.emulate_shard <= 1 and D.glm_obs_shardable(M, data) and path != _lib.PATH_FP64
     comm = None
+    comm_note = None
+    if obs_mode:
+        # the in-library exchanges need CUDA IPC + peer access between the ranks' GPUs; without them (agreed on by all ranks) the
+        # line falls back to the node-sharded protocol with NCCL all_gathers and says so
+        try:
+            comm = D.comm_for(ctx, 0, None, min_bulk=1 << 24)
+            ok = comm is not None
+        except Exception as ex:      # noqa: BLE001
+            ok, comm_note = False, "in-library exchanges unavailable (%s): node-sharded NCCL protocol" % str(ex)[:120]
+        flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag.cpu()[0]) < 1.0:
+            obs_mode, comm = False, None
+            os.environ["JP_NO_P2P"] = "1"
+            comm_note = comm_note or "in-library exchanges unavailable on a peer rank: node-sharded NCCL protocol"
     rows = D.row_slice(obs.shape[0], rank, world)[:2]
     # ---- one-time setup: data upload, mode, grid build (timed, reported, not part of the step)
     t0 = time.perf_counter()
@@ -419,10 +434,6 @@ def run_product(args):
         dd = ctx.upload(data)
     ctx.sync()
     t_up = time.perf_counter() - t0
-    if obs_mode:
-        comm = D.comm_for(ctx, 0, None, min_bulk=1 << 24)
-        if comm is None:
-            raise SystemExit("bench.py: --shard obs needs the in-library exchanges (JP_NO_P2P is set?)")
     t0 = time.perf_counter()
     x, U, neg_min = D.mode_p2p(M, dd, comm) if obs_mode else jp.mode(M, dd)
     t_mode = time.perf_counter() - t0
@@ -724,6 +735,8 @@ def run_product(args):
                                             else "node-sharded x%d" % world) if args.emulate_shard <= 1 else
                                "DIAGNOSTIC: node block of rank 0 of %d on one GPU" % args.emulate_shard, path="tc" if path_used == _lib.PATH_TC else "fp64",
                                prep=("observation-sharded-p2p" if obs_mode else getattr(loc, "last_prep", "replicated")) if world > 1 else "single",
+                               exchanges=comm_note or ("in-library kernels over NVLink peer memory (csrc/jp_comm.cu)" if world > 1 and not os.environ.get("JP_NO_P2P") else
+                                                       ("NCCL all_gathers through torch.distributed" if world > 1 else "none")),
                                l2="256 MiB flush buffer written between timed iterations",
                                marginals="%d coordinate marginals per step (moments + 100-knot Grid CDF)" % d),
                    fit_ms=tot_fit_ms / args.steps, marginal_ms=tot_marg_ms / args.steps, grid_build_ms=t_grid,

@@ -162,11 +162,14 @@ class Comm:
 
     def __init__(self, ctx, rank, world, bulk_bytes=0, group=None, exchange=None):
         h = C.c_void_p()
-        check(lib().jp_comm_create(ctx.handle, C.c_int(rank), C.c_int(world), C.c_longlong(int(bulk_bytes)), C.byref(h)))
-        self.handle, self.ctx, self.rank, self.world, self.group = h, ctx, int(rank), int(world), group
+        rc = lib().jp_comm_create(ctx.handle, C.c_int(rank), C.c_int(world), C.c_longlong(int(bulk_bytes)), C.byref(h))
+        self.handle, self.ctx, self.rank, self.world, self.group = (h if rc == 0 else None), ctx, int(rank), int(world), group
         if world > 1:
+            # a rank whose mailbox could not be created still takes part in the handle exchange (with an empty handle), so
+            # that every rank of the group fails together instead of the others waiting in the collective
             buf = (C.c_ubyte * 64)()
-            check(lib().jp_comm_ipc_handle(h, buf))
+            if rc == 0:
+                rc = lib().jp_comm_ipc_handle(h, buf)
             if exchange is None:
                 import torch.distributed as dist
 
@@ -174,11 +177,15 @@ class Comm:
                     out = [None] * world
                     dist.all_gather_object(out, mine, group=group)
                     return out
-            handles = exchange(bytes(buf))
+            handles = exchange(bytes(buf) if rc == 0 else b"")
+            check(rc)
             blob = b"".join(handles)
             if len(blob) != 64 * world:
-                raise ValueError("Comm: expected %d handles of 64 bytes" % world)
+                self.destroy()
+                raise ValueError("Comm: expected %d handles of 64 bytes (a peer rank could not create its mailbox)" % world)
             check(lib().jp_comm_connect_ipc(h, C.c_char_p(blob)))
+        else:
+            check(rc)
 
     @property
     def bulk_bytes(self):
