@@ -12,6 +12,8 @@
 int jp_glm_grad_hess_comm(jp_ctx* ctx, const jp_data* data, jp_comm* comm, int d, const double* h_beta, double* h_g, double* h_Hneg,
                           double* h_logpost);
 
+int jp_mode_dev_try(jp_ctx* ctx, const jp_data* data, int d, const int* h_transform, double* h_x, double* h_H, double* fx,
+                    int iters, int* evals, int* iterations, int* converged, double* grad, int* used);      // jp_mode_dev.cu
 static thread_local char g_err[1024] = "";
 
 void jp_set_error(const char* fmt, ...) {
@@ -544,9 +546,16 @@ int jp_mode(jp_ctx* ctx, const jp_data* data, int d, const int* h_transform, int
       }
     s = mode_glm(ctx, data, nullptr, d, h_x, h_H, neg_min, &n_eval, 60);
   } else {
-    ModeProblem P(ctx, data, d, h_transform);
-    s = mode_generic(P, h_x, h_H, neg_min, 100);
-    n_eval = P.evals;
+    // small models: the whole search as one kernel launch (jp_mode_dev.cu); otherwise, or if that did not converge, the same
+    // iteration driven from here with one batched evaluation per step
+    int used = 0;
+    s = jp_mode_dev_try(ctx, data, d, h_transform, h_x, h_H, neg_min, 100, &n_eval, &g_mode_iterations, &g_mode_converged,
+                        &g_mode_grad, &used);
+    if (s == JP_OK && !used) {
+      ModeProblem P(ctx, data, d, h_transform);
+      s = mode_generic(P, h_x, h_H, neg_min, 100);
+      n_eval += P.evals;
+    }
   }
   if (evals) *evals = n_eval;
   return s;

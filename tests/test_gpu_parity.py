@@ -292,6 +292,40 @@ def test_gpu_mode_matches_cpu_mode(jp, O, gpu_ctx):
                             Hs.ctypes.data_as(C.c_void_p), C.byref(fmin), C.byref(evals)) == 1
 
 
+@pytest.mark.parametrize("case", [0, 3, 4, 5, 6, 7], ids=[FAMILY_CASES[c][0] for c in (0, 3, 4, 5, 6, 7)])
+def test_one_launch_mode_search_matches_host_driven(jp, gpu_ctx, case, monkeypatch):
+    """jp_mode of a small non-GLM model runs the whole saddle-free Newton search inside one kernel (csrc/jp_mode_dev.cu); the
+    host-driven iteration (JP_MODE_HOST=1: one batched evaluation per step) must arrive at the same mode, Hessian and minimum,
+    and the one-launch path must have been the one that ran (1 kernel launch for the whole search)."""
+    name, family, code, obs, hyper = FAMILY_CASES[case]
+    d = len(code)
+    dd = _upload(jp, gpu_ctx, family, obs, hyper)
+    codes = np.array(code, dtype=np.int32)
+    x0 = np.zeros(d)
+
+    def run():
+        x, H = x0.copy(), np.zeros((d, d), order="F")
+        fmin, evals = C.c_double(), C.c_int()
+        n0 = gpu_ctx.launches()
+        assert jp.lib().jp_mode(gpu_ctx.handle, dd.handle, d, codes.ctypes.data_as(C.c_void_p), 0, x.ctypes.data_as(C.c_void_p),
+                                H.ctypes.data_as(C.c_void_p), C.byref(fmin), C.byref(evals)) == 0
+        g, it, ok = C.c_double(), C.c_int(), C.c_int()
+        jp.lib().jp_mode_report(C.byref(g), C.byref(it), C.byref(ok))
+        return x, np.array(H), fmin.value, evals.value, gpu_ctx.launches() - n0, g.value, it.value, ok.value
+
+    xd, Hd, fd, ed, ld, gd, itd, okd = run()
+    monkeypatch.setenv("JP_MODE_HOST", "1")
+    xh, Hh, fh, eh, lh, gh, ith, okh = run()
+    monkeypatch.delenv("JP_MODE_HOST")
+    assert okh == 1 and okd == 1, (name, okd, okh, gd, gh)
+    assert ld == 1 and lh >= 2 * eh, (name, ld, lh, eh)          # one launch against two per evaluation
+    assert abs(fd - fh) <= 1e-9 * (1 + abs(fh)), (name, fd, fh)
+    scale = 1.0 / np.sqrt(np.abs(np.diag(Hh)))                    # a coordinate's posterior scale: the mode agrees far inside it
+    assert np.max(np.abs(xd - xh) / scale) < 1e-4, (name, xd, xh)
+    assert np.allclose(Hd, Hh, rtol=1e-4, atol=1e-6 * np.max(np.abs(Hh))), (name, Hd, Hh)
+    assert np.allclose(Hd, Hd.T)
+
+
 def test_adopted_device_records(jp, O, gpu_ctx):
     """jp_data_adopt_device: records already on the GPU (what Context.upload_sharded builds from the NVLink all_gather)
     give bit-identical results to jp_data_upload of the same host array; host pointers are refused."""
