@@ -187,6 +187,9 @@ int jp_glm_grad_hess(jp_ctx* ctx, const jp_data* data, int d, const double* h_be
  * posterior mode by Newton iterations driven from native host code, every function / derivative evaluation one
  * batched GPU call.  glm != 0 (LOGISTIC / POISSON with unconstrained coefficients): analytic score and information
  * (jp_glm_grad_hess); glm == 0: saddle-free Newton on Richardson finite differences of jp_log_density_points.
+ * Small models (d <= 16, records <= 32 KB: the reference's own examples) run the whole glm == 0 search inside ONE launch of
+ * a thread-block cluster (csrc/jp_mode_dev.cu) and fall back to the host-driven iteration if that does not converge;
+ * environment: JP_MODE_HOST=1 forces the host-driven iteration, JP_MODE_TRACE=1 prints the kernel's cycle account.
  * h_x: in = start, out = mode; h_H: d x d Hessian of the NEGATIVE log-density at the mode (what `mode` doubles and
  * hands to deduce_scale!, :167); *neg_min: the minimised objective (:166); *evals: GPU evaluations used. */
 int jp_mode(jp_ctx* ctx, const jp_data* data, int d, const int* h_transform, int glm, double* h_x, double* h_H,

@@ -33,6 +33,7 @@ namespace cg = cooperative_groups;
 
 struct JpModeDevParams {
   int d, ncols, iters, K, n, S;       // n = stencil points per step size, K = 1 + 2 n, S = observation slices per point
+  int split;                          // 1: independent coordinate transforms only, shared out over a point's S lanes
   long long N;
   double h;
   const double* obs;                  // N x ncols (device)
@@ -53,9 +54,10 @@ struct MdShared {
   unsigned char pi[JP_MD_DMAX * (JP_MD_DMAX - 1) / 2], pj[JP_MD_DMAX * (JP_MD_DMAX - 1) / 2];
   double rot_a[JP_MD_DMAX], rot_b[JP_MD_DMAX];      // one round of disjoint Jacobi rotations: new col_j = a_j col_j + b_j col_partner(j)
   int rot_p[JP_MD_DMAX];
-  int action, evals, n_eigen, n_values;
+  int action, evals, n_eigen, n_values, imin, split_construct;
   long long cyc_values, cyc_linalg, cyc_derivs, cyc_chol, cyc_eigen;
   int n_sweeps;
+  long long cyc_r1, cyc_r2, cyc_r3, cyc_chk;
 };
 
 enum { MD_STEP = 0, MD_ESCAPE = 1, MD_DONE = 2 };
@@ -78,37 +80,54 @@ __device__ __forceinline__ void md_offset(const MdShared& s, int d, int o, int& 
 // value buffer of EVERY CTA (distributed shared memory); two buffers alternate from call to call, so a fast CTA writing the
 // next evaluation's values never touches what a slower one is still reading.  Returns this call's buffer.
 template <class F, int DPAD>
-__device__ double* md_values(const JpModeDevParams& P, MdShared& s, const double* s_obs, double* s_val2, int kind, const double* xc,
+__device__ __noinline__ double* md_values(const JpModeDevParams& P, MdShared& s, const double* s_obs, double* s_val2, int kind, const double* xc,
                              int count) {
   cg::cluster_group cluster = cg::this_cluster();
   const int S = P.S, W = count * S, d = P.d, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cta = (int)cluster.block_rank(), n_cta = (int)cluster.num_blocks();
   double* s_val = s_val2 + (s.n_values & 1) * (P.K + 1);
   for (int chunk = cta + n_cta * warp; 32 * chunk < W; chunk += n_cta * (JP_MD_THREADS / 32)) {
-    const int item = 32 * chunk + lane, point = item / S, slice = item - point * S;
+    const int item = 32 * chunk + lane, slice = item & (S - 1);
     const bool live = item < W;
+    const int point = live ? item / S : 0;      // lanes past the end shadow point 0: they take part in the shuffles only
+    double th[DPAD];
+#pragma unroll
+    for (int k = 0; k < DPAD; ++k) th[k] = 0.0;
+    if (kind == 0) {
+      int i = -1, j = -1;
+      double si = 0, sj = 0, hh = 0;
+      if (point > 0) {
+        const int o = point - 1;
+        hh = (o < P.n) ? P.h : 0.5 * P.h;
+        md_offset(s, d, o < P.n ? o : o - P.n, i, si, j, sj);
+      }
+#pragma unroll
+      for (int k = 0; k < DPAD; ++k)
+        if (k < d) th[k] = xc[k] + (k == i ? hh * si : (k == j ? hh * sj : 0.0));
+    } else {
+#pragma unroll
+      for (int k = 0; k < DPAD; ++k)
+        if (k < d) th[k] = s.cand[point * JP_MD_DMAX + k];
+    }
+    double lj;
+    if (s.split_construct) {
+      // independent coordinate transforms (real / positive / probability only): the S lanes of a point take the coordinates in
+      // turn and exchange the results -- the critical path is one transform instead of d of them
+      double ljp = 0.0;
+#pragma unroll
+      for (int k = 0; k < DPAD; ++k)
+        if (k < d && (k & (S - 1)) == slice) th[k] = jp_transform(s.code[k], th[k], ljp);
+      const int first = lane & ~(S - 1);
+#pragma unroll
+      for (int k = 0; k < DPAD; ++k)
+        if (k < d) th[k] = __shfl_sync(0xffffffffu, th[k], first + (k & (S - 1)));
+      for (int o = S >> 1; o > 0; o >>= 1) ljp += __shfl_xor_sync(0xffffffffu, ljp, o);
+      lj = ljp;
+    } else {
+      lj = jp_construct<DPAD>(th, d, s.code);
+    }
     double sum = 0.0;
     if (live) {
-      double th[DPAD];
-#pragma unroll
-      for (int k = 0; k < DPAD; ++k) th[k] = 0.0;
-      if (kind == 0) {
-        int i = -1, j = -1;
-        double si = 0, sj = 0, hh = 0;
-        if (point > 0) {
-          const int o = point - 1;
-          hh = (o < P.n) ? P.h : 0.5 * P.h;
-          md_offset(s, d, o < P.n ? o : o - P.n, i, si, j, sj);
-        }
-#pragma unroll
-        for (int k = 0; k < DPAD; ++k)
-          if (k < d) th[k] = xc[k] + (k == i ? hh * si : (k == j ? hh * sj : 0.0));
-      } else {
-#pragma unroll
-        for (int k = 0; k < DPAD; ++k)
-          if (k < d) th[k] = s.cand[point * JP_MD_DMAX + k];
-      }
-      const double lj = jp_construct<DPAD>(th, d, s.code);
       for (long long n = slice; n < P.N; n += S) sum += F::template obs<DPAD>(th, d, s_obs + n * P.ncols, n, P.hyper);
       if (slice == 0) sum += lj;
       if (slice == S - 1) sum += F::template prior<DPAD>(th, d, P.N, P.hyper);      // not on the lane that adds the Jacobian: shorter critical path
@@ -124,7 +143,7 @@ __device__ double* md_values(const JpModeDevParams& P, MdShared& s, const double
 
 // f(xc) and O(h^4) derivatives: the stencils at h and h/2 (FdStencil::derivs + the Richardson combination of jp_hostlinalg.cpp)
 template <class F, int DPAD>
-__device__ void md_richardson(const JpModeDevParams& P, MdShared& s, const double* s_obs, double* s_val2, const double* xc,
+__device__ __noinline__ void md_richardson(const JpModeDevParams& P, MdShared& s, const double* s_obs, double* s_val2, const double* xc,
                               double* f0, double* g, double* H) {
   const long long c_begin = clock64();
   const double* s_val = md_values<F, DPAD>(P, s, s_obs, s_val2, 0, xc, P.K);
@@ -167,7 +186,7 @@ __device__ __forceinline__ double md_max_abs(const double* v, int n) {
 
 // Newton step by warp 0: Cholesky H = L L' with lane r holding row r, then the two triangular solves with the right-hand side in
 // registers; step = -H^-1 g.  false (uniformly) unless every pivot is comfortably positive.
-__device__ bool md_chol_step(MdShared& s, int d) {
+__device__ __noinline__ bool md_chol_step(MdShared& s, int d) {
   const int lane = threadIdx.x;
   const double* H = s.H;
   double* L = s.A;                      // L(r, k) = L[k * d + r]
@@ -206,8 +225,8 @@ __device__ bool md_chol_step(MdShared& s, int d) {
 // Jacobi eigen-decomposition by warp 0 (the role of symmetric_eigen in jp_hostlinalg.cpp) in the PARALLEL ordering: a sweep is
 // m - 1 rounds of a round-robin tournament over the m = d (+1 if odd) indices, the floor(d / 2) disjoint rotations of a round are
 // applied together -- every element of A' = J' A J and V' = V J from four (two) old elements, the lanes share the d^2 elements.
-// Eigenvalues ascending in s.lam, eigenvector i in V[i * d + k], largest entry positive.
-__device__ void md_eigen_warp(MdShared& s, int d) {
+// Eigenvalue i in s.lam[i] (unsorted; s.imin = index of the smallest), its eigenvector in V[i * d + k].
+__device__ __noinline__ void md_eigen_warp(MdShared& s, int d) {
   const int lane = threadIdx.x;
   double* A = s.A;                      // A(r, c) = A[c * d + r]
   double* V = s.V;
@@ -229,38 +248,48 @@ __device__ void md_eigen_warp(MdShared& s, int d) {
   int tp = lane == 0 ? m - 1 : lane % (m - 1), tq = lane == 0 ? 0 : (m - 1 - lane) % (m - 1);
   __syncwarp();
   for (int sweep = 0; sweep < 64; ++sweep) {
+    const long long t_chk = clock64();
     double off = 0.0, diag = 0.0;
-    if (lane < d) {
-      diag = A[lane * d + lane] * A[lane * d + lane];
-      for (int r = 0; r < lane; ++r) off += A[lane * d + r] * A[lane * d + r];
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      off += __shfl_xor_sync(0xffffffffu, off, o);
-      diag += __shfl_xor_sync(0xffffffffu, diag, o);
+    if (d <= 4) {                       // a handful of elements: every lane adds them up itself, cheaper than ten shuffles
+      for (int c = 0; c < d; ++c) {
+        diag += A[c * d + c] * A[c * d + c];
+        for (int r = 0; r < c; ++r) off += A[c * d + r] * A[c * d + r];
+      }
+    } else {
+      if (lane < d) {
+        diag = A[lane * d + lane] * A[lane * d + lane];
+        for (int r = 0; r < lane; ++r) off += A[lane * d + r] * A[lane * d + r];
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        off += __shfl_xor_sync(0xffffffffu, off, o);
+        diag += __shfl_xor_sync(0xffffffffu, diag, o);
+      }
     }
     // off-diagonal norm below 1e-6 of the diagonal's: eigenvalues to ~1e-12 of the largest -- ample for a step direction in a
     // region where the Hessian is indefinite (near the mode the step comes from the Cholesky factor), and for the signs
     if (off <= 1e-12 * diag || off < 1e-300) break;
-    if (lane == 0) s.n_sweeps += 1;
+    if (lane == 0) {
+      s.n_sweeps += 1;
+      s.cyc_chk += clock64() - t_chk;
+    }
     for (int round = 0; round < m - 1; ++round) {
+      const long long t_r0 = clock64();
       if (lane < m / 2) {
         int p = min(tp, tq), q = max(tp, tq);
         if (q < d) {
           double cs = 1.0, sn = 0.0;
           const double apq = A[q * d + p];
           if (apq != 0.0) {
-            // the angle only has to be close to the annihilating one (the next sweep removes what is left), the rotation itself
-            // has to be orthogonal to double precision: tangent from single-precision arithmetic, cosine = (1 + t^2)^-1/2 by two
-            // Newton steps from its single-precision value
-            const float tau = __fdividef((float)(A[q * d + q] - A[p * d + p]), 2.0f * (float)apq);
+            // A dependent FP64 operation costs this single warp ~40 cycles, a single-precision one a fraction of that.  The angle only
+            // has to be CLOSE to the annihilating one (the next sweep removes what is left), so the tangent and the first guess of the
+            // cosine are single-precision arithmetic on the rounded entries; one Newton step in double makes cos^2 + sin^2 = 1 to 1e-14.
+            const float fpq = (float)apq, tau = __fdividef((float)A[q * d + q] - (float)A[p * d + p], 2.0f * fpq);
             float tf = __fdividef(copysignf(1.0f, tau), fabsf(tau) + __fsqrt_rn(fmaf(tau, tau, 1.0f)));
             if (!(fabsf(tf) <= 1.0f)) tf = 0.0f;      // overflow / 0 / 0 in single precision: the element is negligible or the pair degenerate
-            const double t = (double)tf, u = 1.0 + t * t;
-            double c = (double)rsqrtf((float)u);
-            c = c * (1.5 - 0.5 * u * c * c);
-            c = c * (1.5 - 0.5 * u * c * c);
-            cs = c;
-            sn = t * c;
+            const double c0 = (double)rsqrtf(fmaf(tf, tf, 1.0f)), t = (double)tf;
+            const double u = fma(t, t, 1.0);
+            cs = c0 * fma(-0.5 * u, c0 * c0, 1.5);
+            sn = t * cs;
           }
           s.rot_a[p] = cs; s.rot_b[p] = -sn; s.rot_p[p] = q;
           s.rot_a[q] = cs; s.rot_b[q] = sn;  s.rot_p[q] = p;
@@ -275,6 +304,7 @@ __device__ void md_eigen_warp(MdShared& s, int d) {
         }
       }
       __syncwarp();
+      const long long t_r1 = clock64();
       double na[kPerLane], nv[kPerLane];
 #pragma unroll
       for (int e = 0; e < kPerLane; ++e) {
@@ -287,6 +317,7 @@ __device__ void md_eigen_warp(MdShared& s, int d) {
         }
       }
       __syncwarp();
+      const long long t_r2 = clock64();
 #pragma unroll
       for (int e = 0; e < kPerLane; ++e) {
         const int idx = lane + 32 * e;
@@ -296,25 +327,23 @@ __device__ void md_eigen_warp(MdShared& s, int d) {
         }
       }
       __syncwarp();
+      if (lane == 0) {
+        s.cyc_r1 += t_r1 - t_r0;
+        s.cyc_r2 += t_r2 - t_r1;
+        s.cyc_r3 += clock64() - t_r2;
+      }
     }
   }
   __syncwarp();
+  // eigenvalues in the order they ended up on the diagonal (nobody needs them sorted, nor the eigenvectors' signs: the escape
+  // tries both directions); the smallest is found by every lane for itself
+  if (lane < d) s.lam[lane] = A[lane * d + lane];
+  __syncwarp();
   if (lane == 0) {
-    for (int i = 0; i < d; ++i) s.lam[i] = A[i * d + i];
-    for (int i = 0; i < d; ++i) {
-      int best = i;
-      for (int j = i + 1; j < d; ++j)
-        if (s.lam[j] < s.lam[best]) best = j;
-      if (best != i) {
-        double tmp = s.lam[i]; s.lam[i] = s.lam[best]; s.lam[best] = tmp;
-        for (int k = 0; k < d; ++k) { tmp = V[i * d + k]; V[i * d + k] = V[best * d + k]; V[best * d + k] = tmp; }
-      }
-      int big = 0;
-      for (int k = 1; k < d; ++k)
-        if (fabs(V[i * d + k]) > fabs(V[i * d + big])) big = k;
-      if (V[i * d + big] < 0)
-        for (int k = 0; k < d; ++k) V[i * d + k] = -V[i * d + k];
-    }
+    int imin = 0;
+    for (int i = 1; i < d; ++i)
+      if (s.lam[i] < s.lam[imin]) imin = i;
+    s.imin = imin;
   }
   __syncwarp();
 }
@@ -335,11 +364,13 @@ __global__ void __launch_bounds__(JP_MD_THREADS, 1) jp_mode_dev_kernel(const JpM
     int q = 0;
     for (int i = 0; i < d; ++i)
       for (int j = i + 1; j < d; ++j, ++q) { s.pi[q] = (unsigned char)i; s.pj[q] = (unsigned char)j; }
+    s.split_construct = P.split;
     s.evals = 0;
     s.n_eigen = 0;
     s.n_values = 0;
     s.cyc_values = s.cyc_linalg = s.cyc_derivs = s.cyc_chol = s.cyc_eigen = 0;
     s.n_sweeps = 0;
+    s.cyc_r1 = s.cyc_r2 = s.cyc_r3 = s.cyc_chk = 0;
   }
   cg::this_cluster().sync();      // every CTA of the cluster is running (and initialised) before anyone stores into its shared memory
   md_richardson<F, DPAD>(P, s, s_obs, s_val, s.x, &s.fx, s.g, s.H);
@@ -350,40 +381,51 @@ __global__ void __launch_bounds__(JP_MD_THREADS, 1) jp_mode_dev_kernel(const JpM
     if (tid < 32) {
       const long long c_la = clock64();
       const bool pd = md_chol_step(s, d);
+      double lam_min = 1.0;
       const long long c_ch = clock64();
       if (tid == 0) s.cyc_chol += c_ch - c_la;
       int action = MD_STEP;
       if (!pd) {
         md_eigen_warp(s, d);
         if (tid == 0) s.cyc_eigen += clock64() - c_ch;
-        if (tid == 0) {
-          double scale = 0;
-          for (int i = 0; i < d; ++i) scale = fmax(scale, fabs(s.lam[i]));
-          scale = fmax(scale, 1e-300);
-          const double gnorm = md_max_abs(s.g, d);
-          if (s.lam[0] < -1e-8 * scale && gnorm < 1e-6 * scale) {
-            // a stationary point with negative curvature: leave along the most negative eigenvector
-            const double sgn[4] = {1, 1, -1, -1}, tt[4] = {1.0, 0.25, 1.0, 0.25};
-            for (int c = 0; c < 4; ++c)
-              for (int k = 0; k < d; ++k) s.cand[c * JP_MD_DMAX + k] = s.x[k] + tt[c] * sgn[c] * s.V[k];
-            action = MD_ESCAPE;
-          } else {
-            for (int k = 0; k < d; ++k) s.step[k] = 0;
-            for (int i = 0; i < d; ++i) {
-              double c = 0;
-              for (int k = 0; k < d; ++k) c += s.V[i * d + k] * s.g[k];
-              c /= fmax(fabs(s.lam[i]), 1e-10 * scale);
-              for (int k = 0; k < d; ++k) s.step[k] -= s.V[i * d + k] * c;
-            }
+        // (every lane repeats the O(d) scalars for itself; the O(d^2) products are shared out, lane i owning eigenpair / coordinate i)
+        double scale = 0;
+        for (int i = 0; i < d; ++i) scale = fmax(scale, fabs(s.lam[i]));
+        scale = fmax(scale, 1e-300);
+        const double gnorm = md_max_abs(s.g, d);
+        const int imin = s.imin;
+        lam_min = s.lam[imin];
+        if (lam_min < -1e-8 * scale && gnorm < 1e-6 * scale) {
+          // a stationary point with negative curvature: leave along the most negative eigenvector
+          if (tid < d) {
+            const double v = s.V[imin * d + tid], xk = s.x[tid];
+            s.cand[0 * JP_MD_DMAX + tid] = xk + v;
+            s.cand[1 * JP_MD_DMAX + tid] = xk + 0.25 * v;
+            s.cand[2 * JP_MD_DMAX + tid] = xk - v;
+            s.cand[3 * JP_MD_DMAX + tid] = xk - 0.25 * v;
           }
+          action = MD_ESCAPE;
+        } else {
+          double c = 0.0;             // lane i: (v_i . g) / |lambda_i|
+          if (tid < d) {
+            for (int k = 0; k < d; ++k) c += s.V[tid * d + k] * s.g[k];
+            c /= fmax(fabs(s.lam[tid]), 1e-10 * scale);
+          }
+          double st = 0.0;            // lane k: -sum_i v_i[k] c_i
+          for (int i = 0; i < d; ++i) {
+            const double ci = __shfl_sync(0xffffffffu, c, i);
+            if (tid < d) st -= s.V[i * d + tid] * ci;
+          }
+          if (tid < d) s.step[tid] = st;
         }
+        __syncwarp();
       }
       if (tid == 0) {
         if (action == MD_STEP) {
           const double nrm = md_max_abs(s.step, d);
           if (nrm > 10.0)
             for (int k = 0; k < d; ++k) s.step[k] *= 10.0 / nrm;
-          if ((pd || s.lam[0] > 0) && md_max_abs(s.step, d) < 1e-9 * (1 + md_max_abs(s.x, d))) action = MD_DONE;   // below the FD resolution
+          if ((pd || lam_min > 0) && md_max_abs(s.step, d) < 1e-9 * (1 + md_max_abs(s.x, d))) action = MD_DONE;   // below the FD resolution
         }
         s.action = action;
         s.t = 1.0;
@@ -469,6 +511,7 @@ __global__ void __launch_bounds__(JP_MD_THREADS, 1) jp_mode_dev_kernel(const JpM
     o[10] = (double)s.cyc_chol;
     o[11] = (double)s.cyc_eigen;
     o[12] = s.n_sweeps;
+    o[13] = (double)s.cyc_r1; o[14] = (double)s.cyc_r2; o[15] = (double)s.cyc_r3; o[16] = (double)s.cyc_chk;
   }
 }
 
@@ -531,6 +574,9 @@ int jp_mode_dev_try(jp_ctx* ctx, const jp_data* data, int d, const int* h_transf
   int S = 1;
   while (S < 32 && 2 * S * K <= JP_MD_THREADS * JP_MD_CTAS && 2 * S <= data->N) S *= 2;
   P.S = S;
+  P.split = S > 1 ? 1 : 0;
+  for (int k = 0; k < d; ++k)
+    if (h_transform[k] != JP_T_REAL && h_transform[k] != JP_T_POSITIVE && h_transform[k] != JP_T_PROBABILITY) P.split = 0;
   P.obs = data->d_obs;
   for (int i = 0; i < JP_MAX_HYPER; ++i) P.hyper[i] = data->hyper[i];
   // zero-copy through the context's pinned buffer, as jp_log_density_points does for the host-driven iteration
@@ -565,8 +611,8 @@ int jp_mode_dev_try(jp_ctx* ctx, const jp_data* data, int d, const int* h_transf
   if (evals) *evals += (int)o[4];
   if (std::getenv("JP_MODE_TRACE"))
     std::fprintf(stderr, "jp_mode (one launch): d=%d K=%d S=%d N=%lld: %d iterations, %d stencil evaluations, converged %d; cycles: values %.0f, "
-                 "derivatives %.0f, linear algebra %.0f (Cholesky %.0f; %d eigen-decompositions %.0f, %d sweeps)\n", d, K, S, data->N, (int)o[2], (int)o[4], (int)o[3],
-                 o[6], o[7], o[8], o[10], (int)o[9], o[11], (int)o[12]);
+                 "derivatives %.0f, linear algebra %.0f (Cholesky %.0f; %d eigen-decompositions %.0f, %d sweeps: angles %.0f, elements %.0f, stores %.0f, convergence checks %.0f)\n", d, K, S, data->N, (int)o[2], (int)o[4], (int)o[3],
+                 o[6], o[7], o[8], o[10], (int)o[9], o[11], (int)o[12], o[13], o[14], o[15], o[16]);
   if (o[5] != 1.0 || o[3] != 1.0) return JP_OK;        // not converged / not finite: the host-driven iteration decides
   std::memcpy(h_x, P.out, sizeof(double) * d);
   std::memcpy(h_H, P.out + d, sizeof(double) * d * d);
