@@ -326,6 +326,50 @@ def test_one_launch_mode_search_matches_host_driven(jp, gpu_ctx, case, monkeypat
     assert np.allclose(Hd, Hd.T)
 
 
+def _mode_both_ways(jp, gpu_ctx, family, code, obs, hyper, monkeypatch):
+    d = len(code)
+    dd = _upload(jp, gpu_ctx, family, obs, hyper)
+    codes = np.array(code, dtype=np.int32)
+
+    def run():
+        x, H = np.zeros(d), np.zeros((d, d), order="F")
+        fmin, evals = C.c_double(), C.c_int()
+        n0 = gpu_ctx.launches()
+        assert jp.lib().jp_mode(gpu_ctx.handle, dd.handle, d, codes.ctypes.data_as(C.c_void_p), 0, x.ctypes.data_as(C.c_void_p),
+                                H.ctypes.data_as(C.c_void_p), C.byref(fmin), C.byref(evals)) == 0
+        ok = C.c_int()
+        jp.lib().jp_mode_report(None, None, C.byref(ok))
+        return x, np.array(H), fmin.value, gpu_ctx.launches() - n0, ok.value
+
+    dev = run()
+    monkeypatch.setenv("JP_MODE_HOST", "1")
+    host = run()
+    monkeypatch.delenv("JP_MODE_HOST")
+    return dev, host
+
+
+def test_one_launch_mode_search_edges(jp, gpu_ctx, monkeypatch):
+    """The one-launch search at the ends of its gate: d = 1 (a two-category simplex: no rotation to make, a 1 x 1 Cholesky),
+    d = 16 (fourteen groups of the hierarchical model: widest padded instantiation, 1025-point stencil over the 8-CTA cluster),
+    and d = 17, which is past the gate and must take the host-driven search (many launches) with the same answer as ever."""
+    sx = 4 | (0 << 8) | (1 << 16)
+    (xd, Hd, fd, ld, okd), (xh, Hh, fh, lh, okh) = _mode_both_ways(jp, gpu_ctx, 5, [sx], np.array([[9.0], [4.0]]), np.array([0.0]), monkeypatch)
+    assert ld == 1 and okd == 1 and okh == 1
+    # mode of theta_1^9 theta_2^4 times the Jacobian theta_1 theta_2 in x = log(theta_1 / theta_2): theta_1 = 10 / 15
+    assert abs(xd[0] - np.log(10.0 / 5.0)) < 1e-6 and abs(xd[0] - xh[0]) < 1e-6 and abs(Hd[0, 0] - Hh[0, 0]) < 1e-5 * abs(Hh[0, 0])
+    rng = np.random.default_rng(5)
+    nc = 3 | (0 << 8) | (1 << 16)
+    for groups, one_launch in ((14, True), (15, False)):
+        ys, ss = rng.normal(5.0, 8.0, groups), rng.uniform(8.0, 16.0, groups)
+        (xd, Hd, fd, ld, okd), (xh, Hh, fh, lh, okh) = _mode_both_ways(jp, gpu_ctx, 3, [0, 1] + [nc] * groups, np.column_stack([ys, ss]),
+                                                                         np.array([25.0]), monkeypatch)
+        assert okd == 1 and okh == 1
+        assert (ld == 1) == one_launch, (groups, ld)
+        scale = 1.0 / np.sqrt(np.abs(np.diag(Hh)))
+        assert abs(fd - fh) <= 1e-9 * (1 + abs(fh)) and np.max(np.abs(xd - xh) / scale) < 1e-4
+        assert np.allclose(Hd, Hh, rtol=1e-4, atol=1e-6 * np.max(np.abs(Hh)))
+
+
 def test_adopted_device_records(jp, O, gpu_ctx):
     """jp_data_adopt_device: records already on the GPU (what Context.upload_sharded builds from the NVLink all_gather)
     give bit-identical results to jp_data_upload of the same host array; host pointers are refused."""
