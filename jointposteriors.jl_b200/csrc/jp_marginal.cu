@@ -13,6 +13,7 @@
 // (left knot = LAST duplicate <= x, right knot = first element of the next tie group).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include "jp_common.cuh"
 #include "jp_sort.cuh"
 
@@ -518,8 +519,19 @@ jp_combine_gathered_kernel(const double* __restrict__ gm, const double* __restri
   }
 }
 
+#define JP_BIN_SLICE 4096
+#define JP_BIN_BLOCKS_MAX 128
 // ------------------------------------------------------------------------------------ host side
-static int bins_blocks_for(long long M) { return (int)std::max(1LL, std::min(64LL, (M + 4095) / 4096)); }
+// blocks per marginal of the binning kernels: slices of JP_BIN_SLICE nodes (JP_BINS_SLICE in the environment overrides, for
+// experiments), at most JP_BIN_BLOCKS_MAX block tables for the last block to combine
+static int bins_blocks_for(long long M) {
+  static const long long slice = [] {
+    const char* e = std::getenv("JP_BINS_SLICE");
+    const long long v = e ? std::atoll(e) : 0;
+    return v >= 256 ? v : (long long)JP_BIN_SLICE;
+  }();
+  return (int)std::max(1LL, std::min((long long)JP_BIN_BLOCKS_MAX, (M + slice - 1) / slice));
+}
 
 // moments of the K value columns in post->d_vptr into d_out[K][4]; partials live in the ctx scratch behind K x 4
 static int launch_moments(jp_posterior* post, int K, double* d_out) {
