@@ -319,6 +319,12 @@ int smooth_newton(SmoothProblem* P, double* x, int max_iter, double g_tol, doubl
   *converged = 0;
   int it = 0;
   double radius = 1.0;
+  // score at the nine forward-difference neighbours of x (gq[j] at x + h[j] e_j).  A trial point is evaluated TOGETHER with
+  // its own nine neighbours (one launch of ten parameter sets): when the step is accepted -- nearly always -- the next
+  // iteration's Hessian needs no launch of its own, so an iteration is one round trip to the device instead of two.
+  double fq[SM_MAX_BATCH], gq[SM_MAX_BATCH][9], h[n];
+  bool have_neighbours = false;
+  auto step_of = [](double xj) { return 1e-6 * std::max(1.0, std::fabs(xj)); };
   for (; it < max_iter; ++it) {
     double gmax = 0;
     for (int i = 0; i < n; ++i) gmax = std::max(gmax, std::fabs(g[i]));
@@ -326,13 +332,16 @@ int smooth_newton(SmoothProblem* P, double* x, int max_iter, double g_tol, doubl
       *converged = 1;
       break;
     }
-    double ph[SM_MAX_BATCH][9], fq[SM_MAX_BATCH], gq[SM_MAX_BATCH][9], h[n], H[n][n], lam[n], V[n][n];
-    for (int j = 0; j < n; ++j) {
-      std::memcpy(ph[j], x, sizeof ph[j]);
-      h[j] = 1e-6 * std::max(1.0, std::fabs(x[j]));
-      ph[j][j] += h[j];
+    double ph[SM_MAX_BATCH][9], H[n][n], lam[n], V[n][n];
+    if (!have_neighbours) {
+      for (int j = 0; j < n; ++j) {
+        std::memcpy(ph[j], x, sizeof ph[j]);
+        h[j] = step_of(x[j]);
+        ph[j][j] += h[j];
+      }
+      JP_TRY(smooth_eval_batch(P, n, ph, fq, gq, nullptr));
+      have_neighbours = true;
     }
-    JP_TRY(smooth_eval_batch(P, n, ph, fq, gq, nullptr));
     bool ok_h = true;
     for (int j = 0; j < n; ++j) ok_h = ok_h && std::isfinite(fq[j]);
     for (int i = 0; i < n; ++i)
@@ -364,7 +373,7 @@ int smooth_newton(SmoothProblem* P, double* x, int max_iter, double g_tol, doubl
     for (int attempt = 0; attempt < 30; ++attempt) {
       // the trust radius clips every eigen-direction on its own: a nearly flat direction that asks for a huge move is cut
       // back without shortening the full Newton steps of the stiff ones
-      double pm = 0, xn[n], gn[n], fn = INFINITY, slope = 0, p[n] = {0};
+      double pm = 0, xn[n], slope = 0, p[n] = {0}, hn[n], fb[SM_MAX_BATCH], gb[SM_MAX_BATCH][9];
       bool clipped = false;
       for (int i = 0; i < n; ++i) {
         double ci = coef[i];
@@ -380,11 +389,23 @@ int smooth_newton(SmoothProblem* P, double* x, int max_iter, double g_tol, doubl
         xn[k] = x[k] + p[k];
         slope += p[k] * g[k];
       }
-      JP_TRY(smooth_eval(P, xn, &fn, gn, nullptr));
+      std::memcpy(ph[0], xn, sizeof xn);      // set 0: the trial point; sets 1 .. 9: its neighbours
+      for (int j = 0; j < n; ++j) {
+        std::memcpy(ph[1 + j], xn, sizeof xn);
+        hn[j] = step_of(xn[j]);
+        ph[1 + j][j] += hn[j];
+      }
+      JP_TRY(smooth_eval_batch(P, n + 1, ph, fb, gb, nullptr));
+      const double fn = fb[0];
       if (std::isfinite(fn) && fn <= f + 1e-4 * slope) {
         std::memcpy(x, xn, sizeof xn);
-        std::memcpy(g, gn, sizeof gn);
+        std::memcpy(g, gb[0], sizeof gb[0]);
         f = fn;
+        for (int j = 0; j < n; ++j) {
+          fq[j] = fb[1 + j];
+          std::memcpy(gq[j], gb[1 + j], sizeof gq[j]);
+          h[j] = hn[j];
+        }
         if (sc == 1.0) radius = std::min(4.0 * radius, 16.0);
         else radius = std::min(2.0 * radius, 16.0);
         stepped = true;

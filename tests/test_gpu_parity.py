@@ -505,7 +505,7 @@ def test_smooth_marginal_normal(jp, O, gpu_ctx):
     print("smooth CDF (KP level 7):", m.itp.info)
     # (the score's infinity norm does not reach Optim's g_tol of 1e-8 on this objective with ANY optimiser -- scipy's BFGS and
     # trust-exact stop at 0.2 / 0.02 after thousands of evaluations, DESIGN.md -- so the fit is judged by what it is for, below)
-    assert m.itp.info["iterations"] <= 300 and m.itp.info["evaluations"] <= 3200
+    assert m.itp.info["iterations"] <= 300 and m.itp.info["evaluations"] <= 6000      # parameter sets: ten per launch (trial point + neighbours)
     rt = GOLD_RUNTESTS
     assert np.isclose(m.mu, rt["tau"]["mu"], rtol=rt["rtol"]) and np.isclose(m.sigma, rt["tau"]["sigma"], rtol=rt["rtol"])
     qs = jp.quantile(m, PROBS5)
