@@ -212,12 +212,13 @@ int smooth_eval_batch(SmoothProblem* P, int nset, const double (*phi)[9], double
   const long long tiles = (P->M + SM_TILE - 1) / SM_TILE;
   const unsigned blocks = (unsigned)std::max(1LL, std::min((long long)(nset == 1 ? SM_MAX_BLOCKS : SM_BATCH_BLOCKS), tiles));
   static_assert(128 + (size_t)SM_MAX_BATCH * SM_MAX_BLOCKS * SM_SUMS <= JP_SCRATCH_DOUBLES, "scratch too small for the smooth-CDF partials");
-  double* d_out = ctx->d_scratch;                 // [nset][12]
+  // zero-copy result: the last block writes the (at most 120) sums straight into the context's pinned buffer, which the device
+  // addresses at its host address (unified addressing) -- launch + synchronise, no copy operation in between
+  JP_CUDA(jp_pinned_acquire(ctx));
+  double* d_out = ctx->h_pinned;                  // [nset][12]
   double* d_part = ctx->d_scratch + 128;          // [nset][blocks][12]
   jp_smooth_sums_kernel<<<dim3(blocks, nset), SM_THREADS, 0, ctx->stream>>>(P->d_V, P->d_cw, P->M, batch, d_part, ctx->d_counters, d_out);
   JP_CHECK_LAUNCH(ctx);
-  JP_CUDA(jp_pinned_acquire(ctx));
-  JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, d_out, (size_t)nset * SM_SUMS * 8, cudaMemcpyDeviceToHost, ctx->stream));
   JP_CUDA(cudaStreamSynchronize(ctx->stream));
   P->evaluations += nset;
   const double n = (double)P->M;
