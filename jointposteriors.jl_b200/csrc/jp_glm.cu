@@ -254,34 +254,46 @@ int jp_glm_grad_hess_comm(jp_ctx* ctx, const jp_data* data, jp_comm* comm, int d
   JP_ENTER_CTX(ctx);
   int nE = d + d * (d + 1) / 2;
   int nb = jp_glm_num_blocks(ctx, data->N);
+  // A Newton iteration of the mode finder is one such call: no allocation when the block partials fit the context's scratch,
+  // beta staged through the pinned buffer, and -- single GPU -- the combined sums written by the last kernel straight into the
+  // pinned buffer (zero-copy), so the call is copy + two launches + one synchronisation.
   double *d_beta = nullptr, *d_out = nullptr, *d_work = nullptr;
-  JP_CUDA(jp_dmalloc(ctx, &d_beta, sizeof(double) * d));
-  JP_CUDA(jp_dmalloc(ctx, &d_out, sizeof(double) * (nE + 1)));
-  JP_CUDA(jp_dmalloc(ctx, &d_work, sizeof(double) * (size_t)nb * (nE + 1)));
-  // staged through the context's pinned buffer (a Newton iteration of the mode finder is one such call)
+  const bool exchange = comm && comm->world > 1;
+  const size_t need = (size_t)JP_MAX_D + (size_t)(nE + 1) + (size_t)nb * (nE + 1);
+  const bool in_scratch = need <= JP_SCRATCH_DOUBLES;
   double* hp = ctx->h_pinned;
+  double* out = hp + JP_MAX_D;     // nE + 1 <= 64 + 64 * 65 / 2 + 1 doubles
+  if (in_scratch) {
+    d_beta = ctx->d_scratch;
+    d_out = ctx->d_scratch + JP_MAX_D;
+    d_work = d_out + (nE + 1);
+  } else {
+    JP_CUDA(jp_dmalloc(ctx, &d_beta, sizeof(double) * d));
+    JP_CUDA(jp_dmalloc(ctx, &d_out, sizeof(double) * (nE + 1)));
+    JP_CUDA(jp_dmalloc(ctx, &d_work, sizeof(double) * (size_t)nb * (nE + 1)));
+  }
   JP_CUDA(jp_pinned_acquire(ctx));
   std::memcpy(hp, h_beta, sizeof(double) * d);
   JP_CUDA(cudaMemcpyAsync(d_beta, hp, sizeof(double) * d, cudaMemcpyHostToDevice, ctx->stream));
-  int st = jp_glm_sums_device(ctx, data, d, d_beta, d_out, d_work, nb);
-  if (st == JP_OK && comm && comm->world > 1) {
+  int st = jp_glm_sums_device(ctx, data, d, d_beta, exchange ? d_out : out, d_work, nb);
+  if (st == JP_OK && exchange) {
     const double* g = nullptr;
     st = jp_comm_exchange(comm, JP_CH_USER, d_out, nE + 1, &g);
     if (st == JP_OK) {
-      jp_sum_gathered_kernel<<<(nE + 1 + 127) / 128, 128, 0, ctx->stream>>>(g, comm->world, nE + 1, d_out);
+      jp_sum_gathered_kernel<<<(nE + 1 + 127) / 128, 128, 0, ctx->stream>>>(g, comm->world, nE + 1, out);
       ctx->launches++;
     }
   }
-  double* out = hp + JP_MAX_D;     // nE + 1 <= 64 + 64 * 65 / 2 + 1 doubles
   if (st == JP_OK) {
-    cudaError_t e = cudaMemcpyAsync(out, d_out, sizeof(double) * (nE + 1), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
       jp_set_error("jp_glm_grad_hess: %s", cudaGetErrorString(e));
       st = JP_ERR_CUDA;
     }
   }
-  jp_dfree(ctx, d_beta); jp_dfree(ctx, d_out); jp_dfree(ctx, d_work);
+  if (!in_scratch) {
+    jp_dfree(ctx, d_beta); jp_dfree(ctx, d_out); jp_dfree(ctx, d_work);
+  }
   JP_TRY(st);
   // add the N(0, s^2) prior and unpack
   double s2 = data->hyper[0] * data->hyper[0];
