@@ -364,7 +364,7 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
   double* s_mu = sh;                       // d
   double* s_U = sh + ((d + 1) & ~1);       // d x p4 row-major: s_U[k * p4 + j] = U[k + j * d]  (16-byte aligned rows)
   double* s_tile = s_U + (size_t)d * p4;   // 2 x TC_PREP_THREADS x rs
-  __shared__ double red[33];
+  __shared__ double red[TC_PREP_THREADS / 32][TC_NBOUND];
   __shared__ int s_kend[16];               // per block of four columns of U: one past its last non-zero row
   for (int k = threadIdx.x; k < d; k += blockDim.x) s_mu[k] = mu[k];
   for (int e = threadIdx.x; e < d * p4; e += blockDim.x) {
@@ -486,26 +486,38 @@ tc_obs_prep_kernel(int family, int d, int p, int ncols, long long N, long long N
       pm *= tm * tm;
     }
   }
-  double* ob = bounds + (size_t)blockIdx.x * TC_NBOUND;
-  double v = jp_block_max(b_tmax, red);
-  if (threadIdx.x == 0) ob[0] = v;
-  v = jp_block_sum(b_a1, red);
-  if (threadIdx.x == 0) ob[1] = v;
+  // block partials of all TC_NBOUND quantities in ONE pass: shuffle trees inside the warps (independent, so they pipeline), one
+  // barrier, then thread q adds the warps' values of quantity q in warp order -- the same tree and order as 22 calls of
+  // jp_block_sum / jp_block_max (bit-identical bounds), without their 66 barriers at the end of every block
+  double vals[TC_NBOUND];
+  vals[0] = b_tmax;
+  vals[1] = b_a1;
+#pragma unroll
   for (int j = 0; j < TC_NORD; ++j) {
-    v = jp_block_sum(b_ref[j], red);
-    if (threadIdx.x == 0) ob[2 + j] = v;
-    v = jp_block_sum(b_max[j], red);
-    if (threadIdx.x == 0) ob[7 + j] = v;
+    vals[2 + j] = b_ref[j];
+    vals[7 + j] = b_max[j];
   }
-  v = jp_block_sum(b_r, red);
-  if (threadIdx.x == 0) ob[12] = v;
-  v = jp_block_sum(b_r2, red);
-  if (threadIdx.x == 0) ob[13] = v;
+  vals[12] = b_r;
+  vals[13] = b_r2;
+#pragma unroll
   for (int j = 0; j < TC_NFOLD; ++j) {
-    v = jp_block_sum(f_ref[j], red);
-    if (threadIdx.x == 0) ob[14 + j] = v;
-    v = jp_block_sum(f_max[j], red);
-    if (threadIdx.x == 0) ob[14 + TC_NFOLD + j] = v;
+    vals[14 + j] = f_ref[j];
+    vals[14 + TC_NFOLD + j] = f_max[j];
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  vals[0] = jp_warp_max(vals[0]);
+#pragma unroll
+  for (int q = 1; q < TC_NBOUND; ++q) vals[q] = jp_warp_sum(vals[q]);
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < TC_NBOUND; ++q) red[wid][q] = vals[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < TC_NBOUND) {
+    const int q = threadIdx.x;
+    double r = (q == 0) ? red[0][0] : 0.0 + red[0][q];
+    for (int w = 1; w < TC_PREP_THREADS / 32; ++w) r = (q == 0) ? fmax(r, red[w][q]) : r + red[w][q];
+    bounds[(size_t)blockIdx.x * TC_NBOUND + q] = r;
   }
 }
 
