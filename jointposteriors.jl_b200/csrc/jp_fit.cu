@@ -384,6 +384,15 @@ static int launch_family(jp_posterior* post, const JpFitLaunchParams& lp) {
   if (d <= 32) return launch_nodes<F, 32>(post, lp);
   return launch_nodes<F, JP_MAX_D>(post, lp);
 }
+// families whose shape_ok admits a single dimension need a single padded width (every (family, width) pair is a kernel to compile)
+template <>
+int launch_family<FamBinomialMixture>(jp_posterior* post, const JpFitLaunchParams& lp) {      // d = 3
+  return launch_nodes<FamBinomialMixture, 4>(post, lp);
+}
+template <>
+int launch_family<FamAnova2>(jp_posterior* post, const JpFitLaunchParams& lp) {               // d = 5
+  return launch_nodes<FamAnova2, 8>(post, lp);
+}
 #define JP_REGISTER_FAMILY(F)                                                                  \
   static struct Reg##F {                                                                        \
     Reg##F() { jp_register_family(JpFamilyEntry{F::kId, F::kName, &launch_family<F>, &F::shape_ok}); } \
