@@ -632,3 +632,55 @@ def test_normal_linear_d10_against_semi_analytic_truth(O):
     assert errs[0][0] < 1e-3 and errs[1][0] < 1e-3
     assert errs[0][2] < 0.25 and errs[1][2] < 0.8 * errs[0][2]             # second moments carry sigma's uncertainty: slower
     assert errs[0][1] < 0.08 and errs[1][1] < 0.8 * errs[0][1] and errs[0][3] < 0.3 and errs[1][3] < 0.8 * errs[0][3]
+
+
+@pytest.mark.parametrize("family,name", [(1, "logistic"), (2, "poisson")])
+def test_glm_posterior_against_tensor_quadrature_truth(O, family, name):
+    """An independent anchor for the two families the headline configurations use (BASELINE configs 3-5): a two-coefficient
+    logistic / Poisson regression whose posterior moments and quantile levels are computed by brute force -- a dense 2-D
+    Gauss-Legendre tensor rule over a box of +-9 posterior standard deviations, plain numpy, nothing shared with the oracle but
+    the model formula -- and must be what the oracle's Laplace-centred Smolyak posterior converges to."""
+    from conftest import synth_glm
+    X, y = synth_glm(31 + family, 150, 2, name, 0.4)
+    obs, hyper = np.ascontiguousarray(np.column_stack([X, y])), np.array([3.0])
+    code = np.zeros(2, dtype=np.int32)
+
+    def logpost(B):      # B [..., 2]
+        eta = B @ X.T                                           # [..., N]
+        ll = y * eta - (np.logaddexp(0.0, eta) if family == 1 else np.exp(eta))
+        return ll.sum(-1) - 0.5 * (B ** 2).sum(-1) / hyper[0] ** 2
+    beta, H, ll = O.glm_mode(family, obs, hyper, 2)
+    C = np.linalg.inv(H)
+    sd = np.sqrt(np.diag(C))
+    gx, gw = np.polynomial.legendre.leggauss(240)
+    b0 = beta[0] + 9 * sd[0] * gx
+    b1 = beta[1] + 9 * sd[1] * gx
+    B = np.stack(np.meshgrid(b0, b1, indexing="ij"), -1)
+    lp = logpost(B)
+    W = np.outer(gw, gw) * np.exp(lp - lp.max())
+    W /= W.sum()
+    assert W[0].max() < 1e-12 and W[-1].max() < 1e-12 and W[:, 0].max() < 1e-12 and W[:, -1].max() < 1e-12
+    mean = np.array([np.sum(W * B[..., 0]), np.sum(W * B[..., 1])])
+    var = np.array([np.sum(W * B[..., 0] ** 2), np.sum(W * B[..., 1] ** 2)]) - mean ** 2
+    cross = np.sum(W * B[..., 0] * B[..., 1]) - mean[0] * mean[1]
+    # ---- the oracle's sparse-grid posterior, two levels
+    U = O.inv_chol(2 * H)
+    errs = []
+    for Lv in (5, 7):
+        idx, w = O.smolyak(0, 2, Lv)
+        ref = O.eval_grid(0, family, code, idx, w, beta, U, -ll, obs, hyper, want_theta=True)
+        t, dens = ref["theta"], ref["density"]
+        assert abs(dens.sum() - 1.0) < 1e-12
+        m = np.array([np.sum(dens * t[0]), np.sum(dens * t[1])])
+        v = np.array([np.sum(dens * t[0] ** 2), np.sum(dens * t[1] ** 2)]) - m ** 2
+        cr = np.sum(dens * t[0] * t[1]) - m[0] * m[1]
+        # the posterior probability of {beta_0 <= its true posterior mean}, against the same probability under the truth
+        p_grid = np.sum(dens[t[0] <= mean[0]])
+        p_true = np.sum(W[B[..., 0] <= mean[0]])
+        errs.append((np.max(np.abs(m - mean) / np.sqrt(var)), np.max(np.abs(v - var) / var), abs(cr - cross) / np.sqrt(var[0] * var[1]),
+                     abs(p_grid - p_true)))
+    print(name, "d=2: (mean in sd, variance, covariance, P(beta_0 <= mean)) errors at levels 5, 7:", errs)
+    assert errs[0][0] < 1e-3 and errs[1][0] < 1e-6          # means, in posterior standard deviations (measured 2e-4, 7e-8)
+    assert errs[0][1] < 3e-3 and errs[1][1] < 3e-6          # variances, relative (measured 7e-4, 4e-7)
+    assert errs[0][2] < 1e-3 and errs[1][2] < 1e-6          # the covariance in units of sd_0 sd_1 (measured 2e-4, 1e-7)
+    assert errs[1][3] < 0.1                                 # signed weights make "probabilities" of half-spaces rough, but bounded
